@@ -1,0 +1,339 @@
+"""TEST INFRASTRUCTURE ONLY.  Generates tests/golden/*.npz by running the UNMODIFIED reference on CPU.
+
+Run inside the build container (needs /root/reference):   python -m oracle.make_golden
+The GPU box never runs this; it only reads the committed .npz files.
+
+Vectors produced (all from the reference's own code through oracle/ref_harness.py):
+  quant_kat.npz     known answers for the fake-quant arithmetic (quant_utils.py:31-82,170-223; QuantAct
+                    quant_modules.py:202-225; QuantBnConv2d fold+quant :364-419; Quant_Conv2d :278-321)
+  deform_kat.npz    known answers for the deformable op (torchvision CPU stand-in, see ref_harness) and for
+                    DeformConvWithOffsetScaleBoundPositive.forward (modules/dcn_deform_conv.py:323-330)
+  decode_kat.npz    ctdet_decode (decode.py:474-505) on random tie-free heatmaps
+  codenet1x_calib.npz   BatchNorm running stats + frozen QuantAct ranges of the synthetic CoDeNet1x
+                    (SURVEY.md 8(d) recipe), per offset mode and resolution
+  codenet1x_256_{round,bilinear}.npz   fp64 reference forward + decode on config a (256^2), with int8-grid
+                    intermediates
+  codenet1x_512_round.npz   one 512^2 image (config c geometry): detections + strided output samples
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import ref_harness as H                      # noqa: E402
+from codenet_b200.arch import NetConfig, build_graph, act_keys, raw_to_quant_key  # noqa: E402
+from codenet_b200.synth import make_raw_state, make_images, state_digest      # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+T = torch.from_numpy
+
+
+def quant_kat():
+    R = H.load_reference()
+    from portable_quantizer.quantization_utils import quant_utils as qu
+    rng = np.random.Generator(np.random.PCG64(11))
+    out = {}
+    # asymmetric activation quant, unclamped (quant_utils.py:191-198)
+    x = rng.standard_normal((2, 5, 7, 6)) * 3
+    for i, (lo, hi) in enumerate([(-7.3, 9.1), (0.0, 6.0), (x.min(), x.max())]):
+        y = qu.AsymmetricQuantFunction.apply(T(x), 8, torch.tensor([lo]), torch.tensor([hi]))
+        out["act%d_x" % i] = x
+        out["act%d_range" % i] = np.array([lo, hi])
+        out["act%d_y" % i] = y.numpy()
+    # symmetric per-channel weight quant, 4 and 8 bit (quant_utils.py:205-223)
+    w = rng.standard_normal((6, 4, 3, 3)) * np.array([0.01, 0.5, 1, 3, 10, 1e-12]).reshape(6, 1, 1, 1)
+    for bits in (4, 8):
+        wv = T(w).view(6, -1)
+        y = qu.SymmetricQuantFunction.apply(T(w), bits, wv.min(1).values, wv.max(1).values, True, False)
+        out["w%d_x" % bits] = w
+        out["w%d_y" % bits] = y.numpy()
+    # QuantBnConv2d: fold + quantise + conv (quant_modules.py:364-419), fp64
+    conv = torch.nn.Conv2d(5, 7, 1, bias=False).double()
+    bn = torch.nn.BatchNorm2d(7).double()
+    with torch.no_grad():
+        conv.weight.copy_(T(rng.standard_normal((7, 5, 1, 1))))
+        bn.weight.copy_(T(rng.uniform(0.5, 1.5, 7)))
+        bn.bias.copy_(T(rng.standard_normal(7) * 0.3))
+        bn.running_mean.copy_(T(rng.standard_normal(7) * 0.2))
+        bn.running_var.copy_(T(rng.uniform(0.3, 2.0, 7)))
+    qc = R.qm.QuantBnConv2d(4, quant_mode="symmetric", per_channel=True)
+    qc.set_param(conv, bn)
+    xi = rng.standard_normal((2, 5, 4, 4))
+    with torch.no_grad():
+        yo = qc(T(xi))
+    out.update(bnconv_w=conv.weight.detach().numpy(), bnconv_gamma=bn.weight.detach().numpy(),
+               bnconv_beta=bn.bias.detach().numpy(), bnconv_mean=bn.running_mean.numpy(),
+               bnconv_var=bn.running_var.numpy(), bnconv_eps=np.array(bn.eps), bnconv_x=xi,
+               bnconv_y=yo.numpy())
+    # QuantAct stateful init then frozen (quant_modules.py:202-225)
+    qa = R.qm.QuantAct(8, quant_mode="asymmetric").double()
+    xa = rng.standard_normal((3, 4, 5, 5))
+    with torch.no_grad():
+        y1 = qa(T(xa))
+    out.update(qact_x=xa, qact_y=y1.numpy(), qact_min=qa.x_min.numpy().copy(), qact_max=qa.x_max.numpy().copy())
+    np.savez_compressed(os.path.join(OUT, "quant_kat.npz"), **out)
+    print("quant_kat ok")
+
+
+def deform_kat():
+    R = H.load_reference()
+    rng = np.random.Generator(np.random.PCG64(12))
+    out = {}
+    cases = [  # name, B, C, H, W, Cout, groups, stride, offset scale
+        ("dw_s1", 2, 6, 9, 11, 6, 6, 1, 2.5),
+        ("dw_s2", 1, 4, 10, 8, 4, 4, 2, 3.0),
+        ("dense", 2, 4, 7, 7, 5, 1, 1, 1.5),
+        ("g2", 1, 6, 6, 9, 4, 2, 1, 4.0),
+    ]
+    for name, B, C, Hh, W, Co, g, st, osc in cases:
+        Ho, Wo = (Hh + 2 - 3) // st + 1, (W + 2 - 3) // st + 1
+        x = rng.standard_normal((B, C, Hh, W))
+        off = rng.standard_normal((B, 18, Ho, Wo)) * osc
+        # make some offsets exactly integral / exactly on the -1 and H borders (range test of kernel.cu:224)
+        off[:, :, 0, 0] = np.round(off[:, :, 0, 0])
+        w = rng.standard_normal((Co, C // g, 3, 3))
+        y = R.deform_conv(T(x), T(off), T(w), st, 1, 1, g, 1)
+        out.update({name + "_x": x, name + "_off": off, name + "_w": w, name + "_y": y.numpy(),
+                    name + "_cfg": np.array([st, 1, 1, g, 1])})
+    # the CoDeNet module itself (modules/dcn_deform_conv.py:285-330), fp64, non-trivial conv_scale
+    for name, cin, cout, st, bound in [("mod_same", 8, 8, 1, 8), ("mod_chan", 8, 5, 1, 3), ("mod_s2", 6, 6, 2, 4)]:
+        import contextlib, io
+        with contextlib.redirect_stdout(io.StringIO()):
+            mod = R.dmod.DeformConvWithOffsetScaleBoundPositive(cin, cout, 3, st, 1, groups=cout,
+                                                                offset_bound=bound).double()
+        with torch.no_grad():
+            mod.conv_scale.weight.copy_(T(rng.standard_normal((1, cin, 1, 1)) * 1.2))
+            mod.conv_scale.bias.fill_(1.0)
+            mod.conv.weight.copy_(T(rng.standard_normal((cin, 1, 3, 3))))
+        x = rng.standard_normal((2, cin, 12, 10))
+        with torch.no_grad():
+            y = mod(T(x))
+        out.update({name + "_x": x, name + "_ws": mod.conv_scale.weight.detach().numpy(),
+                    name + "_bs": mod.conv_scale.bias.detach().numpy(),
+                    name + "_w": mod.conv.weight.detach().numpy(), name + "_y": y.numpy(),
+                    name + "_cfg": np.array([st, bound])})
+        if cin != cout:
+            out[name + "_wc"] = mod.conv_channel.weight.detach().numpy()
+    np.savez_compressed(os.path.join(OUT, "deform_kat.npz"), **out)
+    print("deform_kat ok")
+
+
+def decode_kat():
+    R = H.load_reference()
+    rng = np.random.Generator(np.random.PCG64(13))
+    out = {}
+    for name, B, cat, Hh, W, K in [("voc", 2, 20, 32, 32, 100), ("small", 1, 3, 16, 24, 40)]:
+        hm = 1 / (1 + np.exp(-(rng.standard_normal((B, cat, Hh, W)) * 1.5 - 2.19)))
+        hm = hm.astype(np.float32)
+        wh = (rng.uniform(1, 20, (B, 2, Hh, W))).astype(np.float32)
+        reg = rng.uniform(0, 1, (B, 2, Hh, W)).astype(np.float32)
+        d = R.decode.ctdet_decode(T(hm), T(wh), reg=T(reg), K=K)
+        d2 = R.decode.ctdet_decode(T(hm), T(wh), reg=None, K=K)
+        # tie-free among the K+8 best peaks of every image, so torch.topk's unspecified tie order is moot
+        nms = R.decode._nms(T(hm)).numpy().reshape(B, -1)
+        for b in range(B):
+            top = np.sort(nms[b])[::-1][:K + 8]
+            assert len(np.unique(top)) == K + 8 and top[-1] > 0
+        out.update({name + "_hm": hm, name + "_wh": wh, name + "_reg": reg, name + "_dets": d.numpy(),
+                    name + "_dets_noreg": d2.numpy(), name + "_K": np.array(K)})
+    np.savez_compressed(os.path.join(OUT, "decode_kat.npz"), **out)
+    print("decode_kat ok")
+
+
+# ---------------------------------------------------------------------------------------------------------
+def _calibrate_bn(cfg, raw):
+    """BN momentum 1.0, one train-mode forward on the calibration batch."""
+    m = H.build_reference_model({k: T(v) for k, v in raw.items()}, dict(cfg.head_list()), cfg.w2, cfg.maxpool,
+                                dtype=torch.float64)
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.momentum = 1.0
+    m.train()
+    with torch.no_grad():
+        m(T(make_images(4, 256, seed=1)).double())
+    m.eval()
+    sd = m.state_dict()
+    bn = {k: sd[k].float().numpy() for k in sd if k.endswith("running_mean") or k.endswith("running_var")}
+    return bn
+
+
+def _quant_model(cfg, raw, integer_offsets):
+    m = H.build_reference_model({k: T(v) for k, v in raw.items()}, dict(cfg.head_list()), cfg.w2, cfg.maxpool,
+                                dtype=torch.float64)
+    m.eval()
+    H.quantize_reference_model(m, cfg.w2, cfg.maxpool, cfg.w_bit, cfg.a_bit)
+    m.double()
+    H.set_integer_offsets(m, integer_offsets)
+    return m
+
+
+def _init_ranges(m, x):
+    """Frozen ranges for the parity vectors.
+
+    One eval forward with running_stat=True initialises every range the reference's way
+    (quant_modules.py:209-212).  A stage-shared QuantAct is initialised by its FIRST call only and later units
+    exceed it (the reference then extrapolates past the 8-bit grid, quant_utils.py:191-198), which an int8
+    engine cannot represent.  So the ranges are then frozen and widened monotonically -- forward, record the
+    min/max of every call of every QuantAct, grow the range, repeat -- until nothing leaves its range, and
+    finally rounded outward to fp32 (what a checkpoint would hold).
+    """
+    R = H.load_reference()
+    acts = [mod for mod in m.modules() if isinstance(mod, R.qm.QuantAct)]
+    for a in acts:
+        a.x_min.zero_(); a.x_max.zero_(); a.running_stat = True
+    with torch.no_grad():
+        m(x)
+    H.freeze_ranges(m)
+    seen = {}
+
+    def pre(mod, inp):
+        lo, hi = inp[0].min().item(), inp[0].max().item()
+        cur = seen.get(mod, (lo, hi))
+        seen[mod] = (min(cur[0], lo), max(cur[1], hi))
+
+    hooks = [a.register_forward_pre_hook(pre) for a in acts]
+    for it in range(12):
+        seen.clear()
+        with torch.no_grad():
+            m(x)
+        grew = 0
+        for a in acts:
+            lo, hi = seen[a]
+            cl, ch = a.x_min.item(), a.x_max.item()
+            if lo < cl or hi > ch:
+                grew += 1
+                nl, nh = min(lo, cl), max(hi, ch)
+                pad = 1e-6 * max(abs(nl), abs(nh), 1e-3)
+                nl32 = np.float32(nl - pad) if nl != 0.0 else np.float32(0.0)
+                a.x_min.fill_(float(nl32)); a.x_max.fill_(float(np.float32(nh + pad)))
+        if not grew:
+            break
+    else:
+        raise RuntimeError("range calibration did not converge")
+    for h in hooks:
+        h.remove()
+    for a in acts:                                     # fp32-representable, as a checkpoint would hold
+        a.x_min.fill_(float(np.float32(a.x_min.item()))); a.x_max.fill_(float(np.float32(a.x_max.item())))
+
+
+def _ranges_of(m, g):
+    sd = m.state_dict()
+    return {lbl: np.array([sd[p + ".x_min"].item(), sd[p + ".x_max"].item()]) for lbl, p in act_keys(g).items()}
+
+
+def _grid(x, lo, hi, bits=8):
+    """Recover the integer grid index of a fake-quantised tensor (quant_utils.py:58-73,31-50)."""
+    s = (2 ** bits - 1) / max(hi - lo, 1e-10)
+    z = np.round(s * lo) + 2 ** (bits - 1)
+    q = x * s - z
+    qi = np.round(q)
+    assert np.abs(q - qi).max() < 1e-6, np.abs(q - qi).max()
+    return qi.astype(np.int16)
+
+
+def _run_and_capture(m, g, x, K=100):
+    R = H.load_reference()
+    ak = act_keys(g)
+    mods = dict(m.named_modules())
+    cap = {}
+    hooks = []
+
+    def hook_act(lbl):
+        def f(mod, inp, out):
+            cap[lbl] = _grid(out.numpy(), mod.x_min.item(), mod.x_max.item())
+        return f
+
+    want = ["stem", "layer4"] + ["up%d.%s" % (i, t) for i in range(3) for t in ("s", "deform", "out")] + \
+           ["layer1.0.act1", "layer1.0.act2", "layer1.0.act4", "layer1.1.act1", "layer1.1.act2", "hm.act1", "hm.act3"]
+    for lbl in want:
+        hooks.append(mods[ak[lbl]].register_forward_hook(hook_act(lbl)))
+    for s in (1, 2, 3):
+        sh = mods[ak["layer%d.shared" % s]]
+
+        def f(mod, inp, out, s=s, sh=sh):
+            cap["layer%d.out" % s] = _grid(out.numpy(), sh.x_min.item(), sh.x_max.item())
+        hooks.append(mods["layer%d" % s].register_forward_hook(f))
+    # the dilation scalar s actually handed to the deformable op (after optional rounding)
+    for i in range(3):
+        qd = mods["deconv_layers.%d" % (3 * i)]
+
+        def f(mod, inp, out, i=i):
+            cap["up%d.sval" % i] = out.numpy().copy()
+        hooks.append(qd.quant_act.register_forward_hook(f))
+    with torch.no_grad():
+        o = m(x)[-1]
+        hm_logit = o["hm"].clone()
+        hm = o["hm"].sigmoid_()
+        dets = R.decode.ctdet_decode(hm, o["wh"], reg=o["reg"], K=K)
+    for h in hooks:
+        h.remove()
+    cap.update(hm_logit=hm_logit.numpy(), hm=hm.numpy(), wh=o["wh"].numpy(), reg=o["reg"].numpy(),
+               dets=dets.numpy())
+    return cap
+
+
+def codenet1x():
+    cfg = NetConfig(num_classes=20)
+    g = build_graph(cfg)
+    raw = make_raw_state(cfg, 0)
+    digest = state_digest(raw)
+    raw.update(_calibrate_bn(cfg, raw))
+    calib = {"digest": np.array(digest), "seed": np.array(0)}
+    for k, v in raw.items():
+        if k.endswith("running_mean") or k.endswith("running_var"):
+            calib["bn/" + k] = v
+
+    x256 = np.concatenate([make_images(2, 256, seed=2), make_images(2, 256, seed=1)[:2]])
+    x512 = make_images(2, 512, seed=3)
+    for mode, integer in (("round", True), ("bilinear", False)):
+        m = _quant_model(cfg, raw, integer)
+        for res, xs in ((256, x256), (512, x512)):
+            _init_ranges(m, T(xs).double())
+            for lbl, r in _ranges_of(m, g).items():
+                calib["ranges_%s_%d/%s" % (mode, res, lbl)] = r
+            nimg = 2 if res == 256 else 1
+            cap = _run_and_capture(m, g, T(xs[:nimg]).double())
+            # batch independence with frozen ranges
+            cap1 = _run_and_capture(m, g, T(xs[:1]).double())
+            assert np.array_equal(cap1["dets"][0], cap["dets"][0])
+            sat = max(int(np.abs(v).max()) for k, v in cap.items() if v.dtype == np.int16)
+            print(mode, res, "max |grid| =", sat, " unique scores:", len(np.unique(cap["dets"][0, :, 4])))
+            out = {"seed_images": np.array(2 if res == 256 else 3), "nimg": np.array(nimg)}
+            if res == 256:
+                for k, v in cap.items():
+                    if v.dtype == np.int16:
+                        assert v.min() >= -128 and v.max() <= 127, (k, v.min(), v.max())
+                        if mode == "bilinear" and not (k.startswith("up") or k in ("layer4", "stem")):
+                            continue
+                        out[k] = v.astype(np.int8)
+                    elif k in ("hm_logit", "wh", "reg"):
+                        out[k] = v                      # fp64
+                    elif k.endswith("sval") or k == "dets":
+                        out[k] = v
+                np.savez_compressed(os.path.join(OUT, "codenet1x_256_%s.npz" % mode), **out)
+            elif mode == "round":
+                out["dets"] = cap["dets"]
+                for k in ("hm_logit", "wh", "reg"):
+                    out[k + "_s8"] = cap[k][:, :, ::8, ::8]
+                out["up2.out"] = cap["up2.out"].astype(np.int8)[:, :, ::4, ::4]
+                out["stem"] = cap["stem"].astype(np.int8)[:, :, ::4, ::4]
+                np.savez_compressed(os.path.join(OUT, "codenet1x_512_round.npz"), **out)
+    np.savez_compressed(os.path.join(OUT, "codenet1x_calib.npz"), **calib)
+    print("codenet1x ok")
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    which = sys.argv[1:] or ["quant", "deform", "decode", "codenet1x"]
+    if "quant" in which:
+        quant_kat()
+    if "deform" in which:
+        deform_kat()
+    if "decode" in which:
+        decode_kat()
+    if "codenet1x" in which:
+        codenet1x()
