@@ -1,0 +1,156 @@
+"""ctypes binding of libcodenet_b200.so (the C ABI declared in include/codenet_b200.h).
+
+There is no CPU fallback: if the library is missing it is built with nvcc, and if that is impossible, or no
+sm_100 device is visible when a device function is called, an exception is raised.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libcodenet_b200.so")
+_lib = None
+
+
+class CdnError(RuntimeError):
+    pass
+
+
+class Requant(C.Structure):
+    _fields_ = [("M", C.POINTER(C.c_double)), ("B", C.POINTER(C.c_double)), ("lo", C.c_int), ("n", C.c_int)]
+
+
+class DeformScale(C.Structure):
+    _fields_ = [("ws", C.POINTER(C.c_int8)), ("Ms", C.c_double), ("bs", C.c_double), ("ss", C.c_double),
+                ("zs", C.c_double), ("bound", C.c_int), ("mode", C.c_int)]
+
+
+class PwChunk(C.Structure):
+    _fields_ = [("col", C.c_int16), ("count", C.c_int16), ("pass_off", C.c_int16), ("dst_off", C.c_int16)]
+
+
+class PwDesc(C.Structure):
+    _fields_ = [("K", C.c_int), ("k_off", C.c_int), ("N", C.c_int), ("zx", C.c_int), ("wq", C.POINTER(C.c_int8)),
+                ("rq", Requant), ("chunks", C.POINTER(PwChunk)), ("n_chunks", C.c_int),
+                ("n_f32", C.c_int), ("Mf", C.POINTER(C.c_double)), ("bf", C.POINTER(C.c_double))]
+
+
+EXPORTS = {
+    "cdn_last_error": (C.c_char_p, []),
+    "cdn_version": (C.c_int, []),
+    "cdn_check_device": (C.c_int, [C.c_int]),
+    "cdn_set_debug_flags": (C.c_int, [C.c_uint]),
+    "cdn_stem_f32_i8": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int8), C.c_int,
+                                  C.POINTER(Requant), C.c_void_p, C.c_int, C.c_void_p]),
+    "cdn_dw3x3_i8": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int8),
+                               C.c_int, C.c_int, C.POINTER(Requant), C.c_void_p, C.c_int, C.c_void_p]),
+    "cdn_deform_dw_w4a8": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(DeformScale),
+                                     C.POINTER(C.c_int8), C.c_int, C.c_int, C.POINTER(Requant), C.c_void_p, C.c_int,
+                                     C.c_void_p, C.c_void_p]),
+    "cdn_pw_gemm_i8": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.POINTER(PwDesc), C.c_void_p, C.c_int, C.c_void_p,
+                                 C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "cdn_ctdet_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cdn_deform_conv_forward_f32": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 16 + [C.c_void_p]),
+    "cdn_engine_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
+    "cdn_engine_destroy": (C.c_int, [C.c_void_p]),
+    "cdn_engine_add_tensor": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "cdn_engine_add_stem": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int8),
+                                      C.c_int, C.POINTER(Requant)]),
+    "cdn_engine_add_dw": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int8), C.c_int,
+                                    C.c_int, C.POINTER(Requant)]),
+    "cdn_engine_add_deform": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(DeformScale),
+                                        C.POINTER(C.c_int8), C.c_int, C.c_int, C.POINTER(Requant)]),
+    "cdn_engine_add_pw": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(PwDesc)]),
+    "cdn_engine_set_heads": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "cdn_engine_finalize": (C.c_int, [C.c_void_p, C.c_int]),
+    "cdn_engine_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p]),
+    "cdn_engine_run_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "cdn_engine_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
+    "cdn_engine_read_tensor": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "cdn_engine_read_heads": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "cdn_engine_num_launches": (C.c_int, [C.c_void_p]),
+    "cdn_engine_profile": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+}
+
+
+def lib_path():
+    return _LIB_PATH
+
+
+def load():
+    """Loads (building first if necessary) the shared library.  Raises if it cannot be produced."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        from . import build as _build
+        _build.build()
+    lib = C.CDLL(_LIB_PATH)
+    for name, (res, args) in EXPORTS.items():
+        fn = getattr(lib, name)                  # AttributeError if a declared symbol is not exported
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise CdnError("codenet_b200: %s (status %d)" % (load().cdn_last_error().decode(), rc))
+
+
+# ---- numpy -> ctypes helpers (keep the arrays alive for the duration of the call) --------------------------------
+def i8p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int8))
+
+
+def f64p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class Keep:
+    """Collects the contiguous arrays whose pointers were handed to C."""
+
+    def __init__(self):
+        self.refs = []
+
+    def i8(self, a):
+        a = np.ascontiguousarray(a, dtype=np.int8); self.refs.append(a); return i8p(a)
+
+    def f64(self, a):
+        a = np.ascontiguousarray(a, dtype=np.float64); self.refs.append(a); return f64p(a)
+
+    def requant(self, M, B, lo):
+        M = np.ascontiguousarray(M, dtype=np.float64); B = np.ascontiguousarray(B, dtype=np.float64)
+        self.refs += [M, B]
+        r = Requant(f64p(M), f64p(B), int(lo), int(M.size))
+        self.refs.append(r)
+        return r
+
+    def chunks(self, arr):
+        arr = np.ascontiguousarray(arr, dtype=np.int16).reshape(-1, 4)
+        self.refs.append(arr)
+        return arr.ctypes.data_as(C.POINTER(PwChunk)), int(arr.shape[0])
+
+    def pw_desc(self, a):
+        d = PwDesc()
+        d.K, d.k_off, d.N, d.zx = int(a["K"]), int(a["k_off"]), int(a["N"]), int(a["zx"])
+        d.wq = self.i8(a["wq"])
+        d.n_f32 = int(a.get("n_f32", 0))
+        if d.n_f32:
+            d.Mf, d.bf = self.f64(a["Mf"]), self.f64(a["bf"])
+            d.rq = Requant(None, None, -128, 0)
+            d.chunks, d.n_chunks = None, 0
+        else:
+            d.rq = self.requant(a["M"], a["B"], a["lo"])
+            d.chunks, d.n_chunks = self.chunks(a["chunks"])
+        self.refs.append(d)
+        return d
+
+    def deform_scale(self, a):
+        s = DeformScale(self.i8(a["ws"]), float(a["Ms"]), float(a["bs"]), float(a["ss"]), float(a["zs"]),
+                        int(a["bound"]), int(a["mode"]))
+        self.refs.append(s)
+        return s

@@ -1,0 +1,109 @@
+// Shared device/host helpers of libcodenet_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string.h>
+#include <math.h>
+#include <vector>
+#include <string>
+#include "../../include/codenet_b200.h"
+
+// ---------------------------------------------------------------------------------------------------------
+// error plumbing (no exceptions across the C ABI)
+// ---------------------------------------------------------------------------------------------------------
+int cdn_fail(int code, const char* fmt, ...);
+#define CDN_CHECK(cond, code, ...) do { if (!(cond)) return cdn_fail(code, __VA_ARGS__); } while (0)
+#define CDN_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) \
+    return cdn_fail(CDN_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); } while (0)
+#define CDN_LAUNCH_CHECK(name) do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) \
+    return cdn_fail(CDN_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e__)); } while (0)
+
+extern unsigned g_cdn_debug_flags;
+int cdn_num_sms();
+
+// ---------------------------------------------------------------------------------------------------------
+// Requantisation  q = clamp(rint(fl64(fl64(acc*M) + B)), lo, 127)   (DESIGN.md "requantisation")
+//
+// Fast path: t = fmaf((float)acc, Mh, Bh) in fp32, rounded half-to-even with the 1.5*2^23 trick.  |t - t_exact| is
+// bounded per channel by `eps` (computed on the host from |B| and the int8 range), so whenever t is further than eps
+// from a rounding boundary the fp32 result equals the fp64 one; otherwise the fp64 formula is evaluated.  The
+// result is therefore bit-identical to the fp64 formula for every input.  Requires |acc| < 2^24 (checked on the host).
+// ---------------------------------------------------------------------------------------------------------
+struct RqFast { float Mh, Bh, thr; };        // thr = 0.5 - eps
+
+// Host: derive the fast constants.
+static inline RqFast rq_fast_from(double M, double B) {
+  RqFast r;
+  r.Mh = (float)M;
+  r.Bh = (float)B;
+  // |t_fp32 - t_fp64| <= 2^-24 (|acc*M| + |B| + |t|) with |acc*M| <= |t| + |B| and |t| <= 130 inside the clamp; x2 safety
+  double eps = 2.0 * ldexp(1.0, -24) * (2.0 * fabs(B) + 2.0 * 130.0 + 1.0);
+  if (eps > 0.49) eps = 0.49;
+  r.thr = (float)(0.5 - eps);
+  return r;
+}
+
+#ifdef __CUDACC__
+#define CDN_MAGIC_F 12582912.0f              // 1.5 * 2^23
+#define CDN_MAGIC_I 0x4B400000
+
+// Returns the float whose LOW BYTE (of its bit pattern) is the int8 result; rq_bits_to_int() gives the int.
+__device__ __forceinline__ uint32_t requant_bits(int acc, float Mh, float Bh, float thr, float lo_f,
+                                                 const double* __restrict__ Md, const double* __restrict__ Bd, int ch) {
+  float t = fmaf((float)acc, Mh, Bh);
+  t = fminf(fmaxf(t, lo_f), 127.0f);
+  float r = t + CDN_MAGIC_F;
+  float k = r - CDN_MAGIC_F;
+  if (fabsf(t - k) > thr) {                  // within eps of a rounding boundary: exact fp64 evaluation
+    double td = __dadd_rn(__dmul_rn((double)acc, __ldg(Md + ch)), __ldg(Bd + ch));
+    td = fmin(fmax(td, (double)lo_f), 127.0);
+    r = (float)__double2int_rn(td) + CDN_MAGIC_F;
+  }
+  return __float_as_uint(r);
+}
+__device__ __forceinline__ int rq_bits_to_int(uint32_t bits) { return (int)bits - CDN_MAGIC_I; }
+
+// pack the low bytes of four requant_bits() results into one little-endian word
+__device__ __forceinline__ uint32_t pack4_lowbytes(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  uint32_t ab = __byte_perm(a, b, 0x0040);   // [a.0, b.0, a.0, a.0] -> bytes0,1 used
+  uint32_t cd = __byte_perm(c, d, 0x0040);
+  return __byte_perm(ab, cd, 0x5410);
+}
+
+__device__ __forceinline__ int dp4a_ss(uint32_t a, uint32_t b, int c) {
+  return __dp4a((int)a, (int)b, c);
+}
+
+// 4x4 byte transpose: in x0..x3 (word t = 4 channels of tap t); out y[c] = (x0[c], x1[c], x2[c], x3[c])
+__device__ __forceinline__ void transpose4x4(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3,
+                                             uint32_t& y0, uint32_t& y1, uint32_t& y2, uint32_t& y3) {
+  uint32_t a = __byte_perm(x0, x1, 0x5140);  // x0.0 x1.0 x0.1 x1.1
+  uint32_t b = __byte_perm(x0, x1, 0x7362);  // x0.2 x1.2 x0.3 x1.3
+  uint32_t c = __byte_perm(x2, x3, 0x5140);
+  uint32_t d = __byte_perm(x2, x3, 0x7362);
+  y0 = __byte_perm(a, c, 0x5410);
+  y1 = __byte_perm(a, c, 0x7632);
+  y2 = __byte_perm(b, d, 0x5410);
+  y3 = __byte_perm(b, d, 0x7632);
+}
+#endif
+
+// ---------------------------------------------------------------------------------------------------------
+// Device-side constant blocks owned by the library (uploaded once per layer)
+// ---------------------------------------------------------------------------------------------------------
+struct DevRequant {                          // arrays of length n (padded by the caller as needed)
+  float* Mh = nullptr; float* Bh = nullptr; float* thr = nullptr;
+  double* M = nullptr; double* B = nullptr; int32_t* acc_bias = nullptr;
+  int lo = -128; int n = 0;
+};
+int dev_requant_upload(DevRequant& d, const cdn_requant* rq, const int32_t* acc_bias_host, int n_pad);
+void dev_requant_free(DevRequant& d);
+
+template <typename T> int dev_upload(T** dptr, const T* host, size_t n) {
+  CDN_CUDA(cudaMalloc((void**)dptr, n * sizeof(T) > 0 ? n * sizeof(T) : 16));
+  if (n) CDN_CUDA(cudaMemcpy(*dptr, host, n * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}

@@ -1,0 +1,184 @@
+// ctdet decode: 3x3 max-pool NMS + top-K + gather + box assembly in ONE launch, one CTA per image.
+// Restates lib/models/decode.py:474-505 (_nms :10-16, _topk :110-126, gathers lib/models/utils.py:14-29) on the
+// heat-map LOGITS (sigmoid is monotone, so peaks and order are unchanged; the score written is sigmoid(logit)).
+// The reference's two-stage top-K (per class, then over classes) selects the same set as one global top-K.
+// Order / ties: logit descending, then class ascending, then spatial index ascending (torch.topk leaves ties open).
+//
+// Phase 1  every thread scans its share of the map, tests "equal to the max of the 3x3 neighbourhood" and appends
+//          peaks as 64-bit composites (ordered key << 32 | ~flat_index) to a per-image list (warp-aggregated).
+// Phase 2  radix select (11-bit digits, warp-shuffle scans) of the K-th largest composite over the peak list.
+// Phase 3  the K survivors are bitonic-sorted in shared memory and turned into boxes.
+#include "layers.cuh"
+
+#define DEC_THREADS 1024
+#define DEC_BINS 2048
+#define DEC_MAXK 1024
+
+__device__ __forceinline__ uint32_t f2key(float f) {
+  uint32_t b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(uint32_t k) {
+  uint32_t b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+  return __uint_as_float(b);
+}
+
+struct DecParams {
+  const float* hm; const float* wh; const float* reg;
+  long long hm_is, wh_is, reg_is;            // per-image strides (elements)
+  int cat, H, W, K;
+  unsigned long long* list;                  // [batch][cat*H*W] peak composites
+  float* dets; int32_t* inds;
+};
+
+__global__ void __launch_bounds__(DEC_THREADS) ctdet_decode_kernel(DecParams p) {
+  __shared__ unsigned int hist[DEC_BINS];
+  __shared__ unsigned long long sel[DEC_MAXK];
+  __shared__ unsigned int s_count, s_nsel;
+  __shared__ unsigned long long s_prefix, s_mask;
+  __shared__ unsigned int s_krem, s_done;
+  __shared__ unsigned int warp_sums[32];
+
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int HW = p.H * p.W;
+  const long long n = (long long)p.cat * HW;
+  const float* hm = p.hm + (size_t)b * p.hm_is;
+  unsigned long long* list = p.list + (size_t)b * n;
+
+  if (tid == 0) { s_count = 0; s_nsel = 0; }
+  __syncthreads();
+
+  // ---- phase 1: peaks -> list ------------------------------------------------------------------------
+  for (long long base = 0; base < n; base += DEC_THREADS) {
+    long long e = base + tid;
+    bool peak = false; float v = 0.f;
+    if (e < n) {
+      int sp = (int)(e % HW); int y = sp / p.W, x = sp - y * p.W;
+      const float* plane = hm + (e - sp);
+      v = __ldg(plane + sp);
+      peak = true;
+#pragma unroll
+      for (int dy = -1; dy <= 1; ++dy) {
+        int yy = y + dy; if ((unsigned)yy >= (unsigned)p.H) continue;
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) {
+          int xx = x + dx; if ((dx | dy) == 0 || (unsigned)xx >= (unsigned)p.W) continue;
+          if (__ldg(plane + yy * p.W + xx) > v) peak = false;
+        }
+      }
+      if (v != v) peak = false;              // NaN never is a peak
+    }
+    unsigned m = __ballot_sync(0xffffffffu, peak);
+    if (m) {
+      unsigned pos = 0;
+      if (lane == 0) pos = atomicAdd(&s_count, __popc(m));
+      pos = __shfl_sync(0xffffffffu, pos, 0);
+      if (peak) list[pos + __popc(m & ((1u << lane) - 1u))] =
+          ((unsigned long long)f2key(v) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)e);
+    }
+  }
+  __syncthreads();
+  const unsigned int count = s_count;
+  const unsigned int Ksel = min((unsigned)p.K, count);
+
+  // ---- phase 2: radix select of the Ksel-th largest composite ------------------------------------------
+  if (tid == 0) { s_prefix = 0ull; s_mask = 0ull; s_krem = Ksel; s_done = (Ksel == 0 || Ksel == count) ? 1u : 0u; }
+  __syncthreads();
+  for (int shift = 53; !s_done; shift = max(shift - 11, 0)) {
+    const int width = (shift == 0) ? 9 : 11;   // 53,42,31,20,9 -> 11 bits each, then the last 9 bits
+    const unsigned nb = 1u << width;
+    for (int i = tid; i < DEC_BINS; i += DEC_THREADS) hist[i] = 0;
+    __syncthreads();
+    const unsigned long long prefix = s_prefix, mask = s_mask;
+    for (unsigned i = tid; i < count; i += DEC_THREADS) {
+      unsigned long long c = list[i];
+      if ((c & mask) == prefix) atomicAdd(&hist[(unsigned)(c >> shift) & (nb - 1)], 1u);
+    }
+    __syncthreads();
+    // suffix counts from the top digit: each thread owns 2 bins (DEC_BINS / DEC_THREADS)
+    {
+      unsigned d0 = nb - 1 - 2 * tid, d1 = nb - 2 - 2 * tid;           // descending digit order
+      unsigned c0 = (2 * tid < nb) ? hist[d0] : 0u, c1 = (2 * tid + 1 < nb) ? hist[d1] : 0u;
+      unsigned mine = c0 + c1, incl = mine;
+      for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+      if (lane == 31) warp_sums[warp] = incl;
+      __syncthreads();
+      unsigned woff = 0;
+      for (int w2 = 0; w2 < warp; ++w2) woff += warp_sums[w2];
+      unsigned before = woff + incl - mine;                              // elements with a larger digit
+      const unsigned krem = s_krem;
+      __syncthreads();
+      if (2 * tid < nb && before < krem && krem <= before + c0) {
+        s_prefix = prefix | ((unsigned long long)d0 << shift);
+        s_mask = mask | ((unsigned long long)(nb - 1) << shift);
+        s_krem = krem - before;
+        if (krem == before + c0 || shift == 0) s_done = 1u;               // whole bin taken (or fully resolved)
+      } else if (2 * tid + 1 < nb && before + c0 < krem && krem <= before + c0 + c1) {
+        s_prefix = prefix | ((unsigned long long)d1 << shift);
+        s_mask = mask | ((unsigned long long)(nb - 1) << shift);
+        s_krem = krem - before - c0;
+        if (krem == before + c0 + c1 || shift == 0) s_done = 1u;
+      }
+      __syncthreads();
+    }
+    if (shift == 0) break;
+  }
+  __syncthreads();
+  // threshold: every composite >= (prefix restricted to the resolved bits) is selected
+  const unsigned long long thr = (Ksel == count) ? 0ull : s_prefix;
+  for (unsigned i = tid; i < count && Ksel > 0; i += DEC_THREADS) {
+    unsigned long long c = list[i];
+    if (c >= thr) { unsigned pos = atomicAdd(&s_nsel, 1u); if (pos < DEC_MAXK) sel[pos] = c; }
+  }
+  __syncthreads();
+  // ---- phase 3: sort (descending) and emit ------------------------------------------------------------
+  unsigned nsel = min(s_nsel, (unsigned)DEC_MAXK);
+  unsigned np2 = 1; while (np2 < nsel) np2 <<= 1;
+  for (unsigned i = nsel + tid; i < np2; i += DEC_THREADS) sel[i] = 0ull;
+  __syncthreads();
+  for (unsigned k2 = 2; k2 <= np2; k2 <<= 1)
+    for (unsigned j = k2 >> 1; j > 0; j >>= 1) {
+      for (unsigned i = tid; i < np2; i += DEC_THREADS) {
+        unsigned ixj = i ^ j;
+        if (ixj > i) {
+          unsigned long long a = sel[i], c = sel[ixj];
+          bool desc = ((i & k2) == 0);
+          if (desc ? (a < c) : (a > c)) { sel[i] = c; sel[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  for (int i = tid; i < p.K; i += DEC_THREADS) {
+    float* d = p.dets + ((size_t)b * p.K + i) * 6;
+    if ((unsigned)i < nsel && (unsigned)i < Ksel) {
+      unsigned long long c = sel[i];
+      uint32_t flat = 0xffffffffu - (uint32_t)(c & 0xffffffffull);
+      float logit = key2f((uint32_t)(c >> 32));
+      int cls = flat / HW, sp = flat - cls * HW;
+      float xs = (float)(sp % p.W), ys = (float)(sp / p.W);
+      if (p.reg) { xs += p.reg[(size_t)b * p.reg_is + sp]; ys += p.reg[(size_t)b * p.reg_is + HW + sp]; }
+      else { xs += 0.5f; ys += 0.5f; }
+      float w = p.wh[(size_t)b * p.wh_is + sp], h = p.wh[(size_t)b * p.wh_is + HW + sp];
+      d[0] = xs - w / 2; d[1] = ys - h / 2; d[2] = xs + w / 2; d[3] = ys + h / 2;
+      d[4] = (float)(1.0 / (1.0 + exp(-(double)logit)));
+      d[5] = (float)cls;
+      if (p.inds) p.inds[(size_t)b * p.K + i] = (int32_t)flat;
+    } else {
+      d[0] = d[1] = d[2] = d[3] = d[4] = d[5] = 0.f;
+      if (p.inds) p.inds[(size_t)b * p.K + i] = -1;
+    }
+  }
+}
+
+int decode_launch(const float* hm, long long hm_img_stride, const float* wh, long long wh_img_stride, const float* reg,
+                  long long reg_img_stride, int batch, int cat, int H, int W, int K, unsigned long long* scratch,
+                  float* dets, int32_t* inds, cudaStream_t st) {
+  CDN_CHECK(K >= 1 && K <= DEC_MAXK, CDN_ERR_INVALID, "decode: K=%d must be in 1..%d", K, DEC_MAXK);
+  CDN_CHECK(cat >= 1 && H >= 1 && W >= 1 && (long long)cat * H * W < (1ll << 31), CDN_ERR_INVALID, "decode: bad shape");
+  CDN_CHECK(hm && wh && dets && scratch, CDN_ERR_INVALID, "decode: null pointer");
+  if (batch == 0) return 0;
+  DecParams p{hm, wh, reg, hm_img_stride, wh_img_stride, reg_img_stride, cat, H, W, K, scratch, dets, inds};
+  ctdet_decode_kernel<<<batch, DEC_THREADS, 0, st>>>(p);
+  CDN_LAUNCH_CHECK("ctdet_decode_kernel");
+  return 0;
+}

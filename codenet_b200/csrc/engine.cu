@@ -1,0 +1,496 @@
+// C ABI entry points: error plumbing, stand-alone operator calls, and the whole-network engine
+// (a static plan of kernel launches over pre-allocated NHWC int8 activation buffers, replayed as a CUDA graph).
+#include "layers.cuh"
+#include <algorithm>
+#include <mutex>
+
+// ---- error plumbing -----------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+unsigned g_cdn_debug_flags = 0;
+
+int cdn_fail(int code, const char* fmt, ...) {
+  va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+  return code;
+}
+int cdn_num_sms() {
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+  return sms;
+}
+
+int dev_requant_upload(DevRequant& d, const cdn_requant* rq, const int32_t* acc_bias_host, int n_pad) {
+  CDN_CHECK(rq && rq->n <= n_pad, CDN_ERR_INVALID, "requant: n=%d exceeds padded size %d", rq ? rq->n : -1, n_pad);
+  std::vector<float> Mh(n_pad, 0.f), Bh(n_pad, 0.f), thr(n_pad, 0.5f);
+  std::vector<double> M(n_pad, 0.0), B(n_pad, 0.0);
+  std::vector<int32_t> ab(n_pad, 0);
+  for (int i = 0; i < rq->n; ++i) {
+    CDN_CHECK(std::isfinite(rq->M[i]) && std::isfinite(rq->B[i]), CDN_ERR_INVALID, "requant: non-finite constant at channel %d", i);
+    RqFast f = rq_fast_from(rq->M[i], rq->B[i]);
+    Mh[i] = f.Mh; Bh[i] = f.Bh; thr[i] = f.thr; M[i] = rq->M[i]; B[i] = rq->B[i];
+  }
+  if (acc_bias_host) for (int i = 0; i < n_pad; ++i) ab[i] = acc_bias_host[i];
+  if (dev_upload(&d.Mh, Mh.data(), n_pad)) return CDN_ERR_CUDA;
+  if (dev_upload(&d.Bh, Bh.data(), n_pad)) return CDN_ERR_CUDA;
+  if (dev_upload(&d.thr, thr.data(), n_pad)) return CDN_ERR_CUDA;
+  if (dev_upload(&d.M, M.data(), n_pad)) return CDN_ERR_CUDA;
+  if (dev_upload(&d.B, B.data(), n_pad)) return CDN_ERR_CUDA;
+  if (dev_upload(&d.acc_bias, ab.data(), n_pad)) return CDN_ERR_CUDA;
+  d.lo = std::max(-128, std::min(127, rq->lo)); d.n = n_pad;
+  return 0;
+}
+void dev_requant_free(DevRequant& d) {
+  cudaFree(d.Mh); cudaFree(d.Bh); cudaFree(d.thr); cudaFree(d.M); cudaFree(d.B); cudaFree(d.acc_bias);
+  d = DevRequant();
+}
+
+extern "C" const char* cdn_last_error(void) { return g_err; }
+extern "C" int cdn_version(void) { return 100; }
+extern "C" int cdn_set_debug_flags(unsigned flags) { g_cdn_debug_flags = flags; return 0; }
+extern "C" int cdn_check_device(int device) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); return cdn_fail(CDN_ERR_NO_DEVICE, "no CUDA device visible; codenet_b200 has no CPU fallback"); }
+  CDN_CHECK(device >= 0 && device < n, CDN_ERR_NO_DEVICE, "device %d out of range (%d visible)", device, n);
+  int major = 0;
+  CDN_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+  CDN_CHECK(major == 10, CDN_ERR_NO_DEVICE, "device %d has compute capability %d.x; this library is built for sm_100a only", device, major);
+  return 0;
+}
+
+// ---- stand-alone operator calls (tests / integration; they synchronise the stream before returning) -----------
+extern "C" int cdn_stem_f32_i8(const float* d_img, int batch, int H, int W, int stride, int pool, const int8_t* wq, int C,
+                               const cdn_requant* rq, int8_t* d_out, int out_pitch, cdn_stream_t stream) {
+  StemDevice d{}; int8_t* tmp = nullptr;
+  int r = stem_device_build(d, wq, C, rq);
+  if (!r && pool) {
+    size_t bytes = (size_t)batch * ((H - 1) / stride + 1) * ((W - 1) / stride + 1) * out_pitch;
+    if (cudaMalloc(&tmp, bytes ? bytes : 16) != cudaSuccess) r = cdn_fail(CDN_ERR_CUDA, "stem: scratch allocation failed");
+  }
+  if (!r) r = stem_launch(d, d_img, batch, H, W, stride, pool, d_out, out_pitch, tmp, (cudaStream_t)stream);
+  cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+  if (!r && e != cudaSuccess) r = cdn_fail(CDN_ERR_CUDA, "stem: %s", cudaGetErrorString(e));
+  cudaFree(tmp); stem_device_free(d);
+  return r;
+}
+
+extern "C" int cdn_dw3x3_i8(const int8_t* d_in, int in_pitch, int batch, int H, int W, int in_shift, int stride,
+                            const int8_t* wq, int C, int zx, const cdn_requant* rq, int8_t* d_out, int out_pitch,
+                            cdn_stream_t stream) {
+  DwDevice d{};
+  int Cp = std::min(in_pitch, out_pitch);
+  int r = dw_device_build(d, wq, nullptr, C, Cp, zx, rq);
+  if (!r) r = dw_launch(d, d_in, in_pitch, d_out, out_pitch, batch, H, W, in_shift, stride, zx, (cudaStream_t)stream);
+  cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+  if (!r && e != cudaSuccess) r = cdn_fail(CDN_ERR_CUDA, "dw3x3: %s", cudaGetErrorString(e));
+  dw_device_free(d);
+  return r;
+}
+
+extern "C" int cdn_deform_dw_w4a8(const int8_t* d_in, int in_pitch, int batch, int H, int W, int in_shift,
+                                  const cdn_deform_scale* sc, const int8_t* wq, int C, int zx, const cdn_requant* rq,
+                                  int8_t* d_out, int out_pitch, float* d_sval, cdn_stream_t stream) {
+  CDN_CHECK(sc && sc->ws, CDN_ERR_INVALID, "deform: null scale descriptor");
+  DwDevice d{};
+  int Cp = std::min(in_pitch, out_pitch);
+  int r = dw_device_build(d, wq, sc->ws, C, Cp, zx, rq);
+  if (!r) r = deform_launch(d, sc, d_in, in_pitch, d_out, out_pitch, batch, H, W, in_shift, zx, d_sval, (cudaStream_t)stream);
+  cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+  if (!r && e != cudaSuccess) r = cdn_fail(CDN_ERR_CUDA, "deform: %s", cudaGetErrorString(e));
+  dw_device_free(d);
+  return r;
+}
+
+extern "C" int cdn_pw_gemm_i8(const int8_t* d_in, int in_pitch, int64_t pixels, const cdn_pw_desc* desc,
+                              const int8_t* d_pass, int pass_pitch, int8_t* d_out, int out_pitch,
+                              float* d_out_f32, int pixels_per_image, cdn_stream_t stream) {
+  PwDevice d{};
+  int r = pw_device_build(d, desc, pass_pitch);
+  if (!r) r = pw_launch(d, d_in, in_pitch, pixels, d_pass, pass_pitch, d_out, out_pitch, d_out_f32, pixels_per_image,
+                        nullptr, nullptr, nullptr, (cudaStream_t)stream);
+  cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+  if (!r && e != cudaSuccess) r = cdn_fail(CDN_ERR_CUDA, "pw_gemm: %s", cudaGetErrorString(e));
+  pw_device_free(d);
+  return r;
+}
+
+extern "C" int cdn_ctdet_decode(const float* d_hm, const float* d_wh, const float* d_reg, int batch, int cat, int H, int W,
+                                int K, float* d_dets, int32_t* d_inds, cdn_stream_t stream) {
+  unsigned long long* scratch = nullptr;
+  size_t n = (size_t)batch * cat * H * W;
+  CDN_CUDA(cudaMalloc(&scratch, (n ? n : 1) * sizeof(unsigned long long)));
+  long long hw = (long long)H * W;
+  int r = decode_launch(d_hm, cat * hw, d_wh, 2 * hw, d_reg, 2 * hw, batch, cat, H, W, K, scratch, d_dets, d_inds, (cudaStream_t)stream);
+  cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+  if (!r && e != cudaSuccess) r = cdn_fail(CDN_ERR_CUDA, "decode: %s", cudaGetErrorString(e));
+  cudaFree(scratch);
+  return r;
+}
+
+// ---- engine -------------------------------------------------------------------------------------------------
+struct EngTensor { int H, W, pitch; int8_t* ptr; };
+struct EngOp {
+  int kind;                                  // 0 stem, 1 dw, 2 deform, 3 pw
+  int in_t, pass_t, out_t, in_shift, stride, pool, zx, H, W;
+  StemDevice stem; DwDevice dw; PwDevice pw; cdn_deform_scale sc; std::vector<int8_t> ws_host;
+  CUtensorMap tmA, tmP, tmO;
+};
+
+struct cdn_engine {
+  int device = 0, max_batch = 0, finalized = 0;
+  int in_H = 0, in_W = 0;
+  std::vector<EngTensor> tensors;
+  std::vector<EngOp*> ops;
+  int cat = 0, hH = 0, hW = 0, K = 100, has_reg = 1, n_f32 = 0;
+  float* heads = nullptr;                    // fp32 [batch][n_f32][hH*hW] logits / wh / reg
+  unsigned long long* dec_scratch = nullptr;
+  float* dets = nullptr; int32_t* inds = nullptr;
+  int8_t* stem_tmp = nullptr;
+  // host path
+  float* d_img = nullptr; size_t d_img_bytes = 0;
+  cudaStream_t s_compute = nullptr, s_copy = nullptr;
+  std::vector<cudaEvent_t> ev;
+  int host_chunk = 32, use_graph = 1, micro_batch = 0;
+  // graph cache
+  struct GraphKey { const void* a[6]; int batch; bool operator==(const GraphKey& o) const { return memcmp(this, &o, sizeof(*this)) == 0; } };
+  std::vector<std::pair<GraphKey, cudaGraphExec_t>> graphs;
+  int launches = 0;
+};
+
+__global__ void heads_copyout_kernel(const float* heads, int n_f32, int cat, int ppi, long long total,
+                                     float* hm, float* wh, float* reg) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int pi = (int)(i % ppi); long long t = i / ppi; int n = (int)(t % n_f32); long long b = t / n_f32;
+  float v = heads[i];
+  if (n < cat) { if (hm) hm[((size_t)b * cat + n) * ppi + pi] = 1.f / (1.f + __expf(-v)); }
+  else if (n < cat + 2) { if (wh) wh[((size_t)b * 2 + (n - cat)) * ppi + pi] = v; }
+  else if (n < cat + 4) { if (reg) reg[((size_t)b * 2 + (n - cat - 2)) * ppi + pi] = v; }
+}
+
+#define ENG_CHECK(e) CDN_CHECK((e) != nullptr, CDN_ERR_INVALID, "null engine")
+
+extern "C" int cdn_engine_create(cdn_engine** out, int device) {
+  CDN_CHECK(out != nullptr, CDN_ERR_INVALID, "null out pointer");
+  if (int r = cdn_check_device(device)) return r;
+  CDN_CUDA(cudaSetDevice(device));
+  cdn_engine* e = new cdn_engine();
+  e->device = device;
+  CDN_CUDA(cudaStreamCreateWithFlags(&e->s_compute, cudaStreamNonBlocking));
+  CDN_CUDA(cudaStreamCreateWithFlags(&e->s_copy, cudaStreamNonBlocking));
+  *out = e;
+  return 0;
+}
+
+extern "C" int cdn_engine_destroy(cdn_engine* e) {
+  if (!e) return 0;
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  for (auto& g : e->graphs) cudaGraphExecDestroy(g.second);
+  for (auto* op : e->ops) { stem_device_free(op->stem); dw_device_free(op->dw); pw_device_free(op->pw); delete op; }
+  for (auto& t : e->tensors) cudaFree(t.ptr);
+  cudaFree(e->heads); cudaFree(e->dec_scratch); cudaFree(e->dets); cudaFree(e->inds); cudaFree(e->stem_tmp); cudaFree(e->d_img);
+  for (auto ev : e->ev) cudaEventDestroy(ev);
+  if (e->s_compute) cudaStreamDestroy(e->s_compute);
+  if (e->s_copy) cudaStreamDestroy(e->s_copy);
+  delete e;
+  return 0;
+}
+
+extern "C" int cdn_engine_set_option(cdn_engine* e, const char* name, int value) {
+  ENG_CHECK(e);
+  if (!strcmp(name, "host_chunk")) e->host_chunk = std::max(1, value);
+  else if (!strcmp(name, "use_graph")) e->use_graph = value;
+  else if (!strcmp(name, "micro_batch")) e->micro_batch = std::max(0, value);
+  else return cdn_fail(CDN_ERR_INVALID, "unknown engine option '%s'", name);
+  return 0;
+}
+
+extern "C" int cdn_engine_add_tensor(cdn_engine* e, int H, int W, int pitch) {
+  ENG_CHECK(e);
+  CDN_CHECK(!e->finalized, CDN_ERR_STATE, "engine already finalized");
+  CDN_CHECK(H > 0 && W > 0 && pitch > 0 && pitch % 32 == 0, CDN_ERR_INVALID, "tensor %dx%d pitch %d: pitch must be a multiple of 32", H, W, pitch);
+  e->tensors.push_back(EngTensor{H, W, pitch, nullptr});
+  return (int)e->tensors.size() - 1;
+}
+
+static int check_t(cdn_engine* e, int t, const char* what) {
+  CDN_CHECK(t >= 0 && t < (int)e->tensors.size(), CDN_ERR_INVALID, "%s: tensor id %d out of range", what, t);
+  return 0;
+}
+
+extern "C" int cdn_engine_add_stem(cdn_engine* e, int out_t, int H, int W, int stride, int pool, const int8_t* wq, int C,
+                                   const cdn_requant* rq) {
+  ENG_CHECK(e);
+  CDN_CHECK(!e->finalized, CDN_ERR_STATE, "engine already finalized");
+  if (int r = check_t(e, out_t, "stem")) return r;
+  CDN_CUDA(cudaSetDevice(e->device));
+  EngOp* op = new EngOp();
+  op->kind = 0; op->out_t = out_t; op->H = H; op->W = W; op->stride = stride; op->pool = pool;
+  if (int r = stem_device_build(op->stem, wq, C, rq)) { delete op; return r; }
+  int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  if (pool) { Ho = (Ho - 1) / 2 + 1; Wo = (Wo - 1) / 2 + 1; }
+  const EngTensor& t = e->tensors[out_t];
+  CDN_CHECK(t.H == Ho && t.W == Wo, CDN_ERR_INVALID, "stem: output tensor is %dx%d, expected %dx%d", t.H, t.W, Ho, Wo);
+  e->in_H = H; e->in_W = W;
+  e->ops.push_back(op);
+  return 0;
+}
+
+extern "C" int cdn_engine_add_dw(cdn_engine* e, int in_t, int out_t, int in_shift, int stride, const int8_t* wq, int C,
+                                 int zx, const cdn_requant* rq) {
+  ENG_CHECK(e);
+  CDN_CHECK(!e->finalized, CDN_ERR_STATE, "engine already finalized");
+  if (int r = check_t(e, in_t, "dw")) return r;
+  if (int r = check_t(e, out_t, "dw")) return r;
+  CDN_CUDA(cudaSetDevice(e->device));
+  const EngTensor &ti = e->tensors[in_t], &to = e->tensors[out_t];
+  int H = ti.H << in_shift, W = ti.W << in_shift;
+  CDN_CHECK(to.H == (H - 1) / stride + 1 && to.W == (W - 1) / stride + 1, CDN_ERR_INVALID, "dw: output tensor shape mismatch");
+  EngOp* op = new EngOp();
+  op->kind = 1; op->in_t = in_t; op->out_t = out_t; op->in_shift = in_shift; op->stride = stride; op->zx = zx; op->H = H; op->W = W;
+  if (int r = dw_device_build(op->dw, wq, nullptr, C, std::min(ti.pitch, to.pitch), zx, rq)) { delete op; return r; }
+  e->ops.push_back(op);
+  return 0;
+}
+
+extern "C" int cdn_engine_add_deform(cdn_engine* e, int in_t, int out_t, int in_shift, const cdn_deform_scale* sc,
+                                     const int8_t* wq, int C, int zx, const cdn_requant* rq) {
+  ENG_CHECK(e);
+  CDN_CHECK(!e->finalized, CDN_ERR_STATE, "engine already finalized");
+  CDN_CHECK(sc && sc->ws, CDN_ERR_INVALID, "deform: null scale descriptor");
+  if (int r = check_t(e, in_t, "deform")) return r;
+  if (int r = check_t(e, out_t, "deform")) return r;
+  CDN_CUDA(cudaSetDevice(e->device));
+  const EngTensor &ti = e->tensors[in_t], &to = e->tensors[out_t];
+  int H = ti.H << in_shift, W = ti.W << in_shift;
+  CDN_CHECK(to.H == H && to.W == W, CDN_ERR_INVALID, "deform: output tensor shape mismatch");
+  EngOp* op = new EngOp();
+  op->kind = 2; op->in_t = in_t; op->out_t = out_t; op->in_shift = in_shift; op->stride = 1; op->zx = zx; op->H = H; op->W = W;
+  op->sc = *sc; op->ws_host.assign(sc->ws, sc->ws + C); op->sc.ws = op->ws_host.data();
+  if (int r = dw_device_build(op->dw, wq, sc->ws, C, std::min(ti.pitch, to.pitch), zx, rq)) { delete op; return r; }
+  e->ops.push_back(op);
+  return 0;
+}
+
+extern "C" int cdn_engine_add_pw(cdn_engine* e, int in_t, int pass_t, int out_t, const cdn_pw_desc* desc) {
+  ENG_CHECK(e);
+  CDN_CHECK(!e->finalized, CDN_ERR_STATE, "engine already finalized");
+  if (int r = check_t(e, in_t, "pw")) return r;
+  if (pass_t >= 0) if (int r = check_t(e, pass_t, "pw pass")) return r;
+  if (out_t >= 0) if (int r = check_t(e, out_t, "pw out")) return r;
+  CDN_CUDA(cudaSetDevice(e->device));
+  const EngTensor& ti = e->tensors[in_t];
+  if (pass_t >= 0) CDN_CHECK(e->tensors[pass_t].H == ti.H && e->tensors[pass_t].W == ti.W, CDN_ERR_INVALID, "pw: pass tensor shape mismatch");
+  if (out_t >= 0) CDN_CHECK(e->tensors[out_t].H == ti.H && e->tensors[out_t].W == ti.W, CDN_ERR_INVALID, "pw: output tensor shape mismatch");
+  CDN_CHECK((out_t >= 0) != (desc && desc->n_f32 > 0), CDN_ERR_INVALID, "pw: exactly one of int8 output tensor / fp32 head output must be set");
+  EngOp* op = new EngOp();
+  op->kind = 3; op->in_t = in_t; op->pass_t = pass_t; op->out_t = out_t; op->H = ti.H; op->W = ti.W;
+  if (int r = pw_device_build(op->pw, desc, pass_t >= 0 ? e->tensors[pass_t].pitch : 0)) { delete op; return r; }
+  if (desc->n_f32 > 0) e->n_f32 = desc->n_f32;
+  e->ops.push_back(op);
+  return 0;
+}
+
+extern "C" int cdn_engine_set_heads(cdn_engine* e, int cat, int H, int W, int K, int has_reg) {
+  ENG_CHECK(e);
+  CDN_CHECK(cat > 0 && H > 0 && W > 0 && K > 0 && K <= 1024, CDN_ERR_INVALID, "heads: bad arguments");
+  e->cat = cat; e->hH = H; e->hW = W; e->K = K; e->has_reg = has_reg;
+  return 0;
+}
+
+extern "C" int cdn_engine_finalize(cdn_engine* e, int max_batch) {
+  ENG_CHECK(e);
+  CDN_CHECK(!e->finalized, CDN_ERR_STATE, "engine already finalized");
+  CDN_CHECK(max_batch > 0 && !e->ops.empty() && e->cat > 0, CDN_ERR_INVALID, "finalize: empty plan, heads not set, or bad batch");
+  CDN_CHECK(e->n_f32 == e->cat + 2 + (e->has_reg ? 2 : 0), CDN_ERR_INVALID, "finalize: head conv has %d fp32 planes, expected %d", e->n_f32, e->cat + 2 + (e->has_reg ? 2 : 0));
+  CDN_CUDA(cudaSetDevice(e->device));
+  e->max_batch = max_batch;
+  for (auto& t : e->tensors) {
+    size_t bytes = (size_t)max_batch * t.H * t.W * t.pitch;
+    CDN_CUDA(cudaMalloc((void**)&t.ptr, bytes));
+    CDN_CUDA(cudaMemset(t.ptr, 0, bytes));
+  }
+  size_t ppi = (size_t)e->hH * e->hW;
+  CDN_CUDA(cudaMalloc((void**)&e->heads, (size_t)max_batch * e->n_f32 * ppi * sizeof(float)));
+  CDN_CUDA(cudaMalloc((void**)&e->dec_scratch, (size_t)max_batch * e->cat * ppi * sizeof(unsigned long long)));
+  CDN_CUDA(cudaMalloc((void**)&e->dets, (size_t)max_batch * e->K * 6 * sizeof(float)));
+  CDN_CUDA(cudaMalloc((void**)&e->inds, (size_t)max_batch * e->K * sizeof(int32_t)));
+  for (auto* op : e->ops) {
+    if (op->kind == 0 && op->pool) {
+      size_t b = (size_t)max_batch * ((op->H - 1) / op->stride + 1) * ((op->W - 1) / op->stride + 1) * 32;
+      CDN_CUDA(cudaMalloc((void**)&e->stem_tmp, b));
+    }
+    if (op->kind == 3) {
+      const EngTensor& ti = e->tensors[op->in_t];
+      uint64_t rows = (uint64_t)max_batch * ti.H * ti.W;
+      if (int r = make_tmap_2d(&op->tmA, ti.ptr, ti.pitch, rows, ti.pitch, 128)) return r;
+      if (op->pass_t >= 0) { const EngTensor& tp = e->tensors[op->pass_t]; if (int r = make_tmap_2d(&op->tmP, tp.ptr, tp.pitch, rows, tp.pitch, 128)) return r; }
+      if (op->out_t >= 0) { const EngTensor& to = e->tensors[op->out_t]; if (int r = make_tmap_2d(&op->tmO, to.ptr, to.pitch, rows, to.pitch, 128)) return r; }
+    }
+  }
+  CDN_CUDA(cudaDeviceSynchronize());
+  e->finalized = 1;
+  return 0;
+}
+
+static int engine_enqueue(cdn_engine* e, const float* d_img, int batch, float* d_hm, float* d_wh, float* d_reg,
+                          float* d_dets, int32_t* d_inds, cudaStream_t st, std::vector<cudaEvent_t>* marks = nullptr) {
+  int launches = 0;
+  auto mark = [&]() { if (marks) { cudaEvent_t ev; cudaEventCreate(&ev); cudaEventRecord(ev, st); marks->push_back(ev); } };
+  mark();
+  for (auto* op : e->ops) {
+    int r = 0;
+    switch (op->kind) {
+      case 0: {
+        const EngTensor& to = e->tensors[op->out_t];
+        r = stem_launch(op->stem, d_img, batch, op->H, op->W, op->stride, op->pool, to.ptr, to.pitch, e->stem_tmp, st);
+        launches += op->pool ? 2 : 1;
+      } break;
+      case 1: {
+        const EngTensor &ti = e->tensors[op->in_t], &to = e->tensors[op->out_t];
+        r = dw_launch(op->dw, ti.ptr, ti.pitch, to.ptr, to.pitch, batch, op->H, op->W, op->in_shift, op->stride, op->zx, st);
+        launches++;
+      } break;
+      case 2: {
+        const EngTensor &ti = e->tensors[op->in_t], &to = e->tensors[op->out_t];
+        r = deform_launch(op->dw, &op->sc, ti.ptr, ti.pitch, to.ptr, to.pitch, batch, op->H, op->W, op->in_shift, op->zx, nullptr, st);
+        launches++;
+      } break;
+      case 3: {
+        const EngTensor& ti = e->tensors[op->in_t];
+        const int8_t* pass = op->pass_t >= 0 ? e->tensors[op->pass_t].ptr : nullptr;
+        int pass_pitch = op->pass_t >= 0 ? e->tensors[op->pass_t].pitch : 0;
+        int8_t* out = op->out_t >= 0 ? e->tensors[op->out_t].ptr : nullptr;
+        int out_pitch = op->out_t >= 0 ? e->tensors[op->out_t].pitch : 0;
+        r = pw_launch(op->pw, ti.ptr, ti.pitch, (long long)batch * ti.H * ti.W, pass, pass_pitch, out, out_pitch,
+                      op->out_t < 0 ? e->heads : nullptr, e->hH * e->hW, &op->tmA, op->pass_t >= 0 ? &op->tmP : nullptr,
+                      op->out_t >= 0 ? &op->tmO : nullptr, st);
+        launches++;
+      } break;
+    }
+    if (r) return r;
+    mark();
+  }
+  const long long ppi = (long long)e->hH * e->hW;
+  if (d_hm || d_wh || d_reg) {
+    long long total = (long long)batch * e->n_f32 * ppi;
+    heads_copyout_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(e->heads, e->n_f32, e->cat, (int)ppi, total, d_hm, d_wh, d_reg);
+    CDN_LAUNCH_CHECK("heads_copyout_kernel");
+    launches++;
+  }
+  mark();
+  if (d_dets) {
+    const float* hm = e->heads;
+    const float* wh = e->heads + (size_t)e->cat * ppi;
+    const float* reg = e->has_reg ? e->heads + (size_t)(e->cat + 2) * ppi : nullptr;
+    long long is = (long long)e->n_f32 * ppi;
+    if (int r = decode_launch(hm, is, wh, is, reg, is, batch, e->cat, e->hH, e->hW, e->K, e->dec_scratch, d_dets, d_inds, st)) return r;
+    launches++;
+  }
+  mark();
+  e->launches = launches;
+  return 0;
+}
+
+// Eager run with a CUDA event between consecutive launches: ms[i] = duration of op i (plan order), then the
+// heads copy-out and the decode.  n must be >= number of ops + 2.  Used by bench.py for the per-kernel roofline.
+extern "C" int cdn_engine_profile(cdn_engine* e, const float* d_img, int batch, float* ms, int n, cdn_stream_t stream) {
+  ENG_CHECK(e);
+  CDN_CHECK(e->finalized && batch > 0 && batch <= e->max_batch && d_img && ms, CDN_ERR_INVALID, "profile: bad arguments");
+  CDN_CHECK(n >= (int)e->ops.size() + 2, CDN_ERR_INVALID, "profile: need room for %d timings", (int)e->ops.size() + 2);
+  CDN_CUDA(cudaSetDevice(e->device));
+  std::vector<cudaEvent_t> marks;
+  int r = engine_enqueue(e, d_img, batch, nullptr, nullptr, nullptr, e->dets, e->inds, (cudaStream_t)stream, &marks);
+  cudaError_t ce = cudaStreamSynchronize((cudaStream_t)stream);
+  if (!r && ce != cudaSuccess) r = cdn_fail(CDN_ERR_CUDA, "profile: %s", cudaGetErrorString(ce));
+  for (int i = 0; i < n; ++i) ms[i] = 0.f;
+  if (!r) for (size_t i = 0; i + 1 < marks.size() && (int)i < n; ++i) cudaEventElapsedTime(&ms[i], marks[i], marks[i + 1]);
+  for (auto ev : marks) cudaEventDestroy(ev);
+  return r;
+}
+
+extern "C" int cdn_engine_run(cdn_engine* e, const float* d_img, int batch, float* d_hm, float* d_wh, float* d_reg,
+                              float* d_dets, int32_t* d_inds, cdn_stream_t stream) {
+  ENG_CHECK(e);
+  CDN_CHECK(e->finalized, CDN_ERR_STATE, "engine not finalized");
+  CDN_CHECK(batch >= 0 && batch <= e->max_batch, CDN_ERR_INVALID, "batch %d exceeds the finalized maximum %d", batch, e->max_batch);
+  CDN_CHECK(d_img != nullptr, CDN_ERR_INVALID, "null image pointer");
+  if (batch == 0) return 0;
+  CDN_CUDA(cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!e->use_graph || (g_cdn_debug_flags & 2u)) return engine_enqueue(e, d_img, batch, d_hm, d_wh, d_reg, d_dets, d_inds, st);
+  cdn_engine::GraphKey key; memset(&key, 0, sizeof(key));
+  key.a[0] = d_img; key.a[1] = d_hm; key.a[2] = d_wh; key.a[3] = d_reg; key.a[4] = d_dets; key.a[5] = d_inds; key.batch = batch;
+  for (auto& g : e->graphs) if (g.first == key) { CDN_CUDA(cudaGraphLaunch(g.second, st)); return 0; }
+  // capture once per (pointers, batch)
+  cudaStream_t cap = e->s_compute;
+  CDN_CUDA(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
+  int r = engine_enqueue(e, d_img, batch, d_hm, d_wh, d_reg, d_dets, d_inds, cap);
+  cudaGraph_t graph = nullptr;
+  cudaError_t ce = cudaStreamEndCapture(cap, &graph);
+  if (r) { if (graph) cudaGraphDestroy(graph); return r; }
+  CDN_CHECK(ce == cudaSuccess && graph, CDN_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+  cudaGraphExec_t exec = nullptr;
+  ce = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  CDN_CHECK(ce == cudaSuccess, CDN_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ce));
+  if (e->graphs.size() >= 16) { cudaGraphExecDestroy(e->graphs.front().second); e->graphs.erase(e->graphs.begin()); }
+  e->graphs.push_back({key, exec});
+  CDN_CUDA(cudaGraphLaunch(exec, st));
+  return 0;
+}
+
+extern "C" int cdn_engine_run_host(cdn_engine* e, const float* h_img, int batch, float* h_dets, int32_t* h_inds) {
+  ENG_CHECK(e);
+  CDN_CHECK(e->finalized, CDN_ERR_STATE, "engine not finalized");
+  CDN_CHECK(batch >= 0 && batch <= e->max_batch && h_img && h_dets, CDN_ERR_INVALID, "run_host: bad arguments");
+  if (batch == 0) return 0;
+  CDN_CUDA(cudaSetDevice(e->device));
+  const size_t img_elems = (size_t)3 * e->in_H * e->in_W;
+  if (!e->d_img) {
+    e->d_img_bytes = (size_t)e->max_batch * img_elems * sizeof(float);
+    CDN_CUDA(cudaMalloc((void**)&e->d_img, e->d_img_bytes));
+  }
+  const int chunk = std::min(batch, e->host_chunk);
+  const int nchunks = (batch + chunk - 1) / chunk;
+  while ((int)e->ev.size() < nchunks) { cudaEvent_t ev; CDN_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); e->ev.push_back(ev); }
+  // H2D of chunk i+1 overlaps the compute of chunk i (two streams, one event per chunk)
+  for (int c = 0; c < nchunks; ++c) {
+    int b0 = c * chunk, nb = std::min(chunk, batch - b0);
+    CDN_CUDA(cudaMemcpyAsync(e->d_img + (size_t)b0 * img_elems, h_img + (size_t)b0 * img_elems, (size_t)nb * img_elems * sizeof(float),
+                             cudaMemcpyHostToDevice, e->s_copy));
+    CDN_CUDA(cudaEventRecord(e->ev[c], e->s_copy));
+  }
+  for (int c = 0; c < nchunks; ++c) {
+    int b0 = c * chunk, nb = std::min(chunk, batch - b0);
+    CDN_CUDA(cudaStreamWaitEvent(e->s_compute, e->ev[c], 0));
+    if (int r = cdn_engine_run(e, e->d_img + (size_t)b0 * img_elems, nb, nullptr, nullptr, nullptr,
+                               e->dets + (size_t)b0 * e->K * 6, e->inds + (size_t)b0 * e->K, e->s_compute)) return r;
+  }
+  CDN_CUDA(cudaMemcpyAsync(h_dets, e->dets, (size_t)batch * e->K * 6 * sizeof(float), cudaMemcpyDeviceToHost, e->s_compute));
+  if (h_inds) CDN_CUDA(cudaMemcpyAsync(h_inds, e->inds, (size_t)batch * e->K * sizeof(int32_t), cudaMemcpyDeviceToHost, e->s_compute));
+  CDN_CUDA(cudaStreamSynchronize(e->s_compute));
+  return 0;
+}
+
+extern "C" int cdn_engine_read_tensor(cdn_engine* e, int tensor, int batch, int8_t* h_out) {
+  ENG_CHECK(e);
+  CDN_CHECK(e->finalized, CDN_ERR_STATE, "engine not finalized");
+  if (int r = check_t(e, tensor, "read_tensor")) return r;
+  CDN_CHECK(batch > 0 && batch <= e->max_batch && h_out, CDN_ERR_INVALID, "read_tensor: bad arguments");
+  CDN_CUDA(cudaSetDevice(e->device));
+  CDN_CUDA(cudaDeviceSynchronize());
+  const EngTensor& t = e->tensors[tensor];
+  CDN_CUDA(cudaMemcpy(h_out, t.ptr, (size_t)batch * t.H * t.W * t.pitch, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int cdn_engine_read_heads(cdn_engine* e, int batch, float* h_out) {
+  ENG_CHECK(e);
+  CDN_CHECK(e->finalized && batch > 0 && batch <= e->max_batch && h_out, CDN_ERR_INVALID, "read_heads: bad arguments");
+  CDN_CUDA(cudaSetDevice(e->device));
+  CDN_CUDA(cudaDeviceSynchronize());
+  CDN_CUDA(cudaMemcpy(h_out, e->heads, (size_t)batch * e->n_f32 * e->hH * e->hW * sizeof(float), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int cdn_engine_num_launches(cdn_engine* e) { return e ? e->launches : 0; }

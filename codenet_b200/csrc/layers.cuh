@@ -1,0 +1,44 @@
+// Per-layer device state and launchers shared between the translation units of libcodenet_b200.
+#pragma once
+#include "common.cuh"
+
+struct DwDevice {                            // depthwise / deformable layer constants
+  uint32_t *wA = nullptr, *wB = nullptr, *wC = nullptr, *ws = nullptr;
+  DevRequant rq;
+  int cw_total = 0;
+  long long acc_s_bias = 0;
+};
+int dw_device_build(DwDevice& d, const int8_t* wq, const int8_t* ws, int C, int Cp, int zx, const cdn_requant* rq);
+void dw_device_free(DwDevice& d);
+int dw_launch(const DwDevice& d, const int8_t* in, int in_pitch, int8_t* out, int out_pitch, int batch, int H, int W,
+              int in_shift, int stride, int zx, cudaStream_t st);
+int deform_launch(const DwDevice& d, const cdn_deform_scale* sc, const int8_t* in, int in_pitch, int8_t* out,
+                  int out_pitch, int batch, int H, int W, int in_shift, int zx, float* sval, cudaStream_t st);
+
+struct StemDevice { double* w = nullptr; double* M = nullptr; double* B = nullptr; int C = 0; double lo = -128; };
+int stem_device_build(StemDevice& d, const int8_t* wq, int C, const cdn_requant* rq);
+void stem_device_free(StemDevice& d);
+int stem_launch(const StemDevice& d, const float* img, int batch, int H, int W, int stride, int pool,
+                int8_t* out, int out_pitch, int8_t* tmp, cudaStream_t st);
+
+struct PwDevice {
+  int K = 0, k_off = 0, N = 0, Kp = 0, BN = 0, n_tiles = 0, num_k_blocks = 0, stages = 0;
+  int has_pass = 0, pass_segs = 0, max_segs = 0, n_chunks = 0, n_f32 = 0;
+  size_t smem_bytes = 0;
+  int8_t* w = nullptr;                       // [BN*n_tiles][Kp]
+  cdn_pw_chunk* chunks = nullptr; int* chunk_begin = nullptr; int* seg_begin = nullptr;
+  double* Mf = nullptr; double* bf = nullptr;
+  DevRequant rq;
+  CUtensorMap tmB;
+};
+int pw_device_build(PwDevice& d, const cdn_pw_desc* desc, int pass_pitch);
+void pw_device_free(PwDevice& d);
+int pw_init_attrs();
+int pw_launch(const PwDevice& d, const int8_t* in, int in_pitch, long long pixels, const int8_t* pass, int pass_pitch,
+              int8_t* out, int out_pitch, float* out_f32, int ppi, const CUtensorMap* tmA, const CUtensorMap* tmP,
+              const CUtensorMap* tmO, cudaStream_t st);
+int make_tmap_2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t pitch, uint32_t box_rows);
+
+int decode_launch(const float* hm, long long hm_img_stride, const float* wh, long long wh_img_stride, const float* reg,
+                  long long reg_img_stride, int batch, int cat, int H, int W, int K, unsigned long long* scratch,
+                  float* dets, int32_t* inds, cudaStream_t st);

@@ -1,0 +1,113 @@
+// Stem: fp32 NCHW image -> 3x3 conv (8-bit integer weights) -> ReLU -> QuantAct -> int8 NHWC [-> MaxPool(3,2,1)].
+// Restates layer0 of the quantised graph (portable_quantizer/quantization_utils/quantize_model.py:26-35).
+// The image is raw fp32, so the accumulation runs in fp64: every product (fp32 value x int8) is exact and the sum
+// follows the oracle's (ci, i, j) order, which makes the accumulator bit-identical to the CPU restatement.
+#include "layers.cuh"
+
+#define STEM_MAXC 32
+
+struct StemParams {
+  const float* img; int8_t* out;
+  int H, W, Ho, Wo, stride, C, out_pitch;
+  long long total;
+  const double* w;                           // [C][27] as doubles
+  const double* M; const double* B;
+  double lo;
+};
+
+__global__ void __launch_bounds__(128) stem_kernel(StemParams p) {
+  __shared__ double sw[STEM_MAXC * 27];
+  __shared__ double sM[STEM_MAXC], sB[STEM_MAXC];
+  for (int i = threadIdx.x; i < p.C * 27; i += blockDim.x) sw[i] = p.w[i];
+  for (int i = threadIdx.x; i < p.C; i += blockDim.x) { sM[i] = p.M[i]; sB[i] = p.B[i]; }
+  __syncthreads();
+  long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= p.total) return;
+  int wo = (int)(pix % p.Wo); long long t = pix / p.Wo; int ho = (int)(t % p.Ho); long long b = t / p.Ho;
+  double x[27];
+#pragma unroll
+  for (int ci = 0; ci < 3; ++ci) {
+    const float* plane = p.img + ((size_t)b * 3 + ci) * p.H * p.W;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      int y = ho * p.stride - 1 + i;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        int xx = wo * p.stride - 1 + j;
+        bool ok = (unsigned)y < (unsigned)p.H && (unsigned)xx < (unsigned)p.W;
+        x[ci * 9 + i * 3 + j] = ok ? (double)__ldg(plane + (size_t)y * p.W + xx) : 0.0;
+      }
+    }
+  }
+  uint32_t words[STEM_MAXC / 4];
+#pragma unroll
+  for (int i = 0; i < STEM_MAXC / 4; ++i) words[i] = 0;
+  for (int c = 0; c < p.C; ++c) {
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < 27; ++k) acc = fma(sw[c * 27 + k], x[k], acc);   // products exact => fma == mul,add
+    double td = __dadd_rn(__dmul_rn(acc, sM[c]), sB[c]);
+    td = fmin(fmax(rint(td), p.lo), 127.0);
+    words[c >> 2] |= (uint32_t)((int)td & 0xff) << (8 * (c & 3));
+  }
+  uint4* dst = (uint4*)(p.out + (size_t)pix * p.out_pitch);
+  dst[0] = make_uint4(words[0], words[1], words[2], words[3]);
+  dst[1] = make_uint4(words[4], words[5], words[6], words[7]);
+}
+
+// MaxPool2d(3, 2, 1) on the int8 grid (monotone, so it commutes with the quantiser; padding = -inf)
+__global__ void maxpool3s2_kernel(const uint32_t* in, uint32_t* out, int H, int W, int Ho, int Wo, int pitch_w,
+                                  long long total_words) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total_words) return;
+  int cw = (int)(idx % pitch_w); long long pix = idx / pitch_w;
+  int wo = (int)(pix % Wo); long long t = pix / Wo; int ho = (int)(t % Ho); long long b = t / Ho;
+  uint32_t m = 0x80808080u;
+  for (int i = 0; i < 3; ++i) {
+    int y = 2 * ho - 1 + i; if ((unsigned)y >= (unsigned)H) continue;
+    for (int j = 0; j < 3; ++j) {
+      int x = 2 * wo - 1 + j; if ((unsigned)x >= (unsigned)W) continue;
+      m = __vmaxs4(m, __ldg(in + (((size_t)b * H + y) * W + x) * pitch_w + cw));
+    }
+  }
+  out[idx] = m;
+}
+
+
+int stem_device_build(StemDevice& d, const int8_t* wq, int C, const cdn_requant* rq) {
+  CDN_CHECK(C > 0 && C <= STEM_MAXC, CDN_ERR_INVALID, "stem: C=%d must be in 1..%d", C, STEM_MAXC);
+  CDN_CHECK(rq && rq->n == C && rq->M && rq->B, CDN_ERR_INVALID, "stem: requant constants must have n == C");
+  std::vector<double> w(C * 27);
+  for (int i = 0; i < C * 27; ++i) w[i] = (double)wq[i];
+  if (dev_upload(&d.w, w.data(), w.size())) return CDN_ERR_CUDA;
+  if (dev_upload(&d.M, rq->M, C)) return CDN_ERR_CUDA;
+  if (dev_upload(&d.B, rq->B, C)) return CDN_ERR_CUDA;
+  d.C = C; d.lo = (double)rq->lo;
+  return 0;
+}
+void stem_device_free(StemDevice& d) { cudaFree(d.w); cudaFree(d.M); cudaFree(d.B); d = StemDevice(); }
+
+// tmp: scratch for the un-pooled map when pool != 0 (batch*Ho*Wo*out_pitch bytes), else unused.
+int stem_launch(const StemDevice& d, const float* img, int batch, int H, int W, int stride, int pool,
+                int8_t* out, int out_pitch, int8_t* tmp, cudaStream_t st) {
+  CDN_CHECK(out_pitch == 32, CDN_ERR_INVALID, "stem: out pitch must be 32");
+  CDN_CHECK(stride >= 1 && stride <= 4, CDN_ERR_INVALID, "stem: bad stride");
+  StemParams p;
+  p.img = img; p.H = H; p.W = W; p.stride = stride; p.C = d.C; p.out_pitch = out_pitch;
+  p.Ho = (H - 1) / stride + 1; p.Wo = (W - 1) / stride + 1;
+  p.total = (long long)batch * p.Ho * p.Wo;
+  p.w = d.w; p.M = d.M; p.B = d.B; p.lo = d.lo;
+  p.out = pool ? tmp : out;
+  CDN_CHECK(!pool || tmp, CDN_ERR_INVALID, "stem: pooling needs a scratch buffer");
+  if (p.total == 0) return 0;
+  stem_kernel<<<(unsigned)((p.total + 127) / 128), 128, 0, st>>>(p);
+  CDN_LAUNCH_CHECK("stem_kernel");
+  if (pool) {
+    int Hp = (p.Ho - 1) / 2 + 1, Wp = (p.Wo - 1) / 2 + 1;
+    long long words = (long long)batch * Hp * Wp * (out_pitch / 4);
+    maxpool3s2_kernel<<<(unsigned)((words + 255) / 256), 256, 0, st>>>((const uint32_t*)tmp, (uint32_t*)out, p.Ho, p.Wo,
+                                                                        Hp, Wp, out_pitch / 4, words);
+    CDN_LAUNCH_CHECK("maxpool3s2_kernel");
+  }
+  return 0;
+}

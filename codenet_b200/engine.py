@@ -1,0 +1,160 @@
+"""Python host of the engine: feeds a Plan to libcodenet_b200 through the C ABI and runs it.
+
+PyTorch is used only for device memory and streams (plumbing); every kernel is hand-written CUDA in csrc/.
+There is no CPU path: constructing an Engine without an sm_100 GPU raises CdnError.
+"""
+import ctypes as C
+import os
+from typing import Dict, Optional
+
+import numpy as np
+
+from . import _lib
+from .arch import NetConfig
+from .plan import Plan, build_plan
+
+
+class Engine:
+    def __init__(self, plan: Plan, max_batch: int, device: int = 0, K: int = 100):
+        self.plan, self.max_batch, self.device, self.K = plan, int(max_batch), int(device), int(K)
+        self.lib = _lib.load()
+        if os.environ.get("CODENET_PW_SIMT") == "1":      # bring-up switch: SIMT cross-check kernel for 1x1 convs
+            self.lib.cdn_set_debug_flags(1)
+        self._h = C.c_void_p()
+        _lib.check(self.lib.cdn_engine_create(C.byref(self._h), self.device))
+        keep = _lib.Keep()
+        L = self.lib
+        for t in plan.tensors:
+            tid = L.cdn_engine_add_tensor(self._h, t.H, t.W, t.pitch)
+            if tid != t.id:
+                _lib.check(tid if tid < 0 else -1)
+        for op in plan.ops:
+            a = op.a
+            if op.kind == "stem":
+                rq = keep.requant(a["M"], a["B"], a["lo"])
+                rc = L.cdn_engine_add_stem(self._h, a["out_t"], a["H"], a["W"], a["stride"], a["pool"], keep.i8(a["wq"]),
+                                           a["C"], C.byref(rq))
+            elif op.kind == "dw":
+                rq = keep.requant(a["M"], a["B"], a["lo"])
+                rc = L.cdn_engine_add_dw(self._h, a["in_t"], a["out_t"], a["in_shift"], a["stride"], keep.i8(a["wq"]),
+                                         a["C"], a["zx"], C.byref(rq))
+            elif op.kind == "deform":
+                rq = keep.requant(a["M"], a["B"], a["lo"])
+                sc = keep.deform_scale(a)
+                rc = L.cdn_engine_add_deform(self._h, a["in_t"], a["out_t"], a["in_shift"], C.byref(sc), keep.i8(a["wq"]),
+                                             a["C"], a["zx"], C.byref(rq))
+            elif op.kind == "pw":
+                d = keep.pw_desc(a)
+                rc = L.cdn_engine_add_pw(self._h, a["in_t"], a["pass_t"], a["out_t"], C.byref(d))
+            else:
+                raise ValueError(op.kind)
+            if rc != 0:
+                raise _lib.CdnError("codenet_b200: op %s: %s" % (op.name, L.cdn_last_error().decode()))
+        has_reg = 1 if len(plan.cfg.head_list()) > 2 else 0
+        _lib.check(L.cdn_engine_set_heads(self._h, plan.cat, plan.out_H, plan.out_W, self.K, has_reg))
+        _lib.check(L.cdn_engine_finalize(self._h, self.max_batch))
+        self.n_f32 = plan.cat + 2 + 2 * has_reg
+
+    # -- construction helpers -------------------------------------------------------------------------------------
+    @classmethod
+    def from_state_dict(cls, cfg: NetConfig, state: Dict[str, np.ndarray], in_H: int, in_W: int, max_batch: int,
+                        offset_mode: str = "round", device: int = 0, K: int = 100):
+        state = {k: (v.detach().cpu().numpy() if hasattr(v, "detach") else np.asarray(v)) for k, v in state.items()}
+        return cls(build_plan(cfg, state, in_H, in_W, offset_mode), max_batch, device, K)
+
+    @classmethod
+    def from_module(cls, model, in_H: int, in_W: int, max_batch: int, offset_mode: str = "bilinear", device: int = 0,
+                    K: int = 100):
+        """`model`: a PoseShuffleNetV2 already rewritten by quantize_shufflenetv2_dcn (reference or our mirror)."""
+        sd = model.state_dict()
+        w2 = sd["layer4.0.conv.weight"].shape[0] == 2153
+        maxpool = tuple(getattr(model.layer0[0].conv, "stride", (4, 4))) == (2, 2)
+        heads = tuple((h, int(sd[h + ".quant_conv.weight"].shape[0])) for h in model.heads)
+        cfg = NetConfig(num_classes=heads[0][1], w2=w2, maxpool=maxpool, heads=heads)
+        return cls.from_state_dict(cfg, sd, in_H, in_W, max_batch, offset_mode, device, K)
+
+    def close(self):
+        if self._h:
+            self.lib.cdn_engine_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, name: str, value: int):
+        _lib.check(self.lib.cdn_engine_set_option(self._h, name.encode(), int(value)))
+
+    # -- execution ----------------------------------------------------------------------------------------------------
+    def run(self, images, maps: bool = True, dets: bool = True, out: Optional[dict] = None):
+        """images: torch CUDA fp32 [B,3,H,W] (contiguous).  Returns dict of torch CUDA tensors:
+        hm (post-sigmoid, ctdet.py:32), wh, reg [B,*,H/4,W/4]; dets [B,K,6]; inds [B,K]."""
+        import torch
+        assert images.is_cuda and images.dtype == torch.float32 and images.is_contiguous()
+        B = images.shape[0]
+        assert images.shape[1:] == (3, self.plan.in_H, self.plan.in_W), images.shape
+        Ho, Wo, cat = self.plan.out_H, self.plan.out_W, self.plan.cat
+        o = out if out is not None else {}
+        dev = images.device
+        if maps and "hm" not in o:
+            o["hm"] = torch.empty((B, cat, Ho, Wo), dtype=torch.float32, device=dev)
+            o["wh"] = torch.empty((B, 2, Ho, Wo), dtype=torch.float32, device=dev)
+            o["reg"] = torch.empty((B, 2, Ho, Wo), dtype=torch.float32, device=dev)
+        if dets and "dets" not in o:
+            o["dets"] = torch.empty((B, self.K, 6), dtype=torch.float32, device=dev)
+            o["inds"] = torch.empty((B, self.K), dtype=torch.int32, device=dev)
+        p = lambda k: C.c_void_p(o[k].data_ptr()) if k in o else None
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(self.lib.cdn_engine_run(self._h, C.c_void_p(images.data_ptr()), B, p("hm") if maps else None,
+                                           p("wh") if maps else None, p("reg") if maps else None,
+                                           p("dets") if dets else None, p("inds") if dets else None, stream))
+        return o
+
+    def run_host(self, images: np.ndarray, dets: Optional[np.ndarray] = None, inds: Optional[np.ndarray] = None):
+        """images: host fp32 [B,3,H,W] (numpy, ideally backed by pinned memory).  H2D, forward, decode, D2H."""
+        B = images.shape[0]
+        assert images.dtype == np.float32 and images.flags["C_CONTIGUOUS"]
+        if dets is None:
+            dets = np.empty((B, self.K, 6), np.float32)
+        if inds is None:
+            inds = np.empty((B, self.K), np.int32)
+        _lib.check(self.lib.cdn_engine_run_host(self._h, C.c_void_p(images.ctypes.data), B, C.c_void_p(dets.ctypes.data),
+                                                C.c_void_p(inds.ctypes.data)))
+        return dets, inds
+
+    def profile(self, images):
+        """Per-op device times (ms) of one eager run: list of (op name, kind, ms) + ('decode', ...)."""
+        import torch
+        n = len(self.plan.ops) + 2
+        ms = np.zeros(n, np.float32)
+        stream = C.c_void_p(torch.cuda.current_stream(images.device).cuda_stream)
+        _lib.check(self.lib.cdn_engine_profile(self._h, C.c_void_p(images.data_ptr()), images.shape[0],
+                                               C.c_void_p(ms.ctypes.data), n, stream))
+        out = [(op.name, op.kind, float(ms[i])) for i, op in enumerate(self.plan.ops)]
+        out.append(("heads_copyout", "copyout", float(ms[n - 2])))
+        out.append(("ctdet_decode", "decode", float(ms[n - 1])))
+        return out
+
+    @property
+    def num_launches(self):
+        return int(self.lib.cdn_engine_num_launches(self._h))
+
+    # -- test / debug access ------------------------------------------------------------------------------------------
+    def read_tensor(self, tid: int, batch: int) -> np.ndarray:
+        t = self.plan.tensors[tid]
+        buf = np.empty((batch, t.H, t.W, t.pitch), np.int8)
+        _lib.check(self.lib.cdn_engine_read_tensor(self._h, tid, batch, C.c_void_p(buf.ctypes.data)))
+        return buf
+
+    def read_logical(self, label: str, batch: int) -> np.ndarray:
+        """Activation of a tapped QuantAct as logical NCHW int8."""
+        t = self.plan.tensors[self.plan.taps[label]]
+        raw = self.read_tensor(t.id, batch)
+        return np.ascontiguousarray(raw[..., t.phys(np.arange(t.C))].transpose(0, 3, 1, 2))
+
+    def read_heads(self, batch: int) -> np.ndarray:
+        buf = np.empty((batch, self.n_f32, self.plan.out_H, self.plan.out_W), np.float32)
+        _lib.check(self.lib.cdn_engine_read_heads(self._h, batch, C.c_void_p(buf.ctypes.data)))
+        return buf

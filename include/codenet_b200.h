@@ -1,0 +1,189 @@
+/* codenet_b200 -- C ABI of the B200-native CoDeNet inference hot path (libcodenet_b200.so).
+ *
+ * Plain pointers and sizes only; every function returns 0 on success or a negative cdn_status, and
+ * cdn_last_error() returns a thread-local message.  No exception crosses this boundary, no hidden device
+ * allocation happens after cdn_engine_finalize(), all device pointers are caller-owned unless stated, and every
+ * launch goes to the cudaStream_t passed in (the reference launches on the legacy default stream and only
+ * printf()s launch errors, lib/models/external/src/dcn_deform_conv_cuda_kernel.cu:264-275).
+ *
+ * Reference interfaces replaced (paths relative to the reference tree, see INTEGRATION.md for the bindings):
+ *   cdn_deform_conv_forward_f32   <- deform_conv_forward_cuda, lib/models/external/src/dcn_deform_conv_cuda.cpp:151-258
+ *                                    (pybind export :681-695; called from functions/dcn_deform_conv.py:51-56)
+ *   cdn_deform_dw_w4a8            <- QuantDeformConvWithOffsetScaleBoundPositive.forward up to quant_identity_deform,
+ *                                    portable_quantizer/quant_modules.py:668-671 (scale conv :648-650, Hardtanh+QuantAct
+ *                                    :651-653, QuantDeformConv2d :473-517, QuantAct :202-225)
+ *   cdn_pw_gemm_i8                <- QuantBnConv2d.forward / Quant_Conv2d.forward for 1x1 convs, quant_modules.py:364-419,
+ *                                    :278-321, with the following ReLU + QuantAct and cat/channel_shuffle
+ *                                    (lib/models/networks/shufflenetv2_dcn.py:29-34) folded into the store
+ *   cdn_dw3x3_i8                  <- QuantBnConv2d.forward for depthwise 3x3 convs (same lines) + QuantAct
+ *   cdn_stem_f32_i8               <- layer0 = QuantBnConv2d(8 bit) + ReLU + QuantAct [+ MaxPool], quantize_model.py:26-35
+ *   cdn_ctdet_decode              <- ctdet_decode, lib/models/decode.py:474-505 (_nms :10-16, _topk :110-126)
+ *   cdn_engine_*                  <- PoseShuffleNetV2.forward (shufflenetv2_dcn.py:314-330) as rewritten by
+ *                                    quantize_shufflenetv2_dcn (quantize_model.py:7-82) + CtdetDetector.process
+ *                                    (lib/detectors/ctdet.py:29-46)
+ *
+ * Activation layout: NHWC int8, `pitch` bytes per pixel (a multiple of 32); the real value of an element is
+ * (q + z) / s for the (s, z) of the QuantAct that produced it (quant_utils.py:58-73).
+ *
+ * Requantisation constants (one per output channel): q = clamp(rint(acc*M + B), lo, 127) with
+ * M, B in fp64.  The library derives an fp32 copy and a per-channel guard band inside which the kernels re-evaluate
+ * in fp64, so results are bit-identical to the fp64 formula.
+ */
+#ifndef CODENET_B200_H
+#define CODENET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* cdn_stream_t;                 /* a cudaStream_t */
+
+typedef enum {
+  CDN_OK = 0,
+  CDN_ERR_INVALID = -1,                     /* bad argument / unsupported shape */
+  CDN_ERR_CUDA = -2,                        /* CUDA runtime or driver error (message has the CUDA string) */
+  CDN_ERR_NO_DEVICE = -3,                   /* no usable sm_100 device: there is NO CPU fallback */
+  CDN_ERR_STATE = -4                        /* engine used in the wrong order */
+} cdn_status;
+
+const char* cdn_last_error(void);
+int cdn_version(void);
+/* 0 = ok; CDN_ERR_NO_DEVICE if `device` is not a compute-capability-10.x GPU. */
+int cdn_check_device(int device);
+/* bit 0: run 1x1 convolutions on the SIMT cross-check kernel instead of tcgen05 (bring-up / tests only). */
+int cdn_set_debug_flags(unsigned flags);
+
+/* ---- per-output-channel requantisation constants (host arrays, length n) ------------------------------- */
+typedef struct {
+  const double* M;                          /* s_out / (sigma_c * s_x) */
+  const double* B;                          /* s_out * b'_c - z_out */
+  int lo;                                   /* max(-128, relu ? -z_out : -128) */
+  int n;
+} cdn_requant;
+
+/* ---- stem: fp32 NCHW image -> int8 NHWC -----------------------------------------------------------------
+ * 3x3 conv, pad 1, stride `stride`, 3 -> C (C <= 32), 8-bit integer weights wq[C][3][3][3] (host), then ReLU and
+ * QuantAct.  If pool != 0 a MaxPool2d(3,2,1) follows on the quantised grid.  out pitch = 32. */
+int cdn_stem_f32_i8(const float* d_img, int batch, int H, int W, int stride, int pool,
+                    const int8_t* wq, int C, const cdn_requant* rq, int8_t* d_out, int out_pitch,
+                    cdn_stream_t stream);
+
+/* ---- depthwise 3x3 (pad 1), int8 NHWC -> int8 NHWC -------------------------------------------------------
+ * wq[C][9] (host).  in_shift = 1 reads the input through a virtual nearest x2 upsample (input stored at H/2 x W/2).
+ * zx is the input zero point: out-of-image taps contribute real zero, i.e. q = -zx, which must fit int8. */
+int cdn_dw3x3_i8(const int8_t* d_in, int in_pitch, int batch, int H, int W, int in_shift, int stride,
+                 const int8_t* wq, int C, int zx, const cdn_requant* rq, int8_t* d_out, int out_pitch,
+                 cdn_stream_t stream);
+
+/* ---- fused co-designed deformable depthwise conv (W4A8) --------------------------------------------------
+ * Per output pixel: u = clamp(acc_s*Ms + bs, -bound+1, bound) with acc_s = sum_c ws[c]*(q+zx);
+ * qs = rint(ss*u - zs); s = (qs+zs)/ss; mode 0: s = rint(s) and tap (i,j) reads pixel (h+(i-1)s, w+(j-1)s);
+ * mode 1: bilinear sampling at the fractional position (reference default).  Then 3x3 depthwise MAC with wq[C][9]
+ * and requantisation.  H, W are the OUTPUT/sampling-grid size; in_shift as for cdn_dw3x3_i8.
+ * d_sval (optional, may be NULL): float [batch*H*W] receives s as used. */
+typedef struct {
+  const int8_t* ws;                         /* [C] 4-bit integer weights of the C->1 scale conv (host) */
+  double Ms, bs;                            /* 1/(sigma_s*s_x), bias */
+  double ss, zs;                            /* QuantAct of s */
+  int bound;                                /* offset_bound (Hardtanh -bound+1 .. bound) */
+  int mode;                                 /* 0 = integer offsets (round half even), 1 = bilinear */
+} cdn_deform_scale;
+
+int cdn_deform_dw_w4a8(const int8_t* d_in, int in_pitch, int batch, int H, int W, int in_shift,
+                       const cdn_deform_scale* sc, const int8_t* wq, int C, int zx, const cdn_requant* rq,
+                       int8_t* d_out, int out_pitch, float* d_sval, cdn_stream_t stream);
+
+/* ---- 1x1 convolution as int8 tcgen05 GEMM ---------------------------------------------------------------
+ * acc[p][n] = sum_k wq[n][k] * (in[p][k_off + k] + zx)   (exact int32; the library adds zx*sum_k wq[n][k] itself)
+ * Output "chunks" describe where each group of <=16 output channels lands in the NHWC row, so that split /
+ * cat / channel_shuffle cost nothing: a chunk takes `count` consecutive GEMM columns starting at `col`, optionally
+ * interleaves them with `count` bytes of a pass-through tensor starting at byte `pass_off` (out[2i] = pass[i],
+ * out[2i+1] = new[i]), zero-fills up to 16 bytes and stores them at byte `dst_off` of the output pixel. */
+typedef struct {
+  int16_t col;                              /* first GEMM column (multiple of 8) */
+  int16_t count;                            /* valid columns: <=16 plain, <=8 interleaved, 0 = zero fill */
+  int16_t pass_off;                         /* -1: plain; else byte offset inside the pass-through pixel */
+  int16_t dst_off;                          /* byte offset inside the output pixel (multiple of 16) */
+} cdn_pw_chunk;
+
+typedef struct {
+  int K;                                    /* input channels actually read: in[p][k_off .. k_off+K) */
+  int k_off;                                /* byte offset of the first input channel inside the pixel */
+  int N;                                    /* GEMM columns (rows of wq), multiple of 16, <= 1024 */
+  int zx;                                   /* zero point of the input QuantAct */
+  const int8_t* wq;                         /* host [N][K] integer weights (zero rows/cols for padding) */
+  cdn_requant rq;                           /* per GEMM column, n = N */
+  const cdn_pw_chunk* chunks; int n_chunks; /* int8 output description (ignored when f32 output is used) */
+  /* fp32 NCHW output (head convs): column n < n_f32 goes to d_out_f32[image][n][pixel] with
+   * y = acc*Mf[n] + bf[n] (fp64, rounded once to fp32); sigmoid is NOT applied. */
+  int n_f32; const double* Mf; const double* bf;
+} cdn_pw_desc;
+
+int cdn_pw_gemm_i8(const int8_t* d_in, int in_pitch, int64_t pixels, const cdn_pw_desc* desc,
+                   const int8_t* d_pass, int pass_pitch, int8_t* d_out, int out_pitch,
+                   float* d_out_f32, int pixels_per_image, cdn_stream_t stream);
+
+/* ---- ctdet decode ---------------------------------------------------------------------------------------
+ * hm: LOGITS fp32 [batch][cat][H][W]; wh, reg: fp32 [batch][2][H][W] (reg may be NULL -> +0.5).
+ * Peaks = elements equal to the max of their 3x3 neighbourhood; the K best by (logit desc, class asc, index asc).
+ * dets: fp32 [batch][K][6] = x1,y1,x2,y2,sigmoid(logit),class.  inds (optional): int32 [batch][K] = class*H*W+index.
+ * If an image has fewer than K peaks the remaining rows are zero and inds = -1. */
+int cdn_ctdet_decode(const float* d_hm, const float* d_wh, const float* d_reg, int batch, int cat, int H, int W,
+                     int K, float* d_dets, int32_t* d_inds, cdn_stream_t stream);
+
+/* ---- general deformable convolution forward, fp32 (the reference's native plug-in point) ----------------
+ * Same argument meaning and order (W before H) as deform_conv_forward_cuda; tensors are contiguous NCHW device
+ * pointers: input [B][C][H][W], weight [Co][C/group][kH][kW], offset [B][2*kH*kW*dg][Ho][Wo], output [B][Co][Ho][Wo].
+ * im2col_step is accepted and ignored (no im2col buffer exists).  Returns 0 (the reference returns 1). */
+int cdn_deform_conv_forward_f32(const float* input, const float* weight, const float* offset, float* output,
+                                int B, int C, int H, int W, int Co, int kW, int kH, int dW, int dH,
+                                int padW, int padH, int dilW, int dilH, int group, int deformable_group,
+                                int im2col_step, cdn_stream_t stream);
+
+/* ---- whole-network engine -------------------------------------------------------------------------------
+ * A plan is a list of tensors (activation buffers) and ops appended in execution order, then finalised for a
+ * maximum batch.  All descriptor arrays are copied at add time. */
+typedef struct cdn_engine cdn_engine;
+
+int cdn_engine_create(cdn_engine** out, int device);
+int cdn_engine_destroy(cdn_engine* e);
+/* returns tensor id >= 0; H, W per image; pitch bytes per pixel. */
+int cdn_engine_add_tensor(cdn_engine* e, int H, int W, int pitch);
+int cdn_engine_add_stem(cdn_engine* e, int out_t, int H, int W, int stride, int pool,
+                        const int8_t* wq, int C, const cdn_requant* rq);
+int cdn_engine_add_dw(cdn_engine* e, int in_t, int out_t, int in_shift, int stride, const int8_t* wq, int C, int zx,
+                      const cdn_requant* rq);
+int cdn_engine_add_deform(cdn_engine* e, int in_t, int out_t, int in_shift, const cdn_deform_scale* sc,
+                          const int8_t* wq, int C, int zx, const cdn_requant* rq);
+/* pass_t = -1 when no chunk interleaves; out_t = -1 for fp32 head output (then f32_slot selects hm/wh/reg via
+ * desc->f32 planes: plane index p < cat -> hm[p], cat <= p < cat+2 -> wh, else reg). */
+int cdn_engine_add_pw(cdn_engine* e, int in_t, int pass_t, int out_t, const cdn_pw_desc* desc);
+int cdn_engine_set_heads(cdn_engine* e, int cat, int H, int W, int K, int has_reg);
+int cdn_engine_finalize(cdn_engine* e, int max_batch);
+/* d_img: fp32 [batch][3][H][W] on the device.  Outputs (device, may be NULL to skip the copy-out of a map):
+ * hm fp32 [batch][cat][Ho][Wo] AFTER sigmoid (ctdet.py:32), wh/reg fp32 [batch][2][Ho][Wo], dets [batch][K][6],
+ * inds int32 [batch][K]. */
+int cdn_engine_run(cdn_engine* e, const float* d_img, int batch, float* d_hm, float* d_wh, float* d_reg,
+                   float* d_dets, int32_t* d_inds, cdn_stream_t stream);
+/* Same through HOST buffers: pinned staging, chunked H2D overlapped with compute, D2H of the detections. */
+int cdn_engine_run_host(cdn_engine* e, const float* h_img, int batch, float* h_dets, int32_t* h_inds);
+/* Options: "host_chunk" (images per H2D/compute pipeline step of run_host, default 32), "use_graph" (replay the
+ * launch sequence as a CUDA graph, default 1), "micro_batch" (run the layers over sub-batches of this many images
+ * so consecutive layers hit L2, 0 = whole batch). */
+int cdn_engine_set_option(cdn_engine* e, const char* name, int value);
+/* Debug/test access to an activation tensor of the last run: copies batch*H*W*pitch bytes to host. */
+int cdn_engine_read_tensor(cdn_engine* e, int tensor, int batch, int8_t* h_out);
+/* Raw head outputs of the last run: fp32 [batch][cat+4][Ho*Wo] = hm logits, wh, reg. */
+int cdn_engine_read_heads(cdn_engine* e, int batch, float* h_out);
+/* Eager run with CUDA events between launches: ms[i] = device time of plan op i, then heads copy-out, then decode
+ * (n >= number of ops + 2).  For per-kernel roofline reporting. */
+int cdn_engine_profile(cdn_engine* e, const float* d_img, int batch, float* ms, int n, cdn_stream_t stream);
+/* Number of kernels one cdn_engine_run launches (for bench.py's gpu_launches). */
+int cdn_engine_num_launches(cdn_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

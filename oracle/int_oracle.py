@@ -34,7 +34,8 @@ F = np.float64
 
 def act_params(lo, hi, bits=8):
     lo, hi = F(lo), F(hi)
-    s = F(2 ** bits - 1) / max(hi - lo, F(1e-10))
+    # `n / tensor` in torch is tensor.reciprocal() * n (Tensor.__rtruediv__): two roundings, restated as such
+    s = (F(1) / max(hi - lo, F(1e-10))) * F(2 ** bits - 1)
     z = np.rint(s * lo) + F(2 ** (bits - 1))
     return s, z
 
@@ -43,7 +44,7 @@ def quant_weight(w, bits):
     """w: [Cout, ...] fp64.  Returns integer weights (int64) and the per-channel scale sigma."""
     flat = w.reshape(w.shape[0], -1)
     mag = np.maximum(np.abs(flat.min(1)), np.abs(flat.max(1)))
-    sigma = F(2 ** (bits - 1) - 1) / np.maximum(mag, F(1e-10))
+    sigma = (F(1) / np.maximum(mag, F(1e-10))) * F(2 ** (bits - 1) - 1)   # reciprocal * n, as torch evaluates n / tensor
     q = np.rint(sigma.reshape(-1, *([1] * (w.ndim - 1))) * w)
     q = np.clip(q, -(2 ** (bits - 1)), 2 ** (bits - 1) - 1)
     return q.astype(np.int64), sigma

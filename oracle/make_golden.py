@@ -38,7 +38,8 @@ def quant_kat():
     # asymmetric activation quant, unclamped (quant_utils.py:191-198)
     x = rng.standard_normal((2, 5, 7, 6)) * 3
     for i, (lo, hi) in enumerate([(-7.3, 9.1), (0.0, 6.0), (x.min(), x.max())]):
-        y = qu.AsymmetricQuantFunction.apply(T(x), 8, torch.tensor([lo]), torch.tensor([hi]))
+        y = qu.AsymmetricQuantFunction.apply(T(x), 8, torch.tensor([lo], dtype=torch.float64),
+                                               torch.tensor([hi], dtype=torch.float64))
         out["act%d_x" % i] = x
         out["act%d_range" % i] = np.array([lo, hi])
         out["act%d_y" % i] = y.numpy()

@@ -1,0 +1,166 @@
+"""Whole-network parity on the GPU: engine vs the vectors of the unmodified reference (fp64) and vs the oracle."""
+import numpy as np
+import pytest
+
+from codenet_b200 import _lib
+from codenet_b200.arch import NetConfig
+from codenet_b200.engine import Engine
+from codenet_b200.synth import make_quant_state, make_images
+from oracle import int_oracle as io
+from util import assert_dets_match_tie_aware, int8_mismatch
+
+pytestmark = pytest.mark.gpu
+CFG = NetConfig(num_classes=20)
+
+
+def _engine(calib, mode, res, max_batch):
+    st = make_quant_state(CFG, calib, mode, res)
+    return Engine.from_state_dict(CFG, st, res, res, max_batch, offset_mode=mode)
+
+
+def _up2(a):
+    return np.repeat(np.repeat(a, 2, axis=2), 2, axis=3)
+
+
+@pytest.mark.parametrize("mode", ["round", "bilinear"])
+def test_engine_matches_reference_vectors_256(golden, calib, mode):
+    import torch
+    g = golden("codenet1x_256_%s.npz" % mode)
+    eng = _engine(calib, mode, 256, 4)
+    x = make_images(2, 256, seed=2)
+    out = eng.run(torch.from_numpy(x).cuda())
+    torch.cuda.synchronize()
+    # every int8 grid recorded from the reference, bit for bit
+    names = {"hm.act1": ("heads.act1", slice(0, 64), True), "hm.act3": ("heads.act3", slice(0, 64), False)}
+    checked = 0
+    for k in g.files:
+        if g[k].dtype != np.int8 or k.endswith(".s"):
+            continue
+        lbl, sl, up = names.get(k, (k, slice(None), False))
+        got = eng.read_logical(lbl, 2)[:, sl]
+        if up:
+            got = _up2(got)
+        assert int8_mismatch(got, g[k]) == 0, k
+        checked += 1
+    assert checked >= (16 if mode == "round" else 8)
+    # head outputs: exact integer accumulator, fp64 epilogue, one rounding to fp32
+    heads = eng.read_heads(2)
+    ref = np.concatenate([g["hm_logit"], g["wh"], g["reg"]], 1)
+    np.testing.assert_allclose(heads, ref, rtol=2e-7, atol=1e-7)
+    hm = out["hm"].cpu().numpy()
+    np.testing.assert_allclose(hm, 1 / (1 + np.exp(-g["hm_logit"])), rtol=2e-6, atol=1e-7)
+    np.testing.assert_array_equal(out["wh"].cpu().numpy(), heads[:, 20:22])
+    np.testing.assert_array_equal(out["reg"].cpu().numpy(), heads[:, 22:24])
+    # detections: indices/order bit-exact against the deterministic oracle, tie-aware against the reference
+    dets = out["dets"].cpu().numpy().astype(np.float64)
+    inds = out["inds"].cpu().numpy()
+    h64 = heads.astype(np.float64)
+    odets, oinds = io.ctdet_decode(h64[:, :20], h64[:, 20:22], h64[:, 22:24], 100)
+    more, _ = io.ctdet_decode(h64[:, :20], h64[:, 20:22], h64[:, 22:24], 160)
+    np.testing.assert_array_equal(inds, oinds)
+    np.testing.assert_allclose(dets, odets, rtol=1e-5, atol=1e-4)
+    for b in range(2):
+        assert_dets_match_tie_aware(g["dets"][b], odets[b], more[b])
+    eng.close()
+
+
+def test_engine_matches_reference_vectors_512(golden, calib):
+    import torch
+    g = golden("codenet1x_512_round.npz")
+    eng = _engine(calib, "round", 512, 2)
+    x = make_images(2, 512, seed=3)[:1]
+    out = eng.run(torch.from_numpy(x).cuda())
+    torch.cuda.synchronize()
+    assert int8_mismatch(eng.read_logical("stem", 1)[:, :, ::4, ::4], g["stem"]) == 0
+    assert int8_mismatch(eng.read_logical("up2.out", 1)[:, :, ::4, ::4], g["up2.out"]) == 0
+    heads = eng.read_heads(1)
+    ref = np.concatenate([g["hm_logit_s8"], g["wh_s8"], g["reg_s8"]], 1)
+    np.testing.assert_allclose(heads[:, :, ::8, ::8], ref, rtol=2e-7, atol=1e-7)
+    h64 = heads.astype(np.float64)
+    odets, oinds = io.ctdet_decode(h64[:, :20], h64[:, 20:22], h64[:, 22:24], 100)
+    more, _ = io.ctdet_decode(h64[:, :20], h64[:, 20:22], h64[:, 22:24], 160)
+    np.testing.assert_array_equal(out["inds"].cpu().numpy(), oinds)
+    assert_dets_match_tie_aware(g["dets"][0], odets[0], more[0])
+    eng.close()
+
+
+def test_engine_equals_oracle_on_fresh_images(calib):
+    """Other seeds than the golden ones (activations may saturate: the oracle saturates identically)."""
+    import torch
+    st = make_quant_state(CFG, calib, "round", 256)
+    eng = Engine.from_state_dict(CFG, st, 256, 256, 4, offset_mode="round")
+    x = make_images(3, 256, seed=77, clamp=4.0)
+    out = eng.run(torch.from_numpy(x).cuda())
+    torch.cuda.synchronize()
+    o = io.IntOracle(CFG, st, "round")
+    ref = o.forward(x)
+    for lbl in ("stem", "layer1.out", "layer2.out", "layer3.out", "layer4", "up0.deform", "up1.deform", "up2.deform", "up2.out"):
+        assert int8_mismatch(eng.read_logical(lbl, 3), o.cap[lbl]) == 0, lbl
+    heads = eng.read_heads(3)
+    np.testing.assert_array_equal(heads, np.concatenate([ref["hm"], ref["wh"], ref["reg"]], 1).astype(np.float32))
+    eng.close()
+
+
+def test_batch_independence_graph_and_host_path(calib):
+    """Frozen ranges make images independent: replicas give identical rows; graph replay, eager
+    launches, the SIMT cross-check kernel and the host-buffer path all agree bit for bit."""
+    import torch
+    eng = _engine(calib, "round", 256, 8)
+    base = make_images(2, 256, seed=5)
+    x = np.concatenate([base, base, base[::-1], base])            # 8 images
+    xt = torch.from_numpy(x).cuda()
+    o1 = eng.run(xt, maps=False)
+    torch.cuda.synchronize()
+    d1, i1 = o1["dets"].cpu().numpy(), o1["inds"].cpu().numpy()
+    np.testing.assert_array_equal(d1[0], d1[2]); np.testing.assert_array_equal(d1[0], d1[5]); np.testing.assert_array_equal(d1[1], d1[7])
+    o2 = eng.run(xt, maps=False)                                   # second call = graph replay
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(o2["dets"].cpu().numpy(), d1)
+    eng.set_option("use_graph", 0)
+    o3 = eng.run(xt, maps=False)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(o3["dets"].cpu().numpy(), d1)
+    _lib.load().cdn_set_debug_flags(1)
+    o4 = eng.run(xt, maps=False)
+    torch.cuda.synchronize()
+    _lib.load().cdn_set_debug_flags(0)
+    np.testing.assert_array_equal(o4["inds"].cpu().numpy(), i1)
+    np.testing.assert_array_equal(o4["dets"].cpu().numpy(), d1)
+    eng.set_option("use_graph", 1)
+    eng.set_option("host_chunk", 3)
+    hd, hi = eng.run_host(x)
+    np.testing.assert_array_equal(hi, i1)
+    np.testing.assert_array_equal(hd, d1)
+    # a smaller batch through the same engine
+    o5 = eng.run(xt[:3].contiguous(), maps=False)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(o5["dets"].cpu().numpy(), d1[:3])
+    assert eng.num_launches >= 60
+    eng.close()
+
+
+def test_config_c_geometry_large_batch(golden, calib):
+    """BASELINE config c geometry (512^2) at a batch that exceeds L2: replicas must equal the single-image result,
+    which is pinned to the reference vector."""
+    import torch
+    g = golden("codenet1x_512_round.npz")
+    eng = _engine(calib, "round", 512, 64)
+    two = make_images(2, 512, seed=3)
+    x = np.concatenate([two] * 32)
+    out = eng.run(torch.from_numpy(x).cuda(), maps=False)
+    torch.cuda.synchronize()
+    d = out["dets"].cpu().numpy()
+    for b in range(2, 64):
+        np.testing.assert_array_equal(d[b], d[b % 2])
+    np.testing.assert_allclose(np.sort(d[0][:, 4]), np.sort(g["dets"][0][:, 4]), rtol=2e-6)
+    eng.close()
+
+
+def test_errors_are_loud(calib):
+    import torch
+    eng = _engine(calib, "round", 256, 2)
+    with pytest.raises(_lib.CdnError):
+        eng.run(torch.zeros((3, 3, 256, 256), device="cuda"))       # batch above the finalized maximum
+    with pytest.raises(_lib.CdnError):
+        eng.set_option("nonsense", 1)
+    eng.close()

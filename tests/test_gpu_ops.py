@@ -1,0 +1,265 @@
+"""GPU parity tests of the individual kernels, called through the C ABI (run on the B200 box with -m gpu)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import plan_sim
+from codenet_b200 import _lib
+from codenet_b200.arch import NetConfig
+from codenet_b200.plan import build_plan, Plan, Op, TensorSpec
+from codenet_b200.synth import make_quant_state, make_images
+from oracle import int_oracle as io
+from oracle import deform_ref
+from util import int8_mismatch
+
+pytestmark = pytest.mark.gpu
+CFG = NetConfig(num_classes=20)
+
+
+@pytest.fixture(scope="module")
+def sim256(calib):
+    st = make_quant_state(CFG, calib, "round", 256)
+    x = make_images(2, 256, seed=2)
+    plan = build_plan(CFG, st, 256, 256, "round")
+    T, heads = plan_sim.run_plan(plan, x)
+    return plan, x, T, heads
+
+
+@pytest.fixture(autouse=True)
+def _reset_flags():
+    _lib.load().cdn_set_debug_flags(0)
+    yield
+    _lib.load().cdn_set_debug_flags(0)
+
+
+def test_device_is_sm100():
+    _lib.check(_lib.load().cdn_check_device(0))
+
+
+def _check_ops(sim256, kinds, flags=0):
+    from gpu_util import run_op
+    plan, x, T, heads = sim256
+    _lib.load().cdn_set_debug_flags(flags)
+    bad = []
+    n = 0
+    for op in plan.ops:
+        if op.kind not in kinds:
+            continue
+        got = run_op(plan, op, T, images=x)
+        n += 1
+        if op.kind == "pw" and op.a["n_f32"]:
+            if not np.array_equal(got, heads.astype(np.float32)):
+                bad.append((op.name, float(np.abs(got - heads).max())))
+            continue
+        want = T[op.a["out_t"]]
+        mism = int8_mismatch(got, want)
+        if mism:
+            bad.append((op.name, mism, want.size))
+    assert n > 0
+    assert not bad, "ops with mismatching elements: %s" % bad[:12]
+
+
+def test_stem_every_layer(sim256):
+    _check_ops(sim256, ("stem",))
+
+
+def test_depthwise_every_layer(sim256):
+    _check_ops(sim256, ("dw",))
+
+
+def test_deform_every_layer(sim256):
+    _check_ops(sim256, ("deform",))
+
+
+def test_pointwise_simt_every_layer(sim256):
+    _check_ops(sim256, ("pw",), flags=1)
+
+
+def test_pointwise_tcgen05_every_layer(sim256):
+    _check_ops(sim256, ("pw",), flags=0)
+
+
+# ---- randomised shapes -------------------------------------------------------------------------------------------
+def _mini_plan():
+    return Plan(CFG, 0, 0, "round")
+
+
+@pytest.mark.parametrize("C,H,W,stride,shift", [(24, 20, 28, 2, 0), (58, 17, 9, 1, 0), (116, 12, 12, 2, 0), (232, 8, 8, 1, 0),
+                                                (192, 16, 16, 1, 1), (464, 6, 10, 1, 0), (2153, 4, 4, 1, 0)])
+def test_depthwise_random(C, H, W, stride, shift):
+    from gpu_util import run_op
+    rng = np.random.default_rng(C * 7 + stride)
+    P = _mini_plan()
+    pitch = (C + 31) // 32 * 32
+    tin = P.add_tensor(H >> shift, W >> shift, C, pitch)
+    Hl, Wl = tin.H << shift, tin.W << shift
+    tout = P.add_tensor((Hl - 1) // stride + 1, (Wl - 1) // stride + 1, C, pitch)
+    wq = np.zeros((pitch, 9), np.int8); wq[:C] = rng.integers(-8, 8, (C, 9))
+    M = np.zeros(pitch); B = np.zeros(pitch)
+    M[:C] = rng.uniform(0.002, 0.02, C); B[:C] = rng.uniform(-140, -100, C)
+    zx = int(rng.integers(100, 129))
+    op = Op("dw", "t", dict(in_t=0, out_t=1, in_shift=shift, stride=stride, wq=wq, C=pitch, zx=zx, M=M, B=B, lo=-128))
+    P.ops.append(op)
+    x = np.zeros((3, tin.H, tin.W, pitch), np.int64); x[..., :C] = rng.integers(-128, 128, (3, tin.H, tin.W, C))
+    sim = plan_sim.run_plan_seeded(P, {0: x})[0]
+    got = run_op(P, op, {0: x})
+    assert int8_mismatch(got, sim[1]) == 0
+    assert len(np.unique(got)) > 20
+
+
+@pytest.mark.parametrize("C,H,W,bound,shift,mode", [(128, 24, 24, 8, 0, 0), (256, 16, 16, 4, 1, 0), (1024, 8, 8, 8, 0, 0),
+                                                    (58, 20, 12, 3, 0, 0), (24, 32, 32, 2, 0, 0), (464, 8, 8, 1, 0, 0),
+                                                    (128, 12, 12, 8, 0, 1), (256, 8, 8, 4, 1, 1), (1024, 6, 6, 8, 0, 1),
+                                                    (2153, 4, 4, 8, 0, 0)])
+def test_deform_random(C, H, W, bound, shift, mode):
+    """Config-2 style isolated layer: uniform s over the whole bound, int8 inputs, 4-bit weights, both modes."""
+    from gpu_util import run_op
+    rng = np.random.default_rng(C + 13 * bound + mode)
+    P = _mini_plan()
+    pitch = (C + 31) // 32 * 32
+    tin = P.add_tensor(H >> shift, W >> shift, C, pitch)
+    tout = P.add_tensor(H, W, C, pitch)
+    Bn = 2
+    wq = np.zeros((pitch, 9), np.int8); wq[:C] = rng.integers(-8, 8, (C, 9))
+    M = np.zeros(pitch); Bc = np.zeros(pitch)
+    M[:C] = rng.uniform(0.002, 0.01, C); Bc[:C] = rng.uniform(-20, 20, C)
+    zx = 128
+    ws = np.zeros(pitch, np.int8); ws[:C] = rng.integers(-8, 8, C)
+    x = np.zeros((Bn, tin.H, tin.W, pitch), np.int64); x[..., :C] = rng.integers(-128, 128, (Bn, tin.H, tin.W, C))
+    # choose Ms/bs so that u spans a bit more than [-bound+1, bound]
+    acc_s = (x[..., :C] * ws[:C].astype(np.int64)).sum(-1) + zx * int(ws[:C].astype(np.int64).sum())
+    span = max(1.0, float(np.abs(acc_s - acc_s.mean()).max()))
+    Ms = (bound + 1.0) / span
+    bs = 0.5 - Ms * float(acc_s.mean())
+    ss, zs = io.act_params(-bound + 1, bound)
+    a = dict(in_t=0, out_t=1, in_shift=shift, stride=1, wq=wq, C=pitch, zx=zx, M=M, B=Bc, lo=-128,
+             ws=ws, Ms=Ms, bs=bs, ss=float(ss), zs=float(zs), bound=bound, mode=mode)
+    op = Op("deform", "t", a)
+    got, sval = run_op(P, op, {0: x}, sval=True)
+    # oracle (NCHW) on the virtually upsampled input
+    xin = x[..., :C]
+    if shift:
+        xin = np.repeat(np.repeat(xin, 2, axis=1), 2, axis=2)
+    A = (xin + zx).transpose(0, 3, 1, 2)
+    u = acc_s.astype(np.float64) * np.float64(Ms) + np.float64(bs)
+    if shift:
+        u = np.repeat(np.repeat(u, 2, axis=1), 2, axis=2)
+    u = np.clip(u, -bound + 1.0, float(bound))
+    qs = np.rint(ss * u - zs)
+    s = (qs + zs) / ss
+    wq3 = wq[:C].astype(np.int64).reshape(C, 3, 3)
+    if mode == 0:
+        s = np.rint(s)
+        acc = io.deform_dw_int(A, wq3, s)
+        q = np.clip(io.requant(acc, M[:C], Bc[:C], 0, False), -128, 127)
+    else:
+        acc = io.deform_dw_bilinear(A, wq3, s)
+        q = np.clip(io.requant_f(acc, M[:C], Bc[:C], 0, False), -128, 127)
+    np.testing.assert_array_equal(sval, s.astype(np.float32))
+    assert len(np.unique(s)) >= min(4, 2 * bound)
+    assert int8_mismatch(got[..., :C].transpose(0, 3, 1, 2), q) == 0
+    assert not got[..., C:].any()
+
+
+@pytest.mark.parametrize("K,N,relu,flags", [(24, 58, 1, 0), (58, 58, 1, 0), (116, 232, 0, 0), (464, 1024, 1, 0), (1024, 256, 1, 0),
+                                            (64, 192, 1, 0), (200, 64, 0, 0), (58, 58, 1, 1), (464, 1024, 1, 1)])
+def test_pointwise_random_dense(K, N, relu, flags):
+    from gpu_util import run_op
+    _lib.load().cdn_set_debug_flags(flags)
+    rng = np.random.default_rng(K * 31 + N)
+    P = _mini_plan()
+    Kp, Np = (K + 31) // 32 * 32, (N + 31) // 32 * 32
+    H, W, Bn = 9, 15, 3                                                # 405 pixels: a partial last tile
+    tin = P.add_tensor(H, W, K, Kp)
+    tout = P.add_tensor(H, W, N, Np)
+    N16 = (N + 15) // 16 * 16
+    w = np.zeros((N16, Kp), np.int8); w[:N, :K] = rng.integers(-8, 8, (N, K))
+    M = np.zeros(N16); Bc = np.zeros(N16)
+    M[:N] = rng.uniform(0.2, 1.0, N) / np.sqrt(K) / 30; Bc[:N] = rng.uniform(-130, -90, N)
+    chunks = [((16 * j) if N - 16 * j > 0 else 0, int(np.clip(N - 16 * j, 0, 16)), -1, 16 * j) for j in range(Np // 16)]
+    a = dict(in_t=0, out_t=1, pass_t=-1, k_off=0, K=Kp, N=N16, zx=128, wq=w, M=M, B=Bc, lo=-128 if not relu else -128,
+             chunks=np.array(chunks, np.int16), n_f32=0)
+    op = Op("pw", "t", a)
+    P.ops.append(op)
+    x = np.zeros((Bn, H, W, Kp), np.int64); x[..., :K] = rng.integers(-128, 128, (Bn, H, W, K))
+    sim = plan_sim.run_plan_seeded(P, {0: x})[0]
+    got = run_op(P, op, {0: x})
+    assert int8_mismatch(got, sim[1]) == 0
+    assert len(np.unique(got)) > 20
+
+
+def test_general_deform_conv_f32(golden):
+    """cdn_deform_conv_forward_f32 against the vectors of the reference's op (B1 boundary)."""
+    import torch
+    from gpu_util import dev, ptr, stream
+    g = golden("deform_kat.npz")
+    L = _lib.load()
+    for name in ("dw_s1", "dw_s2", "dense", "g2"):
+        x, off, w, y = (g[name + s] for s in ("_x", "_off", "_w", "_y"))
+        st, pad, dil, groups, dg = (int(v) for v in g[name + "_cfg"])
+        Bn, Cc, H, W = x.shape
+        Co = w.shape[0]
+        out = torch.zeros(y.shape, dtype=torch.float32, device="cuda")
+        tx, to, tw = dev(x.astype(np.float32)), dev(off.astype(np.float32)), dev(w.astype(np.float32))
+        _lib.check(L.cdn_deform_conv_forward_f32(ptr(tx), ptr(tw), ptr(to), ptr(out), Bn, Cc, H, W, Co, 3, 3, st, st,
+                                                 pad, pad, dil, dil, groups, dg, 64, stream()))
+        torch.cuda.synchronize()
+        # offsets landing within float rounding of an integer can flip a floor(); compare robustly
+        err = np.abs(out.cpu().numpy() - y)
+        assert np.quantile(err, 0.999) < 1e-4 * max(1.0, np.abs(y).max()), (name, err.max())
+    # error behaviour of shape_check (dcn_deform_conv_cuda.cpp:61-149)
+    assert L.cdn_deform_conv_forward_f32(ptr(tx), ptr(tw), ptr(to), ptr(out), 1, 4, 2, 2, 4, 3, 3, 1, 1, 0, 0, 1, 1, 1, 1, 64, stream()) == -1
+
+
+@pytest.mark.parametrize("name", ["voc", "small"])
+def test_decode_kat_gpu(golden, name):
+    import torch
+    from gpu_util import dev, ptr, stream
+    g = golden("decode_kat.npz")
+    hm = g[name + "_hm"]
+    logit = (np.log(hm.astype(np.float64)) - np.log1p(-hm.astype(np.float64))).astype(np.float32)
+    assert len(np.unique(logit)) == len(np.unique(hm))
+    Bn, cat, H, W = hm.shape
+    K = int(g[name + "_K"])
+    L = _lib.load()
+    for reg, ref in ((g[name + "_reg"], g[name + "_dets"]), (None, g[name + "_dets_noreg"])):
+        dets = torch.zeros((Bn, K, 6), dtype=torch.float32, device="cuda")
+        inds = torch.zeros((Bn, K), dtype=torch.int32, device="cuda")
+        _lib.check(L.cdn_ctdet_decode(ptr(dev(logit)), ptr(dev(g[name + "_wh"])), ptr(dev(reg)) if reg is not None else None,
+                                      Bn, cat, H, W, K, ptr(dets), ptr(inds), stream()))
+        d = dets.cpu().numpy()
+        odets, oinds = io.ctdet_decode(logit.astype(np.float64), g[name + "_wh"].astype(np.float64),
+                                       None if reg is None else reg.astype(np.float64), K)
+        np.testing.assert_array_equal(inds.cpu().numpy(), oinds)                    # bit-exact top-K indices and order
+        np.testing.assert_allclose(d[..., :4], ref[..., :4], rtol=1e-5, atol=1e-4)
+        np.testing.assert_allclose(d[..., 4], ref[..., 4], rtol=2e-6)
+        np.testing.assert_array_equal(d[..., 5], ref[..., 5])
+
+
+@pytest.mark.parametrize("cat,H,W,K,levels", [(20, 64, 64, 100, 37), (80, 32, 48, 100, 500), (3, 16, 16, 40, 5), (1, 8, 8, 100, 3),
+                                              (20, 128, 128, 100, 2000)])
+def test_decode_with_ties(cat, H, W, K, levels):
+    """Quantised heads produce heavy ties; order = (logit desc, class asc, index asc), fewer-than-K peaks -> -1."""
+    import torch
+    from gpu_util import dev, ptr, stream
+    rng = np.random.default_rng(cat + H + levels)
+    Bn = 3
+    logit = (rng.integers(0, levels, (Bn, cat, H, W)) / levels * 8 - 6).astype(np.float32)
+    wh = rng.uniform(1, 10, (Bn, 2, H, W)).astype(np.float32)
+    reg = rng.uniform(0, 1, (Bn, 2, H, W)).astype(np.float32)
+    dets = torch.zeros((Bn, K, 6), dtype=torch.float32, device="cuda")
+    inds = torch.zeros((Bn, K), dtype=torch.int32, device="cuda")
+    _lib.check(_lib.load().cdn_ctdet_decode(ptr(dev(logit)), ptr(dev(wh)), ptr(dev(reg)), Bn, cat, H, W, K, ptr(dets),
+                                            ptr(inds), stream()))
+    got = inds.cpu().numpy()
+    for b in range(Bn):
+        p = np.full((cat, H + 2, W + 2), -np.inf, np.float32); p[:, 1:-1, 1:-1] = logit[b]
+        mx = np.max([p[:, i:i + H, j:j + W] for i in range(3) for j in range(3)], axis=0)
+        flat = np.where(mx == logit[b], logit[b], -np.inf).reshape(-1)
+        order = np.lexsort((np.arange(flat.size), -flat))
+        npk = int(np.isfinite(flat).sum())
+        want = np.full(K, -1, np.int64); want[:min(K, npk)] = order[:min(K, npk)]
+        np.testing.assert_array_equal(got[b], want)
+    d = dets.cpu().numpy()
+    assert np.all(d[got < 0] == 0)

@@ -1,0 +1,108 @@
+"""The oracle is only trusted after it reproduces vectors made by the UNMODIFIED reference (oracle/make_golden.py)."""
+import numpy as np
+import pytest
+
+from codenet_b200.arch import NetConfig
+from codenet_b200.synth import make_quant_state, make_images
+from oracle import int_oracle as io
+from oracle import deform_ref
+from util import assert_dets_match_tie_aware, int8_mismatch
+
+CFG = NetConfig(num_classes=20)
+
+
+def test_activation_quant_kat(golden):
+    g = golden("quant_kat.npz")
+    for i in range(3):
+        lo, hi = g["act%d_range" % i]
+        s, z = io.act_params(lo, hi)
+        q = np.rint(s * g["act%d_x" % i] - z)
+        np.testing.assert_array_equal((q + z) / s, g["act%d_y" % i])
+    # stateful init of QuantAct = batch min/max (quant_modules.py:209-212)
+    assert g["qact_min"][0] == g["qact_x"].min() and g["qact_max"][0] == g["qact_x"].max()
+    s, z = io.act_params(g["qact_min"][0], g["qact_max"][0])
+    np.testing.assert_array_equal((np.rint(s * g["qact_x"] - z) + z) / s, g["qact_y"])
+
+
+@pytest.mark.parametrize("bits", [4, 8])
+def test_weight_quant_kat(golden, bits):
+    g = golden("quant_kat.npz")
+    wq, sigma = io.quant_weight(g["w%d_x" % bits], bits)
+    np.testing.assert_array_equal(wq / sigma.reshape(-1, 1, 1, 1), g["w%d_y" % bits])
+    assert wq.min() >= -(2 ** (bits - 1)) and wq.max() <= 2 ** (bits - 1) - 1
+
+
+def test_bn_fold_conv_kat(golden):
+    g = golden("quant_kat.npz")
+    w, b = io.fold_bn(g["bnconv_w"], g["bnconv_gamma"], g["bnconv_beta"], g["bnconv_mean"], g["bnconv_var"],
+                      float(g["bnconv_eps"]))
+    wq, sigma = io.quant_weight(w, 4)
+    y = np.einsum("oc,bchw->bohw", (wq / sigma.reshape(-1, 1, 1, 1)).reshape(7, 5), g["bnconv_x"]) + b.reshape(1, -1, 1, 1)
+    np.testing.assert_allclose(y, g["bnconv_y"], rtol=1e-13, atol=1e-13)
+
+
+@pytest.mark.parametrize("name", ["dw_s1", "dw_s2", "dense", "g2"])
+def test_deform_op_kat(golden, name):
+    g = golden("deform_kat.npz")
+    st, pad, dil, groups, dg = g[name + "_cfg"]
+    y = deform_ref.deform_conv(g[name + "_x"], g[name + "_off"], g[name + "_w"], st, pad, dil, groups, dg)
+    np.testing.assert_allclose(y, g[name + "_y"], rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["mod_same", "mod_chan", "mod_s2"])
+def test_codesigned_module_kat(golden, name):
+    g = golden("deform_kat.npz")
+    st, bound = g[name + "_cfg"]
+    wc = g[name + "_wc"] if name + "_wc" in g.files else None
+    y = deform_ref.codesigned_module(g[name + "_x"], g[name + "_ws"], g[name + "_bs"], g[name + "_w"], int(st), int(bound), wc)
+    np.testing.assert_allclose(y, g[name + "_y"], rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["voc", "small"])
+def test_decode_kat(golden, name):
+    g = golden("decode_kat.npz")
+    hm = g[name + "_hm"].astype(np.float64)
+    logit = np.log(hm) - np.log1p(-hm)                   # any monotone map gives the same peaks and order
+    K = int(g[name + "_K"])
+    for reg, ref in ((g[name + "_reg"], g[name + "_dets"]), (None, g[name + "_dets_noreg"])):
+        dets, inds = io.ctdet_decode(logit, g[name + "_wh"].astype(np.float64), None if reg is None else reg.astype(np.float64), K)
+        dets[..., 4] = np.take_along_axis(hm.reshape(hm.shape[0], -1), inds, 1)
+        np.testing.assert_allclose(dets, ref, rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("mode", ["round", "bilinear"])
+def test_int_oracle_reproduces_reference_fp64(golden, calib, mode):
+    """Every int8 grid the reference produced in fp64 is reproduced bit for bit; head outputs to 1e-12."""
+    g = golden("codenet1x_256_%s.npz" % mode)
+    st = make_quant_state(CFG, calib, mode, 256)
+    o = io.IntOracle(CFG, st, mode)
+    out = o.forward(make_images(2, 256, seed=2))
+    assert o.saturated == 0
+    checked = 0
+    for k in g.files:
+        if g[k].dtype == np.int8:
+            assert int8_mismatch(o.cap[k], g[k]) == 0, k
+            checked += 1
+    assert checked >= 10
+    for i in range(3):
+        np.testing.assert_allclose(o.cap["up%d.sval" % i], g["up%d.sval" % i], rtol=0, atol=1e-12)
+    for n, k in (("hm", "hm_logit"), ("wh", "wh"), ("reg", "reg")):
+        np.testing.assert_allclose(out[n], g[k], rtol=1e-12, atol=1e-12)
+    dets, _ = io.ctdet_decode(out["hm"], out["wh"], out["reg"], 100)
+    more, _ = io.ctdet_decode(out["hm"], out["wh"], out["reg"], 160)
+    for b in range(2):
+        assert_dets_match_tie_aware(g["dets"][b], dets[b], more[b])
+
+
+def test_int_oracle_512(golden, calib):
+    g = golden("codenet1x_512_round.npz")
+    st = make_quant_state(CFG, calib, "round", 512)
+    o = io.IntOracle(CFG, st, "round")
+    out = o.forward(make_images(2, 512, seed=3)[:1])
+    assert int8_mismatch(o.cap["stem"][:, :, ::4, ::4], g["stem"]) == 0
+    assert int8_mismatch(o.cap["up2.out"][:, :, ::4, ::4], g["up2.out"]) == 0
+    for n, k in (("hm", "hm_logit_s8"), ("wh", "wh_s8"), ("reg", "reg_s8")):
+        np.testing.assert_allclose(out[n][:, :, ::8, ::8], g[k], rtol=1e-12, atol=1e-12)
+    dets, _ = io.ctdet_decode(out["hm"], out["wh"], out["reg"], 100)
+    more, _ = io.ctdet_decode(out["hm"], out["wh"], out["reg"], 160)
+    assert_dets_match_tie_aware(g["dets"][0], dets[0], more[0])

@@ -1,0 +1,96 @@
+"""Host logic without a GPU: the plan compiler against the oracle, and the C-ABI surface."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import plan_sim
+from codenet_b200 import _lib
+from codenet_b200.arch import NetConfig, build_graph, raw_param_shapes, raw_to_quant_key, act_keys
+from codenet_b200.plan import build_plan
+from codenet_b200.synth import make_quant_state, make_images, make_raw_state, state_digest
+from oracle import int_oracle as io
+from util import int8_mismatch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CFG = NetConfig(num_classes=20)
+
+
+def test_synthetic_weights_match_calibration_archive(calib):
+    assert state_digest(make_raw_state(CFG, 0)) == str(calib["digest"])
+
+
+def test_key_spaces_are_consistent():
+    g = build_graph(CFG)
+    raw = raw_param_shapes(g)
+    r2q = raw_to_quant_key(g)
+    assert set(raw) == set(r2q) and len(set(r2q.values())) == len(r2q)
+    assert len(act_keys(g)) == 1 + 16 * 2 + 3 + 3 + 1 + 9 + 6          # stem, units, act4 x3, shared x3, layer4, ups, heads
+    # CoDeNet1x parameter count, SURVEY.md section 6: 1.588 M
+    n = sum(int(np.prod(s)) for k, s in raw.items() if "running" not in k)
+    assert abs(n - 1.588e6) < 0.01e6
+
+
+@pytest.mark.parametrize("res", [256])
+def test_plan_descriptors_reproduce_oracle(calib, res):
+    """Interpreting the descriptors handed to the kernels (chunk tables = split/cat/shuffle, HALF layout, virtual
+    upsampling, 1x1-before-upsample, fused heads) with integer arithmetic gives the oracle's grids exactly."""
+    st = make_quant_state(CFG, calib, "round", res)
+    x = make_images(2, res, seed=2)
+    plan = build_plan(CFG, st, res, res, "round")
+    o = io.IntOracle(CFG, st, "round")
+    out = o.forward(x)
+    T, heads = plan_sim.run_plan(plan, x)
+    n = 0
+    for lbl in plan.taps:
+        if lbl in o.cap:
+            assert int8_mismatch(plan_sim.logical(plan, T, lbl), o.cap[lbl]) == 0, lbl
+            n += 1
+    assert n >= 40
+    np.testing.assert_array_equal(heads, np.concatenate([out["hm"], out["wh"], out["reg"]], 1))
+
+
+def test_plan_shapes_config_c(calib):
+    st = make_quant_state(CFG, calib, "round", 512)
+    plan = build_plan(CFG, st, 512, 512, "round")
+    kinds = [op.kind for op in plan.ops]
+    assert kinds.count("deform") == 3 and kinds.count("stem") == 1 and kinds.count("pw") == 41 and kinds.count("dw") == 20
+    assert (plan.out_H, plan.out_W, plan.cat) == (128, 128, 20)
+    # the three deformable layers of SURVEY.md F2: C=1024@16, 256@32, 128@64
+    d = [(op.a["C"], plan.tensors[op.a["out_t"]].H) for op in plan.ops if op.kind == "deform"]
+    assert d == [(1024, 16), (256, 32), (128, 64)]
+    for t in plan.tensors:
+        assert t.pitch % 32 == 0
+
+
+def test_plan_rejects_bad_input():
+    with pytest.raises(ValueError):
+        build_plan(CFG, {}, 250, 256)
+    with pytest.raises(ValueError):
+        build_plan(CFG, {}, 256, 256, "nearest")
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    hdr = open(os.path.join(ROOT, "include", "codenet_b200.h")).read()
+    declared = set(re.findall(r"\b(cdn_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"cdn_stream_t"}
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(lib, name), "symbol %s declared in include/codenet_b200.h is not exported" % name
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    assert lib.cdn_version() >= 100
+
+
+def test_no_cpu_fallback():
+    """Without a GPU the product path must fail loudly, never compute on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = _lib.load()
+    assert lib.cdn_check_device(0) == -3
+    assert b"no CPU fallback" in lib.cdn_last_error()
+    import ctypes as C
+    h = C.c_void_p()
+    assert lib.cdn_engine_create(C.byref(h), 0) == -3
