@@ -186,6 +186,12 @@ def run_ours(args):
         pr = eng.profile(dev)
         acc = [x[2] for x in pr] if acc is None else [a + x[2] for a, x in zip(acc, pr)]
     per_op = [a / prof_runs for a in acc]
+    if args.dump_ops:
+        rows = [{"op": o.name, "kind": o.kind, "ms": round(m, 4), "MB": round(op_bytes(eng.plan, o, B) / 1e6, 1),
+                 "GBps": round(op_bytes(eng.plan, o, B) / m / 1e6, 1)} for o, m in zip(eng.plan.ops, per_op)]
+        rows.append({"op": "ctdet_decode", "kind": "decode", "ms": round(per_op[-1], 4)})
+        with open(args.dump_ops, "w") as f:
+            json.dump(rows, f, indent=1)
     fam_ms, fam_bytes, deform_layers = {}, {}, []
     for op, msop in zip(eng.plan.ops, per_op):
         f = family(op)
@@ -286,6 +292,7 @@ def main():
     ap.add_argument("--offset-mode", default="round", choices=["round", "bilinear"])
     ap.add_argument("--micro-batch", type=int, default=0)
     ap.add_argument("--host-chunk", type=int, default=32)
+    ap.add_argument("--dump-ops", default="", help="write the per-op device times (JSON) to this file")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
