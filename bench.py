@@ -215,7 +215,7 @@ def run_ours(args):
     dby = sum(op_bytes(eng.plan, op, B) for op in eng.plan.ops if op.kind == "deform")
     deform = {"GBps": round(dby / fam_ms["deform_dw_kernel"] / 1e6, 1), "frac_of_hbm_peak": round(dby / fam_ms["deform_dw_kernel"] / 1e6 / peak, 4),
               "layers": deform_layers}
-    cpu = cpu_baseline(args, sample_images=1)
+    cpu = None if args.no_cpu else cpu_baseline(args, sample_images=1)
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
@@ -292,6 +292,7 @@ def main():
     ap.add_argument("--offset-mode", default="round", choices=["round", "bilinear"])
     ap.add_argument("--micro-batch", type=int, default=0)
     ap.add_argument("--host-chunk", type=int, default=32)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs only)")
     ap.add_argument("--dump-ops", default="", help="write the per-op device times (JSON) to this file")
     args = ap.parse_args()
     if args.impl == "reference":

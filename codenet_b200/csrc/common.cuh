@@ -46,6 +46,7 @@ static inline RqFast rq_fast_from(double M, double B) {
   return r;
 }
 
+#define CDN_MAGIC_I_HOST 0x4B400000
 #ifdef __CUDACC__
 #define CDN_MAGIC_F 12582912.0f              // 1.5 * 2^23
 #define CDN_MAGIC_I 0x4B400000

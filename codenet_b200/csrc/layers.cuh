@@ -23,10 +23,11 @@ int stem_launch(const StemDevice& d, const float* img, int batch, int H, int W, 
 
 struct PwDevice {
   int K = 0, k_off = 0, N = 0, Kp = 0, BN = 0, n_tiles = 0, num_k_blocks = 0, stages = 0;
-  int has_pass = 0, pass_segs = 0, max_segs = 0, n_chunks = 0, n_f32 = 0;
+  int has_pass = 0, pass_segs = 0, nbuf = 0, resident = 0, n_chunks = 0, n_segs = 0, n_f32 = 0;
+  float thr = 0.5f;                          // layer-wide rounding-boundary guard (min over columns)
   size_t smem_bytes = 0;
   int8_t* w = nullptr;                       // [BN*n_tiles][Kp]
-  cdn_pw_chunk* chunks = nullptr; int* chunk_begin = nullptr; int* seg_begin = nullptr;
+  cdn_pw_chunk* chunks = nullptr; void* segs = nullptr; int* tile_seg = nullptr; void* kc = nullptr;
   double* Mf = nullptr; double* bf = nullptr;
   DevRequant rq;
   CUtensorMap tmB;

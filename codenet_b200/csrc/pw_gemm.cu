@@ -1,14 +1,20 @@
 // 1x1 convolutions as int8 tcgen05 GEMMs (sm_100a): D[pixel][n] = sum_k A[pixel][k] * W[n][k], s8 x s8 -> s32 in TMEM.
 //
-//   * persistent, warp-specialised CTA (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner),
-//     warps 2..5 = epilogue (each owns the 32 TMEM lanes of its quarter)
-//   * A (activations, NHWC rows = pixels) and W (weights, K-major) arrive by TMA as [rows x 128 B] boxes with the
-//     128-byte swizzle, 128 bytes of K per stage; UMMA 128 x BN x 32, four per stage; accumulators double-buffered
-//     in TMEM (2 x BN columns) so the epilogue of tile i overlaps the main loop of tile i+1
-//   * epilogue: tcgen05.ld -> exact requantisation (common.cuh) -> bytes are placed by the layer's chunk table
-//     (plain / interleaved with a pass-through tensor = split + cat + channel_shuffle) into a swizzled staging tile
-//     -> TMA store.  Head convs instead write fp32 NCHW planes.
-//   * a SIMT dp4a kernel with identical semantics exists for bring-up and as an on-device cross-check
+// These GEMMs are HBM-bound (K, N = 24..1024, M = millions of pixels): the kernel is built around the byte stream,
+// not around the tensor pipe.
+//   * persistent, warp-specialised CTA (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner),
+//     warps 2..9 = epilogue (two warps per TMEM lane quarter, splitting the column chunks between them)
+//   * weights stay RESIDENT in shared memory for the whole kernel whenever [N x K] fits (all but two layers); the
+//     activation tiles (128 pixels x 128 B of K) stream through a ring of up to 8 TMA stages, so several tiles are
+//     in flight per SM; accumulators are double-buffered in TMEM (2 x BN columns): the epilogue of tile i overlaps
+//     the loads and MMAs of tiles i+1..
+//   * epilogue (the issue-bound part): tcgen05.ld -> branch-free fp32 requantisation with a rounding-boundary guard
+//     (exact fp64 re-evaluation of a 16-column group only when some lane is within eps of a boundary, ~1e-4 of the
+//     elements) -> bytes placed by the layer's chunk table (plain / interleaved with the pass-through half = split +
+//     cat + channel_shuffle) into a swizzled staging segment -> one TMA store per 128-byte output segment, staging
+//     double/triple buffered.  Per-column constants live in shared memory as one 16-byte record.
+//     Head convs instead write fp32 NCHW planes (fp64 epilogue, 24 columns).
+//   * a SIMT kernel with identical semantics exists for bring-up and as an on-device cross-check
 //     (cdn_set_debug_flags bit 0); it is not a fallback: nothing selects it automatically.
 #include "layers.cuh"
 #include <algorithm>
@@ -16,16 +22,23 @@
 #define PW_BM 128
 #define PW_BK 128
 #define PW_MAX_BN 256
-#define PW_THREADS 192
+#define PW_EPI_WARPS 8
+#define PW_EPI_THREADS (32 * PW_EPI_WARPS)
+#define PW_THREADS (64 + PW_EPI_THREADS)
+#define PW_MAX_STAGES 8
 #define PW_SPIN_LIMIT (1u << 26)
+#define PW_SMEM_LIMIT (227 * 1024)
+
+struct PwSeg { int seg, cb, ce, pad; };       // output segment (128-byte column of the out tensor) and its chunk range
 
 struct PwParams {
-  int num_k_blocks, k_off, BN, n_tiles, stages, has_pass, pass_segs, max_segs;
+  int num_k_blocks, k_off, BN, n_tiles, stages, has_pass, pass_segs, nbuf, resident, n_chunks, n_segs;
   long long m_tiles, pixels;
-  const cdn_pw_chunk* chunks; const int* chunk_begin;  // chunk_begin[n_tiles + 1]
-  const int* seg_begin;                                // [2*t] first 128-byte output segment of N tile t, [2*t+1] count
-  const float* Mh; const float* Bh; const float* thr; const double* M; const double* B; const int32_t* acc_bias;
-  float lo_f;
+  const cdn_pw_chunk* chunks;                // sorted by (N tile, output segment)
+  const PwSeg* segs; const int* tile_seg;    // tile_seg[n_tiles + 1]: first PwSeg of every N tile
+  const float4* kc;                          // per GEMM column {Mh, Bh, bits(acc_bias + MAGIC_I), 0}
+  const double* M; const double* B; const int32_t* acc_bias;
+  float lo_f, thr;
   // fp32 head output
   int n_f32, ppi; float* out_f32; const double* Mf; const double* bf;
   // SIMT cross-check path
@@ -65,7 +78,8 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int
                ::"l"(map), "r"(c0), "r"(c1), "r"(src) : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -104,35 +118,73 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[16]) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------------------
-// shared epilogue math: 16 (or 8 interleaved) output bytes of one chunk from accumulators
+// epilogue math
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t rq_col(const PwParams& p, int acc, int n) {
-  return requant_bits(acc + __ldg(p.acc_bias + n), __ldg(p.Mh + n), __ldg(p.Bh + n), __ldg(p.thr + n), p.lo_f, p.M, p.B, n);
+// NCOL accumulators -> NCOL "magic" floats whose low byte is the int8 result.  `kc` points at the per-column
+// records {Mh, Bh, bits(acc_bias + MAGIC_I), -} of the first column (shared memory in the tcgen05 kernel).
+// Returns true when some column of this lane came within eps of a rounding boundary (fp32 not trustworthy).
+template <int NCOL>
+__device__ __forceinline__ bool requant_cols_fast(const uint32_t (&acc)[16], const float4* __restrict__ kc, float lo_f,
+                                                  float thr, uint32_t (&rb)[16]) {
+  bool bad = false;
+#pragma unroll
+  for (int i = 0; i < NCOL; ++i) {
+    const float4 k = kc[i];
+    // (acc + acc_bias) is an integer of magnitude < 2^22, so MAGIC_I + it is the float 1.5*2^23 + it, exactly
+    const float f = __fadd_rn(__int_as_float((int)acc[i] + __float_as_int(k.z)), -CDN_MAGIC_F);
+    float t = __fmaf_rn(f, k.x, k.y);
+    t = fminf(fmaxf(t, lo_f), 127.0f);
+    const float r = __fadd_rn(t, CDN_MAGIC_F);
+    const float kk = __fadd_rn(r, -CDN_MAGIC_F);
+    bad |= fabsf(__fadd_rn(t, -kk)) > thr;
+    rb[i] = __float_as_uint(r);
+  }
+  return bad;
 }
 
-// acc[0..count) -> out words; passb: 8 pass-through bytes packed in two words (interleave mode)
-__device__ __forceinline__ uint4 chunk_bytes(const PwParams& p, const cdn_pw_chunk& ck, const uint32_t (&acc)[16],
+// exact fp64 re-evaluation of the same NCOL columns (rare)
+template <int NCOL>
+__device__ __forceinline__ void requant_cols_exact(const uint32_t (&acc)[16], const float4* __restrict__ kc, int col,
+                                                const double* __restrict__ Md, const double* __restrict__ Bd, float lo_f,
+                                                uint32_t (&rb)[16]) {
+#pragma unroll
+  for (int i = 0; i < NCOL; ++i) {
+    const int a = (int)acc[i] + (__float_as_int(kc[i].z) - CDN_MAGIC_I);
+    double td = __dadd_rn(__dmul_rn((double)a, __ldg(Md + col + i)), __ldg(Bd + col + i));
+    td = fmin(fmax(td, (double)lo_f), 127.0);
+    rb[i] = __float_as_uint((float)__double2int_rn(td) + CDN_MAGIC_F);
+  }
+}
+
+// keep the first nb bytes of a 16-byte vector, zero the rest
+__device__ __forceinline__ uint32_t mask_word(uint32_t w, int rem) {
+  return rem >= 4 ? w : (rem <= 0 ? 0u : (w & (0xffffffffu >> (8 * (4 - rem)))));
+}
+__device__ __forceinline__ uint4 mask_tail(uint4 o, int nb) {
+  return make_uint4(mask_word(o.x, nb), mask_word(o.y, nb - 4), mask_word(o.z, nb - 8), mask_word(o.w, nb - 12));
+}
+
+// 16 output bytes of one chunk.  acc: raw accumulators of the chunk's columns; pass_lo/hi: 8 pass-through bytes.
+__device__ __forceinline__ uint4 chunk_bytes(const cdn_pw_chunk& ck, const uint32_t (&acc)[16], const float4* __restrict__ kc,
+                                             const double* __restrict__ Md, const double* __restrict__ Bd, float lo_f, float thr,
                                              uint32_t pass_lo, uint32_t pass_hi) {
   uint32_t q[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) q[i] = (i < ck.count) ? rq_col(p, (int)acc[i], ck.col + i) : 0u;
   uint4 o;
   if (ck.pass_off < 0) {
+    if (ck.count == 0) return make_uint4(0u, 0u, 0u, 0u);
+    const bool bad = requant_cols_fast<16>(acc, kc + ck.col, lo_f, thr, q);
+    if (__any_sync(__activemask(), bad)) { if (bad) requant_cols_exact<16>(acc, kc + ck.col, ck.col, Md, Bd, lo_f, q); }
     o.x = pack4_lowbytes(q[0], q[1], q[2], q[3]);   o.y = pack4_lowbytes(q[4], q[5], q[6], q[7]);
     o.z = pack4_lowbytes(q[8], q[9], q[10], q[11]); o.w = pack4_lowbytes(q[12], q[13], q[14], q[15]);
+    if (ck.count < 16) o = mask_tail(o, ck.count);   // pad bytes of the pixel stay zero
   } else {
-    uint32_t n_lo = pack4_lowbytes(q[0], q[1], q[2], q[3]), n_hi = pack4_lowbytes(q[4], q[5], q[6], q[7]);
+    const bool bad = requant_cols_fast<8>(acc, kc + ck.col, lo_f, thr, q);
+    if (__any_sync(__activemask(), bad)) { if (bad) requant_cols_exact<8>(acc, kc + ck.col, ck.col, Md, Bd, lo_f, q); }
+    const uint32_t n_lo = pack4_lowbytes(q[0], q[1], q[2], q[3]), n_hi = pack4_lowbytes(q[4], q[5], q[6], q[7]);
     // out[2i] = pass[i], out[2i+1] = new[i]
     o.x = __byte_perm(pass_lo, n_lo, 0x5140); o.y = __byte_perm(pass_lo, n_lo, 0x7362);
     o.z = __byte_perm(pass_hi, n_hi, 0x5140); o.w = __byte_perm(pass_hi, n_hi, 0x7362);
-    // zero the tail beyond 2*count bytes
-    int nb = 2 * ck.count;
-    uint32_t* ow = &o.x;
-#pragma unroll
-    for (int wd = 0; wd < 4; ++wd) {
-      int rem = nb - 4 * wd;
-      ow[wd] = rem >= 4 ? ow[wd] : (rem <= 0 ? 0u : (ow[wd] & (0xffffffffu >> (8 * (4 - rem)))));
-    }
+    if (ck.count < 8) o = mask_tail(o, 2 * ck.count);
   }
   return o;
 }
@@ -140,41 +192,62 @@ __device__ __forceinline__ uint4 chunk_bytes(const PwParams& p, const cdn_pw_chu
 // ---------------------------------------------------------------------------------------------------------
 // tcgen05 kernel
 // ---------------------------------------------------------------------------------------------------------
+// Shared memory carve (host mirrors this in pw_device_build):
+//   [B resident: num_k_blocks x Ntot x 128 B]  (resident only)
+//   [ring: stages x (A 16 KB [+ B block BN x 128 B rounded to 1 KB when streamed])]
+//   [pass: 2 x pass_segs x 16 KB] [staging: nbuf x 16 KB] [kc: Ntot x 16 B] [chunks] [segs] [tile_seg] [barriers]
 __global__ void __launch_bounds__(PW_THREADS, 1)
 pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmO,
                   const PwParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [stages x (A 16 KB | B BN*128)] [pass: pass_segs x 16 KB] [out staging: max_segs x 16 KB] [barriers]
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  const uint32_t a_bytes = PW_BM * PW_BK, b_bytes = (uint32_t)p.BN * PW_BK;
-  const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023u);
-  uint8_t* s_pass = smem + (size_t)p.stages * stage_bytes;
-  uint8_t* s_out = s_pass + (size_t)p.pass_segs * 16384;
-  uint64_t* bars = (uint64_t*)(s_out + (size_t)p.max_segs * 16384);
-  // barrier slots: full[8], empty[8], tmem_full[2], tmem_empty[2], pass_full, pass_empty, tmem_ptr
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
+  const int Ntot = p.BN * p.n_tiles;
+  const uint32_t a_bytes = PW_BM * PW_BK, b_blk = ((uint32_t)p.BN * PW_BK + 1023) & ~1023u;
+  const uint32_t stage_bytes = a_bytes + (p.resident ? 0u : b_blk);
+  uint8_t* s_B = smem;
+  uint8_t* s_ring = s_B + (p.resident ? (size_t)p.num_k_blocks * Ntot * PW_BK : 0);
+  uint8_t* s_pass = s_ring + (size_t)p.stages * stage_bytes;
+  uint8_t* s_out = s_pass + (size_t)2 * p.pass_segs * 16384;
+  float4* s_kc = (float4*)(s_out + (size_t)p.nbuf * 16384);
+  cdn_pw_chunk* s_chunks = (cdn_pw_chunk*)(s_kc + Ntot);
+  PwSeg* s_segs = (PwSeg*)(s_chunks + ((p.n_chunks + 1) & ~1));
+  int* s_tile_seg = (int*)(s_segs + p.n_segs);
+  uint64_t* bars = (uint64_t*)(s_tile_seg + ((p.n_tiles + 1 + 3) & ~3));
+  // barrier slots: full[8], empty[8], tmem_full[2], tmem_empty[2], pass_full[2], pass_empty[2], b_full, tmem_ptr
   const uint32_t bar_base = smem_u32(bars);
   auto FULL = [&](int s) { return bar_base + 8u * s; };
   auto EMPTY = [&](int s) { return bar_base + 8u * (8 + s); };
   auto TFULL = [&](int s) { return bar_base + 8u * (16 + s); };
   auto TEMPTY = [&](int s) { return bar_base + 8u * (18 + s); };
-  const uint32_t PFULL = bar_base + 8u * 20, PEMPTY = bar_base + 8u * 21;
-  volatile uint32_t* tmem_slot = (volatile uint32_t*)(bars + 22);
+  auto PFULL = [&](int s) { return bar_base + 8u * (20 + s); };
+  auto PEMPTY = [&](int s) { return bar_base + 8u * (22 + s); };
+  const uint32_t BFULL = bar_base + 8u * 24;
+  volatile uint32_t* tmem_slot = (volatile uint32_t*)(bars + 25);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(TFULL(s), 1); mbar_init(TEMPTY(s), 128); }
-    mbar_init(PFULL, 1); mbar_init(PEMPTY, 128);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(TFULL(s), 1); mbar_init(TEMPTY(s), PW_EPI_THREADS);
+      mbar_init(PFULL(s), 1); mbar_init(PEMPTY(s), PW_EPI_THREADS);
+    }
+    mbar_init(BFULL, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmO) : "memory");
   }
   if (warp == 1) {                           // TMEM: the whole 512 columns (1 CTA per SM)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
+  // per-column constants and the chunk / segment tables -> shared memory
+  for (int i = threadIdx.x; i < Ntot; i += PW_THREADS) s_kc[i] = p.kc[i];
+  for (int i = threadIdx.x; i < p.n_chunks; i += PW_THREADS) s_chunks[i] = p.chunks[i];
+  for (int i = threadIdx.x; i < p.n_segs; i += PW_THREADS) s_segs[i] = p.segs[i];
+  for (int i = threadIdx.x; i <= p.n_tiles; i += PW_THREADS) s_tile_seg[i] = p.tile_seg[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -185,22 +258,33 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      int stage = 0; uint32_t phase = 0, pphase = 0;
-      for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      if (p.resident) {
+        mbar_expect_tx(BFULL, (uint32_t)p.num_k_blocks * (uint32_t)Ntot * PW_BK);
+        for (int kb = 0; kb < p.num_k_blocks; ++kb)
+          for (int nt = 0; nt < p.n_tiles; ++nt)
+            tma_load_2d(smem_u32(s_B + ((size_t)kb * Ntot + (size_t)nt * p.BN) * PW_BK), &tmB, kb * PW_BK, nt * p.BN, BFULL);
+      }
+      int stage = 0; uint32_t phase = 0; uint32_t it = 0;
+      for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const long long mt = tile / p.n_tiles; const int nt = (int)(tile % p.n_tiles);
         if (p.has_pass) {
-          mbar_wait(PEMPTY, pphase ^ 1);
-          mbar_expect_tx(PFULL, (uint32_t)p.pass_segs * 16384u);
+          const int pb = it & 1; const uint32_t pph = (it >> 1) & 1;
+          mbar_wait(PEMPTY(pb), pph ^ 1);
+          mbar_expect_tx(PFULL(pb), (uint32_t)p.pass_segs * 16384u);
           for (int s = 0; s < p.pass_segs; ++s)
-            tma_load_2d(smem_u32(s_pass + (size_t)s * 16384), &tmP, s * 128, (int)(mt * PW_BM), PFULL);
-          pphase ^= 1;
+            tma_load_2d(smem_u32(s_pass + ((size_t)pb * p.pass_segs + s) * 16384), &tmP, s * 128, (int)(mt * PW_BM), PFULL(pb));
         }
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(EMPTY(stage), phase ^ 1);
-          mbar_expect_tx(FULL(stage), a_bytes + b_bytes);
-          uint8_t* sa = smem + (size_t)stage * stage_bytes;
-          tma_load_2d(smem_u32(sa), &tmA, p.k_off + kb * PW_BK, (int)(mt * PW_BM), FULL(stage));
-          tma_load_2d(smem_u32(sa + a_bytes), &tmB, kb * PW_BK, nt * p.BN, FULL(stage));
+          uint8_t* sa = s_ring + (size_t)stage * stage_bytes;
+          if (p.resident) {
+            mbar_expect_tx(FULL(stage), a_bytes);
+            tma_load_2d(smem_u32(sa), &tmA, p.k_off + kb * PW_BK, (int)(mt * PW_BM), FULL(stage));
+          } else {
+            mbar_expect_tx(FULL(stage), a_bytes + (uint32_t)p.BN * PW_BK);
+            tma_load_2d(smem_u32(sa), &tmA, p.k_off + kb * PW_BK, (int)(mt * PW_BM), FULL(stage));
+            tma_load_2d(smem_u32(sa + a_bytes), &tmB, kb * PW_BK, nt * p.BN, FULL(stage));
+          }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -210,16 +294,20 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (lane == 0) {
       // instruction descriptor: S32 accumulate, A/B signed int8, K-major both, N = BN, M = 128
       const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(PW_BM >> 4) << 24);
-      int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
-      for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      if (p.resident) { mbar_wait(BFULL, 0); tc_fence_after(); }
+      int stage = 0; uint32_t phase = 0; uint32_t it = 0;
+      for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int nt = (int)(tile % p.n_tiles);
+        const int as = it & 1; const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(TEMPTY(as), aphase ^ 1);
         tc_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(as * PW_MAX_BN);
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(FULL(stage), phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-          const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sa + a_bytes);
+          const uint32_t sa = smem_u32(s_ring + (size_t)stage * stage_bytes);
+          const uint32_t sb = p.resident ? smem_u32(s_B + ((size_t)kb * Ntot + (size_t)nt * p.BN) * PW_BK) : sa + a_bytes;
+          const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sb);
 #pragma unroll
           for (int k = 0; k < PW_BK / 32; ++k)
             umma_i8(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
@@ -227,37 +315,37 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
         umma_commit(TFULL(as));                // accumulator complete
-        if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;          // which of the two warps of the quarter
     const int row = q * 32 + lane;             // row inside the tile
-    const int et = threadIdx.x - 64;           // 0..127
-    int as = 0; uint32_t aphase = 0, pphase = 0;
-    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int et = threadIdx.x - 64;           // 0..255
+    uint32_t it = 0, g = 0;                    // tiles / output segments done by this CTA
+    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const long long mt = tile / p.n_tiles; const int nt = (int)(tile % p.n_tiles);
+      const int as = it & 1; const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(TFULL(as), aphase);
       tc_fence_after();
-      if (p.has_pass) mbar_wait(PFULL, pphase);
+      if (p.has_pass) mbar_wait(PFULL(as), aphase);
       const uint32_t tacc = tmem_base + (uint32_t)(as * PW_MAX_BN) + ((uint32_t)(q * 32) << 16);
-      const int c_begin = p.chunk_begin[nt], c_end = p.chunk_begin[nt + 1];
-      const int seg0 = p.seg_begin[2 * nt], nseg = p.seg_begin[2 * nt + 1];
       if (p.n_f32 > 0) {
-        // fp32 NCHW planes: out[img][n][pix] = acc*Mf[n] + bf[n]
+        // fp32 NCHW planes: out[img][n][pix] = fl32(fl64(acc*Mf[n]) + bf[n])
         const long long pix = mt * PW_BM + row;
         const long long img = pix / p.ppi; const int pi = (int)(pix - img * p.ppi);
-        for (int c0 = 0; c0 < p.BN; c0 += 16) {
+        for (int c0 = half * 16; c0 < p.BN; c0 += 32) {
           uint32_t acc[16];
           tmem_ld16(tacc + (uint32_t)c0, acc);
           tmem_ld_wait();
           if (pix < p.pixels) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              int n = nt * p.BN + c0 + i;
+              const int n = nt * p.BN + c0 + i;
               if (n < p.n_f32) {
-                double y = __dadd_rn(__dmul_rn((double)((int)acc[i] + __ldg(p.acc_bias + n)), __ldg(p.Mf + n)), __ldg(p.bf + n));
+                const int a = (int)acc[i] + (__float_as_int(s_kc[n].z) - CDN_MAGIC_I);
+                const double y = __dadd_rn(__dmul_rn((double)a, __ldg(p.Mf + n)), __ldg(p.bf + n));
                 p.out_f32[((size_t)img * p.n_f32 + n) * p.ppi + pi] = (float)y;
               }
             }
@@ -266,47 +354,50 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tc_fence_before();
         mbar_arrive(TEMPTY(as));
       } else {
-        // the previous tile's TMA stores must have finished reading the staging buffer
-        if (et == 0) tma_store_wait_read();
-        named_bar_sync(1, 128);
-        for (int c = c_begin; c < c_end; ++c) {
-          const cdn_pw_chunk ck = p.chunks[c];
-          uint32_t acc[16];
-          uint32_t pass_lo = 0, pass_hi = 0;
-          if (ck.count > 0) {
-            const uint32_t ta = tacc + (uint32_t)(ck.col - nt * p.BN);
-            if (ck.pass_off < 0) tmem_ld16(ta, acc); else tmem_ld8(ta, acc);
-          }
-          if (ck.pass_off >= 0) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              int off = ck.pass_off + i;
-              uint32_t byte = 0;
-              if (i < ck.count) {
-                const uint8_t* seg = s_pass + (size_t)(off >> 7) * 16384 + row * 128;
-                byte = seg[(((off & 127) >> 4) ^ (row & 7)) << 4 | (off & 15)];
-              }
-              if (i < 4) pass_lo |= byte << (8 * i); else pass_hi |= byte << (8 * (i - 4));
+        const uint8_t* pass_row = s_pass + (size_t)as * p.pass_segs * 16384 + row * 128;
+        const int sg0 = s_tile_seg[nt], sg1 = s_tile_seg[nt + 1];
+        for (int sg = sg0; sg < sg1; ++sg, ++g) {
+          const PwSeg S = s_segs[sg];
+          uint8_t* stg = s_out + (size_t)(g % (uint32_t)p.nbuf) * 16384 + row * 128;
+          for (int c = S.cb + half; c < S.ce; c += 2) {
+            const cdn_pw_chunk ck = s_chunks[c];
+            uint32_t acc[16];
+            uint32_t pass_lo = 0, pass_hi = 0;
+            if (ck.count > 0) {
+              const uint32_t ta = tacc + (uint32_t)(ck.col - nt * p.BN);
+              if (ck.pass_off < 0) tmem_ld16(ta, acc); else tmem_ld8(ta, acc);
             }
+            if (ck.pass_off >= 0) {
+              // 8 pass-through bytes at an arbitrary byte offset: two aligned 8-byte words (each inside one 16-byte
+              // swizzle unit) and a funnel shift
+              const int o8 = ck.pass_off & ~7, b = ck.pass_off & 7, o9 = o8 + 8;
+              const uint2 pa = *(const uint2*)(pass_row + (size_t)(o8 >> 7) * 16384 + (((((o8 & 127) >> 4) ^ (row & 7)) << 4) | (o8 & 8)));
+              const uint2 pb = *(const uint2*)(pass_row + (size_t)(o9 >> 7) * 16384 + (((((o9 & 127) >> 4) ^ (row & 7)) << 4) | (o9 & 8)));
+              uint32_t w0 = pa.x, w1 = pa.y, w2 = pb.x;
+              if (b >= 4) { w0 = pa.y; w1 = pb.x; w2 = pb.y; }
+              const int sh = 8 * (b & 3);
+              pass_lo = __funnelshift_r(w0, w1, sh); pass_hi = __funnelshift_r(w1, w2, sh);
+            }
+            tmem_ld_wait();
+            const uint4 o = chunk_bytes(ck, acc, s_kc, p.M, p.B, p.lo_f, p.thr, pass_lo, pass_hi);
+            const int j = (ck.dst_off & 127) >> 4;
+            *(uint4*)(stg + ((j ^ (row & 7)) << 4)) = o;
           }
-          tmem_ld_wait();
-          uint4 o = chunk_bytes(p, ck, acc, pass_lo, pass_hi);
-          const int seg = (ck.dst_off >> 7) - seg0, j = (ck.dst_off & 127) >> 4;
-          *(uint4*)(s_out + (size_t)seg * 16384 + row * 128 + ((j ^ (row & 7)) << 4)) = o;
-        }
-        tc_fence_before();
-        mbar_arrive(TEMPTY(as));
-        if (p.has_pass) mbar_arrive(PEMPTY);
-        fence_async_smem();
-        named_bar_sync(1, 128);
-        if (et == 0) {
-          for (int s = 0; s < nseg; ++s)
-            tma_store_2d(&tmO, (seg0 + s) * 128, (int)(mt * PW_BM), smem_u32(s_out + (size_t)s * 16384));
-          tma_store_commit();
+          if (sg + 1 == sg1) {                 // last TMEM / pass read of this tile is behind us
+            tc_fence_before();
+            mbar_arrive(TEMPTY(as));
+            if (p.has_pass) mbar_arrive(PEMPTY(as));
+          }
+          fence_async_smem();
+          named_bar_sync(1, PW_EPI_THREADS);
+          if (et == 0) {
+            tma_store_2d(&tmO, S.seg * 128, (int)(mt * PW_BM), smem_u32(s_out + (size_t)(g % (uint32_t)p.nbuf) * 16384));
+            tma_store_commit();
+            // before anyone passes the NEXT barrier, the store that used the buffer after next must have drained
+            if (p.nbuf >= 3) tma_store_wait_read1(); else tma_store_wait_read0();
+          }
         }
       }
-      if (p.has_pass) pphase ^= 1;
-      if (++as == 2) { as = 0; aphase ^= 1; }
     }
     if (et == 0) tma_store_wait_all();
   }
@@ -331,9 +422,10 @@ __global__ void pw_gemm_simt_kernel(const PwParams p, int total_chunks) {
   else ck = p.chunks[ci];
   uint32_t acc[16];
   const int8_t* a = p.in + (size_t)pix * p.in_pitch + p.k_off;
+  const int ncol = ck.pass_off < 0 ? 16 : 8;
   for (int i = 0; i < 16; ++i) {
     int s = 0;
-    if (i < ck.count) {
+    if (i < ncol && ck.count > 0) {
       const int8_t* w = p.w + (size_t)(ck.col + i) * p.Kp;
       for (int k = 0; k < p.Kp; ++k) {
         int kk = p.k_off + k;
@@ -357,10 +449,10 @@ __global__ void pw_gemm_simt_kernel(const PwParams p, int total_chunks) {
   uint32_t pass_lo = 0, pass_hi = 0;
   if (ck.pass_off >= 0)
     for (int i = 0; i < 8; ++i) {
-      uint32_t byte = (i < ck.count) ? (uint8_t)p.pass[(size_t)pix * p.pass_pitch + ck.pass_off + i] : 0u;
+      uint32_t byte = (ck.pass_off + i < p.pass_pitch) ? (uint8_t)p.pass[(size_t)pix * p.pass_pitch + ck.pass_off + i] : 0u;
       if (i < 4) pass_lo |= byte << (8 * i); else pass_hi |= byte << (8 * (i - 4));
     }
-  uint4 o = chunk_bytes(p, ck, acc, pass_lo, pass_hi);
+  uint4 o = chunk_bytes(ck, acc, p.kc, p.M, p.B, p.lo_f, p.thr, pass_lo, pass_hi);
   if (ck.dst_off + 16 <= p.out_pitch) *(uint4*)(p.out + (size_t)pix * p.out_pitch + ck.dst_off) = o;
 }
 
@@ -398,7 +490,7 @@ int make_tmap_2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows,
 }
 
 void pw_device_free(PwDevice& d) {
-  cudaFree(d.w); cudaFree(d.chunks); cudaFree(d.chunk_begin); cudaFree(d.seg_begin); cudaFree(d.Mf); cudaFree(d.bf);
+  cudaFree(d.w); cudaFree(d.chunks); cudaFree(d.segs); cudaFree(d.tile_seg); cudaFree(d.kc); cudaFree(d.Mf); cudaFree(d.bf);
   dev_requant_free(d.rq);
   d = PwDevice();
 }
@@ -413,17 +505,34 @@ int pw_device_build(PwDevice& d, const cdn_pw_desc* desc, int pass_pitch) {
   // N tiling: one tile when N <= 256, else tiles of 256 columns (so tiles own whole 128-byte output segments)
   d.n_tiles = (d.N + PW_MAX_BN - 1) / PW_MAX_BN;
   d.BN = d.n_tiles == 1 ? d.N : PW_MAX_BN;
-  CDN_CHECK((long long)d.K * 8 * 383 < (1 << 24), CDN_ERR_INVALID, "pw: K=%d too large for exact fp32 conversion of the accumulator", d.K);
   const int Np = d.BN * d.n_tiles;
-  // weights, zero padded to [Np][Kp]; acc_bias = zx * sum_k w
+  // weights, zero padded to [Np][Kp]; acc_bias = zx * sum_k w.  The epilogue converts the accumulator through the
+  // 1.5*2^23 magic constant, which needs |acc + acc_bias| < 2^22: with a = q + zx in [-255, 255] that is a bound on
+  // sum_k |w|, checked per column.
   std::vector<int8_t> w((size_t)Np * d.Kp, 0);
   std::vector<int32_t> ab(Np, 0);
   for (int n = 0; n < d.N; ++n) {
-    int sum = 0;
-    for (int k = 0; k < d.K; ++k) { int8_t v = desc->wq[(size_t)n * d.K + k]; w[(size_t)n * d.Kp + k] = v; sum += v; }
-    ab[n] = desc->zx * sum;
+    long long sum = 0, asum = 0;
+    for (int k = 0; k < d.K; ++k) { int8_t v = desc->wq[(size_t)n * d.K + k]; w[(size_t)n * d.Kp + k] = v; sum += v; asum += v < 0 ? -v : v; }
+    CDN_CHECK(asum * 255 < (1ll << 22), CDN_ERR_INVALID, "pw: column %d: sum|w| = %lld makes the accumulator exceed 2^22 (K=%d)", n, asum, d.K);
+    ab[n] = (int32_t)(desc->zx * sum);
   }
   if (dev_upload(&d.w, w.data(), w.size())) return CDN_ERR_CUDA;
+  std::vector<float4> kc(Np);
+  double min_thr = 0.5;
+  auto fill_kc = [&](const DevRequant&, const cdn_requant* rq) {
+    for (int n = 0; n < Np; ++n) {
+      RqFast f{0.f, 0.f, 0.5f};
+      if (rq && n < rq->n) f = rq_fast_from(rq->M[n], rq->B[n]);
+      int32_t bits = ab[n] + CDN_MAGIC_I_HOST;
+      float z; memcpy(&z, &bits, 4);
+      kc[n] = make_float4(f.Mh, f.Bh, z, 0.f);
+      if (rq && n < rq->n) min_thr = std::min(min_thr, (double)f.thr);
+    }
+  };
+  std::vector<cdn_pw_chunk> ch;
+  std::vector<PwSeg> segs;
+  std::vector<int> tile_seg(d.n_tiles + 1, 0);
   if (d.n_f32 > 0) {
     CDN_CHECK(desc->Mf && desc->bf && d.n_f32 <= d.N, CDN_ERR_INVALID, "pw: fp32 output needs Mf/bf and n_f32 <= N");
     std::vector<double> Mf(Np, 0.0), bf(Np, 0.0), one(Np, 1.0), zero(Np, 0.0);
@@ -432,76 +541,100 @@ int pw_device_build(PwDevice& d, const cdn_pw_desc* desc, int pass_pitch) {
     if (dev_upload(&d.bf, bf.data(), Np)) return CDN_ERR_CUDA;
     cdn_requant dummy{one.data(), zero.data(), -128, Np};
     if (int r = dev_requant_upload(d.rq, &dummy, ab.data(), Np)) return r;
-    d.max_segs = 0; d.has_pass = 0; d.n_chunks = 0;
-    std::vector<int> zb(2 * d.n_tiles + 2, 0);
-    if (dev_upload(&d.chunk_begin, zb.data(), zb.size())) return CDN_ERR_CUDA;
-    if (dev_upload(&d.seg_begin, zb.data(), zb.size())) return CDN_ERR_CUDA;
+    fill_kc(d.rq, nullptr);
+    d.has_pass = 0; d.n_chunks = 0; d.n_segs = 0; d.nbuf = 0; d.pass_segs = 0;
+    ch.push_back(cdn_pw_chunk{0, 0, -1, 0});      // keep the device arrays non-empty
+    segs.push_back(PwSeg{0, 0, 0, 0});
   } else {
     CDN_CHECK(desc->rq.n == d.N && desc->rq.M && desc->rq.B, CDN_ERR_INVALID, "pw: requant constants must have n == N");
     CDN_CHECK(desc->chunks && desc->n_chunks > 0, CDN_ERR_INVALID, "pw: int8 output needs a chunk table");
     if (int r = dev_requant_upload(d.rq, &desc->rq, ab.data(), Np)) return r;
-    // sort chunks by N tile, validate, derive the 128-byte output segments each tile owns
-    std::vector<cdn_pw_chunk> ch;
-    std::vector<int> cb(d.n_tiles + 1, 0), sb(2 * d.n_tiles, 0);
-    d.has_pass = 0; d.max_segs = 0;
+    fill_kc(d.rq, &desc->rq);
+    // chunks grouped by N tile, then by 128-byte output segment; every tile owns whole segments
+    d.has_pass = 0;
     int seg_cursor = 0;
     for (int t = 0; t < d.n_tiles; ++t) {
-      cb[t] = (int)ch.size();
+      tile_seg[t] = (int)segs.size();
+      std::vector<cdn_pw_chunk> mine;
       int smin = 1 << 30, smax = -1;
       for (int i = 0; i < desc->n_chunks; ++i) {
         cdn_pw_chunk c = desc->chunks[i];
-        int tile = c.count > 0 ? c.col / d.BN : -1;
-        if (c.count == 0) {                  // zero-fill chunk: give it to the tile owning its segment (decided below)
-          continue;
-        }
-        if (tile != t) continue;
-        CDN_CHECK(c.col % 8 == 0 && c.col + c.count <= (t + 1) * d.BN && c.col + c.count <= d.N,
+        if (c.count == 0 || c.col / d.BN != t) continue;
+        const int width = c.pass_off < 0 ? 16 : 8;
+        CDN_CHECK(c.col % 8 == 0 && c.col % d.BN + width <= d.BN && c.col + c.count <= d.N && c.count <= width,
                   CDN_ERR_INVALID, "pw: chunk col=%d count=%d crosses the tile/N boundary", c.col, c.count);
-        CDN_CHECK(c.count <= (c.pass_off < 0 ? 16 : 8) && c.dst_off % 16 == 0, CDN_ERR_INVALID, "pw: bad chunk");
-        if (c.pass_off >= 0) { d.has_pass = 1; CDN_CHECK(c.pass_off + c.count <= pass_pitch, CDN_ERR_INVALID, "pw: pass offset beyond pass pitch"); }
-        ch.push_back(c);
+        CDN_CHECK(c.dst_off % 16 == 0 && c.dst_off >= 0, CDN_ERR_INVALID, "pw: chunk dst_off must be a multiple of 16");
+        if (c.pass_off >= 0) {
+          d.has_pass = 1;
+          CDN_CHECK(c.pass_off + c.count <= pass_pitch, CDN_ERR_INVALID, "pw: pass offset %d beyond the pass pixel", c.pass_off);
+        }
+        mine.push_back(c);
         smin = std::min(smin, c.dst_off >> 7); smax = std::max(smax, c.dst_off >> 7);
       }
       CDN_CHECK(smax >= 0, CDN_ERR_INVALID, "pw: N tile %d has no output chunk", t);
-      // zero-fill chunks that fall into this tile's segment range
-      for (int i = 0; i < desc->n_chunks; ++i) {
+      for (int i = 0; i < desc->n_chunks; ++i) {   // zero-fill chunks that fall into this tile's segment range
         cdn_pw_chunk c = desc->chunks[i];
-        if (c.count == 0 && (c.dst_off >> 7) >= smin && (c.dst_off >> 7) <= smax) { c.pass_off = -1; c.col = (int16_t)(t * d.BN); ch.push_back(c); }
+        if (c.count == 0 && (c.dst_off >> 7) >= smin && (c.dst_off >> 7) <= smax) { c.pass_off = -1; c.col = (int16_t)(t * d.BN); mine.push_back(c); }
       }
       CDN_CHECK(smin >= seg_cursor, CDN_ERR_INVALID, "pw: output segments of N tiles overlap (tile %d)", t);
       seg_cursor = smax + 1;
-      sb[2 * t] = smin; sb[2 * t + 1] = smax - smin + 1;
-      d.max_segs = std::max(d.max_segs, smax - smin + 1);
+      std::stable_sort(mine.begin(), mine.end(), [](const cdn_pw_chunk& a, const cdn_pw_chunk& b) { return a.dst_off < b.dst_off; });
+      for (size_t i = 0; i < mine.size(); ++i) {
+        const int sg = mine[i].dst_off >> 7;
+        if (segs.size() == (size_t)tile_seg[t] || segs.back().seg != sg) segs.push_back(PwSeg{sg, (int)ch.size(), (int)ch.size(), 0});
+        ch.push_back(mine[i]);
+        segs.back().ce = (int)ch.size();
+      }
     }
-    cb[d.n_tiles] = (int)ch.size();
-    // a TMEM 16-column load must stay inside the accumulator stage
-    for (auto& c : ch) CDN_CHECK((c.col % d.BN) + (c.pass_off < 0 ? 16 : 8) <= PW_MAX_BN, CDN_ERR_INVALID, "pw: chunk column overflow");
-    d.n_chunks = (int)ch.size();
-    if (dev_upload(&d.chunks, ch.data(), ch.size())) return CDN_ERR_CUDA;
-    if (dev_upload(&d.chunk_begin, cb.data(), cb.size())) return CDN_ERR_CUDA;
-    if (dev_upload(&d.seg_begin, sb.data(), sb.size())) return CDN_ERR_CUDA;
+    tile_seg[d.n_tiles] = (int)segs.size();
+    d.n_chunks = (int)ch.size(); d.n_segs = (int)segs.size();
   }
-  if (int r = make_tmap_2d(&d.tmB, d.w, (uint64_t)d.Kp, (uint64_t)Np, (uint64_t)d.Kp, (uint32_t)d.BN)) return r;
-  // shared memory budget
-  const size_t stage_bytes = PW_BM * PW_BK + (((size_t)d.BN * PW_BK + 1023) & ~(size_t)1023);
+  d.thr = (float)min_thr;
+  if (dev_upload(&d.chunks, ch.data(), ch.size())) return CDN_ERR_CUDA;
+  if (dev_upload((PwSeg**)&d.segs, segs.data(), segs.size())) return CDN_ERR_CUDA;
+  if (dev_upload(&d.tile_seg, tile_seg.data(), tile_seg.size())) return CDN_ERR_CUDA;
+  if (dev_upload((float4**)&d.kc, kc.data(), kc.size())) return CDN_ERR_CUDA;
+  // shared memory plan (mirrors the carve in the kernel)
   int pass_need = 0;
-  if (d.has_pass) for (int i = 0; i < desc->n_chunks; ++i) if (desc->chunks[i].pass_off >= 0) pass_need = std::max(pass_need, desc->chunks[i].pass_off + desc->chunks[i].count);
-  const int pass_segs = d.has_pass ? (pass_need + 127) / 128 : 0;
-  d.pass_segs = pass_segs;
-  const size_t fixed = (size_t)(pass_segs + d.max_segs) * 16384 + 256 + 1024;
-  int stages = (int)((227 * 1024 - fixed) / stage_bytes);
-  if (stages > 6) stages = 6;
-  if (stages > d.num_k_blocks * 2 && stages > 2) stages = std::max(2, d.num_k_blocks * 2);
-  CDN_CHECK(stages >= 2, CDN_ERR_INVALID, "pw: layer does not fit in shared memory (BN=%d, out segs=%d, pass segs=%d)", d.BN, d.max_segs, pass_segs);
+  if (d.has_pass) for (int i = 0; i < desc->n_chunks; ++i) if (desc->chunks[i].pass_off >= 0) pass_need = std::max(pass_need, (desc->chunks[i].pass_off & ~7) + 16);
+  d.pass_segs = d.has_pass ? (pass_need + 127) / 128 : 0;
+  const size_t b_blk = ((size_t)d.BN * PW_BK + 1023) & ~(size_t)1023;
+  const size_t b_all = (size_t)d.num_k_blocks * Np * PW_BK;
+  const size_t tables = (size_t)Np * 16 + (size_t)((d.n_chunks + 1) & ~1) * 8 + (size_t)d.n_segs * 16 + (size_t)((d.n_tiles + 1 + 3) & ~3) * 4 + 32 * 8;
+  auto plan = [&](bool resident, int nbuf, int& stages) {
+    const size_t fixed = 1024 + (resident ? b_all : 0) + (size_t)2 * d.pass_segs * 16384 + (size_t)nbuf * 16384 + tables;
+    const size_t stage_bytes = 16384 + (resident ? 0 : b_blk);
+    if (fixed + 2 * stage_bytes > PW_SMEM_LIMIT) { stages = 0; return (size_t)0; }
+    stages = (int)std::min<size_t>(PW_MAX_STAGES, (PW_SMEM_LIMIT - fixed) / stage_bytes);
+    return fixed + (size_t)stages * stage_bytes;
+  };
+  const int want_buf = d.n_f32 > 0 ? 0 : 3;
+  int stages = 0; size_t bytes = 0;
+  d.resident = 0;
+  // prefer resident weights with at least two tiles' worth of activation stages in flight
+  for (int nbuf = want_buf; nbuf >= (d.n_f32 > 0 ? 0 : 2) && !d.resident; --nbuf) {
+    bytes = plan(true, nbuf, stages);
+    if (stages >= std::max(2, 2 * d.num_k_blocks) || (stages >= 2 && d.num_k_blocks > 4)) { d.resident = 1; d.nbuf = nbuf; }
+    if (d.n_f32 > 0) break;
+  }
+  if (!d.resident) {
+    for (int nbuf = want_buf; nbuf >= (d.n_f32 > 0 ? 0 : 2); --nbuf) {
+      bytes = plan(false, nbuf, stages);
+      if (stages >= 2) { d.nbuf = nbuf; break; }
+      if (d.n_f32 > 0) break;
+    }
+  }
+  CDN_CHECK(stages >= 2, CDN_ERR_INVALID, "pw: layer does not fit in shared memory (K=%d N=%d BN=%d pass segs=%d)", d.K, d.N, d.BN, d.pass_segs);
   d.stages = stages;
-  d.smem_bytes = (size_t)stages * stage_bytes + fixed;
+  d.smem_bytes = bytes;
+  if (int r = make_tmap_2d(&d.tmB, d.w, (uint64_t)d.Kp, (uint64_t)Np, (uint64_t)d.Kp, (uint32_t)d.BN)) return r;
   return 0;
 }
 
 int pw_init_attrs() {
   static bool attr_set = false;
   if (!attr_set) {
-    CDN_CUDA(cudaFuncSetAttribute(pw_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CDN_CUDA(cudaFuncSetAttribute(pw_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_LIMIT));
     attr_set = true;
   }
   return 0;
@@ -516,11 +649,12 @@ int pw_launch(const PwDevice& d, const int8_t* in, int in_pitch, long long pixel
   CDN_CHECK(d.n_f32 > 0 ? (out_f32 != nullptr && ppi > 0) : (out != nullptr), CDN_ERR_INVALID, "pw: missing output pointer");
   PwParams p; memset(&p, 0, sizeof(p));
   p.num_k_blocks = d.num_k_blocks; p.k_off = d.k_off; p.BN = d.BN; p.n_tiles = d.n_tiles; p.stages = d.stages;
-  p.has_pass = d.has_pass; p.pass_segs = d.pass_segs; p.max_segs = d.max_segs;
+  p.has_pass = d.has_pass; p.pass_segs = d.pass_segs; p.nbuf = d.nbuf; p.resident = d.resident;
+  p.n_chunks = d.n_chunks; p.n_segs = d.n_segs;
   p.m_tiles = (pixels + PW_BM - 1) / PW_BM; p.pixels = pixels;
-  p.chunks = d.chunks; p.chunk_begin = d.chunk_begin; p.seg_begin = d.seg_begin;
-  p.Mh = d.rq.Mh; p.Bh = d.rq.Bh; p.thr = d.rq.thr; p.M = d.rq.M; p.B = d.rq.B; p.acc_bias = d.rq.acc_bias;
-  p.lo_f = (float)d.rq.lo;
+  p.chunks = d.chunks; p.segs = (const PwSeg*)d.segs; p.tile_seg = d.tile_seg; p.kc = (const float4*)d.kc;
+  p.M = d.rq.M; p.B = d.rq.B; p.acc_bias = d.rq.acc_bias;
+  p.lo_f = (float)d.rq.lo; p.thr = d.thr;
   p.n_f32 = d.n_f32; p.ppi = ppi; p.out_f32 = out_f32; p.Mf = d.Mf; p.bf = d.bf;
   p.in = in; p.in_pitch = in_pitch; p.pass = pass; p.pass_pitch = pass_pitch; p.out = out; p.out_pitch = out_pitch;
   p.w = d.w; p.Kp = d.Kp; p.N = d.BN * d.n_tiles;
