@@ -67,6 +67,37 @@ __device__ __forceinline__ uint32_t requant_bits(int acc, float Mh, float Bh, fl
 }
 __device__ __forceinline__ int rq_bits_to_int(uint32_t bits) { return (int)bits - CDN_MAGIC_I; }
 
+// ---- lean requantisation (v2 kernels) ----------------------------------------------------------------------
+// One element costs IADD, FADD, FFMA, FMNMX, 3 FADD and two halves of 3-input FMNMX: the rounding-boundary guard
+// and the upper clamp are accumulated as running maxima over a group of elements and tested ONCE per group
+// (a serial predicate chain per element costs ~40% more issue cycles; tools/ubench_requant.cu).
+//   v_magic = acc + acc_bias + MAGIC_I   (|acc + acc_bias| < 2^22, so the bits ARE the float 1.5*2^23 + value)
+// Returns the float r = rint(clamp(t)) + 1.5*2^23 whose LOW BYTE is the int8 result, valid iff !rq_group_bad().
+struct RqGuard { float d0, d1, tmax; };
+__device__ __forceinline__ void rq_guard_init(RqGuard& g) { g.d0 = 0.f; g.d1 = 0.f; g.tmax = -3.0e38f; }
+template <int PARITY>
+__device__ __forceinline__ uint32_t rq_fast(int v_magic, float Mh, float Bh, float lo_f, RqGuard& g) {
+  const float f = __fadd_rn(__int_as_float(v_magic), -CDN_MAGIC_F);
+  float t = __fmaf_rn(f, Mh, Bh);
+  t = fmaxf(t, lo_f);
+  g.tmax = fmaxf(g.tmax, t);
+  const float r = __fadd_rn(t, CDN_MAGIC_F);
+  const float kk = __fadd_rn(r, -CDN_MAGIC_F);
+  const float d = fabsf(__fadd_rn(t, -kk));
+  if (PARITY) g.d1 = fmaxf(g.d1, d); else g.d0 = fmaxf(g.d0, d);
+  return __float_as_uint(r);
+}
+// true when some element of the group was within eps of a rounding boundary or above the int8 range
+__device__ __forceinline__ bool rq_group_bad(const RqGuard& g, float thr) {
+  return fmaxf(g.d0, g.d1) > thr || g.tmax > 127.0f + thr;
+}
+// exact value of the same element: fl64(fl64(v*M) + B), clamped, rounded half-to-even
+__device__ __forceinline__ uint32_t rq_exact(int v, double M, double B, float lo_f) {
+  double td = __dadd_rn(__dmul_rn((double)v, M), B);
+  td = fmin(fmax(td, (double)lo_f), 127.0);
+  return __float_as_uint((float)__double2int_rn(td) + CDN_MAGIC_F);
+}
+
 // pack the low bytes of four requant_bits() results into one little-endian word
 __device__ __forceinline__ uint32_t pack4_lowbytes(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   uint32_t ab = __byte_perm(a, b, 0x0040);   // [a.0, b.0, a.0, a.0] -> bytes0,1 used

@@ -64,37 +64,161 @@ __device__ __forceinline__ uint32_t mac9_requant(const uint32_t (&x)[9], const L
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// plain depthwise 3x3, stride 1/2, optional virtual x2 upsample of the input
+// plain depthwise 3x3 (v2): sliding window down a column strip, horizontal taps packed for dp4a
+//
+// A thread owns one 32-bit channel word (4 channels) of a PAIR of horizontally adjacent output pixels and walks
+// down R output rows.  Per input row it loads the 4 pixels x0-1 .. x0+2 (coalesced: lanes run along channels),
+// transposes them once (8 PRMT) into per-channel words T[c] = (p(x0-1), p(x0), p(x0+1), p(x0+2)), and keeps the last
+// three rows' T in registers.  An output is then 3 dp4a per channel: weights (w0,w1,w2,0) for the left pixel and
+// (0,w0,w1,w2) for the right one -- 4.5 issue slots per output byte instead of 15 for tap-by-tap code.
+//   STRIDE 2: one output pixel per thread, taps (2x-1, 2x, 2x+1), two new input rows per output row.
+//   SHIFT 1 (virtual nearest x2 upsample of the input, stride 1): the 2x2 outputs that share a stored pixel
+//   neighbourhood are produced together; rows/columns that read the same stored pixel twice have their weights
+//   pre-added on the host, so an output costs 2 dp4a per channel.
+// Accumulators start at acc_bias + MAGIC_I and are requantised with the lean guarded sequence of common.cuh.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) dw3x3_kernel(DwParams p) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  const int ppw = 32 / p.lpp, sub = lane / p.lpp, cl = lane % p.lpp;
-  const long long pblocks = (p.total + ppw - 1) / ppw;
-  const long long items = pblocks * p.G;       // (pixel block, channel group) pairs, group fastest
-  LaneConsts k; int cur_g = -1;
-  for (long long it = (long long)blockIdx.x * nw + warp; it < items; it += (long long)gridDim.x * nw) {
-    const int g = (int)(it % p.G);
-    const int cw = g * 32 + cl;
-    const bool active = cw < p.cw_total;
-    if (g != cur_g) { load_lane_consts(p, cw, active, k); cur_g = g; }
-    long long pix = (it / p.G) * ppw + sub;
-    if (pix >= p.total || !active) continue;
-    int wo = (int)(pix % p.Wout); long long t = pix / p.Wout; int ho = (int)(t % p.Hout); long long b = t / p.Hout;
-    const uint32_t* img = p.in + (size_t)b * p.Hs * p.Ws * p.in_pitch_w + cw;
-    uint32_t x[9];
+template <int STRIDE, int SHIFT> struct DwV2 { static constexpr int NW = STRIDE == 2 ? 3 : (SHIFT ? 8 : 6); };
+
+struct DwV2Params {
+  const uint32_t* in; uint32_t* out;
+  int in_pitch_w, out_pitch_w;
+  int Hs, Ws, Hout, Wout;                    // stored input size, output size
+  int cw_total, PG, R, nstrips;              // channel words, pixel groups per row, rows per strip, strips per image
+  long long nthreads;
+  uint32_t pad_word;
+  const uint32_t* wpk;                       // [channel][NW] packed tap weights
+  const float2* mb; const int* abm;          // per channel (Mh, Bh), acc_bias + MAGIC_I
+  const double* M; const double* B;
+  float lo_f, thr;
+};
+
+struct DwLane { float Mh[4], Bh[4]; int abm[4]; };
+
+// requantise 4 channels of one pixel: accumulators (already magic-biased) -> packed word
+__device__ __forceinline__ uint32_t dw_rq_word(const int (&acc)[4], const DwLane& k, float lo_f, RqGuard& g) {
+  const uint32_t r0 = rq_fast<0>(acc[0], k.Mh[0], k.Bh[0], lo_f, g);
+  const uint32_t r1 = rq_fast<1>(acc[1], k.Mh[1], k.Bh[1], lo_f, g);
+  const uint32_t r2 = rq_fast<0>(acc[2], k.Mh[2], k.Bh[2], lo_f, g);
+  const uint32_t r3 = rq_fast<1>(acc[3], k.Mh[3], k.Bh[3], lo_f, g);
+  return pack4_lowbytes(r0, r1, r2, r3);
+}
+__device__ __noinline__ uint32_t dw_rq_word_exact(int a0, int a1, int a2, int a3, const double* __restrict__ M,
+                                                  const double* __restrict__ B, int ch, float lo_f) {
+  const uint32_t r0 = rq_exact(a0 - CDN_MAGIC_I, __ldg(M + ch), __ldg(B + ch), lo_f);
+  const uint32_t r1 = rq_exact(a1 - CDN_MAGIC_I, __ldg(M + ch + 1), __ldg(B + ch + 1), lo_f);
+  const uint32_t r2 = rq_exact(a2 - CDN_MAGIC_I, __ldg(M + ch + 2), __ldg(B + ch + 2), lo_f);
+  const uint32_t r3 = rq_exact(a3 - CDN_MAGIC_I, __ldg(M + ch + 3), __ldg(B + ch + 3), lo_f);
+  return pack4_lowbytes(r0, r1, r2, r3);
+}
+
+// one stored row -> per-channel words of NPIX (3 or 4) horizontally adjacent stored pixels starting at xs0
+template <int NPIX>
+__device__ __forceinline__ void dw_load_row(const uint32_t* __restrict__ img, int pitch_w, int Hs, int Ws, int ys, int xs0,
+                                            int xstep, uint32_t pad, uint32_t (&T)[4]) {
+  if ((unsigned)ys >= (unsigned)Hs) { T[0] = T[1] = T[2] = T[3] = pad; return; }
+  const uint32_t* row = img + (size_t)ys * Ws * pitch_w;
+  uint32_t w[4];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      int y = ho * p.stride - 1 + i;
-      bool yok = (unsigned)y < (unsigned)p.Hin;
-      const uint32_t* row = img + (size_t)(y >> p.shift) * p.Ws * p.in_pitch_w;
+  for (int j = 0; j < 4; ++j) {
+    const int xx = xs0 + j * xstep;
+    w[j] = (j < NPIX && (unsigned)xx < (unsigned)Ws) ? __ldg(row + (size_t)xx * pitch_w) : pad;
+  }
+  transpose4x4(w[0], w[1], w[2], w[3], T[0], T[1], T[2], T[3]);
+}
+
+template <int STRIDE, int SHIFT>
+__global__ void __launch_bounds__(256) dw3x3_v2_kernel(const DwV2Params p) {
+  constexpr int NW = DwV2<STRIDE, SHIFT>::NW;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p.nthreads) return;
+  const int cw = (int)(idx % p.cw_total); long long t = idx / p.cw_total;
+  const int pg = (int)(t % p.PG); t /= p.PG;
+  const int strip = (int)(t % p.nstrips); const long long b = t / p.nstrips;
+  // per-lane constants
+  uint32_t W[4][NW]; DwLane k;
 #pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        int xx = wo * p.stride - 1 + j;
-        bool ok = yok && (unsigned)xx < (unsigned)p.Win;
-        x[i * 3 + j] = ok ? __ldg(row + (size_t)(xx >> p.shift) * p.in_pitch_w) : p.pad_word;
+  for (int c = 0; c < 4; ++c) {
+    const int ch = cw * 4 + c;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) W[c][i] = __ldg(p.wpk + (size_t)ch * NW + i);
+    const float2 mb = __ldg(p.mb + ch); k.Mh[c] = mb.x; k.Bh[c] = mb.y; k.abm[c] = __ldg(p.abm + ch);
+  }
+  const uint32_t* img = p.in + (size_t)b * p.Hs * p.Ws * p.in_pitch_w + cw;
+  uint32_t* outb = p.out + (size_t)b * p.Hout * p.Wout * p.out_pitch_w + cw;
+  const int ch0 = cw * 4;
+
+  if (STRIDE == 1 && SHIFT == 0) {
+    const int x0 = 2 * pg, y0 = strip * p.R, y1 = min(y0 + p.R, p.Hout);
+    uint32_t Tm[4], Tc[4], Tp[4];
+    dw_load_row<4>(img, p.in_pitch_w, p.Hs, p.Ws, y0 - 1, x0 - 1, 1, p.pad_word, Tm);
+    dw_load_row<4>(img, p.in_pitch_w, p.Hs, p.Ws, y0, x0 - 1, 1, p.pad_word, Tc);
+    for (int y = y0; y < y1; ++y) {
+      dw_load_row<4>(img, p.in_pitch_w, p.Hs, p.Ws, y + 1, x0 - 1, 1, p.pad_word, Tp);
+      int a0[4], a1[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        a0[c] = dp4a_ss(Tp[c], W[c][4], dp4a_ss(Tc[c], W[c][2], dp4a_ss(Tm[c], W[c][0], k.abm[c])));
+        a1[c] = dp4a_ss(Tp[c], W[c][5], dp4a_ss(Tc[c], W[c][3], dp4a_ss(Tm[c], W[c][1], k.abm[c])));
       }
+      RqGuard g; rq_guard_init(g);
+      uint32_t o0 = dw_rq_word(a0, k, p.lo_f, g), o1 = dw_rq_word(a1, k, p.lo_f, g);
+      if (rq_group_bad(g, p.thr)) {
+        o0 = dw_rq_word_exact(a0[0], a0[1], a0[2], a0[3], p.M, p.B, ch0, p.lo_f);
+        o1 = dw_rq_word_exact(a1[0], a1[1], a1[2], a1[3], p.M, p.B, ch0, p.lo_f);
+      }
+      uint32_t* o = outb + ((size_t)y * p.Wout + x0) * p.out_pitch_w;
+      o[0] = o0;
+      if (x0 + 1 < p.Wout) o[p.out_pitch_w] = o1;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { Tm[c] = Tc[c]; Tc[c] = Tp[c]; }
     }
-    p.out[(size_t)pix * p.out_pitch_w + cw] = mac9_requant(x, k, p, cw);
+  } else if (STRIDE == 2) {
+    const int xo = pg, y0 = strip * p.R, y1 = min(y0 + p.R, p.Hout);
+    uint32_t Tm[4], Tc[4], Tp[4];
+    dw_load_row<3>(img, p.in_pitch_w, p.Hs, p.Ws, 2 * y0 - 1, 2 * xo - 1, 1, p.pad_word, Tm);
+    for (int y = y0; y < y1; ++y) {
+      dw_load_row<3>(img, p.in_pitch_w, p.Hs, p.Ws, 2 * y, 2 * xo - 1, 1, p.pad_word, Tc);
+      dw_load_row<3>(img, p.in_pitch_w, p.Hs, p.Ws, 2 * y + 1, 2 * xo - 1, 1, p.pad_word, Tp);
+      int a0[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        a0[c] = dp4a_ss(Tp[c], W[c][2], dp4a_ss(Tc[c], W[c][1], dp4a_ss(Tm[c], W[c][0], k.abm[c])));
+      RqGuard g; rq_guard_init(g);
+      uint32_t o0 = dw_rq_word(a0, k, p.lo_f, g);
+      if (rq_group_bad(g, p.thr)) o0 = dw_rq_word_exact(a0[0], a0[1], a0[2], a0[3], p.M, p.B, ch0, p.lo_f);
+      outb[((size_t)y * p.Wout + xo) * p.out_pitch_w] = o0;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) Tm[c] = Tp[c];
+    }
+  } else {
+    // SHIFT 1: stored pixel column s = pg, stored rows r0 .. r1-1 -> output rows 2r, 2r+1 and columns 2s, 2s+1
+    const int s = pg, r0 = strip * p.R, r1 = min(r0 + p.R, p.Hs);
+    uint32_t Tm[4], Tc[4], Tp[4];
+    dw_load_row<3>(img, p.in_pitch_w, p.Hs, p.Ws, r0 - 1, s - 1, 1, p.pad_word, Tm);
+    dw_load_row<3>(img, p.in_pitch_w, p.Hs, p.Ws, r0, s - 1, 1, p.pad_word, Tc);
+    for (int r = r0; r < r1; ++r) {
+      dw_load_row<3>(img, p.in_pitch_w, p.Hs, p.Ws, r + 1, s - 1, 1, p.pad_word, Tp);
+#pragma unroll
+      for (int yp = 0; yp < 2; ++yp) {
+        int a0[4], a1[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t ta = yp ? Tc[c] : Tm[c], tb = yp ? Tp[c] : Tc[c];
+          a0[c] = dp4a_ss(tb, W[c][4 * yp + 2], dp4a_ss(ta, W[c][4 * yp + 0], k.abm[c]));
+          a1[c] = dp4a_ss(tb, W[c][4 * yp + 3], dp4a_ss(ta, W[c][4 * yp + 1], k.abm[c]));
+        }
+        RqGuard g; rq_guard_init(g);
+        uint32_t o0 = dw_rq_word(a0, k, p.lo_f, g), o1 = dw_rq_word(a1, k, p.lo_f, g);
+        if (rq_group_bad(g, p.thr)) {
+          o0 = dw_rq_word_exact(a0[0], a0[1], a0[2], a0[3], p.M, p.B, ch0, p.lo_f);
+          o1 = dw_rq_word_exact(a1[0], a1[1], a1[2], a1[3], p.M, p.B, ch0, p.lo_f);
+        }
+        uint32_t* o = outb + ((size_t)(2 * r + yp) * p.Wout + 2 * s) * p.out_pitch_w;
+        o[0] = o0; o[p.out_pitch_w] = o1;
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { Tm[c] = Tc[c]; Tc[c] = Tp[c]; }
+    }
   }
 }
 
@@ -234,6 +358,50 @@ int dw_device_build(DwDevice& d, const int8_t* wq, const int8_t* ws, int C, int 
   d.acc_s_bias = 0;
   if (ws) for (int c = 0; c < C; ++c) { wsw[c / 4] |= (uint32_t)(uint8_t)ws[c] << (8 * (c & 3)); d.acc_s_bias += (long long)zx * ws[c]; }
   d.cw_total = Cp / 4;
+  // v2 kernels: tap weights packed for horizontal dp4a (see dw3x3_v2_kernel), per-channel fast constants
+  {
+    auto pk = [](int b0, int b1, int b2, int b3) {
+      return (uint32_t)(uint8_t)(int8_t)b0 | ((uint32_t)(uint8_t)(int8_t)b1 << 8) | ((uint32_t)(uint8_t)(int8_t)b2 << 16) |
+             ((uint32_t)(uint8_t)(int8_t)b3 << 24);
+    };
+    std::vector<uint32_t> w1((size_t)Cp * 6, 0), w2((size_t)Cp * 3, 0), wu((size_t)Cp * 8, 0);
+    std::vector<float2> mb(Cp, make_float2(0.f, 0.f));
+    std::vector<int32_t> abm(Cp, CDN_MAGIC_I_HOST);
+    double min_thr = 0.5; bool u_ok = true;
+    for (int c = 0; c < C; ++c) {
+      const int8_t* w = wq + c * 9;
+      for (int r = 0; r < 3; ++r) {
+        w1[(size_t)c * 6 + 2 * r] = pk(w[3 * r], w[3 * r + 1], w[3 * r + 2], 0);
+        w1[(size_t)c * 6 + 2 * r + 1] = pk(0, w[3 * r], w[3 * r + 1], w[3 * r + 2]);
+        w2[(size_t)c * 3 + r] = pk(w[3 * r], w[3 * r + 1], w[3 * r + 2], 0);
+      }
+      // upsample-folded: [ypar][term] row vectors, each -> px0 (v0, v1+v2, 0, 0) and px1 (0, v0+v1, v2, 0)
+      int rows[2][2][3];
+      for (int j = 0; j < 3; ++j) {
+        rows[0][0][j] = w[j];            rows[0][1][j] = w[3 + j] + w[6 + j];
+        rows[1][0][j] = w[j] + w[3 + j]; rows[1][1][j] = w[6 + j];
+      }
+      for (int yp = 0; yp < 2; ++yp)
+        for (int tm = 0; tm < 2; ++tm) {
+          const int* v = rows[yp][tm];
+          const int a[2][3] = {{v[0], v[1] + v[2], 0}, {0, v[0] + v[1], v[2]}};
+          for (int px = 0; px < 2; ++px) {
+            for (int j = 0; j < 3; ++j) if (a[px][j] < -128 || a[px][j] > 127) u_ok = false;
+            wu[(size_t)c * 8 + 4 * yp + 2 * tm + px] = pk(a[px][0], a[px][1], a[px][2], 0);
+          }
+        }
+      RqFast f = rq_fast_from(rq->M[c], rq->B[c]);
+      mb[c] = make_float2(f.Mh, f.Bh);
+      abm[c] = ab[c] + CDN_MAGIC_I_HOST;
+      min_thr = std::min(min_thr, (double)f.thr);
+    }
+    d.thr = (float)min_thr; d.u_ok = u_ok ? 1 : 0;
+    if (dev_upload(&d.wpk1, w1.data(), w1.size())) return CDN_ERR_CUDA;
+    if (dev_upload(&d.wpk2, w2.data(), w2.size())) return CDN_ERR_CUDA;
+    if (dev_upload(&d.wpku, wu.data(), wu.size())) return CDN_ERR_CUDA;
+    if (dev_upload(&d.mb, mb.data(), mb.size())) return CDN_ERR_CUDA;
+    if (dev_upload(&d.abm, abm.data(), abm.size())) return CDN_ERR_CUDA;
+  }
   if (dev_upload(&d.wA, wA.data(), Cp)) return CDN_ERR_CUDA;
   if (dev_upload(&d.wB, wB.data(), Cp)) return CDN_ERR_CUDA;
   if (dev_upload(&d.wC, wC.data(), Cp)) return CDN_ERR_CUDA;
@@ -243,6 +411,7 @@ int dw_device_build(DwDevice& d, const int8_t* wq, const int8_t* ws, int C, int 
 
 void dw_device_free(DwDevice& d) {
   cudaFree(d.wA); cudaFree(d.wB); cudaFree(d.wC); cudaFree(d.ws); dev_requant_free(d.rq);
+  cudaFree(d.wpk1); cudaFree(d.wpk2); cudaFree(d.wpku); cudaFree(d.mb); cudaFree(d.abm);
   d = DwDevice();
 }
 
@@ -269,18 +438,31 @@ static void fill_common(DwParams& p, const DwDevice& d, const int8_t* in, int in
 int dw_launch(const DwDevice& d, const int8_t* in, int in_pitch, int8_t* out, int out_pitch, int batch, int H, int W,
               int in_shift, int stride, int zx, cudaStream_t st) {
   CDN_CHECK(stride == 1 || stride == 2, CDN_ERR_INVALID, "dw: stride must be 1 or 2");
-  CDN_CHECK(in_shift == 0 || (in_shift == 1 && H % 2 == 0 && W % 2 == 0), CDN_ERR_INVALID, "dw: bad in_shift");
+  CDN_CHECK(in_shift == 0 || (in_shift == 1 && stride == 1 && H % 2 == 0 && W % 2 == 0), CDN_ERR_INVALID, "dw: bad in_shift");
   CDN_CHECK(in_pitch >= d.cw_total * 4 && out_pitch >= d.cw_total * 4, CDN_ERR_INVALID, "dw: pitch smaller than channels");
-  DwParams p; memset(&p, 0, sizeof(p));
-  fill_common(p, d, in, in_pitch, out, out_pitch, batch, H, W, in_shift, stride, zx);
-  if (p.total == 0) return 0;
-  const int nw = 8;
-  long long items = ((p.total + (32 / p.lpp) - 1) / (32 / p.lpp)) * p.G;
-  long long blocks = (items + nw - 1) / nw;
-  long long cap = (long long)cdn_num_sms() * 16;
-  if (blocks > cap) blocks = cap;
-  dw3x3_kernel<<<(unsigned)blocks, nw * 32, 0, st>>>(p);
-  CDN_LAUNCH_CHECK("dw3x3_kernel");
+  CDN_CHECK(!in_shift || d.u_ok, CDN_ERR_INVALID, "dw: weights too large for the upsample-folded kernel (sums exceed int8)");
+  DwV2Params p; memset(&p, 0, sizeof(p));
+  p.in = (const uint32_t*)in; p.out = (uint32_t*)out;
+  p.in_pitch_w = in_pitch / 4; p.out_pitch_w = out_pitch / 4;
+  p.Hs = H >> in_shift; p.Ws = W >> in_shift;
+  p.Hout = (H - 1) / stride + 1; p.Wout = (W - 1) / stride + 1;
+  p.cw_total = d.cw_total;
+  const int rows = in_shift ? p.Hs : p.Hout;            // rows a strip walks over
+  p.R = in_shift ? 4 : 8;
+  if (rows < p.R) p.R = rows;
+  p.nstrips = (rows + p.R - 1) / p.R;
+  p.PG = in_shift ? p.Ws : (stride == 2 ? p.Wout : (p.Wout + 1) / 2);
+  p.nthreads = (long long)batch * p.nstrips * p.PG * p.cw_total;
+  p.pad_word = (uint32_t)(uint8_t)(int8_t)(-zx) * 0x01010101u;
+  p.wpk = in_shift ? d.wpku : (stride == 2 ? d.wpk2 : d.wpk1);
+  p.mb = d.mb; p.abm = d.abm; p.M = d.rq.M; p.B = d.rq.B;
+  p.lo_f = (float)d.rq.lo; p.thr = d.thr;
+  if (p.nthreads == 0) return 0;
+  const unsigned blocks = (unsigned)((p.nthreads + 255) / 256);
+  if (in_shift) dw3x3_v2_kernel<1, 1><<<blocks, 256, 0, st>>>(p);
+  else if (stride == 2) dw3x3_v2_kernel<2, 0><<<blocks, 256, 0, st>>>(p);
+  else dw3x3_v2_kernel<1, 0><<<blocks, 256, 0, st>>>(p);
+  CDN_LAUNCH_CHECK("dw3x3_v2_kernel");
   return 0;
 }
 

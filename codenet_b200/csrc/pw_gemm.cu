@@ -126,34 +126,24 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 template <int NCOL>
 __device__ __forceinline__ bool requant_cols_fast(const uint32_t (&acc)[16], const float4* __restrict__ kc, float lo_f,
                                                   float thr, uint32_t (&rb)[16]) {
-  bool bad = false;
+  RqGuard g; rq_guard_init(g);
 #pragma unroll
-  for (int i = 0; i < NCOL; ++i) {
-    const float4 k = kc[i];
-    // (acc + acc_bias) is an integer of magnitude < 2^22, so MAGIC_I + it is the float 1.5*2^23 + it, exactly
-    const float f = __fadd_rn(__int_as_float((int)acc[i] + __float_as_int(k.z)), -CDN_MAGIC_F);
-    float t = __fmaf_rn(f, k.x, k.y);
-    t = fminf(fmaxf(t, lo_f), 127.0f);
-    const float r = __fadd_rn(t, CDN_MAGIC_F);
-    const float kk = __fadd_rn(r, -CDN_MAGIC_F);
-    bad |= fabsf(__fadd_rn(t, -kk)) > thr;
-    rb[i] = __float_as_uint(r);
+  for (int i = 0; i < NCOL; i += 2) {
+    const float4 k0 = kc[i], k1 = kc[i + 1];
+    rb[i] = rq_fast<0>((int)acc[i] + __float_as_int(k0.z), k0.x, k0.y, lo_f, g);
+    rb[i + 1] = rq_fast<1>((int)acc[i + 1] + __float_as_int(k1.z), k1.x, k1.y, lo_f, g);
   }
-  return bad;
+  return rq_group_bad(g, thr);
 }
 
 // exact fp64 re-evaluation of the same NCOL columns (rare)
 template <int NCOL>
 __device__ __forceinline__ void requant_cols_exact(const uint32_t (&acc)[16], const float4* __restrict__ kc, int col,
-                                                const double* __restrict__ Md, const double* __restrict__ Bd, float lo_f,
-                                                uint32_t (&rb)[16]) {
+                                                   const double* __restrict__ Md, const double* __restrict__ Bd, float lo_f,
+                                                   uint32_t (&rb)[16]) {
 #pragma unroll
-  for (int i = 0; i < NCOL; ++i) {
-    const int a = (int)acc[i] + (__float_as_int(kc[i].z) - CDN_MAGIC_I);
-    double td = __dadd_rn(__dmul_rn((double)a, __ldg(Md + col + i)), __ldg(Bd + col + i));
-    td = fmin(fmax(td, (double)lo_f), 127.0);
-    rb[i] = __float_as_uint((float)__double2int_rn(td) + CDN_MAGIC_F);
-  }
+  for (int i = 0; i < NCOL; ++i)
+    rb[i] = rq_exact((int)acc[i] + (__float_as_int(kc[i].z) - CDN_MAGIC_I), __ldg(Md + col + i), __ldg(Bd + col + i), lo_f);
 }
 
 // keep the first nb bytes of a 16-byte vector, zero the rest
