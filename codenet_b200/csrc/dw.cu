@@ -111,49 +111,63 @@ __device__ __noinline__ uint32_t dw_rq_word_exact(int a0, int a1, int a2, int a3
   return pack4_lowbytes(r0, r1, r2, r3);
 }
 
-// one stored row -> per-channel words of NPIX (3 or 4) horizontally adjacent stored pixels starting at xs0
-template <int NPIX>
-__device__ __forceinline__ void dw_load_row(const uint32_t* __restrict__ img, int pitch_w, int Hs, int Ws, int ys, int xs0,
-                                            int xstep, uint32_t pad, uint32_t (&T)[4]) {
-  if ((unsigned)ys >= (unsigned)Hs) { T[0] = T[1] = T[2] = T[3] = pad; return; }
-  const uint32_t* row = img + (size_t)ys * Ws * pitch_w;
+// one stored row -> per-channel words of 4 (or 3) horizontally adjacent stored pixels; xo[j] = word offset of pixel j
+// inside the row or -1 when that pixel is outside the image (or unused)
+__device__ __forceinline__ void dw_load_row(const uint32_t* __restrict__ row, bool yok, const int (&xo)[4], uint32_t pad,
+                                            uint32_t (&T)[4]) {
+  if (!yok) { T[0] = T[1] = T[2] = T[3] = pad; return; }
   uint32_t w[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int xx = xs0 + j * xstep;
-    w[j] = (j < NPIX && (unsigned)xx < (unsigned)Ws) ? __ldg(row + (size_t)xx * pitch_w) : pad;
-  }
+  for (int j = 0; j < 4; ++j) w[j] = xo[j] >= 0 ? __ldg(row + xo[j]) : pad;
   transpose4x4(w[0], w[1], w[2], w[3], T[0], T[1], T[2], T[3]);
 }
 
 template <int STRIDE, int SHIFT>
-__global__ void __launch_bounds__(256) dw3x3_v2_kernel(const DwV2Params p) {
+__global__ void __launch_bounds__(128) dw3x3_v2_kernel(const DwV2Params p) {
   constexpr int NW = DwV2<STRIDE, SHIFT>::NW;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= p.nthreads) return;
-  const int cw = (int)(idx % p.cw_total); long long t = idx / p.cw_total;
-  const int pg = (int)(t % p.PG); t /= p.PG;
-  const int strip = (int)(t % p.nstrips); const long long b = t / p.nstrips;
-  // per-lane constants
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;        // host guarantees nthreads < 2^31
+  if (idx >= (unsigned)p.nthreads) return;
+  const int cw = (int)(idx % (unsigned)p.cw_total); unsigned t = idx / (unsigned)p.cw_total;
+  const int pg = (int)(t % (unsigned)p.PG); t /= (unsigned)p.PG;
+  const int strip = (int)(t % (unsigned)p.nstrips); const int b = (int)(t / (unsigned)p.nstrips);
+  // per-lane constants: 4 channels x NW packed weight words are contiguous (16-byte aligned)
   uint32_t W[4][NW]; DwLane k;
+  {
+    const uint4* wv = (const uint4*)(p.wpk + (size_t)cw * 4 * NW);
+    uint32_t flat[4 * NW];
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    const int ch = cw * 4 + c;
+    for (int i = 0; i < NW; ++i) { const uint4 v = __ldg(wv + i); flat[4 * i] = v.x; flat[4 * i + 1] = v.y; flat[4 * i + 2] = v.z; flat[4 * i + 3] = v.w; }
 #pragma unroll
-    for (int i = 0; i < NW; ++i) W[c][i] = __ldg(p.wpk + (size_t)ch * NW + i);
-    const float2 mb = __ldg(p.mb + ch); k.Mh[c] = mb.x; k.Bh[c] = mb.y; k.abm[c] = __ldg(p.abm + ch);
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int i = 0; i < NW; ++i) W[c][i] = flat[c * NW + i];
+    const float4 m0 = __ldg((const float4*)(p.mb + cw * 4)), m1 = __ldg((const float4*)(p.mb + cw * 4) + 1);
+    k.Mh[0] = m0.x; k.Bh[0] = m0.y; k.Mh[1] = m0.z; k.Bh[1] = m0.w; k.Mh[2] = m1.x; k.Bh[2] = m1.y; k.Mh[3] = m1.z; k.Bh[3] = m1.w;
+    const int4 av = __ldg((const int4*)(p.abm + cw * 4));
+    k.abm[0] = av.x; k.abm[1] = av.y; k.abm[2] = av.z; k.abm[3] = av.w;
   }
-  const uint32_t* img = p.in + (size_t)b * p.Hs * p.Ws * p.in_pitch_w + cw;
+  const int rs_in = p.Ws * p.in_pitch_w;                                 // words per stored input row
+  const uint32_t* img = p.in + (size_t)b * p.Hs * rs_in + cw;
   uint32_t* outb = p.out + (size_t)b * p.Hout * p.Wout * p.out_pitch_w + cw;
   const int ch0 = cw * 4;
+  const int xs0 = (STRIDE == 2 ? 2 * pg : (SHIFT ? pg : 2 * pg)) - 1;     // first stored pixel of the window
+  int xo[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int xx = xs0 + j;
+    xo[j] = ((STRIDE == 2 || SHIFT) && j == 3) || (unsigned)xx >= (unsigned)p.Ws ? -1 : xx * p.in_pitch_w;
+  }
 
   if (STRIDE == 1 && SHIFT == 0) {
     const int x0 = 2 * pg, y0 = strip * p.R, y1 = min(y0 + p.R, p.Hout);
     uint32_t Tm[4], Tc[4], Tp[4];
-    dw_load_row<4>(img, p.in_pitch_w, p.Hs, p.Ws, y0 - 1, x0 - 1, 1, p.pad_word, Tm);
-    dw_load_row<4>(img, p.in_pitch_w, p.Hs, p.Ws, y0, x0 - 1, 1, p.pad_word, Tc);
+    const uint32_t* row = img + (y0 - 1) * rs_in;                          // may point before the image; guarded by yok
+    dw_load_row(row, y0 >= 1, xo, p.pad_word, Tm); row += rs_in;
+    dw_load_row(row, true, xo, p.pad_word, Tc); row += rs_in;
+    uint32_t* o = outb + (y0 * p.Wout + x0) * p.out_pitch_w;
+    const bool two = x0 + 1 < p.Wout;
     for (int y = y0; y < y1; ++y) {
-      dw_load_row<4>(img, p.in_pitch_w, p.Hs, p.Ws, y + 1, x0 - 1, 1, p.pad_word, Tp);
+      dw_load_row(row, y + 1 < p.Hs, xo, p.pad_word, Tp); row += rs_in;
       int a0[4], a1[4];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -166,19 +180,21 @@ __global__ void __launch_bounds__(256) dw3x3_v2_kernel(const DwV2Params p) {
         o0 = dw_rq_word_exact(a0[0], a0[1], a0[2], a0[3], p.M, p.B, ch0, p.lo_f);
         o1 = dw_rq_word_exact(a1[0], a1[1], a1[2], a1[3], p.M, p.B, ch0, p.lo_f);
       }
-      uint32_t* o = outb + ((size_t)y * p.Wout + x0) * p.out_pitch_w;
       o[0] = o0;
-      if (x0 + 1 < p.Wout) o[p.out_pitch_w] = o1;
+      if (two) o[p.out_pitch_w] = o1;
+      o += p.Wout * p.out_pitch_w;
 #pragma unroll
       for (int c = 0; c < 4; ++c) { Tm[c] = Tc[c]; Tc[c] = Tp[c]; }
     }
   } else if (STRIDE == 2) {
-    const int xo = pg, y0 = strip * p.R, y1 = min(y0 + p.R, p.Hout);
+    const int xo_ = pg, y0 = strip * p.R, y1 = min(y0 + p.R, p.Hout);
     uint32_t Tm[4], Tc[4], Tp[4];
-    dw_load_row<3>(img, p.in_pitch_w, p.Hs, p.Ws, 2 * y0 - 1, 2 * xo - 1, 1, p.pad_word, Tm);
+    const uint32_t* row = img + (2 * y0 - 1) * rs_in;
+    dw_load_row(row, y0 >= 1, xo, p.pad_word, Tm); row += rs_in;
+    uint32_t* o = outb + (y0 * p.Wout + xo_) * p.out_pitch_w;
     for (int y = y0; y < y1; ++y) {
-      dw_load_row<3>(img, p.in_pitch_w, p.Hs, p.Ws, 2 * y, 2 * xo - 1, 1, p.pad_word, Tc);
-      dw_load_row<3>(img, p.in_pitch_w, p.Hs, p.Ws, 2 * y + 1, 2 * xo - 1, 1, p.pad_word, Tp);
+      dw_load_row(row, true, xo, p.pad_word, Tc); row += rs_in;
+      dw_load_row(row, 2 * y + 1 < p.Hs, xo, p.pad_word, Tp); row += rs_in;
       int a0[4];
 #pragma unroll
       for (int c = 0; c < 4; ++c)
@@ -186,18 +202,21 @@ __global__ void __launch_bounds__(256) dw3x3_v2_kernel(const DwV2Params p) {
       RqGuard g; rq_guard_init(g);
       uint32_t o0 = dw_rq_word(a0, k, p.lo_f, g);
       if (rq_group_bad(g, p.thr)) o0 = dw_rq_word_exact(a0[0], a0[1], a0[2], a0[3], p.M, p.B, ch0, p.lo_f);
-      outb[((size_t)y * p.Wout + xo) * p.out_pitch_w] = o0;
+      o[0] = o0;
+      o += p.Wout * p.out_pitch_w;
 #pragma unroll
       for (int c = 0; c < 4; ++c) Tm[c] = Tp[c];
     }
   } else {
     // SHIFT 1: stored pixel column s = pg, stored rows r0 .. r1-1 -> output rows 2r, 2r+1 and columns 2s, 2s+1
-    const int s = pg, r0 = strip * p.R, r1 = min(r0 + p.R, p.Hs);
+    const int s_ = pg, r0 = strip * p.R, r1 = min(r0 + p.R, p.Hs);
     uint32_t Tm[4], Tc[4], Tp[4];
-    dw_load_row<3>(img, p.in_pitch_w, p.Hs, p.Ws, r0 - 1, s - 1, 1, p.pad_word, Tm);
-    dw_load_row<3>(img, p.in_pitch_w, p.Hs, p.Ws, r0, s - 1, 1, p.pad_word, Tc);
+    const uint32_t* row = img + (r0 - 1) * rs_in;
+    dw_load_row(row, r0 >= 1, xo, p.pad_word, Tm); row += rs_in;
+    dw_load_row(row, true, xo, p.pad_word, Tc); row += rs_in;
+    uint32_t* o = outb + (2 * r0 * p.Wout + 2 * s_) * p.out_pitch_w;
     for (int r = r0; r < r1; ++r) {
-      dw_load_row<3>(img, p.in_pitch_w, p.Hs, p.Ws, r + 1, s - 1, 1, p.pad_word, Tp);
+      dw_load_row(row, r + 1 < p.Hs, xo, p.pad_word, Tp); row += rs_in;
 #pragma unroll
       for (int yp = 0; yp < 2; ++yp) {
         int a0[4], a1[4];
@@ -213,8 +232,8 @@ __global__ void __launch_bounds__(256) dw3x3_v2_kernel(const DwV2Params p) {
           o0 = dw_rq_word_exact(a0[0], a0[1], a0[2], a0[3], p.M, p.B, ch0, p.lo_f);
           o1 = dw_rq_word_exact(a1[0], a1[1], a1[2], a1[3], p.M, p.B, ch0, p.lo_f);
         }
-        uint32_t* o = outb + ((size_t)(2 * r + yp) * p.Wout + 2 * s) * p.out_pitch_w;
         o[0] = o0; o[p.out_pitch_w] = o1;
+        o += p.Wout * p.out_pitch_w;
       }
 #pragma unroll
       for (int c = 0; c < 4; ++c) { Tm[c] = Tc[c]; Tc[c] = Tp[c]; }
@@ -448,7 +467,7 @@ int dw_launch(const DwDevice& d, const int8_t* in, int in_pitch, int8_t* out, in
   p.Hout = (H - 1) / stride + 1; p.Wout = (W - 1) / stride + 1;
   p.cw_total = d.cw_total;
   const int rows = in_shift ? p.Hs : p.Hout;            // rows a strip walks over
-  p.R = in_shift ? 4 : 8;
+  p.R = stride == 2 ? 8 : 16;
   if (rows < p.R) p.R = rows;
   p.nstrips = (rows + p.R - 1) / p.R;
   p.PG = in_shift ? p.Ws : (stride == 2 ? p.Wout : (p.Wout + 1) / 2);
@@ -458,10 +477,12 @@ int dw_launch(const DwDevice& d, const int8_t* in, int in_pitch, int8_t* out, in
   p.mb = d.mb; p.abm = d.abm; p.M = d.rq.M; p.B = d.rq.B;
   p.lo_f = (float)d.rq.lo; p.thr = d.thr;
   if (p.nthreads == 0) return 0;
-  const unsigned blocks = (unsigned)((p.nthreads + 255) / 256);
-  if (in_shift) dw3x3_v2_kernel<1, 1><<<blocks, 256, 0, st>>>(p);
-  else if (stride == 2) dw3x3_v2_kernel<2, 0><<<blocks, 256, 0, st>>>(p);
-  else dw3x3_v2_kernel<1, 0><<<blocks, 256, 0, st>>>(p);
+  CDN_CHECK(p.nthreads < (1ll << 31) && (long long)p.Hs * p.Ws * p.in_pitch_w < (1ll << 31) &&
+            (long long)p.Hout * p.Wout * p.out_pitch_w < (1ll << 31), CDN_ERR_INVALID, "dw: tensor too large for 32-bit indexing");
+  const unsigned blocks = (unsigned)((p.nthreads + 127) / 128);
+  if (in_shift) dw3x3_v2_kernel<1, 1><<<blocks, 128, 0, st>>>(p);
+  else if (stride == 2) dw3x3_v2_kernel<2, 0><<<blocks, 128, 0, st>>>(p);
+  else dw3x3_v2_kernel<1, 0><<<blocks, 128, 0, st>>>(p);
   CDN_LAUNCH_CHECK("dw3x3_v2_kernel");
   return 0;
 }
