@@ -9,6 +9,7 @@
 // Out-of-image taps contribute REAL zero, i.e. the grid value -zx (a = q + zx = 0); zx*sum(w) is added back
 // exactly through acc_bias.
 #include "layers.cuh"
+#include <algorithm>
 
 struct DwParams {
   const uint32_t* in; uint32_t* out;
@@ -29,6 +30,7 @@ struct DwParams {
   long long acc_s_bias;                      // zx * sum(ws)
   double Ms, bs, ss, zs, u_lo, u_hi;
   float* sval;
+  const float2* mb; const int* abm; float thr_layer;   // lean requantisation constants (v2 kernels)
 };
 
 struct LaneConsts {
@@ -242,117 +244,161 @@ __global__ void __launch_bounds__(128) dw3x3_v2_kernel(const DwV2Params p) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// fused deformable depthwise conv.  MODE 0: integer offsets; MODE 1: bilinear (fp64, follows the oracle's
-// operation order exactly: dcn_deform_conv_cuda_kernel.cu:83-114,210-227 restated on exact integers).
+// fused co-designed deformable depthwise conv (v2).  One CTA works on tiles of DEF_NP consecutive output pixels:
+//   phase A  offset scalar: every warp reduces the C->1 scale conv of its pixels (dp4a + shuffle tree), then ONE
+//            lane per pixel runs the fp64 Hardtanh / QuantAct / (round) chain, so that scalar code is issued once
+//            per 8 pixels instead of once per pixel and channel group; s goes to shared memory
+//   phase C  gather + 3x3 depthwise MAC + requantisation: a warp owns a fixed group of 128 channels (constants in
+//            registers) and walks over the tile's pixels.  MODE 0 (integer offsets): 9 coalesced 128-byte taps,
+//            two byte transposes, 12 dp4a, lean guarded requantisation.  MODE 1 (bilinear): fp64, following the
+//            oracle's operation order exactly (dcn_deform_conv_cuda_kernel.cu:83-114,210-227 on exact integers).
 // ---------------------------------------------------------------------------------------------------------
-template <int MODE, int MAXT>
-__global__ void __launch_bounds__(MAXT) deform_dw_kernel(DwParams p) {
-  extern __shared__ int s_part[];            // [2][pixels_per_iter][G] partial scale dots (G > 1 only)
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  const int g = warp % p.G, slot = warp / p.G, nslots = nw / p.G;
-  const int ppw = 32 / p.lpp, sub = lane / p.lpp, cl = lane % p.lpp;
-  const int cw = g * 32 + cl;
-  const bool active = cw < p.cw_total;
-  LaneConsts k; load_lane_consts(p, cw, active, k);
-  const uint32_t wsw = active ? p.ws[cw] : 0u;
-  const int per_iter = nslots * ppw;
-  int parity = 0;
-  for (long long base = (long long)blockIdx.x * per_iter; base < p.total; base += (long long)gridDim.x * per_iter) {
-    const int pslot = slot * ppw + sub;
-    long long pix = base + pslot;
-    const bool pv = pix < p.total;
-    long long pp = pv ? pix : p.total - 1;
-    int w = (int)(pp % p.Wout); long long t = pp / p.Wout; int h = (int)(t % p.Hout); long long b = t / p.Hout;
-    const uint32_t* img = p.in + (size_t)b * p.Hs * p.Ws * p.in_pitch_w + cw;
-    uint32_t xc = active ? __ldg(img + ((size_t)(h >> p.shift) * p.Ws + (w >> p.shift)) * p.in_pitch_w) : 0u;
-    int part = dp4a_ss(xc, wsw, 0);
-    for (int o = p.lpp >> 1; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    if (p.G > 1) {
-      int* sp = s_part + parity * per_iter * p.G;
-      if (cl == 0) sp[pslot * p.G + g] = part;
-      __syncthreads();
-      part = 0;
-      for (int gg = 0; gg < p.G; ++gg) part += sp[pslot * p.G + gg];
-      parity ^= 1;                            // next iteration writes the other buffer: one barrier per iteration
+#define DEF_NP 64
+
+template <int MODE>
+__global__ void __launch_bounds__(256) deform_dw_v2_kernel(const DwParams p) {
+  __shared__ double s_s[DEF_NP];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rs_in = p.Ws * p.in_pitch_w;
+  // channel-group assignment of this warp in phase C
+  const int Gw = p.G >= 8 ? 8 : (p.G >= 4 ? 4 : (p.G >= 2 ? 2 : 1));
+  const int wg = warp % Gw, wslot = warp / Gw, nslot = 8 / Gw;
+  const long long ntiles = (p.total + DEF_NP - 1) / DEF_NP;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long base = tile * DEF_NP;
+    // ---------------- phase A: s for the tile's pixels ----------------
+    {
+      int mine = 0;
+#pragma unroll 1
+      for (int i = 0; i < DEF_NP / 8; ++i) {
+        const long long pix = base + warp + 8 * i;
+        int part = 0;
+        if (pix < p.total) {
+          const int w = (int)(pix % p.Wout); const long long t = pix / p.Wout; const int h = (int)(t % p.Hout); const long long b = t / p.Hout;
+          const uint32_t* c = p.in + (size_t)b * p.Hs * rs_in + (size_t)(h >> p.shift) * rs_in + (size_t)(w >> p.shift) * p.in_pitch_w;
+          for (int cw = lane; cw < p.cw_total; cw += 32) part = dp4a_ss(__ldg(c + cw), __ldg(p.ws + cw), part);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane == i) mine = part;
+      }
+      if (lane < DEF_NP / 8) {
+        // fp64, mul/add kept separate as in the oracle
+        double u = __dadd_rn(__dmul_rn((double)((long long)mine + p.acc_s_bias), p.Ms), p.bs);
+        u = fmin(fmax(u, p.u_lo), p.u_hi);
+        const double qs = rint(__dsub_rn(__dmul_rn(p.ss, u), p.zs));
+        double s = __ddiv_rn(__dadd_rn(qs, p.zs), p.ss);
+        if (MODE == 0) s = rint(s);
+        s_s[warp + 8 * lane] = s;
+        const long long pix = base + warp + 8 * lane;
+        if (p.sval != nullptr && pix < p.total) p.sval[pix] = (float)s;
+      }
     }
-    // offset scalar (all lanes of the pixel compute it redundantly; fp64, mul/add kept separate as in the oracle)
-    double u = __dadd_rn(__dmul_rn((double)((long long)part + p.acc_s_bias), p.Ms), p.bs);
-    u = fmin(fmax(u, p.u_lo), p.u_hi);
-    double qs = rint(__dsub_rn(__dmul_rn(p.ss, u), p.zs));
-    double s = __ddiv_rn(__dadd_rn(qs, p.zs), p.ss);
-    if (MODE == 0) s = rint(s);
-    if (p.sval != nullptr && pv && g == 0 && cl == 0) p.sval[pix] = (float)s;
-    if (!pv || !active) continue;
-    if (MODE == 0) {
-      const int si = (int)s;
-      uint32_t x[9];
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        int y = h + (i - 1) * si;
-        bool yok = (unsigned)y < (unsigned)p.Hin;
-        const uint32_t* row = img + (size_t)(y >> p.shift) * p.Ws * p.in_pitch_w;
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          int xx = w + (j - 1) * si;
-          bool ok = yok && (unsigned)xx < (unsigned)p.Win;
-          x[i * 3 + j] = (i == 1 && j == 1) ? xc : (ok ? __ldg(row + (size_t)(xx >> p.shift) * p.in_pitch_w) : p.pad_word);
-        }
-      }
-      p.out[(size_t)pix * p.out_pitch_w + cw] = mac9_requant(x, k, p, cw);
-    } else {
-      // bilinear: real values a = q + zx, zero outside the image
-      const int zx = -(int)(int8_t)(p.pad_word & 0xff);
-      const double d = __dsub_rn(s, 1.0);
-      double acc[4] = {0.0, 0.0, 0.0, 0.0};
-      // unpack per-channel tap weights from the packed registers
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        double h_im = __dadd_rn((double)(h - 1 + i), (double)(i - 1) * d);
-        double hl_d = floor(h_im);
-        double lh = __dsub_rn(h_im, hl_d), hh = __dsub_rn(1.0, lh);
-        int hl = (int)hl_d;
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          const int tap = i * 3 + j;
-          double w_im = __dadd_rn((double)(w - 1 + j), (double)(j - 1) * d);
-          bool inside = h_im > -1.0 && w_im > -1.0 && h_im < (double)p.Hin && w_im < (double)p.Win;
-          double wl_d = floor(w_im);
-          double lw = __dsub_rn(w_im, wl_d), hw = __dsub_rn(1.0, lw);
-          int wl = (int)wl_d;
-          double bw[4] = {__dmul_rn(hh, hw), __dmul_rn(hh, lw), __dmul_rn(lh, hw), __dmul_rn(lh, lw)};
-          double val[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-          for (int cnr = 0; cnr < 4; ++cnr) {
-            int yy = hl + (cnr >> 1), xx = wl + (cnr & 1);
-            bool ok = inside && yy >= 0 && yy <= p.Hin - 1 && xx >= 0 && xx <= p.Win - 1;
-            uint32_t word = 0; 
-            if (ok) word = __ldg(img + ((size_t)(yy >> p.shift) * p.Ws + (xx >> p.shift)) * p.in_pitch_w);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              double v = ok ? (double)((int)(int8_t)((word >> (8 * c)) & 0xff) + zx) : 0.0;
-              double term = __dmul_rn(bw[cnr], v);
-              val[c] = (cnr == 0) ? term : __dadd_rn(val[c], term);
-            }
-          }
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint32_t wword = tap < 4 ? k.wA[c] : (tap < 8 ? k.wB[c] : k.wC[c]);
-            int sh = tap < 8 ? 8 * (tap & 3) : 8 * c;
-            double wq = (double)(int)(int8_t)((wword >> sh) & 0xff);
-            acc[c] = __dadd_rn(acc[c], __dmul_rn(wq, val[c]));
-          }
-        }
-      }
-      uint32_t r[4];
+    __syncthreads();
+    // ---------------- phase C: gather, MAC, requantise ----------------
+    for (int g = wg; g < p.G; g += Gw) {
+      const int cw = g * 32 + lane;
+      const bool active = cw < p.cw_total;
+      LaneConsts k; load_lane_consts(p, cw, active, k);
+      float Mh[4], Bh[4]; int abm[4];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        int ch = cw * 4 + c;
-        double td = __dadd_rn(__dmul_rn(acc[c], __ldg(p.M + ch)), __ldg(p.B + ch));
-        td = fmin(fmax(rint(td), (double)p.lo_f), 127.0);
-        r[c] = (uint32_t)((int)td & 0xff);
+        const float2 mb = active ? __ldg(p.mb + cw * 4 + c) : make_float2(0.f, 0.f);
+        Mh[c] = mb.x; Bh[c] = mb.y; abm[c] = active ? __ldg(p.abm + cw * 4 + c) : CDN_MAGIC_I;
       }
-      p.out[(size_t)pix * p.out_pitch_w + cw] = r[0] | (r[1] << 8) | (r[2] << 16) | (r[3] << 24);
+#pragma unroll 1
+      for (int j = wslot; j < DEF_NP; j += nslot) {
+        const long long pix = base + j;
+        if (pix >= p.total || !active) continue;
+        const int w = (int)(pix % p.Wout); const long long t = pix / p.Wout; const int h = (int)(t % p.Hout); const long long b = t / p.Hout;
+        const uint32_t* img = p.in + (size_t)b * p.Hs * rs_in + cw;
+        const double s = s_s[j];
+        if (MODE == 0) {
+          const int si = (int)s;
+          int ro[3], co[3]; bool yok[3], xok[3];
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const int y = h + (i - 1) * si, x = w + (i - 1) * si;
+            yok[i] = (unsigned)y < (unsigned)p.Hin; xok[i] = (unsigned)x < (unsigned)p.Win;
+            ro[i] = (y >> p.shift) * rs_in; co[i] = (x >> p.shift) * p.in_pitch_w;
+          }
+          uint32_t x[9];
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int jj = 0; jj < 3; ++jj)
+              x[i * 3 + jj] = (yok[i] && xok[jj]) ? __ldg(img + ro[i] + co[jj]) : p.pad_word;
+          uint32_t a0, a1, a2, a3, b0, b1, b2, b3;
+          transpose4x4(x[0], x[1], x[2], x[3], a0, a1, a2, a3);
+          transpose4x4(x[4], x[5], x[6], x[7], b0, b1, b2, b3);
+          int acc[4];
+          acc[0] = dp4a_ss(x[8], k.wC[0], dp4a_ss(b0, k.wB[0], dp4a_ss(a0, k.wA[0], abm[0])));
+          acc[1] = dp4a_ss(x[8], k.wC[1], dp4a_ss(b1, k.wB[1], dp4a_ss(a1, k.wA[1], abm[1])));
+          acc[2] = dp4a_ss(x[8], k.wC[2], dp4a_ss(b2, k.wB[2], dp4a_ss(a2, k.wA[2], abm[2])));
+          acc[3] = dp4a_ss(x[8], k.wC[3], dp4a_ss(b3, k.wB[3], dp4a_ss(a3, k.wA[3], abm[3])));
+          RqGuard gd; rq_guard_init(gd);
+          const uint32_t r0 = rq_fast<0>(acc[0], Mh[0], Bh[0], p.lo_f, gd), r1 = rq_fast<1>(acc[1], Mh[1], Bh[1], p.lo_f, gd);
+          const uint32_t r2 = rq_fast<0>(acc[2], Mh[2], Bh[2], p.lo_f, gd), r3 = rq_fast<1>(acc[3], Mh[3], Bh[3], p.lo_f, gd);
+          uint32_t o = pack4_lowbytes(r0, r1, r2, r3);
+          if (rq_group_bad(gd, p.thr_layer)) o = dw_rq_word_exact(acc[0], acc[1], acc[2], acc[3], p.M, p.B, cw * 4, p.lo_f);
+          p.out[(size_t)pix * p.out_pitch_w + cw] = o;
+        } else {
+        // bilinear: real values a = q + zx, zero outside the image
+        const int zx = -(int)(int8_t)(p.pad_word & 0xff);
+        const double d = __dsub_rn(s, 1.0);
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        // unpack per-channel tap weights from the packed registers
+  #pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          double h_im = __dadd_rn((double)(h - 1 + i), (double)(i - 1) * d);
+          double hl_d = floor(h_im);
+          double lh = __dsub_rn(h_im, hl_d), hh = __dsub_rn(1.0, lh);
+          int hl = (int)hl_d;
+  #pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const int tap = i * 3 + j;
+            double w_im = __dadd_rn((double)(w - 1 + j), (double)(j - 1) * d);
+            bool inside = h_im > -1.0 && w_im > -1.0 && h_im < (double)p.Hin && w_im < (double)p.Win;
+            double wl_d = floor(w_im);
+            double lw = __dsub_rn(w_im, wl_d), hw = __dsub_rn(1.0, lw);
+            int wl = (int)wl_d;
+            double bw[4] = {__dmul_rn(hh, hw), __dmul_rn(hh, lw), __dmul_rn(lh, hw), __dmul_rn(lh, lw)};
+            double val[4] = {0.0, 0.0, 0.0, 0.0};
+  #pragma unroll
+            for (int cnr = 0; cnr < 4; ++cnr) {
+              int yy = hl + (cnr >> 1), xx = wl + (cnr & 1);
+              bool ok = inside && yy >= 0 && yy <= p.Hin - 1 && xx >= 0 && xx <= p.Win - 1;
+              uint32_t word = 0; 
+              if (ok) word = __ldg(img + ((size_t)(yy >> p.shift) * p.Ws + (xx >> p.shift)) * p.in_pitch_w);
+  #pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                double v = ok ? (double)((int)(int8_t)((word >> (8 * c)) & 0xff) + zx) : 0.0;
+                double term = __dmul_rn(bw[cnr], v);
+                val[c] = (cnr == 0) ? term : __dadd_rn(val[c], term);
+              }
+            }
+  #pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint32_t wword = tap < 4 ? k.wA[c] : (tap < 8 ? k.wB[c] : k.wC[c]);
+              int sh = tap < 8 ? 8 * (tap & 3) : 8 * c;
+              double wq = (double)(int)(int8_t)((wword >> sh) & 0xff);
+              acc[c] = __dadd_rn(acc[c], __dmul_rn(wq, val[c]));
+            }
+          }
+        }
+        uint32_t r[4];
+  #pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          int ch = cw * 4 + c;
+          double td = __dadd_rn(__dmul_rn(acc[c], __ldg(p.M + ch)), __ldg(p.B + ch));
+          td = fmin(fmax(rint(td), (double)p.lo_f), 127.0);
+          r[c] = (uint32_t)((int)td & 0xff);
+        }
+          p.out[(size_t)pix * p.out_pitch_w + cw] = r[0] | (r[1] << 8) | (r[2] << 16) | (r[3] << 24);
+        }
+      }
     }
+    __syncthreads();                         // s_s is rewritten by the next tile
   }
 }
 
@@ -452,6 +498,7 @@ static void fill_common(DwParams& p, const DwDevice& d, const int8_t* in, int in
   p.lo_f = (float)d.rq.lo;
   p.acc_s_bias = d.acc_s_bias;
   p.sval = nullptr;
+  p.mb = d.mb; p.abm = d.abm; p.thr_layer = d.thr;
 }
 
 int dw_launch(const DwDevice& d, const int8_t* in, int in_pitch, int8_t* out, int out_pitch, int batch, int H, int W,
@@ -499,20 +546,12 @@ int deform_launch(const DwDevice& d, const cdn_deform_scale* sc, const int8_t* i
   p.u_lo = (double)(-sc->bound + 1); p.u_hi = (double)sc->bound;
   p.sval = sval;
   if (p.total == 0) return 0;
-  CDN_CHECK(p.G <= 32, CDN_ERR_INVALID, "deform: more than 4096 channels not supported");
-  int nw = 8; if (p.G > 8) nw = p.G; else nw = (8 / p.G) * p.G;
-  int per_iter = (nw / p.G) * (32 / p.lpp);
-  long long blocks = (p.total + per_iter - 1) / per_iter;
-  long long cap = (long long)cdn_num_sms() * (nw > 16 ? 2 : 8);
-  if (blocks > cap) blocks = cap;
-  size_t smem = p.G > 1 ? (size_t)2 * per_iter * p.G * sizeof(int) : 0;
-  if (nw <= 8) {
-    if (sc->mode == 0) deform_dw_kernel<0, 256><<<(unsigned)blocks, nw * 32, smem, st>>>(p);
-    else deform_dw_kernel<1, 256><<<(unsigned)blocks, nw * 32, smem, st>>>(p);
-  } else {
-    if (sc->mode == 0) deform_dw_kernel<0, 1024><<<(unsigned)blocks, nw * 32, smem, st>>>(p);
-    else deform_dw_kernel<1, 1024><<<(unsigned)blocks, nw * 32, smem, st>>>(p);
-  }
-  CDN_LAUNCH_CHECK("deform_dw_kernel");
+  CDN_CHECK((long long)p.Hs * p.Ws * p.in_pitch_w < (1ll << 31), CDN_ERR_INVALID, "deform: image too large for 32-bit indexing");
+  const long long ntiles = (p.total + DEF_NP - 1) / DEF_NP;
+  const long long cap = (long long)cdn_num_sms() * 8;
+  const unsigned blocks = (unsigned)std::min(ntiles, cap);
+  if (sc->mode == 0) deform_dw_v2_kernel<0><<<blocks, 256, 0, st>>>(p);
+  else deform_dw_v2_kernel<1><<<blocks, 256, 0, st>>>(p);
+  CDN_LAUNCH_CHECK("deform_dw_v2_kernel");
   return 0;
 }

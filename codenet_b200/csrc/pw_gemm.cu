@@ -22,7 +22,12 @@
 #define PW_BM 128
 #define PW_BK 128
 #define PW_MAX_BN 256
-#define PW_EPI_WARPS 8
+#ifndef PW_EPI_WARPS
+#define PW_EPI_WARPS 16
+#endif
+#define PW_EPI_GROUPS 2                      // independent epilogue groups working on alternate tiles (antiphase)
+#define PW_GROUP_THREADS (32 * PW_EPI_WARPS / PW_EPI_GROUPS)
+#define PW_EPI_PARTS (PW_EPI_WARPS / PW_EPI_GROUPS / 4)
 #define PW_EPI_THREADS (32 * PW_EPI_WARPS)
 #define PW_THREADS (64 + PW_EPI_THREADS)
 #define PW_MAX_STAGES 8
@@ -32,7 +37,7 @@
 struct PwSeg { int seg, cb, ce, pad; };       // output segment (128-byte column of the out tensor) and its chunk range
 
 struct PwParams {
-  int num_k_blocks, k_off, BN, n_tiles, stages, has_pass, pass_segs, nbuf, resident, n_chunks, n_segs;
+  int num_k_blocks, k_off, BN, n_tiles, stages, has_pass, pass_segs, pass_bufs, nbuf, resident, n_chunks, n_segs;
   long long m_tiles, pixels;
   const cdn_pw_chunk* chunks;                // sorted by (N tile, output segment)
   const PwSeg* segs; const int* tile_seg;    // tile_seg[n_tiles + 1]: first PwSeg of every N tile
@@ -198,8 +203,8 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint8_t* s_B = smem;
   uint8_t* s_ring = s_B + (p.resident ? (size_t)p.num_k_blocks * Ntot * PW_BK : 0);
   uint8_t* s_pass = s_ring + (size_t)p.stages * stage_bytes;
-  uint8_t* s_out = s_pass + (size_t)2 * p.pass_segs * 16384;
-  float4* s_kc = (float4*)(s_out + (size_t)p.nbuf * 16384);
+  uint8_t* s_out = s_pass + (size_t)p.pass_bufs * p.pass_segs * 16384;
+  float4* s_kc = (float4*)(s_out + (size_t)PW_EPI_GROUPS * p.nbuf * 16384);
   cdn_pw_chunk* s_chunks = (cdn_pw_chunk*)(s_kc + Ntot);
   PwSeg* s_segs = (PwSeg*)(s_chunks + ((p.n_chunks + 1) & ~1));
   int* s_tile_seg = (int*)(s_segs + p.n_segs);
@@ -220,8 +225,8 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(TFULL(s), 1); mbar_init(TEMPTY(s), PW_EPI_THREADS);
-      mbar_init(PFULL(s), 1); mbar_init(PEMPTY(s), PW_EPI_THREADS);
+      mbar_init(TFULL(s), 1); mbar_init(TEMPTY(s), PW_GROUP_THREADS);
+      mbar_init(PFULL(s), 1); mbar_init(PEMPTY(s), PW_GROUP_THREADS);
     }
     mbar_init(BFULL, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -243,7 +248,7 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const long long total_tiles = p.m_tiles * p.n_tiles;
+  const unsigned total_tiles = (unsigned)(p.m_tiles * p.n_tiles);   // host guarantees < 2^31
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -255,10 +260,10 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tma_load_2d(smem_u32(s_B + ((size_t)kb * Ntot + (size_t)nt * p.BN) * PW_BK), &tmB, kb * PW_BK, nt * p.BN, BFULL);
       }
       int stage = 0; uint32_t phase = 0; uint32_t it = 0;
-      for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const long long mt = tile / p.n_tiles; const int nt = (int)(tile % p.n_tiles);
+      for (unsigned tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const unsigned mt = tile / (unsigned)p.n_tiles; const int nt = (int)(tile % (unsigned)p.n_tiles);
         if (p.has_pass) {
-          const int pb = it & 1; const uint32_t pph = (it >> 1) & 1;
+          const int pb = (int)(it % (uint32_t)p.pass_bufs); const uint32_t pph = (it / (uint32_t)p.pass_bufs) & 1;
           mbar_wait(PEMPTY(pb), pph ^ 1);
           mbar_expect_tx(PFULL(pb), (uint32_t)p.pass_segs * 16384u);
           for (int s = 0; s < p.pass_segs; ++s)
@@ -286,8 +291,8 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(PW_BM >> 4) << 24);
       if (p.resident) { mbar_wait(BFULL, 0); tc_fence_after(); }
       int stage = 0; uint32_t phase = 0; uint32_t it = 0;
-      for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int nt = (int)(tile % p.n_tiles);
+      for (unsigned tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int nt = (int)(tile % (unsigned)p.n_tiles);
         const int as = it & 1; const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(TEMPTY(as), aphase ^ 1);
         tc_fence_after();
@@ -308,24 +313,32 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else {
-    // ===================== epilogue (warps 2..9) =====================
+    // ===================== epilogue (warps 2..17) =====================
+    // Two independent groups of 8 warps: group g owns TMEM accumulator stage g, pass buffer g and its own staging
+    // buffers, and handles every other tile of this CTA, so one group's latency phases (barrier waits, TMEM /
+    // shared-memory loads, the TMA store hand-off) overlap the other group's arithmetic.
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;          // which of the two warps of the quarter
+    const int grp = (warp - 2) / (PW_EPI_WARPS / PW_EPI_GROUPS);
+    const int half = ((warp - 2) >> 2) % PW_EPI_PARTS;   // which of the PW_EPI_PARTS warps of the quarter (inside the group)
     const int row = q * 32 + lane;             // row inside the tile
-    const int et = threadIdx.x - 64;           // 0..255
-    uint32_t it = 0, g = 0;                    // tiles / output segments done by this CTA
-    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const long long mt = tile / p.n_tiles; const int nt = (int)(tile % p.n_tiles);
-      const int as = it & 1; const uint32_t aphase = (it >> 1) & 1;
+    const int gt = (threadIdx.x - 64) % PW_GROUP_THREADS;
+    const int as = grp;
+    uint8_t* const s_out_g = s_out + (size_t)grp * p.nbuf * 16384;
+    uint32_t it2 = 0, g = 0;                   // tiles / output segments done by this group
+    for (unsigned tile = blockIdx.x + grp * gridDim.x; tile < total_tiles; tile += PW_EPI_GROUPS * gridDim.x, ++it2) {
+      const unsigned mt = tile / (unsigned)p.n_tiles; const int nt = (int)(tile % (unsigned)p.n_tiles);
+      const uint32_t aphase = it2 & 1;
       mbar_wait(TFULL(as), aphase);
       tc_fence_after();
-      if (p.has_pass) mbar_wait(PFULL(as), aphase);
+      const uint32_t itg = it2 * PW_EPI_GROUPS + grp;                     // CTA-wide tile counter (as the producer counts)
+      const int pb = (int)(itg % (uint32_t)p.pass_bufs);
+      if (p.has_pass) mbar_wait(PFULL(pb), (itg / (uint32_t)p.pass_bufs) & 1);
       const uint32_t tacc = tmem_base + (uint32_t)(as * PW_MAX_BN) + ((uint32_t)(q * 32) << 16);
       if (p.n_f32 > 0) {
         // fp32 NCHW planes: out[img][n][pix] = fl32(fl64(acc*Mf[n]) + bf[n])
-        const long long pix = mt * PW_BM + row;
-        const long long img = pix / p.ppi; const int pi = (int)(pix - img * p.ppi);
-        for (int c0 = half * 16; c0 < p.BN; c0 += 32) {
+        const unsigned pix = mt * PW_BM + row;
+        const unsigned img = pix / (unsigned)p.ppi; const int pi = (int)(pix - img * (unsigned)p.ppi);
+        for (int c0 = half * 16; c0 < p.BN; c0 += 16 * PW_EPI_PARTS) {
           uint32_t acc[16];
           tmem_ld16(tacc + (uint32_t)c0, acc);
           tmem_ld_wait();
@@ -344,12 +357,12 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tc_fence_before();
         mbar_arrive(TEMPTY(as));
       } else {
-        const uint8_t* pass_row = s_pass + (size_t)as * p.pass_segs * 16384 + row * 128;
+        const uint8_t* pass_row = s_pass + (size_t)pb * p.pass_segs * 16384 + row * 128;
         const int sg0 = s_tile_seg[nt], sg1 = s_tile_seg[nt + 1];
         for (int sg = sg0; sg < sg1; ++sg, ++g) {
           const PwSeg S = s_segs[sg];
-          uint8_t* stg = s_out + (size_t)(g % (uint32_t)p.nbuf) * 16384 + row * 128;
-          for (int c = S.cb + half; c < S.ce; c += 2) {
+          uint8_t* stg = s_out_g + (size_t)(g % (uint32_t)p.nbuf) * 16384 + row * 128;
+          for (int c = S.cb + half; c < S.ce; c += PW_EPI_PARTS) {
             const cdn_pw_chunk ck = s_chunks[c];
             uint32_t acc[16];
             uint32_t pass_lo = 0, pass_hi = 0;
@@ -376,12 +389,12 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (sg + 1 == sg1) {                 // last TMEM / pass read of this tile is behind us
             tc_fence_before();
             mbar_arrive(TEMPTY(as));
-            if (p.has_pass) mbar_arrive(PEMPTY(as));
+            if (p.has_pass) mbar_arrive(PEMPTY(pb));
           }
           fence_async_smem();
-          named_bar_sync(1, PW_EPI_THREADS);
-          if (et == 0) {
-            tma_store_2d(&tmO, S.seg * 128, (int)(mt * PW_BM), smem_u32(s_out + (size_t)(g % (uint32_t)p.nbuf) * 16384));
+          named_bar_sync(1 + grp, PW_GROUP_THREADS);
+          if (gt == 0) {
+            tma_store_2d(&tmO, S.seg * 128, (int)(mt * PW_BM), smem_u32(s_out_g + (size_t)(g % (uint32_t)p.nbuf) * 16384));
             tma_store_commit();
             // before anyone passes the NEXT barrier, the store that used the buffer after next must have drained
             if (p.nbuf >= 3) tma_store_wait_read1(); else tma_store_wait_read0();
@@ -389,7 +402,7 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       }
     }
-    if (et == 0) tma_store_wait_all();
+    if (gt == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -591,29 +604,24 @@ int pw_device_build(PwDevice& d, const cdn_pw_desc* desc, int pass_pitch) {
   const size_t b_blk = ((size_t)d.BN * PW_BK + 1023) & ~(size_t)1023;
   const size_t b_all = (size_t)d.num_k_blocks * Np * PW_BK;
   const size_t tables = (size_t)Np * 16 + (size_t)((d.n_chunks + 1) & ~1) * 8 + (size_t)d.n_segs * 16 + (size_t)((d.n_tiles + 1 + 3) & ~3) * 4 + 32 * 8;
-  auto plan = [&](bool resident, int nbuf, int& stages) {
-    const size_t fixed = 1024 + (resident ? b_all : 0) + (size_t)2 * d.pass_segs * 16384 + (size_t)nbuf * 16384 + tables;
+  auto plan = [&](bool resident, int pass_bufs, int nbuf, int& stages) {
+    const size_t fixed = 1024 + (resident ? b_all : 0) + (size_t)pass_bufs * d.pass_segs * 16384 + (size_t)PW_EPI_GROUPS * nbuf * 16384 + tables;
     const size_t stage_bytes = 16384 + (resident ? 0 : b_blk);
     if (fixed + 2 * stage_bytes > PW_SMEM_LIMIT) { stages = 0; return (size_t)0; }
     stages = (int)std::min<size_t>(PW_MAX_STAGES, (PW_SMEM_LIMIT - fixed) / stage_bytes);
     return fixed + (size_t)stages * stage_bytes;
   };
-  const int want_buf = d.n_f32 > 0 ? 0 : 3;
-  int stages = 0; size_t bytes = 0;
-  d.resident = 0;
-  // prefer resident weights with at least two tiles' worth of activation stages in flight
-  for (int nbuf = want_buf; nbuf >= (d.n_f32 > 0 ? 0 : 2) && !d.resident; --nbuf) {
-    bytes = plan(true, nbuf, stages);
-    if (stages >= std::max(2, 2 * d.num_k_blocks) || (stages >= 2 && d.num_k_blocks > 4)) { d.resident = 1; d.nbuf = nbuf; }
-    if (d.n_f32 > 0) break;
-  }
-  if (!d.resident) {
-    for (int nbuf = want_buf; nbuf >= (d.n_f32 > 0 ? 0 : 2); --nbuf) {
-      bytes = plan(false, nbuf, stages);
-      if (stages >= 2) { d.nbuf = nbuf; break; }
-      if (d.n_f32 > 0) break;
-    }
-  }
+  // preference: resident weights, double-buffered pass tile, and at least two tiles' worth of activation stages;
+  // relax one requirement at a time until the layer fits
+  const int nbuf = d.n_f32 > 0 ? 0 : 2;
+  int stages = 0; size_t bytes = 0; bool found = false;
+  for (int want = 2; want >= 0 && !found; --want)            // tiles in flight we insist on (0: anything that runs)
+    for (int resident = 1; resident >= 0 && !found; --resident)
+      for (int pass_bufs = d.has_pass ? 2 : 1; pass_bufs >= 1 && !found; --pass_bufs) {
+        int st = 0; const size_t by = plan(resident != 0, pass_bufs, nbuf, st);
+        const int need = std::max(2, std::min(want * d.num_k_blocks, want == 2 ? 8 : 3));
+        if (st >= need) { found = true; stages = st; bytes = by; d.resident = resident; d.pass_bufs = pass_bufs; d.nbuf = nbuf; }
+      }
   CDN_CHECK(stages >= 2, CDN_ERR_INVALID, "pw: layer does not fit in shared memory (K=%d N=%d BN=%d pass segs=%d)", d.K, d.N, d.BN, d.pass_segs);
   d.stages = stages;
   d.smem_bytes = bytes;
@@ -639,7 +647,7 @@ int pw_launch(const PwDevice& d, const int8_t* in, int in_pitch, long long pixel
   CDN_CHECK(d.n_f32 > 0 ? (out_f32 != nullptr && ppi > 0) : (out != nullptr), CDN_ERR_INVALID, "pw: missing output pointer");
   PwParams p; memset(&p, 0, sizeof(p));
   p.num_k_blocks = d.num_k_blocks; p.k_off = d.k_off; p.BN = d.BN; p.n_tiles = d.n_tiles; p.stages = d.stages;
-  p.has_pass = d.has_pass; p.pass_segs = d.pass_segs; p.nbuf = d.nbuf; p.resident = d.resident;
+  p.has_pass = d.has_pass; p.pass_segs = d.pass_segs; p.pass_bufs = d.pass_bufs; p.nbuf = d.nbuf; p.resident = d.resident;
   p.n_chunks = d.n_chunks; p.n_segs = d.n_segs;
   p.m_tiles = (pixels + PW_BM - 1) / PW_BM; p.pixels = pixels;
   p.chunks = d.chunks; p.segs = (const PwSeg*)d.segs; p.tile_seg = d.tile_seg; p.kc = (const float4*)d.kc;
@@ -663,6 +671,7 @@ int pw_launch(const PwDevice& d, const int8_t* in, int in_pitch, long long pixel
   else o = a;
   if (int r = pw_init_attrs()) return r;
   long long tiles = p.m_tiles * p.n_tiles;
+  CDN_CHECK(tiles < (1ll << 31) && pixels < (1ll << 31), CDN_ERR_INVALID, "pw: too many pixels for 32-bit tile indexing");
   int grid = (int)std::min<long long>(tiles, cdn_num_sms());
   pw_gemm_tc_kernel<<<grid, PW_THREADS, d.smem_bytes, st>>>(a, d.tmB, pm, o, p);
   CDN_LAUNCH_CHECK("pw_gemm_tc_kernel");
