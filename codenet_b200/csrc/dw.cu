@@ -258,6 +258,8 @@ __global__ void __launch_bounds__(128) dw3x3_v2_kernel(const DwV2Params p) {
 template <int MODE>
 __global__ void __launch_bounds__(256) deform_dw_v2_kernel(const DwParams p) {
   __shared__ double s_s[DEF_NP];
+  __shared__ uint32_t s_hw[DEF_NP];
+  __shared__ int s_b[DEF_NP];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rs_in = p.Ws * p.in_pitch_w;
   // channel-group assignment of this warp in phase C
@@ -268,19 +270,24 @@ __global__ void __launch_bounds__(256) deform_dw_v2_kernel(const DwParams p) {
     const long long base = tile * DEF_NP;
     // ---------------- phase A: s for the tile's pixels ----------------
     {
-      int mine = 0;
+      int mine = 0; uint32_t my_hw = 0; int my_b = 0;
+      // pixel coordinates advance incrementally (one division per warp and tile)
+      const unsigned pix0 = (unsigned)base + warp;
+      int w = (int)(pix0 % (unsigned)p.Wout); unsigned t0 = pix0 / (unsigned)p.Wout;
+      int h = (int)(t0 % (unsigned)p.Hout); int b = (int)(t0 / (unsigned)p.Hout);
 #pragma unroll 1
       for (int i = 0; i < DEF_NP / 8; ++i) {
         const long long pix = base + warp + 8 * i;
         int part = 0;
         if (pix < p.total) {
-          const int w = (int)(pix % p.Wout); const long long t = pix / p.Wout; const int h = (int)(t % p.Hout); const long long b = t / p.Hout;
-          const uint32_t* c = p.in + (size_t)b * p.Hs * rs_in + (size_t)(h >> p.shift) * rs_in + (size_t)(w >> p.shift) * p.in_pitch_w;
+          const uint32_t* c = p.in + (size_t)b * p.Hs * rs_in + (h >> p.shift) * rs_in + (w >> p.shift) * p.in_pitch_w;
           for (int cw = lane; cw < p.cw_total; cw += 32) part = dp4a_ss(__ldg(c + cw), __ldg(p.ws + cw), part);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-        if (lane == i) mine = part;
+        if (lane == i) { mine = part; my_hw = ((uint32_t)h << 16) | (uint32_t)w; my_b = b; }
+        w += 8;
+        while (w >= p.Wout) { w -= p.Wout; if (++h == p.Hout) { h = 0; ++b; } }
       }
       if (lane < DEF_NP / 8) {
         // fp64, mul/add kept separate as in the oracle
@@ -290,6 +297,7 @@ __global__ void __launch_bounds__(256) deform_dw_v2_kernel(const DwParams p) {
         double s = __ddiv_rn(__dadd_rn(qs, p.zs), p.ss);
         if (MODE == 0) s = rint(s);
         s_s[warp + 8 * lane] = s;
+        s_hw[warp + 8 * lane] = my_hw; s_b[warp + 8 * lane] = my_b;
         const long long pix = base + warp + 8 * lane;
         if (p.sval != nullptr && pix < p.total) p.sval[pix] = (float)s;
       }
@@ -310,8 +318,9 @@ __global__ void __launch_bounds__(256) deform_dw_v2_kernel(const DwParams p) {
       for (int j = wslot; j < DEF_NP; j += nslot) {
         const long long pix = base + j;
         if (pix >= p.total || !active) continue;
-        const int w = (int)(pix % p.Wout); const long long t = pix / p.Wout; const int h = (int)(t % p.Hout); const long long b = t / p.Hout;
-        const uint32_t* img = p.in + (size_t)b * p.Hs * rs_in + cw;
+        const uint32_t hw = s_hw[j];
+        const int w = (int)(hw & 0xffffu), h = (int)(hw >> 16);
+        const uint32_t* img = p.in + (size_t)s_b[j] * p.Hs * rs_in + cw;
         const double s = s_s[j];
         if (MODE == 0) {
           const int si = (int)s;
@@ -546,7 +555,8 @@ int deform_launch(const DwDevice& d, const cdn_deform_scale* sc, const int8_t* i
   p.u_lo = (double)(-sc->bound + 1); p.u_hi = (double)sc->bound;
   p.sval = sval;
   if (p.total == 0) return 0;
-  CDN_CHECK((long long)p.Hs * p.Ws * p.in_pitch_w < (1ll << 31), CDN_ERR_INVALID, "deform: image too large for 32-bit indexing");
+  CDN_CHECK((long long)p.Hs * p.Ws * p.in_pitch_w < (1ll << 31) && p.total < (1ll << 31) && p.Hout < 65536 && p.Wout < 65536,
+            CDN_ERR_INVALID, "deform: tensor too large for 32-bit indexing");
   const long long ntiles = (p.total + DEF_NP - 1) / DEF_NP;
   const long long cap = (long long)cdn_num_sms() * 8;
   const unsigned blocks = (unsigned)std::min(ntiles, cap);
