@@ -27,9 +27,51 @@ struct DecParams {
   const float* hm; const float* wh; const float* reg;
   long long hm_is, wh_is, reg_is;            // per-image strides (elements)
   int cat, H, W, K;
+  int is_prob;                               // heat map holds probabilities (reference API) instead of logits
   unsigned long long* list;                  // [batch][cat*H*W] peak composites
+  unsigned int* counts;                      // [batch] peaks found by ctdet_peaks_kernel (reset by the select kernel)
   float* dets; int32_t* inds;
 };
+
+// Phase 1 as its own grid-wide kernel: one thread per heat-map element (all images), warp-aggregated append to the
+// image's peak list.  The list order is arbitrary; the selection below orders by the (unique) composite value.
+__global__ void __launch_bounds__(256) ctdet_peaks_kernel(DecParams p, int batch) {
+  const int HW = p.H * p.W;
+  const unsigned n = (unsigned)p.cat * HW;                   // elements per image (< 2^31, checked on the host)
+  const unsigned e = blockIdx.x * 256u + threadIdx.x;        // grid.y = image
+  const int b = blockIdx.y, lane = threadIdx.x & 31;
+  bool peak = false; float v = 0.f;
+  if (e < n) {
+    const int sp = (int)(e % (unsigned)HW); const int y = sp / p.W, x = sp - y * p.W;
+    const float* plane = p.hm + (size_t)b * p.hm_is + (e - sp);
+    v = __ldg(plane + sp);
+    peak = (v == v);                                         // NaN never is a peak
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int yy = y + dy; if ((unsigned)yy >= (unsigned)p.H) continue;
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int xx = x + dx; if ((dx | dy) == 0 || (unsigned)xx >= (unsigned)p.W) continue;
+        if (__ldg(plane + yy * p.W + xx) > v) peak = false;
+      }
+    }
+  }
+  // block-aggregated append: one global atomic per block (per-warp atomics on 256 counters serialise in L2)
+  __shared__ unsigned s_wcnt[8], s_base;
+  const unsigned m = __ballot_sync(0xffffffffu, peak);
+  const int warp = threadIdx.x >> 5;
+  if (lane == 0) s_wcnt[warp] = __popc(m);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned tot = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { const unsigned c = s_wcnt[w]; s_wcnt[w] = tot; tot += c; }
+    s_base = tot ? atomicAdd(p.counts + b, tot) : 0u;
+  }
+  __syncthreads();
+  if (peak) p.list[(size_t)b * n + s_base + s_wcnt[warp] + __popc(m & ((1u << lane) - 1u))] =
+      ((unsigned long long)f2key(v) << 32) | (unsigned long long)(0xffffffffu - e);
+}
 
 __global__ void __launch_bounds__(DEC_THREADS) ctdet_decode_kernel(DecParams p) {
   __shared__ unsigned int hist[DEC_BINS];
@@ -45,38 +87,7 @@ __global__ void __launch_bounds__(DEC_THREADS) ctdet_decode_kernel(DecParams p) 
   const float* hm = p.hm + (size_t)b * p.hm_is;
   unsigned long long* list = p.list + (size_t)b * n;
 
-  if (tid == 0) { s_count = 0; s_nsel = 0; }
-  __syncthreads();
-
-  // ---- phase 1: peaks -> list ------------------------------------------------------------------------
-  for (long long base = 0; base < n; base += DEC_THREADS) {
-    long long e = base + tid;
-    bool peak = false; float v = 0.f;
-    if (e < n) {
-      int sp = (int)(e % HW); int y = sp / p.W, x = sp - y * p.W;
-      const float* plane = hm + (e - sp);
-      v = __ldg(plane + sp);
-      peak = true;
-#pragma unroll
-      for (int dy = -1; dy <= 1; ++dy) {
-        int yy = y + dy; if ((unsigned)yy >= (unsigned)p.H) continue;
-#pragma unroll
-        for (int dx = -1; dx <= 1; ++dx) {
-          int xx = x + dx; if ((dx | dy) == 0 || (unsigned)xx >= (unsigned)p.W) continue;
-          if (__ldg(plane + yy * p.W + xx) > v) peak = false;
-        }
-      }
-      if (v != v) peak = false;              // NaN never is a peak
-    }
-    unsigned m = __ballot_sync(0xffffffffu, peak);
-    if (m) {
-      unsigned pos = 0;
-      if (lane == 0) pos = atomicAdd(&s_count, __popc(m));
-      pos = __shfl_sync(0xffffffffu, pos, 0);
-      if (peak) list[pos + __popc(m & ((1u << lane) - 1u))] =
-          ((unsigned long long)f2key(v) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)e);
-    }
-  }
+  if (tid == 0) { s_count = p.counts[b]; s_nsel = 0; }
   __syncthreads();
   const unsigned int count = s_count;
   const unsigned int Ksel = min((unsigned)p.K, count);
@@ -160,7 +171,7 @@ __global__ void __launch_bounds__(DEC_THREADS) ctdet_decode_kernel(DecParams p) 
       else { xs += 0.5f; ys += 0.5f; }
       float w = p.wh[(size_t)b * p.wh_is + sp], h = p.wh[(size_t)b * p.wh_is + HW + sp];
       d[0] = xs - w / 2; d[1] = ys - h / 2; d[2] = xs + w / 2; d[3] = ys + h / 2;
-      d[4] = (float)(1.0 / (1.0 + exp(-(double)logit)));
+      d[4] = p.is_prob ? logit : (float)(1.0 / (1.0 + exp(-(double)logit)));
       d[5] = (float)cls;
       if (p.inds) p.inds[(size_t)b * p.K + i] = (int32_t)flat;
     } else {
@@ -171,13 +182,18 @@ __global__ void __launch_bounds__(DEC_THREADS) ctdet_decode_kernel(DecParams p) 
 }
 
 int decode_launch(const float* hm, long long hm_img_stride, const float* wh, long long wh_img_stride, const float* reg,
-                  long long reg_img_stride, int batch, int cat, int H, int W, int K, unsigned long long* scratch,
-                  float* dets, int32_t* inds, cudaStream_t st) {
+                  long long reg_img_stride, int batch, int cat, int H, int W, int K, int is_prob,
+                  unsigned long long* scratch, unsigned int* counts, float* dets, int32_t* inds, cudaStream_t st) {
   CDN_CHECK(K >= 1 && K <= DEC_MAXK, CDN_ERR_INVALID, "decode: K=%d must be in 1..%d", K, DEC_MAXK);
   CDN_CHECK(cat >= 1 && H >= 1 && W >= 1 && (long long)cat * H * W < (1ll << 31), CDN_ERR_INVALID, "decode: bad shape");
-  CDN_CHECK(hm && wh && dets && scratch, CDN_ERR_INVALID, "decode: null pointer");
+  CDN_CHECK(hm && wh && dets && scratch && counts, CDN_ERR_INVALID, "decode: null pointer");
+  CDN_CHECK(batch <= 65535, CDN_ERR_INVALID, "decode: batch %d exceeds 65535", batch);
   if (batch == 0) return 0;
-  DecParams p{hm, wh, reg, hm_img_stride, wh_img_stride, reg_img_stride, cat, H, W, K, scratch, dets, inds};
+  DecParams p{hm, wh, reg, hm_img_stride, wh_img_stride, reg_img_stride, cat, H, W, K, is_prob, scratch, counts, dets, inds};
+  CDN_CUDA(cudaMemsetAsync(counts, 0, (size_t)batch * sizeof(unsigned int), st));
+  const unsigned n = (unsigned)cat * H * W;
+  ctdet_peaks_kernel<<<dim3((n + 255) / 256, batch), 256, 0, st>>>(p, batch);
+  CDN_LAUNCH_CHECK("ctdet_peaks_kernel");
   ctdet_decode_kernel<<<batch, DEC_THREADS, 0, st>>>(p);
   CDN_LAUNCH_CHECK("ctdet_decode_kernel");
   return 0;

@@ -259,7 +259,8 @@ template <int MODE>
 __global__ void __launch_bounds__(256) deform_dw_v2_kernel(const DwParams p) {
   __shared__ double s_s[DEF_NP];
   __shared__ uint32_t s_hw[DEF_NP];
-  __shared__ int s_b[DEF_NP];
+  __shared__ int s_b[DEF_NP];                  // word offset of the pixel's image
+  __shared__ int s_si[DEF_NP];                 // integer offset scalar (MODE 0)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rs_in = p.Ws * p.in_pitch_w;
   // channel-group assignment of this warp in phase C
@@ -281,7 +282,13 @@ __global__ void __launch_bounds__(256) deform_dw_v2_kernel(const DwParams p) {
         int part = 0;
         if (pix < p.total) {
           const uint32_t* c = p.in + (size_t)b * p.Hs * rs_in + (h >> p.shift) * rs_in + (w >> p.shift) * p.in_pitch_w;
-          for (int cw = lane; cw < p.cw_total; cw += 32) part = dp4a_ss(__ldg(c + cw), __ldg(p.ws + cw), part);
+          int cw = lane;
+          for (; cw + 96 < p.cw_total; cw += 128) {            // 4 independent loads in flight
+            const uint32_t x0 = __ldg(c + cw), x1 = __ldg(c + cw + 32), x2 = __ldg(c + cw + 64), x3 = __ldg(c + cw + 96);
+            part = dp4a_ss(x0, __ldg(p.ws + cw), part); part = dp4a_ss(x1, __ldg(p.ws + cw + 32), part);
+            part = dp4a_ss(x2, __ldg(p.ws + cw + 64), part); part = dp4a_ss(x3, __ldg(p.ws + cw + 96), part);
+          }
+          for (; cw < p.cw_total; cw += 32) part = dp4a_ss(__ldg(c + cw), __ldg(p.ws + cw), part);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
@@ -297,7 +304,7 @@ __global__ void __launch_bounds__(256) deform_dw_v2_kernel(const DwParams p) {
         double s = __ddiv_rn(__dadd_rn(qs, p.zs), p.ss);
         if (MODE == 0) s = rint(s);
         s_s[warp + 8 * lane] = s;
-        s_hw[warp + 8 * lane] = my_hw; s_b[warp + 8 * lane] = my_b;
+        s_hw[warp + 8 * lane] = my_hw; s_b[warp + 8 * lane] = my_b * p.Hs * rs_in; s_si[warp + 8 * lane] = (int)s;
         const long long pix = base + warp + 8 * lane;
         if (p.sval != nullptr && pix < p.total) p.sval[pix] = (float)s;
       }
@@ -320,23 +327,28 @@ __global__ void __launch_bounds__(256) deform_dw_v2_kernel(const DwParams p) {
         if (pix >= p.total || !active) continue;
         const uint32_t hw = s_hw[j];
         const int w = (int)(hw & 0xffffu), h = (int)(hw >> 16);
-        const uint32_t* img = p.in + (size_t)s_b[j] * p.Hs * rs_in + cw;
+        const uint32_t* img = p.in + s_b[j] + cw;
         const double s = s_s[j];
         if (MODE == 0) {
-          const int si = (int)s;
+          const int si = s_si[j];
+          // rows / columns of the dilated 3x3 stencil: clamped 32-bit offsets (loads are unconditional), validity flags
           int ro[3], co[3]; bool yok[3], xok[3];
 #pragma unroll
-          for (int i = 0; i < 3; ++i) {
+          for (int i = 0; i < 3; i += 2) {
             const int y = h + (i - 1) * si, x = w + (i - 1) * si;
             yok[i] = (unsigned)y < (unsigned)p.Hin; xok[i] = (unsigned)x < (unsigned)p.Win;
-            ro[i] = (y >> p.shift) * rs_in; co[i] = (x >> p.shift) * p.in_pitch_w;
+            ro[i] = (min(max(y, 0), p.Hin - 1) >> p.shift) * rs_in; co[i] = (min(max(x, 0), p.Win - 1) >> p.shift) * p.in_pitch_w;
           }
+          yok[1] = xok[1] = true; ro[1] = (h >> p.shift) * rs_in; co[1] = (w >> p.shift) * p.in_pitch_w;
           uint32_t x[9];
 #pragma unroll
           for (int i = 0; i < 3; ++i)
 #pragma unroll
-            for (int jj = 0; jj < 3; ++jj)
-              x[i * 3 + jj] = (yok[i] && xok[jj]) ? __ldg(img + ro[i] + co[jj]) : p.pad_word;
+            for (int jj = 0; jj < 3; ++jj) x[i * 3 + jj] = __ldg(img + (ro[i] + co[jj]));
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int jj = 0; jj < 3; ++jj) if (!(yok[i] && xok[jj])) x[i * 3 + jj] = p.pad_word;
           uint32_t a0, a1, a2, a3, b0, b1, b2, b3;
           transpose4x4(x[0], x[1], x[2], x[3], a0, a1, a2, a3);
           transpose4x4(x[4], x[5], x[6], x[7], b0, b1, b2, b3);
@@ -555,7 +567,7 @@ int deform_launch(const DwDevice& d, const cdn_deform_scale* sc, const int8_t* i
   p.u_lo = (double)(-sc->bound + 1); p.u_hi = (double)sc->bound;
   p.sval = sval;
   if (p.total == 0) return 0;
-  CDN_CHECK((long long)p.Hs * p.Ws * p.in_pitch_w < (1ll << 31) && p.total < (1ll << 31) && p.Hout < 65536 && p.Wout < 65536,
+  CDN_CHECK((long long)batch * p.Hs * p.Ws * p.in_pitch_w < (1ll << 31) && p.total < (1ll << 31) && p.Hout < 65536 && p.Wout < 65536,
             CDN_ERR_INVALID, "deform: tensor too large for 32-bit indexing");
   const long long ntiles = (p.total + DEF_NP - 1) / DEF_NP;
   const long long cap = (long long)cdn_num_sms() * 8;

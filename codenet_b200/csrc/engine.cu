@@ -112,17 +112,27 @@ extern "C" int cdn_pw_gemm_i8(const int8_t* d_in, int in_pitch, int64_t pixels, 
   return r;
 }
 
-extern "C" int cdn_ctdet_decode(const float* d_hm, const float* d_wh, const float* d_reg, int batch, int cat, int H, int W,
-                                int K, float* d_dets, int32_t* d_inds, cdn_stream_t stream) {
+static int decode_standalone(const float* d_hm, const float* d_wh, const float* d_reg, int batch, int cat, int H, int W,
+                             int K, int is_prob, float* d_dets, int32_t* d_inds, cdn_stream_t stream) {
   unsigned long long* scratch = nullptr;
+  CDN_CHECK(batch >= 0 && cat >= 1 && H >= 1 && W >= 1, CDN_ERR_INVALID, "decode: bad shape");
   size_t n = (size_t)batch * cat * H * W;
-  CDN_CUDA(cudaMalloc(&scratch, (n ? n : 1) * sizeof(unsigned long long)));
+  CDN_CUDA(cudaMalloc(&scratch, (n ? n : 1) * sizeof(unsigned long long) + ((size_t)batch + 1) * sizeof(unsigned int)));
   long long hw = (long long)H * W;
-  int r = decode_launch(d_hm, cat * hw, d_wh, 2 * hw, d_reg, 2 * hw, batch, cat, H, W, K, scratch, d_dets, d_inds, (cudaStream_t)stream);
+  int r = decode_launch(d_hm, cat * hw, d_wh, 2 * hw, d_reg, 2 * hw, batch, cat, H, W, K, is_prob, scratch,
+                        (unsigned int*)(scratch + (n ? n : 1)), d_dets, d_inds, (cudaStream_t)stream);
   cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
   if (!r && e != cudaSuccess) r = cdn_fail(CDN_ERR_CUDA, "decode: %s", cudaGetErrorString(e));
   cudaFree(scratch);
   return r;
+}
+extern "C" int cdn_ctdet_decode(const float* d_hm, const float* d_wh, const float* d_reg, int batch, int cat, int H, int W,
+                                int K, float* d_dets, int32_t* d_inds, cdn_stream_t stream) {
+  return decode_standalone(d_hm, d_wh, d_reg, batch, cat, H, W, K, 0, d_dets, d_inds, stream);
+}
+extern "C" int cdn_ctdet_decode_prob(const float* d_heat, const float* d_wh, const float* d_reg, int batch, int cat, int H,
+                                     int W, int K, float* d_dets, int32_t* d_inds, cdn_stream_t stream) {
+  return decode_standalone(d_heat, d_wh, d_reg, batch, cat, H, W, K, 1, d_dets, d_inds, stream);
 }
 
 // ---- engine -------------------------------------------------------------------------------------------------
@@ -311,7 +321,7 @@ extern "C" int cdn_engine_finalize(cdn_engine* e, int max_batch) {
   }
   size_t ppi = (size_t)e->hH * e->hW;
   CDN_CUDA(cudaMalloc((void**)&e->heads, (size_t)max_batch * e->n_f32 * ppi * sizeof(float)));
-  CDN_CUDA(cudaMalloc((void**)&e->dec_scratch, (size_t)max_batch * e->cat * ppi * sizeof(unsigned long long)));
+  CDN_CUDA(cudaMalloc((void**)&e->dec_scratch, (size_t)max_batch * e->cat * ppi * sizeof(unsigned long long) + ((size_t)max_batch + 1) * sizeof(unsigned int)));
   CDN_CUDA(cudaMalloc((void**)&e->dets, (size_t)max_batch * e->K * 6 * sizeof(float)));
   CDN_CUDA(cudaMalloc((void**)&e->inds, (size_t)max_batch * e->K * sizeof(int32_t)));
   for (auto* op : e->ops) {
@@ -383,8 +393,9 @@ static int engine_enqueue(cdn_engine* e, const float* d_img, int batch, float* d
     const float* wh = e->heads + (size_t)e->cat * ppi;
     const float* reg = e->has_reg ? e->heads + (size_t)(e->cat + 2) * ppi : nullptr;
     long long is = (long long)e->n_f32 * ppi;
-    if (int r = decode_launch(hm, is, wh, is, reg, is, batch, e->cat, e->hH, e->hW, e->K, e->dec_scratch, d_dets, d_inds, st)) return r;
-    launches++;
+    if (int r = decode_launch(hm, is, wh, is, reg, is, batch, e->cat, e->hH, e->hW, e->K, 0, e->dec_scratch,
+                              (unsigned int*)(e->dec_scratch + (size_t)e->max_batch * e->cat * ppi), d_dets, d_inds, st)) return r;
+    launches += 2;
   }
   mark();
   e->launches = launches;

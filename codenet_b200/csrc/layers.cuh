@@ -43,5 +43,5 @@ int pw_launch(const PwDevice& d, const int8_t* in, int in_pitch, long long pixel
 int make_tmap_2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t pitch, uint32_t box_rows);
 
 int decode_launch(const float* hm, long long hm_img_stride, const float* wh, long long wh_img_stride, const float* reg,
-                  long long reg_img_stride, int batch, int cat, int H, int W, int K, unsigned long long* scratch,
-                  float* dets, int32_t* inds, cudaStream_t st);
+                  long long reg_img_stride, int batch, int cat, int H, int W, int K, int is_prob,
+                  unsigned long long* scratch, unsigned int* counts, float* dets, int32_t* inds, cudaStream_t st);

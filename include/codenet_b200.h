@@ -132,6 +132,10 @@ int cdn_pw_gemm_i8(const int8_t* d_in, int in_pitch, int64_t pixels, const cdn_p
  * If an image has fewer than K peaks the remaining rows are zero and inds = -1. */
 int cdn_ctdet_decode(const float* d_hm, const float* d_wh, const float* d_reg, int batch, int cat, int H, int W,
                      int K, float* d_dets, int32_t* d_inds, cdn_stream_t stream);
+/* Same with the heat map already holding probabilities (what the reference's ctdet_decode receives after
+ * hm.sigmoid_(), lib/detectors/ctdet.py:32): peaks, order and the score written are taken from the values as given. */
+int cdn_ctdet_decode_prob(const float* d_heat, const float* d_wh, const float* d_reg, int batch, int cat, int H, int W,
+                          int K, float* d_dets, int32_t* d_inds, cdn_stream_t stream);
 
 /* ---- general deformable convolution forward, fp32 (the reference's native plug-in point) ----------------
  * Same argument meaning and order (W before H) as deform_conv_forward_cuda; tensors are contiguous NCHW device
