@@ -158,7 +158,7 @@ struct cdn_engine {
   float* d_img = nullptr; size_t d_img_bytes = 0;
   cudaStream_t s_compute = nullptr, s_copy = nullptr;
   std::vector<cudaEvent_t> ev;
-  int host_chunk = 32, use_graph = 1, micro_batch = 0;
+  int host_chunk = 32, use_graph = 1, micro_batch = 0, hm_logits = 0;
   // graph cache
   struct GraphKey { const void* a[6]; int batch; bool operator==(const GraphKey& o) const { return memcmp(this, &o, sizeof(*this)) == 0; } };
   std::vector<std::pair<GraphKey, cudaGraphExec_t>> graphs;
@@ -166,12 +166,12 @@ struct cdn_engine {
 };
 
 __global__ void heads_copyout_kernel(const float* heads, int n_f32, int cat, int ppi, long long total,
-                                     float* hm, float* wh, float* reg) {
+                                     float* hm, float* wh, float* reg, int hm_logits) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   int pi = (int)(i % ppi); long long t = i / ppi; int n = (int)(t % n_f32); long long b = t / n_f32;
   float v = heads[i];
-  if (n < cat) { if (hm) hm[((size_t)b * cat + n) * ppi + pi] = 1.f / (1.f + __expf(-v)); }
+  if (n < cat) { if (hm) hm[((size_t)b * cat + n) * ppi + pi] = hm_logits ? v : 1.f / (1.f + __expf(-v)); }
   else if (n < cat + 2) { if (wh) wh[((size_t)b * 2 + (n - cat)) * ppi + pi] = v; }
   else if (n < cat + 4) { if (reg) reg[((size_t)b * 2 + (n - cat - 2)) * ppi + pi] = v; }
 }
@@ -210,6 +210,7 @@ extern "C" int cdn_engine_set_option(cdn_engine* e, const char* name, int value)
   if (!strcmp(name, "host_chunk")) e->host_chunk = std::max(1, value);
   else if (!strcmp(name, "use_graph")) e->use_graph = value;
   else if (!strcmp(name, "micro_batch")) e->micro_batch = std::max(0, value);
+  else if (!strcmp(name, "hm_logits")) e->hm_logits = value ? 1 : 0;
   else return cdn_fail(CDN_ERR_INVALID, "unknown engine option '%s'", name);
   return 0;
 }
@@ -383,7 +384,7 @@ static int engine_enqueue(cdn_engine* e, const float* d_img, int batch, float* d
   const long long ppi = (long long)e->hH * e->hW;
   if (d_hm || d_wh || d_reg) {
     long long total = (long long)batch * e->n_f32 * ppi;
-    heads_copyout_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(e->heads, e->n_f32, e->cat, (int)ppi, total, d_hm, d_wh, d_reg);
+    heads_copyout_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(e->heads, e->n_f32, e->cat, (int)ppi, total, d_hm, d_wh, d_reg, e->hm_logits);
     CDN_LAUNCH_CHECK("heads_copyout_kernel");
     launches++;
   }
@@ -430,7 +431,7 @@ extern "C" int cdn_engine_run(cdn_engine* e, const float* d_img, int batch, floa
   cudaStream_t st = (cudaStream_t)stream;
   if (!e->use_graph || (g_cdn_debug_flags & 2u)) return engine_enqueue(e, d_img, batch, d_hm, d_wh, d_reg, d_dets, d_inds, st);
   cdn_engine::GraphKey key; memset(&key, 0, sizeof(key));
-  key.a[0] = d_img; key.a[1] = d_hm; key.a[2] = d_wh; key.a[3] = d_reg; key.a[4] = d_dets; key.a[5] = d_inds; key.batch = batch;
+  key.a[0] = d_img; key.a[1] = d_hm; key.a[2] = d_wh; key.a[3] = d_reg; key.a[4] = d_dets; key.a[5] = d_inds; key.batch = batch | (e->hm_logits << 30);
   for (auto& g : e->graphs) if (g.first == key) { CDN_CUDA(cudaGraphLaunch(g.second, st)); return 0; }
   // capture once per (pointers, batch)
   cudaStream_t cap = e->s_compute;

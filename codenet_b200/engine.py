@@ -70,7 +70,12 @@ class Engine:
         w2 = sd["layer4.0.conv.weight"].shape[0] == 2153
         maxpool = tuple(getattr(model.layer0[0].conv, "stride", (4, 4))) == (2, 2)
         heads = tuple((h, int(sd[h + ".quant_conv.weight"].shape[0])) for h in model.heads)
-        cfg = NetConfig(num_classes=heads[0][1], w2=w2, maxpool=maxpool, heads=heads)
+        bound = 8
+        try:                                  # Hardtanh(-bound+1, bound) of the first deformable block
+            bound = int(round(float(model.deconv_layers[0].quant_act[0].max_val)))
+        except Exception:
+            pass
+        cfg = NetConfig(num_classes=heads[0][1], w2=w2, maxpool=maxpool, heads=heads, offset_bound=bound)
         return cls.from_state_dict(cfg, sd, in_H, in_W, max_batch, offset_mode, device, K)
 
     def close(self):
@@ -88,10 +93,13 @@ class Engine:
         _lib.check(self.lib.cdn_engine_set_option(self._h, name.encode(), int(value)))
 
     # -- execution ----------------------------------------------------------------------------------------------------
-    def run(self, images, maps: bool = True, dets: bool = True, out: Optional[dict] = None):
+    def run(self, images, maps: bool = True, dets: bool = True, out: Optional[dict] = None, raw_hm: bool = False):
         """images: torch CUDA fp32 [B,3,H,W] (contiguous).  Returns dict of torch CUDA tensors:
-        hm (post-sigmoid, ctdet.py:32), wh, reg [B,*,H/4,W/4]; dets [B,K,6]; inds [B,K]."""
+        hm (post-sigmoid, ctdet.py:32; logits when raw_hm), wh, reg [B,*,H/4,W/4]; dets [B,K,6]; inds [B,K]."""
         import torch
+        if raw_hm != getattr(self, "_raw_hm", False):
+            self.set_option("hm_logits", 1 if raw_hm else 0)
+            self._raw_hm = raw_hm
         assert images.is_cuda and images.dtype == torch.float32 and images.is_contiguous()
         B = images.shape[0]
         assert images.shape[1:] == (3, self.plan.in_H, self.plan.in_W), images.shape

@@ -175,7 +175,8 @@ int cdn_engine_run(cdn_engine* e, const float* d_img, int batch, float* d_hm, fl
 int cdn_engine_run_host(cdn_engine* e, const float* h_img, int batch, float* h_dets, int32_t* h_inds);
 /* Options: "host_chunk" (images per H2D/compute pipeline step of run_host, default 32), "use_graph" (replay the
  * launch sequence as a CUDA graph, default 1), "micro_batch" (run the layers over sub-batches of this many images
- * so consecutive layers hit L2, 0 = whole batch). */
+ * so consecutive layers hit L2, 0 = whole batch), "hm_logits" (cdn_engine_run writes the heat map as logits, what
+ * PoseShuffleNetV2.forward returns, instead of post-sigmoid; default 0). */
 int cdn_engine_set_option(cdn_engine* e, const char* name, int value);
 /* Debug/test access to an activation tensor of the last run: copies batch*H*W*pitch bytes to host. */
 int cdn_engine_read_tensor(cdn_engine* e, int tensor, int batch, int8_t* h_out);

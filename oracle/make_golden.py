@@ -14,6 +14,7 @@ Vectors produced (all from the reference's own code through oracle/ref_harness.p
   codenet1x_256_{round,bilinear}.npz   fp64 reference forward + decode on config a (256^2), with int8-grid
                     intermediates
   codenet1x_512_round.npz   one 512^2 image (config c geometry): detections + strided output samples
+  ref_state_keys.json   state-dict key spaces of the reference network before / after quantisation (1x, w2, maxpool)
 """
 import os
 import sys
@@ -325,11 +326,31 @@ def codenet1x():
     print("codenet1x ok")
 
 
+def ref_keys():
+    """State-dict key spaces (name -> shape) of the UNMODIFIED reference network before and after
+    quantize_shufflenetv2_dcn, for 1x / w2 / maxpool: what codenet_b200.compat must reproduce so checkpoints load."""
+    import json
+    out = {}
+    for tag, w2, mp in [("1x", False, False), ("w2", True, False), ("1x_maxpool", False, True)]:
+        import contextlib, io
+        R = H.load_reference()
+        with contextlib.redirect_stdout(io.StringIO()):
+            m = R.net.PoseShuffleNetV2({"hm": 20, "wh": 2, "reg": 2}, head_conv=64, w2=w2, deform=False, maxpool=mp)
+        out[tag + "/raw"] = {k: list(v.shape) for k, v in m.state_dict().items()}
+        H.quantize_reference_model(m, w2=w2, maxpool=mp)
+        out[tag + "/quant"] = {k: list(v.shape) for k, v in m.state_dict().items()}
+    with open(os.path.join(OUT, "ref_state_keys.json"), "w") as f:
+        json.dump(out, f, indent=0, sort_keys=True)
+    print("ref_keys ok", {k: len(v) for k, v in out.items()})
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["quant", "deform", "decode", "codenet1x"]
+    which = sys.argv[1:] or ["quant", "deform", "decode", "codenet1x", "keys"]
+    if "keys" in which:
+        ref_keys()
     if "quant" in which:
         quant_kat()
     if "deform" in which:

@@ -1,0 +1,120 @@
+"""GPU parity of the reference-facing interface (codenet_b200.compat): the calls a user of the reference makes."""
+import numpy as np
+import pytest
+
+from codenet_b200.arch import NetConfig
+from codenet_b200.synth import make_quant_state, make_images
+from oracle import int_oracle as io
+
+pytestmark = pytest.mark.gpu
+CFG = NetConfig(num_classes=20)
+
+
+def test_deform_conv_function_matches_reference_vectors(golden):
+    """`deform_conv(x, offset, weight, stride, padding, dilation, groups, deformable_groups)` -- boundary B1."""
+    import torch
+    from codenet_b200 import compat
+    g = golden("deform_kat.npz")
+    for name in ("dw_s1", "dw_s2", "dense", "g2"):
+        x, off, w, y = (torch.from_numpy(g[name + s].astype(np.float32)).cuda() for s in ("_x", "_off", "_w", "_y"))
+        st, pad, dil, groups, dg = (int(v) for v in g[name + "_cfg"])
+        out = compat.deform_conv(x, off, w, st, pad, dil, groups, dg)
+        err = (out - y).abs().cpu().numpy()
+        assert out.shape == y.shape and np.quantile(err, 0.999) < 1e-4 * max(1.0, float(y.abs().max())), name
+    with pytest.raises(AssertionError, match="im2col step must divide batchsize"):
+        compat.deform_conv(torch.zeros(3, 4, 5, 5).cuda(), torch.zeros(3, 18, 5, 5).cuda(), torch.zeros(4, 1, 3, 3).cuda(),
+                           1, 1, 1, 4, 1, 2)
+
+
+@pytest.mark.parametrize("name", ["mod_same", "mod_chan", "mod_s2"])
+def test_codesigned_module_fp32(golden, name):
+    """DeformConvWithOffsetScaleBoundPositive.forward (fp32, bilinear offsets) within 1e-4 relative of the reference."""
+    import torch
+    from codenet_b200 import compat
+    g = golden("deform_kat.npz")
+    st, bound = (int(v) for v in g[name + "_cfg"])
+    x = g[name + "_x"]
+    cin, cout = x.shape[1], g[name + "_y"].shape[1]
+    m = compat.DeformConvWithOffsetScaleBoundPositive(cin, cout, 3, st, 1, groups=cout, offset_bound=bound).cuda()
+    with torch.no_grad():
+        m.conv_scale.weight.copy_(torch.from_numpy(g[name + "_ws"])); m.conv_scale.bias.copy_(torch.from_numpy(g[name + "_bs"]))
+        m.conv.weight.copy_(torch.from_numpy(g[name + "_w"]))
+        if cin != cout:
+            m.conv_channel.weight.copy_(torch.from_numpy(g[name + "_wc"]))
+        old = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False
+        y = m(torch.from_numpy(x.astype(np.float32)).cuda())
+        torch.backends.cudnn.allow_tf32 = old
+    ref = g[name + "_y"]
+    err = np.abs(y.cpu().numpy() - ref)
+    assert np.quantile(err, 0.995) < 1e-4 * max(1.0, np.abs(ref).max()), err.max()
+
+
+@pytest.mark.parametrize("name", ["voc", "small"])
+def test_ctdet_decode_on_probabilities(golden, name):
+    """ctdet_decode(heat, wh, reg, K) on the reference's own post-sigmoid vectors (lib/models/decode.py:474-505)."""
+    import torch
+    from codenet_b200 import compat
+    g = golden("decode_kat.npz")
+    K = int(g[name + "_K"])
+    hm, wh, reg = (torch.from_numpy(g[name + s]).cuda() for s in ("_hm", "_wh", "_reg"))
+    d = compat.ctdet_decode(hm, wh, reg=reg, K=K).cpu().numpy()
+    ref = g[name + "_dets"]
+    np.testing.assert_array_equal(d[..., 5], ref[..., 5])                 # classes in the reference's order (tie-free vectors)
+    np.testing.assert_array_equal(d[..., 4], ref[..., 4])                 # scores are the given probabilities, untouched
+    np.testing.assert_allclose(d[..., :4], ref[..., :4], rtol=1e-6, atol=1e-5)
+    d2 = compat.ctdet_decode(hm, wh, reg=None, K=K).cpu().numpy()
+    np.testing.assert_allclose(d2[..., :4], g[name + "_dets_noreg"][..., :4], rtol=1e-6, atol=1e-5)
+
+
+def _detector(calib, mode, res, **kw):
+    from codenet_b200 import compat
+    from codenet_b200.compat.detector import default_opt
+    st = make_quant_state(CFG, calib, mode, res)
+    opt = default_opt(state_dict=st, offset_mode=mode, input_h=res, input_w=res, **kw)
+    return compat.CtdetDetector(opt)
+
+
+@pytest.mark.parametrize("mode", ["round", "bilinear"])
+def test_detector_process_matches_reference_vectors(golden, calib, mode):
+    """CtdetDetector.process(images) -- boundary B3 -- against the fp64 run of the unmodified reference."""
+    import torch
+    g = golden("codenet1x_256_%s.npz" % mode)
+    det = _detector(calib, mode, 256, max_batch=2)
+    x = torch.from_numpy(make_images(2, 256, seed=2)).cuda()
+    output, dets = det.process(x)
+    np.testing.assert_allclose(output["hm"].cpu().numpy(), 1 / (1 + np.exp(-g["hm_logit"])), rtol=2e-6, atol=1e-7)
+    np.testing.assert_allclose(output["wh"].cpu().numpy(), g["wh"], rtol=2e-7, atol=1e-7)
+    np.testing.assert_allclose(output["reg"].cpu().numpy(), g["reg"], rtol=2e-7, atol=1e-7)
+    h64 = np.concatenate([g["hm_logit"], g["wh"], g["reg"]], 1).astype(np.float32).astype(np.float64)
+    odets, _ = io.ctdet_decode(h64[:, :20], h64[:, 20:22], h64[:, 22:24], 100)
+    np.testing.assert_allclose(dets.cpu().numpy(), odets, rtol=1e-5, atol=1e-4)
+    # the network mirror returns logits like PoseShuffleNetV2.forward
+    out = det.model(x)[-1]
+    np.testing.assert_allclose(out["hm"].cpu().numpy(), g["hm_logit"], rtol=2e-7, atol=1e-7)
+
+
+def test_detector_run_and_flip_test(calib):
+    """run() on a raw image: same result keys as the reference (base_detector.py:153-155); flip_test averages the
+    mirrored pass (ctdet.py:35-38) and must agree with doing that by hand from two plain passes."""
+    import torch
+    pytest.importorskip("cv2")
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, (300, 400, 3), dtype=np.uint8)
+    det = _detector(calib, "round", 256, max_batch=2)
+    ret = det.run(img)
+    assert set(ret) == {"results", "tot", "load", "pre", "net", "dec", "post", "merge"}
+    assert sorted(ret["results"]) == list(range(1, 21)) and sum(len(v) for v in ret["results"].values()) == 100
+    assert all(v.shape[1] == 5 and v.dtype == np.float32 for v in ret["results"].values())
+    det.opt.flip_test = True
+    images, meta = det.pre_process(img, 1.0)
+    assert images.shape == (2, 3, 256, 256)
+    output, dets = det.process(images.cuda())
+    det.opt.flip_test = False
+    o2, _ = det.process(images.cuda())
+    hm = (o2["hm"][0:1] + torch.flip(o2["hm"][1:2], [3])) / 2
+    wh = (o2["wh"][0:1] + torch.flip(o2["wh"][1:2], [3])) / 2
+    from codenet_b200 import compat
+    want = compat.ctdet_decode(hm, wh, reg=o2["reg"][0:1], K=100)
+    assert dets.shape == (1, 100, 6)
+    np.testing.assert_array_equal(dets.cpu().numpy(), want.cpu().numpy())
