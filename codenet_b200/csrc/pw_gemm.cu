@@ -29,7 +29,8 @@
 #define PW_GROUP_THREADS (32 * PW_EPI_WARPS / PW_EPI_GROUPS)
 #define PW_EPI_PARTS (PW_EPI_WARPS / PW_EPI_GROUPS / 4)
 #define PW_EPI_THREADS (32 * PW_EPI_WARPS)
-#define PW_THREADS (64 + PW_EPI_THREADS)
+#define PW_STORE_WARP0 (2 + PW_EPI_WARPS)     // one TMA-store warp per epilogue group follows the epilogue warps
+#define PW_THREADS (64 + PW_EPI_THREADS + 32 * PW_EPI_GROUPS)
 #define PW_MAX_STAGES 8
 #define PW_SPIN_LIMIT (1u << 26)
 #define PW_SMEM_LIMIT (227 * 1024)
@@ -44,6 +45,8 @@ struct PwParams {
   const float4* kc;                          // per GEMM column {Mh, Bh, bits(acc_bias + MAGIC_I), 0}
   const double* M; const double* B; const int32_t* acc_bias;
   float lo_f, thr;
+  unsigned dbg;                              // experiments only (cdn_set_debug_flags bits 2..4)
+  unsigned long long* dbg_cyc;               // [16] cycle accumulators of block 0 (bit 4)
   // fp32 head output
   int n_f32, ppi; float* out_f32; const double* Mf; const double* bf;
   // SIMT cross-check path
@@ -65,6 +68,8 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+#define DBG_T0() long long t0__ = (p.dbg & 16u) ? clock64() : 0
+#define DBG_ACC(slot) do { if ((p.dbg & 16u) && blockIdx.x == 0 && lane == 0) { long long t1__ = clock64(); atomicAdd(p.dbg_cyc + (slot), (unsigned long long)(t1__ - t0__)); t0__ = t1__; } } while (0)
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0, spins = 0;
   while (true) {
@@ -73,6 +78,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (done) break;
     if (++spins > PW_SPIN_LIMIT) { printf("cdn pw_gemm: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
   }
+}
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  return done != 0;
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
@@ -209,25 +220,31 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   PwSeg* s_segs = (PwSeg*)(s_chunks + ((p.n_chunks + 1) & ~1));
   int* s_tile_seg = (int*)(s_segs + p.n_segs);
   uint64_t* bars = (uint64_t*)(s_tile_seg + ((p.n_tiles + 1 + 3) & ~3));
-  // barrier slots: full[8], empty[8], tmem_full[2], tmem_empty[2], pass_full[2], pass_empty[2], b_full, tmem_ptr
+  // barrier slots: full[8], empty[8], tmem_full[4], tmem_empty[4], pass_full[2], pass_empty[2], b_full, tmem_ptr
   const uint32_t bar_base = smem_u32(bars);
   auto FULL = [&](int s) { return bar_base + 8u * s; };
   auto EMPTY = [&](int s) { return bar_base + 8u * (8 + s); };
   auto TFULL = [&](int s) { return bar_base + 8u * (16 + s); };
-  auto TEMPTY = [&](int s) { return bar_base + 8u * (18 + s); };
-  auto PFULL = [&](int s) { return bar_base + 8u * (20 + s); };
-  auto PEMPTY = [&](int s) { return bar_base + 8u * (22 + s); };
-  const uint32_t BFULL = bar_base + 8u * 24;
-  volatile uint32_t* tmem_slot = (volatile uint32_t*)(bars + 25);
+  auto TEMPTY = [&](int s) { return bar_base + 8u * (20 + s); };
+  auto PFULL = [&](int s) { return bar_base + 8u * (42 + s); };
+  auto PEMPTY = [&](int s) { return bar_base + 8u * (46 + s); };
+  const uint32_t BFULL = bar_base + 8u * 28;
+  volatile uint32_t* tmem_slot = (volatile uint32_t*)(bars + 29);
+  auto SFULL = [&](int g_, int b_) { return bar_base + 8u * (30 + g_ * 3 + b_); };     // staging buffer written by the group
+  auto SEMPTY = [&](int g_, int b_) { return bar_base + 8u * (36 + g_ * 3 + b_); };    // ... drained by its TMA store
+  // accumulator stages: each epilogue group owns one (BN > 128) or two (BN <= 128) of the 512 TMEM columns' stages, so
+  // the MMAs of a group's next tile run while it still drains the previous one
+  const int nacc = p.BN <= 128 ? 4 : 2;
+  const uint32_t acc_stride = p.BN <= 128 ? 128u : 256u;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(TFULL(s), 1); mbar_init(TEMPTY(s), PW_GROUP_THREADS);
-      mbar_init(PFULL(s), 1); mbar_init(PEMPTY(s), PW_GROUP_THREADS);
-    }
+    for (int s = 0; s < 4; ++s) { mbar_init(TFULL(s), 1); mbar_init(TEMPTY(s), PW_GROUP_THREADS); }
+    for (int s = 0; s < 4; ++s) { mbar_init(PFULL(s), 1); mbar_init(PEMPTY(s), PW_GROUP_THREADS); }
+    for (int g_ = 0; g_ < PW_EPI_GROUPS; ++g_)
+      for (int b_ = 0; b_ < 3; ++b_) { mbar_init(SFULL(g_, b_), PW_GROUP_THREADS); mbar_init(SEMPTY(g_, b_), 1); }
     mbar_init(BFULL, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -249,6 +266,7 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t tmem_base = *tmem_slot;
 
   const unsigned total_tiles = (unsigned)(p.m_tiles * p.n_tiles);   // host guarantees < 2^31
+  const long long t_start = (p.dbg & 16u) ? clock64() : 0;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -259,29 +277,44 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int nt = 0; nt < p.n_tiles; ++nt)
             tma_load_2d(smem_u32(s_B + ((size_t)kb * Ntot + (size_t)nt * p.BN) * PW_BK), &tmB, kb * PW_BK, nt * p.BN, BFULL);
       }
-      int stage = 0; uint32_t phase = 0; uint32_t it = 0;
-      for (unsigned tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const unsigned mt = tile / (unsigned)p.n_tiles; const int nt = (int)(tile % (unsigned)p.n_tiles);
-        if (p.has_pass) {
-          const int pb = (int)(it % (uint32_t)p.pass_bufs); const uint32_t pph = (it / (uint32_t)p.pass_bufs) & 1;
-          mbar_wait(PEMPTY(pb), pph ^ 1);
-          mbar_expect_tx(PFULL(pb), (uint32_t)p.pass_segs * 16384u);
-          for (int s = 0; s < p.pass_segs; ++s)
-            tma_load_2d(smem_u32(s_pass + ((size_t)pb * p.pass_segs + s) * 16384), &tmP, s * 128, (int)(mt * PW_BM), PFULL(pb));
+      // Two independent cursors -- activation (and streamed weight) blocks into the ring, pass-through tiles into
+      // their own buffers -- advanced by polling, so a full pass buffer never stops the activation prefetch.
+      int stage = 0; uint32_t phase = 0;
+      unsigned a_tile = blockIdx.x; int a_kb = 0;
+      unsigned p_tile = p.has_pass ? blockIdx.x : total_tiles; uint32_t p_it = 0;
+      uint32_t idle = 0;
+      while (a_tile < total_tiles || p_tile < total_tiles) {
+        bool progressed = false;
+        if (p_tile < total_tiles) {
+          const int pb = (int)(p_it % (uint32_t)p.pass_bufs); const uint32_t pph = (p_it / (uint32_t)p.pass_bufs) & 1;
+          if (mbar_test(PEMPTY(pb), pph ^ 1)) {
+            const unsigned mt = p_tile / (unsigned)p.n_tiles;
+            mbar_expect_tx(PFULL(pb), (uint32_t)p.pass_segs * 16384u);
+            for (int s = 0; s < p.pass_segs; ++s)
+              tma_load_2d(smem_u32(s_pass + ((size_t)pb * p.pass_segs + s) * 16384), &tmP, s * 128, (int)(mt * PW_BM), PFULL(pb));
+            p_tile += gridDim.x; ++p_it; progressed = true;
+          }
         }
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-          mbar_wait(EMPTY(stage), phase ^ 1);
+        // without pass-through tiles there is nothing to interleave: block on the ring slot (hardware-suspended wait)
+        if (a_tile < total_tiles && !p.has_pass) { DBG_T0(); mbar_wait(EMPTY(stage), phase ^ 1); DBG_ACC(0); }
+        if (a_tile < total_tiles && (!p.has_pass || mbar_test(EMPTY(stage), phase ^ 1))) {
+          const unsigned mt = a_tile / (unsigned)p.n_tiles; const int nt = (int)(a_tile % (unsigned)p.n_tiles);
           uint8_t* sa = s_ring + (size_t)stage * stage_bytes;
           if (p.resident) {
             mbar_expect_tx(FULL(stage), a_bytes);
-            tma_load_2d(smem_u32(sa), &tmA, p.k_off + kb * PW_BK, (int)(mt * PW_BM), FULL(stage));
+            tma_load_2d(smem_u32(sa), &tmA, p.k_off + a_kb * PW_BK, (int)(mt * PW_BM), FULL(stage));
           } else {
             mbar_expect_tx(FULL(stage), a_bytes + (uint32_t)p.BN * PW_BK);
-            tma_load_2d(smem_u32(sa), &tmA, p.k_off + kb * PW_BK, (int)(mt * PW_BM), FULL(stage));
-            tma_load_2d(smem_u32(sa + a_bytes), &tmB, kb * PW_BK, nt * p.BN, FULL(stage));
+            tma_load_2d(smem_u32(sa), &tmA, p.k_off + a_kb * PW_BK, (int)(mt * PW_BM), FULL(stage));
+            tma_load_2d(smem_u32(sa + a_bytes), &tmB, a_kb * PW_BK, nt * p.BN, FULL(stage));
           }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          if (++a_kb == p.num_k_blocks) { a_kb = 0; a_tile += gridDim.x; }
+          progressed = true;
         }
+        if (!progressed) {
+          if (++idle > PW_SPIN_LIMIT) { printf("cdn pw_gemm: producer timeout (block %d)\n", blockIdx.x); __trap(); }
+        } else idle = 0;
       }
     }
   } else if (warp == 1) {
@@ -293,12 +326,14 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int stage = 0; uint32_t phase = 0; uint32_t it = 0;
       for (unsigned tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int nt = (int)(tile % (unsigned)p.n_tiles);
-        const int as = it & 1; const uint32_t aphase = (it >> 1) & 1;
-        mbar_wait(TEMPTY(as), aphase ^ 1);
+        const uint32_t kq = it >> 1;                               // this tile is the kq-th of epilogue group (it & 1)
+        const int as = (int)(it & 1) + (nacc == 4 ? 2 * (int)(kq & 1) : 0);
+        const uint32_t aphase = (nacc == 4 ? (kq >> 1) : kq) & 1;
+        { DBG_T0(); mbar_wait(TEMPTY(as), aphase ^ 1); DBG_ACC(2); }
         tc_fence_after();
-        const uint32_t tacc = tmem_base + (uint32_t)(as * PW_MAX_BN);
+        const uint32_t tacc = tmem_base + (uint32_t)as * acc_stride;
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-          mbar_wait(FULL(stage), phase);
+          { DBG_T0(); mbar_wait(FULL(stage), phase); DBG_ACC(3); }
           tc_fence_after();
           const uint32_t sa = smem_u32(s_ring + (size_t)stage * stage_bytes);
           const uint32_t sb = p.resident ? smem_u32(s_B + ((size_t)kb * Ntot + (size_t)nt * p.BN) * PW_BK) : sa + a_bytes;
@@ -312,6 +347,31 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         umma_commit(TFULL(as));                // accumulator complete
       }
     }
+  } else if (warp >= PW_STORE_WARP0) {
+    // ===================== TMA-store warps (one per epilogue group) =====================
+    // The hand-off staging buffer -> global memory is off the epilogue's critical path: the group signals SFULL when a
+    // 128-byte output segment is complete, this warp issues the store, waits until the TMA engine has read the
+    // buffer and hands it back through SEMPTY.
+    const int grp = warp - PW_STORE_WARP0;
+    if (lane == 0 && p.n_f32 == 0) {
+      uint32_t g = 0;
+      for (unsigned tile = blockIdx.x + grp * gridDim.x; tile < total_tiles; tile += PW_EPI_GROUPS * gridDim.x) {
+        const unsigned mt = tile / (unsigned)p.n_tiles; const int nt = (int)(tile % (unsigned)p.n_tiles);
+        const int sg0 = s_tile_seg[nt], sg1 = s_tile_seg[nt + 1];
+        for (int sg = sg0; sg < sg1; ++sg, ++g) {
+          const int b_ = (int)(g % (uint32_t)p.nbuf); const uint32_t ph = (g / (uint32_t)p.nbuf) & 1;
+          DBG_T0();
+          mbar_wait(SFULL(grp, b_), ph);
+          if (grp == 0) DBG_ACC(9);
+          tma_store_2d(&tmO, s_segs[sg].seg * 128, (int)(mt * PW_BM), smem_u32(s_out + ((size_t)grp * p.nbuf + b_) * 16384));
+          tma_store_commit();
+          tma_store_wait_read0();
+          if (grp == 0) DBG_ACC(10);
+          mbar_arrive(SEMPTY(grp, b_));
+        }
+      }
+      tma_store_wait_all();
+    }
   } else {
     // ===================== epilogue (warps 2..17) =====================
     // Two independent groups of 8 warps: group g owns TMEM accumulator stage g, pass buffer g and its own staging
@@ -322,18 +382,21 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int half = ((warp - 2) >> 2) % PW_EPI_PARTS;   // which of the PW_EPI_PARTS warps of the quarter (inside the group)
     const int row = q * 32 + lane;             // row inside the tile
     const int gt = (threadIdx.x - 64) % PW_GROUP_THREADS;
-    const int as = grp;
     uint8_t* const s_out_g = s_out + (size_t)grp * p.nbuf * 16384;
     uint32_t it2 = 0, g = 0;                   // tiles / output segments done by this group
     for (unsigned tile = blockIdx.x + grp * gridDim.x; tile < total_tiles; tile += PW_EPI_GROUPS * gridDim.x, ++it2) {
       const unsigned mt = tile / (unsigned)p.n_tiles; const int nt = (int)(tile % (unsigned)p.n_tiles);
-      const uint32_t aphase = it2 & 1;
+      const int as = grp + (nacc == 4 ? 2 * (int)(it2 & 1) : 0);
+      const uint32_t aphase = (nacc == 4 ? (it2 >> 1) : it2) & 1;
+      DBG_T0();
       mbar_wait(TFULL(as), aphase);
+      if (warp == 2) DBG_ACC(4);
       tc_fence_after();
       const uint32_t itg = it2 * PW_EPI_GROUPS + grp;                     // CTA-wide tile counter (as the producer counts)
       const int pb = (int)(itg % (uint32_t)p.pass_bufs);
       if (p.has_pass) mbar_wait(PFULL(pb), (itg / (uint32_t)p.pass_bufs) & 1);
-      const uint32_t tacc = tmem_base + (uint32_t)(as * PW_MAX_BN) + ((uint32_t)(q * 32) << 16);
+      if (warp == 2) DBG_ACC(5);
+      const uint32_t tacc = tmem_base + (uint32_t)as * acc_stride + ((uint32_t)(q * 32) << 16);
       if (p.n_f32 > 0) {
         // fp32 NCHW planes: out[img][n][pix] = fl32(fl64(acc*Mf[n]) + bf[n])
         const unsigned pix = mt * PW_BM + row;
@@ -361,7 +424,10 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int sg0 = s_tile_seg[nt], sg1 = s_tile_seg[nt + 1];
         for (int sg = sg0; sg < sg1; ++sg, ++g) {
           const PwSeg S = s_segs[sg];
-          uint8_t* stg = s_out_g + (size_t)(g % (uint32_t)p.nbuf) * 16384 + row * 128;
+          const int sb = (int)(g % (uint32_t)p.nbuf);
+          mbar_wait(SEMPTY(grp, sb), ((g / (uint32_t)p.nbuf) & 1) ^ 1);            // the store that last used this buffer has drained
+          if (warp == 2) DBG_ACC(6);
+          uint8_t* stg = s_out_g + (size_t)sb * 16384 + row * 128;
           for (int c = S.cb + half; c < S.ce; c += PW_EPI_PARTS) {
             const cdn_pw_chunk ck = s_chunks[c];
             uint32_t acc[16];
@@ -382,30 +448,28 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               pass_lo = __funnelshift_r(w0, w1, sh); pass_hi = __funnelshift_r(w1, w2, sh);
             }
             tmem_ld_wait();
-            const uint4 o = chunk_bytes(ck, acc, s_kc, p.M, p.B, p.lo_f, p.thr, pass_lo, pass_hi);
+            uint4 o;
+            if (p.dbg & 4u) o = make_uint4(acc[0], acc[1], pass_lo, pass_hi);          // experiment: no requant math
+            else o = chunk_bytes(ck, acc, s_kc, p.M, p.B, p.lo_f, p.thr, pass_lo, pass_hi);
             const int j = (ck.dst_off & 127) >> 4;
             *(uint4*)(stg + ((j ^ (row & 7)) << 4)) = o;
           }
+          if (warp == 2) DBG_ACC(7);
           if (sg + 1 == sg1) {                 // last TMEM / pass read of this tile is behind us
             tc_fence_before();
             mbar_arrive(TEMPTY(as));
             if (p.has_pass) mbar_arrive(PEMPTY(pb));
           }
           fence_async_smem();
-          named_bar_sync(1 + grp, PW_GROUP_THREADS);
-          if (gt == 0) {
-            tma_store_2d(&tmO, S.seg * 128, (int)(mt * PW_BM), smem_u32(s_out_g + (size_t)(g % (uint32_t)p.nbuf) * 16384));
-            tma_store_commit();
-            // before anyone passes the NEXT barrier, the store that used the buffer after next must have drained
-            if (p.nbuf >= 3) tma_store_wait_read1(); else tma_store_wait_read0();
-          }
+          mbar_arrive(SFULL(grp, sb));
+          if (warp == 2) DBG_ACC(8);
         }
       }
     }
-    if (gt == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
+  if ((p.dbg & 16u) && blockIdx.x == 0 && threadIdx.x == 0) { atomicAdd(p.dbg_cyc + 11, (unsigned long long)(clock64() - t_start)); atomicAdd(p.dbg_cyc + 12, 1ull); }
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
@@ -603,7 +667,7 @@ int pw_device_build(PwDevice& d, const cdn_pw_desc* desc, int pass_pitch) {
   d.pass_segs = d.has_pass ? (pass_need + 127) / 128 : 0;
   const size_t b_blk = ((size_t)d.BN * PW_BK + 1023) & ~(size_t)1023;
   const size_t b_all = (size_t)d.num_k_blocks * Np * PW_BK;
-  const size_t tables = (size_t)Np * 16 + (size_t)((d.n_chunks + 1) & ~1) * 8 + (size_t)d.n_segs * 16 + (size_t)((d.n_tiles + 1 + 3) & ~3) * 4 + 32 * 8;
+  const size_t tables = (size_t)Np * 16 + (size_t)((d.n_chunks + 1) & ~1) * 8 + (size_t)d.n_segs * 16 + (size_t)((d.n_tiles + 1 + 3) & ~3) * 4 + 56 * 8;
   auto plan = [&](bool resident, int pass_bufs, int nbuf, int& stages) {
     const size_t fixed = 1024 + (resident ? b_all : 0) + (size_t)pass_bufs * d.pass_segs * 16384 + (size_t)PW_EPI_GROUPS * nbuf * 16384 + tables;
     const size_t stage_bytes = 16384 + (resident ? 0 : b_blk);
@@ -613,19 +677,31 @@ int pw_device_build(PwDevice& d, const cdn_pw_desc* desc, int pass_pitch) {
   };
   // preference: resident weights, double-buffered pass tile, and at least two tiles' worth of activation stages;
   // relax one requirement at a time until the layer fits
-  const int nbuf = d.n_f32 > 0 ? 0 : 2;
   int stages = 0; size_t bytes = 0; bool found = false;
+  const int nbuf_hi = d.n_f32 > 0 ? 0 : ((g_cdn_debug_flags & 32u) ? 2 : 3), nbuf_lo = d.n_f32 > 0 ? 0 : 2;
   for (int want = 2; want >= 0 && !found; --want)            // tiles in flight we insist on (0: anything that runs)
     for (int resident = 1; resident >= 0 && !found; --resident)
-      for (int pass_bufs = d.has_pass ? 2 : 1; pass_bufs >= 1 && !found; --pass_bufs) {
-        int st = 0; const size_t by = plan(resident != 0, pass_bufs, nbuf, st);
-        const int need = std::max(2, std::min(want * d.num_k_blocks, want == 2 ? 8 : 3));
-        if (st >= need) { found = true; stages = st; bytes = by; d.resident = resident; d.pass_bufs = pass_bufs; d.nbuf = nbuf; }
-      }
+      // every epilogue group needs its own pass buffer(s): with a shared one a group could be two mbarrier phases behind
+      for (int pass_bufs = d.has_pass ? 4 : 2; pass_bufs >= 2 && !found; pass_bufs -= 2)
+        for (int nbuf = nbuf_hi; nbuf >= nbuf_lo && !found; --nbuf) {
+          int st = 0; const size_t by = plan(resident != 0, pass_bufs, nbuf, st);
+          const int need = std::max(2, std::min(want * d.num_k_blocks, want == 2 ? 8 : 3));
+          if (st >= need) { found = true; stages = st; bytes = by; d.resident = resident; d.pass_bufs = pass_bufs; d.nbuf = nbuf; }
+        }
   CDN_CHECK(stages >= 2, CDN_ERR_INVALID, "pw: layer does not fit in shared memory (K=%d N=%d BN=%d pass segs=%d)", d.K, d.N, d.BN, d.pass_segs);
   d.stages = stages;
   d.smem_bytes = bytes;
   if (int r = make_tmap_2d(&d.tmB, d.w, (uint64_t)d.Kp, (uint64_t)Np, (uint64_t)d.Kp, (uint32_t)d.BN)) return r;
+  return 0;
+}
+
+unsigned long long* g_pw_dbg = nullptr;
+static int g_pw_launch_index = 0;          // experiments: flags bits 8..15 select ONE launch (1-based) to instrument
+extern "C" int cdn_debug_read_cycles(unsigned long long* out16, int reset) {
+  if (!g_pw_dbg) { CDN_CUDA(cudaMalloc(&g_pw_dbg, 16 * 8)); CDN_CUDA(cudaMemset(g_pw_dbg, 0, 16 * 8)); }
+  CDN_CUDA(cudaDeviceSynchronize());
+  if (out16) CDN_CUDA(cudaMemcpy(out16, g_pw_dbg, 16 * 8, cudaMemcpyDeviceToHost));
+  if (reset) { CDN_CUDA(cudaMemset(g_pw_dbg, 0, 16 * 8)); g_pw_launch_index = 0; }
   return 0;
 }
 
@@ -652,7 +728,8 @@ int pw_launch(const PwDevice& d, const int8_t* in, int in_pitch, long long pixel
   p.m_tiles = (pixels + PW_BM - 1) / PW_BM; p.pixels = pixels;
   p.chunks = d.chunks; p.segs = (const PwSeg*)d.segs; p.tile_seg = d.tile_seg; p.kc = (const float4*)d.kc;
   p.M = d.rq.M; p.B = d.rq.B; p.acc_bias = d.rq.acc_bias;
-  p.lo_f = (float)d.rq.lo; p.thr = d.thr;
+  p.lo_f = (float)d.rq.lo; p.thr = d.thr; p.dbg = g_cdn_debug_flags; p.dbg_cyc = g_pw_dbg; if (!g_pw_dbg) p.dbg &= ~16u;
+  { const int sel = (int)((g_cdn_debug_flags >> 8) & 0xff); ++g_pw_launch_index; if (sel && sel != g_pw_launch_index) p.dbg &= ~16u; }
   p.n_f32 = d.n_f32; p.ppi = ppi; p.out_f32 = out_f32; p.Mf = d.Mf; p.bf = d.bf;
   p.in = in; p.in_pitch = in_pitch; p.pass = pass; p.pass_pitch = pass_pitch; p.out = out; p.out_pitch = out_pitch;
   p.w = d.w; p.Kp = d.Kp; p.N = d.BN * d.n_tiles;

@@ -18,6 +18,8 @@ class Engine:
     def __init__(self, plan: Plan, max_batch: int, device: int = 0, K: int = 100):
         self.plan, self.max_batch, self.device, self.K = plan, int(max_batch), int(device), int(K)
         self.lib = _lib.load()
+        if os.environ.get("CODENET_DEBUG_FLAGS"):          # kernel experiments only
+            self.lib.cdn_set_debug_flags(int(os.environ["CODENET_DEBUG_FLAGS"]))
         if os.environ.get("CODENET_PW_SIMT") == "1":      # bring-up switch: SIMT cross-check kernel for 1x1 convs
             self.lib.cdn_set_debug_flags(1)
         self._h = C.c_void_p()
