@@ -113,14 +113,16 @@ __device__ __noinline__ uint32_t dw_rq_word_exact(int a0, int a1, int a2, int a3
   return pack4_lowbytes(r0, r1, r2, r3);
 }
 
-// one stored row -> per-channel words of 4 (or 3) horizontally adjacent stored pixels; xo[j] = word offset of pixel j
-// inside the row or -1 when that pixel is outside the image (or unused)
-__device__ __forceinline__ void dw_load_row(const uint32_t* __restrict__ row, bool yok, const int (&xo)[4], uint32_t pad,
-                                            uint32_t (&T)[4]) {
-  if (!yok) { T[0] = T[1] = T[2] = T[3] = pad; return; }
-  uint32_t w[4];
+// one stored row -> raw pixel words (4 channels each) of 4 (or 3) horizontally adjacent stored pixels; xo[j] = word
+// offset of pixel j inside the row, or -1 when that pixel is outside the image (or unused).  Fetch and transpose are
+// split so that the loads of the NEXT row are issued a whole loop iteration before they are consumed (these kernels
+// were load-latency bound: 60% of the stall samples sat on the first PRMT after the row's LDGs).
+__device__ __forceinline__ void dw_fetch_row(const uint32_t* __restrict__ row, bool yok, const int (&xo)[4], uint32_t pad,
+                                             uint32_t (&w)[4]) {
 #pragma unroll
-  for (int j = 0; j < 4; ++j) w[j] = xo[j] >= 0 ? __ldg(row + xo[j]) : pad;
+  for (int j = 0; j < 4; ++j) w[j] = (yok && xo[j] >= 0) ? __ldg(row + xo[j]) : pad;
+}
+__device__ __forceinline__ void dw_transpose_row(const uint32_t (&w)[4], uint32_t (&T)[4]) {
   transpose4x4(w[0], w[1], w[2], w[3], T[0], T[1], T[2], T[3]);
 }
 
@@ -160,43 +162,62 @@ __global__ void __launch_bounds__(128) dw3x3_v2_kernel(const DwV2Params p) {
     xo[j] = ((STRIDE == 2 || SHIFT) && j == 3) || (unsigned)xx >= (unsigned)p.Ws ? -1 : xx * p.in_pitch_w;
   }
 
-  if (STRIDE == 1 && SHIFT == 0) {
-    const int x0 = 2 * pg, y0 = strip * p.R, y1 = min(y0 + p.R, p.Hout);
-    uint32_t Tm[4], Tc[4], Tp[4];
+  if (STRIDE == 1) {
+    // SHIFT 0: output pixels x0, x0+1 of rows y0..y1-1.  SHIFT 1: stored column pg, stored rows y0..y1-1 -> output
+    // rows 2r, 2r+1 and columns 2pg, 2pg+1.  Both walk stored rows r with the window (r-1, r, r+1).
+    const int rows = SHIFT ? p.Hs : p.Hout;
+    const int y0 = strip * p.R, y1 = min(y0 + p.R, rows);
+    uint32_t Tm[4], Tc[4], Tp[4], raw[4];
     const uint32_t* row = img + (y0 - 1) * rs_in;                          // may point before the image; guarded by yok
-    dw_load_row(row, y0 >= 1, xo, p.pad_word, Tm); row += rs_in;
-    dw_load_row(row, true, xo, p.pad_word, Tc); row += rs_in;
-    uint32_t* o = outb + (y0 * p.Wout + x0) * p.out_pitch_w;
+    dw_fetch_row(row, y0 >= 1, xo, p.pad_word, raw); dw_transpose_row(raw, Tm); row += rs_in;
+    dw_fetch_row(row, true, xo, p.pad_word, raw); dw_transpose_row(raw, Tc); row += rs_in;
+    dw_fetch_row(row, y0 + 1 < p.Hs, xo, p.pad_word, raw); row += rs_in;  // row y0+1, consumed in the first iteration
+    const int x0 = 2 * pg;
+    uint32_t* o = outb + ((SHIFT ? 2 * y0 : y0) * p.Wout + x0) * p.out_pitch_w;
     const bool two = x0 + 1 < p.Wout;
     for (int y = y0; y < y1; ++y) {
-      dw_load_row(row, y + 1 < p.Hs, xo, p.pad_word, Tp); row += rs_in;
-      int a0[4], a1[4];
+      dw_transpose_row(raw, Tp);
+      dw_fetch_row(row, y + 2 < p.Hs && y + 1 < y1, xo, p.pad_word, raw); row += rs_in;   // prefetch for the next iteration
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        a0[c] = dp4a_ss(Tp[c], W[c][4], dp4a_ss(Tc[c], W[c][2], dp4a_ss(Tm[c], W[c][0], k.abm[c])));
-        a1[c] = dp4a_ss(Tp[c], W[c][5], dp4a_ss(Tc[c], W[c][3], dp4a_ss(Tm[c], W[c][1], k.abm[c])));
+      for (int yp = 0; yp < (SHIFT ? 2 : 1); ++yp) {
+        int a0[4], a1[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (SHIFT) {
+            const uint32_t ta = yp ? Tc[c] : Tm[c], tb = yp ? Tp[c] : Tc[c];
+            a0[c] = dp4a_ss(tb, W[c][(4 * yp + 2) % NW], dp4a_ss(ta, W[c][(4 * yp + 0) % NW], k.abm[c]));
+            a1[c] = dp4a_ss(tb, W[c][(4 * yp + 3) % NW], dp4a_ss(ta, W[c][(4 * yp + 1) % NW], k.abm[c]));
+          } else {
+            a0[c] = dp4a_ss(Tp[c], W[c][4 % NW], dp4a_ss(Tc[c], W[c][2], dp4a_ss(Tm[c], W[c][0], k.abm[c])));
+            a1[c] = dp4a_ss(Tp[c], W[c][5 % NW], dp4a_ss(Tc[c], W[c][3 % NW], dp4a_ss(Tm[c], W[c][1], k.abm[c])));
+          }
+        }
+        RqGuard g; rq_guard_init(g);
+        uint32_t o0 = dw_rq_word(a0, k, p.lo_f, g), o1 = dw_rq_word(a1, k, p.lo_f, g);
+        if (rq_group_bad(g, p.thr)) {
+          o0 = dw_rq_word_exact(a0[0], a0[1], a0[2], a0[3], p.M, p.B, ch0, p.lo_f);
+          o1 = dw_rq_word_exact(a1[0], a1[1], a1[2], a1[3], p.M, p.B, ch0, p.lo_f);
+        }
+        o[0] = o0;
+        if (SHIFT || two) o[p.out_pitch_w] = o1;
+        o += p.Wout * p.out_pitch_w;
       }
-      RqGuard g; rq_guard_init(g);
-      uint32_t o0 = dw_rq_word(a0, k, p.lo_f, g), o1 = dw_rq_word(a1, k, p.lo_f, g);
-      if (rq_group_bad(g, p.thr)) {
-        o0 = dw_rq_word_exact(a0[0], a0[1], a0[2], a0[3], p.M, p.B, ch0, p.lo_f);
-        o1 = dw_rq_word_exact(a1[0], a1[1], a1[2], a1[3], p.M, p.B, ch0, p.lo_f);
-      }
-      o[0] = o0;
-      if (two) o[p.out_pitch_w] = o1;
-      o += p.Wout * p.out_pitch_w;
 #pragma unroll
       for (int c = 0; c < 4; ++c) { Tm[c] = Tc[c]; Tc[c] = Tp[c]; }
     }
-  } else if (STRIDE == 2) {
+  } else {
     const int xo_ = pg, y0 = strip * p.R, y1 = min(y0 + p.R, p.Hout);
-    uint32_t Tm[4], Tc[4], Tp[4];
+    uint32_t Tm[4], Tc[4], Tp[4], rawc[4], rawp[4];
     const uint32_t* row = img + (2 * y0 - 1) * rs_in;
-    dw_load_row(row, y0 >= 1, xo, p.pad_word, Tm); row += rs_in;
+    dw_fetch_row(row, y0 >= 1, xo, p.pad_word, rawc); dw_transpose_row(rawc, Tm); row += rs_in;
+    dw_fetch_row(row, true, xo, p.pad_word, rawc); row += rs_in;
+    dw_fetch_row(row, 2 * y0 + 1 < p.Hs, xo, p.pad_word, rawp); row += rs_in;
     uint32_t* o = outb + (y0 * p.Wout + xo_) * p.out_pitch_w;
     for (int y = y0; y < y1; ++y) {
-      dw_load_row(row, true, xo, p.pad_word, Tc); row += rs_in;
-      dw_load_row(row, 2 * y + 1 < p.Hs, xo, p.pad_word, Tp); row += rs_in;
+      dw_transpose_row(rawc, Tc); dw_transpose_row(rawp, Tp);
+      const bool more = y + 1 < y1;
+      dw_fetch_row(row, more, xo, p.pad_word, rawc); row += rs_in;                            // rows 2(y+1), 2(y+1)+1
+      dw_fetch_row(row, more && 2 * y + 3 < p.Hs, xo, p.pad_word, rawp); row += rs_in;
       int a0[4];
 #pragma unroll
       for (int c = 0; c < 4; ++c)
@@ -208,37 +229,6 @@ __global__ void __launch_bounds__(128) dw3x3_v2_kernel(const DwV2Params p) {
       o += p.Wout * p.out_pitch_w;
 #pragma unroll
       for (int c = 0; c < 4; ++c) Tm[c] = Tp[c];
-    }
-  } else {
-    // SHIFT 1: stored pixel column s = pg, stored rows r0 .. r1-1 -> output rows 2r, 2r+1 and columns 2s, 2s+1
-    const int s_ = pg, r0 = strip * p.R, r1 = min(r0 + p.R, p.Hs);
-    uint32_t Tm[4], Tc[4], Tp[4];
-    const uint32_t* row = img + (r0 - 1) * rs_in;
-    dw_load_row(row, r0 >= 1, xo, p.pad_word, Tm); row += rs_in;
-    dw_load_row(row, true, xo, p.pad_word, Tc); row += rs_in;
-    uint32_t* o = outb + (2 * r0 * p.Wout + 2 * s_) * p.out_pitch_w;
-    for (int r = r0; r < r1; ++r) {
-      dw_load_row(row, r + 1 < p.Hs, xo, p.pad_word, Tp); row += rs_in;
-#pragma unroll
-      for (int yp = 0; yp < 2; ++yp) {
-        int a0[4], a1[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const uint32_t ta = yp ? Tc[c] : Tm[c], tb = yp ? Tp[c] : Tc[c];
-          a0[c] = dp4a_ss(tb, W[c][4 * yp + 2], dp4a_ss(ta, W[c][4 * yp + 0], k.abm[c]));
-          a1[c] = dp4a_ss(tb, W[c][4 * yp + 3], dp4a_ss(ta, W[c][4 * yp + 1], k.abm[c]));
-        }
-        RqGuard g; rq_guard_init(g);
-        uint32_t o0 = dw_rq_word(a0, k, p.lo_f, g), o1 = dw_rq_word(a1, k, p.lo_f, g);
-        if (rq_group_bad(g, p.thr)) {
-          o0 = dw_rq_word_exact(a0[0], a0[1], a0[2], a0[3], p.M, p.B, ch0, p.lo_f);
-          o1 = dw_rq_word_exact(a1[0], a1[1], a1[2], a1[3], p.M, p.B, ch0, p.lo_f);
-        }
-        o[0] = o0; o[p.out_pitch_w] = o1;
-        o += p.Wout * p.out_pitch_w;
-      }
-#pragma unroll
-      for (int c = 0; c < 4; ++c) { Tm[c] = Tc[c]; Tc[c] = Tp[c]; }
     }
   }
 }
@@ -321,26 +311,21 @@ __global__ void __launch_bounds__(256) deform_dw_v2_kernel(const DwParams p) {
         const float2 mb = active ? __ldg(p.mb + cw * 4 + c) : make_float2(0.f, 0.f);
         Mh[c] = mb.x; Bh[c] = mb.y; abm[c] = active ? __ldg(p.abm + cw * 4 + c) : CDN_MAGIC_I;
       }
-#pragma unroll 1
-      for (int j = wslot; j < DEF_NP; j += nslot) {
-        const long long pix = base + j;
-        if (pix >= p.total || !active) continue;
-        const uint32_t hw = s_hw[j];
-        const int w = (int)(hw & 0xffffu), h = (int)(hw >> 16);
-        const uint32_t* img = p.in + s_b[j] + cw;
-        const double s = s_s[j];
-        if (MODE == 0) {
-          const int si = s_si[j];
-          // rows / columns of the dilated 3x3 stencil: clamped 32-bit offsets (loads are unconditional), validity flags
+      if (MODE == 0) {
+        // software pipeline: the 9 taps of the NEXT pixel are in flight while this pixel is transposed, MAC-ed and
+        // requantised (the gather is latency-bound otherwise)
+        auto fetch = [&](int j, uint32_t (&x)[9]) {
+          const uint32_t hw = s_hw[j];
+          const int w = (int)(hw & 0xffffu), h = (int)(hw >> 16), si = s_si[j];
+          const uint32_t* img = p.in + s_b[j] + cw;
           int ro[3], co[3]; bool yok[3], xok[3];
 #pragma unroll
           for (int i = 0; i < 3; i += 2) {
-            const int y = h + (i - 1) * si, x = w + (i - 1) * si;
-            yok[i] = (unsigned)y < (unsigned)p.Hin; xok[i] = (unsigned)x < (unsigned)p.Win;
-            ro[i] = (min(max(y, 0), p.Hin - 1) >> p.shift) * rs_in; co[i] = (min(max(x, 0), p.Win - 1) >> p.shift) * p.in_pitch_w;
+            const int y = h + (i - 1) * si, xx = w + (i - 1) * si;
+            yok[i] = (unsigned)y < (unsigned)p.Hin; xok[i] = (unsigned)xx < (unsigned)p.Win;
+            ro[i] = (min(max(y, 0), p.Hin - 1) >> p.shift) * rs_in; co[i] = (min(max(xx, 0), p.Win - 1) >> p.shift) * p.in_pitch_w;
           }
           yok[1] = xok[1] = true; ro[1] = (h >> p.shift) * rs_in; co[1] = (w >> p.shift) * p.in_pitch_w;
-          uint32_t x[9];
 #pragma unroll
           for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -349,6 +334,20 @@ __global__ void __launch_bounds__(256) deform_dw_v2_kernel(const DwParams p) {
           for (int i = 0; i < 3; ++i)
 #pragma unroll
             for (int jj = 0; jj < 3; ++jj) if (!(yok[i] && xok[jj])) x[i * 3 + jj] = p.pad_word;
+        };
+        uint32_t xn[9];
+        bool vn = active && base + wslot < p.total;
+        if (vn) fetch(wslot, xn);
+#pragma unroll 1
+        for (int j = wslot; j < DEF_NP; j += nslot) {
+          uint32_t x[9];
+#pragma unroll
+          for (int i = 0; i < 9; ++i) x[i] = xn[i];
+          const bool v = vn;
+          const int jn = j + nslot;
+          vn = active && jn < DEF_NP && base + jn < p.total;
+          if (vn) fetch(jn, xn);
+          if (!v) continue;
           uint32_t a0, a1, a2, a3, b0, b1, b2, b3;
           transpose4x4(x[0], x[1], x[2], x[3], a0, a1, a2, a3);
           transpose4x4(x[4], x[5], x[6], x[7], b0, b1, b2, b3);
@@ -362,8 +361,18 @@ __global__ void __launch_bounds__(256) deform_dw_v2_kernel(const DwParams p) {
           const uint32_t r2 = rq_fast<0>(acc[2], Mh[2], Bh[2], p.lo_f, gd), r3 = rq_fast<1>(acc[3], Mh[3], Bh[3], p.lo_f, gd);
           uint32_t o = pack4_lowbytes(r0, r1, r2, r3);
           if (rq_group_bad(gd, p.thr_layer)) o = dw_rq_word_exact(acc[0], acc[1], acc[2], acc[3], p.M, p.B, cw * 4, p.lo_f);
-          p.out[(size_t)pix * p.out_pitch_w + cw] = o;
-        } else {
+          p.out[(size_t)(base + j) * p.out_pitch_w + cw] = o;
+        }
+      } else {
+#pragma unroll 1
+      for (int j = wslot; j < DEF_NP; j += nslot) {
+        const long long pix = base + j;
+        if (pix >= p.total || !active) continue;
+        const uint32_t hw = s_hw[j];
+        const int w = (int)(hw & 0xffffu), h = (int)(hw >> 16);
+        const uint32_t* img = p.in + s_b[j] + cw;
+        const double s = s_s[j];
+        {
         // bilinear: real values a = q + zx, zero outside the image
         const int zx = -(int)(int8_t)(p.pad_word & 0xff);
         const double d = __dsub_rn(s, 1.0);
@@ -417,6 +426,7 @@ __global__ void __launch_bounds__(256) deform_dw_v2_kernel(const DwParams p) {
         }
           p.out[(size_t)pix * p.out_pitch_w + cw] = r[0] | (r[1] << 8) | (r[2] << 16) | (r[3] << 24);
         }
+      }
       }
     }
     __syncthreads();                         // s_s is rewritten by the next tile
