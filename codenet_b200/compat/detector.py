@@ -155,13 +155,31 @@ class CtdetDetector:
                 'out_width': inp_width // self.opt.down_ratio}
         return images, meta
 
+    def _engine_for(self, H, W, batch, device):
+        eng = self.model.compile_engine(H, W, max(batch, getattr(self.opt, "max_batch", 1)), device=device, K=self.opt.K)
+        if not getattr(eng, "_norm", False):
+            eng.set_normalization(self.mean.reshape(3), self.std.reshape(3))
+        return eng
+
+    def process_u8(self, images_u8, return_time=False):
+        """Fast path of run(): uint8 [B,H,W,3] images already at the network's input size (then the reference's
+        resize + warpAffine of pre_process are the identity and only the normalisation is left, which the stem kernel
+        applies).  CUDA tensor in, same outputs as process()."""
+        B, H, W, _ = images_u8.shape
+        dev = images_u8.device.index if images_u8.device.index is not None else torch.cuda.current_device()
+        out = self._engine_for(H, W, B, dev).run(images_u8.contiguous(), maps=True, dets=True)
+        torch.cuda.synchronize(images_u8.device)
+        forward_time = time.time()
+        output = {h: out[h] for h in self.opt.heads}
+        return (output, out["dets"], forward_time) if return_time else (output, out["dets"])
+
     def process(self, images, return_time=False):
         """images: CUDA fp32 [B,3,H,W].  Returns (output {'hm' (post-sigmoid), 'wh', 'reg'}, dets [B|1,K,6][, time])."""
         if not images.is_cuda:
             raise RuntimeError("codenet_b200 has no CPU execution path: process() needs CUDA images")
         B, _, H, W = images.shape
         dev = images.device.index if images.device.index is not None else torch.cuda.current_device()
-        eng = self.model.compile_engine(H, W, max(B, getattr(self.opt, "max_batch", 1)), device=dev, K=self.opt.K)
+        eng = self._engine_for(H, W, B, dev)
         x = images.contiguous().float()
         if not self.opt.flip_test:
             # forward + sigmoid + decode in one graph replay; `hm` comes back post-sigmoid like output['hm'].sigmoid_()
@@ -223,7 +241,15 @@ class CtdetDetector:
         detections = []
         for scale in self.scales:
             scale_start_time = time.time()
-            if not pre_processed:
+            fast = (not pre_processed and scale == 1 and not self.opt.flip_test and self.opt.fix_res and
+                    image.dtype == np.uint8 and image.shape[:2] == (self.opt.input_h, self.opt.input_w))
+            if fast:
+                # identity resize/affine: ship the uint8 image, normalise inside the stem kernel
+                h, w = image.shape[:2]
+                meta = {'c': np.array([w / 2., h / 2.], dtype=np.float32), 's': max(h, w) * 1.0,
+                        'out_height': h // self.opt.down_ratio, 'out_width': w // self.opt.down_ratio}
+                images = torch.from_numpy(np.ascontiguousarray(image[None]))
+            elif not pre_processed:
                 images, meta = self.pre_process(image, scale, meta)
             else:
                 images = pre_processed_images['images'][scale][0]
@@ -233,7 +259,10 @@ class CtdetDetector:
             torch.cuda.synchronize()
             pre_process_time = time.time()
             pre_time += pre_process_time - scale_start_time
-            output, dets, forward_time = self.process(images, return_time=True)
+            if fast:
+                output, dets, forward_time = self.process_u8(images, return_time=True)
+            else:
+                output, dets, forward_time = self.process(images, return_time=True)
             torch.cuda.synchronize()
             net_time += forward_time - pre_process_time
             decode_time = time.time()

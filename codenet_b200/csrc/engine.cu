@@ -156,6 +156,7 @@ struct cdn_engine {
   int8_t* stem_tmp = nullptr;
   // host path
   float* d_img = nullptr; size_t d_img_bytes = 0;
+  float* lut = nullptr;                      // 3 x 256 normalisation table for uint8 input
   cudaStream_t s_compute = nullptr, s_copy = nullptr;
   std::vector<cudaEvent_t> ev;
   int host_chunk = 32, use_graph = 1, micro_batch = 0, hm_logits = 0;
@@ -197,7 +198,7 @@ extern "C" int cdn_engine_destroy(cdn_engine* e) {
   for (auto& g : e->graphs) cudaGraphExecDestroy(g.second);
   for (auto* op : e->ops) { stem_device_free(op->stem); dw_device_free(op->dw); pw_device_free(op->pw); delete op; }
   for (auto& t : e->tensors) cudaFree(t.ptr);
-  cudaFree(e->heads); cudaFree(e->dec_scratch); cudaFree(e->dets); cudaFree(e->inds); cudaFree(e->stem_tmp); cudaFree(e->d_img);
+  cudaFree(e->heads); cudaFree(e->dec_scratch); cudaFree(e->dets); cudaFree(e->inds); cudaFree(e->stem_tmp); cudaFree(e->d_img); cudaFree(e->lut);
   for (auto ev : e->ev) cudaEventDestroy(ev);
   if (e->s_compute) cudaStreamDestroy(e->s_compute);
   if (e->s_copy) cudaStreamDestroy(e->s_copy);
@@ -343,7 +344,8 @@ extern "C" int cdn_engine_finalize(cdn_engine* e, int max_batch) {
   return 0;
 }
 
-static int engine_enqueue(cdn_engine* e, const float* d_img, int batch, float* d_hm, float* d_wh, float* d_reg,
+// d_img: fp32 NCHW image, or (is_u8) uint8 NHWC image normalised in the stem through e->lut
+static int engine_enqueue(cdn_engine* e, const void* d_img, int is_u8, int batch, float* d_hm, float* d_wh, float* d_reg,
                           float* d_dets, int32_t* d_inds, cudaStream_t st, std::vector<cudaEvent_t>* marks = nullptr) {
   int launches = 0;
   auto mark = [&]() { if (marks) { cudaEvent_t ev; cudaEventCreate(&ev); cudaEventRecord(ev, st); marks->push_back(ev); } };
@@ -353,7 +355,8 @@ static int engine_enqueue(cdn_engine* e, const float* d_img, int batch, float* d
     switch (op->kind) {
       case 0: {
         const EngTensor& to = e->tensors[op->out_t];
-        r = stem_launch(op->stem, d_img, batch, op->H, op->W, op->stride, op->pool, to.ptr, to.pitch, e->stem_tmp, st);
+        r = stem_launch(op->stem, is_u8 ? nullptr : (const float*)d_img, batch, op->H, op->W, op->stride, op->pool, to.ptr, to.pitch,
+                        e->stem_tmp, st, is_u8 ? (const uint8_t*)d_img : nullptr, e->lut);
         launches += op->pool ? 2 : 1;
       } break;
       case 1: {
@@ -411,7 +414,7 @@ extern "C" int cdn_engine_profile(cdn_engine* e, const float* d_img, int batch, 
   CDN_CHECK(n >= (int)e->ops.size() + 2, CDN_ERR_INVALID, "profile: need room for %d timings", (int)e->ops.size() + 2);
   CDN_CUDA(cudaSetDevice(e->device));
   std::vector<cudaEvent_t> marks;
-  int r = engine_enqueue(e, d_img, batch, nullptr, nullptr, nullptr, e->dets, e->inds, (cudaStream_t)stream, &marks);
+  int r = engine_enqueue(e, d_img, 0, batch, nullptr, nullptr, nullptr, e->dets, e->inds, (cudaStream_t)stream, &marks);
   cudaError_t ce = cudaStreamSynchronize((cudaStream_t)stream);
   if (!r && ce != cudaSuccess) r = cdn_fail(CDN_ERR_CUDA, "profile: %s", cudaGetErrorString(ce));
   for (int i = 0; i < n; ++i) ms[i] = 0.f;
@@ -420,23 +423,24 @@ extern "C" int cdn_engine_profile(cdn_engine* e, const float* d_img, int batch, 
   return r;
 }
 
-extern "C" int cdn_engine_run(cdn_engine* e, const float* d_img, int batch, float* d_hm, float* d_wh, float* d_reg,
-                              float* d_dets, int32_t* d_inds, cdn_stream_t stream) {
+static int engine_run_any(cdn_engine* e, const void* d_img, int is_u8, int batch, float* d_hm, float* d_wh, float* d_reg,
+                          float* d_dets, int32_t* d_inds, cdn_stream_t stream) {
   ENG_CHECK(e);
   CDN_CHECK(e->finalized, CDN_ERR_STATE, "engine not finalized");
   CDN_CHECK(batch >= 0 && batch <= e->max_batch, CDN_ERR_INVALID, "batch %d exceeds the finalized maximum %d", batch, e->max_batch);
   CDN_CHECK(d_img != nullptr, CDN_ERR_INVALID, "null image pointer");
+  CDN_CHECK(!is_u8 || e->lut != nullptr, CDN_ERR_STATE, "uint8 input needs cdn_engine_set_normalization first");
   if (batch == 0) return 0;
   CDN_CUDA(cudaSetDevice(e->device));
   cudaStream_t st = (cudaStream_t)stream;
-  if (!e->use_graph || (g_cdn_debug_flags & 2u)) return engine_enqueue(e, d_img, batch, d_hm, d_wh, d_reg, d_dets, d_inds, st);
+  if (!e->use_graph || (g_cdn_debug_flags & 2u)) return engine_enqueue(e, d_img, is_u8, batch, d_hm, d_wh, d_reg, d_dets, d_inds, st);
   cdn_engine::GraphKey key; memset(&key, 0, sizeof(key));
-  key.a[0] = d_img; key.a[1] = d_hm; key.a[2] = d_wh; key.a[3] = d_reg; key.a[4] = d_dets; key.a[5] = d_inds; key.batch = batch | (e->hm_logits << 30);
+  key.a[0] = d_img; key.a[1] = d_hm; key.a[2] = d_wh; key.a[3] = d_reg; key.a[4] = d_dets; key.a[5] = d_inds; key.batch = batch | (e->hm_logits << 30) | (is_u8 << 29);
   for (auto& g : e->graphs) if (g.first == key) { CDN_CUDA(cudaGraphLaunch(g.second, st)); return 0; }
   // capture once per (pointers, batch)
   cudaStream_t cap = e->s_compute;
   CDN_CUDA(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
-  int r = engine_enqueue(e, d_img, batch, d_hm, d_wh, d_reg, d_dets, d_inds, cap);
+  int r = engine_enqueue(e, d_img, is_u8, batch, d_hm, d_wh, d_reg, d_dets, d_inds, cap);
   cudaGraph_t graph = nullptr;
   cudaError_t ce = cudaStreamEndCapture(cap, &graph);
   if (r) { if (graph) cudaGraphDestroy(graph); return r; }
@@ -451,15 +455,39 @@ extern "C" int cdn_engine_run(cdn_engine* e, const float* d_img, int batch, floa
   return 0;
 }
 
-extern "C" int cdn_engine_run_host(cdn_engine* e, const float* h_img, int batch, float* h_dets, int32_t* h_inds) {
+extern "C" int cdn_engine_run(cdn_engine* e, const float* d_img, int batch, float* d_hm, float* d_wh, float* d_reg,
+                              float* d_dets, int32_t* d_inds, cdn_stream_t stream) {
+  return engine_run_any(e, d_img, 0, batch, d_hm, d_wh, d_reg, d_dets, d_inds, stream);
+}
+extern "C" int cdn_engine_run_u8(cdn_engine* e, const uint8_t* d_img, int batch, float* d_hm, float* d_wh, float* d_reg,
+                                 float* d_dets, int32_t* d_inds, cdn_stream_t stream) {
+  return engine_run_any(e, d_img, 1, batch, d_hm, d_wh, d_reg, d_dets, d_inds, stream);
+}
+
+// LUT[c][u] = fl32((u / 255. - mean[c]) / std[c]) evaluated in double exactly as numpy evaluates
+// ((inp_image / 255. - self.mean) / self.std).astype(np.float32), lib/detectors/base_detector.py:66
+extern "C" int cdn_engine_set_normalization(cdn_engine* e, const float* mean3, const float* std3) {
+  ENG_CHECK(e);
+  CDN_CHECK(mean3 && std3, CDN_ERR_INVALID, "set_normalization: null pointer");
+  CDN_CUDA(cudaSetDevice(e->device));
+  std::vector<float> lut(768);
+  for (int c = 0; c < 3; ++c)
+    for (int u = 0; u < 256; ++u) lut[c * 256 + u] = (float)(((double)u / 255.0 - (double)mean3[c]) / (double)std3[c]);
+  if (!e->lut) CDN_CUDA(cudaMalloc((void**)&e->lut, 768 * sizeof(float)));
+  CDN_CUDA(cudaMemcpy(e->lut, lut.data(), 768 * sizeof(float), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+static int engine_run_host_any(cdn_engine* e, const void* h_img_v, int is_u8, int batch, float* h_dets, int32_t* h_inds) {
+  const uint8_t* h_img = (const uint8_t*)h_img_v;
   ENG_CHECK(e);
   CDN_CHECK(e->finalized, CDN_ERR_STATE, "engine not finalized");
   CDN_CHECK(batch >= 0 && batch <= e->max_batch && h_img && h_dets, CDN_ERR_INVALID, "run_host: bad arguments");
   if (batch == 0) return 0;
   CDN_CUDA(cudaSetDevice(e->device));
-  const size_t img_elems = (size_t)3 * e->in_H * e->in_W;
+  const size_t img_bytes = (size_t)3 * e->in_H * e->in_W * (is_u8 ? 1 : sizeof(float));   // per image
   if (!e->d_img) {
-    e->d_img_bytes = (size_t)e->max_batch * img_elems * sizeof(float);
+    e->d_img_bytes = (size_t)e->max_batch * 3 * e->in_H * e->in_W * sizeof(float);
     CDN_CUDA(cudaMalloc((void**)&e->d_img, e->d_img_bytes));
   }
   const int chunk = std::min(batch, e->host_chunk);
@@ -468,20 +496,27 @@ extern "C" int cdn_engine_run_host(cdn_engine* e, const float* h_img, int batch,
   // H2D of chunk i+1 overlaps the compute of chunk i (two streams, one event per chunk)
   for (int c = 0; c < nchunks; ++c) {
     int b0 = c * chunk, nb = std::min(chunk, batch - b0);
-    CDN_CUDA(cudaMemcpyAsync(e->d_img + (size_t)b0 * img_elems, h_img + (size_t)b0 * img_elems, (size_t)nb * img_elems * sizeof(float),
+    CDN_CUDA(cudaMemcpyAsync((uint8_t*)e->d_img + (size_t)b0 * img_bytes, h_img + (size_t)b0 * img_bytes, (size_t)nb * img_bytes,
                              cudaMemcpyHostToDevice, e->s_copy));
     CDN_CUDA(cudaEventRecord(e->ev[c], e->s_copy));
   }
   for (int c = 0; c < nchunks; ++c) {
     int b0 = c * chunk, nb = std::min(chunk, batch - b0);
     CDN_CUDA(cudaStreamWaitEvent(e->s_compute, e->ev[c], 0));
-    if (int r = cdn_engine_run(e, e->d_img + (size_t)b0 * img_elems, nb, nullptr, nullptr, nullptr,
+    if (int r = engine_run_any(e, (uint8_t*)e->d_img + (size_t)b0 * img_bytes, is_u8, nb, nullptr, nullptr, nullptr,
                                e->dets + (size_t)b0 * e->K * 6, e->inds + (size_t)b0 * e->K, e->s_compute)) return r;
   }
   CDN_CUDA(cudaMemcpyAsync(h_dets, e->dets, (size_t)batch * e->K * 6 * sizeof(float), cudaMemcpyDeviceToHost, e->s_compute));
   if (h_inds) CDN_CUDA(cudaMemcpyAsync(h_inds, e->inds, (size_t)batch * e->K * sizeof(int32_t), cudaMemcpyDeviceToHost, e->s_compute));
   CDN_CUDA(cudaStreamSynchronize(e->s_compute));
   return 0;
+}
+
+extern "C" int cdn_engine_run_host(cdn_engine* e, const float* h_img, int batch, float* h_dets, int32_t* h_inds) {
+  return engine_run_host_any(e, h_img, 0, batch, h_dets, h_inds);
+}
+extern "C" int cdn_engine_run_host_u8(cdn_engine* e, const uint8_t* h_img, int batch, float* h_dets, int32_t* h_inds) {
+  return engine_run_host_any(e, h_img, 1, batch, h_dets, h_inds);
 }
 
 extern "C" int cdn_engine_read_tensor(cdn_engine* e, int tensor, int batch, int8_t* h_out) {

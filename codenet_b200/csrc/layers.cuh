@@ -21,7 +21,8 @@ struct StemDevice { double* w = nullptr; double* M = nullptr; double* B = nullpt
 int stem_device_build(StemDevice& d, const int8_t* wq, int C, const cdn_requant* rq);
 void stem_device_free(StemDevice& d);
 int stem_launch(const StemDevice& d, const float* img, int batch, int H, int W, int stride, int pool,
-                int8_t* out, int out_pitch, int8_t* tmp, cudaStream_t st);
+                int8_t* out, int out_pitch, int8_t* tmp, cudaStream_t st, const uint8_t* img_u8 = nullptr,
+                const float* lut = nullptr);
 
 struct PwDevice {
   int K = 0, k_off = 0, N = 0, Kp = 0, BN = 0, n_tiles = 0, num_k_blocks = 0, stages = 0;

@@ -7,7 +7,7 @@
 #define STEM_MAXC 32
 
 struct StemParams {
-  const float* img; int8_t* out;
+  const float* img; const uint8_t* img_u8; const float* lut; int8_t* out;   // img_u8 != nullptr: uint8 HWC input + LUT
   int H, W, Ho, Wo, stride, C, out_pitch;
   long long total;
   const double* w;                           // [C][27] as doubles
@@ -15,19 +15,25 @@ struct StemParams {
   double lo;
 };
 
+// U8 = true: the image arrives as uint8 [B][H][W][3] (what cv2 hands to the reference's pre_process,
+// lib/detectors/base_detector.py:48-76) and is normalised through a 3x256 look-up table holding
+// fl32((u/255. - mean[c]) / std[c]) exactly as numpy evaluates it (:66), so the result is bit-identical to feeding the
+// pre-normalised fp32 image -- with a quarter of the host-to-device bytes.
+template <bool U8>
 __global__ void __launch_bounds__(128) stem_kernel(StemParams p) {
   __shared__ double sw[STEM_MAXC * 27];
   __shared__ double sM[STEM_MAXC], sB[STEM_MAXC];
+  __shared__ float slut[U8 ? 768 : 1];
   for (int i = threadIdx.x; i < p.C * 27; i += blockDim.x) sw[i] = p.w[i];
   for (int i = threadIdx.x; i < p.C; i += blockDim.x) { sM[i] = p.M[i]; sB[i] = p.B[i]; }
+  if (U8) for (int i = threadIdx.x; i < 768; i += blockDim.x) slut[i] = p.lut[i];
   __syncthreads();
   long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= p.total) return;
   int wo = (int)(pix % p.Wo); long long t = pix / p.Wo; int ho = (int)(t % p.Ho); long long b = t / p.Ho;
   double x[27];
-#pragma unroll
-  for (int ci = 0; ci < 3; ++ci) {
-    const float* plane = p.img + ((size_t)b * 3 + ci) * p.H * p.W;
+  if (U8) {
+    const uint8_t* im = p.img_u8 + (size_t)b * p.H * p.W * 3;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       int y = ho * p.stride - 1 + i;
@@ -35,7 +41,24 @@ __global__ void __launch_bounds__(128) stem_kernel(StemParams p) {
       for (int j = 0; j < 3; ++j) {
         int xx = wo * p.stride - 1 + j;
         bool ok = (unsigned)y < (unsigned)p.H && (unsigned)xx < (unsigned)p.W;
-        x[ci * 9 + i * 3 + j] = ok ? (double)__ldg(plane + (size_t)y * p.W + xx) : 0.0;
+        const uint8_t* px = im + ((size_t)y * p.W + xx) * 3;
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci) x[ci * 9 + i * 3 + j] = ok ? (double)slut[ci * 256 + __ldg(px + ci)] : 0.0;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci) {
+      const float* plane = p.img + ((size_t)b * 3 + ci) * p.H * p.W;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        int y = ho * p.stride - 1 + i;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          int xx = wo * p.stride - 1 + j;
+          bool ok = (unsigned)y < (unsigned)p.H && (unsigned)xx < (unsigned)p.W;
+          x[ci * 9 + i * 3 + j] = ok ? (double)__ldg(plane + (size_t)y * p.W + xx) : 0.0;
+        }
       }
     }
   }
@@ -89,18 +112,20 @@ void stem_device_free(StemDevice& d) { cudaFree(d.w); cudaFree(d.M); cudaFree(d.
 
 // tmp: scratch for the un-pooled map when pool != 0 (batch*Ho*Wo*out_pitch bytes), else unused.
 int stem_launch(const StemDevice& d, const float* img, int batch, int H, int W, int stride, int pool,
-                int8_t* out, int out_pitch, int8_t* tmp, cudaStream_t st) {
+                int8_t* out, int out_pitch, int8_t* tmp, cudaStream_t st, const uint8_t* img_u8, const float* lut) {
   CDN_CHECK(out_pitch == 32, CDN_ERR_INVALID, "stem: out pitch must be 32");
   CDN_CHECK(stride >= 1 && stride <= 4, CDN_ERR_INVALID, "stem: bad stride");
   StemParams p;
-  p.img = img; p.H = H; p.W = W; p.stride = stride; p.C = d.C; p.out_pitch = out_pitch;
+  p.img = img; p.img_u8 = img_u8; p.lut = lut; p.H = H; p.W = W; p.stride = stride; p.C = d.C; p.out_pitch = out_pitch;
   p.Ho = (H - 1) / stride + 1; p.Wo = (W - 1) / stride + 1;
   p.total = (long long)batch * p.Ho * p.Wo;
   p.w = d.w; p.M = d.M; p.B = d.B; p.lo = d.lo;
   p.out = pool ? tmp : out;
   CDN_CHECK(!pool || tmp, CDN_ERR_INVALID, "stem: pooling needs a scratch buffer");
   if (p.total == 0) return 0;
-  stem_kernel<<<(unsigned)((p.total + 127) / 128), 128, 0, st>>>(p);
+  CDN_CHECK(img_u8 == nullptr || lut != nullptr, CDN_ERR_INVALID, "stem: uint8 input needs the normalisation table");
+  if (img_u8) stem_kernel<true><<<(unsigned)((p.total + 127) / 128), 128, 0, st>>>(p);
+  else stem_kernel<false><<<(unsigned)((p.total + 127) / 128), 128, 0, st>>>(p);
   CDN_LAUNCH_CHECK("stem_kernel");
   if (pool) {
     int Hp = (p.Ho - 1) / 2 + 1, Wp = (p.Wo - 1) / 2 + 1;

@@ -95,16 +95,28 @@ class Engine:
         _lib.check(self.lib.cdn_engine_set_option(self._h, name.encode(), int(value)))
 
     # -- execution ----------------------------------------------------------------------------------------------------
+    def set_normalization(self, mean, std):
+        """mean / std as the reference holds them (float32 [3], lib/opts.py): enables uint8 input."""
+        m = np.ascontiguousarray(np.asarray(mean, np.float32).reshape(3))
+        s = np.ascontiguousarray(np.asarray(std, np.float32).reshape(3))
+        _lib.check(self.lib.cdn_engine_set_normalization(self._h, C.c_void_p(m.ctypes.data), C.c_void_p(s.ctypes.data)))
+        self._norm = True
+
     def run(self, images, maps: bool = True, dets: bool = True, out: Optional[dict] = None, raw_hm: bool = False):
-        """images: torch CUDA fp32 [B,3,H,W] (contiguous).  Returns dict of torch CUDA tensors:
+        """images: torch CUDA tensor (contiguous), either fp32 [B,3,H,W] (normalised, what the reference's model takes) or
+        uint8 [B,H,W,3] (what cv2 hands to pre_process; needs set_normalization).  Returns dict of torch CUDA tensors:
         hm (post-sigmoid, ctdet.py:32; logits when raw_hm), wh, reg [B,*,H/4,W/4]; dets [B,K,6]; inds [B,K]."""
         import torch
         if raw_hm != getattr(self, "_raw_hm", False):
             self.set_option("hm_logits", 1 if raw_hm else 0)
             self._raw_hm = raw_hm
-        assert images.is_cuda and images.dtype == torch.float32 and images.is_contiguous()
+        assert images.is_cuda and images.is_contiguous()
+        u8 = images.dtype == torch.uint8
         B = images.shape[0]
-        assert images.shape[1:] == (3, self.plan.in_H, self.plan.in_W), images.shape
+        if u8:
+            assert images.shape[1:] == (self.plan.in_H, self.plan.in_W, 3), images.shape
+        else:
+            assert images.dtype == torch.float32 and images.shape[1:] == (3, self.plan.in_H, self.plan.in_W), images.shape
         Ho, Wo, cat = self.plan.out_H, self.plan.out_W, self.plan.cat
         o = out if out is not None else {}
         dev = images.device
@@ -117,21 +129,23 @@ class Engine:
             o["inds"] = torch.empty((B, self.K), dtype=torch.int32, device=dev)
         p = lambda k: C.c_void_p(o[k].data_ptr()) if k in o else None
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        _lib.check(self.lib.cdn_engine_run(self._h, C.c_void_p(images.data_ptr()), B, p("hm") if maps else None,
-                                           p("wh") if maps else None, p("reg") if maps else None,
-                                           p("dets") if dets else None, p("inds") if dets else None, stream))
+        fn = self.lib.cdn_engine_run_u8 if u8 else self.lib.cdn_engine_run
+        _lib.check(fn(self._h, C.c_void_p(images.data_ptr()), B, p("hm") if maps else None,
+                      p("wh") if maps else None, p("reg") if maps else None,
+                      p("dets") if dets else None, p("inds") if dets else None, stream))
         return o
 
     def run_host(self, images: np.ndarray, dets: Optional[np.ndarray] = None, inds: Optional[np.ndarray] = None):
-        """images: host fp32 [B,3,H,W] (numpy, ideally backed by pinned memory).  H2D, forward, decode, D2H."""
+        """images: host array (ideally backed by pinned memory), fp32 [B,3,H,W] or uint8 [B,H,W,3].
+        H2D (chunked, overlapped with compute), forward, decode, D2H of the detections."""
         B = images.shape[0]
-        assert images.dtype == np.float32 and images.flags["C_CONTIGUOUS"]
+        assert images.dtype in (np.float32, np.uint8) and images.flags["C_CONTIGUOUS"]
         if dets is None:
             dets = np.empty((B, self.K, 6), np.float32)
         if inds is None:
             inds = np.empty((B, self.K), np.int32)
-        _lib.check(self.lib.cdn_engine_run_host(self._h, C.c_void_p(images.ctypes.data), B, C.c_void_p(dets.ctypes.data),
-                                                C.c_void_p(inds.ctypes.data)))
+        fn = self.lib.cdn_engine_run_host_u8 if images.dtype == np.uint8 else self.lib.cdn_engine_run_host
+        _lib.check(fn(self._h, C.c_void_p(images.ctypes.data), B, C.c_void_p(dets.ctypes.data), C.c_void_p(inds.ctypes.data)))
         return dets, inds
 
     def profile(self, images):

@@ -173,6 +173,14 @@ int cdn_engine_run(cdn_engine* e, const float* d_img, int batch, float* d_hm, fl
                    float* d_dets, int32_t* d_inds, cdn_stream_t stream);
 /* Same through HOST buffers: pinned staging, chunked H2D overlapped with compute, D2H of the detections. */
 int cdn_engine_run_host(cdn_engine* e, const float* h_img, int batch, float* h_dets, int32_t* h_inds);
+/* uint8 input: the image as cv2 hands it to the reference's pre_process (lib/detectors/base_detector.py:48-76),
+ * [batch][H][W][3], already at the network's input size.  The normalisation ((u/255. - mean)/std).astype(float32)
+ * (:66) is applied inside the stem kernel through a 3x256 table built by cdn_engine_set_normalization with numpy's
+ * evaluation order, so results are bit-identical to feeding the normalised fp32 image, at a quarter of the H2D bytes. */
+int cdn_engine_set_normalization(cdn_engine* e, const float* mean3, const float* std3);
+int cdn_engine_run_u8(cdn_engine* e, const uint8_t* d_img, int batch, float* d_hm, float* d_wh, float* d_reg,
+                      float* d_dets, int32_t* d_inds, cdn_stream_t stream);
+int cdn_engine_run_host_u8(cdn_engine* e, const uint8_t* h_img, int batch, float* h_dets, int32_t* h_inds);
 /* Options: "host_chunk" (images per H2D/compute pipeline step of run_host, default 32), "use_graph" (replay the
  * launch sequence as a CUDA graph, default 1), "micro_batch" (run the layers over sub-batches of this many images
  * so consecutive layers hit L2, 0 = whole batch), "hm_logits" (cdn_engine_run writes the heat map as logits, what

@@ -132,3 +132,22 @@ def test_shard_bounds():
     assert my_slice(2048, 7, 8) == (1792, 2048)
     with pytest.raises(ValueError):
         my_slice(8, 8, 8)
+
+
+def test_pre_process_is_normalisation_only_at_input_size():
+    """For an image already at the input size the reference's resize + warpAffine (base_detector.py:61-65) are the
+    identity, so the uint8 fast path (normalisation table inside the stem kernel) sees exactly pre_process's tensor."""
+    pytest.importorskip("cv2")
+    from codenet_b200.compat.detector import default_opt
+    det = compat.CtdetDetector.__new__(compat.CtdetDetector)
+    det.opt = default_opt(input_h=96, input_w=96)
+    det.mean = np.array(det.opt.mean, np.float32).reshape(1, 1, 3)
+    det.std = np.array(det.opt.std, np.float32).reshape(1, 1, 3)
+    img = np.random.default_rng(1).integers(0, 256, (96, 96, 3), dtype=np.uint8)
+    images, meta = compat.CtdetDetector.pre_process(det, img, 1.0)
+    # the table cdn_engine_set_normalization builds: fl32((u/255. - mean)/std) evaluated in double
+    lut = ((np.arange(256, dtype=np.float64)[None, :] / 255.0 - det.mean.reshape(3, 1).astype(np.float64))
+           / det.std.reshape(3, 1).astype(np.float64)).astype(np.float32)
+    want = np.stack([lut[c][img[:, :, c]] for c in range(3)])[None]
+    np.testing.assert_array_equal(images.numpy(), want)
+    assert meta["out_height"] == 24 and float(meta["s"]) == 96.0

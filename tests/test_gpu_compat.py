@@ -118,3 +118,35 @@ def test_detector_run_and_flip_test(calib):
     want = compat.ctdet_decode(hm, wh, reg=o2["reg"][0:1], K=100)
     assert dets.shape == (1, 100, 6)
     np.testing.assert_array_equal(dets.cpu().numpy(), want.cpu().numpy())
+
+
+def test_uint8_input_is_bit_identical_to_normalised_fp32(calib):
+    """cdn_engine_run_u8 / run_host_u8 (normalisation table in the stem kernel) against the fp32 path on the tensor the
+    reference's pre_process would build; and CtdetDetector.run() taking the fast path on an image at the input size."""
+    import torch
+    from codenet_b200.engine import Engine
+    st = make_quant_state(CFG, calib, "round", 256)
+    eng = Engine.from_state_dict(CFG, st, 256, 256, 3, offset_mode="round")
+    mean, std = np.array([0.485, 0.456, 0.406], np.float32), np.array([0.229, 0.224, 0.225], np.float32)
+    eng.set_normalization(mean, std)
+    u8 = np.random.default_rng(7).integers(0, 256, (3, 256, 256, 3), dtype=np.uint8)
+    f32 = ((u8 / 255. - mean.reshape(1, 1, 1, 3)) / std.reshape(1, 1, 1, 3)).astype(np.float32).transpose(0, 3, 1, 2).copy()
+    a = eng.run(torch.from_numpy(f32).cuda()); a = {k: v.clone() for k, v in a.items()}
+    ga = eng.read_logical("stem", 3)
+    b = eng.run(torch.from_numpy(u8).cuda())
+    np.testing.assert_array_equal(eng.read_logical("stem", 3), ga)
+    for k in ("hm", "wh", "reg", "dets", "inds"):
+        np.testing.assert_array_equal(a[k].cpu().numpy(), b[k].cpu().numpy(), err_msg=k)
+    d_host, i_host = eng.run_host(u8)
+    np.testing.assert_array_equal(d_host, a["dets"].cpu().numpy())
+    np.testing.assert_array_equal(i_host, a["inds"].cpu().numpy())
+    eng.close()
+    pytest.importorskip("cv2")
+    det = _detector(calib, "round", 256, max_batch=1)
+    img = u8[0]
+    fast = det.run(img)
+    images, meta = det.pre_process(img, 1.0)
+    _, dets = det.process(images.cuda())
+    slow = det.merge_outputs([det.post_process(dets, meta, 1.0)])
+    for j in range(1, 21):
+        np.testing.assert_array_equal(fast["results"][j], slow[j])
