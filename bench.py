@@ -310,7 +310,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--offset-mode", default="round", choices=["round", "bilinear"])
     ap.add_argument("--micro-batch", type=int, default=0)
-    ap.add_argument("--host-chunk", type=int, default=32)
+    ap.add_argument("--host-chunk", type=int, default=64)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs only)")
     ap.add_argument("--dump-ops", default="", help="write the per-op device times (JSON) to this file")
     args = ap.parse_args()

@@ -73,6 +73,71 @@ __global__ void __launch_bounds__(256) ctdet_peaks_kernel(DecParams p, int batch
       ((unsigned long long)f2key(v) << 32) | (unsigned long long)(0xffffffffu - e);
 }
 
+// Row-strip variant of the peak kernel (W % 4 == 0): a thread owns 4 horizontally adjacent elements and walks down a
+// strip of DEC_STRIP rows, keeping the horizontal 3-max of the previous two rows in registers, so every heat-map value
+// is loaded ~1.4 times (one float4 + two halo scalars per row) instead of 9.
+#define DEC_STRIP 16
+__global__ void __launch_bounds__(256) ctdet_peaks_rows_kernel(DecParams p, int strips_per_plane) {
+  const int HW = p.H * p.W, W4 = p.W >> 2;
+  const unsigned n = (unsigned)p.cat * HW;
+  const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned tid = blockIdx.x * 256u + threadIdx.x;
+  const unsigned per_plane = (unsigned)strips_per_plane * W4;
+  const unsigned plane_i = tid / per_plane, rem = tid - plane_i * per_plane;
+  const bool live = plane_i < (unsigned)p.cat;
+  const int strip = (int)(rem / W4), x0 = (int)(rem % W4) * 4;
+  const float* plane = p.hm + (size_t)b * p.hm_is + (size_t)(live ? plane_i : 0) * HW;
+  const int y0 = strip * DEC_STRIP, y1 = min(y0 + DEC_STRIP, p.H);
+  const float NEG = -3.402823466e38f;
+  // row record: the 4 values and the horizontal 3-max at each of the 4 positions
+  auto load_row = [&](int y, float (&v)[4], float (&hm3)[4]) {
+    if ((unsigned)y >= (unsigned)p.H || !live) { v[0] = v[1] = v[2] = v[3] = NEG; hm3[0] = hm3[1] = hm3[2] = hm3[3] = NEG; return; }
+    const float* r = plane + (size_t)y * p.W + x0;
+    const float4 q = __ldg((const float4*)r);
+    const float l = x0 > 0 ? __ldg(r - 1) : NEG, rr = x0 + 4 < p.W ? __ldg(r + 4) : NEG;
+    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    hm3[0] = fmaxf(fmaxf(l, q.x), q.y); hm3[1] = fmaxf(fmaxf(q.x, q.y), q.z);
+    hm3[2] = fmaxf(fmaxf(q.y, q.z), q.w); hm3[3] = fmaxf(fmaxf(q.z, q.w), rr);
+  };
+  float vm[4], hmm[4], vc[4], hmc[4], vp[4], hmp[4];
+  load_row(y0 - 1, vm, hmm); load_row(y0, vc, hmc);
+  __shared__ unsigned s_wcnt[8], s_base;
+  unsigned long long mask = 0ull;                // bit (y - y0) * 4 + i: element is a peak (4 x DEC_STRIP = 64 elements)
+  for (int y = y0; y < y1; ++y) {
+    load_row(y + 1, vp, hmp);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float m = fmaxf(fmaxf(hmm[i], hmc[i]), hmp[i]);
+      if (live && vc[i] == m) mask |= 1ull << ((y - y0) * 4 + i);     // equal to the 3x3 maximum (NaN compares false)
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { vm[i] = vc[i]; hmm[i] = hmc[i]; vc[i] = vp[i]; hmc[i] = hmp[i]; }
+  }
+  const unsigned cnt = (unsigned)__popcll(mask);
+  // block-aggregated append
+  unsigned incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+  if (lane == 31) s_wcnt[warp] = incl;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned tot = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { const unsigned c = s_wcnt[w]; s_wcnt[w] = tot; tot += c; }
+    s_base = tot ? atomicAdd(p.counts + b, tot) : 0u;
+  }
+  __syncthreads();
+  unsigned long long* dst = p.list + (size_t)b * n + s_base + s_wcnt[warp] + (incl - cnt);
+  while (mask) {
+    const int bit = __ffsll((long long)mask) - 1;
+    mask &= mask - 1;
+    const int y = y0 + (bit >> 2), x = x0 + (bit & 3);
+    const float v = __ldg(plane + (size_t)y * p.W + x);            // L1 / L2 hit: the strip was just read
+    const unsigned e = plane_i * HW + (unsigned)y * p.W + x;
+    *dst++ = ((unsigned long long)f2key(v) << 32) | (unsigned long long)(0xffffffffu - e);
+  }
+}
+
 __global__ void __launch_bounds__(DEC_THREADS) ctdet_decode_kernel(DecParams p) {
   __shared__ unsigned int hist[DEC_BINS];
   __shared__ unsigned long long sel[DEC_MAXK];
@@ -192,8 +257,15 @@ int decode_launch(const float* hm, long long hm_img_stride, const float* wh, lon
   DecParams p{hm, wh, reg, hm_img_stride, wh_img_stride, reg_img_stride, cat, H, W, K, is_prob, scratch, counts, dets, inds};
   CDN_CUDA(cudaMemsetAsync(counts, 0, (size_t)batch * sizeof(unsigned int), st));
   const unsigned n = (unsigned)cat * H * W;
-  ctdet_peaks_kernel<<<dim3((n + 255) / 256, batch), 256, 0, st>>>(p, batch);
-  CDN_LAUNCH_CHECK("ctdet_peaks_kernel");
+  if (W % 4 == 0 && (((uintptr_t)hm | (uintptr_t)(hm_img_stride * 4)) & 15) == 0) {
+    const int strips = (H + DEC_STRIP - 1) / DEC_STRIP;
+    const unsigned threads = (unsigned)cat * strips * (W / 4);
+    ctdet_peaks_rows_kernel<<<dim3((threads + 255) / 256, batch), 256, 0, st>>>(p, strips);
+    CDN_LAUNCH_CHECK("ctdet_peaks_rows_kernel");
+  } else {
+    ctdet_peaks_kernel<<<dim3((n + 255) / 256, batch), 256, 0, st>>>(p, batch);
+    CDN_LAUNCH_CHECK("ctdet_peaks_kernel");
+  }
   ctdet_decode_kernel<<<batch, DEC_THREADS, 0, st>>>(p);
   CDN_LAUNCH_CHECK("ctdet_decode_kernel");
   return 0;

@@ -159,7 +159,7 @@ struct cdn_engine {
   float* lut = nullptr;                      // 3 x 256 normalisation table for uint8 input
   cudaStream_t s_compute = nullptr, s_copy = nullptr;
   std::vector<cudaEvent_t> ev;
-  int host_chunk = 32, use_graph = 1, micro_batch = 0, hm_logits = 0;
+  int host_chunk = 64, use_graph = 1, micro_batch = 0, hm_logits = 0;
   // graph cache
   struct GraphKey { const void* a[6]; int batch; bool operator==(const GraphKey& o) const { return memcmp(this, &o, sizeof(*this)) == 0; } };
   std::vector<std::pair<GraphKey, cudaGraphExec_t>> graphs;

@@ -181,7 +181,7 @@ int cdn_engine_set_normalization(cdn_engine* e, const float* mean3, const float*
 int cdn_engine_run_u8(cdn_engine* e, const uint8_t* d_img, int batch, float* d_hm, float* d_wh, float* d_reg,
                       float* d_dets, int32_t* d_inds, cdn_stream_t stream);
 int cdn_engine_run_host_u8(cdn_engine* e, const uint8_t* h_img, int batch, float* h_dets, int32_t* h_inds);
-/* Options: "host_chunk" (images per H2D/compute pipeline step of run_host, default 32), "use_graph" (replay the
+/* Options: "host_chunk" (images per H2D/compute pipeline step of run_host, default 64), "use_graph" (replay the
  * launch sequence as a CUDA graph, default 1), "micro_batch" (run the layers over sub-batches of this many images
  * so consecutive layers hit L2, 0 = whole batch), "hm_logits" (cdn_engine_run writes the heat map as logits, what
  * PoseShuffleNetV2.forward returns, instead of post-sigmoid; default 0). */
