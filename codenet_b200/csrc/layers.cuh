@@ -17,7 +17,10 @@ int dw_launch(const DwDevice& d, const int8_t* in, int in_pitch, int8_t* out, in
 int deform_launch(const DwDevice& d, const cdn_deform_scale* sc, const int8_t* in, int in_pitch, int8_t* out,
                   int out_pitch, int batch, int H, int W, int in_shift, int zx, float* sval, cudaStream_t st);
 
-struct StemDevice { double* w = nullptr; double* M = nullptr; double* B = nullptr; int C = 0; double lo = -128; };
+struct StemDevice {
+  double* w = nullptr; double* M = nullptr; double* B = nullptr; int C = 0; double lo = -128;
+  std::vector<double> hw, hM, hB;            // host copies: passed to the kernel by value (constant bank)
+};
 int stem_device_build(StemDevice& d, const int8_t* wq, int C, const cdn_requant* rq);
 void stem_device_free(StemDevice& d);
 int stem_launch(const StemDevice& d, const float* img, int batch, int H, int W, int stride, int pool,
