@@ -94,7 +94,18 @@ def op_bytes(plan, op, batch):
 
 
 def family(op):
-    return {"pw": "pw_gemm_tc_kernel", "dw": "dw3x3_kernel", "deform": "deform_dw_kernel", "stem": "stem_kernel"}[op.kind]
+    return {"pw": "pw_gemm_tc_kernel", "dw": "dw3x3_v2_kernel", "deform": "deform_dw_v2_kernel", "stem": "stem_kernel"}[op.kind]
+
+
+def ncu_traffic():
+    """DRAM bytes per step and kernel family from the latest committed ncu launch list (profiles/*_families.json)."""
+    d = os.path.join(ROOT, "profiles")
+    try:
+        f = sorted(x for x in os.listdir(d) if x.endswith("_families.json"))[-1]
+        j = json.load(open(os.path.join(d, f)))
+        return {k: (v["dram_bytes"], v["launches"]) for k, v in j["families"].items()}, f
+    except Exception:
+        return {}, None
 
 
 def run_ours(args):
@@ -213,19 +224,28 @@ def run_ours(args):
         if op.kind == "deform":
             deform_layers.append({"layer": op.name, "C": int(op.a["C"]), "H": int(eng.plan.tensors[op.a["out_t"]].H),
                                   "ms": round(msop, 4), "GBps": round(by / msop / 1e6, 1)})
-    fam_ms["ctdet_decode_kernel"] = per_op[-1]
-    fam_bytes["ctdet_decode_kernel"] = B * (eng.plan.cat + 4) * eng.plan.out_H * eng.plan.out_W * 4
+    fam_ms["ctdet_decode"] = per_op[-1]
+    fam_bytes["ctdet_decode"] = B * (eng.plan.cat + 4) * eng.plan.out_H * eng.plan.out_W * 4
+    fam_launches = {"ctdet_decode": 2}
+    for op in eng.plan.ops:
+        fam_launches[family(op)] = fam_launches.get(family(op), 0) + 1
     total_ms = sum(fam_ms.values())
     dom = max(fam_ms, key=fam_ms.get)
     peak, peak_src = peaks()
     ach = fam_bytes[dom] / fam_ms[dom] / 1e6
+    traffic, traffic_src = ncu_traffic()
+    tr = traffic.get(dom)
     roofline = {"kernel": dom, "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
+                "frac": round(ach / peak, 4),
+                "traffic": (round(tr[0] / tr[1]) if tr and B == 256 else None),
+                "traffic_note": "mean DRAM bytes per launch of this family (ncu dram__bytes_read+write, %s); algorithmic bytes "
+                                "per launch: %d" % (traffic_src, fam_bytes[dom] // max(fam_launches.get(dom, 1), 1)),
+                "launches_per_step": fam_launches.get(dom), "peak_source": peak_src,
                 "share_of_step": round(fam_ms[dom] / total_ms, 3),
                 "families": {k: {"ms": round(v, 4), "GBps": round(fam_bytes[k] / v / 1e6, 1), "share": round(v / total_ms, 3)}
                              for k, v in sorted(fam_ms.items(), key=lambda kv: -kv[1])}}
     dby = sum(op_bytes(eng.plan, op, B) for op in eng.plan.ops if op.kind == "deform")
-    deform = {"GBps": round(dby / fam_ms["deform_dw_kernel"] / 1e6, 1), "frac_of_hbm_peak": round(dby / fam_ms["deform_dw_kernel"] / 1e6 / peak, 4),
+    deform = {"GBps": round(dby / fam_ms["deform_dw_v2_kernel"] / 1e6, 1), "frac_of_hbm_peak": round(dby / fam_ms["deform_dw_v2_kernel"] / 1e6 / peak, 4),
               "layers": deform_layers}
     cpu = None if args.no_cpu else cpu_baseline(args, sample_images=1)
     line = {

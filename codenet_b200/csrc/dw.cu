@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(128) dw3x3_v2_kernel(const DwV2Params p) {
 #define DEF_NP 64
 
 template <int MODE>
-__global__ void __launch_bounds__(256) deform_dw_v2_kernel(const DwParams p) {
+__global__ void __launch_bounds__(256, MODE == 0 ? 4 : 1) deform_dw_v2_kernel(const DwParams p) {
   __shared__ double s_s[DEF_NP];
   __shared__ uint32_t s_hw[DEF_NP];
   __shared__ int s_b[DEF_NP];                  // word offset of the pixel's image
@@ -312,42 +312,35 @@ __global__ void __launch_bounds__(256) deform_dw_v2_kernel(const DwParams p) {
         Mh[c] = mb.x; Bh[c] = mb.y; abm[c] = active ? __ldg(p.abm + cw * 4 + c) : CDN_MAGIC_I;
       }
       if (MODE == 0) {
-        // software pipeline: the 9 taps of the NEXT pixel are in flight while this pixel is transposed, MAC-ed and
-        // requantised (the gather is latency-bound otherwise)
+        // Software pipeline, unrolled by two with ping-pong tap registers: the 9 taps of the NEXT pixel are in flight
+        // while this pixel is transposed, MAC-ed and requantised.  All addressing is unsigned 32-bit off one base
+        // pointer (one IMAD.WIDE per load; the 64-bit version spent half of its issue slots on address arithmetic).
+        const uint32_t* const base_in = p.in + cw;
+        uint32_t* const base_out = p.out + (size_t)base * p.out_pitch_w + cw;
+        const int nvalid = active ? (int)min((long long)DEF_NP, p.total - base) : 0;
         auto fetch = [&](int j, uint32_t (&x)[9]) {
           const uint32_t hw = s_hw[j];
           const int w = (int)(hw & 0xffffu), h = (int)(hw >> 16), si = s_si[j];
-          const uint32_t* img = p.in + s_b[j] + cw;
-          int ro[3], co[3]; bool yok[3], xok[3];
+          const unsigned ob = (unsigned)s_b[j];
+          unsigned ro[3], co[3]; bool yok[3], xok[3];
 #pragma unroll
           for (int i = 0; i < 3; i += 2) {
             const int y = h + (i - 1) * si, xx = w + (i - 1) * si;
             yok[i] = (unsigned)y < (unsigned)p.Hin; xok[i] = (unsigned)xx < (unsigned)p.Win;
-            ro[i] = (min(max(y, 0), p.Hin - 1) >> p.shift) * rs_in; co[i] = (min(max(xx, 0), p.Win - 1) >> p.shift) * p.in_pitch_w;
+            ro[i] = ob + (unsigned)((min(max(y, 0), p.Hin - 1) >> p.shift) * rs_in);
+            co[i] = (unsigned)((min(max(xx, 0), p.Win - 1) >> p.shift) * p.in_pitch_w);
           }
-          yok[1] = xok[1] = true; ro[1] = (h >> p.shift) * rs_in; co[1] = (w >> p.shift) * p.in_pitch_w;
+          yok[1] = xok[1] = true; ro[1] = ob + (unsigned)((h >> p.shift) * rs_in); co[1] = (unsigned)((w >> p.shift) * p.in_pitch_w);
 #pragma unroll
           for (int i = 0; i < 3; ++i)
 #pragma unroll
-            for (int jj = 0; jj < 3; ++jj) x[i * 3 + jj] = __ldg(img + (ro[i] + co[jj]));
+            for (int jj = 0; jj < 3; ++jj) x[i * 3 + jj] = __ldg(base_in + (ro[i] + co[jj]));
 #pragma unroll
           for (int i = 0; i < 3; ++i)
 #pragma unroll
             for (int jj = 0; jj < 3; ++jj) if (!(yok[i] && xok[jj])) x[i * 3 + jj] = p.pad_word;
         };
-        uint32_t xn[9];
-        bool vn = active && base + wslot < p.total;
-        if (vn) fetch(wslot, xn);
-#pragma unroll 1
-        for (int j = wslot; j < DEF_NP; j += nslot) {
-          uint32_t x[9];
-#pragma unroll
-          for (int i = 0; i < 9; ++i) x[i] = xn[i];
-          const bool v = vn;
-          const int jn = j + nslot;
-          vn = active && jn < DEF_NP && base + jn < p.total;
-          if (vn) fetch(jn, xn);
-          if (!v) continue;
+        auto compute = [&](int j, const uint32_t (&x)[9]) {
           uint32_t a0, a1, a2, a3, b0, b1, b2, b3;
           transpose4x4(x[0], x[1], x[2], x[3], a0, a1, a2, a3);
           transpose4x4(x[4], x[5], x[6], x[7], b0, b1, b2, b3);
@@ -361,7 +354,18 @@ __global__ void __launch_bounds__(256) deform_dw_v2_kernel(const DwParams p) {
           const uint32_t r2 = rq_fast<0>(acc[2], Mh[2], Bh[2], p.lo_f, gd), r3 = rq_fast<1>(acc[3], Mh[3], Bh[3], p.lo_f, gd);
           uint32_t o = pack4_lowbytes(r0, r1, r2, r3);
           if (rq_group_bad(gd, p.thr_layer)) o = dw_rq_word_exact(acc[0], acc[1], acc[2], acc[3], p.M, p.B, cw * 4, p.lo_f);
-          p.out[(size_t)(base + j) * p.out_pitch_w + cw] = o;
+          base_out[(unsigned)(j * p.out_pitch_w)] = o;
+        };
+        uint32_t xa[9], xb[9];
+        int j = wslot;
+        if (j < nvalid) fetch(j, xa);
+#pragma unroll 1
+        for (; j < nvalid; j += 2 * nslot) {
+          const int j1 = j + nslot, j2 = j + 2 * nslot;
+          if (j1 < nvalid) fetch(j1, xb);
+          compute(j, xa);
+          if (j2 < nvalid) fetch(j2, xa);
+          if (j1 < nvalid) compute(j1, xb);
         }
       } else {
 #pragma unroll 1
