@@ -29,7 +29,7 @@ int stem_launch(const StemDevice& d, const float* img, int batch, int H, int W, 
 
 struct PwDevice {
   int K = 0, k_off = 0, N = 0, Kp = 0, BN = 0, n_tiles = 0, num_k_blocks = 0, stages = 0;
-  int has_pass = 0, pass_segs = 0, pass_bufs = 1, nbuf = 0, resident = 0, n_chunks = 0, n_segs = 0, n_f32 = 0;
+  int has_pass = 0, pass_segs = 0, pass_bufs = 1, groups = 2, nbuf = 0, resident = 0, n_chunks = 0, n_segs = 0, n_f32 = 0;
   float thr = 0.5f;                          // layer-wide rounding-boundary guard (min over columns)
   size_t smem_bytes = 0;
   int8_t* w = nullptr;                       // [BN*n_tiles][Kp]

@@ -39,6 +39,7 @@ struct PwSeg { int seg, cb, ce, pad; };       // output segment (128-byte column
 
 struct PwParams {
   int num_k_blocks, k_off, BN, n_tiles, stages, has_pass, pass_segs, pass_bufs, nbuf, resident, n_chunks, n_segs;
+  int groups;                                // epilogue groups in use: 2, or 1 when shared memory is too tight for two
   long long m_tiles, pixels;
   const cdn_pw_chunk* chunks;                // sorted by (N tile, output segment)
   const PwSeg* segs; const int* tile_seg;    // tile_seg[n_tiles + 1]: first PwSeg of every N tile
@@ -215,7 +216,7 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint8_t* s_ring = s_B + (p.resident ? (size_t)p.num_k_blocks * Ntot * PW_BK : 0);
   uint8_t* s_pass = s_ring + (size_t)p.stages * stage_bytes;
   uint8_t* s_out = s_pass + (size_t)p.pass_bufs * p.pass_segs * 16384;
-  float4* s_kc = (float4*)(s_out + (size_t)PW_EPI_GROUPS * p.nbuf * 16384);
+  float4* s_kc = (float4*)(s_out + (size_t)p.groups * p.nbuf * 16384);
   cdn_pw_chunk* s_chunks = (cdn_pw_chunk*)(s_kc + Ntot);
   PwSeg* s_segs = (PwSeg*)(s_chunks + ((p.n_chunks + 1) & ~1));
   int* s_tile_seg = (int*)(s_segs + p.n_segs);
@@ -326,9 +327,8 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int stage = 0; uint32_t phase = 0; uint32_t it = 0;
       for (unsigned tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int nt = (int)(tile % (unsigned)p.n_tiles);
-        const uint32_t kq = it >> 1;                               // this tile is the kq-th of epilogue group (it & 1)
-        const int as = (int)(it & 1) + (nacc == 4 ? 2 * (int)(kq & 1) : 0);
-        const uint32_t aphase = (nacc == 4 ? (kq >> 1) : kq) & 1;
+        const int as = (int)(it % (uint32_t)nacc);                 // accumulator stages rotate over the CTA's tiles
+        const uint32_t aphase = (it / (uint32_t)nacc) & 1;
         { DBG_T0(); mbar_wait(TEMPTY(as), aphase ^ 1); DBG_ACC(2); }
         tc_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)as * acc_stride;
@@ -353,9 +353,9 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // 128-byte output segment is complete, this warp issues the store, waits until the TMA engine has read the
     // buffer and hands it back through SEMPTY.
     const int grp = warp - PW_STORE_WARP0;
-    if (lane == 0 && p.n_f32 == 0) {
+    if (lane == 0 && p.n_f32 == 0 && grp < p.groups) {
       uint32_t g = 0;
-      for (unsigned tile = blockIdx.x + grp * gridDim.x; tile < total_tiles; tile += PW_EPI_GROUPS * gridDim.x) {
+      for (unsigned tile = blockIdx.x + grp * gridDim.x; tile < total_tiles; tile += p.groups * gridDim.x) {
         const unsigned mt = tile / (unsigned)p.n_tiles; const int nt = (int)(tile % (unsigned)p.n_tiles);
         const int sg0 = s_tile_seg[nt], sg1 = s_tile_seg[nt + 1];
         for (int sg = sg0; sg < sg1; ++sg, ++g) {
@@ -384,15 +384,15 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int gt = (threadIdx.x - 64) % PW_GROUP_THREADS;
     uint8_t* const s_out_g = s_out + (size_t)grp * p.nbuf * 16384;
     uint32_t it2 = 0, g = 0;                   // tiles / output segments done by this group
-    for (unsigned tile = blockIdx.x + grp * gridDim.x; tile < total_tiles; tile += PW_EPI_GROUPS * gridDim.x, ++it2) {
+    for (unsigned tile = blockIdx.x + grp * gridDim.x; tile < total_tiles && grp < p.groups; tile += p.groups * gridDim.x, ++it2) {
       const unsigned mt = tile / (unsigned)p.n_tiles; const int nt = (int)(tile % (unsigned)p.n_tiles);
-      const int as = grp + (nacc == 4 ? 2 * (int)(it2 & 1) : 0);
-      const uint32_t aphase = (nacc == 4 ? (it2 >> 1) : it2) & 1;
+      const uint32_t itg = it2 * (uint32_t)p.groups + grp;                   // CTA-wide tile counter (as producer / MMA count)
+      const int as = (int)(itg % (uint32_t)nacc);
+      const uint32_t aphase = (itg / (uint32_t)nacc) & 1;
       DBG_T0();
       mbar_wait(TFULL(as), aphase);
       if (warp == 2) DBG_ACC(4);
       tc_fence_after();
-      const uint32_t itg = it2 * PW_EPI_GROUPS + grp;                     // CTA-wide tile counter (as the producer counts)
       const int pb = (int)(itg % (uint32_t)p.pass_bufs);
       if (p.has_pass) mbar_wait(PFULL(pb), (itg / (uint32_t)p.pass_bufs) & 1);
       if (warp == 2) DBG_ACC(5);
@@ -668,8 +668,8 @@ int pw_device_build(PwDevice& d, const cdn_pw_desc* desc, int pass_pitch) {
   const size_t b_blk = ((size_t)d.BN * PW_BK + 1023) & ~(size_t)1023;
   const size_t b_all = (size_t)d.num_k_blocks * Np * PW_BK;
   const size_t tables = (size_t)Np * 16 + (size_t)((d.n_chunks + 1) & ~1) * 8 + (size_t)d.n_segs * 16 + (size_t)((d.n_tiles + 1 + 3) & ~3) * 4 + 56 * 8;
-  auto plan = [&](bool resident, int pass_bufs, int nbuf, int& stages) {
-    const size_t fixed = 1024 + (resident ? b_all : 0) + (size_t)pass_bufs * d.pass_segs * 16384 + (size_t)PW_EPI_GROUPS * nbuf * 16384 + tables;
+  auto plan = [&](bool resident, int groups, int pass_bufs, int nbuf, int& stages) {
+    const size_t fixed = 1024 + (resident ? b_all : 0) + (size_t)pass_bufs * d.pass_segs * 16384 + (size_t)groups * nbuf * 16384 + tables;
     const size_t stage_bytes = 16384 + (resident ? 0 : b_blk);
     if (fixed + 2 * stage_bytes > PW_SMEM_LIMIT) { stages = 0; return (size_t)0; }
     stages = (int)std::min<size_t>(PW_MAX_STAGES, (PW_SMEM_LIMIT - fixed) / stage_bytes);
@@ -679,15 +679,16 @@ int pw_device_build(PwDevice& d, const cdn_pw_desc* desc, int pass_pitch) {
   // relax one requirement at a time until the layer fits
   int stages = 0; size_t bytes = 0; bool found = false;
   const int nbuf_hi = d.n_f32 > 0 ? 0 : ((g_cdn_debug_flags & 32u) ? 2 : 3), nbuf_lo = d.n_f32 > 0 ? 0 : 2;
-  for (int want = 2; want >= 0 && !found; --want)            // tiles in flight we insist on (0: anything that runs)
-    for (int resident = 1; resident >= 0 && !found; --resident)
-      // every epilogue group needs its own pass buffer(s): with a shared one a group could be two mbarrier phases behind
-      for (int pass_bufs = d.has_pass ? 4 : 2; pass_bufs >= 2 && !found; pass_bufs -= 2)
-        for (int nbuf = nbuf_hi; nbuf >= nbuf_lo && !found; --nbuf) {
-          int st = 0; const size_t by = plan(resident != 0, pass_bufs, nbuf, st);
-          const int need = std::max(2, std::min(want * d.num_k_blocks, want == 2 ? 8 : 3));
-          if (st >= need) { found = true; stages = st; bytes = by; d.resident = resident; d.pass_bufs = pass_bufs; d.nbuf = nbuf; }
-        }
+  for (int groups = PW_EPI_GROUPS; groups >= 1 && !found; --groups)   // one epilogue group only when nothing else fits
+    for (int want = 2; want >= 0 && !found; --want)          // tiles in flight we insist on (0: anything that runs)
+      for (int resident = 1; resident >= 0 && !found; --resident)
+        // every epilogue group needs its own pass buffer(s): with a shared one a group could be two mbarrier phases behind
+        for (int pass_bufs = d.has_pass ? 2 * groups : groups; pass_bufs >= groups && !found; pass_bufs -= groups)
+          for (int nbuf = nbuf_hi; nbuf >= nbuf_lo && !found; --nbuf) {
+            int st = 0; const size_t by = plan(resident != 0, groups, pass_bufs, nbuf, st);
+            const int need = std::max(2, std::min(want * d.num_k_blocks, want == 2 ? 8 : 3));
+            if (st >= need) { found = true; stages = st; bytes = by; d.resident = resident; d.pass_bufs = pass_bufs; d.nbuf = nbuf; d.groups = groups; }
+          }
   CDN_CHECK(stages >= 2, CDN_ERR_INVALID, "pw: layer does not fit in shared memory (K=%d N=%d BN=%d pass segs=%d)", d.K, d.N, d.BN, d.pass_segs);
   d.stages = stages;
   d.smem_bytes = bytes;
@@ -723,7 +724,7 @@ int pw_launch(const PwDevice& d, const int8_t* in, int in_pitch, long long pixel
   CDN_CHECK(d.n_f32 > 0 ? (out_f32 != nullptr && ppi > 0) : (out != nullptr), CDN_ERR_INVALID, "pw: missing output pointer");
   PwParams p; memset(&p, 0, sizeof(p));
   p.num_k_blocks = d.num_k_blocks; p.k_off = d.k_off; p.BN = d.BN; p.n_tiles = d.n_tiles; p.stages = d.stages;
-  p.has_pass = d.has_pass; p.pass_segs = d.pass_segs; p.pass_bufs = d.pass_bufs; p.nbuf = d.nbuf; p.resident = d.resident;
+  p.groups = d.groups; p.has_pass = d.has_pass; p.pass_segs = d.pass_segs; p.pass_bufs = d.pass_bufs; p.nbuf = d.nbuf; p.resident = d.resident;
   p.n_chunks = d.n_chunks; p.n_segs = d.n_segs;
   p.m_tiles = (pixels + PW_BM - 1) / PW_BM; p.pixels = pixels;
   p.chunks = d.chunks; p.segs = (const PwSeg*)d.segs; p.tile_seg = d.tile_seg; p.kc = (const float4*)d.kc;

@@ -14,6 +14,7 @@ Vectors produced (all from the reference's own code through oracle/ref_harness.p
   codenet1x_256_{round,bilinear}.npz   fp64 reference forward + decode on config a (256^2), with int8-grid
                     intermediates
   codenet1x_512_round.npz   one 512^2 image (config c geometry): detections + strided output samples
+  codenet_w2mp_{calib,256_round}.npz   the same for the w2 + S2/MaxPool configuration (config e geometry), one 256^2 image
   ref_state_keys.json   state-dict key spaces of the reference network before / after quantisation (1x, w2, maxpool)
 """
 import os
@@ -326,6 +327,36 @@ def codenet1x():
     print("codenet1x ok")
 
 
+def codenet_w2mp():
+    """Config e geometry (w2 width, stride-2 stem + MaxPool) at 256^2, integer offsets:
+    calibration archive + one image of int8 grids / heads / detections from the fp64 reference."""
+    cfg = NetConfig(num_classes=20, w2=True, maxpool=True)
+    g = build_graph(cfg)
+    raw = make_raw_state(cfg, 0)
+    digest = state_digest(raw)
+    raw.update(_calibrate_bn(cfg, raw))
+    calib = {"digest": np.array(digest), "seed": np.array(0)}
+    for k, v in raw.items():
+        if k.endswith("running_mean") or k.endswith("running_var"):
+            calib["bn/" + k] = v
+    xs = np.concatenate([make_images(2, 256, seed=2), make_images(2, 256, seed=1)[:2]])
+    m = _quant_model(cfg, raw, True)
+    _init_ranges(m, T(xs).double())
+    for lbl, r in _ranges_of(m, g).items():
+        calib["ranges_round_256/%s" % lbl] = r
+    cap = _run_and_capture(m, g, T(xs[:1]).double())
+    out = {"seed_images": np.array(2), "nimg": np.array(1)}
+    for k, v in cap.items():
+        if v.dtype == np.int16:
+            assert v.min() >= -128 and v.max() <= 127, (k, v.min(), v.max())
+            out[k] = v.astype(np.int8)
+        elif k in ("hm_logit", "wh", "reg", "dets") or k.endswith("sval"):
+            out[k] = v
+    np.savez_compressed(os.path.join(OUT, "codenet_w2mp_256_round.npz"), **out)
+    np.savez_compressed(os.path.join(OUT, "codenet_w2mp_calib.npz"), **calib)
+    print("codenet_w2mp ok; unique scores:", len(np.unique(cap["dets"][0, :, 4])))
+
+
 def ref_keys():
     """State-dict key spaces (name -> shape) of the UNMODIFIED reference network before and after
     quantize_shufflenetv2_dcn, for 1x / w2 / maxpool: what codenet_b200.compat must reproduce so checkpoints load."""
@@ -351,6 +382,8 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["quant", "deform", "decode", "codenet1x", "keys"]
     if "keys" in which:
         ref_keys()
+    if "w2mp" in which:
+        codenet_w2mp()
     if "quant" in which:
         quant_kat()
     if "deform" in which:

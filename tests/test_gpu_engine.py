@@ -164,3 +164,36 @@ def test_errors_are_loud(calib):
     with pytest.raises(_lib.CdnError):
         eng.set_option("nonsense", 1)
     eng.close()
+
+
+def test_engine_w2_maxpool_matches_reference_vectors(golden):
+    """Config e geometry (2x width, stride-2 stem + MaxPool) against the fp64 run of the unmodified reference."""
+    import torch
+    from util import maxpool3s2_int8
+    cfg = NetConfig(num_classes=20, w2=True, maxpool=True)
+    g = golden("codenet_w2mp_256_round.npz")
+    st = make_quant_state(cfg, golden("codenet_w2mp_calib.npz"), "round", 256)
+    eng = Engine.from_state_dict(cfg, st, 256, 256, 2, offset_mode="round")
+    x = make_images(2, 256, seed=2)[:1]
+    out = eng.run(torch.from_numpy(x.copy()).cuda())
+    torch.cuda.synchronize()
+    names = {"hm.act1": ("heads.act1", slice(0, 64), True), "hm.act3": ("heads.act3", slice(0, 64), False)}
+    checked = 0
+    for k in g.files:
+        if g[k].dtype != np.int8 or k.endswith(".s"):
+            continue
+        lbl, sl, up = names.get(k, (k, slice(None), False))
+        got = eng.read_logical(lbl, 1)[:, sl]
+        if up:
+            got = _up2(got)
+        ref = maxpool3s2_int8(g[k]) if k == "stem" else g[k]
+        assert int8_mismatch(got, ref) == 0, k
+        checked += 1
+    assert checked >= 17
+    heads = eng.read_heads(1)
+    np.testing.assert_allclose(heads, np.concatenate([g["hm_logit"], g["wh"], g["reg"]], 1), rtol=2e-7, atol=1e-7)
+    h64 = heads.astype(np.float64)
+    odets, oinds = io.ctdet_decode(h64[:, :20], h64[:, 20:22], h64[:, 22:24], 100)
+    np.testing.assert_array_equal(out["inds"].cpu().numpy(), oinds)
+    np.testing.assert_allclose(out["dets"].cpu().numpy(), odets, rtol=1e-5, atol=1e-4)
+    eng.close()

@@ -106,3 +106,27 @@ def test_int_oracle_512(golden, calib):
     dets, _ = io.ctdet_decode(out["hm"], out["wh"], out["reg"], 100)
     more, _ = io.ctdet_decode(out["hm"], out["wh"], out["reg"], 160)
     assert_dets_match_tie_aware(g["dets"][0], dets[0], more[0])
+
+
+def test_int_oracle_w2_maxpool(golden):
+    """Config e geometry (2x width, stride-2 stem + MaxPool): grids, heads and detections of the fp64 reference."""
+    from codenet_b200.arch import NetConfig
+    from util import maxpool3s2_int8
+    cfg = NetConfig(num_classes=20, w2=True, maxpool=True)
+    g = golden("codenet_w2mp_256_round.npz")
+    st = make_quant_state(cfg, golden("codenet_w2mp_calib.npz"), "round", 256)
+    o = io.IntOracle(cfg, st, "round")
+    out = o.forward(make_images(2, 256, seed=2)[:1])
+    assert o.saturated == 0
+    checked = 0
+    for k in g.files:
+        if g[k].dtype == np.int8:
+            ref = maxpool3s2_int8(g[k]) if k == "stem" else g[k]
+            assert int8_mismatch(o.cap[k], ref) == 0, k
+            checked += 1
+    assert checked >= 20
+    for n, k in (("hm", "hm_logit"), ("wh", "wh"), ("reg", "reg")):
+        np.testing.assert_allclose(out[n], g[k], rtol=1e-12, atol=1e-12)
+    dets, _ = io.ctdet_decode(out["hm"], out["wh"], out["reg"], 100)
+    more, _ = io.ctdet_decode(out["hm"], out["wh"], out["reg"], 160)
+    assert_dets_match_tie_aware(g["dets"][0], dets[0], more[0])

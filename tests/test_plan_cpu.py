@@ -51,6 +51,25 @@ def test_plan_descriptors_reproduce_oracle(calib, res):
     np.testing.assert_array_equal(heads, np.concatenate([out["hm"], out["wh"], out["reg"]], 1))
 
 
+def test_plan_descriptors_w2_maxpool(golden):
+    """The same for the 2x-width, stride-2 + MaxPool configuration (odd interleave groups of 61 channels, two N tiles
+    in stage 3, 2153-channel deformable layer)."""
+    cfg = NetConfig(num_classes=20, w2=True, maxpool=True)
+    st = make_quant_state(cfg, golden("codenet_w2mp_calib.npz"), "round", 256)
+    x = make_images(2, 256, seed=2)[:1]
+    plan = build_plan(cfg, st, 256, 256, "round")
+    o = io.IntOracle(cfg, st, "round")
+    out = o.forward(x)
+    T, heads = plan_sim.run_plan(plan, x)
+    n = 0
+    for lbl in plan.taps:
+        if lbl in o.cap:
+            assert int8_mismatch(plan_sim.logical(plan, T, lbl), o.cap[lbl]) == 0, lbl
+            n += 1
+    assert n >= 40
+    np.testing.assert_array_equal(heads, np.concatenate([out["hm"], out["wh"], out["reg"]], 1))
+
+
 def test_plan_shapes_config_c(calib):
     st = make_quant_state(CFG, calib, "round", 512)
     plan = build_plan(CFG, st, 512, 512, "round")

@@ -32,3 +32,11 @@ def int8_mismatch(a, b):
     a, b = np.asarray(a).astype(np.int64), np.asarray(b).astype(np.int64)
     assert a.shape == b.shape, (a.shape, b.shape)
     return int((a != b).sum())
+
+
+def maxpool3s2_int8(a):
+    """MaxPool2d(3, 2, 1) of an int8 grid [B,C,H,W] (the reference records the stem grid before its MaxPool)."""
+    B, C, H, W = a.shape
+    p = np.full((B, C, H + 2, W + 2), -128, np.int8)
+    p[:, :, 1:-1, 1:-1] = a
+    return np.max([p[:, :, i:i + H:2, j:j + W:2] for i in range(3) for j in range(3)], axis=0)
