@@ -87,6 +87,31 @@ __device__ __forceinline__ uint32_t rq_fast(int v_magic, float Mh, float Bh, flo
   if (PARITY) g.d1 = fmaxf(g.d1, d); else g.d0 = fmaxf(g.d0, d);
   return __float_as_uint(r);
 }
+// Two elements per FMA-pipe instruction with Blackwell's packed fp32 ops (FADD2 / FFMA2; `add/fma.rn.f32x2`): the same
+// sequence on register pairs, 23% fewer issue cycles per element at saturation (tools/ubench_requant.cu V10 vs V8).
+__device__ __forceinline__ float2 cdn_fadd2(float2 a, float2 b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+  return *reinterpret_cast<float2*>(&r);
+}
+__device__ __forceinline__ float2 cdn_ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(*reinterpret_cast<unsigned long long*>(&a)),
+      "l"(*reinterpret_cast<unsigned long long*>(&b)), "l"(*reinterpret_cast<unsigned long long*>(&c)));
+  return *reinterpret_cast<float2*>(&r);
+}
+// v0, v1: magic-biased accumulators of two elements; M2 = (Mh0, Mh1), B2 = (Bh0, Bh1).  Bit-identical to two rq_fast calls.
+__device__ __forceinline__ void rq_fast2(int v0, int v1, float2 M2, float2 B2, float lo_f, RqGuard& g, uint32_t& r0, uint32_t& r1) {
+  const float2 f = cdn_fadd2(make_float2(__int_as_float(v0), __int_as_float(v1)), make_float2(-CDN_MAGIC_F, -CDN_MAGIC_F));
+  float2 t = cdn_ffma2(f, M2, B2);
+  t.x = fmaxf(t.x, lo_f); t.y = fmaxf(t.y, lo_f);
+  g.tmax = fmaxf(g.tmax, fmaxf(t.x, t.y));
+  const float2 r = cdn_fadd2(t, make_float2(CDN_MAGIC_F, CDN_MAGIC_F));
+  const float2 kk = cdn_fadd2(r, make_float2(-CDN_MAGIC_F, -CDN_MAGIC_F));
+  const float2 d = cdn_ffma2(kk, make_float2(-1.0f, -1.0f), t);          // t - kk, exact (kk is an integer near t)
+  g.d0 = fmaxf(g.d0, fabsf(d.x)); g.d1 = fmaxf(g.d1, fabsf(d.y));
+  r0 = __float_as_uint(r.x); r1 = __float_as_uint(r.y);
+}
 // true when some element of the group was within eps of a rounding boundary or above the int8 range
 __device__ __forceinline__ bool rq_group_bad(const RqGuard& g, float thr) {
   return fmaxf(g.d0, g.d1) > thr || g.tmax > 127.0f + thr;

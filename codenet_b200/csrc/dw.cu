@@ -96,12 +96,11 @@ struct DwV2Params {
 
 struct DwLane { float Mh[4], Bh[4]; int abm[4]; };
 
-// requantise 4 channels of one pixel: accumulators (already magic-biased) -> packed word
+// requantise 4 channels of one pixel: accumulators (already magic-biased) -> packed word (two packed f32x2 pairs)
 __device__ __forceinline__ uint32_t dw_rq_word(const int (&acc)[4], const DwLane& k, float lo_f, RqGuard& g) {
-  const uint32_t r0 = rq_fast<0>(acc[0], k.Mh[0], k.Bh[0], lo_f, g);
-  const uint32_t r1 = rq_fast<1>(acc[1], k.Mh[1], k.Bh[1], lo_f, g);
-  const uint32_t r2 = rq_fast<0>(acc[2], k.Mh[2], k.Bh[2], lo_f, g);
-  const uint32_t r3 = rq_fast<1>(acc[3], k.Mh[3], k.Bh[3], lo_f, g);
+  uint32_t r0, r1, r2, r3;
+  rq_fast2(acc[0], acc[1], make_float2(k.Mh[0], k.Mh[1]), make_float2(k.Bh[0], k.Bh[1]), lo_f, g, r0, r1);
+  rq_fast2(acc[2], acc[3], make_float2(k.Mh[2], k.Mh[3]), make_float2(k.Bh[2], k.Bh[3]), lo_f, g, r2, r3);
   return pack4_lowbytes(r0, r1, r2, r3);
 }
 __device__ __noinline__ uint32_t dw_rq_word_exact(int a0, int a1, int a2, int a3, const double* __restrict__ M,
@@ -350,8 +349,9 @@ __global__ void __launch_bounds__(256, MODE == 0 ? 4 : 1) deform_dw_v2_kernel(co
           acc[2] = dp4a_ss(x[8], k.wC[2], dp4a_ss(b2, k.wB[2], dp4a_ss(a2, k.wA[2], abm[2])));
           acc[3] = dp4a_ss(x[8], k.wC[3], dp4a_ss(b3, k.wB[3], dp4a_ss(a3, k.wA[3], abm[3])));
           RqGuard gd; rq_guard_init(gd);
-          const uint32_t r0 = rq_fast<0>(acc[0], Mh[0], Bh[0], p.lo_f, gd), r1 = rq_fast<1>(acc[1], Mh[1], Bh[1], p.lo_f, gd);
-          const uint32_t r2 = rq_fast<0>(acc[2], Mh[2], Bh[2], p.lo_f, gd), r3 = rq_fast<1>(acc[3], Mh[3], Bh[3], p.lo_f, gd);
+          uint32_t r0, r1, r2, r3;
+          rq_fast2(acc[0], acc[1], make_float2(Mh[0], Mh[1]), make_float2(Bh[0], Bh[1]), p.lo_f, gd, r0, r1);
+          rq_fast2(acc[2], acc[3], make_float2(Mh[2], Mh[3]), make_float2(Bh[2], Bh[3]), p.lo_f, gd, r2, r3);
           uint32_t o = pack4_lowbytes(r0, r1, r2, r3);
           if (rq_group_bad(gd, p.thr_layer)) o = dw_rq_word_exact(acc[0], acc[1], acc[2], acc[3], p.M, p.B, cw * 4, p.lo_f);
           base_out[(unsigned)(j * p.out_pitch_w)] = o;

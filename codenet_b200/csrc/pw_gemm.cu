@@ -137,30 +137,36 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // ---------------------------------------------------------------------------------------------------------
 // epilogue math
 // ---------------------------------------------------------------------------------------------------------
-// NCOL accumulators -> NCOL "magic" floats whose low byte is the int8 result.  `kc` points at the per-column
-// records {Mh, Bh, bits(acc_bias + MAGIC_I), -} of the first column (shared memory in the tcgen05 kernel).
-// Returns true when some column of this lane came within eps of a rounding boundary (fp32 not trustworthy).
+// NCOL accumulators -> NCOL "magic" floats whose low byte is the int8 result.  `kc` points at the constants of the
+// first column, stored per PAIR of columns (c even): kc[c] = {Mh[c], Mh[c+1], Bh[c], Bh[c+1]},
+// kc[c+1] = {bits(acc_bias[c] + MAGIC_I), bits(acc_bias[c+1] + MAGIC_I), -, -}: one LDS.128 + one LDS.64 feed a
+// packed FFMA2 directly.  Returns true when some column of this lane came within eps of a rounding boundary.
 template <int NCOL>
 __device__ __forceinline__ bool requant_cols_fast(const uint32_t (&acc)[16], const float4* __restrict__ kc, float lo_f,
                                                   float thr, uint32_t (&rb)[16]) {
   RqGuard g; rq_guard_init(g);
 #pragma unroll
   for (int i = 0; i < NCOL; i += 2) {
-    const float4 k0 = kc[i], k1 = kc[i + 1];
-    rb[i] = rq_fast<0>((int)acc[i] + __float_as_int(k0.z), k0.x, k0.y, lo_f, g);
-    rb[i + 1] = rq_fast<1>((int)acc[i + 1] + __float_as_int(k1.z), k1.x, k1.y, lo_f, g);
+    const float4 mb = kc[i];
+    const float2 ab = *reinterpret_cast<const float2*>(kc + i + 1);
+    rq_fast2((int)acc[i] + __float_as_int(ab.x), (int)acc[i + 1] + __float_as_int(ab.y), make_float2(mb.x, mb.y),
+             make_float2(mb.z, mb.w), lo_f, g, rb[i], rb[i + 1]);
   }
   return rq_group_bad(g, thr);
 }
+__device__ __forceinline__ int kc_acc_bias(const float4* __restrict__ kc, int n) {     // kc = table base, n = column
+  const float4 r = kc[(n & ~1) + 1];
+  return __float_as_int((n & 1) ? r.y : r.x) - CDN_MAGIC_I;
+}
 
-// exact fp64 re-evaluation of the same NCOL columns (rare)
+// exact fp64 re-evaluation of the same NCOL columns (rare); kc = table base here
 template <int NCOL>
 __device__ __forceinline__ void requant_cols_exact(const uint32_t (&acc)[16], const float4* __restrict__ kc, int col,
                                                    const double* __restrict__ Md, const double* __restrict__ Bd, float lo_f,
                                                    uint32_t (&rb)[16]) {
 #pragma unroll
   for (int i = 0; i < NCOL; ++i)
-    rb[i] = rq_exact((int)acc[i] + (__float_as_int(kc[i].z) - CDN_MAGIC_I), __ldg(Md + col + i), __ldg(Bd + col + i), lo_f);
+    rb[i] = rq_exact((int)acc[i] + kc_acc_bias(kc, col + i), __ldg(Md + col + i), __ldg(Bd + col + i), lo_f);
 }
 
 // keep the first nb bytes of a 16-byte vector, zero the rest
@@ -180,13 +186,13 @@ __device__ __forceinline__ uint4 chunk_bytes(const cdn_pw_chunk& ck, const uint3
   if (ck.pass_off < 0) {
     if (ck.count == 0) return make_uint4(0u, 0u, 0u, 0u);
     const bool bad = requant_cols_fast<16>(acc, kc + ck.col, lo_f, thr, q);
-    if (__any_sync(__activemask(), bad)) { if (bad) requant_cols_exact<16>(acc, kc + ck.col, ck.col, Md, Bd, lo_f, q); }
+    if (__any_sync(__activemask(), bad)) { if (bad) requant_cols_exact<16>(acc, kc, ck.col, Md, Bd, lo_f, q); }
     o.x = pack4_lowbytes(q[0], q[1], q[2], q[3]);   o.y = pack4_lowbytes(q[4], q[5], q[6], q[7]);
     o.z = pack4_lowbytes(q[8], q[9], q[10], q[11]); o.w = pack4_lowbytes(q[12], q[13], q[14], q[15]);
     if (ck.count < 16) o = mask_tail(o, ck.count);   // pad bytes of the pixel stay zero
   } else {
     const bool bad = requant_cols_fast<8>(acc, kc + ck.col, lo_f, thr, q);
-    if (__any_sync(__activemask(), bad)) { if (bad) requant_cols_exact<8>(acc, kc + ck.col, ck.col, Md, Bd, lo_f, q); }
+    if (__any_sync(__activemask(), bad)) { if (bad) requant_cols_exact<8>(acc, kc, ck.col, Md, Bd, lo_f, q); }
     const uint32_t n_lo = pack4_lowbytes(q[0], q[1], q[2], q[3]), n_hi = pack4_lowbytes(q[4], q[5], q[6], q[7]);
     // out[2i] = pass[i], out[2i+1] = new[i]
     o.x = __byte_perm(pass_lo, n_lo, 0x5140); o.y = __byte_perm(pass_lo, n_lo, 0x7362);
@@ -410,7 +416,7 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int i = 0; i < 16; ++i) {
               const int n = nt * p.BN + c0 + i;
               if (n < p.n_f32) {
-                const int a = (int)acc[i] + (__float_as_int(s_kc[n].z) - CDN_MAGIC_I);
+                const int a = (int)acc[i] + kc_acc_bias(s_kc, n);
                 const double y = __dadd_rn(__dmul_rn((double)a, __ldg(p.Mf + n)), __ldg(p.bf + n));
                 p.out_f32[((size_t)img * p.n_f32 + n) * p.ppi + pi] = (float)y;
               }
@@ -587,14 +593,17 @@ int pw_device_build(PwDevice& d, const cdn_pw_desc* desc, int pass_pitch) {
   if (dev_upload(&d.w, w.data(), w.size())) return CDN_ERR_CUDA;
   std::vector<float4> kc(Np);
   double min_thr = 0.5;
-  auto fill_kc = [&](const DevRequant&, const cdn_requant* rq) {
-    for (int n = 0; n < Np; ++n) {
-      RqFast f{0.f, 0.f, 0.5f};
-      if (rq && n < rq->n) f = rq_fast_from(rq->M[n], rq->B[n]);
-      int32_t bits = ab[n] + CDN_MAGIC_I_HOST;
-      float z; memcpy(&z, &bits, 4);
-      kc[n] = make_float4(f.Mh, f.Bh, z, 0.f);
-      if (rq && n < rq->n) min_thr = std::min(min_thr, (double)f.thr);
+  auto fill_kc = [&](const DevRequant&, const cdn_requant* rq) {      // pair layout, see requant_cols_fast
+    for (int n = 0; n < Np; n += 2) {
+      RqFast f[2] = {{0.f, 0.f, 0.5f}, {0.f, 0.f, 0.5f}};
+      float z[2];
+      for (int j = 0; j < 2; ++j) {
+        if (rq && n + j < rq->n) { f[j] = rq_fast_from(rq->M[n + j], rq->B[n + j]); min_thr = std::min(min_thr, (double)f[j].thr); }
+        int32_t bits = ab[n + j] + CDN_MAGIC_I_HOST;
+        memcpy(&z[j], &bits, 4);
+      }
+      kc[n] = make_float4(f[0].Mh, f[1].Mh, f[0].Bh, f[1].Bh);
+      kc[n + 1] = make_float4(z[0], z[1], 0.f, 0.f);
     }
   };
   std::vector<cdn_pw_chunk> ch;
