@@ -48,6 +48,11 @@ EXPORTS = {
     "cdn_deform_dw_w4a8": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(DeformScale),
                                      C.POINTER(C.c_int8), C.c_int, C.c_int, C.POINTER(Requant), C.c_void_p, C.c_int,
                                      C.c_void_p, C.c_void_p]),
+    "cdn_deform_layer_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(DeformScale), C.POINTER(C.c_int8), C.c_int, C.c_int,
+                                          C.c_int, C.POINTER(Requant)]),
+    "cdn_deform_layer_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                       C.c_int, C.c_void_p, C.c_void_p]),
+    "cdn_deform_layer_destroy": (C.c_int, [C.c_void_p]),
     "cdn_pw_gemm_i8": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.POINTER(PwDesc), C.c_void_p, C.c_int, C.c_void_p,
                                  C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "cdn_ctdet_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

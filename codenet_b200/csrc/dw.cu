@@ -254,7 +254,10 @@ __global__ void __launch_bounds__(256, MODE == 0 ? 4 : 1) deform_dw_v2_kernel(co
   const int rs_in = p.Ws * p.in_pitch_w;
   // channel-group assignment of this warp in phase C
   const int Gw = p.G >= 8 ? 8 : (p.G >= 4 ? 4 : (p.G >= 2 ? 2 : 1));
-  const int wg = warp % Gw, wslot = warp / Gw, nslot = 8 / Gw;
+  const int wg = warp % Gw, nslot = 8 / Gw;
+  // narrow layers (fewer than 32 channel words): a warp covers ppw = 32 / lpp pixels at once instead of idling lanes
+  const int lpp = p.lpp, ppw = 32 / lpp, sub = lane / lpp, cl = lane % lpp;
+  const int wslot = (warp / Gw) * ppw + sub, jstep = nslot * ppw;
   const long long ntiles = (p.total + DEF_NP - 1) / DEF_NP;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long long base = tile * DEF_NP;
@@ -301,7 +304,7 @@ __global__ void __launch_bounds__(256, MODE == 0 ? 4 : 1) deform_dw_v2_kernel(co
     __syncthreads();
     // ---------------- phase C: gather, MAC, requantise ----------------
     for (int g = wg; g < p.G; g += Gw) {
-      const int cw = g * 32 + lane;
+      const int cw = g * 32 + cl;
       const bool active = cw < p.cw_total;
       LaneConsts k; load_lane_consts(p, cw, active, k);
       float Mh[4], Bh[4]; int abm[4];
@@ -360,8 +363,8 @@ __global__ void __launch_bounds__(256, MODE == 0 ? 4 : 1) deform_dw_v2_kernel(co
         int j = wslot;
         if (j < nvalid) fetch(j, xa);
 #pragma unroll 1
-        for (; j < nvalid; j += 2 * nslot) {
-          const int j1 = j + nslot, j2 = j + 2 * nslot;
+        for (; j < nvalid; j += 2 * jstep) {
+          const int j1 = j + jstep, j2 = j + 2 * jstep;
           if (j1 < nvalid) fetch(j1, xb);
           compute(j, xa);
           if (j2 < nvalid) fetch(j2, xa);
@@ -369,7 +372,7 @@ __global__ void __launch_bounds__(256, MODE == 0 ? 4 : 1) deform_dw_v2_kernel(co
         }
       } else {
 #pragma unroll 1
-      for (int j = wslot; j < DEF_NP; j += nslot) {
+      for (int j = wslot; j < DEF_NP; j += jstep) {
         const long long pix = base + j;
         if (pix >= p.total || !active) continue;
         const uint32_t hw = s_hw[j];

@@ -112,6 +112,36 @@ extern "C" int cdn_pw_gemm_i8(const int8_t* d_in, int in_pitch, int64_t pixels, 
   return r;
 }
 
+// ---- persistent fused deformable layer (constants uploaded once; used by the layer sweep and by integrations that
+// keep the reference's module structure) ------------------------------------------------------------------------------
+struct cdn_deform_layer { DwDevice dw; cdn_deform_scale sc; std::vector<int8_t> ws; int C, Cp, zx, device; };
+
+extern "C" int cdn_deform_layer_create(cdn_deform_layer** out, const cdn_deform_scale* sc, const int8_t* wq, int C, int pitch,
+                                       int zx, const cdn_requant* rq) {
+  CDN_CHECK(out && sc && sc->ws && wq && rq, CDN_ERR_INVALID, "deform layer: null argument");
+  int dev = 0; CDN_CUDA(cudaGetDevice(&dev));
+  if (int r = cdn_check_device(dev)) return r;
+  cdn_deform_layer* L = new cdn_deform_layer();
+  L->C = C; L->Cp = pitch; L->zx = zx; L->device = dev;
+  L->sc = *sc; L->ws.assign(sc->ws, sc->ws + C); L->sc.ws = L->ws.data();
+  if (int r = dw_device_build(L->dw, wq, sc->ws, C, pitch, zx, rq)) { delete L; return r; }
+  *out = L;
+  return 0;
+}
+extern "C" int cdn_deform_layer_run(cdn_deform_layer* L, const int8_t* d_in, int in_pitch, int batch, int H, int W, int in_shift,
+                                    int8_t* d_out, int out_pitch, float* d_sval, cdn_stream_t stream) {
+  CDN_CHECK(L != nullptr, CDN_ERR_INVALID, "null deform layer");
+  CDN_CHECK(std::min(in_pitch, out_pitch) >= L->Cp, CDN_ERR_INVALID, "deform layer: pitch smaller than the layer's %d", L->Cp);
+  return deform_launch(L->dw, &L->sc, d_in, in_pitch, d_out, out_pitch, batch, H, W, in_shift, L->zx, d_sval, (cudaStream_t)stream);
+}
+extern "C" int cdn_deform_layer_destroy(cdn_deform_layer* L) {
+  if (!L) return 0;
+  cudaSetDevice(L->device);
+  dw_device_free(L->dw);
+  delete L;
+  return 0;
+}
+
 static int decode_standalone(const float* d_hm, const float* d_wh, const float* d_reg, int batch, int cat, int H, int W,
                              int K, int is_prob, float* d_dets, int32_t* d_inds, cdn_stream_t stream) {
   unsigned long long* scratch = nullptr;

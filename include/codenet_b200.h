@@ -95,6 +95,16 @@ int cdn_deform_dw_w4a8(const int8_t* d_in, int in_pitch, int batch, int H, int W
                        const cdn_deform_scale* sc, const int8_t* wq, int C, int zx, const cdn_requant* rq,
                        int8_t* d_out, int out_pitch, float* d_sval, cdn_stream_t stream);
 
+/* The same layer with its constants uploaded once (no allocation or synchronisation per call): what an integration that
+ * keeps the reference's module structure holds per QuantDeformConvWithOffsetScaleBoundPositive, and what the isolated
+ * layer sweep (tools/deform_sweep.py, BASELINE config 2) times.  `pitch` = bytes per pixel of the tensors it will see. */
+typedef struct cdn_deform_layer cdn_deform_layer;
+int cdn_deform_layer_create(cdn_deform_layer** out, const cdn_deform_scale* sc, const int8_t* wq, int C, int pitch, int zx,
+                            const cdn_requant* rq);
+int cdn_deform_layer_run(cdn_deform_layer* layer, const int8_t* d_in, int in_pitch, int batch, int H, int W, int in_shift,
+                         int8_t* d_out, int out_pitch, float* d_sval, cdn_stream_t stream);
+int cdn_deform_layer_destroy(cdn_deform_layer* layer);
+
 /* ---- 1x1 convolution as int8 tcgen05 GEMM ---------------------------------------------------------------
  * acc[p][n] = sum_k wq[n][k] * (in[p][k_off + k] + zx)   (exact int32; the library adds zx*sum_k wq[n][k] itself)
  * Output "chunks" describe where each group of <=16 output channels lands in the NHWC row, so that split /
