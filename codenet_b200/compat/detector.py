@@ -201,6 +201,23 @@ class CtdetDetector:
         return (output, dets, forward_time) if return_time else (output, dets)
 
     def post_process(self, dets, meta, scale=1):
+        if torch.is_tensor(dets) and dets.is_cuda and dets.dtype == torch.float32:
+            # coordinate transform on the device (cdn_ctdet_post_affine), only the per-class grouping stays on the host
+            import ctypes as C
+            from .. import _lib
+            d = dets.detach().reshape(1, -1, dets.shape[2]).contiguous().clone()
+            t = np.ascontiguousarray(get_affine_transform(meta['c'], meta['s'], 0, (meta['out_width'], meta['out_height']),
+                                                          inv=1), dtype=np.float64).reshape(1, 6)
+            with torch.cuda.device(d.device):
+                _lib.check(_lib.load().cdn_ctdet_post_affine(C.c_void_p(d.data_ptr()), 1, d.shape[1], C.c_void_p(t.ctypes.data),
+                                                             C.c_void_p(torch.cuda.current_stream(d.device).cuda_stream)))
+            d = d.cpu().numpy()
+            classes = d[0, :, -1]
+            out = {}
+            for j in range(self.num_classes):
+                out[j + 1] = np.ascontiguousarray(d[0, classes == j, :5], dtype=np.float32).reshape(-1, 5)
+                out[j + 1][:, :4] /= scale
+            return out
         dets = dets.detach().cpu().numpy()
         dets = dets.reshape(1, -1, dets.shape[2])
         dets = ctdet_post_process(dets.copy(), [meta['c']], [meta['s']], meta['out_height'], meta['out_width'],

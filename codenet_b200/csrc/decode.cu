@@ -270,3 +270,40 @@ int decode_launch(const float* hm, long long hm_img_stride, const float* wh, lon
   CDN_LAUNCH_CHECK("ctdet_decode_kernel");
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// ctdet_post_process on the device (lib/utils/post_process.py:86-103 with transform_preds / affine_transform,
+// lib/utils/image.py:14-21,58-61): both box corners of every detection go through the image's inverse affine map,
+// evaluated like numpy does -- np.dot(t[float64 2x3], [x, y, 1][float32]) accumulated left to right in double, then
+// stored into the float32 detections array.  In place on dets [batch][K][6]; trans: [batch][6] doubles (row major 2x3).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void ctdet_post_affine_kernel(float* dets, const double* trans, int K, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const double* t = trans + (i / K) * 6;
+  float* d = dets + i * 6;
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const double x = (double)d[2 * c], y = (double)d[2 * c + 1];
+    const double nx = __dadd_rn(__dadd_rn(__dmul_rn(t[0], x), __dmul_rn(t[1], y)), t[2]);
+    const double ny = __dadd_rn(__dadd_rn(__dmul_rn(t[3], x), __dmul_rn(t[4], y)), t[5]);
+    d[2 * c] = (float)nx; d[2 * c + 1] = (float)ny;
+  }
+}
+
+extern "C" int cdn_ctdet_post_affine(float* d_dets, int batch, int K, const double* h_trans, cdn_stream_t stream) {
+  CDN_CHECK(d_dets && h_trans && batch >= 0 && K >= 1, CDN_ERR_INVALID, "post_affine: bad arguments");
+  if (batch == 0) return 0;
+  double* d_t = nullptr;
+  CDN_CUDA(cudaMalloc(&d_t, (size_t)batch * 6 * sizeof(double)));
+  cudaError_t e = cudaMemcpyAsync(d_t, h_trans, (size_t)batch * 6 * sizeof(double), cudaMemcpyHostToDevice, (cudaStream_t)stream);
+  const long long total = (long long)batch * K;
+  if (e == cudaSuccess) {
+    ctdet_post_affine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_dets, d_t, K, total);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+  cudaFree(d_t);
+  CDN_CHECK(e == cudaSuccess, CDN_ERR_CUDA, "post_affine: %s", cudaGetErrorString(e));
+  return 0;
+}

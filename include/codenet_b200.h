@@ -147,6 +147,12 @@ int cdn_ctdet_decode(const float* d_hm, const float* d_wh, const float* d_reg, i
 int cdn_ctdet_decode_prob(const float* d_heat, const float* d_wh, const float* d_reg, int batch, int cat, int H, int W,
                           int K, float* d_dets, int32_t* d_inds, cdn_stream_t stream);
 
+/* ctdet_post_process's coordinate transform on the device (lib/utils/post_process.py:86-103, transform_preds /
+ * affine_transform lib/utils/image.py:14-21,58-61): both corners of every box of dets [batch][K][6] (in place) go through
+ * the image's inverse affine map h_trans [batch][6] (host doubles, row-major 2x3), evaluated as numpy evaluates
+ * np.dot(t, [x, y, 1]) in double and rounded once to float.  Synchronises the stream. */
+int cdn_ctdet_post_affine(float* d_dets, int batch, int K, const double* h_trans, cdn_stream_t stream);
+
 /* ---- general deformable convolution forward, fp32 (the reference's native plug-in point) ----------------
  * Same argument meaning and order (W before H) as deform_conv_forward_cuda; tensors are contiguous NCHW device
  * pointers: input [B][C][H][W], weight [Co][C/group][kH][kW], offset [B][2*kH*kW*dg][Ho][Wo], output [B][Co][Ho][Wo].

@@ -15,6 +15,7 @@ Vectors produced (all from the reference's own code through oracle/ref_harness.p
                     intermediates
   codenet1x_512_round.npz   one 512^2 image (config c geometry): detections + strided output samples
   codenet_w2mp_{calib,256_round}.npz   the same for the w2 + S2/MaxPool configuration (config e geometry), one 256^2 image
+  post_kat.npz      ctdet_post_process (lib/utils/post_process.py:86-103) on random detections
   ref_state_keys.json   state-dict key spaces of the reference network before / after quantisation (1x, w2, maxpool)
 """
 import os
@@ -357,6 +358,25 @@ def codenet_w2mp():
     print("codenet_w2mp ok; unique scores:", len(np.unique(cap["dets"][0, :, 4])))
 
 
+def post_kat():
+    """ctdet_post_process (lib/utils/post_process.py:86-103) on random detections: the host / device restatements
+    of the box transform are pinned against it."""
+    H.load_reference()
+    from utils.post_process import ctdet_post_process
+    rng = np.random.Generator(np.random.PCG64(14))
+    dets = np.zeros((2, 50, 6), np.float32)
+    dets[:, :, :4] = rng.uniform(-5, 130, (2, 50, 4)); dets[:, :, 4] = rng.uniform(0, 1, (2, 50)); dets[:, :, 5] = rng.integers(0, 5, (2, 50))
+    c = [np.array([213.5, 160.0], np.float32), np.array([320.0, 240.0], np.float32)]
+    s = [427.0, np.array([672.0, 512.0], np.float32)]
+    out = ctdet_post_process(dets.copy(), c, s, 128, 128, 5)
+    flat = {}
+    for i, d in enumerate(out):
+        for j, v in d.items():
+            flat["img%d_cls%d" % (i, j)] = np.array(v, np.float32).reshape(-1, 5)
+    np.savez_compressed(os.path.join(OUT, "post_kat.npz"), dets=dets, c0=c[0], c1=c[1], s0=np.array(s[0]), s1=s[1], **flat)
+    print("post_kat ok")
+
+
 def ref_keys():
     """State-dict key spaces (name -> shape) of the UNMODIFIED reference network before and after
     quantize_shufflenetv2_dcn, for 1x / w2 / maxpool: what codenet_b200.compat must reproduce so checkpoints load."""
@@ -379,9 +399,11 @@ if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["quant", "deform", "decode", "codenet1x", "keys"]
+    which = sys.argv[1:] or ["quant", "deform", "decode", "codenet1x", "keys", "post", "w2mp"]
     if "keys" in which:
         ref_keys()
+    if "post" in which:
+        post_kat()
     if "w2mp" in which:
         codenet_w2mp()
     if "quant" in which:

@@ -151,3 +151,14 @@ def test_pre_process_is_normalisation_only_at_input_size():
     want = np.stack([lut[c][img[:, :, c]] for c in range(3)])[None]
     np.testing.assert_array_equal(images.numpy(), want)
     assert meta["out_height"] == 24 and float(meta["s"]) == 96.0
+
+
+def test_post_process_matches_the_reference(golden):
+    """The numpy restatement of ctdet_post_process against vectors from the reference's own function (cv2 affine)."""
+    from codenet_b200.compat import detector as D
+    g = golden("post_kat.npz")
+    out = D.ctdet_post_process(g["dets"].copy(), [g["c0"], g["c1"]], [float(g["s0"]), g["s1"]], 128, 128, 5)
+    for i in range(2):
+        for j in range(1, 6):
+            got = np.array(out[i][j], np.float32).reshape(-1, 5)
+            np.testing.assert_allclose(got, g["img%d_cls%d" % (i, j)], rtol=1e-6, atol=1e-4)

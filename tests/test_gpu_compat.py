@@ -150,3 +150,20 @@ def test_uint8_input_is_bit_identical_to_normalised_fp32(calib):
     slow = det.merge_outputs([det.post_process(dets, meta, 1.0)])
     for j in range(1, 21):
         np.testing.assert_array_equal(fast["results"][j], slow[j])
+
+
+def test_post_process_on_device_matches_host_restatement(calib):
+    """cdn_ctdet_post_affine against the numpy restatement of ctdet_post_process (lib/utils/post_process.py:86-103)."""
+    import torch
+    from codenet_b200.compat import detector as D
+    det = _detector(calib, "round", 256, max_batch=1)
+    rng = np.random.default_rng(4)
+    dets = np.zeros((1, 100, 6), np.float32)
+    dets[0, :, :4] = rng.uniform(-5, 70, (100, 4)); dets[0, :, 4] = np.sort(rng.uniform(0, 1, 100))[::-1]
+    dets[0, :, 5] = rng.integers(0, 20, 100)
+    meta = {'c': np.array([213.5, 160.0], np.float32), 's': 427.0, 'out_height': 64, 'out_width': 64}
+    got = det.post_process(torch.from_numpy(dets).cuda(), meta, 1.0)
+    want = D.ctdet_post_process(dets.copy(), [meta['c']], [meta['s']], 64, 64, 20)[0]
+    for j in range(1, 21):
+        w = np.array(want[j], dtype=np.float32).reshape(-1, 5)
+        np.testing.assert_array_equal(got[j], w)
