@@ -31,6 +31,7 @@ struct DwParams {
   double Ms, bs, ss, zs, u_lo, u_hi;
   float* sval;
   const float2* mb; const int* abm; float thr_layer;   // lean requantisation constants (v2 kernels)
+  float thr_bil;                             // guard of the fp32 bilinear fast path (0.5 - eps, host-derived bound)
 };
 
 struct LaneConsts {
@@ -242,14 +243,76 @@ __global__ void __launch_bounds__(128) dw3x3_v2_kernel(const DwV2Params p) {
 //            two byte transposes, 12 dp4a, lean guarded requantisation.  MODE 1 (bilinear): fp64, following the
 //            oracle's operation order exactly (dcn_deform_conv_cuda_kernel.cu:83-114,210-227 on exact integers).
 // ---------------------------------------------------------------------------------------------------------
+// Exact bilinear evaluation of one output word (4 channels): fp64 on exact integers in the oracle's operation order
+// (dcn_deform_conv_cuda_kernel.cu:83-114,210-227).  Used for every element by nothing any more: it is the fallback of the
+// guarded fp32 fast path below (and the definition of the result).
+__device__ __noinline__ uint32_t deform_bilinear_exact_word(const DwParams& p, const uint32_t* __restrict__ img, int h, int w,
+                                                            double s, int cw) {
+  LaneConsts k; load_lane_consts(p, cw, true, k);        // rare path: fetch its own constants, keep the fast loop lean
+        // bilinear: real values a = q + zx, zero outside the image
+  const int zx = -(int)(int8_t)(p.pad_word & 0xff);
+  const double d = __dsub_rn(s, 1.0);
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  // unpack per-channel tap weights from the packed registers
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    double h_im = __dadd_rn((double)(h - 1 + i), (double)(i - 1) * d);
+    double hl_d = floor(h_im);
+    double lh = __dsub_rn(h_im, hl_d), hh = __dsub_rn(1.0, lh);
+    int hl = (int)hl_d;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int tap = i * 3 + j;
+      double w_im = __dadd_rn((double)(w - 1 + j), (double)(j - 1) * d);
+      bool inside = h_im > -1.0 && w_im > -1.0 && h_im < (double)p.Hin && w_im < (double)p.Win;
+      double wl_d = floor(w_im);
+      double lw = __dsub_rn(w_im, wl_d), hw = __dsub_rn(1.0, lw);
+      int wl = (int)wl_d;
+      double bw[4] = {__dmul_rn(hh, hw), __dmul_rn(hh, lw), __dmul_rn(lh, hw), __dmul_rn(lh, lw)};
+      double val[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int cnr = 0; cnr < 4; ++cnr) {
+        int yy = hl + (cnr >> 1), xx = wl + (cnr & 1);
+        bool ok = inside && yy >= 0 && yy <= p.Hin - 1 && xx >= 0 && xx <= p.Win - 1;
+        uint32_t word = 0; 
+        if (ok) word = __ldg(img + ((size_t)(yy >> p.shift) * p.Ws + (xx >> p.shift)) * p.in_pitch_w);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          double v = ok ? (double)((int)(int8_t)((word >> (8 * c)) & 0xff) + zx) : 0.0;
+          double term = __dmul_rn(bw[cnr], v);
+          val[c] = (cnr == 0) ? term : __dadd_rn(val[c], term);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t wword = tap < 4 ? k.wA[c] : (tap < 8 ? k.wB[c] : k.wC[c]);
+        int sh = tap < 8 ? 8 * (tap & 3) : 8 * c;
+        double wq = (double)(int)(int8_t)((wword >> sh) & 0xff);
+        acc[c] = __dadd_rn(acc[c], __dmul_rn(wq, val[c]));
+      }
+    }
+  }
+  uint32_t r[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    int ch = cw * 4 + c;
+    double td = __dadd_rn(__dmul_rn(acc[c], __ldg(p.M + ch)), __ldg(p.B + ch));
+    td = fmin(fmax(rint(td), (double)p.lo_f), 127.0);
+    r[c] = (uint32_t)((int)td & 0xff);
+  }
+  return r[0] | (r[1] << 8) | (r[2] << 16) | (r[3] << 24);
+}
+
 #define DEF_NP 64
 
 template <int MODE>
-__global__ void __launch_bounds__(256, MODE == 0 ? 4 : 1) deform_dw_v2_kernel(const DwParams p) {
+__global__ void __launch_bounds__(256, MODE == 0 ? 4 : 3) deform_dw_v2_kernel(const DwParams p) {
   __shared__ double s_s[DEF_NP];
   __shared__ uint32_t s_hw[DEF_NP];
   __shared__ int s_b[DEF_NP];                  // word offset of the pixel's image
   __shared__ int s_si[DEF_NP];                 // integer offset scalar (MODE 0)
+  __shared__ int s_hl[MODE == 1 ? 2 * DEF_NP : 1], s_wl[MODE == 1 ? 2 * DEF_NP : 1];      // MODE 1: floor of the outer tap rows / columns
+  __shared__ float s_lh[MODE == 1 ? 2 * DEF_NP : 1], s_lw[MODE == 1 ? 2 * DEF_NP : 1];   //         and their fractional parts
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rs_in = p.Ws * p.in_pitch_w;
   // channel-group assignment of this warp in phase C
@@ -297,6 +360,20 @@ __global__ void __launch_bounds__(256, MODE == 0 ? 4 : 1) deform_dw_v2_kernel(co
         if (MODE == 0) s = rint(s);
         s_s[warp + 8 * lane] = s;
         s_hw[warp + 8 * lane] = my_hw; s_b[warp + 8 * lane] = my_b * p.Hs * rs_in; s_si[warp + 8 * lane] = (int)s;
+        if (MODE == 1) {
+          // sample rows / columns of the outer taps (i, j = 0 and 2; the centre row / column is h, w exactly):
+          // h_im = (h - 1 + i) + (i - 1)(s - 1) in fp64 as the oracle forms it, its floor and fractional part
+          const int jp = warp + 8 * lane, hh_ = (int)(my_hw >> 16), ww_ = (int)(my_hw & 0xffffu);
+          const double dd = __dsub_rn(s, 1.0);
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const double sg = e ? 1.0 : -1.0;
+            const double him = __dadd_rn((double)(hh_ - 1 + 2 * e), sg * dd), wim = __dadd_rn((double)(ww_ - 1 + 2 * e), sg * dd);
+            const double hf = floor(him), wf = floor(wim);
+            s_hl[2 * jp + e] = (int)hf; s_lh[2 * jp + e] = (float)__dsub_rn(him, hf);
+            s_wl[2 * jp + e] = (int)wf; s_lw[2 * jp + e] = (float)__dsub_rn(wim, wf);
+          }
+        }
         const long long pix = base + warp + 8 * lane;
         if (p.sval != nullptr && pix < p.total) p.sval[pix] = (float)s;
       }
@@ -307,6 +384,17 @@ __global__ void __launch_bounds__(256, MODE == 0 ? 4 : 1) deform_dw_v2_kernel(co
       const int cw = g * 32 + cl;
       const bool active = cw < p.cw_total;
       LaneConsts k; load_lane_consts(p, cw, active, k);
+      float wf[MODE == 1 ? 4 : 1][MODE == 1 ? 9 : 1];                     // MODE 1: tap weights as floats
+      if (MODE == 1) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            const uint32_t wword = tap < 4 ? k.wA[c] : (tap < 8 ? k.wB[c] : k.wC[c]);
+            const int sh = tap < 8 ? 8 * (tap & 3) : 8 * c;
+            wf[MODE == 1 ? c : 0][MODE == 1 ? tap : 0] = (float)(int)(int8_t)((wword >> sh) & 0xff);
+          }
+      }
       float Mh[4], Bh[4]; int abm[4];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -379,60 +467,59 @@ __global__ void __launch_bounds__(256, MODE == 0 ? 4 : 1) deform_dw_v2_kernel(co
         const int w = (int)(hw & 0xffffu), h = (int)(hw >> 16);
         const uint32_t* img = p.in + s_b[j] + cw;
         const double s = s_s[j];
+        // ---- fp32 fast path: the 36 corners of the 9 taps lie on a 5 x 5 lattice (rows hl0, hl0+1, h, hl2, hl2+1 and the
+        // same for columns); blend separably (columns, then the row weight), guard the rounding, fall back to fp64
+        uint32_t oword;
         {
-        // bilinear: real values a = q + zx, zero outside the image
-        const int zx = -(int)(int8_t)(p.pad_word & 0xff);
-        const double d = __dsub_rn(s, 1.0);
-        double acc[4] = {0.0, 0.0, 0.0, 0.0};
-        // unpack per-channel tap weights from the packed registers
-  #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          double h_im = __dadd_rn((double)(h - 1 + i), (double)(i - 1) * d);
-          double hl_d = floor(h_im);
-          double lh = __dsub_rn(h_im, hl_d), hh = __dsub_rn(1.0, lh);
-          int hl = (int)hl_d;
-  #pragma unroll
-          for (int j = 0; j < 3; ++j) {
-            const int tap = i * 3 + j;
-            double w_im = __dadd_rn((double)(w - 1 + j), (double)(j - 1) * d);
-            bool inside = h_im > -1.0 && w_im > -1.0 && h_im < (double)p.Hin && w_im < (double)p.Win;
-            double wl_d = floor(w_im);
-            double lw = __dsub_rn(w_im, wl_d), hw = __dsub_rn(1.0, lw);
-            int wl = (int)wl_d;
-            double bw[4] = {__dmul_rn(hh, hw), __dmul_rn(hh, lw), __dmul_rn(lh, hw), __dmul_rn(lh, lw)};
-            double val[4] = {0.0, 0.0, 0.0, 0.0};
-  #pragma unroll
-            for (int cnr = 0; cnr < 4; ++cnr) {
-              int yy = hl + (cnr >> 1), xx = wl + (cnr & 1);
-              bool ok = inside && yy >= 0 && yy <= p.Hin - 1 && xx >= 0 && xx <= p.Win - 1;
-              uint32_t word = 0; 
-              if (ok) word = __ldg(img + ((size_t)(yy >> p.shift) * p.Ws + (xx >> p.shift)) * p.in_pitch_w);
-  #pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                double v = ok ? (double)((int)(int8_t)((word >> (8 * c)) & 0xff) + zx) : 0.0;
-                double term = __dmul_rn(bw[cnr], v);
-                val[c] = (cnr == 0) ? term : __dadd_rn(val[c], term);
-              }
-            }
-  #pragma unroll
+          const int zx = -(int)(int8_t)(p.pad_word & 0xff);
+          const float unb = 8388608.0f + 128.0f - (float)zx;                 // as_float(0x4B000000 | (q ^ 0x80)) - unb = q + zx
+          const int hl0 = s_hl[2 * j], hl2 = s_hl[2 * j + 1], wl0 = s_wl[2 * j], wl2 = s_wl[2 * j + 1];
+          const float lh0 = s_lh[2 * j], lh2 = s_lh[2 * j + 1], lw0 = s_lw[2 * j], lw2 = s_lw[2 * j + 1];
+          const int R[5] = {hl0, hl0 + 1, h, hl2, hl2 + 1}, Cc[5] = {wl0, wl0 + 1, w, wl2, wl2 + 1};
+          const float rho[5] = {1.0f - lh0, lh0, 1.0f, 1.0f - lh2, lh2};
+          const float cwt[4] = {1.0f - lw0, lw0, 1.0f - lw2, lw2};
+          unsigned co[5]; bool cv[5];
+#pragma unroll
+          for (int q = 0; q < 5; ++q) {
+            cv[q] = (unsigned)Cc[q] < (unsigned)p.Win;
+            co[q] = (unsigned)((min(max(Cc[q], 0), p.Win - 1) >> p.shift) * p.in_pitch_w);
+          }
+          float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int r = 0; r < 5; ++r) {
+            const bool rv = (unsigned)R[r] < (unsigned)p.Hin;
+            const unsigned ro = (unsigned)((min(max(R[r], 0), p.Hin - 1) >> p.shift) * rs_in);
+            uint32_t xw[5];
+#pragma unroll
+            for (int q = 0; q < 5; ++q) xw[q] = __ldg(img + (ro + co[q]));
+#pragma unroll
+            for (int q = 0; q < 5; ++q) xw[q] = ((rv && cv[q]) ? xw[q] : p.pad_word) ^ 0x80808080u;
+            const int ti = r < 2 ? 0 : (r == 2 ? 1 : 2);                     // tap row fed by this lattice row
+#pragma unroll
             for (int c = 0; c < 4; ++c) {
-              uint32_t wword = tap < 4 ? k.wA[c] : (tap < 8 ? k.wB[c] : k.wC[c]);
-              int sh = tap < 8 ? 8 * (tap & 3) : 8 * c;
-              double wq = (double)(int)(int8_t)((wword >> sh) & 0xff);
-              acc[c] = __dadd_rn(acc[c], __dmul_rn(wq, val[c]));
+              float a[5];
+#pragma unroll
+              for (int q = 0; q < 5; ++q) a[q] = __uint_as_float(__byte_perm(xw[q], 0x4B000000u, 0x7650 + c)) - unb;
+              const float u0 = fmaf(cwt[1], a[1], cwt[0] * a[0]), u1 = a[2], u2 = fmaf(cwt[3], a[4], cwt[2] * a[3]);
+              const float t = fmaf(wf[c][ti * 3 + 2], u2, fmaf(wf[c][ti * 3 + 1], u1, wf[c][ti * 3] * u0));
+              acc[c] = fmaf(rho[r], t, acc[c]);
             }
           }
+          RqGuard gd; rq_guard_init(gd);
+          uint32_t rr[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            float t = fmaf(acc[c], Mh[c], Bh[c]);
+            t = fmaxf(t, p.lo_f);
+            gd.tmax = fmaxf(gd.tmax, t);
+            const float r_ = __fadd_rn(t, CDN_MAGIC_F), kk = __fadd_rn(r_, -CDN_MAGIC_F);
+            gd.d0 = fmaxf(gd.d0, fabsf(__fadd_rn(t, -kk)));
+            rr[c] = __float_as_uint(r_);
+          }
+          oword = pack4_lowbytes(rr[0], rr[1], rr[2], rr[3]);
+          if (rq_group_bad(gd, p.thr_bil)) oword = deform_bilinear_exact_word(p, img, h, w, s, cw);
         }
-        uint32_t r[4];
-  #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          int ch = cw * 4 + c;
-          double td = __dadd_rn(__dmul_rn(acc[c], __ldg(p.M + ch)), __ldg(p.B + ch));
-          td = fmin(fmax(rint(td), (double)p.lo_f), 127.0);
-          r[c] = (uint32_t)((int)td & 0xff);
-        }
-          p.out[(size_t)pix * p.out_pitch_w + cw] = r[0] | (r[1] << 8) | (r[2] << 16) | (r[3] << 24);
-        }
+        p.out[(size_t)pix * p.out_pitch_w + cw] = oword;
       }
       }
     }
@@ -499,6 +586,17 @@ int dw_device_build(DwDevice& d, const int8_t* wq, const int8_t* ws, int C, int 
       min_thr = std::min(min_thr, (double)f.thr);
     }
     d.thr = (float)min_thr; d.u_ok = u_ok ? 1 : 0;
+    // fp32 bilinear fast path (deform MODE 1): |acc_fp32 - acc| <= sum|w| * 255 * 25u (separable blend: 2u per
+    // interpolation weight, one rounding per FMUL/FFMA, 5 lattice rows; u = 2^-24), times 1.25 for safety; mapped through
+    // M and added to the requantisation bound
+    double max_eps = 0.0;
+    for (int c = 0; c < C; ++c) {
+      double asum = 0; for (int t = 0; t < 9; ++t) asum += fabs((double)wq[c * 9 + t]);
+      const double eps_acc = 1.25 * asum * 255.0 * 25.0 * ldexp(1.0, -24);
+      RqFast f = rq_fast_from(rq->M[c], rq->B[c]);
+      max_eps = std::max(max_eps, eps_acc * fabs(rq->M[c]) + (0.5 - (double)f.thr));
+    }
+    d.thr_bil = (float)(0.5 - std::min(max_eps, 0.49));
     if (dev_upload(&d.wpk1, w1.data(), w1.size())) return CDN_ERR_CUDA;
     if (dev_upload(&d.wpk2, w2.data(), w2.size())) return CDN_ERR_CUDA;
     if (dev_upload(&d.wpku, wu.data(), wu.size())) return CDN_ERR_CUDA;
@@ -536,7 +634,7 @@ static void fill_common(DwParams& p, const DwDevice& d, const int8_t* in, int in
   p.lo_f = (float)d.rq.lo;
   p.acc_s_bias = d.acc_s_bias;
   p.sval = nullptr;
-  p.mb = d.mb; p.abm = d.abm; p.thr_layer = d.thr;
+  p.mb = d.mb; p.abm = d.abm; p.thr_layer = d.thr; p.thr_bil = d.thr_bil;
 }
 
 int dw_launch(const DwDevice& d, const int8_t* in, int in_pitch, int8_t* out, int out_pitch, int batch, int H, int W,

@@ -5,7 +5,7 @@
 struct DwDevice {                            // depthwise / deformable layer constants
   uint32_t *wA = nullptr, *wB = nullptr, *wC = nullptr, *ws = nullptr;
   uint32_t *wpk1 = nullptr, *wpk2 = nullptr, *wpku = nullptr;   // v2 packings: stride 1, stride 2, upsample-folded
-  float2* mb = nullptr; int32_t* abm = nullptr; float thr = 0.5f; int u_ok = 1;
+  float2* mb = nullptr; int32_t* abm = nullptr; float thr = 0.5f, thr_bil = 0.01f; int u_ok = 1;
   DevRequant rq;
   int cw_total = 0;
   long long acc_s_bias = 0;
