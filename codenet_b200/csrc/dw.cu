@@ -304,6 +304,7 @@ __device__ __noinline__ uint32_t deform_bilinear_exact_word(const DwParams& p, c
 }
 
 #define DEF_NP 64
+#define DEF_QCAP 1024
 
 template <int MODE>
 __global__ void __launch_bounds__(256, MODE == 0 ? 4 : 3) deform_dw_v2_kernel(const DwParams p) {
@@ -311,6 +312,7 @@ __global__ void __launch_bounds__(256, MODE == 0 ? 4 : 3) deform_dw_v2_kernel(co
   __shared__ uint32_t s_hw[DEF_NP];
   __shared__ int s_b[DEF_NP];                  // word offset of the pixel's image
   __shared__ int s_si[DEF_NP];                 // integer offset scalar (MODE 0)
+  __shared__ uint32_t s_q[MODE == 1 ? DEF_QCAP : 1]; __shared__ int s_qn;   // MODE 1: words awaiting exact evaluation
   __shared__ int s_hl[MODE == 1 ? 2 * DEF_NP : 1], s_wl[MODE == 1 ? 2 * DEF_NP : 1];      // MODE 1: floor of the outer tap rows / columns
   __shared__ float s_lh[MODE == 1 ? 2 * DEF_NP : 1], s_lw[MODE == 1 ? 2 * DEF_NP : 1];   //         and their fractional parts
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -322,6 +324,7 @@ __global__ void __launch_bounds__(256, MODE == 0 ? 4 : 3) deform_dw_v2_kernel(co
   const int lpp = p.lpp, ppw = 32 / lpp, sub = lane / lpp, cl = lane % lpp;
   const int wslot = (warp / Gw) * ppw + sub, jstep = nslot * ppw;
   const long long ntiles = (p.total + DEF_NP - 1) / DEF_NP;
+  if (threadIdx.x == 0) s_qn = 0;              // published by the first tile's __syncthreads
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long long base = tile * DEF_NP;
     // ---------------- phase A: s for the tile's pixels ----------------
@@ -469,7 +472,7 @@ __global__ void __launch_bounds__(256, MODE == 0 ? 4 : 3) deform_dw_v2_kernel(co
         const double s = s_s[j];
         // ---- fp32 fast path: the 36 corners of the 9 taps lie on a 5 x 5 lattice (rows hl0, hl0+1, h, hl2, hl2+1 and the
         // same for columns); blend separably (columns, then the row weight), guard the rounding, fall back to fp64
-        uint32_t oword;
+        uint32_t oword; bool queued = false;
         {
           const int zx = -(int)(int8_t)(p.pad_word & 0xff);
           const float unb = 8388608.0f + 128.0f - (float)zx;                 // as_float(0x4B000000 | (q ^ 0x80)) - unb = q + zx
@@ -517,13 +520,31 @@ __global__ void __launch_bounds__(256, MODE == 0 ? 4 : 3) deform_dw_v2_kernel(co
             rr[c] = __float_as_uint(r_);
           }
           oword = pack4_lowbytes(rr[0], rr[1], rr[2], rr[3]);
-          if (rq_group_bad(gd, p.thr_bil)) oword = deform_bilinear_exact_word(p, img, h, w, s, cw);
+          if (rq_group_bad(gd, p.thr_bil)) {
+            // Rare (~1 % of the words) but ~30x the work: doing it here would stall the whole warp for one lane, so
+            // the word is queued and all 256 threads drain the queue densely at the end of the tile.
+            const int pos = atomicAdd(&s_qn, 1);
+            if (pos < DEF_QCAP) { s_q[pos] = ((uint32_t)j << 16) | (uint32_t)cw; queued = true; }
+            else oword = deform_bilinear_exact_word(p, img, h, w, s, cw);
+          }
         }
-        p.out[(size_t)pix * p.out_pitch_w + cw] = oword;
+        if (!queued) p.out[(size_t)pix * p.out_pitch_w + cw] = oword;
       }
       }
     }
+    if (MODE == 1) {                           // drain the exact-evaluation queue of this tile
+      __syncthreads();
+      const int nq = min(s_qn, DEF_QCAP);
+      for (int i = threadIdx.x; i < nq; i += blockDim.x) {
+        const uint32_t e = s_q[i];
+        const int j = (int)(e >> 16), cw = (int)(e & 0xffffu);
+        const uint32_t hw = s_hw[j];
+        p.out[(size_t)(base + j) * p.out_pitch_w + cw] =
+            deform_bilinear_exact_word(p, p.in + s_b[j] + cw, (int)(hw >> 16), (int)(hw & 0xffffu), s_s[j], cw);
+      }
+    }
     __syncthreads();                         // s_s is rewritten by the next tile
+    if (MODE == 1 && threadIdx.x == 0) s_qn = 0;
   }
 }
 
@@ -586,13 +607,15 @@ int dw_device_build(DwDevice& d, const int8_t* wq, const int8_t* ws, int C, int 
       min_thr = std::min(min_thr, (double)f.thr);
     }
     d.thr = (float)min_thr; d.u_ok = u_ok ? 1 : 0;
-    // fp32 bilinear fast path (deform MODE 1): |acc_fp32 - acc| <= sum|w| * 255 * 25u (separable blend: 2u per
-    // interpolation weight, one rounding per FMUL/FFMA, 5 lattice rows; u = 2^-24), times 1.25 for safety; mapped through
-    // M and added to the requantisation bound
+    // fp32 bilinear fast path (deform MODE 1), u = 2^-24, A = 255 >= |q + zx|, S = sum_ij |w_ij| of the channel:
+    //   column blend u0 = fl(c1*a1 + fl(c0*a0)), c0 + c1 = 1, weights off by <= u each:        |err| <= 4 A u
+    //   t_r = 3 fma over the tap columns:                     |err| <= S_i A (4 + 3) u  (S_i = sum_j |w_ij|)
+    //   acc += rho_r * t_r, rho off by <= 2u, the rho of a tap row sum to 1, 5 fma roundings:  |err| <= S A (7 + 2 + 5) u
+    // so |acc_fp32 - acc| <= 14 S A u; 16 is used.  Mapped through M and added to the requantisation bound.
     double max_eps = 0.0;
     for (int c = 0; c < C; ++c) {
       double asum = 0; for (int t = 0; t < 9; ++t) asum += fabs((double)wq[c * 9 + t]);
-      const double eps_acc = 1.25 * asum * 255.0 * 25.0 * ldexp(1.0, -24);
+      const double eps_acc = asum * 255.0 * 16.0 * ldexp(1.0, -24);
       RqFast f = rq_fast_from(rq->M[c], rq->B[c]);
       max_eps = std::max(max_eps, eps_acc * fabs(rq->M[c]) + (0.5 - (double)f.thr));
     }
