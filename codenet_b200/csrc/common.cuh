@@ -48,6 +48,11 @@ static inline RqFast rq_fast_from(double M, double B) {
 
 #define CDN_MAGIC_I_HOST 0x4B400000
 #ifdef __CUDACC__
+// Programmatic dependent launch: every engine kernel lets its successor start early (launch_dependents at entry); a
+// successor launched with the programmatic-serialization attribute runs its prologue (barrier init, TMEM allocation,
+// constant tables, weight loads) while this grid drains and calls pdl_wait() before touching activations.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 #define CDN_MAGIC_F 12582912.0f              // 1.5 * 2^23
 #define CDN_MAGIC_I 0x4B400000
 

@@ -78,6 +78,7 @@ __global__ void __launch_bounds__(256) ctdet_peaks_kernel(DecParams p, int batch
 // is loaded ~1.4 times (one float4 + two halo scalars per row) instead of 9.
 #define DEC_STRIP 16
 __global__ void __launch_bounds__(256) ctdet_peaks_rows_kernel(DecParams p, int strips_per_plane) {
+  pdl_launch_dependents();
   const int HW = p.H * p.W, W4 = p.W >> 2;
   const unsigned n = (unsigned)p.cat * HW;
   const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

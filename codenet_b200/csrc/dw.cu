@@ -128,6 +128,7 @@ __device__ __forceinline__ void dw_transpose_row(const uint32_t (&w)[4], uint32_
 
 template <int STRIDE, int SHIFT>
 __global__ void __launch_bounds__(128) dw3x3_v2_kernel(const DwV2Params p) {
+  pdl_launch_dependents();
   constexpr int NW = DwV2<STRIDE, SHIFT>::NW;
   const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;        // host guarantees nthreads < 2^31
   if (idx >= (unsigned)p.nthreads) return;
@@ -150,6 +151,7 @@ __global__ void __launch_bounds__(128) dw3x3_v2_kernel(const DwV2Params p) {
     const int4 av = __ldg((const int4*)(p.abm + cw * 4));
     k.abm[0] = av.x; k.abm[1] = av.y; k.abm[2] = av.z; k.abm[3] = av.w;
   }
+  pdl_wait();                                  // constants above do not depend on the previous grid; activations do
   const int rs_in = p.Ws * p.in_pitch_w;                                 // words per stored input row
   const uint32_t* img = p.in + (size_t)b * p.Hs * rs_in + cw;
   uint32_t* outb = p.out + (size_t)b * p.Hout * p.Wout * p.out_pitch_w + cw;
@@ -308,6 +310,7 @@ __device__ __noinline__ uint32_t deform_bilinear_exact_word(const DwParams& p, c
 
 template <int MODE>
 __global__ void __launch_bounds__(256, MODE == 0 ? 4 : 3) deform_dw_v2_kernel(const DwParams p) {
+  pdl_launch_dependents();
   __shared__ double s_s[DEF_NP];
   __shared__ uint32_t s_hw[DEF_NP];
   __shared__ int s_b[DEF_NP];                  // word offset of the pixel's image
@@ -325,6 +328,7 @@ __global__ void __launch_bounds__(256, MODE == 0 ? 4 : 3) deform_dw_v2_kernel(co
   const int wslot = (warp / Gw) * ppw + sub, jstep = nslot * ppw;
   const long long ntiles = (p.total + DEF_NP - 1) / DEF_NP;
   if (threadIdx.x == 0) s_qn = 0;              // published by the first tile's __syncthreads
+  pdl_wait();
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long long base = tile * DEF_NP;
     // ---------------- phase A: s for the tile's pixels ----------------
@@ -686,9 +690,15 @@ int dw_launch(const DwDevice& d, const int8_t* in, int in_pitch, int8_t* out, in
   CDN_CHECK(p.nthreads < (1ll << 31) && (long long)p.Hs * p.Ws * p.in_pitch_w < (1ll << 31) &&
             (long long)p.Hout * p.Wout * p.out_pitch_w < (1ll << 31), CDN_ERR_INVALID, "dw: tensor too large for 32-bit indexing");
   const unsigned blocks = (unsigned)((p.nthreads + 127) / 128);
-  if (in_shift) dw3x3_v2_kernel<1, 1><<<blocks, 128, 0, st>>>(p);
-  else if (stride == 2) dw3x3_v2_kernel<2, 0><<<blocks, 128, 0, st>>>(p);
-  else dw3x3_v2_kernel<1, 0><<<blocks, 128, 0, st>>>(p);
+  cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(128); cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = (g_cdn_debug_flags & 64u) ? 0 : 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  if (in_shift) CDN_CUDA(cudaLaunchKernelEx(&cfg, dw3x3_v2_kernel<1, 1>, p));
+  else if (stride == 2) CDN_CUDA(cudaLaunchKernelEx(&cfg, dw3x3_v2_kernel<2, 0>, p));
+  else CDN_CUDA(cudaLaunchKernelEx(&cfg, dw3x3_v2_kernel<1, 0>, p));
   CDN_LAUNCH_CHECK("dw3x3_v2_kernel");
   return 0;
 }
@@ -710,8 +720,14 @@ int deform_launch(const DwDevice& d, const cdn_deform_scale* sc, const int8_t* i
   const long long ntiles = (p.total + DEF_NP - 1) / DEF_NP;
   const long long cap = (long long)cdn_num_sms() * 8;
   const unsigned blocks = (unsigned)std::min(ntiles, cap);
-  if (sc->mode == 0) deform_dw_v2_kernel<0><<<blocks, 256, 0, st>>>(p);
-  else deform_dw_v2_kernel<1><<<blocks, 256, 0, st>>>(p);
+  cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(256); cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = (g_cdn_debug_flags & 64u) ? 0 : 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  if (sc->mode == 0) CDN_CUDA(cudaLaunchKernelEx(&cfg, deform_dw_v2_kernel<0>, p));
+  else CDN_CUDA(cudaLaunchKernelEx(&cfg, deform_dw_v2_kernel<1>, p));
   CDN_LAUNCH_CHECK("deform_dw_v2_kernel");
   return 0;
 }

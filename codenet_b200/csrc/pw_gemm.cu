@@ -213,6 +213,7 @@ __global__ void __launch_bounds__(PW_THREADS, 1)
 pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmO,
                   const PwParams p) {
+  pdl_launch_dependents();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
   const int Ntot = p.BN * p.n_tiles;
@@ -284,6 +285,7 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int nt = 0; nt < p.n_tiles; ++nt)
             tma_load_2d(smem_u32(s_B + ((size_t)kb * Ntot + (size_t)nt * p.BN) * PW_BK), &tmB, kb * PW_BK, nt * p.BN, BFULL);
       }
+      pdl_wait();                              // weights above are constants; activations need the previous grid
       // Two independent cursors -- activation (and streamed weight) blocks into the ring, pass-through tiles into
       // their own buffers -- advanced by polling, so a full pass buffer never stops the activation prefetch.
       int stage = 0; uint32_t phase = 0;
@@ -359,6 +361,7 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // 128-byte output segment is complete, this warp issues the store, waits until the TMA engine has read the
     // buffer and hands it back through SEMPTY.
     const int grp = warp - PW_STORE_WARP0;
+    pdl_wait();
     if (lane == 0 && p.n_f32 == 0 && grp < p.groups) {
       uint32_t g = 0;
       for (unsigned tile = blockIdx.x + grp * gridDim.x; tile < total_tiles; tile += p.groups * gridDim.x) {
@@ -383,6 +386,7 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // Two independent groups of 8 warps: group g owns TMEM accumulator stage g, pass buffer g and its own staging
     // buffers, and handles every other tile of this CTA, so one group's latency phases (barrier waits, TMEM /
     // shared-memory loads, the TMA store hand-off) overlap the other group's arithmetic.
+    pdl_wait();                                // the fp32 head path stores to global memory directly
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
     const int grp = (warp - 2) / (PW_EPI_WARPS / PW_EPI_GROUPS);
     const int half = ((warp - 2) >> 2) % PW_EPI_PARTS;   // which of the PW_EPI_PARTS warps of the quarter (inside the group)
@@ -760,7 +764,13 @@ int pw_launch(const PwDevice& d, const int8_t* in, int in_pitch, long long pixel
   long long tiles = p.m_tiles * p.n_tiles;
   CDN_CHECK(tiles < (1ll << 31) && pixels < (1ll << 31), CDN_ERR_INVALID, "pw: too many pixels for 32-bit tile indexing");
   int grid = (int)std::min<long long>(tiles, cdn_num_sms());
-  pw_gemm_tc_kernel<<<grid, PW_THREADS, d.smem_bytes, st>>>(a, d.tmB, pm, o, p);
+  cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(PW_THREADS); cfg.dynamicSmemBytes = d.smem_bytes; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = (g_cdn_debug_flags & 64u) ? 0 : 1;   // bit 6: disable PDL (experiments)
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  CDN_CUDA(cudaLaunchKernelEx(&cfg, pw_gemm_tc_kernel, a, d.tmB, pm, o, p));
   CDN_LAUNCH_CHECK("pw_gemm_tc_kernel");
   return 0;
 }

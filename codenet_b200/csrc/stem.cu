@@ -24,6 +24,7 @@ struct StemParams {
 // pre-normalised fp32 image -- with a quarter of the host-to-device bytes.
 template <bool U8>
 __global__ void __launch_bounds__(128) stem_kernel(const __grid_constant__ StemParams p) {
+  pdl_launch_dependents();
   __shared__ float slut[U8 ? 768 : 1];
   if (U8) for (int i = threadIdx.x; i < 768; i += blockDim.x) slut[i] = p.lut[i];
   __syncthreads();
@@ -83,6 +84,7 @@ __global__ void __launch_bounds__(128) stem_kernel(const __grid_constant__ StemP
 // MaxPool2d(3, 2, 1) on the int8 grid (monotone, so it commutes with the quantiser; padding = -inf)
 __global__ void maxpool3s2_kernel(const uint32_t* in, uint32_t* out, int H, int W, int Ho, int Wo, int pitch_w,
                                   long long total_words) {
+  pdl_launch_dependents();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total_words) return;
   int cw = (int)(idx % pitch_w); long long pix = idx / pitch_w;
