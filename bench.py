@@ -126,8 +126,6 @@ def run_ours(args):
     st = make_quant_state(cfg, calib, args.offset_mode, 512)
     B, R = args.batch, 512
     eng = Engine.from_state_dict(cfg, st, R, R, B, offset_mode=args.offset_mode, device=local)
-    if args.micro_batch:
-        eng.set_option("micro_batch", args.micro_batch)
     eng.set_option("host_chunk", args.host_chunk)
     # synthetic images: 16 distinct ones per rank, tiled to the batch (805 MB fp32 at B=256: larger than L2)
     base = make_images(min(16, B), R, seed=100 + rank)
@@ -329,7 +327,6 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--offset-mode", default="round", choices=["round", "bilinear"])
-    ap.add_argument("--micro-batch", type=int, default=0)
     ap.add_argument("--host-chunk", type=int, default=64)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs only)")
     ap.add_argument("--dump-ops", default="", help="write the per-op device times (JSON) to this file")

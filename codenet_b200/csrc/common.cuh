@@ -56,22 +56,6 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 #define CDN_MAGIC_F 12582912.0f              // 1.5 * 2^23
 #define CDN_MAGIC_I 0x4B400000
 
-// Returns the float whose LOW BYTE (of its bit pattern) is the int8 result; rq_bits_to_int() gives the int.
-__device__ __forceinline__ uint32_t requant_bits(int acc, float Mh, float Bh, float thr, float lo_f,
-                                                 const double* __restrict__ Md, const double* __restrict__ Bd, int ch) {
-  float t = fmaf((float)acc, Mh, Bh);
-  t = fminf(fmaxf(t, lo_f), 127.0f);
-  float r = t + CDN_MAGIC_F;
-  float k = r - CDN_MAGIC_F;
-  if (fabsf(t - k) > thr) {                  // within eps of a rounding boundary: exact fp64 evaluation
-    double td = __dadd_rn(__dmul_rn((double)acc, __ldg(Md + ch)), __ldg(Bd + ch));
-    td = fmin(fmax(td, (double)lo_f), 127.0);
-    r = (float)__double2int_rn(td) + CDN_MAGIC_F;
-  }
-  return __float_as_uint(r);
-}
-__device__ __forceinline__ int rq_bits_to_int(uint32_t bits) { return (int)bits - CDN_MAGIC_I; }
-
 // ---- lean requantisation (v2 kernels) ----------------------------------------------------------------------
 // One element costs IADD, FADD, FFMA, FMNMX, 3 FADD and two halves of 3-input FMNMX: the rounding-boundary guard
 // and the upper clamp are accumulated as running maxima over a group of elements and tested ONCE per group
@@ -128,7 +112,7 @@ __device__ __forceinline__ uint32_t rq_exact(int v, double M, double B, float lo
   return __float_as_uint((float)__double2int_rn(td) + CDN_MAGIC_F);
 }
 
-// pack the low bytes of four requant_bits() results into one little-endian word
+// pack the low bytes of four rq_fast / rq_exact results into one little-endian word
 __device__ __forceinline__ uint32_t pack4_lowbytes(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   uint32_t ab = __byte_perm(a, b, 0x0040);   // [a.0, b.0, a.0, a.0] -> bytes0,1 used
   uint32_t cd = __byte_perm(c, d, 0x0040);

@@ -50,22 +50,6 @@ __device__ __forceinline__ void load_lane_consts(const DwParams& p, int cw, bool
   }
 }
 
-// 9 tap words (4 channels each) -> requantised word
-__device__ __forceinline__ uint32_t mac9_requant(const uint32_t (&x)[9], const LaneConsts& k, const DwParams& p, int cw) {
-  uint32_t a0, a1, a2, a3, b0, b1, b2, b3;
-  transpose4x4(x[0], x[1], x[2], x[3], a0, a1, a2, a3);
-  transpose4x4(x[4], x[5], x[6], x[7], b0, b1, b2, b3);
-  int acc0 = dp4a_ss(a0, k.wA[0], k.ab[0]); acc0 = dp4a_ss(b0, k.wB[0], acc0); acc0 = dp4a_ss(x[8], k.wC[0], acc0);
-  int acc1 = dp4a_ss(a1, k.wA[1], k.ab[1]); acc1 = dp4a_ss(b1, k.wB[1], acc1); acc1 = dp4a_ss(x[8], k.wC[1], acc1);
-  int acc2 = dp4a_ss(a2, k.wA[2], k.ab[2]); acc2 = dp4a_ss(b2, k.wB[2], acc2); acc2 = dp4a_ss(x[8], k.wC[2], acc2);
-  int acc3 = dp4a_ss(a3, k.wA[3], k.ab[3]); acc3 = dp4a_ss(b3, k.wB[3], acc3); acc3 = dp4a_ss(x[8], k.wC[3], acc3);
-  uint32_t r0 = requant_bits(acc0, k.Mh[0], k.Bh[0], k.thr[0], p.lo_f, p.M, p.B, cw * 4 + 0);
-  uint32_t r1 = requant_bits(acc1, k.Mh[1], k.Bh[1], k.thr[1], p.lo_f, p.M, p.B, cw * 4 + 1);
-  uint32_t r2 = requant_bits(acc2, k.Mh[2], k.Bh[2], k.thr[2], p.lo_f, p.M, p.B, cw * 4 + 2);
-  uint32_t r3 = requant_bits(acc3, k.Mh[3], k.Bh[3], k.thr[3], p.lo_f, p.M, p.B, cw * 4 + 3);
-  return pack4_lowbytes(r0, r1, r2, r3);
-}
-
 // ---------------------------------------------------------------------------------------------------------
 // plain depthwise 3x3 (v2): sliding window down a column strip, horizontal taps packed for dp4a
 //

@@ -189,7 +189,7 @@ struct cdn_engine {
   float* lut = nullptr;                      // 3 x 256 normalisation table for uint8 input
   cudaStream_t s_compute = nullptr, s_copy = nullptr;
   std::vector<cudaEvent_t> ev;
-  int host_chunk = 64, use_graph = 1, micro_batch = 0, hm_logits = 0;
+  int host_chunk = 64, use_graph = 1, hm_logits = 0;
   // graph cache
   struct GraphKey { const void* a[6]; int batch; bool operator==(const GraphKey& o) const { return memcmp(this, &o, sizeof(*this)) == 0; } };
   std::vector<std::pair<GraphKey, cudaGraphExec_t>> graphs;
@@ -240,7 +240,6 @@ extern "C" int cdn_engine_set_option(cdn_engine* e, const char* name, int value)
   ENG_CHECK(e);
   if (!strcmp(name, "host_chunk")) e->host_chunk = std::max(1, value);
   else if (!strcmp(name, "use_graph")) e->use_graph = value;
-  else if (!strcmp(name, "micro_batch")) e->micro_batch = std::max(0, value);
   else if (!strcmp(name, "hm_logits")) e->hm_logits = value ? 1 : 0;
   else return cdn_fail(CDN_ERR_INVALID, "unknown engine option '%s'", name);
   return 0;

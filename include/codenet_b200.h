@@ -52,7 +52,9 @@ const char* cdn_last_error(void);
 int cdn_version(void);
 /* 0 = ok; CDN_ERR_NO_DEVICE if `device` is not a compute-capability-10.x GPU. */
 int cdn_check_device(int device);
-/* bit 0: run 1x1 convolutions on the SIMT cross-check kernel instead of tcgen05 (bring-up / tests only). */
+/* Bring-up / measurement switches, never needed in production.  bit 0: 1x1 convolutions on the SIMT cross-check kernel
+ * instead of tcgen05; bit 1: no CUDA graph (eager launches); bit 4: in-kernel phase cycle accounting of the GEMM
+ * (tools/pw_phase_cycles.py); bit 6: no programmatic dependent launch; bits 2, 3, 5: experiments that BREAK results. */
 int cdn_set_debug_flags(unsigned flags);
 
 /* ---- per-output-channel requantisation constants (host arrays, length n) ------------------------------- */
@@ -197,10 +199,9 @@ int cdn_engine_set_normalization(cdn_engine* e, const float* mean3, const float*
 int cdn_engine_run_u8(cdn_engine* e, const uint8_t* d_img, int batch, float* d_hm, float* d_wh, float* d_reg,
                       float* d_dets, int32_t* d_inds, cdn_stream_t stream);
 int cdn_engine_run_host_u8(cdn_engine* e, const uint8_t* h_img, int batch, float* h_dets, int32_t* h_inds);
-/* Options: "host_chunk" (images per H2D/compute pipeline step of run_host, default 64), "use_graph" (replay the
- * launch sequence as a CUDA graph, default 1), "micro_batch" (run the layers over sub-batches of this many images
- * so consecutive layers hit L2, 0 = whole batch), "hm_logits" (cdn_engine_run writes the heat map as logits, what
- * PoseShuffleNetV2.forward returns, instead of post-sigmoid; default 0). */
+/* Options: "host_chunk" (granularity of the H2D / compute pipeline of run_host: chunks grow x1.6 from host_chunk/2,
+ * default 64), "use_graph" (replay the launch sequence as a CUDA graph, default 1), "hm_logits" (cdn_engine_run writes
+ * the heat map as logits, what PoseShuffleNetV2.forward returns, instead of post-sigmoid; default 0). */
 int cdn_engine_set_option(cdn_engine* e, const char* name, int value);
 /* Debug/test access to an activation tensor of the last run: copies batch*H*W*pitch bytes to host. */
 int cdn_engine_read_tensor(cdn_engine* e, int tensor, int batch, int8_t* h_out);
