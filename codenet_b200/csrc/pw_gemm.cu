@@ -244,6 +244,12 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   // the MMAs of a group's next tile run while it still drains the previous one
   const int nacc = p.BN <= 128 ? 4 : 2;
   const uint32_t acc_stride = p.BN <= 128 ? 128u : 256u;
+  // nacc and pass_bufs are powers of two and n_tiles is 1 for most layers: no integer division on the per-tile paths
+  const uint32_t acc_mask = (uint32_t)nacc - 1u, acc_shift = nacc == 4 ? 2u : 1u;
+  const uint32_t pb_mask = (uint32_t)p.pass_bufs - 1u, pb_shift = p.pass_bufs == 4 ? 2u : (p.pass_bufs == 2 ? 1u : 0u);
+  auto split_tile = [&](unsigned tile, unsigned& mt, int& nt) {
+    if (p.n_tiles == 1) { mt = tile; nt = 0; } else { mt = tile / (unsigned)p.n_tiles; nt = (int)(tile - mt * (unsigned)p.n_tiles); }
+  };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -295,9 +301,9 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       while (a_tile < total_tiles || p_tile < total_tiles) {
         bool progressed = false;
         if (p_tile < total_tiles) {
-          const int pb = (int)(p_it % (uint32_t)p.pass_bufs); const uint32_t pph = (p_it / (uint32_t)p.pass_bufs) & 1;
+          const int pb = (int)(p_it & pb_mask); const uint32_t pph = (p_it >> pb_shift) & 1;
           if (mbar_test(PEMPTY(pb), pph ^ 1)) {
-            const unsigned mt = p_tile / (unsigned)p.n_tiles;
+            unsigned mt; int nt_; split_tile(p_tile, mt, nt_);
             mbar_expect_tx(PFULL(pb), (uint32_t)p.pass_segs * 16384u);
             for (int s = 0; s < p.pass_segs; ++s)
               tma_load_2d(smem_u32(s_pass + ((size_t)pb * p.pass_segs + s) * 16384), &tmP, s * 128, (int)(mt * PW_BM), PFULL(pb));
@@ -307,7 +313,7 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // without pass-through tiles there is nothing to interleave: block on the ring slot (hardware-suspended wait)
         if (a_tile < total_tiles && !p.has_pass) { DBG_T0(); mbar_wait(EMPTY(stage), phase ^ 1); DBG_ACC(0); }
         if (a_tile < total_tiles && (!p.has_pass || mbar_test(EMPTY(stage), phase ^ 1))) {
-          const unsigned mt = a_tile / (unsigned)p.n_tiles; const int nt = (int)(a_tile % (unsigned)p.n_tiles);
+          unsigned mt; int nt; split_tile(a_tile, mt, nt);
           uint8_t* sa = s_ring + (size_t)stage * stage_bytes;
           if (p.resident) {
             mbar_expect_tx(FULL(stage), a_bytes);
@@ -334,9 +340,9 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (p.resident) { mbar_wait(BFULL, 0); tc_fence_after(); }
       int stage = 0; uint32_t phase = 0; uint32_t it = 0;
       for (unsigned tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int nt = (int)(tile % (unsigned)p.n_tiles);
-        const int as = (int)(it % (uint32_t)nacc);                 // accumulator stages rotate over the CTA's tiles
-        const uint32_t aphase = (it / (uint32_t)nacc) & 1;
+        unsigned mt_; int nt; split_tile(tile, mt_, nt);
+        const int as = (int)(it & acc_mask);                       // accumulator stages rotate over the CTA's tiles
+        const uint32_t aphase = (it >> acc_shift) & 1;
         { DBG_T0(); mbar_wait(TEMPTY(as), aphase ^ 1); DBG_ACC(2); }
         tc_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)as * acc_stride;
@@ -363,12 +369,13 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int grp = warp - PW_STORE_WARP0;
     pdl_wait();
     if (lane == 0 && p.n_f32 == 0 && grp < p.groups) {
-      uint32_t g = 0;
+      uint32_t g = 0; int sbuf = 0; uint32_t sph = 0;          // staging buffer cursor (index, phase)
       for (unsigned tile = blockIdx.x + grp * gridDim.x; tile < total_tiles; tile += p.groups * gridDim.x) {
-        const unsigned mt = tile / (unsigned)p.n_tiles; const int nt = (int)(tile % (unsigned)p.n_tiles);
+        unsigned mt; int nt; split_tile(tile, mt, nt);
         const int sg0 = s_tile_seg[nt], sg1 = s_tile_seg[nt + 1];
         for (int sg = sg0; sg < sg1; ++sg, ++g) {
-          const int b_ = (int)(g % (uint32_t)p.nbuf); const uint32_t ph = (g / (uint32_t)p.nbuf) & 1;
+          const int b_ = sbuf; const uint32_t ph = sph;
+          if (++sbuf == p.nbuf) { sbuf = 0; sph ^= 1; }
           DBG_T0();
           mbar_wait(SFULL(grp, b_), ph);
           if (grp == 0) DBG_ACC(9);
@@ -394,17 +401,18 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int gt = (threadIdx.x - 64) % PW_GROUP_THREADS;
     uint8_t* const s_out_g = s_out + (size_t)grp * p.nbuf * 16384;
     uint32_t it2 = 0, g = 0;                   // tiles / output segments done by this group
+    int sbuf = 0; uint32_t sph = 0;            // staging buffer cursor (index, phase)
     for (unsigned tile = blockIdx.x + grp * gridDim.x; tile < total_tiles && grp < p.groups; tile += p.groups * gridDim.x, ++it2) {
-      const unsigned mt = tile / (unsigned)p.n_tiles; const int nt = (int)(tile % (unsigned)p.n_tiles);
+      unsigned mt; int nt; split_tile(tile, mt, nt);
       const uint32_t itg = it2 * (uint32_t)p.groups + grp;                   // CTA-wide tile counter (as producer / MMA count)
-      const int as = (int)(itg % (uint32_t)nacc);
-      const uint32_t aphase = (itg / (uint32_t)nacc) & 1;
+      const int as = (int)(itg & acc_mask);
+      const uint32_t aphase = (itg >> acc_shift) & 1;
       DBG_T0();
       mbar_wait(TFULL(as), aphase);
       if (warp == 2) DBG_ACC(4);
       tc_fence_after();
-      const int pb = (int)(itg % (uint32_t)p.pass_bufs);
-      if (p.has_pass) mbar_wait(PFULL(pb), (itg / (uint32_t)p.pass_bufs) & 1);
+      const int pb = (int)(itg & pb_mask);
+      if (p.has_pass) mbar_wait(PFULL(pb), (itg >> pb_shift) & 1);
       if (warp == 2) DBG_ACC(5);
       const uint32_t tacc = tmem_base + (uint32_t)as * acc_stride + ((uint32_t)(q * 32) << 16);
       if (p.n_f32 > 0) {
@@ -434,8 +442,9 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int sg0 = s_tile_seg[nt], sg1 = s_tile_seg[nt + 1];
         for (int sg = sg0; sg < sg1; ++sg, ++g) {
           const PwSeg S = s_segs[sg];
-          const int sb = (int)(g % (uint32_t)p.nbuf);
-          mbar_wait(SEMPTY(grp, sb), ((g / (uint32_t)p.nbuf) & 1) ^ 1);            // the store that last used this buffer has drained
+          const int sb = sbuf;
+          mbar_wait(SEMPTY(grp, sb), sph ^ 1);                                     // the store that last used this buffer has drained
+          if (++sbuf == p.nbuf) { sbuf = 0; sph ^= 1; }
           if (warp == 2) DBG_ACC(6);
           uint8_t* stg = s_out_g + (size_t)sb * 16384 + row * 128;
           for (int c = S.cb + half; c < S.ce; c += PW_EPI_PARTS) {
