@@ -61,6 +61,9 @@ EXPORTS = {
                                         C.c_void_p, C.c_void_p, C.c_void_p]),
     "cdn_ctdet_post_affine": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "cdn_deform_conv_forward_f32": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 16 + [C.c_void_p]),
+    "cdn_deform_dw_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                    C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "cdn_pw_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "cdn_engine_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
     "cdn_engine_destroy": (C.c_int, [C.c_void_p]),
     "cdn_engine_add_tensor": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),

@@ -126,9 +126,34 @@ class DeformConvWithOffsetScaleBoundPositive(nn.Module):
         self.anchor_offset = torch.FloatTensor(ANCHOR_OFFSET).unsqueeze(0).unsqueeze(2).unsqueeze(2)
 
     def forward(self, x):
-        """fp32 module-level forward on CUDA tensors: the gather + depthwise MAC is our kernel; the two 1x1 convs are
-        plain library convolutions here (the fused fp32 path is not built yet)."""
-        s = self.conv_bound(self.conv_scale(x))
-        o = self.anchor_offset.to(x.device) * (s - 1)
-        y = self.conv(x, o)
-        return self.conv_channel(y) if self.in_channels != self.out_channels else y
+        """fp32 module forward on CUDA tensors through two kernels of libcodenet_b200: the fused scale-conv + Hardtanh +
+        bilinear gather + depthwise MAC (cdn_deform_dw_f32: no offset tensor, no im2col) and, when in != out, the 1x1
+        conv_channel (cdn_pw_f32)."""
+        if x.dim() != 4:
+            raise ValueError("Expected 4D tensor as input, got {}D tensor instead.".format(x.dim()))
+        if not x.is_cuda:
+            raise NotImplementedError          # as the reference's DeformConvFunction does for CPU tensors
+        if x.dtype != torch.float32 or self.conv_scale.out_channels != 1 or self.conv.kernel_size != (3, 3) \
+                or self.conv.padding != (1, 1) or self.conv.dilation != (1, 1):
+            raise NotImplementedError("codenet_b200: the fused fp32 module covers CoDeNet's configuration "
+                                      "(float32, 3x3, pad 1, dilation 1, deformable_groups 1)")
+        L = _lib.load()
+        x = x.contiguous()
+        B, Cc, H, W = x.shape
+        st = self.conv.stride[0]
+        Ho, Wo = (H + 2 - 3) // st + 1, (W + 2 - 3) // st + 1
+        y = x.new_empty((B, Cc, Ho, Wo))
+        ws = self.conv_scale.weight.detach().reshape(-1).contiguous().float()
+        wd = self.conv.weight.detach().reshape(Cc, 9).contiguous().float()
+        stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+        with torch.cuda.device(x.device):
+            _lib.check(L.cdn_deform_dw_f32(C.c_void_p(x.data_ptr()), C.c_void_p(ws.data_ptr()),
+                                           C.c_float(float(self.conv_scale.bias.detach()[0])), int(self.offset_bound),
+                                           C.c_void_p(wd.data_ptr()), C.c_void_p(y.data_ptr()), B, Cc, H, W, st, stream))
+            if self.in_channels == self.out_channels:
+                return y
+            wc = self.conv_channel.weight.detach().reshape(self.out_channels, Cc).contiguous().float()
+            out = x.new_empty((B, self.out_channels, Ho, Wo))
+            _lib.check(L.cdn_pw_f32(C.c_void_p(y.data_ptr()), C.c_void_p(wc.data_ptr()), None, C.c_void_p(out.data_ptr()),
+                                    B, Cc, self.out_channels, Ho * Wo, stream))
+        return out

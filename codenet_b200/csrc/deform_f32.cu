@@ -78,3 +78,134 @@ extern "C" int cdn_deform_conv_forward_f32(const float* input, const float* weig
                  deformable_group, Ho, Wo, (long long)B * Co * Ho * Wo};
   return deform_f32_launch(p, (cudaStream_t)stream);
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Fused co-designed deformable module, fp32 NCHW (row a1 of SURVEY.md 8(a)):
+//   DeformConvWithOffsetScaleBoundPositive.forward, lib/models/external/modules/dcn_deform_conv.py:323-330 --
+//   s = Hardtanh[-bound+1, bound](conv1x1_{C->1, stride}(x) + bias);  o = anchor * (s - 1);
+//   y = deform_conv(x, o, W_dw[C,1,3,3], stride, pad 1, groups = C)
+// in ONE kernel: one thread per output pixel (lanes along W: coalesced NCHW rows).  The scale scalar is reduced over
+// the channels first; the 9 taps then share their sample geometry across all channels -- row / column floors and
+// fractions are computed once per pixel and kept in registers (the outer taps sit at (i-1)*s from the centre, the centre
+// row / column is integral), so the 18-channel offset tensor, the im2col buffer and the per-channel GEMMs of the
+// reference (dcn_deform_conv_cuda.cpp:196-245) never exist.  Sampling follows dcn_deform_conv_cuda_kernel.cu:83-114
+// (zero outside the image, per corner).
+// ---------------------------------------------------------------------------------------------------------
+struct DefDwF32Params {
+  const float* in; const float* ws; const float* wdw; float* out;
+  float bs, lo, hi;
+  int B, C, H, W, Ho, Wo, stride;
+  long long total;
+};
+
+__global__ void __launch_bounds__(128) deform_dw_f32_kernel(DefDwF32Params p) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p.total) return;
+  const int wo = (int)(idx % p.Wo); const long long t = idx / p.Wo; const int ho = (int)(t % p.Ho); const int b = (int)(t / p.Ho);
+  const size_t plane = (size_t)p.H * p.W;
+  const float* xb = p.in + (size_t)b * p.C * plane;
+  const int hc = ho * p.stride, wc = wo * p.stride;             // conv_scale has kernel 1, padding 0, stride = stride
+  float s = p.bs;
+  for (int c = 0; c < p.C; ++c) s = fmaf(__ldg(p.ws + c), __ldg(xb + c * plane + (size_t)hc * p.W + wc), s);
+  s = fminf(fmaxf(s, p.lo), p.hi);
+  const float d = s - 1.0f;
+  // sample rows / columns of the three tap rows / columns: h_im = ho*stride - 1 + i + (i - 1)*d
+  int r0[3], c0[3]; float lr[3], lc[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const float him = (float)(hc - 1 + i) + (float)(i - 1) * d, wim = (float)(wc - 1 + i) + (float)(i - 1) * d;
+    const float hf = floorf(him), wf = floorf(wim);
+    r0[i] = (int)hf; lr[i] = him - hf; c0[i] = (int)wf; lc[i] = wim - wf;
+    // outside the reference's range test (h_im > -1 && h_im < H): every corner is invalid or has weight zero already
+  }
+  float* ob = p.out + ((size_t)b * p.C * p.Ho + ho) * p.Wo + wo;
+  for (int c = 0; c < p.C; ++c) {
+    const float* img = xb + c * plane;
+    const float* wk = p.wdw + c * 9;
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int ya = r0[i], yb = ya + 1;
+      const bool va = (unsigned)ya < (unsigned)p.H, vb = (unsigned)yb < (unsigned)p.H;
+      const float* ra = img + (size_t)min(max(ya, 0), p.H - 1) * p.W;
+      const float* rb = img + (size_t)min(max(yb, 0), p.H - 1) * p.W;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int xa = c0[j], xb2 = xa + 1;
+        const bool ua = (unsigned)xa < (unsigned)p.W, ub = (unsigned)xb2 < (unsigned)p.W;
+        const int xac = min(max(xa, 0), p.W - 1), xbc = min(max(xb2, 0), p.W - 1);
+        const float v1 = (va && ua) ? __ldg(ra + xac) : 0.f, v2 = (va && ub) ? __ldg(ra + xbc) : 0.f;
+        const float v3 = (vb && ua) ? __ldg(rb + xac) : 0.f, v4 = (vb && ub) ? __ldg(rb + xbc) : 0.f;
+        const float lh = lr[i], lw = lc[j], hh = 1.f - lh, hw = 1.f - lw;
+        const float val = hh * hw * v1 + hh * lw * v2 + lh * hw * v3 + lh * lw * v4;
+        acc = fmaf(__ldg(wk + i * 3 + j), val, acc);
+      }
+    }
+    ob[(size_t)c * p.Ho * p.Wo] = acc;
+  }
+}
+
+extern "C" int cdn_deform_dw_f32(const float* input, const float* w_scale, float b_scale, int offset_bound, const float* w_dw,
+                                 float* output, int B, int C, int H, int W, int stride, cdn_stream_t stream) {
+  CDN_CHECK(input && w_scale && w_dw && output, CDN_ERR_INVALID, "deform_dw_f32: null tensor");
+  CDN_CHECK(B >= 0 && C >= 1 && H >= 1 && W >= 1 && (stride == 1 || stride == 2) && offset_bound >= 1, CDN_ERR_INVALID,
+            "deform_dw_f32: bad shape / stride / bound");
+  DefDwF32Params p;
+  p.in = input; p.ws = w_scale; p.wdw = w_dw; p.out = output; p.bs = b_scale;
+  p.lo = (float)(-offset_bound + 1); p.hi = (float)offset_bound;
+  p.B = B; p.C = C; p.H = H; p.W = W; p.stride = stride;
+  p.Ho = (H + 2 - 3) / stride + 1; p.Wo = (W + 2 - 3) / stride + 1;
+  p.total = (long long)B * p.Ho * p.Wo;
+  if (p.total == 0) return 0;
+  deform_dw_f32_kernel<<<(unsigned)((p.total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(p);
+  CDN_LAUNCH_CHECK("deform_dw_f32_kernel");
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// fp32 1x1 convolution, NCHW: out[b][co][p] = sum_c W[co][c] * in[b][c][p] (+ bias[co]).  Used by the fp32 module for its
+// conv_channel (modules/dcn_deform_conv.py:311-317).  One thread = one pixel x PWF_CO output channels; the weight rows
+// are broadcast from shared memory; pixels run along lanes (coalesced planes).  fp32 FMA accumulation (the 1e-4 contract
+// of the float path rules TF32 out).
+// ---------------------------------------------------------------------------------------------------------
+#define PWF_CO 8
+__global__ void __launch_bounds__(128) pw_f32_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
+                                                     float* __restrict__ out, int C, int Co, int ppi, long long total_px) {
+  extern __shared__ float sw[];                 // [PWF_CO][C]
+  const int co0 = blockIdx.y * PWF_CO;
+  for (int i = threadIdx.x; i < PWF_CO * C; i += blockDim.x) {
+    const int r = i / C, c = i - r * C;
+    sw[i] = (co0 + r < Co) ? w[(size_t)(co0 + r) * C + c] : 0.f;
+  }
+  __syncthreads();
+  const long long px = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (px >= total_px) return;
+  const long long b = px / ppi; const int pi = (int)(px - b * ppi);
+  const float* x = in + (size_t)b * C * ppi + pi;
+  float acc[PWF_CO];
+#pragma unroll
+  for (int r = 0; r < PWF_CO; ++r) acc[r] = (bias && co0 + r < Co) ? bias[co0 + r] : 0.f;
+  for (int c = 0; c < C; ++c) {
+    const float v = __ldg(x + (size_t)c * ppi);
+#pragma unroll
+    for (int r = 0; r < PWF_CO; ++r) acc[r] = fmaf(sw[r * C + c], v, acc[r]);
+  }
+#pragma unroll
+  for (int r = 0; r < PWF_CO; ++r)
+    if (co0 + r < Co) out[((size_t)b * Co + co0 + r) * ppi + pi] = acc[r];
+}
+
+extern "C" int cdn_pw_f32(const float* input, const float* weight, const float* bias, float* output, int B, int C, int Co,
+                          int pixels_per_image, cdn_stream_t stream) {
+  CDN_CHECK(input && weight && output && B >= 0 && C >= 1 && Co >= 1 && pixels_per_image >= 1, CDN_ERR_INVALID, "pw_f32: bad arguments");
+  CDN_CHECK((size_t)PWF_CO * C * sizeof(float) <= 160 * 1024, CDN_ERR_INVALID, "pw_f32: C=%d too large for the shared weight tile", C);
+  const long long total = (long long)B * pixels_per_image;
+  if (total == 0) return 0;
+  const size_t smem = (size_t)PWF_CO * C * sizeof(float);
+  static bool attr = false;
+  if (!attr) { CDN_CUDA(cudaFuncSetAttribute(pw_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr = true; }
+  dim3 grid((unsigned)((total + 127) / 128), (unsigned)((Co + PWF_CO - 1) / PWF_CO));
+  pw_f32_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(input, weight, bias, output, C, Co, pixels_per_image, total);
+  CDN_LAUNCH_CHECK("pw_f32_kernel");
+  return 0;
+}

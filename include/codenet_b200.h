@@ -164,6 +164,17 @@ int cdn_deform_conv_forward_f32(const float* input, const float* weight, const f
                                 int padW, int padH, int dilW, int dilH, int group, int deformable_group,
                                 int im2col_step, cdn_stream_t stream);
 
+/* ---- fused co-designed deformable module, fp32 (the float model's layer) -------------------------------------
+ * DeformConvWithOffsetScaleBoundPositive.forward (lib/models/external/modules/dcn_deform_conv.py:323-330) without its
+ * optional conv_channel: s = Hardtanh[-bound+1, bound](w_scale . x + b_scale) per output pixel (1x1 conv C -> 1 with
+ * stride `stride`), offsets anchor*(s-1), depthwise 3x3 deformable conv (pad 1, bilinear) -- one kernel, no offset
+ * tensor.  input [B][C][H][W], w_scale [C], w_dw [C][3][3], output [B][C][Ho][Wo] (contiguous NCHW device pointers). */
+int cdn_deform_dw_f32(const float* input, const float* w_scale, float b_scale, int offset_bound, const float* w_dw,
+                      float* output, int B, int C, int H, int W, int stride, cdn_stream_t stream);
+/* fp32 1x1 convolution NCHW (the module's conv_channel): output [B][Co][P] = weight [Co][C] x input [B][C][P] (+ bias). */
+int cdn_pw_f32(const float* input, const float* weight, const float* bias, float* output, int B, int C, int Co,
+               int pixels_per_image, cdn_stream_t stream);
+
 /* ---- whole-network engine -------------------------------------------------------------------------------
  * A plan is a list of tensors (activation buffers) and ops appended in execution order, then finalised for a
  * maximum batch.  All descriptor arrays are copied at add time. */
