@@ -1,0 +1,207 @@
+// fp32 NCHW building blocks of the float CoDeNet model (BASELINE config 5 / SURVEY.md 8(a) a1, a10-a12): BN is folded on
+// the host, so every layer is conv + bias (+ ReLU).  These are plain SIMT kernels (coalesced along W, fp32 FMA
+// accumulation -- the 1e-4 contract of the float path rules TF32 out); the W4A8 path is the optimised one.
+#include "common.cuh"
+
+// ---- dense 3x3 conv for the stem (Ci = 3): one thread per output pixel computes every output channel --------------
+#define C3_MAXCO 32
+__global__ void __launch_bounds__(128) conv3x3_f32_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
+                                                          float* __restrict__ out, int Ci, int Co, int H, int W, int Ho, int Wo, int stride,
+                                                          int relu, long long total) {
+  extern __shared__ float sw[];                 // [Co][Ci][9] + [Co]
+  for (int i = threadIdx.x; i < Co * Ci * 9; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < Co; i += blockDim.x) sw[Co * Ci * 9 + i] = bias ? bias[i] : 0.f;
+  __syncthreads();
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int wo = (int)(idx % Wo); const long long t = idx / Wo; const int ho = (int)(t % Ho); const long long b = t / Ho;
+  float acc[C3_MAXCO];
+#pragma unroll
+  for (int c = 0; c < C3_MAXCO; ++c) acc[c] = c < Co ? sw[Co * Ci * 9 + c] : 0.f;
+  for (int ci = 0; ci < Ci; ++ci) {
+    const float* plane = in + ((size_t)b * Ci + ci) * H * W;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int y = ho * stride - 1 + i;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int x = wo * stride - 1 + j;
+        const float v = ((unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W) ? __ldg(plane + (size_t)y * W + x) : 0.f;
+#pragma unroll
+        for (int c = 0; c < C3_MAXCO; ++c) if (c < Co) acc[c] = fmaf(sw[(c * Ci + ci) * 9 + i * 3 + j], v, acc[c]);
+      }
+    }
+  }
+  for (int c = 0; c < Co; ++c) {
+    float v = acc[c];
+    if (relu) v = fmaxf(v, 0.f);
+    out[(((size_t)b * Co + c) * Ho + ho) * Wo + wo] = v;
+  }
+}
+
+extern "C" int cdn_conv3x3_f32(const float* input, const float* weight, const float* bias, float* output, int B, int Ci, int Co,
+                               int H, int W, int stride, int relu, cdn_stream_t stream) {
+  CDN_CHECK(input && weight && output && Ci >= 1 && Co >= 1 && Co <= C3_MAXCO && stride >= 1, CDN_ERR_INVALID,
+            "conv3x3_f32: bad arguments (Co <= %d)", C3_MAXCO);
+  const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
+  const long long total = (long long)B * Ho * Wo;
+  if (total == 0) return 0;
+  const size_t smem = ((size_t)Co * Ci * 9 + Co) * sizeof(float);
+  conv3x3_f32_kernel<<<(unsigned)((total + 127) / 128), 128, smem, (cudaStream_t)stream>>>(input, weight, bias, output, Ci, Co, H, W, Ho, Wo,
+                                                                                         stride, relu, total);
+  CDN_LAUNCH_CHECK("conv3x3_f32_kernel");
+  return 0;
+}
+
+// ---- depthwise 3x3, pad 1, stride 1/2 -----------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dw3x3_f32_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
+                                                        float* __restrict__ out, int C, int H, int W, int Ho, int Wo, int stride, int relu,
+                                                        long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int wo = (int)(idx % Wo); long long t = idx / Wo; const int ho = (int)(t % Ho); t /= Ho; const int c = (int)(t % C);
+  const float* plane = in + (size_t)t * H * W;                      // t = b*C + c
+  const float* wk = w + c * 9;
+  float acc = bias ? __ldg(bias + c) : 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int y = ho * stride - 1 + i;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int x = wo * stride - 1 + j;
+      if ((unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W) acc = fmaf(__ldg(wk + i * 3 + j), __ldg(plane + (size_t)y * W + x), acc);
+    }
+  }
+  out[idx] = relu ? fmaxf(acc, 0.f) : acc;
+}
+
+extern "C" int cdn_dw3x3_f32(const float* input, const float* weight, const float* bias, float* output, int B, int C, int H, int W,
+                             int stride, int relu, cdn_stream_t stream) {
+  CDN_CHECK(input && weight && output && C >= 1 && (stride == 1 || stride == 2), CDN_ERR_INVALID, "dw3x3_f32: bad arguments");
+  const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
+  const long long total = (long long)B * C * Ho * Wo;
+  if (total == 0) return 0;
+  dw3x3_f32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(input, weight, bias, output, C, H, W, Ho, Wo, stride, relu, total);
+  CDN_LAUNCH_CHECK("dw3x3_f32_kernel");
+  return 0;
+}
+
+// ---- 1x1 conv on channel slices with a strided output channel map (split / cat / channel_shuffle folded) --------------
+//   out[b][out_coff + co*out_cstride][p] = act(bias[co] + sum_c W[co][c] * in[b][in_coff + c][p])
+#define PWS_CO 8
+__global__ void __launch_bounds__(128) pw_slice_f32_kernel(const float* __restrict__ in, int in_ctotal, int in_coff, int C,
+                                                           const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out,
+                                                           int out_ctotal, int out_coff, int out_cstride, int Co, int relu, int ppi,
+                                                           long long total_px) {
+  extern __shared__ float sw[];                 // [PWS_CO][C]
+  const int co0 = blockIdx.y * PWS_CO;
+  for (int i = threadIdx.x; i < PWS_CO * C; i += blockDim.x) {
+    const int r = i / C, c = i - r * C;
+    sw[i] = (co0 + r < Co) ? w[(size_t)(co0 + r) * C + c] : 0.f;
+  }
+  __syncthreads();
+  const long long px = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (px >= total_px) return;
+  const long long b = px / ppi; const int pi = (int)(px - b * ppi);
+  const float* x = in + ((size_t)b * in_ctotal + in_coff) * ppi + pi;
+  // two-level accumulation: fp32 FMA over blocks of 32 input channels, block sums added in fp64 -- a plain fp32 chain
+  // over K = 1024 loses ~1e-5 relative per layer, which the 1e-4 end-to-end contract of the float path cannot afford
+  double tot[PWS_CO];
+#pragma unroll
+  for (int r = 0; r < PWS_CO; ++r) tot[r] = (bias && co0 + r < Co) ? (double)bias[co0 + r] : 0.0;
+  for (int c0 = 0; c0 < C; c0 += 32) {
+    float acc[PWS_CO];
+#pragma unroll
+    for (int r = 0; r < PWS_CO; ++r) acc[r] = 0.f;
+    const int c1 = min(c0 + 32, C);
+    for (int c = c0; c < c1; ++c) {
+      const float v = __ldg(x + (size_t)c * ppi);
+#pragma unroll
+      for (int r = 0; r < PWS_CO; ++r) acc[r] = fmaf(sw[r * C + c], v, acc[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < PWS_CO; ++r) tot[r] += (double)acc[r];
+  }
+#pragma unroll
+  for (int r = 0; r < PWS_CO; ++r)
+    if (co0 + r < Co) {
+      const float a = (float)tot[r];
+      const float v = relu ? fmaxf(a, 0.f) : a;
+      out[((size_t)b * out_ctotal + out_coff + (size_t)(co0 + r) * out_cstride) * ppi + pi] = v;
+    }
+}
+
+extern "C" int cdn_pw_slice_f32(const float* input, int in_ctotal, int in_coff, int C, const float* weight, const float* bias,
+                                float* output, int out_ctotal, int out_coff, int out_cstride, int Co, int relu, int B,
+                                int pixels_per_image, cdn_stream_t stream) {
+  CDN_CHECK(input && weight && output && C >= 1 && Co >= 1 && in_coff >= 0 && in_coff + C <= in_ctotal && out_cstride >= 1 &&
+            out_coff >= 0 && out_coff + (Co - 1) * out_cstride < out_ctotal, CDN_ERR_INVALID, "pw_slice_f32: channel slice out of range");
+  CDN_CHECK((size_t)PWS_CO * C * sizeof(float) <= 160 * 1024, CDN_ERR_INVALID, "pw_slice_f32: C=%d too large", C);
+  const long long total = (long long)B * pixels_per_image;
+  if (total == 0) return 0;
+  static bool attr = false;
+  if (!attr) { CDN_CUDA(cudaFuncSetAttribute(pw_slice_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr = true; }
+  dim3 grid((unsigned)((total + 127) / 128), (unsigned)((Co + PWS_CO - 1) / PWS_CO));
+  pw_slice_f32_kernel<<<grid, 128, (size_t)PWS_CO * C * sizeof(float), (cudaStream_t)stream>>>(
+      input, in_ctotal, in_coff, C, weight, bias, output, out_ctotal, out_coff, out_cstride, Co, relu, pixels_per_image, total);
+  CDN_LAUNCH_CHECK("pw_slice_f32_kernel");
+  return 0;
+}
+
+// ---- channel copy with the same output map (the pass-through half of a unit), max-pool 3/2/1, nearest x2 upsample -------
+__global__ void copy_channels_f32_kernel(const float* __restrict__ in, int in_ctotal, int in_coff, float* __restrict__ out, int out_ctotal,
+                                         int out_coff, int out_cstride, int n, int ppi, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int pi = (int)(idx % ppi); long long t = idx / ppi; const int c = (int)(t % n); const long long b = t / n;
+  out[((size_t)b * out_ctotal + out_coff + (size_t)c * out_cstride) * ppi + pi] = in[((size_t)b * in_ctotal + in_coff + c) * ppi + pi];
+}
+extern "C" int cdn_copy_channels_f32(const float* input, int in_ctotal, int in_coff, float* output, int out_ctotal, int out_coff,
+                                     int out_cstride, int n, int B, int pixels_per_image, cdn_stream_t stream) {
+  CDN_CHECK(input && output && n >= 1 && in_coff >= 0 && in_coff + n <= in_ctotal && out_coff >= 0 &&
+            out_coff + (n - 1) * out_cstride < out_ctotal, CDN_ERR_INVALID, "copy_channels_f32: slice out of range");
+  const long long total = (long long)B * n * pixels_per_image;
+  if (total == 0) return 0;
+  copy_channels_f32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(input, in_ctotal, in_coff, output, out_ctotal,
+                                                                                             out_coff, out_cstride, n, pixels_per_image, total);
+  CDN_LAUNCH_CHECK("copy_channels_f32_kernel");
+  return 0;
+}
+
+__global__ void maxpool3s2_f32_kernel(const float* __restrict__ in, float* __restrict__ out, int H, int W, int Ho, int Wo, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int wo = (int)(idx % Wo); long long t = idx / Wo; const int ho = (int)(t % Ho); t /= Ho;
+  const float* plane = in + (size_t)t * H * W;
+  float m = -3.402823466e38f;
+  for (int i = 0; i < 3; ++i) {
+    const int y = 2 * ho - 1 + i; if ((unsigned)y >= (unsigned)H) continue;
+    for (int j = 0; j < 3; ++j) { const int x = 2 * wo - 1 + j; if ((unsigned)x < (unsigned)W) m = fmaxf(m, plane[(size_t)y * W + x]); }
+  }
+  out[idx] = m;
+}
+extern "C" int cdn_maxpool3s2_f32(const float* input, float* output, int planes, int H, int W, cdn_stream_t stream) {
+  CDN_CHECK(input && output && planes >= 0 && H >= 1 && W >= 1, CDN_ERR_INVALID, "maxpool3s2_f32: bad arguments");
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const long long total = (long long)planes * Ho * Wo;
+  if (total == 0) return 0;
+  maxpool3s2_f32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(input, output, H, W, Ho, Wo, total);
+  CDN_LAUNCH_CHECK("maxpool3s2_f32_kernel");
+  return 0;
+}
+
+__global__ void upsample2x_f32_kernel(const float* __restrict__ in, float* __restrict__ out, int H, int W, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int W2 = 2 * W, H2 = 2 * H;
+  const int x = (int)(idx % W2); long long t = idx / W2; const int y = (int)(t % H2); t /= H2;
+  out[idx] = in[((size_t)t * H + (y >> 1)) * W + (x >> 1)];
+}
+extern "C" int cdn_upsample2x_f32(const float* input, float* output, int planes, int H, int W, cdn_stream_t stream) {
+  CDN_CHECK(input && output && planes >= 0 && H >= 1 && W >= 1, CDN_ERR_INVALID, "upsample2x_f32: bad arguments");
+  const long long total = (long long)planes * 4 * H * W;
+  if (total == 0) return 0;
+  upsample2x_f32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(input, output, H, W, total);
+  CDN_LAUNCH_CHECK("upsample2x_f32_kernel");
+  return 0;
+}

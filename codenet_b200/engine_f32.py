@@ -1,0 +1,154 @@
+"""Float (fp32) CoDeNet forward + decode on libcodenet_b200 -- BASELINE config 5 / SURVEY.md 8(a) a1, a10-a12.
+
+Executes the UNQUANTISED network (`PoseShuffleNetV2.forward`, lib/models/networks/shufflenetv2_dcn.py:314-330) with
+BatchNorm folded on the host (fp64, then rounded to fp32) and every layer as one of the fp32 NCHW kernels of
+csrc/f32_net.cu / deform_f32.cu: conv + bias (+ ReLU), split / cat / channel_shuffle folded into channel-slice indexing,
+the co-designed deformable module as ONE fused kernel (bilinear offsets, the reference's behaviour).  Results agree with
+the reference evaluated in fp64 within 1e-4 relative (tests/test_gpu_f32.py).  This path is functional, not tuned:
+launches are eager and the 1x1 convolutions are SIMT fp32 (TF32 tensor cores cannot hold the 1e-4 contract without a
+3-way split); the optimised path of this repository is the W4A8 engine.
+
+Input: a state dict in the reference's RAW (pre-quantisation) key space, e.g. `model.state_dict()` of the float model
+or a `model_last.pth` of a float training run.  There is no CPU path.
+"""
+import ctypes as C
+from typing import Dict
+
+import numpy as np
+
+from . import _lib
+from .arch import NetConfig, build_graph
+
+F = np.float64
+
+
+def _fold(st, c, eps=1e-5):
+    """conv (+ BatchNorm) -> (weight fp32, bias fp32): W' = W*gamma/sqrt(var+eps), b' = (b - mean)*gamma/sqrt(var+eps) + beta."""
+    w = np.asarray(st[c.raw_conv + ".weight"], F)
+    b = np.asarray(st[c.raw_conv + ".bias"], F) if c.has_bias else np.zeros(c.cout, F)
+    if c.raw_bn:
+        g, beta, mean, var = (np.asarray(st[c.raw_bn + "." + k], F) for k in ("weight", "bias", "running_mean", "running_var"))
+        sf = g / np.sqrt(var + F(eps))
+        w = w * sf.reshape(-1, 1, 1, 1)
+        b = (b - mean) * sf + beta
+    return w.astype(np.float32), b.astype(np.float32)
+
+
+class EngineF32:
+    def __init__(self, cfg: NetConfig, state: Dict[str, np.ndarray], device: int = 0, K: int = 100):
+        import torch
+        self.torch = torch
+        self.cfg, self.K = cfg, int(K)
+        self.lib = _lib.load()
+        _lib.check(self.lib.cdn_check_device(device))
+        self.dev = torch.device("cuda", device)
+        self.g = build_graph(cfg)
+        st = {k: (v.detach().cpu().numpy() if hasattr(v, "detach") else np.asarray(v)) for k, v in state.items()}
+        self.P = {}
+        for c in self.g.all_convs():
+            w, b = _fold(st, c)
+            self.P[c.name] = (torch.from_numpy(np.ascontiguousarray(w.reshape(c.cout, -1))).to(self.dev),
+                              torch.from_numpy(np.ascontiguousarray(b)).to(self.dev))
+
+    # -- thin kernel wrappers ---------------------------------------------------------------------------------------------
+    def _st(self):
+        return C.c_void_p(self.torch.cuda.current_stream(self.dev).cuda_stream)
+
+    @staticmethod
+    def _p(t):
+        return C.c_void_p(t.data_ptr()) if t is not None else None
+
+    def _pw(self, x, in_off, cin, name, out, out_off, out_stride, relu):
+        w, b = self.P[name]
+        B, ct, H, W = x.shape
+        _lib.check(self.lib.cdn_pw_slice_f32(self._p(x), ct, in_off, cin, self._p(w), self._p(b), self._p(out), out.shape[1], out_off,
+                                             out_stride, w.shape[0], 1 if relu else 0, B, H * W, self._st()))
+
+    def _dw(self, x, name, stride, relu):
+        w, b = self.P[name]
+        B, Cc, H, W = x.shape
+        out = x.new_empty((B, Cc, (H - 1) // stride + 1, (W - 1) // stride + 1))
+        _lib.check(self.lib.cdn_dw3x3_f32(self._p(x), self._p(w), self._p(b), self._p(out), B, Cc, H, W, stride, 1 if relu else 0, self._st()))
+        return out
+
+    def _new(self, x, c, H=None, W=None):
+        return x.new_empty((x.shape[0], c, H if H else x.shape[2], W if W else x.shape[3]))
+
+    # -- the network --------------------------------------------------------------------------------------------------------
+    def forward(self, x):
+        """x: CUDA fp32 [B,3,H,W] -> {'hm' (logits), 'wh', 'reg'} fp32 [B,*,H/4,W/4] (views of one heads tensor)."""
+        torch, L, g, cfg = self.torch, self.lib, self.g, self.cfg
+        assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 4
+        x = x.contiguous()
+        B = x.shape[0]
+        with torch.cuda.device(self.dev):
+            w, b = self.P["layer0"]
+            s = g.stem.stride
+            y = x.new_empty((B, g.stem.cout, (x.shape[2] - 1) // s + 1, (x.shape[3] - 1) // s + 1))
+            _lib.check(L.cdn_conv3x3_f32(self._p(x), self._p(w), self._p(b), self._p(y), B, 3, g.stem.cout, x.shape[2], x.shape[3], s, 1, self._st()))
+            if cfg.maxpool:
+                z = x.new_empty((B, y.shape[1], (y.shape[2] - 1) // 2 + 1, (y.shape[3] - 1) // 2 + 1))
+                _lib.check(L.cdn_maxpool3s2_f32(self._p(y), self._p(z), B * y.shape[1], y.shape[2], y.shape[3], self._st()))
+                y = z
+            x = y
+            for u in g.units:                                      # BaseNode.forward, shufflenetv2_dcn.py:102-114
+                r = "layer%d.%d." % (u["stage"], u["unit"])
+                half = u["oup"] // 2
+                if u["stride"] == 2:
+                    d4 = self._dw(x, r + "dw4", 2, False)
+                    out = self._new(d4, u["oup"])
+                    self._pw(d4, 0, u["inp"], r + "pw5", out, 0, 2, True)              # x1 -> even channels
+                    c1 = self._new(x, half)
+                    self._pw(x, 0, u["inp"], r + "pw1", c1, 0, 1, True)
+                    d2 = self._dw(c1, r + "dw2", 2, False)
+                    self._pw(d2, 0, half, r + "pw3", out, 1, 2, True)                  # x2 -> odd channels
+                else:
+                    out = self._new(x, u["oup"])
+                    _lib.check(L.cdn_copy_channels_f32(self._p(x), u["oup"], 0, self._p(out), u["oup"], 0, 2, half, B,
+                                                       x.shape[2] * x.shape[3], self._st()))
+                    c1 = self._new(x, half)
+                    self._pw(x, half, half, r + "pw1", c1, 0, 1, True)
+                    d2 = self._dw(c1, r + "dw2", 1, False)
+                    self._pw(d2, 0, half, r + "pw3", out, 1, 2, True)
+                x = out
+            y = self._new(x, g.layer4.cout)
+            self._pw(x, 0, g.layer4.cin, "layer4", y, 0, 1, True)
+            x = y
+            for up in g.ups:                                       # deform module + BN + ReLU + nearest x2
+                i = up["idx"]
+                ws, bs = self.P["up%d.scale" % i]
+                wd, _ = self.P["up%d.deform" % i]
+                Bc, Cc, H, W = x.shape
+                y = x.new_empty(x.shape)
+                _lib.check(L.cdn_deform_dw_f32(self._p(x), self._p(ws), C.c_float(float(bs[0])), cfg.offset_bound, self._p(wd), self._p(y),
+                                               Bc, Cc, H, W, 1, self._st()))
+                z = self._new(y, up["cout"])
+                self._pw(y, 0, Cc, "up%d.channel" % i, z, 0, 1, True)
+                x = z.new_empty((Bc, up["cout"], 2 * H, 2 * W))
+                _lib.check(L.cdn_upsample2x_f32(self._p(z), self._p(x), Bc * up["cout"], H, W, self._st()))
+            n_out = sum(h["classes"] for h in g.heads)
+            heads = self._new(x, n_out)
+            off = 0
+            views = {}
+            for h in g.heads:                                      # depthwise-separable heads, :244-271
+                a = self._new(x, 64)
+                self._pw(x, 0, 64, h["name"] + ".pw1", a, 0, 1, True)
+                d = self._dw(a, h["name"] + ".dw2", 1, True)
+                self._pw(d, 0, 64, h["name"] + ".out", heads, off, 1, False)
+                views[h["name"]] = heads[:, off:off + h["classes"]]
+                off += h["classes"]
+        self._heads = heads
+        return views
+
+    def detect(self, x):
+        """forward + ctdet decode (lib/detectors/ctdet.py:31-41 without flip): dets [B,K,6], heads views."""
+        torch = self.torch
+        v = self.forward(x)
+        hm, wh = v["hm"].contiguous(), v["wh"].contiguous()
+        reg = v["reg"].contiguous() if "reg" in v else None
+        B, cat, H, W = hm.shape
+        dets = torch.empty((B, self.K, 6), dtype=torch.float32, device=self.dev)
+        inds = torch.empty((B, self.K), dtype=torch.int32, device=self.dev)
+        with torch.cuda.device(self.dev):
+            _lib.check(self.lib.cdn_ctdet_decode(self._p(hm), self._p(wh), self._p(reg), B, cat, H, W, self.K, self._p(dets), self._p(inds), self._st()))
+        return dets, inds, v

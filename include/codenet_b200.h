@@ -175,6 +175,23 @@ int cdn_deform_dw_f32(const float* input, const float* w_scale, float b_scale, i
 int cdn_pw_f32(const float* input, const float* weight, const float* bias, float* output, int B, int C, int Co,
                int pixels_per_image, cdn_stream_t stream);
 
+/* ---- fp32 NCHW building blocks of the float model (BN folded on the host: conv + bias [+ ReLU]) -------------------
+ * Contiguous NCHW device pointers.  cdn_pw_slice_f32 reads input channels [in_coff, in_coff + C) of a tensor with
+ * in_ctotal channels and writes output channel out_coff + co*out_cstride of a tensor with out_ctotal channels, which folds
+ * split / cat / channel_shuffle (lib/models/networks/shufflenetv2_dcn.py:29-34,102-114) into the indexing;
+ * cdn_copy_channels_f32 moves the pass-through half with the same map. */
+int cdn_conv3x3_f32(const float* input, const float* weight, const float* bias, float* output, int B, int Ci, int Co,
+                    int H, int W, int stride, int relu, cdn_stream_t stream);
+int cdn_dw3x3_f32(const float* input, const float* weight, const float* bias, float* output, int B, int C, int H, int W,
+                  int stride, int relu, cdn_stream_t stream);
+int cdn_pw_slice_f32(const float* input, int in_ctotal, int in_coff, int C, const float* weight, const float* bias,
+                     float* output, int out_ctotal, int out_coff, int out_cstride, int Co, int relu, int B,
+                     int pixels_per_image, cdn_stream_t stream);
+int cdn_copy_channels_f32(const float* input, int in_ctotal, int in_coff, float* output, int out_ctotal, int out_coff,
+                          int out_cstride, int n, int B, int pixels_per_image, cdn_stream_t stream);
+int cdn_maxpool3s2_f32(const float* input, float* output, int planes, int H, int W, cdn_stream_t stream);
+int cdn_upsample2x_f32(const float* input, float* output, int planes, int H, int W, cdn_stream_t stream);
+
 /* ---- whole-network engine -------------------------------------------------------------------------------
  * A plan is a list of tensors (activation buffers) and ops appended in execution order, then finalised for a
  * maximum batch.  All descriptor arrays are copied at add time. */

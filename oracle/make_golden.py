@@ -15,6 +15,7 @@ Vectors produced (all from the reference's own code through oracle/ref_harness.p
                     intermediates
   codenet1x_512_round.npz   one 512^2 image (config c geometry): detections + strided output samples
   codenet_w2mp_{calib,256_round}.npz   the same for the w2 + S2/MaxPool configuration (config e geometry), one 256^2 image
+  codenet_float_{1x,2x_coco}_256.npz   the float (unquantised) model evaluated by the reference in fp64: heads + detections
   post_kat.npz      ctdet_post_process (lib/utils/post_process.py:86-103) on random detections
   ref_state_keys.json   state-dict key spaces of the reference network before / after quantisation (1x, w2, maxpool)
 """
@@ -358,6 +359,44 @@ def codenet_w2mp():
     print("codenet_w2mp ok; unique scores:", len(np.unique(cap["dets"][0, :, 4])))
 
 
+def codenet_float():
+    """The FLOAT model (no quantisation) evaluated by the reference in fp64: head outputs + detections for
+    CoDeNet1x / VOC and CoDeNet2x / COCO (config 5 geometry: w2, stride 4, 80 classes, bilinear offsets) at 256^2.
+    The BatchNorm statistics of the calibration pass travel in the same file."""
+    R = H.load_reference()
+    for tag, cfg in (("1x", NetConfig(num_classes=20)), ("2x_coco", NetConfig(num_classes=80, w2=True))):
+        raw = make_raw_state(cfg, 0)
+        digest = state_digest(raw)
+        bn = _calibrate_bn(cfg, raw)
+        raw.update(bn)
+        m = H.build_reference_model({k: T(v) for k, v in raw.items()}, dict(cfg.head_list()), cfg.w2, cfg.maxpool,
+                                    dtype=torch.float64)
+        m.eval()
+        x = make_images(2, 256, seed=2)[:1]
+        with torch.no_grad():
+            o = m(T(x).double())[-1]
+            hm_logit = o["hm"].clone()
+            dets = R.decode.ctdet_decode(o["hm"].sigmoid_(), o["wh"], reg=o["reg"], K=100)
+        out = {"digest": np.array(digest), "hm_logit": hm_logit.numpy().astype(np.float32), "wh": o["wh"].numpy().astype(np.float32),
+               "reg": o["reg"].numpy().astype(np.float32), "dets": dets.numpy().astype(np.float32)}
+        # how far the reference's OWN fp32 evaluation is from its fp64 evaluation on this (ill-conditioned, random) network:
+        # the yardstick for any fp32 implementation
+        m32 = H.build_reference_model({k: T(v) for k, v in raw.items()}, dict(cfg.head_list()), cfg.w2, cfg.maxpool,
+                                      dtype=torch.float32)
+        m32.eval()
+        with torch.no_grad():
+            o32 = m32(T(x))[-1]
+        ref64 = {"hm": hm_logit, "wh": o["wh"], "reg": o["reg"]}
+        for k in ("hm", "wh", "reg"):
+            e = (o32[k].double() - ref64[k]).abs()
+            out["ref_fp32_maxerr/" + k] = np.array(float(e.max()))
+            out["ref_fp32_l2rel/" + k] = np.array(float(e.pow(2).sum().sqrt() / ref64[k].pow(2).sum().sqrt()))
+        for k, v in bn.items():
+            out["bn/" + k] = v
+        np.savez_compressed(os.path.join(OUT, "codenet_float_%s_256.npz" % tag), **out)
+        print("codenet_float", tag, "ok; |hm| max", float(np.abs(out["hm_logit"]).max()))
+
+
 def post_kat():
     """ctdet_post_process (lib/utils/post_process.py:86-103) on random detections: the host / device restatements
     of the box transform are pinned against it."""
@@ -399,9 +438,11 @@ if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["quant", "deform", "decode", "codenet1x", "keys", "post", "w2mp"]
+    which = sys.argv[1:] or ["quant", "deform", "decode", "codenet1x", "keys", "post", "w2mp", "float"]
     if "keys" in which:
         ref_keys()
+    if "float" in which:
+        codenet_float()
     if "post" in which:
         post_kat()
     if "w2mp" in which:
