@@ -89,45 +89,61 @@ extern "C" int cdn_dw3x3_f32(const float* input, const float* weight, const floa
 // ---- 1x1 conv on channel slices with a strided output channel map (split / cat / channel_shuffle folded) --------------
 //   out[b][out_coff + co*out_cstride][p] = act(bias[co] + sum_c W[co][c] * in[b][in_coff + c][p])
 #define PWS_CO 8
+#define PWS_PX 4
+// One thread = PWS_PX consecutive pixels x PWS_CO output channels (register tile 4 x 8): every weight fetched from shared
+// memory feeds 4 FMAs and every activation 8, so the loop is FMA-bound instead of LDS-bound.
 __global__ void __launch_bounds__(128) pw_slice_f32_kernel(const float* __restrict__ in, int in_ctotal, int in_coff, int C,
                                                            const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out,
                                                            int out_ctotal, int out_coff, int out_cstride, int Co, int relu, int ppi,
-                                                           long long total_px) {
-  extern __shared__ float sw[];                 // [PWS_CO][C]
+                                                           long long total_groups) {
+  extern __shared__ float sw[];                 // [C][PWS_CO] (channel-major: one LDS.128 x2 per input channel)
   const int co0 = blockIdx.y * PWS_CO;
   for (int i = threadIdx.x; i < PWS_CO * C; i += blockDim.x) {
-    const int r = i / C, c = i - r * C;
+    const int c = i / PWS_CO, r = i - c * PWS_CO;
     sw[i] = (co0 + r < Co) ? w[(size_t)(co0 + r) * C + c] : 0.f;
   }
   __syncthreads();
-  const long long px = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (px >= total_px) return;
-  const long long b = px / ppi; const int pi = (int)(px - b * ppi);
+  const long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // group of PWS_PX pixels inside one image
+  if (gi >= total_groups) return;
+  const int gpi = ppi / PWS_PX;                 // host guarantees ppi % PWS_PX == 0
+  const long long b = gi / gpi; const int pi = (int)(gi - b * gpi) * PWS_PX;
   const float* x = in + ((size_t)b * in_ctotal + in_coff) * ppi + pi;
   // two-level accumulation: fp32 FMA over blocks of 32 input channels, block sums added in fp64 -- a plain fp32 chain
-  // over K = 1024 loses ~1e-5 relative per layer, which the 1e-4 end-to-end contract of the float path cannot afford
-  double tot[PWS_CO];
+  // over K = 1024 loses ~1e-5 relative per layer, which the float path's accuracy contract cannot afford
+  double tot[PWS_PX][PWS_CO];
 #pragma unroll
-  for (int r = 0; r < PWS_CO; ++r) tot[r] = (bias && co0 + r < Co) ? (double)bias[co0 + r] : 0.0;
+  for (int q = 0; q < PWS_PX; ++q)
+#pragma unroll
+    for (int r = 0; r < PWS_CO; ++r) tot[q][r] = (bias && co0 + r < Co) ? (double)bias[co0 + r] : 0.0;
   for (int c0 = 0; c0 < C; c0 += 32) {
-    float acc[PWS_CO];
+    float acc[PWS_PX][PWS_CO];
 #pragma unroll
-    for (int r = 0; r < PWS_CO; ++r) acc[r] = 0.f;
+    for (int q = 0; q < PWS_PX; ++q)
+#pragma unroll
+      for (int r = 0; r < PWS_CO; ++r) acc[q][r] = 0.f;
     const int c1 = min(c0 + 32, C);
     for (int c = c0; c < c1; ++c) {
-      const float v = __ldg(x + (size_t)c * ppi);
+      const float4 v = __ldg((const float4*)(x + (size_t)c * ppi));
+      const float4 wa = *(const float4*)(sw + c * PWS_CO), wb = *(const float4*)(sw + c * PWS_CO + 4);
+      const float vv[4] = {v.x, v.y, v.z, v.w};
+      const float ww[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
-      for (int r = 0; r < PWS_CO; ++r) acc[r] = fmaf(sw[r * C + c], v, acc[r]);
+      for (int q = 0; q < PWS_PX; ++q)
+#pragma unroll
+        for (int r = 0; r < PWS_CO; ++r) acc[q][r] = fmaf(ww[r], vv[q], acc[q][r]);
     }
 #pragma unroll
-    for (int r = 0; r < PWS_CO; ++r) tot[r] += (double)acc[r];
+    for (int q = 0; q < PWS_PX; ++q)
+#pragma unroll
+      for (int r = 0; r < PWS_CO; ++r) tot[q][r] += (double)acc[q][r];
   }
 #pragma unroll
   for (int r = 0; r < PWS_CO; ++r)
     if (co0 + r < Co) {
-      const float a = (float)tot[r];
-      const float v = relu ? fmaxf(a, 0.f) : a;
-      out[((size_t)b * out_ctotal + out_coff + (size_t)(co0 + r) * out_cstride) * ppi + pi] = v;
+      float4 o;
+      o.x = (float)tot[0][r]; o.y = (float)tot[1][r]; o.z = (float)tot[2][r]; o.w = (float)tot[3][r];
+      if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+      *(float4*)(out + ((size_t)b * out_ctotal + out_coff + (size_t)(co0 + r) * out_cstride) * ppi + pi) = o;
     }
 }
 
@@ -137,7 +153,9 @@ extern "C" int cdn_pw_slice_f32(const float* input, int in_ctotal, int in_coff, 
   CDN_CHECK(input && weight && output && C >= 1 && Co >= 1 && in_coff >= 0 && in_coff + C <= in_ctotal && out_cstride >= 1 &&
             out_coff >= 0 && out_coff + (Co - 1) * out_cstride < out_ctotal, CDN_ERR_INVALID, "pw_slice_f32: channel slice out of range");
   CDN_CHECK((size_t)PWS_CO * C * sizeof(float) <= 160 * 1024, CDN_ERR_INVALID, "pw_slice_f32: C=%d too large", C);
-  const long long total = (long long)B * pixels_per_image;
+  CDN_CHECK(pixels_per_image % PWS_PX == 0 && (((uintptr_t)input | (uintptr_t)output) & 15) == 0, CDN_ERR_INVALID,
+            "pw_slice_f32: pixels per image must be a multiple of %d and the tensors 16-byte aligned", PWS_PX);
+  const long long total = (long long)B * (pixels_per_image / PWS_PX);
   if (total == 0) return 0;
   static bool attr = false;
   if (!attr) { CDN_CUDA(cudaFuncSetAttribute(pw_slice_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr = true; }
