@@ -41,6 +41,8 @@ EXPORTS = {
     "cdn_version": (C.c_int, []),
     "cdn_check_device": (C.c_int, [C.c_int]),
     "cdn_set_debug_flags": (C.c_int, [C.c_uint]),
+    "cdn_rq_int_solve": (C.c_int, [C.c_double, C.c_double, C.c_int, C.c_int64, C.c_int64, C.POINTER(C.c_int32),
+                                   C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "cdn_stem_f32_i8": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int8), C.c_int,
                                   C.POINTER(Requant), C.c_void_p, C.c_int, C.c_void_p]),
     "cdn_dw3x3_i8": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int8),

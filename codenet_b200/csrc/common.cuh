@@ -47,6 +47,25 @@ static inline RqFast rq_fast_from(double M, double B) {
 }
 
 #define CDN_MAGIC_I_HOST 0x4B400000
+
+// ---------------------------------------------------------------------------------------------------------
+// Integer requantisation (the path the int8 kernels run):  q = sat8(max(((v*Mi + Bi) >> 32) >> sh, lo))
+//
+// v -> rint(fl64(fl64(v*M) + B)) is a monotone step function of the integer accumulator v, fully described by the 255
+// accumulator values at which the result steps from k-1 to k.  The host finds those step positions with the fp64 formula
+// (the definition of the result) and solves for a 31-bit multiplier Mi and a 64-bit offset Bi whose fixed-point line
+// v*Mi + Bi crosses k * 2^(32+sh) at exactly the same integers, over the whole accumulator range the layer can produce.
+// The 64-bit product is exact, so the device result equals the fp64 formula for EVERY accumulator in that range -- by
+// construction, no guard band and no slow path: IMAD.HI + SHF (+ VIMNMX when lo > -128) + half an I2IP per element
+// instead of the ~7 instructions of the guarded fp32 sequence below.  If no (Mi, Bi) exists for some channel (never
+// observed; needs a multiplier >= 0.5 or step positions closer than 2^-31 relative) the layer keeps the guarded fp32
+// sequence, which is exact by re-evaluation.
+// ---------------------------------------------------------------------------------------------------------
+struct RqInt { int32_t Mi; int32_t sh; long long Bi; };     // 16 bytes: one LDS.128 / LDG.128 per channel
+// v in [vmin, vmax] (inclusive) is the accumulator INCLUDING acc_bias; returns false when no exact pair exists.
+bool rq_int_solve(double M, double B, int lo, long long vmin, long long vmax, RqInt* out);
+// the same constants re-based to a raw accumulator a = v - acc_bias (|a| <= amax); false on 64-bit overflow
+bool rq_int_rebase(RqInt* r, long long acc_bias, long long amax);
 #ifdef __CUDACC__
 // Programmatic dependent launch: every engine kernel lets its successor start early (launch_dependents at entry); a
 // successor launched with the programmatic-serialization attribute runs its prologue (barrier init, TMEM allocation,
@@ -110,6 +129,22 @@ __device__ __forceinline__ uint32_t rq_exact(int v, double M, double B, float lo
   double td = __dadd_rn(__dmul_rn((double)v, M), B);
   td = fmin(fmax(td, (double)lo_f), 127.0);
   return __float_as_uint((float)__double2int_rn(td) + CDN_MAGIC_F);
+}
+
+// ---- integer requantisation (see RqInt above) ---------------------------------------------------------------
+__device__ __forceinline__ int rq_int(int v, int Mi, int sh, long long Bi) {
+  const long long x = (long long)v * Mi + Bi;              // IMAD.HI takes the 64-bit addend
+  return (int)(x >> 32) >> sh;
+}
+__device__ __forceinline__ int rq_int(int v, const int4& r) {
+  return rq_int(v, r.x, r.y, (long long)(((unsigned long long)(uint32_t)r.w << 32) | (uint32_t)r.z));
+}
+// four int32 -> four saturated int8 in one little-endian word (two I2IP.S8.S32.SAT)
+__device__ __forceinline__ uint32_t pack_sat4(int q0, int q1, int q2, int q3) {
+  uint32_t t, w;
+  asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(t) : "r"(q3), "r"(q2), "r"(0));
+  asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(w) : "r"(q1), "r"(q0), "r"(t));
+  return w;
 }
 
 // pack the low bytes of four rq_fast / rq_exact results into one little-endian word

@@ -32,6 +32,7 @@ struct DwParams {
   float* sval;
   const float2* mb; const int* abm; float thr_layer;   // lean requantisation constants (v2 kernels)
   float thr_bil;                             // guard of the fp32 bilinear fast path (0.5 - eps, host-derived bound)
+  const int4* ki; int lo_i;                  // integer requantisation (RqInt per channel, acc_bias folded in)
 };
 
 struct LaneConsts {
@@ -77,9 +78,18 @@ struct DwV2Params {
   const float2* mb; const int* abm;          // per channel (Mh, Bh), acc_bias + MAGIC_I
   const double* M; const double* B;
   float lo_f, thr;
+  const int4* ki; int lo_i;                  // integer requantisation (RqInt per channel, acc_bias folded in)
 };
 
 struct DwLane { float Mh[4], Bh[4]; int abm[4]; };
+// integer requantisation of 4 channels of one pixel (raw accumulators) -> packed word
+template <bool LO>
+__device__ __forceinline__ uint32_t dw_rq_word_int(const int (&acc)[4], const int4 (&r)[4], int lo) {
+  int q[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) { q[c] = rq_int(acc[c], r[c]); if (LO) q[c] = max(q[c], lo); }
+  return pack_sat4(q[0], q[1], q[2], q[3]);
+}
 
 // requantise 4 channels of one pixel: accumulators (already magic-biased) -> packed word (two packed f32x2 pairs)
 __device__ __forceinline__ uint32_t dw_rq_word(const int (&acc)[4], const DwLane& k, float lo_f, RqGuard& g) {
@@ -110,7 +120,7 @@ __device__ __forceinline__ void dw_transpose_row(const uint32_t (&w)[4], uint32_
   transpose4x4(w[0], w[1], w[2], w[3], T[0], T[1], T[2], T[3]);
 }
 
-template <int STRIDE, int SHIFT>
+template <int STRIDE, int SHIFT, bool INT>
 __global__ void __launch_bounds__(128) dw3x3_v2_kernel(const DwV2Params p) {
   pdl_launch_dependents();
   constexpr int NW = DwV2<STRIDE, SHIFT>::NW;
@@ -120,7 +130,7 @@ __global__ void __launch_bounds__(128) dw3x3_v2_kernel(const DwV2Params p) {
   const int pg = (int)(t % (unsigned)p.PG); t /= (unsigned)p.PG;
   const int strip = (int)(t % (unsigned)p.nstrips); const int b = (int)(t / (unsigned)p.nstrips);
   // per-lane constants: 4 channels x NW packed weight words are contiguous (16-byte aligned)
-  uint32_t W[4][NW]; DwLane k;
+  uint32_t W[4][NW]; DwLane k; int4 ki[4];
   {
     const uint4* wv = (const uint4*)(p.wpk + (size_t)cw * 4 * NW);
     uint32_t flat[4 * NW];
@@ -130,11 +140,17 @@ __global__ void __launch_bounds__(128) dw3x3_v2_kernel(const DwV2Params p) {
     for (int c = 0; c < 4; ++c)
 #pragma unroll
       for (int i = 0; i < NW; ++i) W[c][i] = flat[c * NW + i];
-    const float4 m0 = __ldg((const float4*)(p.mb + cw * 4)), m1 = __ldg((const float4*)(p.mb + cw * 4) + 1);
-    k.Mh[0] = m0.x; k.Bh[0] = m0.y; k.Mh[1] = m0.z; k.Bh[1] = m0.w; k.Mh[2] = m1.x; k.Bh[2] = m1.y; k.Mh[3] = m1.z; k.Bh[3] = m1.w;
-    const int4 av = __ldg((const int4*)(p.abm + cw * 4));
-    k.abm[0] = av.x; k.abm[1] = av.y; k.abm[2] = av.z; k.abm[3] = av.w;
+    if (INT) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { ki[c] = __ldg(p.ki + cw * 4 + c); k.abm[c] = 0; }
+    } else {
+      const float4 m0 = __ldg((const float4*)(p.mb + cw * 4)), m1 = __ldg((const float4*)(p.mb + cw * 4) + 1);
+      k.Mh[0] = m0.x; k.Bh[0] = m0.y; k.Mh[1] = m0.z; k.Bh[1] = m0.w; k.Mh[2] = m1.x; k.Bh[2] = m1.y; k.Mh[3] = m1.z; k.Bh[3] = m1.w;
+      const int4 av = __ldg((const int4*)(p.abm + cw * 4));
+      k.abm[0] = av.x; k.abm[1] = av.y; k.abm[2] = av.z; k.abm[3] = av.w;
+    }
   }
+  const bool lo_on = p.lo_i > -128;
   pdl_wait();                                  // constants above do not depend on the previous grid; activations do
   const int rs_in = p.Ws * p.in_pitch_w;                                 // words per stored input row
   const uint32_t* img = p.in + (size_t)b * p.Hs * rs_in + cw;
@@ -178,11 +194,17 @@ __global__ void __launch_bounds__(128) dw3x3_v2_kernel(const DwV2Params p) {
             a1[c] = dp4a_ss(Tp[c], W[c][5 % NW], dp4a_ss(Tc[c], W[c][3 % NW], dp4a_ss(Tm[c], W[c][1], k.abm[c])));
           }
         }
-        RqGuard g; rq_guard_init(g);
-        uint32_t o0 = dw_rq_word(a0, k, p.lo_f, g), o1 = dw_rq_word(a1, k, p.lo_f, g);
-        if (rq_group_bad(g, p.thr)) {
-          o0 = dw_rq_word_exact(a0[0], a0[1], a0[2], a0[3], p.M, p.B, ch0, p.lo_f);
-          o1 = dw_rq_word_exact(a1[0], a1[1], a1[2], a1[3], p.M, p.B, ch0, p.lo_f);
+        uint32_t o0, o1;
+        if (INT) {
+          if (lo_on) { o0 = dw_rq_word_int<true>(a0, ki, p.lo_i); o1 = dw_rq_word_int<true>(a1, ki, p.lo_i); }
+          else { o0 = dw_rq_word_int<false>(a0, ki, p.lo_i); o1 = dw_rq_word_int<false>(a1, ki, p.lo_i); }
+        } else {
+          RqGuard g; rq_guard_init(g);
+          o0 = dw_rq_word(a0, k, p.lo_f, g); o1 = dw_rq_word(a1, k, p.lo_f, g);
+          if (rq_group_bad(g, p.thr)) {
+            o0 = dw_rq_word_exact(a0[0], a0[1], a0[2], a0[3], p.M, p.B, ch0, p.lo_f);
+            o1 = dw_rq_word_exact(a1[0], a1[1], a1[2], a1[3], p.M, p.B, ch0, p.lo_f);
+          }
         }
         o[0] = o0;
         if (SHIFT || two) o[p.out_pitch_w] = o1;
@@ -208,9 +230,13 @@ __global__ void __launch_bounds__(128) dw3x3_v2_kernel(const DwV2Params p) {
 #pragma unroll
       for (int c = 0; c < 4; ++c)
         a0[c] = dp4a_ss(Tp[c], W[c][2], dp4a_ss(Tc[c], W[c][1], dp4a_ss(Tm[c], W[c][0], k.abm[c])));
-      RqGuard g; rq_guard_init(g);
-      uint32_t o0 = dw_rq_word(a0, k, p.lo_f, g);
-      if (rq_group_bad(g, p.thr)) o0 = dw_rq_word_exact(a0[0], a0[1], a0[2], a0[3], p.M, p.B, ch0, p.lo_f);
+      uint32_t o0;
+      if (INT) o0 = lo_on ? dw_rq_word_int<true>(a0, ki, p.lo_i) : dw_rq_word_int<false>(a0, ki, p.lo_i);
+      else {
+        RqGuard g; rq_guard_init(g);
+        o0 = dw_rq_word(a0, k, p.lo_f, g);
+        if (rq_group_bad(g, p.thr)) o0 = dw_rq_word_exact(a0[0], a0[1], a0[2], a0[3], p.M, p.B, ch0, p.lo_f);
+      }
       o[0] = o0;
       o += p.Wout * p.out_pitch_w;
 #pragma unroll
@@ -292,7 +318,7 @@ __device__ __noinline__ uint32_t deform_bilinear_exact_word(const DwParams& p, c
 #define DEF_NP 64
 #define DEF_QCAP 1024
 
-template <int MODE>
+template <int MODE, bool INT>
 __global__ void __launch_bounds__(256, MODE == 0 ? 4 : 3) deform_dw_v2_kernel(const DwParams p) {
   pdl_launch_dependents();
   __shared__ double s_s[DEF_NP];
@@ -386,11 +412,14 @@ __global__ void __launch_bounds__(256, MODE == 0 ? 4 : 3) deform_dw_v2_kernel(co
             wf[MODE == 1 ? c : 0][MODE == 1 ? tap : 0] = (float)(int)(int8_t)((wword >> sh) & 0xff);
           }
       }
-      float Mh[4], Bh[4]; int abm[4];
+      float Mh[4], Bh[4]; int abm[4]; int4 ki[4];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        const float2 mb = active ? __ldg(p.mb + cw * 4 + c) : make_float2(0.f, 0.f);
-        Mh[c] = mb.x; Bh[c] = mb.y; abm[c] = active ? __ldg(p.abm + cw * 4 + c) : CDN_MAGIC_I;
+        if (INT) { ki[c] = active ? __ldg(p.ki + cw * 4 + c) : make_int4(0, 0, 0, 0); abm[c] = 0; }
+        else {
+          const float2 mb = active ? __ldg(p.mb + cw * 4 + c) : make_float2(0.f, 0.f);
+          Mh[c] = mb.x; Bh[c] = mb.y; abm[c] = active ? __ldg(p.abm + cw * 4 + c) : CDN_MAGIC_I;
+        }
       }
       if (MODE == 0) {
         // Software pipeline, unrolled by two with ping-pong tap registers: the 9 taps of the NEXT pixel are in flight
@@ -430,12 +459,16 @@ __global__ void __launch_bounds__(256, MODE == 0 ? 4 : 3) deform_dw_v2_kernel(co
           acc[1] = dp4a_ss(x[8], k.wC[1], dp4a_ss(b1, k.wB[1], dp4a_ss(a1, k.wA[1], abm[1])));
           acc[2] = dp4a_ss(x[8], k.wC[2], dp4a_ss(b2, k.wB[2], dp4a_ss(a2, k.wA[2], abm[2])));
           acc[3] = dp4a_ss(x[8], k.wC[3], dp4a_ss(b3, k.wB[3], dp4a_ss(a3, k.wA[3], abm[3])));
-          RqGuard gd; rq_guard_init(gd);
-          uint32_t r0, r1, r2, r3;
-          rq_fast2(acc[0], acc[1], make_float2(Mh[0], Mh[1]), make_float2(Bh[0], Bh[1]), p.lo_f, gd, r0, r1);
-          rq_fast2(acc[2], acc[3], make_float2(Mh[2], Mh[3]), make_float2(Bh[2], Bh[3]), p.lo_f, gd, r2, r3);
-          uint32_t o = pack4_lowbytes(r0, r1, r2, r3);
-          if (rq_group_bad(gd, p.thr_layer)) o = dw_rq_word_exact(acc[0], acc[1], acc[2], acc[3], p.M, p.B, cw * 4, p.lo_f);
+          uint32_t o;
+          if (INT) o = p.lo_i > -128 ? dw_rq_word_int<true>(acc, ki, p.lo_i) : dw_rq_word_int<false>(acc, ki, p.lo_i);
+          else {
+            RqGuard gd; rq_guard_init(gd);
+            uint32_t r0, r1, r2, r3;
+            rq_fast2(acc[0], acc[1], make_float2(Mh[0], Mh[1]), make_float2(Bh[0], Bh[1]), p.lo_f, gd, r0, r1);
+            rq_fast2(acc[2], acc[3], make_float2(Mh[2], Mh[3]), make_float2(Bh[2], Bh[3]), p.lo_f, gd, r2, r3);
+            o = pack4_lowbytes(r0, r1, r2, r3);
+            if (rq_group_bad(gd, p.thr_layer)) o = dw_rq_word_exact(acc[0], acc[1], acc[2], acc[3], p.M, p.B, cw * 4, p.lo_f);
+          }
           base_out[(unsigned)(j * p.out_pitch_w)] = o;
         };
         uint32_t xa[9], xb[9];
@@ -595,6 +628,21 @@ int dw_device_build(DwDevice& d, const int8_t* wq, const int8_t* ws, int C, int 
       min_thr = std::min(min_thr, (double)f.thr);
     }
     d.thr = (float)min_thr; d.u_ok = u_ok ? 1 : 0;
+    // integer requantisation (common.cuh, RqInt): exact over |v| <= A * sum|w|, A = max |q + zx|; acc_bias folded in so the
+    // dp4a chains start at zero.  The upsample-folded kernel pre-adds weights, which can only shrink the reachable range.
+    d.use_int = 0;
+    if (!(g_cdn_debug_flags & 128u)) {
+      const long long A = std::max(std::abs((long long)zx - 128), std::abs((long long)zx + 127));
+      std::vector<RqInt> ki(Cp, RqInt{0, 0, 0});
+      bool ok = true;
+      for (int c = 0; c < C && ok; ++c) {
+        long long asum = 0;
+        for (int t = 0; t < 9; ++t) { const int v = wq[c * 9 + t]; asum += v < 0 ? -v : v; }
+        ok = rq_int_solve(rq->M[c], rq->B[c], std::max(-128, std::min(127, rq->lo)), -A * asum, A * asum, &ki[c]) &&
+             rq_int_rebase(&ki[c], ab[c], 128 * asum);
+      }
+      if (ok) { if (dev_upload((RqInt**)&d.ki, ki.data(), ki.size())) return CDN_ERR_CUDA; d.use_int = 1; }
+    }
     // fp32 bilinear fast path (deform MODE 1), u = 2^-24, A = 255 >= |q + zx|, S = sum_ij |w_ij| of the channel:
     //   column blend u0 = fl(c1*a1 + fl(c0*a0)), c0 + c1 = 1, weights off by <= u each:        |err| <= 4 A u
     //   t_r = 3 fma over the tap columns:                     |err| <= S_i A (4 + 3) u  (S_i = sum_j |w_ij|)
@@ -623,7 +671,7 @@ int dw_device_build(DwDevice& d, const int8_t* wq, const int8_t* ws, int C, int 
 
 void dw_device_free(DwDevice& d) {
   cudaFree(d.wA); cudaFree(d.wB); cudaFree(d.wC); cudaFree(d.ws); dev_requant_free(d.rq);
-  cudaFree(d.wpk1); cudaFree(d.wpk2); cudaFree(d.wpku); cudaFree(d.mb); cudaFree(d.abm);
+  cudaFree(d.wpk1); cudaFree(d.wpk2); cudaFree(d.wpku); cudaFree(d.mb); cudaFree(d.abm); cudaFree(d.ki);
   d = DwDevice();
 }
 
@@ -646,6 +694,7 @@ static void fill_common(DwParams& p, const DwDevice& d, const int8_t* in, int in
   p.acc_s_bias = d.acc_s_bias;
   p.sval = nullptr;
   p.mb = d.mb; p.abm = d.abm; p.thr_layer = d.thr; p.thr_bil = d.thr_bil;
+  p.ki = (const int4*)d.ki; p.lo_i = d.rq.lo;
 }
 
 int dw_launch(const DwDevice& d, const int8_t* in, int in_pitch, int8_t* out, int out_pitch, int batch, int H, int W,
@@ -670,6 +719,7 @@ int dw_launch(const DwDevice& d, const int8_t* in, int in_pitch, int8_t* out, in
   p.wpk = in_shift ? d.wpku : (stride == 2 ? d.wpk2 : d.wpk1);
   p.mb = d.mb; p.abm = d.abm; p.M = d.rq.M; p.B = d.rq.B;
   p.lo_f = (float)d.rq.lo; p.thr = d.thr;
+  p.ki = (const int4*)d.ki; p.lo_i = d.rq.lo;
   if (p.nthreads == 0) return 0;
   CDN_CHECK(p.nthreads < (1ll << 31) && (long long)p.Hs * p.Ws * p.in_pitch_w < (1ll << 31) &&
             (long long)p.Hout * p.Wout * p.out_pitch_w < (1ll << 31), CDN_ERR_INVALID, "dw: tensor too large for 32-bit indexing");
@@ -680,9 +730,15 @@ int dw_launch(const DwDevice& d, const int8_t* in, int in_pitch, int8_t* out, in
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = (g_cdn_debug_flags & 64u) ? 0 : 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  if (in_shift) CDN_CUDA(cudaLaunchKernelEx(&cfg, dw3x3_v2_kernel<1, 1>, p));
-  else if (stride == 2) CDN_CUDA(cudaLaunchKernelEx(&cfg, dw3x3_v2_kernel<2, 0>, p));
-  else CDN_CUDA(cudaLaunchKernelEx(&cfg, dw3x3_v2_kernel<1, 0>, p));
+  if (d.use_int) {
+    if (in_shift) CDN_CUDA(cudaLaunchKernelEx(&cfg, dw3x3_v2_kernel<1, 1, true>, p));
+    else if (stride == 2) CDN_CUDA(cudaLaunchKernelEx(&cfg, dw3x3_v2_kernel<2, 0, true>, p));
+    else CDN_CUDA(cudaLaunchKernelEx(&cfg, dw3x3_v2_kernel<1, 0, true>, p));
+  } else {
+    if (in_shift) CDN_CUDA(cudaLaunchKernelEx(&cfg, dw3x3_v2_kernel<1, 1, false>, p));
+    else if (stride == 2) CDN_CUDA(cudaLaunchKernelEx(&cfg, dw3x3_v2_kernel<2, 0, false>, p));
+    else CDN_CUDA(cudaLaunchKernelEx(&cfg, dw3x3_v2_kernel<1, 0, false>, p));
+  }
   CDN_LAUNCH_CHECK("dw3x3_v2_kernel");
   return 0;
 }
@@ -710,8 +766,9 @@ int deform_launch(const DwDevice& d, const cdn_deform_scale* sc, const int8_t* i
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = (g_cdn_debug_flags & 64u) ? 0 : 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  if (sc->mode == 0) CDN_CUDA(cudaLaunchKernelEx(&cfg, deform_dw_v2_kernel<0>, p));
-  else CDN_CUDA(cudaLaunchKernelEx(&cfg, deform_dw_v2_kernel<1>, p));
+  if (sc->mode == 0 && d.use_int) CDN_CUDA(cudaLaunchKernelEx(&cfg, deform_dw_v2_kernel<0, true>, p));
+  else if (sc->mode == 0) CDN_CUDA(cudaLaunchKernelEx(&cfg, deform_dw_v2_kernel<0, false>, p));
+  else CDN_CUDA(cudaLaunchKernelEx(&cfg, deform_dw_v2_kernel<1, false>, p));
   CDN_LAUNCH_CHECK("deform_dw_v2_kernel");
   return 0;
 }

@@ -43,6 +43,97 @@ void dev_requant_free(DevRequant& d) {
   d = DevRequant();
 }
 
+// ---- integer requantisation solver (common.cuh, RqInt) ---------------------------------------------------------
+// the definition of the result: rint(fl64(fl64(v*M) + B)), product and sum rounded separately (no contraction)
+static inline long long rq_q64(long long v, double M, double B) {
+  volatile double p = (double)v * M;
+  volatile double t = p + B;
+  return llrint((double)t);
+}
+
+bool rq_int_solve(double M, double B, int lo, long long vmin, long long vmax, RqInt* out) {
+  if (!(M > 0.0) || !std::isfinite(M) || !std::isfinite(B) || vmin > vmax) return false;
+  if (lo < -128) lo = -128;
+  if (lo > 127) lo = 127;
+  int e = 0; (void)frexp(M, &e);               // M in [2^(e-1), 2^e)  ->  M * 2^(31-e) in [2^30, 2^31)
+  int S = 31 - e;
+  if (S < 32) S = 32;
+  if (S > 63) return false;
+  double mi_d = ldexp(M, S);
+  if (mi_d >= 2147483648.0 - 256.0) {          // keep room for the +-d search below
+    if (S == 32) return false;                 // multiplier >= 0.5: the output grid is as fine as the accumulator's
+    --S; mi_d *= 0.5;
+  }
+  const long long Mi0 = llrint(mi_d);
+  // a[k]: smallest v with result >= k (vmax + 1 when none, vmin when all), k = lo+1 .. 127
+  const int nk = 127 - lo;
+  std::vector<long long> a((size_t)std::max(nk, 0));
+  const long long qmin = rq_q64(vmin, M, B), qmax = rq_q64(vmax, M, B);
+  for (int i = 0; i < nk; ++i) {
+    const int k = lo + 1 + i;
+    if (qmax < k) { a[i] = vmax + 1; continue; }
+    if (qmin >= k) { a[i] = vmin; continue; }
+    long long lo_v = vmin, hi_v = vmax;        // result(lo_v) < k <= result(hi_v)
+    const double est = ceil(((double)k - 0.5 - B) / M);
+    if (est > (double)vmin && est <= (double)vmax) {
+      const long long v0 = (long long)est;
+      for (long long c = v0 - 2; c <= v0 + 2; ++c) {
+        if (c <= vmin || c > vmax) continue;
+        if (rq_q64(c - 1, M, B) < k && rq_q64(c, M, B) >= k) { lo_v = c - 1; hi_v = c; break; }
+      }
+    }
+    while (hi_v - lo_v > 1) {
+      const long long mid = lo_v + (hi_v - lo_v) / 2;
+      if (rq_q64(mid, M, B) >= k) hi_v = mid; else lo_v = mid;
+    }
+    a[i] = hi_v;
+  }
+  const __int128 one = 1;
+  const __int128 nominal = (__int128)ldexpl((long double)B + 0.5L, S);
+  const __int128 vm = std::max(vmin < 0 ? -(__int128)vmin : (__int128)vmin, vmax < 0 ? -(__int128)vmax : (__int128)vmax);
+  for (int t = 0; t <= 256; ++t) {
+    const long long d = (t & 1) ? (t + 1) / 2 : -(long long)(t / 2);       // 0, 1, -1, 2, -2, ...
+    const long long Mi = Mi0 + d;
+    if (Mi <= 0 || Mi >= (1ll << 31)) continue;
+    __int128 L = 0, U = 0; bool hasL = false, hasU = false;
+    for (int i = 0; i < nk; ++i) {
+      const __int128 K2 = (__int128)(lo + 1 + i) * (one << S);
+      if (a[i] <= vmax) { const __int128 c = K2 - (__int128)a[i] * Mi; if (!hasL || c > L) L = c; hasL = true; }
+      if (a[i] - 1 >= vmin) { const __int128 c = K2 - (__int128)(a[i] - 1) * Mi - 1; if (!hasU || c < U) U = c; hasU = true; }
+    }
+    if (hasL && hasU && L > U) continue;
+    __int128 Bi;
+    if (hasL && hasU) Bi = L + (U - L) / 2;
+    else if (hasL) Bi = std::max(L, nominal);
+    else if (hasU) Bi = std::min(U, nominal);
+    else Bi = nominal;
+    const __int128 absB = Bi < 0 ? -Bi : Bi;
+    if (absB + vm * Mi >= (one << 62)) return false;
+    out->Mi = (int32_t)Mi; out->sh = S - 32; out->Bi = (long long)Bi;
+    return true;
+  }
+  return false;
+}
+
+bool rq_int_rebase(RqInt* r, long long acc_bias, long long amax) {
+  const __int128 one = 1;
+  const __int128 Bi = (__int128)r->Bi + (__int128)acc_bias * r->Mi;
+  const __int128 absB = Bi < 0 ? -Bi : Bi;
+  if (absB + (__int128)(amax < 0 ? -amax : amax) * r->Mi >= (one << 62)) return false;
+  r->Bi = (long long)Bi;
+  return true;
+}
+
+extern "C" int cdn_rq_int_solve(double M, double B, int lo, int64_t vmin, int64_t vmax, int32_t* Mi, int32_t* sh, int64_t* Bi) {
+  CDN_CHECK(Mi && sh && Bi, CDN_ERR_INVALID, "rq_int_solve: null output pointer");
+  RqInt r;
+  if (!rq_int_solve(M, B, lo, (long long)vmin, (long long)vmax, &r))
+    return cdn_fail(CDN_ERR_INVALID, "rq_int_solve: no exact fixed-point pair for M=%.17g B=%.17g on [%lld, %lld]", M, B,
+                    (long long)vmin, (long long)vmax);
+  *Mi = r.Mi; *sh = r.sh; *Bi = (int64_t)r.Bi;
+  return 0;
+}
+
 extern "C" const char* cdn_last_error(void) { return g_err; }
 extern "C" int cdn_version(void) { return 100; }
 extern "C" int cdn_set_debug_flags(unsigned flags) { g_cdn_debug_flags = flags; return 0; }

@@ -6,6 +6,7 @@ struct DwDevice {                            // depthwise / deformable layer con
   uint32_t *wA = nullptr, *wB = nullptr, *wC = nullptr, *ws = nullptr;
   uint32_t *wpk1 = nullptr, *wpk2 = nullptr, *wpku = nullptr;   // v2 packings: stride 1, stride 2, upsample-folded
   float2* mb = nullptr; int32_t* abm = nullptr; float thr = 0.5f, thr_bil = 0.01f; int u_ok = 1;
+  RqInt* ki = nullptr; int use_int = 0;        // exact integer requantisation constants (acc_bias folded in)
   DevRequant rq;
   int cw_total = 0;
   long long acc_s_bias = 0;
@@ -31,6 +32,7 @@ struct PwDevice {
   int K = 0, k_off = 0, N = 0, Kp = 0, BN = 0, n_tiles = 0, num_k_blocks = 0, stages = 0;
   int has_pass = 0, pass_segs = 0, pass_bufs = 1, groups = 2, nbuf = 0, resident = 0, n_chunks = 0, n_segs = 0, n_f32 = 0;
   float thr = 0.5f;                          // layer-wide rounding-boundary guard (min over columns)
+  int use_int = 0;                           // kc holds RqInt records (exact integer requantisation) instead of the fp32 pairs
   size_t smem_bytes = 0;
   int8_t* w = nullptr;                       // [BN*n_tiles][Kp]
   cdn_pw_chunk* chunks = nullptr; void* segs = nullptr; int* tile_seg = nullptr; void* kc = nullptr;

@@ -46,6 +46,7 @@ struct PwParams {
   const float4* kc;                          // per GEMM column {Mh, Bh, bits(acc_bias + MAGIC_I), 0}
   const double* M; const double* B; const int32_t* acc_bias;
   float lo_f, thr;
+  int use_int, lo_i;                         // integer requantisation: kc holds one RqInt per column (acc_bias folded in)
   unsigned dbg;                              // experiments only (cdn_set_debug_flags bits 2..4)
   unsigned long long* dbg_cyc;               // [16] cycle accumulators of block 0 (bit 4)
   // fp32 head output
@@ -195,6 +196,40 @@ __device__ __forceinline__ uint4 chunk_bytes(const cdn_pw_chunk& ck, const uint3
     if (__any_sync(__activemask(), bad)) { if (bad) requant_cols_exact<8>(acc, kc, ck.col, Md, Bd, lo_f, q); }
     const uint32_t n_lo = pack4_lowbytes(q[0], q[1], q[2], q[3]), n_hi = pack4_lowbytes(q[4], q[5], q[6], q[7]);
     // out[2i] = pass[i], out[2i+1] = new[i]
+    o.x = __byte_perm(pass_lo, n_lo, 0x5140); o.y = __byte_perm(pass_lo, n_lo, 0x7362);
+    o.z = __byte_perm(pass_hi, n_hi, 0x5140); o.w = __byte_perm(pass_hi, n_hi, 0x7362);
+    if (ck.count < 8) o = mask_tail(o, 2 * ck.count);
+  }
+  return o;
+}
+
+// out-of-line copy for the tensor-core kernel: the guarded fp32 sequence is the fallback there (layers without an exact
+// integer form), and inlining both would spill the hot path's registers
+__device__ __noinline__ uint4 chunk_bytes_guarded(cdn_pw_chunk ck, uint4 a0, uint4 a1, uint4 a2, uint4 a3, const float4* __restrict__ kc,
+                                                  const double* __restrict__ Md, const double* __restrict__ Bd, float lo_f, float thr,
+                                                  uint32_t pass_lo, uint32_t pass_hi) {
+  const uint32_t acc[16] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w, a3.x, a3.y, a3.z, a3.w};
+  return chunk_bytes(ck, acc, kc, Md, Bd, lo_f, thr, pass_lo, pass_hi);
+}
+
+// The same 16 output bytes with the integer requantisation (RqInt per column, raw accumulators): no guard, no slow path.
+template <bool LO>
+__device__ __forceinline__ uint4 chunk_bytes_int(const cdn_pw_chunk& ck, const uint32_t (&acc)[16], const int4* __restrict__ kc,
+                                                 int lo, uint32_t pass_lo, uint32_t pass_hi) {
+  const int4* __restrict__ k = kc + ck.col;
+  int q[16];
+  uint4 o;
+  if (ck.pass_off < 0) {
+    if (ck.count == 0) return make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { q[i] = rq_int((int)acc[i], k[i]); if (LO) q[i] = max(q[i], lo); }
+    o.x = pack_sat4(q[0], q[1], q[2], q[3]);   o.y = pack_sat4(q[4], q[5], q[6], q[7]);
+    o.z = pack_sat4(q[8], q[9], q[10], q[11]); o.w = pack_sat4(q[12], q[13], q[14], q[15]);
+    if (ck.count < 16) o = mask_tail(o, ck.count);   // pad bytes of the pixel stay zero
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { q[i] = rq_int((int)acc[i], k[i]); if (LO) q[i] = max(q[i], lo); }
+    const uint32_t n_lo = pack_sat4(q[0], q[1], q[2], q[3]), n_hi = pack_sat4(q[4], q[5], q[6], q[7]);
     o.x = __byte_perm(pass_lo, n_lo, 0x5140); o.y = __byte_perm(pass_lo, n_lo, 0x7362);
     o.z = __byte_perm(pass_hi, n_hi, 0x5140); o.w = __byte_perm(pass_hi, n_hi, 0x7362);
     if (ck.count < 8) o = mask_tail(o, 2 * ck.count);
@@ -468,8 +503,13 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
             tmem_ld_wait();
             uint4 o;
-            if (p.dbg & 4u) o = make_uint4(acc[0], acc[1], pass_lo, pass_hi);          // experiment: no requant math
-            else o = chunk_bytes(ck, acc, s_kc, p.M, p.B, p.lo_f, p.thr, pass_lo, pass_hi);
+            if (p.use_int) {
+              if (p.lo_i > -128) o = chunk_bytes_int<true>(ck, acc, (const int4*)s_kc, p.lo_i, pass_lo, pass_hi);
+              else o = chunk_bytes_int<false>(ck, acc, (const int4*)s_kc, p.lo_i, pass_lo, pass_hi);
+            } else if (p.dbg & 4u) o = make_uint4(acc[0], acc[1], pass_lo, pass_hi);   // experiment: no requant math
+            else o = chunk_bytes_guarded(ck, make_uint4(acc[0], acc[1], acc[2], acc[3]), make_uint4(acc[4], acc[5], acc[6], acc[7]),
+                                         make_uint4(acc[8], acc[9], acc[10], acc[11]), make_uint4(acc[12], acc[13], acc[14], acc[15]),
+                                         s_kc, p.M, p.B, p.lo_f, p.thr, pass_lo, pass_hi);
             const int j = (ck.dst_off & 127) >> 4;
             *(uint4*)(stg + ((j ^ (row & 7)) << 4)) = o;
           }
@@ -538,7 +578,10 @@ __global__ void pw_gemm_simt_kernel(const PwParams p, int total_chunks) {
       uint32_t byte = (ck.pass_off + i < p.pass_pitch) ? (uint8_t)p.pass[(size_t)pix * p.pass_pitch + ck.pass_off + i] : 0u;
       if (i < 4) pass_lo |= byte << (8 * i); else pass_hi |= byte << (8 * (i - 4));
     }
-  uint4 o = chunk_bytes(ck, acc, p.kc, p.M, p.B, p.lo_f, p.thr, pass_lo, pass_hi);
+  uint4 o;
+  if (p.use_int) {
+    o = chunk_bytes_int<true>(ck, acc, (const int4*)p.kc, p.lo_i, pass_lo, pass_hi);
+  } else o = chunk_bytes(ck, acc, p.kc, p.M, p.B, p.lo_f, p.thr, pass_lo, pass_hi);
   if (ck.dst_off + 16 <= p.out_pitch) *(uint4*)(p.out + (size_t)pix * p.out_pitch + ck.dst_off) = o;
 }
 
@@ -639,6 +682,25 @@ int pw_device_build(PwDevice& d, const cdn_pw_desc* desc, int pass_pitch) {
     CDN_CHECK(desc->chunks && desc->n_chunks > 0, CDN_ERR_INVALID, "pw: int8 output needs a chunk table");
     if (int r = dev_requant_upload(d.rq, &desc->rq, ab.data(), Np)) return r;
     fill_kc(d.rq, &desc->rq);
+    // integer requantisation (common.cuh, RqInt): one exact fixed-point pair per column over the accumulator range the
+    // column can reach (|q + zx| <= A, so |v| <= A * sum|w|), re-based to the raw accumulator sum_k w*q of the MMA.
+    // If any column has none the layer keeps the guarded fp32 table built above.
+    if (!(g_cdn_debug_flags & 128u)) {         // bit 7: force the guarded fp32 epilogue (A/B measurements)
+      const long long A = std::max(std::abs((long long)desc->zx - 128), std::abs((long long)desc->zx + 127));
+      std::vector<RqInt> ki(Np, RqInt{0, 0, 0});
+      bool ok = true;
+      for (int n = 0; n < d.N && ok; ++n) {
+        long long asum = 0;
+        for (int k = 0; k < d.K; ++k) { const int v = desc->wq[(size_t)n * d.K + k]; asum += v < 0 ? -v : v; }
+        ok = rq_int_solve(desc->rq.M[n], desc->rq.B[n], d.rq.lo, -A * asum, A * asum, &ki[n]) &&
+             rq_int_rebase(&ki[n], ab[n], 128 * asum);
+      }
+      if (ok) {
+        static_assert(sizeof(RqInt) == sizeof(float4), "RqInt must be one 16-byte record");
+        memcpy(kc.data(), ki.data(), (size_t)Np * sizeof(RqInt));
+        d.use_int = 1;
+      }
+    }
     // chunks grouped by N tile, then by 128-byte output segment; every tile owns whole segments
     d.has_pass = 0;
     int seg_cursor = 0;
@@ -751,7 +813,7 @@ int pw_launch(const PwDevice& d, const int8_t* in, int in_pitch, long long pixel
   p.m_tiles = (pixels + PW_BM - 1) / PW_BM; p.pixels = pixels;
   p.chunks = d.chunks; p.segs = (const PwSeg*)d.segs; p.tile_seg = d.tile_seg; p.kc = (const float4*)d.kc;
   p.M = d.rq.M; p.B = d.rq.B; p.acc_bias = d.rq.acc_bias;
-  p.lo_f = (float)d.rq.lo; p.thr = d.thr; p.dbg = g_cdn_debug_flags; p.dbg_cyc = g_pw_dbg; if (!g_pw_dbg) p.dbg &= ~16u;
+  p.lo_f = (float)d.rq.lo; p.thr = d.thr; p.use_int = d.use_int; p.lo_i = d.rq.lo; p.dbg = g_cdn_debug_flags; p.dbg_cyc = g_pw_dbg; if (!g_pw_dbg) p.dbg &= ~16u;
   { const int sel = (int)((g_cdn_debug_flags >> 8) & 0xff); ++g_pw_launch_index; if (sel && sel != g_pw_launch_index) p.dbg &= ~16u; }
   p.n_f32 = d.n_f32; p.ppi = ppi; p.out_f32 = out_f32; p.Mf = d.Mf; p.bf = d.bf;
   p.in = in; p.in_pitch = in_pitch; p.pass = pass; p.pass_pitch = pass_pitch; p.out = out; p.out_pitch = out_pitch;

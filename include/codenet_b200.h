@@ -26,8 +26,9 @@
  * (q + z) / s for the (s, z) of the QuantAct that produced it (quant_utils.py:58-73).
  *
  * Requantisation constants (one per output channel): q = clamp(rint(acc*M + B), lo, 127) with
- * M, B in fp64.  The library derives an fp32 copy and a per-channel guard band inside which the kernels re-evaluate
- * in fp64, so results are bit-identical to the fp64 formula.
+ * M, B in fp64.  The library solves, per channel, for an exact 64-bit fixed-point form of this step function
+ * (cdn_rq_int_solve); where none exists it derives an fp32 copy and a guard band inside which the kernels re-evaluate in
+ * fp64.  Either way results are bit-identical to the fp64 formula.
  */
 #ifndef CODENET_B200_H
 #define CODENET_B200_H
@@ -54,7 +55,8 @@ int cdn_version(void);
 int cdn_check_device(int device);
 /* Bring-up / measurement switches, never needed in production.  bit 0: 1x1 convolutions on the SIMT cross-check kernel
  * instead of tcgen05; bit 1: no CUDA graph (eager launches); bit 4: in-kernel phase cycle accounting of the GEMM
- * (tools/pw_phase_cycles.py); bit 6: no programmatic dependent launch; bits 2, 3, 5: experiments that BREAK results. */
+ * (tools/pw_phase_cycles.py); bit 6: no programmatic dependent launch; bit 7 (read when a layer is built): guarded fp32
+ * requantisation instead of the integer form (same results, A/B timing); bits 2, 3, 5: experiments that BREAK results. */
 int cdn_set_debug_flags(unsigned flags);
 
 /* ---- per-output-channel requantisation constants (host arrays, length n) ------------------------------- */
@@ -64,6 +66,13 @@ typedef struct {
   int lo;                                   /* max(-128, relu ? -z_out : -128) */
   int n;
 } cdn_requant;
+
+/* Host-only helper (no device needed): the fixed-point form the int8 kernels evaluate,
+ *   q = sat8(max((((int64)v*Mi + Bi) >> 32) >> sh, lo)),
+ * solved so that it equals clamp(rint(fl64(fl64(v*M) + B)), lo, 127) for EVERY integer accumulator v in [vmin, vmax]
+ * (DESIGN.md "requantisation").  Returns CDN_ERR_INVALID when no exact pair exists (M >= 0.5 or M <= 0); layers fall back
+ * to the guarded fp32 sequence in that case.  Exposed so the exactness claim can be tested exhaustively on the CPU. */
+int cdn_rq_int_solve(double M, double B, int lo, int64_t vmin, int64_t vmax, int32_t* Mi, int32_t* sh, int64_t* Bi);
 
 /* ---- stem: fp32 NCHW image -> int8 NHWC -----------------------------------------------------------------
  * 3x3 conv, pad 1, stride `stride`, 3 -> C (C <= 32), 8-bit integer weights wq[C][3][3][3] (host), then ReLU and

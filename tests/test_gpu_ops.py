@@ -80,6 +80,12 @@ def test_pointwise_tcgen05_every_layer(sim256):
     _check_ops(sim256, ("pw",), flags=0)
 
 
+def test_guarded_fp32_requant_fallback_every_layer(sim256):
+    """Debug flag bit 7 builds the layers with the guarded fp32 requantisation (the path kept for channels that have
+    no exact integer form): it must give the same bytes as the integer form the other tests run."""
+    _check_ops(sim256, ("pw", "dw", "deform"), flags=128)
+
+
 # ---- randomised shapes -------------------------------------------------------------------------------------------
 def _mini_plan():
     return Plan(CFG, 0, 0, "round")
@@ -99,7 +105,7 @@ def test_depthwise_random(C, H, W, stride, shift):
     M = np.zeros(pitch); B = np.zeros(pitch)
     M[:C] = rng.uniform(0.002, 0.02, C); B[:C] = rng.uniform(-140, -100, C)
     zx = int(rng.integers(100, 129))
-    op = Op("dw", "t", dict(in_t=0, out_t=1, in_shift=shift, stride=stride, wq=wq, C=pitch, zx=zx, M=M, B=B, lo=-128))
+    op = Op("dw", "t", dict(in_t=0, out_t=1, in_shift=shift, stride=stride, wq=wq, C=pitch, zx=zx, M=M, B=B, lo=-128 if C % 3 else -97))
     P.ops.append(op)
     x = np.zeros((3, tin.H, tin.W, pitch), np.int64); x[..., :C] = rng.integers(-128, 128, (3, tin.H, tin.W, C))
     sim = plan_sim.run_plan_seeded(P, {0: x})[0]
@@ -163,7 +169,8 @@ def test_deform_random(C, H, W, bound, shift, mode):
 
 
 @pytest.mark.parametrize("K,N,relu,flags", [(24, 58, 1, 0), (58, 58, 1, 0), (116, 232, 0, 0), (464, 1024, 1, 0), (1024, 256, 1, 0),
-                                            (64, 192, 1, 0), (200, 64, 0, 0), (58, 58, 1, 1), (464, 1024, 1, 1)])
+                                            (64, 192, 1, 0), (200, 64, 0, 0), (58, 58, 1, 1), (464, 1024, 1, 1),
+                                            (58, 58, 1, 128), (464, 1024, 0, 128)])
 def test_pointwise_random_dense(K, N, relu, flags):
     from gpu_util import run_op
     _lib.load().cdn_set_debug_flags(flags)
@@ -178,7 +185,7 @@ def test_pointwise_random_dense(K, N, relu, flags):
     M = np.zeros(N16); Bc = np.zeros(N16)
     M[:N] = rng.uniform(0.2, 1.0, N) / np.sqrt(K) / 30; Bc[:N] = rng.uniform(-130, -90, N)
     chunks = [((16 * j) if N - 16 * j > 0 else 0, int(np.clip(N - 16 * j, 0, 16)), -1, 16 * j) for j in range(Np // 16)]
-    a = dict(in_t=0, out_t=1, pass_t=-1, k_off=0, K=Kp, N=N16, zx=128, wq=w, M=M, B=Bc, lo=-128 if not relu else -128,
+    a = dict(in_t=0, out_t=1, pass_t=-1, k_off=0, K=Kp, N=N16, zx=128, wq=w, M=M, B=Bc, lo=-128 if not relu else -101,
              chunks=np.array(chunks, np.int16), n_f32=0)
     op = Op("pw", "t", a)
     P.ops.append(op)
