@@ -265,6 +265,7 @@ def run_ours(args):
                            "input": "normalised fp32 NCHW tensor (the model.forward input), PCIe-bound",
                            "api": "Engine.run_host -> cdn_engine_run_host"},
         "gpu_launches": int(eng.num_launches * args.steps),
+        "requant": dict(zip(("int_layers", "guarded_fp32_layers"), eng.requant_stats)),
         "clocks": clocks, "roofline": roofline, "deform": deform, "cpu_baseline": cpu,
     }
     print(json.dumps(line))

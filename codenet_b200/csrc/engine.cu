@@ -52,9 +52,15 @@ static inline long long rq_q64(long long v, double M, double B) {
 }
 
 bool rq_int_solve(double M, double B, int lo, long long vmin, long long vmax, RqInt* out) {
-  if (!(M > 0.0) || !std::isfinite(M) || !std::isfinite(B) || vmin > vmax) return false;
+  if (!std::isfinite(M) || !std::isfinite(B) || vmin > vmax) return false;
   if (lo < -128) lo = -128;
   if (lo > 127) lo = 127;
+  if (M == 0.0) {                              // padding channels: the result is the constant rint(B) (clamped by the caller's sat8 / lo)
+    const double q = std::min(std::max(nearbyint(B), -1048576.0), 1048576.0);
+    out->Mi = 0; out->sh = 0; out->Bi = (long long)q * (1ll << 32);
+    return true;
+  }
+  if (!(M > 0.0)) return false;
   int e = 0; (void)frexp(M, &e);               // M in [2^(e-1), 2^e)  ->  M * 2^(31-e) in [2^30, 2^31)
   int S = 31 - e;
   if (S < 32) S = 32;
@@ -672,3 +678,15 @@ extern "C" int cdn_engine_read_heads(cdn_engine* e, int batch, float* h_out) {
 }
 
 extern "C" int cdn_engine_num_launches(cdn_engine* e) { return e ? e->launches : 0; }
+extern "C" int cdn_engine_requant_stats(cdn_engine* e, int* int_layers, int* guarded_layers) {
+  ENG_CHECK(e);
+  int ni = 0, ng = 0;
+  for (const EngOp* op : e->ops) {
+    if (op->kind == 1 || (op->kind == 2 && op->sc.mode == 0)) { if (op->dw.use_int) ++ni; else ++ng; }
+    else if (op->kind == 2) ++ng;                      // bilinear: non-integer accumulators, guarded fp32 by construction
+    else if (op->kind == 3 && op->pw.n_f32 == 0) { if (op->pw.use_int) ++ni; else ++ng; }
+  }
+  if (int_layers) *int_layers = ni;
+  if (guarded_layers) *guarded_layers = ng;
+  return 0;
+}

@@ -203,15 +203,6 @@ __device__ __forceinline__ uint4 chunk_bytes(const cdn_pw_chunk& ck, const uint3
   return o;
 }
 
-// out-of-line copy for the tensor-core kernel: the guarded fp32 sequence is the fallback there (layers without an exact
-// integer form), and inlining both would spill the hot path's registers
-__device__ __noinline__ uint4 chunk_bytes_guarded(cdn_pw_chunk ck, uint4 a0, uint4 a1, uint4 a2, uint4 a3, const float4* __restrict__ kc,
-                                                  const double* __restrict__ Md, const double* __restrict__ Bd, float lo_f, float thr,
-                                                  uint32_t pass_lo, uint32_t pass_hi) {
-  const uint32_t acc[16] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w, a3.x, a3.y, a3.z, a3.w};
-  return chunk_bytes(ck, acc, kc, Md, Bd, lo_f, thr, pass_lo, pass_hi);
-}
-
 // The same 16 output bytes with the integer requantisation (RqInt per column, raw accumulators): no guard, no slow path.
 template <bool LO>
 __device__ __forceinline__ uint4 chunk_bytes_int(const cdn_pw_chunk& ck, const uint32_t (&acc)[16], const int4* __restrict__ kc,
@@ -222,8 +213,11 @@ __device__ __forceinline__ uint4 chunk_bytes_int(const cdn_pw_chunk& ck, const u
   if (ck.pass_off < 0) {
     if (ck.count == 0) return make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { q[i] = rq_int((int)acc[i], k[i]); if (LO) q[i] = max(q[i], lo); }
+    for (int i = 0; i < 8; ++i) { q[i] = rq_int((int)acc[i], k[i]); if (LO) q[i] = max(q[i], lo); }
     o.x = pack_sat4(q[0], q[1], q[2], q[3]);   o.y = pack_sat4(q[4], q[5], q[6], q[7]);
+    asm volatile("" ::: "memory");             // keeps the second half's 8 LDS.128 (32 registers) from being hoisted too
+#pragma unroll
+    for (int i = 8; i < 16; ++i) { q[i] = rq_int((int)acc[i], k[i]); if (LO) q[i] = max(q[i], lo); }
     o.z = pack_sat4(q[8], q[9], q[10], q[11]); o.w = pack_sat4(q[12], q[13], q[14], q[15]);
     if (ck.count < 16) o = mask_tail(o, ck.count);   // pad bytes of the pixel stay zero
   } else {
@@ -244,6 +238,9 @@ __device__ __forceinline__ uint4 chunk_bytes_int(const cdn_pw_chunk& ck, const u
 //   [B resident: num_k_blocks x Ntot x 128 B]  (resident only)
 //   [ring: stages x (A 16 KB [+ B block BN x 128 B rounded to 1 KB when streamed])]
 //   [pass: 2 x pass_segs x 16 KB] [staging: nbuf x 16 KB] [kc: Ntot x 16 B] [chunks] [segs] [tile_seg] [barriers]
+// RQ selects the epilogue at compile time, so the hot loop holds one variant only: 0 = guarded fp32 requantisation,
+// 1 = integer requantisation, 2 = integer with an explicit lower clamp (lo > -128), 3 = fp32 NCHW head planes.
+template <int RQ>
 __global__ void __launch_bounds__(PW_THREADS, 1)
 pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmO,
@@ -403,7 +400,7 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // buffer and hands it back through SEMPTY.
     const int grp = warp - PW_STORE_WARP0;
     pdl_wait();
-    if (lane == 0 && p.n_f32 == 0 && grp < p.groups) {
+    if (lane == 0 && RQ != 3 && grp < p.groups) {
       uint32_t g = 0; int sbuf = 0; uint32_t sph = 0;          // staging buffer cursor (index, phase)
       for (unsigned tile = blockIdx.x + grp * gridDim.x; tile < total_tiles; tile += p.groups * gridDim.x) {
         unsigned mt; int nt; split_tile(tile, mt, nt);
@@ -450,7 +447,7 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (p.has_pass) mbar_wait(PFULL(pb), (itg >> pb_shift) & 1);
       if (warp == 2) DBG_ACC(5);
       const uint32_t tacc = tmem_base + (uint32_t)as * acc_stride + ((uint32_t)(q * 32) << 16);
-      if (p.n_f32 > 0) {
+      if (RQ == 3) {
         // fp32 NCHW planes: out[img][n][pix] = fl32(fl64(acc*Mf[n]) + bf[n])
         const unsigned pix = mt * PW_BM + row;
         const unsigned img = pix / (unsigned)p.ppi; const int pi = (int)(pix - img * (unsigned)p.ppi);
@@ -503,13 +500,10 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
             tmem_ld_wait();
             uint4 o;
-            if (p.use_int) {
-              if (p.lo_i > -128) o = chunk_bytes_int<true>(ck, acc, (const int4*)s_kc, p.lo_i, pass_lo, pass_hi);
-              else o = chunk_bytes_int<false>(ck, acc, (const int4*)s_kc, p.lo_i, pass_lo, pass_hi);
-            } else if (p.dbg & 4u) o = make_uint4(acc[0], acc[1], pass_lo, pass_hi);   // experiment: no requant math
-            else o = chunk_bytes_guarded(ck, make_uint4(acc[0], acc[1], acc[2], acc[3]), make_uint4(acc[4], acc[5], acc[6], acc[7]),
-                                         make_uint4(acc[8], acc[9], acc[10], acc[11]), make_uint4(acc[12], acc[13], acc[14], acc[15]),
-                                         s_kc, p.M, p.B, p.lo_f, p.thr, pass_lo, pass_hi);
+            if (RQ == 1) o = chunk_bytes_int<false>(ck, acc, (const int4*)s_kc, p.lo_i, pass_lo, pass_hi);
+            else if (RQ == 2) o = chunk_bytes_int<true>(ck, acc, (const int4*)s_kc, p.lo_i, pass_lo, pass_hi);
+            else if (p.dbg & 4u) o = make_uint4(acc[0], acc[1], pass_lo, pass_hi);     // experiment: no requant math
+            else o = chunk_bytes(ck, acc, s_kc, p.M, p.B, p.lo_f, p.thr, pass_lo, pass_hi);
             const int j = (ck.dst_off & 127) >> 4;
             *(uint4*)(stg + ((j ^ (row & 7)) << 4)) = o;
           }
@@ -793,7 +787,10 @@ extern "C" int cdn_debug_read_cycles(unsigned long long* out16, int reset) {
 int pw_init_attrs() {
   static bool attr_set = false;
   if (!attr_set) {
-    CDN_CUDA(cudaFuncSetAttribute(pw_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_LIMIT));
+    CDN_CUDA(cudaFuncSetAttribute(pw_gemm_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_LIMIT));
+    CDN_CUDA(cudaFuncSetAttribute(pw_gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_LIMIT));
+    CDN_CUDA(cudaFuncSetAttribute(pw_gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_LIMIT));
+    CDN_CUDA(cudaFuncSetAttribute(pw_gemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_LIMIT));
     attr_set = true;
   }
   return 0;
@@ -841,7 +838,10 @@ int pw_launch(const PwDevice& d, const int8_t* in, int in_pitch, long long pixel
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = (g_cdn_debug_flags & 64u) ? 0 : 1;   // bit 6: disable PDL (experiments)
   cfg.attrs = attr; cfg.numAttrs = 1;
-  CDN_CUDA(cudaLaunchKernelEx(&cfg, pw_gemm_tc_kernel, a, d.tmB, pm, o, p));
+  if (d.n_f32 > 0) CDN_CUDA(cudaLaunchKernelEx(&cfg, pw_gemm_tc_kernel<3>, a, d.tmB, pm, o, p));
+  else if (!d.use_int) CDN_CUDA(cudaLaunchKernelEx(&cfg, pw_gemm_tc_kernel<0>, a, d.tmB, pm, o, p));
+  else if (d.rq.lo > -128) CDN_CUDA(cudaLaunchKernelEx(&cfg, pw_gemm_tc_kernel<2>, a, d.tmB, pm, o, p));
+  else CDN_CUDA(cudaLaunchKernelEx(&cfg, pw_gemm_tc_kernel<1>, a, d.tmB, pm, o, p));
   CDN_LAUNCH_CHECK("pw_gemm_tc_kernel");
   return 0;
 }

@@ -165,6 +165,13 @@ class Engine:
     def num_launches(self):
         return int(self.lib.cdn_engine_num_launches(self._h))
 
+    @property
+    def requant_stats(self):
+        """(layers on the exact integer requantisation, layers on the guarded fp32 sequence)."""
+        a, b = C.c_int(0), C.c_int(0)
+        _lib.check(self.lib.cdn_engine_requant_stats(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     # -- test / debug access ------------------------------------------------------------------------------------------
     def read_tensor(self, tid: int, batch: int) -> np.ndarray:
         t = self.plan.tensors[tid]

@@ -249,6 +249,9 @@ int cdn_engine_read_heads(cdn_engine* e, int batch, float* h_out);
 int cdn_engine_profile(cdn_engine* e, const float* d_img, int batch, float* ms, int n, cdn_stream_t stream);
 /* Number of kernels one cdn_engine_run launches (for bench.py's gpu_launches). */
 int cdn_engine_num_launches(cdn_engine* e);
+/* How many int8-producing layers run the exact integer requantisation and how many the guarded fp32 sequence (layers
+ * with a channel that has no exact fixed-point form, and the bilinear deformable layers). */
+int cdn_engine_requant_stats(cdn_engine* e, int* int_layers, int* guarded_layers);
 
 #ifdef __cplusplus
 }

@@ -94,6 +94,9 @@ def test_engine_equals_oracle_on_fresh_images(calib):
     torch.cuda.synchronize()
     o = io.IntOracle(CFG, st, "round")
     ref = o.forward(x)
+    n_int, n_guarded = eng.requant_stats          # every int8-producing layer of this network has an exact integer form
+    assert n_guarded == 0 and n_int == sum(op.kind in ("dw", "deform") or (op.kind == "pw" and not op.a["n_f32"])
+                                           for op in eng.plan.ops)
     for lbl in ("stem", "layer1.out", "layer2.out", "layer3.out", "layer4", "up0.deform", "up1.deform", "up2.deform", "up2.out"):
         assert int8_mismatch(eng.read_logical(lbl, 3), o.cap[lbl]) == 0, lbl
     heads = eng.read_heads(3)

@@ -193,7 +193,7 @@ def test_pointwise_random_dense(K, N, relu, flags):
     sim = plan_sim.run_plan_seeded(P, {0: x})[0]
     got = run_op(P, op, {0: x})
     assert int8_mismatch(got, sim[1]) == 0
-    assert len(np.unique(got)) > 20
+    assert len(np.unique(got)) > (20 if not relu else 8)
 
 
 def test_general_deform_conv_f32(golden):

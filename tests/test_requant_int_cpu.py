@@ -35,7 +35,7 @@ def check_all(M, B, lo, vmax, chunk=1 << 22, may_refuse=False):
     if may_refuse and r != 0:
         return False
     assert r == 0, (M, B, lo, vmax)
-    assert 0 < Mi < 2 ** 31 and 0 <= sh < 32
+    assert (0 < Mi < 2 ** 31 or M == 0.0) and 0 <= sh < 32
     for a in range(-vmax, vmax + 1, chunk):
         v = np.arange(a, min(a + chunk, vmax + 1), dtype=np.int64)
         bad = np.nonzero(ref_q(v, M, B, lo) != int_q(v, Mi, sh, Bi, lo))[0]
@@ -84,6 +84,9 @@ def test_degenerate_ranges():
     check_all(1e-6, 500.0, -128, 1000)            # always saturated high
     check_all(1e-6, -500.0, -128, 1000)           # always saturated low
     check_all(0.01, 0.0, 127, 100000)             # lo == 127: nothing to solve
+    check_all(0.0, 0.0, -128, 1000)               # padding channel (M == 0): constant rint(B)
+    check_all(0.0, -3.5, -128, 1000)
+    check_all(0.0, 2.5, -1, 1000)
 
 
 def test_refuses_what_it_cannot_represent():
