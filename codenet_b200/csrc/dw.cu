@@ -33,6 +33,8 @@ struct DwParams {
   const float2* mb; const int* abm; float thr_layer;   // lean requantisation constants (v2 kernels)
   float thr_bil;                             // guard of the fp32 bilinear fast path (0.5 - eps, host-derived bound)
   const int4* ki; int lo_i;                  // integer requantisation (RqInt per channel, acc_bias folded in)
+  int np;                                    // v3: pixels per tile
+  const int* s_thr; int s_n, s_lo;           // integer offsets (v3): s = s_lo + #{k : acc_s >= s_thr[k]}, thresholds ascending
 };
 
 struct LaneConsts {
@@ -570,6 +572,185 @@ __global__ void __launch_bounds__(256, MODE == 0 ? 4 : 3) deform_dw_v2_kernel(co
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// integer-offset layer, v3.  Everything that is the same for all channels of a pixel is done ONCE per pixel:
+//   phase A  the C->1 scale conv is reduced per pixel by a warp (dp4a + shuffle tree, scale weights in registers); one
+//            lane per pixel then maps the integer dot product to the integer offset scalar s by counting host-computed
+//            thresholds (s is a monotone step function of the dot product: Hardtanh, QuantAct and both roundings are
+//            monotone; the host evaluates the fp64 chain of dcn_deform_conv.py:295-330 / quant_modules.py:648-653 at
+//            the step positions, so no fp64 runs on the device) and writes the 9 clamped tap offsets (32-bit word
+//            offsets from the tensor base) and a 9-bit out-of-image mask to shared memory.
+//   phase C  a warp owns 128 channels: per pixel 3 LDS.128 (tap offsets) + 1 LDS (mask), 9 coalesced 128-byte loads,
+//            (border pixels only: 9 selects of the pad word), two byte transposes, 12 dp4a, requantisation, one store.
+//            v2 recomputed the tap coordinates per channel group and pixel (~230 instructions per pixel and warp with
+//            register spills); this loop is ~80.
+// ---------------------------------------------------------------------------------------------------------
+#ifndef DEF3_CTAS
+#define DEF3_CTAS 3
+#endif
+#define DEF3_MAX_NP 256
+// p.np = pixels per tile (64, 128 or 256; a multiple of 8): wide layers (many channel groups per pixel) take small tiles
+// for load balance, narrow ones large tiles so that the per-tile work (constants, barriers, the per-pixel scalar code that
+// runs on np/8 lanes of every warp) is amortised over 32 pixels per warp.
+template <bool INT>
+__global__ void __launch_bounds__(256, DEF3_CTAS) deform_int_v3_kernel(const DwParams p) {
+  pdl_launch_dependents();
+  __shared__ __align__(16) uint32_t s_off[DEF3_MAX_NP][12];   // word offsets of taps 0..8, out-of-image mask, 2 pad words
+  __shared__ int s_thr[128];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rs_in = p.Ws * p.in_pitch_w;
+  const int Gw = p.G >= 8 ? 8 : (p.G >= 4 ? 4 : (p.G >= 2 ? 2 : 1));
+  const int wg = warp % Gw, nslot = 8 / Gw;
+  const int lpp = p.lpp, ppw = 32 / lpp, sub = lane / lpp, cl = lane % lpp;
+  const int wslot = (warp / Gw) * ppw + sub, jstep = nslot * ppw;
+  const int np = p.np;
+  const long long ntiles = (p.total + np - 1) / np;
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) s_thr[i] = i < p.s_n ? __ldg(p.s_thr + i) : 0x7fffffff;
+  // phase C constants: a warp serves ONE channel group whenever G <= 8 (every shipped layer); they then stay in
+  // registers for the whole kernel
+  uint32_t wA[4], wB[4], wC[4];
+  int Mi[4], sh[4]; long long Bi[4]; float Mh[4], Bh[4]; int abm[4];
+  auto load_consts = [&](int cw, bool active) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int ch = cw * 4 + c;
+      wA[c] = active ? __ldg(p.wA + ch) : 0u; wB[c] = active ? __ldg(p.wB + ch) : 0u; wC[c] = active ? __ldg(p.wC + ch) : 0u;
+      if (INT) {
+        const int4 r = active ? __ldg(p.ki + ch) : make_int4(0, 0, 0, 0);
+        Mi[c] = r.x; sh[c] = r.y; Bi[c] = (long long)(((unsigned long long)(uint32_t)r.w << 32) | (uint32_t)r.z); abm[c] = 0;
+      } else {
+        const float2 mb = active ? __ldg(p.mb + ch) : make_float2(0.f, 0.f);
+        Mh[c] = mb.x; Bh[c] = mb.y; abm[c] = active ? __ldg(p.abm + ch) : CDN_MAGIC_I;
+      }
+    }
+  };
+  const bool single = p.G <= Gw;
+  if (single) load_consts(wg * 32 + cl, wg * 32 + cl < p.cw_total);
+  const uint32_t so = smem_addr_u32(&s_off[0][0]);
+  pdl_wait();
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long base = tile * np;
+    __syncthreads();                           // previous tile's phase C is done with s_off (and s_thr is visible)
+    // ---------------- phase A ----------------
+    {
+      int mine = 0; int my_h = 0, my_w = 0, my_b = 0;
+      // scale-conv weights of this lane's channel words, up to 8 words (C <= 1024) in registers for the tile's pixels
+      uint32_t wsr[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) wsr[i] = lane + 32 * i < p.cw_total ? __ldg(p.ws + lane + 32 * i) : 0u;
+      const unsigned pix0 = (unsigned)base + warp;
+      int w = (int)(pix0 % (unsigned)p.Wout); unsigned t0 = pix0 / (unsigned)p.Wout;
+      int h = (int)(t0 % (unsigned)p.Hout); int b = (int)(t0 / (unsigned)p.Hout);
+      const int per_warp = np >> 3;
+#pragma unroll 1
+      for (int i = 0; i < per_warp; ++i) {
+        const long long pix = base + warp + 8 * i;
+        int part = 0;
+        if (pix < p.total) {
+          const uint32_t* c = p.in + (size_t)b * p.Hs * rs_in + (h >> p.shift) * rs_in + (w >> p.shift) * p.in_pitch_w + lane;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) if (32 * k < p.cw_total) part = dp4a_ss(lane + 32 * k < p.cw_total ? __ldg(c + 32 * k) : 0u, wsr[k], part);
+          for (int cw = lane + 256; cw < p.cw_total; cw += 32) part = dp4a_ss(__ldg(c + cw - lane), __ldg(p.ws + cw), part);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane == i) { mine = part; my_h = h; my_w = w; my_b = b; }
+        w += 8;
+        while (w >= p.Wout) { w -= p.Wout; if (++h == p.Hout) { h = 0; ++b; } }
+      }
+      if (lane < per_warp) {
+        // s = s_lo + number of thresholds <= dot product (binary search over the ascending table, padded with INT_MAX)
+        int cnt = 0;
+#pragma unroll
+        for (int step = 64; step > 0; step >>= 1) if (mine >= s_thr[cnt + step - 1]) cnt += step;
+        const int si = p.s_lo + cnt;
+        const int j = warp + 8 * lane;
+        const unsigned ob = (unsigned)(my_b * p.Hs * rs_in);
+        unsigned ro[3], co[3]; unsigned ybad = 0, xbad = 0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const int y = my_h + (i - 1) * si, xx = my_w + (i - 1) * si;
+          if ((unsigned)y >= (unsigned)p.Hin) ybad |= 1u << i;
+          if ((unsigned)xx >= (unsigned)p.Win) xbad |= 1u << i;
+          ro[i] = ob + (unsigned)((min(max(y, 0), p.Hin - 1) >> p.shift) * rs_in);
+          co[i] = (unsigned)((min(max(xx, 0), p.Win - 1) >> p.shift) * p.in_pitch_w);
+        }
+        unsigned msk = 0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int jj = 0; jj < 3; ++jj) {
+            s_off[j][i * 3 + jj] = ro[i] + co[jj];
+            if (((ybad >> i) | (xbad >> jj)) & 1u) msk |= 1u << (i * 3 + jj);
+          }
+        s_off[j][9] = msk;
+        const long long pix = base + j;
+        if (p.sval != nullptr && pix < p.total) p.sval[pix] = (float)si;
+      }
+    }
+    __syncthreads();
+    // ---------------- phase C ----------------
+    const int nvalid = (int)min((long long)np, p.total - base);
+    for (int g = wg; g < p.G; g += Gw) {
+      const int cw = g * 32 + cl;
+      const bool active = cw < p.cw_total;
+      if (!single) load_consts(cw, active);
+      const uint32_t* base_in = p.in + cw;
+      uint32_t* base_out = p.out + (size_t)base * p.out_pitch_w + cw;
+      asm volatile("" : "+l"(base_in), "+l"(base_out));    // keep them as 64-bit bases: every access is one IMAD.WIDE.U32 away
+      const int nv = active ? nvalid : 0;
+      auto fetch = [&](int j, uint32_t (&x)[9]) {
+        const uint32_t sa = so + (uint32_t)j * 48u;
+        const uint4 o0 = lds_u128(sa), o1 = lds_u128(sa + 16);
+        const uint2 o2 = lds_u64(sa + 32);     // tap 8 and the out-of-image mask
+        x[0] = __ldg(word_ptr(base_in, o0.x)); x[1] = __ldg(word_ptr(base_in, o0.y)); x[2] = __ldg(word_ptr(base_in, o0.z));
+        x[3] = __ldg(word_ptr(base_in, o0.w)); x[4] = __ldg(word_ptr(base_in, o1.x)); x[5] = __ldg(word_ptr(base_in, o1.y));
+        x[6] = __ldg(word_ptr(base_in, o1.z)); x[7] = __ldg(word_ptr(base_in, o1.w)); x[8] = __ldg(word_ptr(base_in, o2.x));
+        if (o2.y != 0u) {                       // border pixels only: out-of-image taps read real zero (q = -zx)
+#pragma unroll
+          for (int t = 0; t < 9; ++t) if ((o2.y >> t) & 1u) x[t] = p.pad_word;
+        }
+      };
+      auto compute = [&](int j, const uint32_t (&x)[9]) {
+        uint32_t a0, a1, a2, a3, b0, b1, b2, b3;
+        transpose4x4(x[0], x[1], x[2], x[3], a0, a1, a2, a3);
+        transpose4x4(x[4], x[5], x[6], x[7], b0, b1, b2, b3);
+        int acc[4];
+        acc[0] = dp4a_ss(x[8], wC[0], dp4a_ss(b0, wB[0], dp4a_ss(a0, wA[0], abm[0])));
+        acc[1] = dp4a_ss(x[8], wC[1], dp4a_ss(b1, wB[1], dp4a_ss(a1, wA[1], abm[1])));
+        acc[2] = dp4a_ss(x[8], wC[2], dp4a_ss(b2, wB[2], dp4a_ss(a2, wA[2], abm[2])));
+        acc[3] = dp4a_ss(x[8], wC[3], dp4a_ss(b3, wB[3], dp4a_ss(a3, wA[3], abm[3])));
+        uint32_t o;
+        if (INT) {
+          int q[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) q[c] = max(rq_int_wide(acc[c], Mi[c], sh[c], Bi[c]), p.lo_i);   // lo_i = -128: absorbed by the saturation
+          o = pack_sat4(q[0], q[1], q[2], q[3]);
+        } else {
+          RqGuard gd; rq_guard_init(gd);
+          uint32_t r0, r1, r2, r3;
+          rq_fast2(acc[0], acc[1], make_float2(Mh[0], Mh[1]), make_float2(Bh[0], Bh[1]), p.lo_f, gd, r0, r1);
+          rq_fast2(acc[2], acc[3], make_float2(Mh[2], Mh[3]), make_float2(Bh[2], Bh[3]), p.lo_f, gd, r2, r3);
+          o = pack4_lowbytes(r0, r1, r2, r3);
+          if (rq_group_bad(gd, p.thr_layer)) o = dw_rq_word_exact(acc[0], acc[1], acc[2], acc[3], p.M, p.B, cw * 4, p.lo_f);
+        }
+        *word_ptr(base_out, (uint32_t)j * (uint32_t)p.out_pitch_w) = o;
+      };
+      uint32_t xa[9], xb[9];
+      int j = wslot;
+      if (j < nv) fetch(j, xa);
+#pragma unroll 1
+      for (; j < nv; j += 2 * jstep) {
+        const int j1 = j + jstep, j2 = j + 2 * jstep;
+        if (j1 < nv) fetch(j1, xb);
+        compute(j, xa);
+        if (j2 < nv) fetch(j2, xa);
+        if (j1 < nv) compute(j1, xb);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------
 int dw_device_build(DwDevice& d, const int8_t* wq, const int8_t* ws, int C, int Cp, int zx, const cdn_requant* rq) {
@@ -669,9 +850,50 @@ int dw_device_build(DwDevice& d, const int8_t* wq, const int8_t* ws, int C, int 
   return dev_requant_upload(d.rq, rq, ab.data(), Cp);
 }
 
+// Integer-offset mode: the offset scalar as a step function of the scale conv's integer dot product.
+//   v = sum_c ws[c]*(q_c + zx);  u = clamp(fl(fl(v*Ms) + bs), -bound+1, bound);  qs = rint(fl(fl(ss*u) - zs));
+//   s = rint(fl(fl(qs + zs) / ss))          (dcn_deform_conv.py:295-330, quant_modules.py:648-653, DeformConvWithOffsetRound)
+// Every step is monotone non-decreasing in v (Ms, ss > 0), so s(v) = s_lo + #{k : v >= T_k}; T_k is found by bisection
+// with exactly these fp64 operations.  Stored relative to the raw dot product sum_c ws[c]*q_c the kernel accumulates.
+static inline double deform_s_of_v(long long v, const cdn_deform_scale* sc) {
+  volatile double a = (double)v * sc->Ms; volatile double u = a + sc->bs;
+  double uc = fmin(fmax((double)u, (double)(-sc->bound + 1)), (double)sc->bound);
+  volatile double m = sc->ss * uc; volatile double d = m - sc->zs;
+  const double qs = nearbyint((double)d);
+  volatile double n = qs + sc->zs; volatile double s = n / sc->ss;
+  return nearbyint((double)s);
+}
+int deform_scale_build(DwDevice& d, const cdn_deform_scale* sc, const int8_t* ws, int C, int zx) {
+  d.s_mode0_ok = 0;
+  if (sc->mode != 0) return 0;
+  CDN_CHECK(sc->Ms > 0.0 && sc->ss > 0.0 && std::isfinite(sc->bs) && std::isfinite(sc->zs), CDN_ERR_INVALID,
+            "deform: scale quantiser must have positive scales (Ms=%g ss=%g)", sc->Ms, sc->ss);
+  long long asum = 0, sum = 0;
+  for (int c = 0; c < C; ++c) { asum += ws[c] < 0 ? -ws[c] : ws[c]; sum += ws[c]; }
+  const long long A = std::max(std::abs((long long)zx - 128), std::abs((long long)zx + 127));
+  const long long vmin = -A * asum, vmax = A * asum, bias = (long long)zx * sum;
+  CDN_CHECK(vmax - bias < (1ll << 31) - 2 && vmin - bias > -(1ll << 31) + 2, CDN_ERR_INVALID, "deform: scale conv accumulator exceeds 32 bits");
+  const int s_min = (int)deform_s_of_v(vmin, sc), s_max = (int)deform_s_of_v(vmax, sc);
+  CDN_CHECK(s_max - s_min <= 127 && s_min >= -sc->bound - 1 && s_max <= sc->bound + 1, CDN_ERR_INVALID,
+            "deform: offset scalar range [%d, %d] inconsistent with bound %d", s_min, s_max, sc->bound);
+  std::vector<int32_t> thr;
+  for (int L = s_min + 1; L <= s_max; ++L) {               // smallest v with s(v) >= L
+    long long lo_v = vmin, hi_v = vmax;                    // s(lo_v) < L <= s(hi_v)
+    while (hi_v - lo_v > 1) {
+      const long long mid = lo_v + (hi_v - lo_v) / 2;
+      if (deform_s_of_v(mid, sc) >= (double)L) hi_v = mid; else lo_v = mid;
+    }
+    thr.push_back((int32_t)(hi_v - bias));
+  }
+  if (d.s_thr) { cudaFree(d.s_thr); d.s_thr = nullptr; }
+  if (dev_upload(&d.s_thr, thr.data(), thr.size())) return CDN_ERR_CUDA;
+  d.s_n = (int)thr.size(); d.s_lo = s_min; d.s_mode0_ok = 1;
+  return 0;
+}
+
 void dw_device_free(DwDevice& d) {
   cudaFree(d.wA); cudaFree(d.wB); cudaFree(d.wC); cudaFree(d.ws); dev_requant_free(d.rq);
-  cudaFree(d.wpk1); cudaFree(d.wpk2); cudaFree(d.wpku); cudaFree(d.mb); cudaFree(d.abm); cudaFree(d.ki);
+  cudaFree(d.wpk1); cudaFree(d.wpk2); cudaFree(d.wpku); cudaFree(d.mb); cudaFree(d.abm); cudaFree(d.ki); cudaFree(d.s_thr);
   d = DwDevice();
 }
 
@@ -757,8 +979,16 @@ int deform_launch(const DwDevice& d, const cdn_deform_scale* sc, const int8_t* i
   if (p.total == 0) return 0;
   CDN_CHECK((long long)batch * p.Hs * p.Ws * p.in_pitch_w < (1ll << 31) && p.total < (1ll << 31) && p.Hout < 65536 && p.Wout < 65536,
             CDN_ERR_INVALID, "deform: tensor too large for 32-bit indexing");
-  const long long ntiles = (p.total + DEF_NP - 1) / DEF_NP;
-  const long long cap = (long long)cdn_num_sms() * 8;
+  // v3 tile size: at least ~3 tiles per CTA slot, and wide layers (8 channel groups per pixel) keep small tiles
+  p.np = DEF_NP;
+  if (sc->mode == 0) {
+    const long long slots = (long long)cdn_num_sms() * DEF3_CTAS;
+    const int want = p.G >= 8 ? 64 : (p.G >= 4 ? 128 : DEF3_MAX_NP);
+    p.np = want;
+    while (p.np > 64 && (p.total + p.np - 1) / p.np < 3 * slots) p.np >>= 1;
+  }
+  const long long ntiles = (p.total + p.np - 1) / p.np;
+  const long long cap = (long long)cdn_num_sms() * (sc->mode == 0 ? DEF3_CTAS : 8);
   const unsigned blocks = (unsigned)std::min(ntiles, cap);
   cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(256); cfg.stream = st;
@@ -766,9 +996,12 @@ int deform_launch(const DwDevice& d, const cdn_deform_scale* sc, const int8_t* i
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = (g_cdn_debug_flags & 64u) ? 0 : 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  if (sc->mode == 0 && d.use_int) CDN_CUDA(cudaLaunchKernelEx(&cfg, deform_dw_v2_kernel<0, true>, p));
-  else if (sc->mode == 0) CDN_CUDA(cudaLaunchKernelEx(&cfg, deform_dw_v2_kernel<0, false>, p));
-  else CDN_CUDA(cudaLaunchKernelEx(&cfg, deform_dw_v2_kernel<1, false>, p));
+  if (sc->mode == 0) {
+    CDN_CHECK(d.s_thr != nullptr && d.s_mode0_ok, CDN_ERR_STATE, "deform: integer-offset thresholds were not built (deform_scale_build)");
+    p.s_thr = d.s_thr; p.s_n = d.s_n; p.s_lo = d.s_lo;
+    if (d.use_int) CDN_CUDA(cudaLaunchKernelEx(&cfg, deform_int_v3_kernel<true>, p));
+    else CDN_CUDA(cudaLaunchKernelEx(&cfg, deform_int_v3_kernel<false>, p));
+  } else CDN_CUDA(cudaLaunchKernelEx(&cfg, deform_dw_v2_kernel<1, false>, p));
   CDN_LAUNCH_CHECK("deform_dw_v2_kernel");
   return 0;
 }

@@ -189,6 +189,7 @@ extern "C" int cdn_deform_dw_w4a8(const int8_t* d_in, int in_pitch, int batch, i
   DwDevice d{};
   int Cp = std::min(in_pitch, out_pitch);
   int r = dw_device_build(d, wq, sc->ws, C, Cp, zx, rq);
+  if (!r) r = deform_scale_build(d, sc, sc->ws, C, zx);
   if (!r) r = deform_launch(d, sc, d_in, in_pitch, d_out, out_pitch, batch, H, W, in_shift, zx, d_sval, (cudaStream_t)stream);
   cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
   if (!r && e != cudaSuccess) r = cdn_fail(CDN_ERR_CUDA, "deform: %s", cudaGetErrorString(e));
@@ -222,6 +223,7 @@ extern "C" int cdn_deform_layer_create(cdn_deform_layer** out, const cdn_deform_
   L->C = C; L->Cp = pitch; L->zx = zx; L->device = dev;
   L->sc = *sc; L->ws.assign(sc->ws, sc->ws + C); L->sc.ws = L->ws.data();
   if (int r = dw_device_build(L->dw, wq, sc->ws, C, pitch, zx, rq)) { delete L; return r; }
+  if (int r = deform_scale_build(L->dw, &L->sc, L->ws.data(), C, zx)) { dw_device_free(L->dw); delete L; return r; }
   *out = L;
   return 0;
 }
@@ -405,6 +407,7 @@ extern "C" int cdn_engine_add_deform(cdn_engine* e, int in_t, int out_t, int in_
   op->kind = 2; op->in_t = in_t; op->out_t = out_t; op->in_shift = in_shift; op->stride = 1; op->zx = zx; op->H = H; op->W = W;
   op->sc = *sc; op->ws_host.assign(sc->ws, sc->ws + C); op->sc.ws = op->ws_host.data();
   if (int r = dw_device_build(op->dw, wq, sc->ws, C, std::min(ti.pitch, to.pitch), zx, rq)) { delete op; return r; }
+  if (int r = deform_scale_build(op->dw, &op->sc, op->ws_host.data(), C, zx)) { dw_device_free(op->dw); delete op; return r; }
   e->ops.push_back(op);
   return 0;
 }

@@ -7,11 +7,13 @@ struct DwDevice {                            // depthwise / deformable layer con
   uint32_t *wpk1 = nullptr, *wpk2 = nullptr, *wpku = nullptr;   // v2 packings: stride 1, stride 2, upsample-folded
   float2* mb = nullptr; int32_t* abm = nullptr; float thr = 0.5f, thr_bil = 0.01f; int u_ok = 1;
   RqInt* ki = nullptr; int use_int = 0;        // exact integer requantisation constants (acc_bias folded in)
+  int32_t* s_thr = nullptr; int s_n = 0, s_lo = 0, s_mode0_ok = 0;   // integer-offset mode: thresholds of s over the scale conv's dot product
   DevRequant rq;
   int cw_total = 0;
   long long acc_s_bias = 0;
 };
 int dw_device_build(DwDevice& d, const int8_t* wq, const int8_t* ws, int C, int Cp, int zx, const cdn_requant* rq);
+int deform_scale_build(DwDevice& d, const cdn_deform_scale* sc, const int8_t* ws, int C, int zx);   // after dw_device_build, deformable layers
 void dw_device_free(DwDevice& d);
 int dw_launch(const DwDevice& d, const int8_t* in, int in_pitch, int8_t* out, int out_pitch, int batch, int H, int W,
               int in_shift, int stride, int zx, cudaStream_t st);
