@@ -632,30 +632,56 @@ __global__ void __launch_bounds__(256, DEF3_CTAS) deform_int_v3_kernel(const DwP
     __syncthreads();                           // previous tile's phase C is done with s_off (and s_thr is visible)
     // ---------------- phase A ----------------
     {
-      int mine = 0; int my_h = 0, my_w = 0, my_b = 0;
-      // scale-conv weights of this lane's channel words, up to 8 words (C <= 1024) in registers for the tile's pixels
-      uint32_t wsr[8];
+      // Lane i of a warp OWNS pixel j = warp + 8 i of the tile (coordinates, offset scalar, tap offsets).  The dot
+      // products are formed 8 pixels at a time so that 8 independent loads are in flight per lane (the one-pixel-at-a-time
+      // version spent a quarter of the kernel's stall samples on its first dp4a), and reduced with a value-halving
+      // butterfly: 4 + 2 + 1 + 1 + 1 shuffles for 8 pixels instead of 8 x 5.
+      const int per_warp = np >> 3;
+      int my_h = 0, my_w = 0; unsigned my_ob = 0, coff = 0;
+      if (lane < per_warp) {
+        const long long pix = base + warp + 8 * lane;
+        if (pix < p.total) {
+          const unsigned pp = (unsigned)pix;
+          my_w = (int)(pp % (unsigned)p.Wout); const unsigned t0 = pp / (unsigned)p.Wout;
+          my_h = (int)(t0 % (unsigned)p.Hout);
+          my_ob = (t0 / (unsigned)p.Hout) * (unsigned)(p.Hs * rs_in);
+          coff = my_ob + (unsigned)((my_h >> p.shift) * rs_in + (my_w >> p.shift) * p.in_pitch_w);
+        }
+      }
+      uint32_t wsr[8];                         // scale-conv weights of this lane's channel words (C <= 1024 in registers)
 #pragma unroll
       for (int i = 0; i < 8; ++i) wsr[i] = lane + 32 * i < p.cw_total ? __ldg(p.ws + lane + 32 * i) : 0u;
-      const unsigned pix0 = (unsigned)base + warp;
-      int w = (int)(pix0 % (unsigned)p.Wout); unsigned t0 = pix0 / (unsigned)p.Wout;
-      int h = (int)(t0 % (unsigned)p.Hout); int b = (int)(t0 / (unsigned)p.Hout);
-      const int per_warp = np >> 3;
+      int mine = 0;
+      const uint32_t* const in_l = p.in + lane;
 #pragma unroll 1
-      for (int i = 0; i < per_warp; ++i) {
-        const long long pix = base + warp + 8 * i;
-        int part = 0;
-        if (pix < p.total) {
-          const uint32_t* c = p.in + (size_t)b * p.Hs * rs_in + (h >> p.shift) * rs_in + (w >> p.shift) * p.in_pitch_w + lane;
+      for (int bt = 0; bt < (per_warp >> 3); ++bt) {
+        unsigned ob[8]; int part[8];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) if (32 * k < p.cw_total) part = dp4a_ss(lane + 32 * k < p.cw_total ? __ldg(c + 32 * k) : 0u, wsr[k], part);
-          for (int cw = lane + 256; cw < p.cw_total; cw += 32) part = dp4a_ss(__ldg(c + cw - lane), __ldg(p.ws + cw), part);
+        for (int b = 0; b < 8; ++b) { ob[b] = __shfl_sync(0xffffffffu, coff, 8 * bt + b); part[b] = 0; }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (32 * k < p.cw_total) {
+            const bool on = lane + 32 * k < p.cw_total;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) part[b] = dp4a_ss(on ? __ldg(word_ptr(in_l, ob[b] + 32u * k)) : 0u, wsr[k], part[b]);
+          }
+        for (int cw = lane + 256; cw < p.cw_total; cw += 32) {
+          const uint32_t wv = __ldg(p.ws + cw);
+#pragma unroll
+          for (int b = 0; b < 8; ++b) part[b] = dp4a_ss(__ldg(word_ptr(p.in, ob[b] + (unsigned)cw)), wv, part[b]);
         }
+        const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+        int u[4], t[2];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-        if (lane == i) { mine = part; my_h = h; my_w = w; my_b = b; }
-        w += 8;
-        while (w >= p.Wout) { w -= p.Wout; if (++h == p.Hout) { h = 0; ++b; } }
+        for (int i = 0; i < 4; ++i) u[i] = (b4 ? part[i + 4] : part[i]) + __shfl_xor_sync(0xffffffffu, b4 ? part[i] : part[i + 4], 16);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) t[i] = (b3 ? u[i + 2] : u[i]) + __shfl_xor_sync(0xffffffffu, b3 ? u[i] : u[i + 2], 8);
+        int r = (b2 ? t[1] : t[0]) + __shfl_xor_sync(0xffffffffu, b2 ? t[0] : t[1], 4);
+        r += __shfl_xor_sync(0xffffffffu, r, 2);
+        r += __shfl_xor_sync(0xffffffffu, r, 1);
+        // lanes 4m .. 4m+3 now hold the dot product of the batch's pixel m, m = 4 b4 + 2 b3 + b2; hand it to its owner
+        const int got = __shfl_sync(0xffffffffu, r, 4 * (lane & 7));
+        if ((lane >> 3) == bt) mine = got;
       }
       if (lane < per_warp) {
         // s = s_lo + number of thresholds <= dot product (binary search over the ascending table, padded with INT_MAX)
@@ -664,7 +690,7 @@ __global__ void __launch_bounds__(256, DEF3_CTAS) deform_int_v3_kernel(const DwP
         for (int step = 64; step > 0; step >>= 1) if (mine >= s_thr[cnt + step - 1]) cnt += step;
         const int si = p.s_lo + cnt;
         const int j = warp + 8 * lane;
-        const unsigned ob = (unsigned)(my_b * p.Hs * rs_in);
+        const unsigned ob = my_ob;
         unsigned ro[3], co[3]; unsigned ybad = 0, xbad = 0;
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
