@@ -156,6 +156,13 @@ __device__ __forceinline__ const uint32_t* word_ptr(const uint32_t* base, uint32
 __device__ __forceinline__ uint32_t* word_ptr(uint32_t* base, uint32_t off) {
   return const_cast<uint32_t*>(word_ptr((const uint32_t*)base, off));
 }
+// word `off` of the array whose 64-bit address is (hi:lo): one IMAD.WIDE.U32 on the FMA pipe
+__device__ __forceinline__ const uint32_t* word_ptr64(uint32_t lo, uint32_t hi, uint32_t off) {
+  unsigned long long b, r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "r"(lo), "r"(hi));
+  asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(r) : "r"(off), "l"(b));
+  return (const uint32_t*)r;
+}
 __device__ __forceinline__ uint4 lds_u128(uint32_t saddr) {
   uint4 r; asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(saddr)); return r;
 }

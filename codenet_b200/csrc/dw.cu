@@ -33,7 +33,7 @@ struct DwParams {
   const float2* mb; const int* abm; float thr_layer;   // lean requantisation constants (v2 kernels)
   float thr_bil;                             // guard of the fp32 bilinear fast path (0.5 - eps, host-derived bound)
   const int4* ki; int lo_i;                  // integer requantisation (RqInt per channel, acc_bias folded in)
-  int np;                                    // v3: pixels per tile
+  int np; const uint32_t* pad_px;            // v3: pixels per tile; a pixel of pad words (q = -zx in every channel)
   const int* s_thr; int s_n, s_lo;           // integer offsets (v3): s = s_lo + #{k : acc_s >= s_thr[k]}, thresholds ascending
 };
 
@@ -591,10 +591,14 @@ __global__ void __launch_bounds__(256, MODE == 0 ? 4 : 3) deform_dw_v2_kernel(co
 // p.np = pixels per tile (64, 128 or 256; a multiple of 8): wide layers (many channel groups per pixel) take small tiles
 // for load balance, narrow ones large tiles so that the per-tile work (constants, barriers, the per-pixel scalar code that
 // runs on np/8 lanes of every warp) is amortised over 32 pixels per warp.
-template <bool INT>
+// RQ: 0 = guarded fp32 requantisation, 1 = integer, 2 = integer with an explicit lower clamp (lo > -128)
+template <int RQ>
 __global__ void __launch_bounds__(256, DEF3_CTAS) deform_int_v3_kernel(const DwParams p) {
+  constexpr bool INT = RQ != 0;
   pdl_launch_dependents();
-  __shared__ __align__(16) uint32_t s_off[DEF3_MAX_NP][12];   // word offsets of taps 0..8, out-of-image mask, 2 pad words
+  // per pixel: the addresses of channel word 0 of the 9 taps (out-of-image taps point at the layer's pad pixel, which
+  // holds q = -zx, i.e. real zero: no select and no mask in the gather loop), padded to 80 bytes
+  __shared__ __align__(16) unsigned long long s_ptr[DEF3_MAX_NP][10];
   __shared__ int s_thr[128];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rs_in = p.Ws * p.in_pitch_w;
@@ -615,8 +619,12 @@ __global__ void __launch_bounds__(256, DEF3_CTAS) deform_int_v3_kernel(const DwP
       const int ch = cw * 4 + c;
       wA[c] = active ? __ldg(p.wA + ch) : 0u; wB[c] = active ? __ldg(p.wB + ch) : 0u; wC[c] = active ? __ldg(p.wC + ch) : 0u;
       if (INT) {
-        const int4 r = active ? __ldg(p.ki + ch) : make_int4(0, 0, 0, 0);
-        Mi[c] = r.x; sh[c] = r.y; Bi[c] = (long long)(((unsigned long long)(uint32_t)r.w << 32) | (uint32_t)r.z); abm[c] = 0;
+        // Unconditional loads (inactive lanes read the last channel word's constants and never store): a select on these
+        // values hides the sign extensions from the compiler, which then expands the 32 x 32 + 64 multiply-add of
+        // rq_int into a generic 64 x 64-bit product (six instructions instead of one IMAD.HI).
+        const int chv = min(cw, p.cw_total - 1) * 4 + c;
+        const int2 ms = __ldg(reinterpret_cast<const int2*>(p.ki + chv));
+        Mi[c] = ms.x; sh[c] = ms.y; Bi[c] = __ldg(reinterpret_cast<const long long*>(p.ki + chv) + 1); abm[c] = 0;
       } else {
         const float2 mb = active ? __ldg(p.mb + ch) : make_float2(0.f, 0.f);
         Mh[c] = mb.x; Bh[c] = mb.y; abm[c] = active ? __ldg(p.abm + ch) : CDN_MAGIC_I;
@@ -625,11 +633,12 @@ __global__ void __launch_bounds__(256, DEF3_CTAS) deform_int_v3_kernel(const DwP
   };
   const bool single = p.G <= Gw;
   if (single) load_consts(wg * 32 + cl, wg * 32 + cl < p.cw_total);
-  const uint32_t so = smem_addr_u32(&s_off[0][0]);
+  uint32_t so = smem_addr_u32(&s_ptr[0][0]);
+  asm volatile("" : "+r"(so));                 // opaque: otherwise the shared-window base is rematerialised in every iteration
   pdl_wait();
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long long base = tile * np;
-    __syncthreads();                           // previous tile's phase C is done with s_off (and s_thr is visible)
+    __syncthreads();                           // previous tile's phase C is done with s_ptr (and s_thr is visible)
     // ---------------- phase A ----------------
     {
       // Lane i of a warp OWNS pixel j = warp + 8 i of the tile (coordinates, offset scalar, tap offsets).  The dot
@@ -700,15 +709,13 @@ __global__ void __launch_bounds__(256, DEF3_CTAS) deform_int_v3_kernel(const DwP
           ro[i] = ob + (unsigned)((min(max(y, 0), p.Hin - 1) >> p.shift) * rs_in);
           co[i] = (unsigned)((min(max(xx, 0), p.Win - 1) >> p.shift) * p.in_pitch_w);
         }
-        unsigned msk = 0;
 #pragma unroll
         for (int i = 0; i < 3; ++i)
 #pragma unroll
           for (int jj = 0; jj < 3; ++jj) {
-            s_off[j][i * 3 + jj] = ro[i] + co[jj];
-            if (((ybad >> i) | (xbad >> jj)) & 1u) msk |= 1u << (i * 3 + jj);
+            const bool bad = ((ybad >> i) | (xbad >> jj)) & 1u;
+            s_ptr[j][i * 3 + jj] = bad ? (unsigned long long)p.pad_px : (unsigned long long)(p.in + (ro[i] + co[jj]));
           }
-        s_off[j][9] = msk;
         const long long pix = base + j;
         if (p.sval != nullptr && pix < p.total) p.sval[pix] = (float)si;
       }
@@ -720,21 +727,17 @@ __global__ void __launch_bounds__(256, DEF3_CTAS) deform_int_v3_kernel(const DwP
       const int cw = g * 32 + cl;
       const bool active = cw < p.cw_total;
       if (!single) load_consts(cw, active);
-      const uint32_t* base_in = p.in + cw;
       uint32_t* base_out = p.out + (size_t)base * p.out_pitch_w + cw;
-      asm volatile("" : "+l"(base_in), "+l"(base_out));    // keep them as 64-bit bases: every access is one IMAD.WIDE.U32 away
+      asm volatile("" : "+l"(base_out));       // keep it a 64-bit base: the store address is one IMAD.WIDE.U32 away
       const int nv = active ? nvalid : 0;
+      const uint32_t cwu = (uint32_t)cw;
       auto fetch = [&](int j, uint32_t (&x)[9]) {
-        const uint32_t sa = so + (uint32_t)j * 48u;
-        const uint4 o0 = lds_u128(sa), o1 = lds_u128(sa + 16);
-        const uint2 o2 = lds_u64(sa + 32);     // tap 8 and the out-of-image mask
-        x[0] = __ldg(word_ptr(base_in, o0.x)); x[1] = __ldg(word_ptr(base_in, o0.y)); x[2] = __ldg(word_ptr(base_in, o0.z));
-        x[3] = __ldg(word_ptr(base_in, o0.w)); x[4] = __ldg(word_ptr(base_in, o1.x)); x[5] = __ldg(word_ptr(base_in, o1.y));
-        x[6] = __ldg(word_ptr(base_in, o1.z)); x[7] = __ldg(word_ptr(base_in, o1.w)); x[8] = __ldg(word_ptr(base_in, o2.x));
-        if (o2.y != 0u) {                       // border pixels only: out-of-image taps read real zero (q = -zx)
-#pragma unroll
-          for (int t = 0; t < 9; ++t) if ((o2.y >> t) & 1u) x[t] = p.pad_word;
-        }
+        const uint32_t sa = so + (uint32_t)j * 80u;
+        const uint4 q0 = lds_u128(sa), q1 = lds_u128(sa + 16), q2 = lds_u128(sa + 32), q3 = lds_u128(sa + 48);
+        const uint2 q4 = lds_u64(sa + 64);
+        x[0] = __ldg(word_ptr64(q0.x, q0.y, cwu)); x[1] = __ldg(word_ptr64(q0.z, q0.w, cwu)); x[2] = __ldg(word_ptr64(q1.x, q1.y, cwu));
+        x[3] = __ldg(word_ptr64(q1.z, q1.w, cwu)); x[4] = __ldg(word_ptr64(q2.x, q2.y, cwu)); x[5] = __ldg(word_ptr64(q2.z, q2.w, cwu));
+        x[6] = __ldg(word_ptr64(q3.x, q3.y, cwu)); x[7] = __ldg(word_ptr64(q3.z, q3.w, cwu)); x[8] = __ldg(word_ptr64(q4.x, q4.y, cwu));
       };
       auto compute = [&](int j, const uint32_t (&x)[9]) {
         uint32_t a0, a1, a2, a3, b0, b1, b2, b3;
@@ -749,7 +752,7 @@ __global__ void __launch_bounds__(256, DEF3_CTAS) deform_int_v3_kernel(const DwP
         if (INT) {
           int q[4];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) q[c] = max(rq_int_wide(acc[c], Mi[c], sh[c], Bi[c]), p.lo_i);   // lo_i = -128: absorbed by the saturation
+          for (int c = 0; c < 4; ++c) { q[c] = rq_int(acc[c], Mi[c], sh[c], Bi[c]); if (RQ == 2) q[c] = max(q[c], p.lo_i); }
           o = pack_sat4(q[0], q[1], q[2], q[3]);
         } else {
           RqGuard gd; rq_guard_init(gd);
@@ -912,6 +915,11 @@ int deform_scale_build(DwDevice& d, const cdn_deform_scale* sc, const int8_t* ws
     thr.push_back((int32_t)(hi_v - bias));
   }
   if (d.s_thr) { cudaFree(d.s_thr); d.s_thr = nullptr; }
+  if (d.pad_px) { cudaFree(d.pad_px); d.pad_px = nullptr; }
+  {                                                        // the pad pixel out-of-image taps are redirected to
+    std::vector<uint32_t> pad((size_t)d.cw_total, (uint32_t)(uint8_t)(int8_t)(-zx) * 0x01010101u);
+    if (dev_upload(&d.pad_px, pad.data(), pad.size())) return CDN_ERR_CUDA;
+  }
   if (dev_upload(&d.s_thr, thr.data(), thr.size())) return CDN_ERR_CUDA;
   d.s_n = (int)thr.size(); d.s_lo = s_min; d.s_mode0_ok = 1;
   return 0;
@@ -919,7 +927,7 @@ int deform_scale_build(DwDevice& d, const cdn_deform_scale* sc, const int8_t* ws
 
 void dw_device_free(DwDevice& d) {
   cudaFree(d.wA); cudaFree(d.wB); cudaFree(d.wC); cudaFree(d.ws); dev_requant_free(d.rq);
-  cudaFree(d.wpk1); cudaFree(d.wpk2); cudaFree(d.wpku); cudaFree(d.mb); cudaFree(d.abm); cudaFree(d.ki); cudaFree(d.s_thr);
+  cudaFree(d.wpk1); cudaFree(d.wpk2); cudaFree(d.wpku); cudaFree(d.mb); cudaFree(d.abm); cudaFree(d.ki); cudaFree(d.s_thr); cudaFree(d.pad_px);
   d = DwDevice();
 }
 
@@ -1025,8 +1033,10 @@ int deform_launch(const DwDevice& d, const cdn_deform_scale* sc, const int8_t* i
   if (sc->mode == 0) {
     CDN_CHECK(d.s_thr != nullptr && d.s_mode0_ok, CDN_ERR_STATE, "deform: integer-offset thresholds were not built (deform_scale_build)");
     p.s_thr = d.s_thr; p.s_n = d.s_n; p.s_lo = d.s_lo;
-    if (d.use_int) CDN_CUDA(cudaLaunchKernelEx(&cfg, deform_int_v3_kernel<true>, p));
-    else CDN_CUDA(cudaLaunchKernelEx(&cfg, deform_int_v3_kernel<false>, p));
+    p.pad_px = d.pad_px;
+    if (!d.use_int) CDN_CUDA(cudaLaunchKernelEx(&cfg, deform_int_v3_kernel<0>, p));
+    else if (d.rq.lo > -128) CDN_CUDA(cudaLaunchKernelEx(&cfg, deform_int_v3_kernel<2>, p));
+    else CDN_CUDA(cudaLaunchKernelEx(&cfg, deform_int_v3_kernel<1>, p));
   } else CDN_CUDA(cudaLaunchKernelEx(&cfg, deform_dw_v2_kernel<1, false>, p));
   CDN_LAUNCH_CHECK("deform_dw_v2_kernel");
   return 0;

@@ -7,6 +7,7 @@ struct DwDevice {                            // depthwise / deformable layer con
   uint32_t *wpk1 = nullptr, *wpk2 = nullptr, *wpku = nullptr;   // v2 packings: stride 1, stride 2, upsample-folded
   float2* mb = nullptr; int32_t* abm = nullptr; float thr = 0.5f, thr_bil = 0.01f; int u_ok = 1;
   RqInt* ki = nullptr; int use_int = 0;        // exact integer requantisation constants (acc_bias folded in)
+  uint32_t* pad_px = nullptr;                  // integer-offset mode: one pixel of pad words (q = -zx), the target of out-of-image taps
   int32_t* s_thr = nullptr; int s_n = 0, s_lo = 0, s_mode0_ok = 0;   // integer-offset mode: thresholds of s over the scale conv's dot product
   DevRequant rq;
   int cw_total = 0;
