@@ -23,11 +23,12 @@ def needs_build():
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
+    extra = os.environ.get("CDN_NVCC_EXTRA", "").split()      # experiments only (e.g. -DPW_EPI_WARPS=8)
     objs = []
     logs = []
     for src in SOURCES:
         obj = os.path.join(CSRC, src.replace(".cu", ".o"))
-        cmd = [NVCC] + FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [NVCC] + FLAGS + extra + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         logs.append(r.stderr)
         if r.returncode != 0:
