@@ -94,7 +94,9 @@ def op_bytes(plan, op, batch):
 
 
 def family(op):
-    return {"pw": "pw_gemm_tc_kernel", "dw": "dw3x3_v2_kernel", "deform": "deform_dw_v2_kernel", "stem": "stem_kernel"}[op.kind]
+    if op.kind == "deform":                      # integer offsets: v3 kernel; bilinear: v2 kernel with the guarded fp32 blend
+        return "deform_int_v3_kernel" if op.a.get("mode", 0) == 0 else "deform_dw_v2_kernel"
+    return {"pw": "pw_gemm_tc_kernel", "dw": "dw3x3_v2_kernel", "stem": "stem_kernel"}[op.kind]
 
 
 def ncu_traffic():
@@ -243,8 +245,8 @@ def run_ours(args):
                 "families": {k: {"ms": round(v, 4), "GBps": round(fam_bytes[k] / v / 1e6, 1), "share": round(v / total_ms, 3)}
                              for k, v in sorted(fam_ms.items(), key=lambda kv: -kv[1])}}
     dby = sum(op_bytes(eng.plan, op, B) for op in eng.plan.ops if op.kind == "deform")
-    deform = {"GBps": round(dby / fam_ms["deform_dw_v2_kernel"] / 1e6, 1), "frac_of_hbm_peak": round(dby / fam_ms["deform_dw_v2_kernel"] / 1e6 / peak, 4),
-              "layers": deform_layers}
+    dms = sum(v for k, v in fam_ms.items() if k.startswith("deform_"))
+    deform = {"GBps": round(dby / dms / 1e6, 1), "frac_of_hbm_peak": round(dby / dms / 1e6 / peak, 4), "layers": deform_layers}
     cpu = None if args.no_cpu else cpu_baseline(args, sample_images=1)
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,

@@ -106,5 +106,5 @@ def full(kernel):
 
 if __name__ == "__main__":
     launch_list()
-    for k in ("pw_gemm_tc", "deform_dw_v2", "dw3x3_v2"):
+    for k in ("pw_gemm_tc", "deform_int_v3", "dw3x3_v2"):
         full(k)
