@@ -25,7 +25,9 @@
 #ifndef PW_EPI_WARPS
 #define PW_EPI_WARPS 16
 #endif
+#ifndef PW_EPI_GROUPS
 #define PW_EPI_GROUPS 2                      // independent epilogue groups working on alternate tiles (antiphase)
+#endif
 #define PW_GROUP_THREADS (32 * PW_EPI_WARPS / PW_EPI_GROUPS)
 #define PW_EPI_PARTS (PW_EPI_WARPS / PW_EPI_GROUPS / 4)
 #define PW_EPI_THREADS (32 * PW_EPI_WARPS)
