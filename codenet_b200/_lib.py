@@ -62,6 +62,8 @@ EXPORTS = {
     "cdn_ctdet_decode_prob": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_void_p, C.c_void_p, C.c_void_p]),
     "cdn_ctdet_post_affine": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "cdn_ctdet_flip_merge": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]),
     "cdn_deform_conv_forward_f32": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 16 + [C.c_void_p]),
     "cdn_deform_dw_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                     C.c_int, C.c_int, C.c_int, C.c_void_p]),

@@ -189,11 +189,19 @@ class CtdetDetector:
             output = {h: out[h] for h in self.opt.heads}
             dets = out["dets"] if self.opt.reg_offset else ctdet_decode(out["hm"], out["wh"], reg=None, K=self.opt.K)
         else:
+            # image + mirrored image: average hm and wh with the mirror flipped back (ctdet.py:35-38), on the device
+            import ctypes as C
+            from .. import _lib
             out = eng.run(x, maps=True, dets=False)
             output = {h: out[h] for h in self.opt.heads}
-            hm, wh = out["hm"], out["wh"]
-            hm = (hm[0:1] + torch.flip(hm[1:2], [3])) / 2
-            wh = (wh[0:1] + torch.flip(wh[1:2], [3])) / 2
+            pairs = B // 2
+            hm = torch.empty((pairs,) + tuple(out["hm"].shape[1:]), dtype=torch.float32, device=images.device)
+            wh = torch.empty((pairs,) + tuple(out["wh"].shape[1:]), dtype=torch.float32, device=images.device)
+            with torch.cuda.device(images.device):
+                _lib.check(_lib.load().cdn_ctdet_flip_merge(
+                    C.c_void_p(out["hm"].data_ptr()), C.c_void_p(out["wh"].data_ptr()), pairs, hm.shape[1], hm.shape[2], hm.shape[3],
+                    C.c_void_p(hm.data_ptr()), C.c_void_p(wh.data_ptr()),
+                    C.c_void_p(torch.cuda.current_stream(images.device).cuda_stream)))
             reg = out["reg"][0:1] if self.opt.reg_offset else None
             torch.cuda.synchronize(images.device)
             forward_time = time.time()

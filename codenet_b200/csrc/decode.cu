@@ -308,3 +308,34 @@ extern "C" int cdn_ctdet_post_affine(float* d_dets, int batch, int K, const doub
   CDN_CHECK(e == cudaSuccess, CDN_ERR_CUDA, "post_affine: %s", cudaGetErrorString(e));
   return 0;
 }
+
+// ---- flip-test merge (lib/detectors/ctdet.py:35-38) --------------------------------------------------------------
+// out[i][c][y][x] = (in[2i][c][y][x] + in[2i+1][c][y][W-1-x]) / 2 in fp32: the reference's
+// (hm[0:1] + flip_tensor(hm[1:2])) / 2 for the image and its mirror (one add, one exact halving).
+__global__ void ctdet_flip_merge_kernel(const float* __restrict__ in, float* __restrict__ out, int planes, int H, int W, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int x = (int)(idx % W); long long t = idx / W;
+  const int y = (int)(t % H); t /= H;
+  const int c = (int)(t % planes); const long long i = t / planes;
+  const size_t plane = (size_t)H * W;
+  const float a = in[((size_t)(2 * i) * planes + c) * plane + (size_t)y * W + x];
+  const float b = in[((size_t)(2 * i + 1) * planes + c) * plane + (size_t)y * W + (W - 1 - x)];
+  out[idx] = __fdiv_rn(__fadd_rn(a, b), 2.0f);
+}
+
+extern "C" int cdn_ctdet_flip_merge(const float* d_hm, const float* d_wh, int pairs, int cat, int H, int W, float* d_out_hm,
+                                    float* d_out_wh, cdn_stream_t stream) {
+  CDN_CHECK(d_hm && d_out_hm && pairs >= 0 && cat >= 1 && H >= 1 && W >= 1, CDN_ERR_INVALID, "flip_merge: bad arguments");
+  CDN_CHECK((d_wh == nullptr) == (d_out_wh == nullptr), CDN_ERR_INVALID, "flip_merge: wh input and output must both be given or both be null");
+  if (pairs == 0) return 0;
+  long long total = (long long)pairs * cat * H * W;
+  ctdet_flip_merge_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_hm, d_out_hm, cat, H, W, total);
+  CDN_LAUNCH_CHECK("ctdet_flip_merge_kernel");
+  if (d_wh) {
+    total = (long long)pairs * 2 * H * W;
+    ctdet_flip_merge_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_wh, d_out_wh, 2, H, W, total);
+    CDN_LAUNCH_CHECK("ctdet_flip_merge_kernel");
+  }
+  return 0;
+}

@@ -164,6 +164,12 @@ int cdn_ctdet_decode_prob(const float* d_heat, const float* d_wh, const float* d
  * np.dot(t, [x, y, 1]) in double and rounded once to float.  Synchronises the stream. */
 int cdn_ctdet_post_affine(float* d_dets, int batch, int K, const double* h_trans, cdn_stream_t stream);
 
+/* --flip_test merge of CtdetDetector.process (lib/detectors/ctdet.py:35-38): inputs hold `pairs` (image, mirrored image)
+ * couples, hm [2*pairs][cat][H][W] (post-sigmoid) and wh [2*pairs][2][H][W]; out[i] = (in[2i] + flip_W(in[2i+1])) / 2 in fp32,
+ * exactly the reference's expression.  reg is taken from the unflipped image by the caller (ctdet.py:38).  Asynchronous. */
+int cdn_ctdet_flip_merge(const float* d_hm, const float* d_wh, int pairs, int cat, int H, int W, float* d_out_hm,
+                         float* d_out_wh, cdn_stream_t stream);
+
 /* ---- general deformable convolution forward, fp32 (the reference's native plug-in point) ----------------
  * Same argument meaning and order (W before H) as deform_conv_forward_cuda; tensors are contiguous NCHW device
  * pointers: input [B][C][H][W], weight [Co][C/group][kH][kW], offset [B][2*kH*kW*dg][Ho][Wo], output [B][Co][Ho][Wo].
