@@ -102,6 +102,11 @@ __device__ __forceinline__ float2 cdn_fadd2(float2 a, float2 b) {
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
   return *reinterpret_cast<float2*>(&r);
 }
+__device__ __forceinline__ float2 cdn_fmul2(float2 a, float2 b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+  return *reinterpret_cast<float2*>(&r);
+}
 __device__ __forceinline__ float2 cdn_ffma2(float2 a, float2 b, float2 c) {
   unsigned long long r;
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(*reinterpret_cast<unsigned long long*>(&a)),

@@ -510,7 +510,10 @@ __global__ void __launch_bounds__(256, MODE == 0 ? 4 : 3) deform_dw_v2_kernel(co
             cv[q] = (unsigned)Cc[q] < (unsigned)p.Win;
             co[q] = (unsigned)((min(max(Cc[q], 0), p.Win - 1) >> p.shift) * p.in_pitch_w);
           }
-          float acc[4] = {0.f, 0.f, 0.f, 0.f};
+          // Two channels per FMA-pipe instruction (Blackwell's packed f32x2 add / mul / fma): per lane the operations and
+          // their order are exactly those of the scalar form (mul, then fma ...), so the error bound above is unchanged.
+          float2 acc2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+          const float2 nunb = make_float2(-unb, -unb);
 #pragma unroll
           for (int r = 0; r < 5; ++r) {
             const bool rv = (unsigned)R[r] < (unsigned)p.Hin;
@@ -521,16 +524,24 @@ __global__ void __launch_bounds__(256, MODE == 0 ? 4 : 3) deform_dw_v2_kernel(co
 #pragma unroll
             for (int q = 0; q < 5; ++q) xw[q] = ((rv && cv[q]) ? xw[q] : p.pad_word) ^ 0x80808080u;
             const int ti = r < 2 ? 0 : (r == 2 ? 1 : 2);                     // tap row fed by this lattice row
+            const float2 rho2 = make_float2(rho[r], rho[r]);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              float a[5];
+            for (int cp = 0; cp < 2; ++cp) {
+              const int c = 2 * cp;
+              float2 a[5];
 #pragma unroll
-              for (int q = 0; q < 5; ++q) a[q] = __uint_as_float(__byte_perm(xw[q], 0x4B000000u, 0x7650 + c)) - unb;
-              const float u0 = fmaf(cwt[1], a[1], cwt[0] * a[0]), u1 = a[2], u2 = fmaf(cwt[3], a[4], cwt[2] * a[3]);
-              const float t = fmaf(wf[c][ti * 3 + 2], u2, fmaf(wf[c][ti * 3 + 1], u1, wf[c][ti * 3] * u0));
-              acc[c] = fmaf(rho[r], t, acc[c]);
+              for (int q = 0; q < 5; ++q)
+                a[q] = cdn_fadd2(make_float2(__uint_as_float(__byte_perm(xw[q], 0x4B000000u, 0x7650 + c)),
+                                             __uint_as_float(__byte_perm(xw[q], 0x4B000000u, 0x7650 + c + 1))), nunb);
+              const float2 u0 = cdn_ffma2(make_float2(cwt[1], cwt[1]), a[1], cdn_fmul2(make_float2(cwt[0], cwt[0]), a[0]));
+              const float2 u2 = cdn_ffma2(make_float2(cwt[3], cwt[3]), a[4], cdn_fmul2(make_float2(cwt[2], cwt[2]), a[3]));
+              const float2 w0 = make_float2(wf[c][ti * 3], wf[c + 1][ti * 3]), w1 = make_float2(wf[c][ti * 3 + 1], wf[c + 1][ti * 3 + 1]),
+                           w2 = make_float2(wf[c][ti * 3 + 2], wf[c + 1][ti * 3 + 2]);
+              const float2 t = cdn_ffma2(w2, u2, cdn_ffma2(w1, a[2], cdn_fmul2(w0, u0)));
+              acc2[cp] = cdn_ffma2(rho2, t, acc2[cp]);
             }
           }
+          const float acc[4] = {acc2[0].x, acc2[0].y, acc2[1].x, acc2[1].y};
           RqGuard gd; rq_guard_init(gd);
           uint32_t rr[4];
 #pragma unroll
