@@ -11,6 +11,7 @@ checkpoints load unchanged and tests read like the reference's own usage -- but 
                          (portable_quantizer/quant_modules.py)
   * quantize_model.py    quantize_shufflenetv2_dcn (portable_quantizer/quantization_utils/quantize_model.py)
   * decode.py            ctdet_decode (lib/models/decode.py)
+  * nms.py               soft_nms (lib/models/external/nms.pyx; host code in the reference too)
   * detector.py          CtdetDetector with run() / process() / pre_process() / post_process() / merge_outputs()
                          (lib/detectors/{base_detector,ctdet}.py)
 
@@ -25,4 +26,5 @@ from .quant_modules import (NotCompiledError, QuantAct, Quant_Conv2d, QuantBnCon
                             QuantDepthwiseNode)
 from .quantize_model import quantize_shufflenetv2_dcn, freeze_ranges  # noqa: F401
 from .decode import ctdet_decode  # noqa: F401
+from .nms import soft_nms  # noqa: F401
 from .detector import CtdetDetector  # noqa: F401

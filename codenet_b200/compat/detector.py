@@ -11,6 +11,7 @@ from types import SimpleNamespace
 import numpy as np
 import torch
 
+from .nms import soft_nms
 from .decode import ctdet_decode
 from .quantize_model import quantize_shufflenetv2_dcn, freeze_ranges
 from .shufflenetv2_dcn import PoseShuffleNetV2
@@ -236,10 +237,13 @@ class CtdetDetector:
         return dets[0]
 
     def merge_outputs(self, detections):
-        if len(self.scales) > 1 or self.opt.nms:
-            raise NotImplementedError("multi-scale / soft-NMS merging (lib/models/external/nms.pyx) is out of scope")
-        results = {j: np.concatenate([d[j] for d in detections], axis=0).astype(np.float32)
+        """lib/detectors/ctdet.py:59-74: concatenate the scales per class, soft-NMS (gaussian, Nt = 0.5, in place, as the
+        reference calls it) when testing at several scales or with --nms, keep the max_per_image best."""
+        results = {j: np.ascontiguousarray(np.concatenate([d[j] for d in detections], axis=0).astype(np.float32))
                    for j in range(1, self.num_classes + 1)}
+        if len(self.scales) > 1 or self.opt.nms:
+            for j in range(1, self.num_classes + 1):
+                soft_nms(results[j], Nt=0.5, method=2)
         scores = np.hstack([results[j][:, 4] for j in range(1, self.num_classes + 1)])
         if len(scores) > self.max_per_image:
             kth = len(scores) - self.max_per_image

@@ -64,6 +64,49 @@ def build(force=False, verbose=False):
     return so
 
 
+NMS_PYX = "/root/reference/lib/models/external/nms.pyx"
+
+
+def build_nms(force=False):
+    """The reference's Cython NMS (lib/models/external/nms.pyx, unmodified): cython -> C in oracle/_ref, gcc -> module
+    `nms`.  Used by oracle/make_golden.py to generate tests/golden/soft_nms_kat.npz; never shipped or imported by the product."""
+    import numpy
+    so = os.path.join(OUT, "nms" + sysconfig.get_config_var("EXT_SUFFIX"))
+    if not os.path.exists(NMS_PYX):
+        return so if os.path.exists(so) else None
+    if not force and os.path.exists(so) and os.path.getmtime(so) > os.path.getmtime(NMS_PYX):
+        return so
+    os.makedirs(OUT, exist_ok=True)
+    c_file = os.path.join(OUT, "nms.c")
+    # numpy 2 dropped the `np.int_t` ctypedef that the (unused here) hard-NMS function of the file names at :32; the file
+    # is cythonised from a temporary copy with that one identifier renamed (deleted again below, never committed) --
+    # the counterpart of the two -D renames of the CUDA extension.  soft_nms (:77-170) is compiled as written.
+    tmp_pyx = os.path.join(OUT, "nms.pyx")
+    with open(NMS_PYX) as f:
+        src = f.read().replace("np.int_t", "np.intp_t")
+    with open(tmp_pyx, "w") as f:
+        f.write(src)
+    cmds = [[sys.executable, "-m", "cython", "-3", tmp_pyx, "-o", c_file],
+            ["gcc", "-O2", "-fPIC", "-shared", "-w", c_file, "-o", so, "-I", sysconfig.get_paths()["include"], "-I", numpy.get_include()]]
+    for cmd in cmds:
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+            raise RuntimeError("building the reference nms.pyx failed")
+    os.remove(c_file)
+    os.remove(tmp_pyx)
+    return so
+
+
+def load_nms():
+    import importlib.util
+    so = os.path.join(OUT, "nms" + sysconfig.get_config_var("EXT_SUFFIX"))
+    spec = importlib.util.spec_from_file_location("nms", so)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def load():
     """Imports the built module (needs torch imported first).  Raises if it was never built."""
     import importlib.util

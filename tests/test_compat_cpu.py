@@ -162,3 +162,37 @@ def test_post_process_matches_the_reference(golden):
         for j in range(1, 6):
             got = np.array(out[i][j], np.float32).reshape(-1, 5)
             np.testing.assert_allclose(got, g["img%d_cls%d" % (i, j)], rtol=1e-6, atol=1e-4)
+
+
+def test_soft_nms_matches_the_compiled_reference(golden):
+    """compat.soft_nms against the reference's own Cython soft_nms (lib/models/external/nms.pyx:77-170), fixtures from
+    oracle/make_golden_nms.py: the in-place result (reordered boxes, decayed scores, discarded tail) and the kept count
+    must be bit-identical for all three methods."""
+    from codenet_b200.compat import soft_nms
+    g = golden("soft_nms_kat.npz")
+    n = 0
+    for key in g.files:
+        if not key.endswith("_in"):
+            continue
+        tag = key[:-3]
+        method = int(tag.split("_m")[1])
+        a = g[key].copy()
+        keep = soft_nms(a, Nt=0.5, method=method)
+        np.testing.assert_array_equal(a, g[tag + "_out"], err_msg=tag)
+        assert len(keep) == int(g[tag + "_keep"]), tag
+        n += 1
+    assert n == 36
+
+
+def test_merge_outputs_multi_scale_uses_soft_nms():
+    """Two scales of the same detections: merge_outputs (ctdet.py:59-74) decays the duplicates instead of raising."""
+    from codenet_b200.compat.detector import CtdetDetector
+    det = CtdetDetector.__new__(CtdetDetector)
+    det.num_classes, det.max_per_image, det.scales = 2, 100, [1.0, 1.5]
+    det.opt = type("O", (), {"nms": False})()
+    a = {1: np.array([[10, 10, 50, 50, 0.9], [100, 100, 140, 150, 0.8]], np.float32), 2: np.zeros((0, 5), np.float32)}
+    b = {1: np.array([[11, 10, 51, 50, 0.7]], np.float32), 2: np.array([[5, 5, 20, 20, 0.3]], np.float32)}
+    r = det.merge_outputs([a, b])
+    assert r[1].shape == (3, 5) and r[2].shape == (1, 5)
+    assert r[1][0, 4] == np.float32(0.9) and r[1][1, 4] == np.float32(0.8)         # sorted by score, untouched
+    assert 0 < r[1][2, 4] < np.float32(0.7) * np.float32(0.2)                      # near-duplicate decayed by exp(-iou^2/0.5)
