@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(128) stem_kernel(const __grid_constant__ StemP
       }
     }
   }
+  const int lo_i = (int)p.lo;
   uint32_t words[STEM_MAXC / 4];
 #pragma unroll
   for (int i = 0; i < STEM_MAXC / 4; ++i) words[i] = 0;
@@ -71,9 +72,11 @@ __global__ void __launch_bounds__(128) stem_kernel(const __grid_constant__ StemP
       double acc = 0.0;
 #pragma unroll
       for (int k = 0; k < 27; ++k) acc = fma(p.cw[c * 27 + k], x[k], acc);   // products exact => fma == mul,add
-      double td = __dadd_rn(__dmul_rn(acc, p.cM[c]), p.cB[c]);
-      td = fmin(fmax(rint(td), p.lo), 127.0);
-      words[c >> 2] |= (uint32_t)((int)td & 0xff) << (8 * (c & 3));
+      const double td = __dadd_rn(__dmul_rn(acc, p.cM[c]), p.cB[c]);
+      // round-half-even + saturating conversion in one instruction, clamp on the integer side (same result as
+      // clamp(rint(td)) for every td; the fp64 min/max/rint of the first version were three slow-pipe operations)
+      const int q = min(max(__double2int_rn(td), lo_i), 127);
+      words[c >> 2] |= (uint32_t)(q & 0xff) << (8 * (c & 3));
     }
   }
   uint4* dst = (uint4*)(p.out + (size_t)pix * p.out_pitch);
