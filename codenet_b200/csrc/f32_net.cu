@@ -147,6 +147,96 @@ __global__ void __launch_bounds__(128) pw_slice_f32_kernel(const float* __restri
     }
 }
 
+// ---- the same 1x1 conv, shared-memory tiled (the path taken whenever pixels_per_image % 128 == 0) -------------------
+// CTA tile = 64 output channels x 128 pixels of one image, K in chunks of 16 input channels staged in shared memory
+// (weights transposed to [k][co], activations [k][pixel]); a thread owns 8 output channels x 4 consecutive pixels.  All
+// lanes of a warp share their 8 output channels, so the weight reads are broadcasts and the activation read is one
+// contiguous 512-byte LDS.128: 3 shared-memory instructions feed 32 FMAs, and every activation is fetched from L2 once
+// per 64 output channels instead of once per 8 (the register-tile kernel above is bound by those re-reads).
+// Arithmetic is the one of the kernel above, bit for bit: fp32 FMA chains over blocks of 32 input channels in ascending
+// order, block sums added in fp64.
+#define PWT_CO 64
+#define PWT_PX 128
+#define PWT_K 16
+__global__ void __launch_bounds__(256, 2) pw_tile_f32_kernel(const float* __restrict__ in, int in_ctotal, int in_coff, int C,
+                                                          const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out,
+                                                          int out_ctotal, int out_coff, int out_cstride, int Co, int relu, int ppi) {
+  __shared__ __align__(16) float sA[2][PWT_K][PWT_CO];          // weights, [k][co]
+  __shared__ __align__(16) float sB[2][PWT_K][PWT_PX];          // activations, [k][pixel]
+  const int tiles_per_img = ppi / PWT_PX;
+  const int b = blockIdx.x / tiles_per_img, px0 = (blockIdx.x - b * tiles_per_img) * PWT_PX;
+  const int co0 = blockIdx.y * PWT_CO;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;        // 4 pixels tx*4.., 8 output channels ty*8..
+  const float* x = in + ((size_t)b * in_ctotal + in_coff) * ppi + px0;
+  // loader roles: weights -- thread -> (co row r = tid / 4, four consecutive k); activations -- two float4 per thread
+  const int a_r = threadIdx.x >> 2, a_k = (threadIdx.x & 3) * 4;
+  const int b_k = threadIdx.x >> 5, b_p = (threadIdx.x & 31) * 4;          // rows b_k and b_k + 8
+  float ra[4]; float4 rb0, rb1;
+  auto gload = [&](int c0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = c0 + a_k + i;
+      ra[i] = (co0 + a_r < Co && c < C) ? __ldg(w + (size_t)(co0 + a_r) * C + c) : 0.f;
+    }
+    rb0 = (c0 + b_k < C) ? __ldg((const float4*)(x + (size_t)(c0 + b_k) * ppi + b_p)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    rb1 = (c0 + b_k + 8 < C) ? __ldg((const float4*)(x + (size_t)(c0 + b_k + 8) * ppi + b_p)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sA[buf][a_k + i][a_r] = ra[i];
+    *(float4*)&sB[buf][b_k][b_p] = rb0;
+    *(float4*)&sB[buf][b_k + 8][b_p] = rb1;
+  };
+  double tot[8][4];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const double bv = (bias && co0 + ty * 8 + r < Co) ? (double)bias[co0 + ty * 8 + r] : 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) tot[r][q] = bv;
+  }
+  float acc[8][4];
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[r][q] = 0.f;
+  const int nchunks = (C + PWT_K - 1) / PWT_K;
+  gload(0); sstore(0);
+  __syncthreads();
+  for (int ch = 0; ch < nchunks; ++ch) {
+    const int buf = ch & 1;
+    if (ch + 1 < nchunks) gload((ch + 1) * PWT_K);              // next chunk's global loads fly during this chunk's FMAs
+#pragma unroll
+    for (int k = 0; k < PWT_K; ++k) {
+      const float4 wa = *(const float4*)&sA[buf][k][ty * 8], wb = *(const float4*)&sA[buf][k][ty * 8 + 4];
+      const float4 v = *(const float4*)&sB[buf][k][tx * 4];
+      const float ww[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+      const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[r][q] = fmaf(ww[r], vv[q], acc[r][q]);
+    }
+    if ((ch & 1) == 1 || ch + 1 == nchunks) {                   // a block of 32 input channels is complete
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { tot[r][q] += (double)acc[r][q]; acc[r][q] = 0.f; }
+    }
+    if (ch + 1 < nchunks) sstore(buf ^ 1);                      // the other buffer was last read in the previous iteration
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int co = co0 + ty * 8 + r;
+    if (co < Co) {
+      float4 o;
+      o.x = (float)tot[r][0]; o.y = (float)tot[r][1]; o.z = (float)tot[r][2]; o.w = (float)tot[r][3];
+      if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+      *(float4*)(out + ((size_t)b * out_ctotal + out_coff + (size_t)co * out_cstride) * ppi + px0 + tx * 4) = o;
+    }
+  }
+}
+
 extern "C" int cdn_pw_slice_f32(const float* input, int in_ctotal, int in_coff, int C, const float* weight, const float* bias,
                                 float* output, int out_ctotal, int out_coff, int out_cstride, int Co, int relu, int B,
                                 int pixels_per_image, cdn_stream_t stream) {
@@ -157,6 +247,13 @@ extern "C" int cdn_pw_slice_f32(const float* input, int in_ctotal, int in_coff, 
             "pw_slice_f32: pixels per image must be a multiple of %d and the tensors 16-byte aligned", PWS_PX);
   const long long total = (long long)B * (pixels_per_image / PWS_PX);
   if (total == 0) return 0;
+  if (pixels_per_image % PWT_PX == 0 && (long long)B * (pixels_per_image / PWT_PX) < (1ll << 31)) {
+    dim3 grid((unsigned)(B * (pixels_per_image / PWT_PX)), (unsigned)((Co + PWT_CO - 1) / PWT_CO));
+    pw_tile_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(input, in_ctotal, in_coff, C, weight, bias, output, out_ctotal, out_coff,
+                                                              out_cstride, Co, relu, pixels_per_image);
+    CDN_LAUNCH_CHECK("pw_tile_f32_kernel");
+    return 0;
+  }
   static bool attr = false;
   if (!attr) { CDN_CUDA(cudaFuncSetAttribute(pw_slice_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr = true; }
   dim3 grid((unsigned)((total + 127) / 128), (unsigned)((Co + PWS_CO - 1) / PWS_CO));
