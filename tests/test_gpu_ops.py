@@ -139,7 +139,8 @@ def test_deform_random(C, H, W, bound, shift, mode):
     Ms = (bound + 1.0) / span
     bs = 0.5 - Ms * float(acc_s.mean())
     ss, zs = io.act_params(-bound + 1, bound)
-    a = dict(in_t=0, out_t=1, in_shift=shift, stride=1, wq=wq, C=pitch, zx=zx, M=M, B=Bc, lo=-128,
+    lo = -90 if C in (58, 256) else -128               # lo > -128: the kernels' explicit lower clamp (ReLU with z_out != 128)
+    a = dict(in_t=0, out_t=1, in_shift=shift, stride=1, wq=wq, C=pitch, zx=zx, M=M, B=Bc, lo=lo,
              ws=ws, Ms=Ms, bs=bs, ss=float(ss), zs=float(zs), bound=bound, mode=mode)
     op = Op("deform", "t", a)
     got, sval = run_op(P, op, {0: x}, sval=True)
@@ -158,10 +159,10 @@ def test_deform_random(C, H, W, bound, shift, mode):
     if mode == 0:
         s = np.rint(s)
         acc = io.deform_dw_int(A, wq3, s)
-        q = np.clip(io.requant(acc, M[:C], Bc[:C], 0, False), -128, 127)
+        q = np.clip(io.requant(acc, M[:C], Bc[:C], 0, False), lo, 127)
     else:
         acc = io.deform_dw_bilinear(A, wq3, s)
-        q = np.clip(io.requant_f(acc, M[:C], Bc[:C], 0, False), -128, 127)
+        q = np.clip(io.requant_f(acc, M[:C], Bc[:C], 0, False), lo, 127)
     np.testing.assert_array_equal(sval, s.astype(np.float32))
     assert len(np.unique(s)) >= min(4, 2 * bound)
     assert int8_mismatch(got[..., :C].transpose(0, 3, 1, 2), q) == 0
