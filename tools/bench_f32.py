@@ -13,12 +13,15 @@ for tag, cfg in (("1x_voc", NetConfig(num_classes=20)), ("2x_coco", NetConfig(nu
     for _ in range(2):
         eng.detect(x)
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    n = 5
-    for _ in range(n):
-        eng.detect(x)
-    e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / n
+    n, best = 5, None                       # eager launches: the host can be the bottleneck on a busy box -> best of 4 repeats
+    for _ in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            eng.detect(x)
+        e1.record(); torch.cuda.synchronize()
+        t = e0.elapsed_time(e1) / n
+        best = t if best is None else min(best, t)
+    ms = best
     print(json.dumps({"config": "float %s 512x512 batch %d, eager fp32 SIMT path" % (tag, B), "ms_per_step": round(ms, 3),
                       "images_per_s": round(B / ms * 1e3, 1)}))
