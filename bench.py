@@ -247,7 +247,7 @@ def run_ours(args):
     dby = sum(op_bytes(eng.plan, op, B) for op in eng.plan.ops if op.kind == "deform")
     dms = sum(v for k, v in fam_ms.items() if k.startswith("deform_"))
     deform = {"GBps": round(dby / dms / 1e6, 1), "frac_of_hbm_peak": round(dby / dms / 1e6 / peak, 4), "layers": deform_layers}
-    cpu = None if args.no_cpu else cpu_baseline(args, sample_images=1)
+    cpu = None if (args.no_cpu or world > 1) else cpu_baseline(args, sample_images=1)     # rank 0 at N = 1 only
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
@@ -277,33 +277,13 @@ def run_ours(args):
 
 # ---- CPU arm: the oracle port of the reference's forward + decode -------------------------------------------------
 def cpu_baseline(args, sample_images=1):
-    import torch
-    from codenet_b200.arch import NetConfig
-    from codenet_b200.synth import make_quant_state, make_images
-    from oracle import int_oracle as io
-    cfg = NetConfig(num_classes=20)
-    calib = np.load(os.path.join(ROOT, "tests", "golden", "codenet1x_calib.npz"))
-    st = make_quant_state(cfg, calib, args.offset_mode, 512)
-    x = make_images(sample_images, 512, seed=100)
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    o = io.IntOracle(cfg, st, args.offset_mode)
-
-    def one():
-        out = o.forward(x)
-        io.ctdet_decode(out["hm"], out["wh"], out["reg"], 100)
-
-    one()
-    t0 = time.perf_counter()
-    n = 0
-    while n < 3 or time.perf_counter() - t0 < 10.0:
-        one()
-        n += 1
-        if time.perf_counter() - t0 > 30.0:
-            break
-    dt = time.perf_counter() - t0
-    return {"value": round(n * sample_images / dt, 3), "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%d x (forward + decode) of %d image(s) at 512x512, integer-exact numpy oracle (oracle/int_oracle.py)" % (n, sample_images)}
+    """The oracle port (the reference path restated in numpy) on all host cores: one worker process per core, each looping
+    over forward + decode of its own 512x512 image for ~10 s (oracle/cpu_bench.py)."""
+    from oracle import cpu_bench
+    value, workers, n = cpu_bench.measure(args.offset_mode, seconds=10.0)
+    return {"value": round(value, 3), "unit": UNIT, "cores": workers, "kind": "port",
+            "sample": "%d x (forward + decode) of 1 image at 512x512 in 10 s on %d worker processes, integer-exact numpy oracle "
+                      "(oracle/int_oracle.py via oracle/cpu_bench.py)" % (n, workers)}
 
 
 def run_reference(args):
