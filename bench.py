@@ -79,6 +79,12 @@ def op_bytes(plan, op, batch):
     if op.kind == "stem":
         to = T[a["out_t"]]
         return batch * (3 * a["H"] * a["W"] * 4 + to.C * to.H * to.W)
+    if op.kind == "dw" and a.get("fused_into_next"):
+        # heads tail as one kernel: stored int8 input read once, fp32 planes written once; nothing in between touches HBM
+        ti = T[a["in_t"]]
+        return batch * (ti.C * ti.H * ti.W + 4 * a["fused_n_f32"] * 4 * ti.H * ti.W) + 9 * ti.C
+    if op.kind == "pw" and a.get("fused_with_prev"):
+        return 0
     if op.kind in ("dw", "deform"):
         ti, to = T[a["in_t"]], T[a["out_t"]]
         return batch * (ti.C * ti.H * ti.W + to.C * to.H * to.W) + 9 * ti.C
@@ -94,6 +100,8 @@ def op_bytes(plan, op, batch):
 
 
 def family(op):
+    if op.a.get("fused_into_next") or op.a.get("fused_with_prev"):
+        return "heads_fused_kernel"
     if op.kind == "deform":                      # integer offsets: v3 kernel; bilinear: v2 kernel with the guarded fp32 blend
         return "deform_int_v3_kernel" if op.a.get("mode", 0) == 0 else "deform_dw_v2_kernel"
     return {"pw": "pw_gemm_tc_kernel", "dw": "dw3x3_v2_kernel", "stem": "stem_kernel"}[op.kind]
@@ -128,6 +136,12 @@ def run_ours(args):
     st = make_quant_state(cfg, calib, args.offset_mode, 512)
     B, R = args.batch, 512
     eng = Engine.from_state_dict(cfg, st, R, R, B, offset_mode=args.offset_mode, device=local)
+    if args.no_fuse_heads:
+        eng.set_option("fuse_heads", 0)
+    if eng.heads_fused:                          # heads.dw2 + heads.out run as one kernel: account them as one launch
+        ops = eng.plan.ops
+        i = next(k for k, o in enumerate(ops) if o.name == "heads.dw2")
+        ops[i].a["fused_into_next"], ops[i].a["fused_n_f32"], ops[i + 1].a["fused_with_prev"] = True, ops[i + 1].a["n_f32"], True
     eng.set_option("host_chunk", args.host_chunk)
     # synthetic images: 16 distinct ones per rank, tiled to the batch (805 MB fp32 at B=256: larger than L2)
     base = make_images(min(16, B), R, seed=100 + rank)
@@ -211,7 +225,7 @@ def run_ours(args):
     per_op = [a / prof_runs for a in acc]
     if args.dump_ops:
         rows = [{"op": o.name, "kind": o.kind, "ms": round(m, 4), "MB": round(op_bytes(eng.plan, o, B) / 1e6, 1),
-                 "GBps": round(op_bytes(eng.plan, o, B) / m / 1e6, 1)} for o, m in zip(eng.plan.ops, per_op)]
+                 "GBps": round(op_bytes(eng.plan, o, B) / m / 1e6, 1) if m > 0 else None} for o, m in zip(eng.plan.ops, per_op)]
         rows.append({"op": "ctdet_decode", "kind": "decode", "ms": round(per_op[-1], 4)})
         with open(args.dump_ops, "w") as f:
             json.dump(rows, f, indent=1)
@@ -228,7 +242,8 @@ def run_ours(args):
     fam_bytes["ctdet_decode"] = B * (eng.plan.cat + 4) * eng.plan.out_H * eng.plan.out_W * 4
     fam_launches = {"ctdet_decode": 2}
     for op in eng.plan.ops:
-        fam_launches[family(op)] = fam_launches.get(family(op), 0) + 1
+        if not op.a.get("fused_with_prev"):
+            fam_launches[family(op)] = fam_launches.get(family(op), 0) + 1
     total_ms = sum(fam_ms.values())
     dom = max(fam_ms, key=fam_ms.get)
     peak, peak_src = peaks()
@@ -311,6 +326,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--offset-mode", default="round", choices=["round", "bilinear"])
     ap.add_argument("--host-chunk", type=int, default=64)
+    ap.add_argument("--no-fuse-heads", action="store_true", help="run heads.dw2 and heads.out as separate kernels (A/B)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs only)")
     ap.add_argument("--dump-ops", default="", help="write the per-op device times (JSON) to this file")
     args = ap.parse_args()

@@ -289,6 +289,7 @@ struct cdn_engine {
   cudaStream_t s_compute = nullptr, s_copy = nullptr;
   std::vector<cudaEvent_t> ev;
   int host_chunk = 64, use_graph = 1, hm_logits = 0;
+  int fuse_heads = 1;                        // heads.dw2 + heads.out as one kernel when the pair is eligible (heads_fused.cu)
   // graph cache
   struct GraphKey { const void* a[6]; int batch; bool operator==(const GraphKey& o) const { return memcmp(this, &o, sizeof(*this)) == 0; } };
   std::vector<std::pair<GraphKey, cudaGraphExec_t>> graphs;
@@ -340,6 +341,7 @@ extern "C" int cdn_engine_set_option(cdn_engine* e, const char* name, int value)
   if (!strcmp(name, "host_chunk")) e->host_chunk = std::max(1, value);
   else if (!strcmp(name, "use_graph")) e->use_graph = value;
   else if (!strcmp(name, "hm_logits")) e->hm_logits = value ? 1 : 0;
+  else if (!strcmp(name, "fuse_heads")) e->fuse_heads = value ? 1 : 0;
   else return cdn_fail(CDN_ERR_INVALID, "unknown engine option '%s'", name);
   return 0;
 }
@@ -473,14 +475,35 @@ extern "C" int cdn_engine_finalize(cdn_engine* e, int max_batch) {
   return 0;
 }
 
+// ops oi, oi+1 = depthwise conv through the virtual x2 upsample feeding the fp32 head conv, eligible for heads_fused.cu
+static bool engine_fuses_heads(const cdn_engine* e, size_t oi) {
+  if (!e->fuse_heads || (g_cdn_debug_flags & 256u) || oi + 1 >= e->ops.size()) return false;   // bit 8: never fuse (A/B)
+  const EngOp *a = e->ops[oi], *b = e->ops[oi + 1];
+  if (a->kind != 1 || b->kind != 3 || a->in_shift != 1 || a->stride != 1 || b->in_t != a->out_t || b->out_t >= 0 || b->pass_t >= 0) return false;
+  const EngTensor &ti = e->tensors[a->in_t], &tm = e->tensors[a->out_t];
+  return heads_fused_ok(a->dw, b->pw, ti.pitch, tm.pitch, ti.H, ti.W) && 2 * ti.H == e->hH && 2 * ti.W == e->hW;
+}
+
 // d_img: fp32 NCHW image, or (is_u8) uint8 NHWC image normalised in the stem through e->lut
 static int engine_enqueue(cdn_engine* e, const void* d_img, int is_u8, int batch, float* d_hm, float* d_wh, float* d_reg,
                           float* d_dets, int32_t* d_inds, cudaStream_t st, std::vector<cudaEvent_t>* marks = nullptr) {
   int launches = 0;
   auto mark = [&]() { if (marks) { cudaEvent_t ev; cudaEventCreate(&ev); cudaEventRecord(ev, st); marks->push_back(ev); } };
   mark();
-  for (auto* op : e->ops) {
+  for (size_t oi = 0; oi < e->ops.size(); ++oi) {
+    EngOp* op = e->ops[oi];
     int r = 0;
+    if (engine_fuses_heads(e, oi)) {
+      // depthwise conv through the upsample + fp32 head conv as one kernel; the int8 tensor between them is not written
+      const EngOp* nx = e->ops[oi + 1];
+      const EngTensor& ti = e->tensors[op->in_t];
+      r = heads_fused_launch(op->dw, nx->pw, ti.ptr, ti.pitch, batch, ti.H, ti.W, op->zx, e->heads, st);
+      if (r) return r;
+      launches++;
+      mark(); mark();                        // the second op of the pair takes no time of its own
+      ++oi;
+      continue;
+    }
     switch (op->kind) {
       case 0: {
         const EngTensor& to = e->tensors[op->out_t];
@@ -564,7 +587,7 @@ static int engine_run_any(cdn_engine* e, const void* d_img, int is_u8, int batch
   cudaStream_t st = (cudaStream_t)stream;
   if (!e->use_graph || (g_cdn_debug_flags & 2u)) return engine_enqueue(e, d_img, is_u8, batch, d_hm, d_wh, d_reg, d_dets, d_inds, st);
   cdn_engine::GraphKey key; memset(&key, 0, sizeof(key));
-  key.a[0] = d_img; key.a[1] = d_hm; key.a[2] = d_wh; key.a[3] = d_reg; key.a[4] = d_dets; key.a[5] = d_inds; key.batch = batch | (e->hm_logits << 30) | (is_u8 << 29);
+  key.a[0] = d_img; key.a[1] = d_hm; key.a[2] = d_wh; key.a[3] = d_reg; key.a[4] = d_dets; key.a[5] = d_inds; key.batch = batch | (e->hm_logits << 30) | (is_u8 << 29) | (e->fuse_heads << 28);
   for (auto& g : e->graphs) if (g.first == key) { CDN_CUDA(cudaGraphLaunch(g.second, st)); return 0; }
   // capture once per (pointers, batch)
   cudaStream_t cap = e->s_compute;
@@ -681,6 +704,11 @@ extern "C" int cdn_engine_read_heads(cdn_engine* e, int batch, float* h_out) {
 }
 
 extern "C" int cdn_engine_num_launches(cdn_engine* e) { return e ? e->launches : 0; }
+extern "C" int cdn_engine_heads_fused(cdn_engine* e) {
+  if (!e || !e->finalized) return 0;
+  for (size_t oi = 0; oi < e->ops.size(); ++oi) if (engine_fuses_heads(e, oi)) return 1;
+  return 0;
+}
 extern "C" int cdn_engine_requant_stats(cdn_engine* e, int* int_layers, int* guarded_layers) {
   ENG_CHECK(e);
   int ni = 0, ng = 0;

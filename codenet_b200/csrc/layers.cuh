@@ -49,6 +49,11 @@ int pw_init_attrs();
 int pw_launch(const PwDevice& d, const int8_t* in, int in_pitch, long long pixels, const int8_t* pass, int pass_pitch,
               int8_t* out, int out_pitch, float* out_f32, int ppi, const CUtensorMap* tmA, const CUtensorMap* tmP,
               const CUtensorMap* tmO, cudaStream_t st);
+// heads tail: depthwise conv through the x2 upsample as the A-tile producer of the fp32 head conv (heads_fused.cu)
+bool heads_fused_ok(const DwDevice& dw, const PwDevice& pw, int in_pitch, int mid_pitch, int Hs, int Ws);
+int heads_fused_launch(const DwDevice& dw, const PwDevice& pw, const int8_t* in, int in_pitch, int batch, int Hs, int Ws,
+                       int zx, float* out_f32, cudaStream_t st);
+int make_tmap_nhwc(CUtensorMap* m, const void* base, uint64_t pitch, uint64_t W, uint64_t H, uint64_t batch, uint32_t box_w, uint32_t box_h);
 int make_tmap_2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t pitch, uint32_t box_rows);
 
 int decode_launch(const float* hm, long long hm_img_stride, const float* wh, long long wh_img_stride, const float* reg,

@@ -162,6 +162,11 @@ class Engine:
         return out
 
     @property
+    def heads_fused(self) -> bool:
+        """True when heads.dw2 + heads.out run as one kernel (option "fuse_heads", default on, and the pair is eligible)."""
+        return bool(self.lib.cdn_engine_heads_fused(self._h))
+
+    @property
     def num_launches(self):
         return int(self.lib.cdn_engine_num_launches(self._h))
 

@@ -244,8 +244,13 @@ int cdn_engine_run_u8(cdn_engine* e, const uint8_t* d_img, int batch, float* d_h
 int cdn_engine_run_host_u8(cdn_engine* e, const uint8_t* h_img, int batch, float* h_dets, int32_t* h_inds);
 /* Options: "host_chunk" (granularity of the H2D / compute pipeline of run_host: chunks grow x1.6 from host_chunk/2,
  * default 64), "use_graph" (replay the launch sequence as a CUDA graph, default 1), "hm_logits" (cdn_engine_run writes
- * the heat map as logits, what PoseShuffleNetV2.forward returns, instead of post-sigmoid; default 0). */
+ * the heat map as logits, what PoseShuffleNetV2.forward returns, instead of post-sigmoid; default 0), "fuse_heads"
+ * (default 1: the heads' depthwise conv, QuantDepthwiseNode.forward quant_modules.py:1061-1071, feeds the fp32 output
+ * conv inside one kernel, so the int8 tensor between them is not materialised; 0 runs the two plan ops separately,
+ * which is what cdn_engine_read_tensor needs to see that tensor.  Same results bit for bit). */
 int cdn_engine_set_option(cdn_engine* e, const char* name, int value);
+/* 1 when the finalized plan runs the heads' tail fused (option on and the layer pair eligible), else 0. */
+int cdn_engine_heads_fused(cdn_engine* e);
 /* Debug/test access to an activation tensor of the last run: copies batch*H*W*pitch bytes to host. */
 int cdn_engine_read_tensor(cdn_engine* e, int tensor, int batch, int8_t* h_out);
 /* Raw head outputs of the last run: fp32 [batch][cat+4][Ho*Wo] = hm logits, wh, reg. */

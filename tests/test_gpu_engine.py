@@ -28,8 +28,10 @@ def test_engine_matches_reference_vectors_256(golden, calib, mode):
     g = golden("codenet1x_256_%s.npz" % mode)
     eng = _engine(calib, mode, 256, 4)
     x = make_images(2, 256, seed=2)
+    eng.set_option("fuse_heads", 0)                     # the int8 grid between heads.dw2 and heads.out is only written unfused
     out = eng.run(torch.from_numpy(x).cuda())
     torch.cuda.synchronize()
+    heads_unfused = eng.read_heads(2)
     # every int8 grid recorded from the reference, bit for bit
     names = {"hm.act1": ("heads.act1", slice(0, 64), True), "hm.act3": ("heads.act3", slice(0, 64), False)}
     checked = 0
@@ -43,8 +45,14 @@ def test_engine_matches_reference_vectors_256(golden, calib, mode):
         assert int8_mismatch(got, g[k]) == 0, k
         checked += 1
     assert checked >= (16 if mode == "round" else 8)
+    # the default path: heads.dw2 + heads.out as one kernel (heads_fused.cu); everything below is checked on ITS output
+    eng.set_option("fuse_heads", 1)
+    assert eng.heads_fused
+    out = eng.run(torch.from_numpy(x).cuda())
+    torch.cuda.synchronize()
     # head outputs: exact integer accumulator, fp64 epilogue, one rounding to fp32
     heads = eng.read_heads(2)
+    np.testing.assert_array_equal(heads, heads_unfused)
     ref = np.concatenate([g["hm_logit"], g["wh"], g["reg"]], 1)
     np.testing.assert_allclose(heads, ref, rtol=2e-7, atol=1e-7)
     hm = out["hm"].cpu().numpy()
@@ -101,6 +109,32 @@ def test_engine_equals_oracle_on_fresh_images(calib):
         assert int8_mismatch(eng.read_logical(lbl, 3), o.cap[lbl]) == 0, lbl
     heads = eng.read_heads(3)
     np.testing.assert_array_equal(heads, np.concatenate([ref["hm"], ref["wh"], ref["reg"]], 1).astype(np.float32))
+    eng.close()
+
+
+@pytest.mark.parametrize("res,batch", [(256, 5), (512, 3), (320, 2)])
+def test_heads_fused_equals_separate_kernels(calib, res, batch):
+    """heads.dw2 + heads.out as one kernel (heads_fused.cu: the depthwise conv produces the UMMA A tile in shared memory)
+    against the two separate launches: fp32 head planes, indices and detections identical bit for bit, eager and as a
+    graph, at tile counts that do and do not fill the persistent grid, and at a size (320 -> 80x80 maps) whose stored
+    40x40 input is a whole number of 4x8 tiles only because 40 % 8 == 0."""
+    import torch
+    st = make_quant_state(CFG, calib, "round", 256)
+    eng = Engine.from_state_dict(CFG, st, res, res, batch, offset_mode="round")
+    xt = torch.from_numpy(make_images(batch, res, seed=11, clamp=4.0)).cuda()
+    got = {}
+    for fuse in (0, 1):
+        eng.set_option("fuse_heads", fuse)
+        assert eng.heads_fused == bool(fuse)
+        for graph in (0, 1):
+            eng.set_option("use_graph", graph)
+            out = eng.run(xt, maps=False)
+            torch.cuda.synchronize()
+            got[fuse, graph] = (eng.read_heads(batch).copy(), out["inds"].cpu().numpy(), out["dets"].cpu().numpy())
+    assert eng.num_launches > 0
+    for key in ((0, 1), (1, 0), (1, 1)):
+        for a, b in zip(got[0, 0], got[key]):
+            np.testing.assert_array_equal(a, b)
     eng.close()
 
 
@@ -178,8 +212,10 @@ def test_engine_w2_maxpool_matches_reference_vectors(golden):
     st = make_quant_state(cfg, golden("codenet_w2mp_calib.npz"), "round", 256)
     eng = Engine.from_state_dict(cfg, st, 256, 256, 2, offset_mode="round")
     x = make_images(2, 256, seed=2)[:1]
+    eng.set_option("fuse_heads", 0)
     out = eng.run(torch.from_numpy(x.copy()).cuda())
     torch.cuda.synchronize()
+    heads_unfused = eng.read_heads(1)
     names = {"hm.act1": ("heads.act1", slice(0, 64), True), "hm.act3": ("heads.act3", slice(0, 64), False)}
     checked = 0
     for k in g.files:
@@ -193,7 +229,12 @@ def test_engine_w2_maxpool_matches_reference_vectors(golden):
         assert int8_mismatch(got, ref) == 0, k
         checked += 1
     assert checked >= 17
+    eng.set_option("fuse_heads", 1)
+    assert eng.heads_fused
+    out = eng.run(torch.from_numpy(x.copy()).cuda())
+    torch.cuda.synchronize()
     heads = eng.read_heads(1)
+    np.testing.assert_array_equal(heads, heads_unfused)
     np.testing.assert_allclose(heads, np.concatenate([g["hm_logit"], g["wh"], g["reg"]], 1), rtol=2e-7, atol=1e-7)
     h64 = heads.astype(np.float64)
     odets, oinds = io.ctdet_decode(h64[:, :20], h64[:, 20:22], h64[:, 22:24], 100)
