@@ -148,6 +148,14 @@ __device__ __forceinline__ int rq_int_wide(int v, int Mi, int sh, long long Bi) 
   asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(x) : "r"(v), "r"(Mi), "l"(Bi));
   return (int)(x >> 32) >> sh;
 }
+// the same with the PTX spelled out as mul.wide.s32 + add.s64 + high half, the form ptxas turns into ONE IMAD.HI with a 64-bit
+// addend: in loops where the front end hoists the sign extension of Mi it otherwise emits a 64-bit multiply (heads_fused.cu)
+__device__ __forceinline__ int rq_int_hi(int v, int Mi, int sh, long long Bi) {
+  int hi;
+  asm("{\n\t.reg .b64 t;\n\t.reg .b32 lo;\n\tmul.wide.s32 t, %1, %2;\n\tadd.s64 t, t, %3;\n\tmov.b64 {lo, %0}, t;\n\t}"
+      : "=r"(hi) : "r"(v), "r"(Mi), "l"(Bi));
+  return hi >> sh;
+}
 __device__ __forceinline__ int rq_int(int v, const int4& r) {
   return rq_int(v, r.x, r.y, (long long)(((unsigned long long)(uint32_t)r.w << 32) | (uint32_t)r.z));
 }

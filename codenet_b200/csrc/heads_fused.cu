@@ -22,6 +22,9 @@
 
 #define HF_MAX_THREADS 192
 #define HF_CTAS 3                            // resident CTAs per SM (shared memory: ~68 KB each)
+#ifndef HF_RQ
+#define HF_RQ rq_int_hi
+#endif
 #define HF_TW 4                              // stored columns per tile
 #define HF_TH 8                              // stored rows per tile
 
@@ -41,14 +44,10 @@ struct HfParams {
 };
 
 template <bool LO>
-__device__ __forceinline__ uint32_t hf_rq_word(const int (&acc)[4], const int4 (&r)[4], int lo) {
+__device__ __forceinline__ uint32_t hf_rq_word(const int (&acc)[4], const int2 (&km)[4], const long long (&kb)[4], int lo) {
   int q[4];
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    // mad.wide.s32 spelled out: here the compiler expands the C form of rq_int into a 64 x 64-bit multiply (6 instructions)
-    q[c] = rq_int_wide(acc[c], r[c].x, r[c].y, (long long)(((unsigned long long)(uint32_t)r[c].w << 32) | (uint32_t)r[c].z));
-    if (LO) q[c] = max(q[c], lo);
-  }
+  for (int c = 0; c < 4; ++c) { q[c] = HF_RQ(acc[c], km[c].x, km[c].y, kb[c]); if (LO) q[c] = max(q[c], lo); }
   return pack_sat4(q[0], q[1], q[2], q[3]);
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
@@ -115,7 +114,7 @@ __global__ void __launch_bounds__(HF_MAX_THREADS, HF_CTAS) heads_fused_kernel(co
     for (int i = tid; i < p.NB; i += blockDim.x) { s_Mf[i] = p.Mf[i]; s_bf[i] = p.bf[i]; s_ab[i] = p.acc_bias[i]; }
   }
   // per-thread depthwise constants: 4 channels x 8 packed weight words, 4 RqInt records
-  uint32_t W[4][8]; int4 ki[4];
+  uint32_t W[4][8]; int2 km[4]; long long kb[4];   // RqInt as {Mi, sh} and a 64-bit Bi (loaded as one 64-bit value)
   if (worker) {
     const uint4* wv = (const uint4*)(p.wpk + (size_t)cw * 32);
     uint32_t flat[32];
@@ -126,7 +125,7 @@ __global__ void __launch_bounds__(HF_MAX_THREADS, HF_CTAS) heads_fused_kernel(co
 #pragma unroll
       for (int i = 0; i < 8; ++i) W[c][i] = flat[c * 8 + i];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) ki[c] = __ldg(p.ki + cw * 4 + c);
+    for (int c = 0; c < 4; ++c) { km[c] = __ldg((const int2*)(p.ki + cw * 4 + c)); kb[c] = __ldg((const long long*)(p.ki + cw * 4 + c) + 1); }
   }
   tc_fence_before();
   __syncthreads();
@@ -170,7 +169,7 @@ __global__ void __launch_bounds__(HF_MAX_THREADS, HF_CTAS) heads_fused_kernel(co
             a0[c] = dp4a_ss(tb, W[c][4 * yp + 2], dp4a_ss(ta, W[c][4 * yp + 0], 0));
             a1[c] = dp4a_ss(tb, W[c][4 * yp + 3], dp4a_ss(ta, W[c][4 * yp + 1], 0));
           }
-          const uint32_t o0 = hf_rq_word<LO>(a0, ki, p.lo_i), o1 = hf_rq_word<LO>(a1, ki, p.lo_i);
+          const uint32_t o0 = hf_rq_word<LO>(a0, km, kb, p.lo_i), o1 = hf_rq_word<LO>(a1, km, kb, p.lo_i);
           const uint32_t m0 = (uint32_t)((2 * r + yp) * 8 + 2 * pc);                            // A row of the left output pixel
           sts_u32(a_base + m0 * 128u + ((a_unit ^ (m0 & 7u)) << 4), o0);
           sts_u32(a_base + (m0 + 1u) * 128u + ((a_unit ^ ((m0 + 1u) & 7u)) << 4), o1);
