@@ -75,10 +75,9 @@ __global__ void __launch_bounds__(HF_MAX_THREADS, HF_CTAS) heads_fused_kernel(co
   uint8_t* s_A = smem;                                       // 2 K blocks x [128 rows][128 B], 128B swizzle
   uint8_t* s_B = s_A + 2 * 16384;                            // 2 K blocks x [NB rows][128 B]
   uint8_t* s_in = s_B + 2 * (size_t)p.NB * 128;              // 2 x [HF_TH + 2][HF_TW + 2][pitch]: staged input tiles
-  double* s_Mf = (double*)(s_in + 2 * (size_t)p.in_bytes);
-  double* s_bf = s_Mf + p.NB;
-  int* s_ab = (int*)(s_bf + p.NB);
-  uint64_t* s_bar = (uint64_t*)(s_ab + p.NB + (p.NB & 1));   // [0] MMA done, [1..2] input buffer full
+  uint8_t* s_colp = s_in + 2 * (size_t)p.in_bytes;           // [NB] 32-byte records {double Mf, double bf, int acc_bias, -}
+  const uint32_t s_col = smem_u32(s_colp);
+  uint64_t* s_bar = (uint64_t*)(s_colp + (size_t)p.NB * 32); // [0] MMA done, [1..2] input buffer full
   volatile uint32_t* tmem_slot = (volatile uint32_t*)(s_bar + 3);
   const uint32_t bar = smem_u32(s_bar), ibar = bar + 8;
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -111,7 +110,9 @@ __global__ void __launch_bounds__(HF_MAX_THREADS, HF_CTAS) heads_fused_kernel(co
       const uint4 v = __ldg((const uint4*)(p.w + (size_t)n * p.Kp) + c);
       *(uint4*)(s_B + (size_t)kb * p.NB * 128 + n * 128 + ((cc ^ (n & 7)) << 4)) = v;
     }
-    for (int i = tid; i < p.NB; i += blockDim.x) { s_Mf[i] = p.Mf[i]; s_bf[i] = p.bf[i]; s_ab[i] = p.acc_bias[i]; }
+    for (int i = tid; i < p.NB; i += blockDim.x) {
+      *(double*)(s_colp + i * 32) = p.Mf[i]; *(double*)(s_colp + i * 32 + 8) = p.bf[i]; *(int*)(s_colp + i * 32 + 16) = p.acc_bias[i];
+    }
   }
   // per-thread depthwise constants: 4 channels x 8 packed weight words, 4 RqInt records
   uint32_t W[4][8]; int2 km[4]; long long kb[4];   // RqInt as {Mi, sh} and a 64-bit Bi (loaded as one 64-bit value)
@@ -200,19 +201,19 @@ __global__ void __launch_bounds__(HF_MAX_THREADS, HF_CTAS) heads_fused_kernel(co
       const int oy = m >> 3, ox = m & 7;
       float* o = p.out + (size_t)b * p.n_f32 * p.ppi + (size_t)(ty * (2 * HF_TH) + oy) * p.Wout + tx * (2 * HF_TW) + ox;
       const uint32_t tacc = tmem_base + ((uint32_t)(warp * 32) << 16);
-      for (int c0 = 0; c0 < p.n_f32; c0 += 8) {
+      const int nf = p.n_f32, ppi = p.ppi;
+      for (int c0 = 0; c0 < nf; c0 += 8) {
         uint32_t acc[16];
         tmem_ld8(tacc + (uint32_t)c0, acc);
         tmem_ld_wait();
+        // branch-free: the constant records are padded to NB >= c0 + 8 columns, only the store is predicated
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int n = c0 + i;
-          if (n < p.n_f32) {
-            const int a = (int)acc[i] + s_ab[n];
-            const double yv = __dadd_rn(__dmul_rn((double)a, s_Mf[n]), s_bf[n]);
-            *o = (float)yv;
-            o += p.ppi;
-          }
+          const uint4 k = lds_u128(s_col + (uint32_t)(c0 + i) * 32u);                 // {Mf, bf}
+          const int a = (int)acc[i] + (int)lds_u32(s_col + (uint32_t)(c0 + i) * 32u + 16u);
+          const double yv = __dadd_rn(__dmul_rn((double)a, __hiloint2double((int)k.y, (int)k.x)), __hiloint2double((int)k.w, (int)k.z));
+          if (c0 + i < nf) *o = (float)yv;
+          o += ppi;
         }
       }
     }
@@ -249,7 +250,7 @@ int heads_fused_launch(const DwDevice& dw, const PwDevice& pw, const int8_t* in,
   p.acc_bias = pw.rq.acc_bias; p.Mf = pw.Mf; p.bf = pw.bf; p.n_f32 = pw.n_f32;
   p.out = out_f32; p.ppi = 4 * Hs * Ws; p.Wout = 2 * Ws;
   const int threads = std::max(128, (p.nthreads + 31) / 32 * 32);
-  const size_t smem = 1024 + 2 * 16384 + 2 * (size_t)p.NB * 128 + 2 * (size_t)p.in_bytes + (size_t)p.NB * (8 + 8 + 4) + 64;
+  const size_t smem = 1024 + 2 * 16384 + 2 * (size_t)p.NB * 128 + 2 * (size_t)p.in_bytes + (size_t)p.NB * 32 + 64;
   CDN_CHECK(smem <= 76 * 1024, CDN_ERR_INVALID, "heads_fused: %zu bytes of shared memory", smem);
   static bool attr_set[2] = {false, false};
   const bool lo_on = p.lo_i > -128;
