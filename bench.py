@@ -266,10 +266,10 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "s8 x s8 -> s32 (4-bit weights, 8-bit activations)",
+        "scaling": "weak", "vs_baseline": None, "dtype": "int8",
         "data": "synthetic", "impl": "codenet_b200",
         "config": {"workload": "BASELINE config c: CoDeNet1x 512x512 stride-4 W4A8, 20 classes, K=100, batch %d per GPU" % B,
-                   "batch_per_gpu": B, "offset_mode": args.offset_mode, "parallelism": "batch-sharded, no collective",
+                   "batch_per_gpu": B, "offset_mode": args.offset_mode, "arithmetic": "s8 x s8 -> s32 (4-bit weights, 8-bit activations), exact integer requantisation", "parallelism": "batch-sharded, no collective",
                    "l2": "inputs larger than L2 (%.0f MB fp32 images per step)" % (B * 3 * R * R * 4 / 1e6),
                    "outputs": "detections [B,100,6] (+ heat-map/wh/reg maps on request)"},
         "e2e": {"value": round(e2e_val, 1), "unit": UNIT, "h2d_bytes_per_step": int(B * 3 * R * R),
@@ -283,6 +283,7 @@ def run_ours(args):
                            "api": "Engine.run_host -> cdn_engine_run_host"},
         "gpu_launches": int(eng.num_launches * args.steps),
         "requant": dict(zip(("int_layers", "guarded_fp32_layers"), eng.requant_stats)),
+        "heads_fused": bool(eng.heads_fused),
         "clocks": clocks, "roofline": roofline, "deform": deform, "cpu_baseline": cpu,
     }
     print(json.dumps(line))

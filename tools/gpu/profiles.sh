@@ -6,8 +6,8 @@ export PYTHONUNBUFFERED=1
 timeout 1500 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 700 --csv \
    --log-file gpurun_out/launches_full.csv python bench.py --steps 1 --warmup 3 --no-cpu > gpurun_out/ncu_launch.log 2>&1
 echo "launch list rc=$?"
-for k in pw_gemm_tc deform_int_v3 dw3x3_v2; do
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k -s 3 -c 3 -f -o gpurun_out/prof_full_$k \
+for k in pw_gemm_tc deform_int_v3 dw3x3_v2 heads_fused; do
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k -s ${SKIPK:-3} -c ${COUNTK:-3} -f -o gpurun_out/prof_full_$k \
      python bench.py --steps 1 --warmup 3 --no-cpu > gpurun_out/ncu_full_$k.log 2>&1
   echo "ncu full $k rc=$?"
 done

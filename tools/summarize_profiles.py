@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 TAG = sys.argv[1] if len(sys.argv) > 1 else "r01"
 OUT = os.path.join(ROOT, "profiles")
 GO = os.path.join(ROOT, "gpurun_out")
-LAUNCHES_PER_STEP = 67          # kernels of one forward + decode (memset excluded)
+LAUNCHES_PER_STEP = 66          # kernels of one forward + decode (memset excluded; heads.dw2 + heads.out are one launch)
 
 
 def fam(name):
@@ -106,5 +106,5 @@ def full(kernel):
 
 if __name__ == "__main__":
     launch_list()
-    for k in ("pw_gemm_tc", "deform_int_v3", "dw3x3_v2"):
+    for k in ("pw_gemm_tc", "deform_int_v3", "dw3x3_v2", "heads_fused"):
         full(k)
