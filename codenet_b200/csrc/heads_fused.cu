@@ -50,14 +50,8 @@ __device__ __forceinline__ uint32_t hf_rq_word(const int (&acc)[4], const int2 (
   for (int c = 0; c < 4; ++c) { q[c] = HF_RQ(acc[c], km[c].x, km[c].y, kb[c]); if (LO) q[c] = max(q[c], lo); }
   return pack_sat4(q[0], q[1], q[2], q[3]);
 }
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
-  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
-               ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
-}
 // one stored row of the staged tile -> the three pixels x-1, x, x+1 of this thread's channel word; TMA zero-fills pixels
 // outside the image, the layer needs REAL zero there (q = -zx)
-__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) { uint32_t v; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(saddr)); return v; }
-__device__ __forceinline__ void sts_u32(uint32_t saddr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory"); }
 __device__ __forceinline__ void hf_row(uint32_t rowp, int pitch, bool yok, const bool (&cok)[3], uint32_t pad, uint32_t (&T)[4]) {
   uint32_t w[3];
 #pragma unroll
