@@ -970,7 +970,7 @@ int dw_launch(const DwDevice& d, const int8_t* in, int in_pitch, int8_t* out, in
   CDN_CHECK(in_shift == 0 || (in_shift == 1 && stride == 1 && H % 2 == 0 && W % 2 == 0), CDN_ERR_INVALID, "dw: bad in_shift");
   CDN_CHECK(in_pitch >= d.cw_total * 4 && out_pitch >= d.cw_total * 4, CDN_ERR_INVALID, "dw: pitch smaller than channels");
   CDN_CHECK(!in_shift || d.u_ok, CDN_ERR_INVALID, "dw: weights too large for the upsample-folded kernel (sums exceed int8)");
-  if (dw_tma_ok(d, in_pitch, out_pitch, H, W, in_shift, stride)) return dw_tma_launch(d, in, in_pitch, out, out_pitch, batch, H, W, zx, st);
+  if (dw_tma_ok(d, in_pitch, out_pitch, H, W, in_shift, stride)) return dw_tma_launch(d, in, in_pitch, out, out_pitch, batch, H, W, stride, zx, st);
   DwV2Params p; memset(&p, 0, sizeof(p));
   p.in = (const uint32_t*)in; p.out = (uint32_t*)out;
   p.in_pitch_w = in_pitch / 4; p.out_pitch_w = out_pitch / 4;

@@ -18,10 +18,10 @@ int deform_scale_build(DwDevice& d, const cdn_deform_scale* sc, const int8_t* ws
 void dw_device_free(DwDevice& d);
 int dw_launch(const DwDevice& d, const int8_t* in, int in_pitch, int8_t* out, int out_pitch, int batch, int H, int W,
               int in_shift, int stride, int zx, cudaStream_t st);
-// stride-1 depthwise conv with the input tile staged by TMA (dw_tma.cu); dw_launch picks it when the shape is eligible
+// depthwise conv (stride 1 / 2) with the input tile staged by TMA (dw_tma.cu); dw_launch picks it when the shape is eligible
 bool dw_tma_ok(const DwDevice& d, int in_pitch, int out_pitch, int H, int W, int in_shift, int stride);
 int dw_tma_launch(const DwDevice& d, const int8_t* in, int in_pitch, int8_t* out, int out_pitch, int batch, int H, int W,
-                  int zx, cudaStream_t st);
+                  int stride, int zx, cudaStream_t st);
 int deform_launch(const DwDevice& d, const cdn_deform_scale* sc, const int8_t* in, int in_pitch, int8_t* out,
                   int out_pitch, int batch, int H, int W, int in_shift, int zx, float* sval, cudaStream_t st);
 
