@@ -104,7 +104,8 @@ def family(op):
         return "heads_fused_kernel"
     if op.kind == "deform":                      # integer offsets: v3 kernel; bilinear: v2 kernel with the guarded fp32 blend
         return "deform_int_v3_kernel" if op.a.get("mode", 0) == 0 else "deform_dw_v2_kernel"
-    return {"pw": "pw_gemm_tc_kernel", "dw": "dw3x3_v2_kernel", "stem": "stem_kernel"}[op.kind]
+    # depthwise: dw3x3_tma_kernel (input tile staged by TMA; every depthwise layer of config c) or dw3x3_v2_kernel (LDG rows)
+    return {"pw": "pw_gemm_tc_kernel", "dw": "dw3x3_kernels", "stem": "stem_kernel"}[op.kind]
 
 
 def ncu_traffic():

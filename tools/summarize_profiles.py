@@ -20,8 +20,8 @@ LAUNCHES_PER_STEP = 66          # kernels of one forward + decode (memset exclud
 
 
 def fam(name):
-    n = name.split("(")[0].replace("void ", "")
-    return n.split("<")[0]
+    n = name.split("(")[0].replace("void ", "").split("<")[0]
+    return "dw3x3_kernels" if n in ("dw3x3_v2_kernel", "dw3x3_tma_kernel") else n      # bench.py's family names
 
 
 def launch_list():
@@ -106,5 +106,5 @@ def full(kernel):
 
 if __name__ == "__main__":
     launch_list()
-    for k in ("pw_gemm_tc", "deform_int_v3", "dw3x3_v2", "heads_fused"):
+    for k in ("pw_gemm_tc", "deform_int_v3", "dw3x3_tma", "heads_fused"):
         full(k)
