@@ -178,8 +178,15 @@ int dw_tma_launch(const DwDevice& d, const int8_t* in, int in_pitch, int8_t* out
                                                      : (lo_on ? dw3x3_tma_kernel<1, true> : dw3x3_tma_kernel<1, false>);
   static bool attr_set[4] = {false, false, false, false};
   const int ai = (stride == 2 ? 2 : 0) + (lo_on ? 1 : 0);
-  if (!attr_set[ai]) { CDN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); attr_set[ai] = true; }
-  const unsigned blocks = (unsigned)std::min<long long>(ntiles, (long long)cdn_num_sms() * DT_CTAS);
+  if (!attr_set[ai]) {
+    CDN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CDN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    attr_set[ai] = true;
+  }
+  // persistent grid = the CTAs that are resident at this shared-memory size (227 KB per SM, 1 KB reserved per CTA; registers
+  // allow DT_CTAS)
+  const int per_sm = std::max(1, std::min<int>(DT_CTAS, (int)((227 * 1024) / (smem + 1024))));
+  const unsigned blocks = (unsigned)std::min<long long>(ntiles, (long long)cdn_num_sms() * per_sm);
   cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(DT_THREADS); cfg.stream = st; cfg.dynamicSmemBytes = smem;
   cudaLaunchAttribute attr[1];

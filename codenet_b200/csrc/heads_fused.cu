@@ -25,6 +25,7 @@
 #ifndef HF_RQ
 #define HF_RQ rq_int_hi
 #endif
+#define HF_SMEM_MAX (96 * 1024)              // N = 128 head planes: 1024 + 32768 + 32768 + 23040 + 4096 + 64
 #define HF_TW 4                              // stored columns per tile
 #define HF_TH 8                              // stored rows per tile
 
@@ -230,7 +231,7 @@ int heads_fused_launch(const DwDevice& dw, const PwDevice& pw, const int8_t* in,
   p.in_pitch = in_pitch; p.in_bytes = (HF_TH + 2) * (HF_TW + 2) * in_pitch;
   p.Hs = Hs; p.Ws = Ws; p.tiles_x = Ws / HF_TW; p.tiles_y = Hs / HF_TH;
   const long long ntiles = (long long)batch * p.tiles_x * p.tiles_y;
-  CDN_CHECK(ntiles < (1ll << 31) - 2 * 148 * HF_CTAS, CDN_ERR_INVALID, "heads_fused: tensor too large for 32-bit indexing");
+  CDN_CHECK(ntiles < (1ll << 31) - 2 * 160 * HF_CTAS, CDN_ERR_INVALID, "heads_fused: tensor too large for 32-bit indexing");
   CDN_CHECK(p.in_bytes % 128 == 0, CDN_ERR_INVALID, "heads_fused: staged tile must be a multiple of 128 bytes");
   CUtensorMap tmI;
   if (int r = make_tmap_nhwc(&tmI, in, (uint64_t)in_pitch, (uint64_t)Ws, (uint64_t)Hs, (uint64_t)batch, HF_TW + 2, HF_TH + 2)) return r;
@@ -245,15 +246,22 @@ int heads_fused_launch(const DwDevice& dw, const PwDevice& pw, const int8_t* in,
   p.out = out_f32; p.ppi = 4 * Hs * Ws; p.Wout = 2 * Ws;
   const int threads = std::max(128, (p.nthreads + 31) / 32 * 32);
   const size_t smem = 1024 + 2 * 16384 + 2 * (size_t)p.NB * 128 + 2 * (size_t)p.in_bytes + (size_t)p.NB * 32 + 64;
-  CDN_CHECK(smem <= 76 * 1024, CDN_ERR_INVALID, "heads_fused: %zu bytes of shared memory", smem);
-  static bool attr_set[2] = {false, false};
+  CDN_CHECK(smem <= HF_SMEM_MAX, CDN_ERR_INVALID, "heads_fused: %zu bytes of shared memory", smem);
   const bool lo_on = p.lo_i > -128;
   auto kern = lo_on ? heads_fused_kernel<true> : heads_fused_kernel<false>;
-  if (!attr_set[lo_on]) {                    // upper bound over NB <= 128: checked above
-    CDN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 76 * 1024));
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[lo_on]) {
+    CDN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, HF_SMEM_MAX));
+    // the kernel lives in shared memory (input by TMA, A tile, weights) and has no use for L1: without this the driver's
+    // carve-out left room for two CTAs per SM only (0.67 instead of 0.43 ms)
+    CDN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     attr_set[lo_on] = true;
   }
-  const unsigned blocks = (unsigned)std::min<long long>(ntiles, (long long)cdn_num_sms() * HF_CTAS);
+  // persistent grid: the CTAs that are resident at this shared-memory size (227 KB per SM, 1 KB reserved per CTA): 3 per SM
+  // for the 20-class heads, 2 for 80 classes.  (cudaOccupancyMaxActiveBlocksPerMultiprocessor answered 2 for the 66 KB
+  // configuration that ncu shows running 3 per SM, which cost a third of the throughput; registers allow 3 in every case.)
+  const int per_sm = std::max(1, std::min<int>(HF_CTAS, (int)((227 * 1024) / (smem + 1024))));
+  const unsigned blocks = (unsigned)std::min<long long>(ntiles, (long long)cdn_num_sms() * per_sm);
   cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(threads); cfg.stream = st; cfg.dynamicSmemBytes = smem;
   cudaLaunchAttribute attr[1];
