@@ -56,7 +56,9 @@ int cdn_check_device(int device);
 /* Bring-up / measurement switches, never needed in production.  bit 0: 1x1 convolutions on the SIMT cross-check kernel
  * instead of tcgen05; bit 1: no CUDA graph (eager launches); bit 4: in-kernel phase cycle accounting of the GEMM
  * (tools/pw_phase_cycles.py); bit 6: no programmatic dependent launch; bit 7 (read when a layer is built): guarded fp32
- * requantisation instead of the integer form (same results, A/B timing); bits 2, 3, 5: experiments that BREAK results. */
+ * requantisation instead of the integer form (same results, A/B timing); bit 8: never fuse the heads' tail (as option
+ * "fuse_heads" = 0); bit 9: depthwise convs on the LDG kernel instead of the TMA-staged one, bit 10: the stride-2 ones only
+ * (same results, A/B timing); bits 2, 3, 5: experiments that BREAK results. */
 int cdn_set_debug_flags(unsigned flags);
 
 /* ---- per-output-channel requantisation constants (host arrays, length n) ------------------------------- */
