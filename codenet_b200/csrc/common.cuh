@@ -23,6 +23,14 @@ int cdn_fail(int code, const char* fmt, ...);
 
 extern unsigned g_cdn_debug_flags;
 int cdn_num_sms();
+// cudaFuncSetAttribute is per device: true the first time it is called for the current device with this flag array
+inline bool cdn_first_on_device(bool (&done)[64]) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;     // unknown device: set the attributes again
+  if (done[dev]) return false;
+  done[dev] = true;
+  return true;
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // Requantisation  q = clamp(rint(fl64(fl64(acc*M) + B)), lo, 127)   (DESIGN.md "requantisation")

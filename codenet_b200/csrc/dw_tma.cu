@@ -176,12 +176,11 @@ int dw_tma_launch(const DwDevice& d, const int8_t* in, int in_pitch, int8_t* out
   const bool lo_on = p.lo_i > -128;
   void (*kern)(CUtensorMap, DwTParams) = stride == 2 ? (lo_on ? dw3x3_tma_kernel<2, true> : dw3x3_tma_kernel<2, false>)
                                                      : (lo_on ? dw3x3_tma_kernel<1, true> : dw3x3_tma_kernel<1, false>);
-  static bool attr_set[4] = {false, false, false, false};
+  static bool attr_set[4][64] = {};
   const int ai = (stride == 2 ? 2 : 0) + (lo_on ? 1 : 0);
-  if (!attr_set[ai]) {
+  if (cdn_first_on_device(attr_set[ai])) {
     CDN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     CDN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    attr_set[ai] = true;
   }
   // persistent grid = the CTAs that are resident at this shared-memory size (227 KB per SM, 1 KB reserved per CTA; registers
   // allow DT_CTAS)

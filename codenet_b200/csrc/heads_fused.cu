@@ -249,13 +249,12 @@ int heads_fused_launch(const DwDevice& dw, const PwDevice& pw, const int8_t* in,
   CDN_CHECK(smem <= HF_SMEM_MAX, CDN_ERR_INVALID, "heads_fused: %zu bytes of shared memory", smem);
   const bool lo_on = p.lo_i > -128;
   auto kern = lo_on ? heads_fused_kernel<true> : heads_fused_kernel<false>;
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[lo_on]) {
+  static bool attr_set[2][64] = {};
+  if (cdn_first_on_device(attr_set[lo_on])) {
     CDN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, HF_SMEM_MAX));
     // the kernel lives in shared memory (input by TMA, A tile, weights) and has no use for L1: without this the driver's
     // carve-out left room for two CTAs per SM only (0.67 instead of 0.43 ms)
     CDN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    attr_set[lo_on] = true;
   }
   // persistent grid: the CTAs that are resident at this shared-memory size (227 KB per SM, 1 KB reserved per CTA): 3 per SM
   // for the 20-class heads, 2 for 80 classes.  (cudaOccupancyMaxActiveBlocksPerMultiprocessor answered 2 for the 66 KB

@@ -729,13 +729,12 @@ extern "C" int cdn_debug_read_cycles(unsigned long long* out16, int reset) {
 }
 
 int pw_init_attrs() {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};
+  if (cdn_first_on_device(attr_set)) {
     CDN_CUDA(cudaFuncSetAttribute(pw_gemm_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_LIMIT));
     CDN_CUDA(cudaFuncSetAttribute(pw_gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_LIMIT));
     CDN_CUDA(cudaFuncSetAttribute(pw_gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_LIMIT));
     CDN_CUDA(cudaFuncSetAttribute(pw_gemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_LIMIT));
-    attr_set = true;
   }
   return 0;
 }
