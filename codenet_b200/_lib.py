@@ -95,6 +95,9 @@ EXPORTS = {
     "cdn_engine_run_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p]),
     "cdn_engine_run_host_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "cdn_engine_submit_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
+    "cdn_engine_submit_host_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
+    "cdn_engine_wait": (C.c_int, [C.c_void_p, C.c_int]),
     "cdn_engine_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "cdn_engine_read_tensor": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "cdn_engine_read_heads": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),

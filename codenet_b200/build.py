@@ -24,17 +24,25 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     extra = os.environ.get("CDN_NVCC_EXTRA", "").split()      # experiments only (e.g. -DPW_EPI_WARPS=8)
-    objs = []
-    logs = []
-    for src in SOURCES:
+    from concurrent.futures import ThreadPoolExecutor
+
+    def compile_one(src):
         obj = os.path.join(CSRC, src.replace(".cu", ".o"))
+        deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))] + \
+               [os.path.join(CSRC, src), os.path.join(HERE, "..", "include", "codenet_b200.h")]
+        if not force and not extra and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(d) for d in deps):
+            return obj, ""                           # up to date
         cmd = [NVCC] + FLAGS + extra + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
-        logs.append(r.stderr)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("nvcc failed on %s" % src)
-        objs.append(obj)
+        return obj, r.stderr
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as ex:
+        res = list(ex.map(compile_one, SOURCES))
+    objs = [r[0] for r in res]
+    logs = [r[1] for r in res]
     cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

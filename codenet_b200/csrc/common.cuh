@@ -9,6 +9,7 @@
 #include <math.h>
 #include <vector>
 #include <string>
+#include <mutex>
 #include "../../include/codenet_b200.h"
 
 // ---------------------------------------------------------------------------------------------------------
@@ -23,10 +24,14 @@ int cdn_fail(int code, const char* fmt, ...);
 
 extern unsigned g_cdn_debug_flags;
 int cdn_num_sms();
-// cudaFuncSetAttribute is per device: true the first time it is called for the current device with this flag array
+// cudaFuncSetAttribute is per device: true the first time it is called for the current device with this flag array.
+// Engines on different devices may be driven from different host threads: the flag tables are guarded by one mutex (a
+// second caller may see "first" only after the first has returned from here, and setting an attribute twice is harmless).
+std::mutex& cdn_attr_mutex();
 inline bool cdn_first_on_device(bool (&done)[64]) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;     // unknown device: set the attributes again
+  std::lock_guard<std::mutex> lk(cdn_attr_mutex());
   if (done[dev]) return false;
   done[dev] = true;
   return true;

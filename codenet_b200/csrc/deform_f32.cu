@@ -213,8 +213,8 @@ extern "C" int cdn_pw_f32(const float* input, const float* weight, const float* 
   const long long total = (long long)B * pixels_per_image;
   if (total == 0) return 0;
   const size_t smem = (size_t)PWF_CO * C * sizeof(float);
-  static bool attr = false;
-  if (!attr) { CDN_CUDA(cudaFuncSetAttribute(pw_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr = true; }
+  static bool attr_set[64] = {};             // function attributes are per DEVICE
+  if (cdn_first_on_device(attr_set)) CDN_CUDA(cudaFuncSetAttribute(pw_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   dim3 grid((unsigned)((total + 127) / 128), (unsigned)((Co + PWF_CO - 1) / PWF_CO));
   pw_f32_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(input, weight, bias, output, C, Co, pixels_per_image, total);
   CDN_LAUNCH_CHECK("pw_f32_kernel");

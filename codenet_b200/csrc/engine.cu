@@ -12,10 +12,14 @@ int cdn_fail(int code, const char* fmt, ...) {
   va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
   return code;
 }
-int cdn_num_sms() {
-  static int sms = 0;
-  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
-  return sms;
+std::mutex& cdn_attr_mutex() { static std::mutex m; return m; }
+int cdn_num_sms() {                            // SM count of the CURRENT device (cached per device)
+  static int sms[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  std::lock_guard<std::mutex> lk(cdn_attr_mutex());
+  if (!sms[dev]) { cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev); if (sms[dev] <= 0) sms[dev] = 148; }
+  return sms[dev];
 }
 
 int dev_requant_upload(DevRequant& d, const cdn_requant* rq, const int32_t* acc_bias_host, int n_pad) {
@@ -288,6 +292,11 @@ struct cdn_engine {
   float* lut = nullptr;                      // 3 x 256 normalisation table for uint8 input
   cudaStream_t s_compute = nullptr, s_copy = nullptr;
   std::vector<cudaEvent_t> ev;
+  // pipelined host path (submit / wait): two input + detection slots, so the H2D of step n+1 overlaps the compute of step n
+  struct Slot {
+    uint8_t* d_img = nullptr; float* dets = nullptr; int32_t* inds = nullptr;
+    cudaEvent_t copied = nullptr, done = nullptr; int busy = 0, used = 0;
+  } slots[2];
   int host_chunk = 64, use_graph = 1, hm_logits = 0;
   int fuse_heads = 1;                        // heads.dw2 + heads.out as one kernel when the pair is eligible (heads_fused.cu)
   // graph cache
@@ -330,6 +339,11 @@ extern "C" int cdn_engine_destroy(cdn_engine* e) {
   for (auto& t : e->tensors) cudaFree(t.ptr);
   cudaFree(e->heads); cudaFree(e->dec_scratch); cudaFree(e->dets); cudaFree(e->inds); cudaFree(e->stem_tmp); cudaFree(e->d_img); cudaFree(e->lut);
   for (auto ev : e->ev) cudaEventDestroy(ev);
+  for (auto& sl : e->slots) {
+    cudaFree(sl.d_img); cudaFree(sl.dets); cudaFree(sl.inds);
+    if (sl.copied) cudaEventDestroy(sl.copied);
+    if (sl.done) cudaEventDestroy(sl.done);
+  }
   if (e->s_compute) cudaStreamDestroy(e->s_compute);
   if (e->s_copy) cudaStreamDestroy(e->s_copy);
   delete e;
@@ -680,6 +694,56 @@ extern "C" int cdn_engine_run_host(cdn_engine* e, const float* h_img, int batch,
 }
 extern "C" int cdn_engine_run_host_u8(cdn_engine* e, const uint8_t* h_img, int batch, float* h_dets, int32_t* h_inds) {
   return engine_run_host_any(e, h_img, 1, batch, h_dets, h_inds);
+}
+
+// ---- pipelined host path ------------------------------------------------------------------------------------------------
+// submit(slot) enqueues H2D (copy stream) -> forward + decode (compute stream) -> D2H of the detections and returns at once;
+// wait(slot) blocks until that step's detections are in the caller's host buffers.  With two slots in flight the copy of
+// step n+1 runs while step n computes: the step time becomes max(copy, compute) instead of their (chunk-pipelined) sum.
+// The activations are shared by both slots; steps are serialised on the compute stream.  Host buffers should be pinned.
+static int engine_submit_any(cdn_engine* e, const void* h_img, int is_u8, int batch, float* h_dets, int32_t* h_inds, int slot) {
+  ENG_CHECK(e);
+  CDN_CHECK(e->finalized, CDN_ERR_STATE, "engine not finalized");
+  CDN_CHECK(slot >= 0 && slot < 2, CDN_ERR_INVALID, "submit: slot must be 0 or 1");
+  CDN_CHECK(batch > 0 && batch <= e->max_batch && h_img && h_dets, CDN_ERR_INVALID, "submit: bad arguments");
+  CDN_CHECK(!is_u8 || e->lut != nullptr, CDN_ERR_STATE, "uint8 input needs cdn_engine_set_normalization first");
+  CDN_CUDA(cudaSetDevice(e->device));
+  cdn_engine::Slot& sl = e->slots[slot];
+  CDN_CHECK(!sl.busy, CDN_ERR_STATE, "submit: slot %d is still in flight (call cdn_engine_wait first)", slot);
+  if (!sl.d_img) {
+    CDN_CUDA(cudaMalloc((void**)&sl.d_img, (size_t)e->max_batch * 3 * e->in_H * e->in_W * sizeof(float)));
+    CDN_CUDA(cudaMalloc((void**)&sl.dets, (size_t)e->max_batch * e->K * 6 * sizeof(float)));
+    CDN_CUDA(cudaMalloc((void**)&sl.inds, (size_t)e->max_batch * e->K * sizeof(int32_t)));
+    CDN_CUDA(cudaEventCreateWithFlags(&sl.copied, cudaEventDisableTiming));
+    CDN_CUDA(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+  }
+  const size_t bytes = (size_t)batch * 3 * e->in_H * e->in_W * (is_u8 ? 1 : sizeof(float));
+  if (sl.used) CDN_CUDA(cudaStreamWaitEvent(e->s_copy, sl.done, 0));     // the previous step of this slot has consumed its input
+  CDN_CUDA(cudaMemcpyAsync(sl.d_img, h_img, bytes, cudaMemcpyHostToDevice, e->s_copy));
+  CDN_CUDA(cudaEventRecord(sl.copied, e->s_copy));
+  CDN_CUDA(cudaStreamWaitEvent(e->s_compute, sl.copied, 0));
+  if (int r = engine_run_any(e, sl.d_img, is_u8, batch, nullptr, nullptr, nullptr, sl.dets, sl.inds, e->s_compute)) return r;
+  CDN_CUDA(cudaMemcpyAsync(h_dets, sl.dets, (size_t)batch * e->K * 6 * sizeof(float), cudaMemcpyDeviceToHost, e->s_compute));
+  if (h_inds) CDN_CUDA(cudaMemcpyAsync(h_inds, sl.inds, (size_t)batch * e->K * sizeof(int32_t), cudaMemcpyDeviceToHost, e->s_compute));
+  CDN_CUDA(cudaEventRecord(sl.done, e->s_compute));
+  sl.busy = 1; sl.used = 1;
+  return 0;
+}
+extern "C" int cdn_engine_submit_host(cdn_engine* e, const float* h_img, int batch, float* h_dets, int32_t* h_inds, int slot) {
+  return engine_submit_any(e, h_img, 0, batch, h_dets, h_inds, slot);
+}
+extern "C" int cdn_engine_submit_host_u8(cdn_engine* e, const uint8_t* h_img, int batch, float* h_dets, int32_t* h_inds, int slot) {
+  return engine_submit_any(e, h_img, 1, batch, h_dets, h_inds, slot);
+}
+extern "C" int cdn_engine_wait(cdn_engine* e, int slot) {
+  ENG_CHECK(e);
+  CDN_CHECK(slot >= 0 && slot < 2, CDN_ERR_INVALID, "wait: slot must be 0 or 1");
+  cdn_engine::Slot& sl = e->slots[slot];
+  if (!sl.busy) return 0;
+  CDN_CUDA(cudaSetDevice(e->device));
+  sl.busy = 0;
+  CDN_CUDA(cudaEventSynchronize(sl.done));
+  return 0;
 }
 
 extern "C" int cdn_engine_read_tensor(cdn_engine* e, int tensor, int batch, int8_t* h_out) {

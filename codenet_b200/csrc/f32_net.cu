@@ -295,8 +295,8 @@ extern "C" int cdn_pw_slice_f32(const float* input, int in_ctotal, int in_coff, 
     CDN_LAUNCH_CHECK("pw_tile_f32_kernel");
     return 0;
   }
-  static bool attr = false;
-  if (!attr) { CDN_CUDA(cudaFuncSetAttribute(pw_slice_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr = true; }
+  static bool attr_set[64] = {};             // function attributes are per DEVICE
+  if (cdn_first_on_device(attr_set)) CDN_CUDA(cudaFuncSetAttribute(pw_slice_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   dim3 grid((unsigned)((total + 127) / 128), (unsigned)((Co + PWS_CO - 1) / PWS_CO));
   pw_slice_f32_kernel<<<grid, 128, (size_t)PWS_CO * C * sizeof(float), (cudaStream_t)stream>>>(
       input, in_ctotal, in_coff, C, weight, bias, output, out_ctotal, out_coff, out_cstride, Co, relu, pixels_per_image, total);

@@ -60,7 +60,9 @@ class Engine:
     # -- construction helpers -------------------------------------------------------------------------------------
     @classmethod
     def from_state_dict(cls, cfg: NetConfig, state: Dict[str, np.ndarray], in_H: int, in_W: int, max_batch: int,
-                        offset_mode: str = "round", device: int = 0, K: int = 100):
+                        offset_mode: str = "bilinear", device: int = 0, K: int = 100):
+        """`offset_mode`: "bilinear" = the reference's semantics (fractional offsets, quant_modules.py:668-671; the default
+        everywhere); "round" = the co-designed integer-offset mode (explicit opt-in)."""
         state = {k: (v.detach().cpu().numpy() if hasattr(v, "detach") else np.asarray(v)) for k, v in state.items()}
         return cls(build_plan(cfg, state, in_H, in_W, offset_mode), max_batch, device, K)
 
@@ -147,6 +149,18 @@ class Engine:
         fn = self.lib.cdn_engine_run_host_u8 if images.dtype == np.uint8 else self.lib.cdn_engine_run_host
         _lib.check(fn(self._h, C.c_void_p(images.ctypes.data), B, C.c_void_p(dets.ctypes.data), C.c_void_p(inds.ctypes.data)))
         return dets, inds
+
+    def submit_host(self, images: np.ndarray, dets: np.ndarray, inds: Optional[np.ndarray], slot: int):
+        """Pipelined run_host: enqueue H2D -> forward + decode -> D2H for `slot` (0 / 1) and return at once; `wait(slot)`
+        blocks until `dets` / `inds` hold the step's result.  Keep both slots in flight and the copy of step n+1 overlaps
+        the compute of step n.  All three host arrays must be pinned and stay alive until `wait`."""
+        assert images.dtype in (np.float32, np.uint8) and images.flags["C_CONTIGUOUS"]
+        fn = self.lib.cdn_engine_submit_host_u8 if images.dtype == np.uint8 else self.lib.cdn_engine_submit_host
+        _lib.check(fn(self._h, C.c_void_p(images.ctypes.data), images.shape[0], C.c_void_p(dets.ctypes.data),
+                      C.c_void_p(inds.ctypes.data) if inds is not None else None, int(slot)))
+
+    def wait(self, slot: int):
+        _lib.check(self.lib.cdn_engine_wait(self._h, int(slot)))
 
     def profile(self, images):
         """Per-op device times (ms) of one eager run: list of (op name, kind, ms) + ('decode', ...)."""

@@ -244,6 +244,14 @@ int cdn_engine_set_normalization(cdn_engine* e, const float* mean3, const float*
 int cdn_engine_run_u8(cdn_engine* e, const uint8_t* d_img, int batch, float* d_hm, float* d_wh, float* d_reg,
                       float* d_dets, int32_t* d_inds, cdn_stream_t stream);
 int cdn_engine_run_host_u8(cdn_engine* e, const uint8_t* h_img, int batch, float* h_dets, int32_t* h_inds);
+/* Pipelined host path -- what a prefetching test loop (test.py:62-80: a DataLoader worker prepares image n+1 while the
+ * detector runs image n) maps to.  submit enqueues H2D -> forward + decode -> D2H for `slot` (0 or 1) and returns without
+ * synchronising; wait blocks until that slot's detections are in h_dets / h_inds.  With both slots in flight the H2D of
+ * step n+1 overlaps the compute of step n.  Host buffers must stay valid until wait returns and should be pinned;
+ * submitting to a slot that is still in flight is CDN_ERR_STATE. */
+int cdn_engine_submit_host(cdn_engine* e, const float* h_img, int batch, float* h_dets, int32_t* h_inds, int slot);
+int cdn_engine_submit_host_u8(cdn_engine* e, const uint8_t* h_img, int batch, float* h_dets, int32_t* h_inds, int slot);
+int cdn_engine_wait(cdn_engine* e, int slot);
 /* Options: "host_chunk" (granularity of the H2D / compute pipeline of run_host: chunks grow x1.6 from host_chunk/2,
  * default 64), "use_graph" (replay the launch sequence as a CUDA graph, default 1), "hm_logits" (cdn_engine_run writes
  * the heat map as logits, what PoseShuffleNetV2.forward returns, instead of post-sigmoid; default 0), "fuse_heads"

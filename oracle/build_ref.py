@@ -64,6 +64,54 @@ def build(force=False, verbose=False):
     return so
 
 
+REF_ROOT = "/root/reference"
+PY_OUT = os.path.join(OUT, "py")
+# what oracle/ref_harness.py imports (and their package __init__ files): the network, the operator modules, the
+# quantizer, decode and the post-processing helpers.  Nothing else of the tree is needed to run the path.
+PY_FILES = [
+    "lib/models/__init__.py", "lib/models/decode.py", "lib/models/utils.py",
+    "lib/models/networks/__init__.py", "lib/models/networks/shufflenetv2_dcn.py",
+    "lib/models/external/__init__.py", "lib/models/external/modules/__init__.py",
+    "lib/models/external/modules/dcn_deform_conv.py", "lib/models/external/functions/__init__.py",
+    "lib/models/external/functions/dcn_deform_conv.py",
+    "lib/utils/__init__.py", "lib/utils/post_process.py", "lib/utils/image.py", "lib/utils/ddd_utils.py",
+    "portable_quantizer/__init__.py", "portable_quantizer/quant_modules.py",
+    "portable_quantizer/quantization_utils/__init__.py", "portable_quantizer/quantization_utils/quant_utils.py",
+    "portable_quantizer/quantization_utils/quantize_model.py",
+]
+
+
+def py_root():
+    """Directory holding an importable reference tree: /root/reference in the build container, the installed copy
+    oracle/_ref/py on the GPU box (None when neither exists)."""
+    if os.path.isdir(os.path.join(REF_ROOT, "lib", "models")):
+        return REF_ROOT
+    if os.path.isdir(os.path.join(PY_OUT, "lib", "models")):
+        return PY_OUT
+    return None
+
+
+def build_py(force=False):
+    """Installs the reference's Python files of the path, UNMODIFIED, into the git-ignored oracle/_ref/py so that
+    `bench.py --impl reference` / `cpu_baseline` can time the reference's own PyTorch CPU forward on the GPU box's host
+    cores (the counterpart of `pip install --target baseline/_ref`: the reference has no setup.py).  Build container
+    only; the copy is never committed (oracle/_ref is git-ignored) and never imported by the product."""
+    import shutil
+    if not os.path.isdir(os.path.join(REF_ROOT, "lib", "models")):
+        return PY_OUT if os.path.isdir(PY_OUT) else None
+    for rel in PY_FILES:
+        src, dst = os.path.join(REF_ROOT, rel), os.path.join(PY_OUT, rel)
+        if not os.path.exists(src):
+            if rel.endswith("__init__.py"):             # namespace-style directories of the reference: keep them importable
+                os.makedirs(os.path.dirname(dst), exist_ok=True)
+                continue
+            raise FileNotFoundError(src)
+        if force or not os.path.exists(dst) or os.path.getmtime(dst) < os.path.getmtime(src):
+            os.makedirs(os.path.dirname(dst), exist_ok=True)
+            shutil.copyfile(src, dst)
+    return PY_OUT
+
+
 NMS_PYX = "/root/reference/lib/models/external/nms.pyx"
 
 

@@ -13,8 +13,10 @@ Vectors produced (all from the reference's own code through oracle/ref_harness.p
                     (SURVEY.md 8(d) recipe), per offset mode and resolution
   codenet1x_256_{round,bilinear}.npz   fp64 reference forward + decode on config a (256^2), with int8-grid
                     intermediates
-  codenet1x_512_round.npz   one 512^2 image (config c geometry): detections + strided output samples
-  codenet_w2mp_{calib,256_round}.npz   the same for the w2 + S2/MaxPool configuration (config e geometry), one 256^2 image
+  codenet1x_512_{round,bilinear}.npz   two 512^2 images (config c geometry): detections, DENSE int8 grids of every stage
+                    output and of the deformable path, dense heads (fp32-rounded)
+  codenet_w2mp_{calib,256_round,512_round}.npz   the same for the w2 + S2/MaxPool configuration (config e geometry), one image
+                    at 256^2 and one (dense) at 512^2
   codenet_float_{1x,2x_coco}_256.npz   the float (unquantised) model evaluated by the reference in fp64: heads + detections
   post_kat.npz      ctdet_post_process (lib/utils/post_process.py:86-103) on random detections
   ref_state_keys.json   state-dict key spaces of the reference network before / after quantisation (1x, w2, maxpool)
@@ -199,28 +201,36 @@ def _init_ranges(m, x):
         seen[mod] = (min(cur[0], lo), max(cur[1], hi))
 
     hooks = [a.register_forward_pre_hook(pre) for a in acts]
-    for it in range(12):
-        seen.clear()
-        with torch.no_grad():
-            m(x)
-        grew = 0
-        for a in acts:
-            lo, hi = seen[a]
-            cl, ch = a.x_min.item(), a.x_max.item()
-            if lo < cl or hi > ch:
-                grew += 1
-                nl, nh = min(lo, cl), max(hi, ch)
-                pad = 1e-6 * max(abs(nl), abs(nh), 1e-3)
-                nl32 = np.float32(nl - pad) if nl != 0.0 else np.float32(0.0)
-                a.x_min.fill_(float(nl32)); a.x_max.fill_(float(np.float32(nh + pad)))
-        if not grew:
-            break
-    else:
+
+    def widen():
+        for it in range(12):
+            seen.clear()
+            with torch.no_grad():
+                m(x)
+            grew = 0
+            for a in acts:
+                lo, hi = seen[a]
+                cl, ch = a.x_min.item(), a.x_max.item()
+                if lo < cl or hi > ch:
+                    grew += 1
+                    nl, nh = min(lo, cl), max(hi, ch)
+                    pad = 1e-6 * max(abs(nl), abs(nh), 1e-3)
+                    nl32 = np.float32(nl - pad) if nl != 0.0 else np.float32(0.0)
+                    a.x_min.fill_(float(nl32)); a.x_max.fill_(float(np.float32(nh + pad)))
+            if not grew:
+                return
         raise RuntimeError("range calibration did not converge")
-    for h in hooks:
-        h.remove()
+
+    widen()
     for a in acts:                                     # fp32-representable, as a checkpoint would hold
         a.x_min.fill_(float(np.float32(a.x_min.item()))); a.x_max.fill_(float(np.float32(a.x_max.item())))
+    # the rounding to fp32 may have moved a bound inward by half an ulp: verify with the final values and widen again if
+    # anything now leaves its range (every value set from here on is fp32-representable, so the rounding is idempotent)
+    widen()
+    for h in hooks:
+        h.remove()
+    for a in acts:
+        assert a.x_min.item() == float(np.float32(a.x_min.item())) and a.x_max.item() == float(np.float32(a.x_max.item()))
 
 
 def _ranges_of(m, g):
@@ -279,6 +289,10 @@ def _run_and_capture(m, g, x, K=100):
     return cap
 
 
+DENSE_512 = ("stem", "layer1.out", "layer2.out", "layer3.out", "layer4", "up0.deform", "up0.out", "up1.deform", "up1.out",
+             "up2.deform", "up2.out")
+
+
 def codenet1x():
     cfg = NetConfig(num_classes=20)
     g = build_graph(cfg)
@@ -298,7 +312,7 @@ def codenet1x():
             _init_ranges(m, T(xs).double())
             for lbl, r in _ranges_of(m, g).items():
                 calib["ranges_%s_%d/%s" % (mode, res, lbl)] = r
-            nimg = 2 if res == 256 else 1
+            nimg = 2
             cap = _run_and_capture(m, g, T(xs[:nimg]).double())
             # batch independence with frozen ranges
             cap1 = _run_and_capture(m, g, T(xs[:1]).double())
@@ -318,13 +332,18 @@ def codenet1x():
                     elif k.endswith("sval") or k == "dets":
                         out[k] = v
                 np.savez_compressed(os.path.join(OUT, "codenet1x_256_%s.npz" % mode), **out)
-            elif mode == "round":
+            else:
+                # 512^2 (config c geometry): DENSE int8 grids of the deformable path + dense fp32-rounded heads for both images,
+                # in both offset modes (the fp64 head values are within half an fp32 ulp of what is stored)
                 out["dets"] = cap["dets"]
                 for k in ("hm_logit", "wh", "reg"):
-                    out[k + "_s8"] = cap[k][:, :, ::8, ::8]
-                out["up2.out"] = cap["up2.out"].astype(np.int8)[:, :, ::4, ::4]
-                out["stem"] = cap["stem"].astype(np.int8)[:, :, ::4, ::4]
-                np.savez_compressed(os.path.join(OUT, "codenet1x_512_round.npz"), **out)
+                    out[k] = cap[k].astype(np.float32)
+                for k in DENSE_512:
+                    assert cap[k].min() >= -128 and cap[k].max() <= 127, (k, cap[k].min(), cap[k].max())
+                    out[k] = cap[k].astype(np.int8)
+                for i in range(3):
+                    out["up%d.sval" % i] = cap["up%d.sval" % i].astype(np.float32)
+                np.savez_compressed(os.path.join(OUT, "codenet1x_512_%s.npz" % mode), **out)
     np.savez_compressed(os.path.join(OUT, "codenet1x_calib.npz"), **calib)
     print("codenet1x ok")
 
@@ -355,8 +374,22 @@ def codenet_w2mp():
         elif k in ("hm_logit", "wh", "reg", "dets") or k.endswith("sval"):
             out[k] = v
     np.savez_compressed(os.path.join(OUT, "codenet_w2mp_256_round.npz"), **out)
+    print("codenet_w2mp 256 ok; unique scores:", len(np.unique(cap["dets"][0, :, 4])))
+    # 512^2 = BASELINE config e / config 4 geometry: ranges + one image, dense deformable path and heads
+    xs = make_images(2, 512, seed=3)
+    _init_ranges(m, T(xs).double())
+    for lbl, r in _ranges_of(m, g).items():
+        calib["ranges_round_512/%s" % lbl] = r
+    cap = _run_and_capture(m, g, T(xs[:1]).double())
+    out = {"seed_images": np.array(3), "nimg": np.array(1), "dets": cap["dets"]}
+    for k in ("hm_logit", "wh", "reg"):
+        out[k] = cap[k].astype(np.float32)
+    for k in DENSE_512:
+        assert cap[k].min() >= -128 and cap[k].max() <= 127, (k, cap[k].min(), cap[k].max())
+        out[k] = cap[k].astype(np.int8)
+    np.savez_compressed(os.path.join(OUT, "codenet_w2mp_512_round.npz"), **out)
     np.savez_compressed(os.path.join(OUT, "codenet_w2mp_calib.npz"), **calib)
-    print("codenet_w2mp ok; unique scores:", len(np.unique(cap["dets"][0, :, 4])))
+    print("codenet_w2mp 512 ok; unique scores:", len(np.unique(cap["dets"][0, :, 4])))
 
 
 def codenet_float():

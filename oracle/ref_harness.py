@@ -20,7 +20,20 @@ import types
 import torch
 import torch.nn as nn
 
-REF = os.environ.get("CODENET_REFERENCE", "/root/reference")
+def _find_ref():
+    """/root/reference in the build container; on the GPU box the unmodified copy that oracle/build_ref.build_py()
+    installed into the git-ignored oracle/_ref/py (it travels with the repository snapshot)."""
+    env = os.environ.get("CODENET_REFERENCE")
+    if env:
+        return env
+    here = os.path.dirname(os.path.abspath(__file__))
+    for cand in ("/root/reference", os.path.join(here, "_ref", "py")):
+        if os.path.isdir(os.path.join(cand, "lib", "models")):
+            return cand
+    return "/root/reference"
+
+
+REF = _find_ref()
 
 
 def available():

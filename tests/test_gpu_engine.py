@@ -7,7 +7,7 @@ from codenet_b200.arch import NetConfig
 from codenet_b200.engine import Engine
 from codenet_b200.synth import make_quant_state, make_images
 from oracle import int_oracle as io
-from util import assert_dets_match_tie_aware, int8_mismatch
+from util import check_reference_dets, int8_mismatch
 
 pytestmark = pytest.mark.gpu
 CFG = NetConfig(num_classes=20)
@@ -64,31 +64,91 @@ def test_engine_matches_reference_vectors_256(golden, calib, mode):
     inds = out["inds"].cpu().numpy()
     h64 = heads.astype(np.float64)
     odets, oinds = io.ctdet_decode(h64[:, :20], h64[:, 20:22], h64[:, 22:24], 100)
-    more, _ = io.ctdet_decode(h64[:, :20], h64[:, 20:22], h64[:, 22:24], 160)
     np.testing.assert_array_equal(inds, oinds)
     np.testing.assert_allclose(dets, odets, rtol=1e-5, atol=1e-4)
-    for b in range(2):
-        assert_dets_match_tie_aware(g["dets"][b], odets[b], more[b])
+    check_reference_dets(g["dets"][:2], h64[:, :20], h64[:, 20:22], h64[:, 22:24])
     eng.close()
 
 
-def test_engine_matches_reference_vectors_512(golden, calib):
+DENSE_512 = ("stem", "layer1.out", "layer2.out", "layer3.out", "layer4", "up0.deform", "up0.out", "up1.deform", "up1.out",
+             "up2.deform", "up2.out")
+
+
+@pytest.mark.parametrize("mode", ["round", "bilinear"])
+def test_engine_matches_reference_vectors_512(golden, calib, mode):
+    """Config c geometry, two images, both offset modes: DENSE int8 grids of every stage output and of the whole deformable
+    path, dense heads and the detections against the fp64 run of the unmodified reference (shufflenetv2_dcn.py:314-330)."""
     import torch
-    g = golden("codenet1x_512_round.npz")
-    eng = _engine(calib, "round", 512, 2)
-    x = make_images(2, 512, seed=3)[:1]
+    g = golden("codenet1x_512_%s.npz" % mode)
+    eng = _engine(calib, mode, 512, 2)
+    x = make_images(2, 512, seed=3)
     out = eng.run(torch.from_numpy(x).cuda())
     torch.cuda.synchronize()
-    assert int8_mismatch(eng.read_logical("stem", 1)[:, :, ::4, ::4], g["stem"]) == 0
-    assert int8_mismatch(eng.read_logical("up2.out", 1)[:, :, ::4, ::4], g["up2.out"]) == 0
-    heads = eng.read_heads(1)
-    ref = np.concatenate([g["hm_logit_s8"], g["wh_s8"], g["reg_s8"]], 1)
-    np.testing.assert_allclose(heads[:, :, ::8, ::8], ref, rtol=2e-7, atol=1e-7)
+    for k in DENSE_512:
+        assert g[k].shape[0] == 2
+        assert int8_mismatch(eng.read_logical(k, 2), g[k]) == 0, k
+    heads = eng.read_heads(2)
+    ref = np.concatenate([g["hm_logit"], g["wh"], g["reg"]], 1)          # fp32-rounded fp64 reference values
+    np.testing.assert_allclose(heads, ref, rtol=2e-7, atol=1e-7)
     h64 = heads.astype(np.float64)
     odets, oinds = io.ctdet_decode(h64[:, :20], h64[:, 20:22], h64[:, 22:24], 100)
-    more, _ = io.ctdet_decode(h64[:, :20], h64[:, 20:22], h64[:, 22:24], 160)
     np.testing.assert_array_equal(out["inds"].cpu().numpy(), oinds)
-    assert_dets_match_tie_aware(g["dets"][0], odets[0], more[0])
+    np.testing.assert_allclose(out["dets"].cpu().numpy(), odets, rtol=1e-5, atol=1e-4)
+    check_reference_dets(g["dets"][:2], h64[:, :20], h64[:, 20:22], h64[:, 22:24])
+    eng.close()
+
+
+def test_config_c_batch_256_equals_oracle(calib):
+    """The BENCHMARKED configuration (BASELINE config c: 512^2, batch 256 on one GPU; bench.py's images: 16 distinct ones
+    tiled): the last int8 grid, the heads and the top-K indices of the distinct images against the oracle, and every replica
+    equal to its original -- through the graph path bench.py times and through the pipelined host path (submit / wait)."""
+    import torch
+    st = make_quant_state(CFG, calib, "round", 512)
+    eng = Engine.from_state_dict(CFG, st, 512, 512, 256, offset_mode="round")
+    base = make_images(16, 512, seed=100)
+    x = np.concatenate([base] * 16)
+    xt = torch.from_numpy(x).cuda()
+    for _ in range(2):                                  # second call = graph replay, as in the timed loop
+        out = eng.run(xt, maps=False)
+    torch.cuda.synchronize()
+    inds, dets = out["inds"].cpu().numpy(), out["dets"].cpu().numpy()
+    up2 = eng.read_logical("up2.out", 256)
+    heads = eng.read_heads(256)
+    o = io.IntOracle(CFG, st, "round")
+    for i in range(16):
+        ref = o.forward(base[i:i + 1])
+        assert int8_mismatch(up2[i:i + 1], o.cap["up2.out"]) == 0, i
+        want = np.concatenate([ref["hm"], ref["wh"], ref["reg"]], 1).astype(np.float32)
+        np.testing.assert_array_equal(heads[i:i + 1], want)
+        h64 = want.astype(np.float64)
+        odets, oinds = io.ctdet_decode(h64[:, :20], h64[:, 20:22], h64[:, 22:24], 100)
+        np.testing.assert_array_equal(inds[i:i + 1], oinds)
+        np.testing.assert_allclose(dets[i:i + 1], odets, rtol=1e-5, atol=1e-4)
+    for r in range(1, 16):
+        assert up2[16 * r:16 * r + 16].tobytes() == up2[:16].tobytes(), r
+        assert heads[16 * r:16 * r + 16].tobytes() == heads[:16].tobytes(), r
+        np.testing.assert_array_equal(inds[16 * r:16 * r + 16], inds[:16])
+        np.testing.assert_array_equal(dets[16 * r:16 * r + 16], dets[:16])
+    # pipelined host path: uint8 images (normalisation in the stem), two slots in flight, four steps
+    mean, std = np.array([0.485, 0.456, 0.406], np.float32), np.array([0.229, 0.224, 0.225], np.float32)
+    eng.set_normalization(mean, std)
+    u8 = np.clip(np.rint((x.transpose(0, 2, 3, 1) * std + mean) * 255.0), 0, 255).astype(np.uint8)
+    u8_t = torch.from_numpy(np.ascontiguousarray(u8)).pin_memory()
+    want_d, want_i = eng.run_host(u8_t.numpy())
+    bufs = [(torch.empty((256, 100, 6), dtype=torch.float32).pin_memory(), torch.empty((256, 100), dtype=torch.int32).pin_memory())
+            for _ in range(2)]
+    for step in range(4):
+        sl = step & 1
+        if step >= 2:
+            eng.wait(sl)
+            assert bufs[sl][1].numpy().tobytes() == want_i.tobytes() and bufs[sl][0].numpy().tobytes() == want_d.tobytes(), step
+            bufs[sl][0].zero_(); bufs[sl][1].zero_()
+        eng.submit_host(u8_t.numpy(), bufs[sl][0].numpy(), bufs[sl][1].numpy(), sl)
+    with pytest.raises(_lib.CdnError):
+        eng.submit_host(u8_t.numpy(), bufs[0][0].numpy(), bufs[0][1].numpy(), 0)          # slot 0 is still in flight
+    for sl in (0, 1):
+        eng.wait(sl)
+        assert bufs[sl][1].numpy().tobytes() == want_i.tobytes() and bufs[sl][0].numpy().tobytes() == want_d.tobytes()
     eng.close()
 
 
@@ -267,6 +327,30 @@ def test_engine_w2_maxpool_matches_reference_vectors(golden):
     odets, oinds = io.ctdet_decode(h64[:, :20], h64[:, 20:22], h64[:, 22:24], 100)
     np.testing.assert_array_equal(out["inds"].cpu().numpy(), oinds)
     np.testing.assert_allclose(out["dets"].cpu().numpy(), odets, rtol=1e-5, atol=1e-4)
+    eng.close()
+
+
+def test_engine_w2_maxpool_512_matches_reference_vectors(golden):
+    """BASELINE config e / config 4 geometry at its own resolution (w2, stride-2 stem + MaxPool, 512^2): dense int8 grids of
+    the stage outputs and the deformable path (first deformable layer C = 2153), dense heads, detections."""
+    import torch
+    from util import maxpool3s2_int8
+    cfg = NetConfig(num_classes=20, w2=True, maxpool=True)
+    g = golden("codenet_w2mp_512_round.npz")
+    st = make_quant_state(cfg, golden("codenet_w2mp_calib.npz"), "round", 512)
+    eng = Engine.from_state_dict(cfg, st, 512, 512, 2, offset_mode="round")
+    x = make_images(2, 512, seed=3)[:1]
+    out = eng.run(torch.from_numpy(x.copy()).cuda())
+    torch.cuda.synchronize()
+    for k in DENSE_512:
+        ref = maxpool3s2_int8(g[k]) if k == "stem" else g[k]
+        assert int8_mismatch(eng.read_logical(k, 1), ref) == 0, k
+    heads = eng.read_heads(1)
+    np.testing.assert_allclose(heads, np.concatenate([g["hm_logit"], g["wh"], g["reg"]], 1), rtol=2e-7, atol=1e-7)
+    h64 = heads.astype(np.float64)
+    odets, oinds = io.ctdet_decode(h64[:, :20], h64[:, 20:22], h64[:, 22:24], 100)
+    np.testing.assert_array_equal(out["inds"].cpu().numpy(), oinds)
+    check_reference_dets(g["dets"][:1], h64[:, :20], h64[:, 20:22], h64[:, 22:24])
     eng.close()
 
 

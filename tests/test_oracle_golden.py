@@ -6,7 +6,7 @@ from codenet_b200.arch import NetConfig
 from codenet_b200.synth import make_quant_state, make_images
 from oracle import int_oracle as io
 from oracle import deform_ref
-from util import assert_dets_match_tie_aware, int8_mismatch
+from util import check_reference_dets, int8_mismatch
 
 CFG = NetConfig(num_classes=20)
 
@@ -88,24 +88,43 @@ def test_int_oracle_reproduces_reference_fp64(golden, calib, mode):
         np.testing.assert_allclose(o.cap["up%d.sval" % i], g["up%d.sval" % i], rtol=0, atol=1e-12)
     for n, k in (("hm", "hm_logit"), ("wh", "wh"), ("reg", "reg")):
         np.testing.assert_allclose(out[n], g[k], rtol=1e-12, atol=1e-12)
-    dets, _ = io.ctdet_decode(out["hm"], out["wh"], out["reg"], 100)
-    more, _ = io.ctdet_decode(out["hm"], out["wh"], out["reg"], 160)
-    for b in range(2):
-        assert_dets_match_tie_aware(g["dets"][b], dets[b], more[b])
+    check_reference_dets(g["dets"][:2], out["hm"], out["wh"], out["reg"])
 
 
-def test_int_oracle_512(golden, calib):
-    g = golden("codenet1x_512_round.npz")
-    st = make_quant_state(CFG, calib, "round", 512)
-    o = io.IntOracle(CFG, st, "round")
+DENSE_512 = ("stem", "layer1.out", "layer2.out", "layer3.out", "layer4", "up0.deform", "up0.out", "up1.deform", "up1.out",
+             "up2.deform", "up2.out")
+
+
+@pytest.mark.parametrize("mode", ["round", "bilinear"])
+def test_int_oracle_512(golden, calib, mode):
+    """Config c geometry, dense: every stage output, the whole deformable path, heads and detections of two images."""
+    g = golden("codenet1x_512_%s.npz" % mode)
+    st = make_quant_state(CFG, calib, mode, 512)
+    o = io.IntOracle(CFG, st, mode)
+    out = o.forward(make_images(2, 512, seed=3))
+    assert o.saturated == 0
+    for k in DENSE_512:
+        assert int8_mismatch(o.cap[k], g[k]) == 0, k
+    for n, k in (("hm", "hm_logit"), ("wh", "wh"), ("reg", "reg")):
+        np.testing.assert_array_equal(out[n].astype(np.float32), g[k])
+    check_reference_dets(g["dets"][:2], out["hm"], out["wh"], out["reg"])
+
+
+def test_int_oracle_w2_maxpool_512(golden):
+    """Config e geometry at 512^2 (first deformable layer C = 2153), dense."""
+    from codenet_b200.arch import NetConfig
+    from util import maxpool3s2_int8
+    cfg = NetConfig(num_classes=20, w2=True, maxpool=True)
+    g = golden("codenet_w2mp_512_round.npz")
+    st = make_quant_state(cfg, golden("codenet_w2mp_calib.npz"), "round", 512)
+    o = io.IntOracle(cfg, st, "round")
     out = o.forward(make_images(2, 512, seed=3)[:1])
-    assert int8_mismatch(o.cap["stem"][:, :, ::4, ::4], g["stem"]) == 0
-    assert int8_mismatch(o.cap["up2.out"][:, :, ::4, ::4], g["up2.out"]) == 0
-    for n, k in (("hm", "hm_logit_s8"), ("wh", "wh_s8"), ("reg", "reg_s8")):
-        np.testing.assert_allclose(out[n][:, :, ::8, ::8], g[k], rtol=1e-12, atol=1e-12)
-    dets, _ = io.ctdet_decode(out["hm"], out["wh"], out["reg"], 100)
-    more, _ = io.ctdet_decode(out["hm"], out["wh"], out["reg"], 160)
-    assert_dets_match_tie_aware(g["dets"][0], dets[0], more[0])
+    for k in DENSE_512:
+        ref = maxpool3s2_int8(g[k]) if k == "stem" else g[k]
+        assert int8_mismatch(o.cap[k], ref) == 0, k
+    for n, k in (("hm", "hm_logit"), ("wh", "wh"), ("reg", "reg")):
+        np.testing.assert_array_equal(out[n].astype(np.float32), g[k])
+    check_reference_dets(g["dets"][:1], out["hm"], out["wh"], out["reg"])
 
 
 def test_int_oracle_w2_maxpool(golden):
@@ -127,6 +146,4 @@ def test_int_oracle_w2_maxpool(golden):
     assert checked >= 20
     for n, k in (("hm", "hm_logit"), ("wh", "wh"), ("reg", "reg")):
         np.testing.assert_allclose(out[n], g[k], rtol=1e-12, atol=1e-12)
-    dets, _ = io.ctdet_decode(out["hm"], out["wh"], out["reg"], 100)
-    more, _ = io.ctdet_decode(out["hm"], out["wh"], out["reg"], 160)
-    assert_dets_match_tie_aware(g["dets"][0], dets[0], more[0])
+    check_reference_dets(g["dets"][:1], out["hm"], out["wh"], out["reg"])

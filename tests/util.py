@@ -2,7 +2,48 @@
 import numpy as np
 
 
-def assert_dets_match_tie_aware(dets, ref, ref_more=None, rtol=1e-5, atol=1e-5):
+def _plateau_mask(hm):
+    """[C,H,W] bool: the pixel has an 8-neighbour of the same class with EXACTLY the same logit.  The reference evaluates
+    `hmax == heat` (decode.py:10-16) on floating-point head outputs: two neighbours whose exact values are equal may differ
+    by an ulp there (summation order of its conv), and then only one of them survives as a peak.  Which one is decided by the
+    reference's rounding noise, not by the arithmetic of the path -- the exact oracle keeps both."""
+    C, H, W = hm.shape
+    p = np.full((C, H + 2, W + 2), np.nan)
+    p[:, 1:-1, 1:-1] = hm
+    m = np.zeros(hm.shape, bool)
+    for i in range(3):
+        for j in range(3):
+            if (i, j) != (1, 1):
+                m |= p[:, i:i + H, j:j + W] == hm
+    return m
+
+
+def assert_dets_match_tie_aware(dets, ref, ref_more=None, rtol=1e-5, atol=1e-5, hm=None, more_inds=None):
+    """`dets`: the REFERENCE's detections; `ref`: the oracle's.  Strict comparison (below) unless the reference dropped
+    members of an exact plateau (see _plateau_mask; needs the oracle's logits `hm` [C,H,W] and the indices `more_inds` of
+    `ref_more`): then every reference row must be one of the oracle's candidates, and every oracle row the reference lacks
+    must sit on a plateau or in the group tied with the K-th score."""
+    if hm is not None and not np.allclose(dets[:, 4], ref[:, 4], rtol=rtol, atol=1e-7):
+        key = lambda r: tuple(np.round(r, 3))
+        cand = {key(r): int(i) for r, i in zip(ref_more, more_inds)}
+        have = set()
+        for r in dets:
+            assert key(r) in cand, "reference row %s is not an oracle peak" % (r,)
+            have.add(cand[key(r)])
+        plateau = _plateau_mask(hm).reshape(-1)
+        kth = dets[-1, 4]
+        dropped = 0
+        for r in ref_more:
+            i = cand[key(r)]
+            if r[4] > kth * (1 + 1e-9) and i not in have:
+                assert plateau[i], "oracle peak %s (index %d) is missing from the reference and is not on a plateau" % (r, i)
+                dropped += 1
+        assert 0 < dropped <= 8, dropped
+        return
+    _assert_dets_match_strict(dets, ref, ref_more, rtol, atol)
+
+
+def _assert_dets_match_strict(dets, ref, ref_more=None, rtol=1e-5, atol=1e-5):
     """dets, ref: [K,6] sorted by score descending.  torch.topk leaves the order inside groups of equal scores
     unspecified, so rows are compared as multisets inside every group of equal score; for
     the group tied with the K-th score the membership itself is ambiguous, there each row must appear in `ref_more`
@@ -40,3 +81,15 @@ def maxpool3s2_int8(a):
     p = np.full((B, C, H + 2, W + 2), -128, np.int8)
     p[:, :, 1:-1, 1:-1] = a
     return np.max([p[:, :, i:i + H:2, j:j + W:2] for i in range(3) for j in range(3)], axis=0)
+
+
+def check_reference_dets(g_dets, hm, wh, reg, K=100):
+    """Reference detections `g_dets` [B,K,6] against the deterministic oracle decode of the (exact) head outputs
+    hm (logits) / wh / reg [B,*,H,W]: strict up to torch.topk's tie order, plateau-aware where the reference's floating-point
+    `hmax == heat` dropped one of two exactly equal neighbours."""
+    from oracle import int_oracle as io
+    hm, wh, reg = (np.asarray(a, np.float64) for a in (hm, wh, reg))
+    odets, _ = io.ctdet_decode(hm, wh, reg, K)
+    more, minds = io.ctdet_decode(hm, wh, reg, K + 60)
+    for b in range(g_dets.shape[0]):
+        assert_dets_match_tie_aware(g_dets[b], odets[b], more[b], hm=hm[b], more_inds=minds[b])
