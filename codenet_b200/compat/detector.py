@@ -3,7 +3,9 @@
 `CtdetDetector(opt)` builds the network, quantises it, loads the checkpoint (`opt.load_model`, reference key space),
 freezes the activation ranges and runs forward + decode through the compiled int8 engine.  `run()` returns the same
 dict as the reference (`results` keyed by 1-based class id and the stage timers test.py prints, test.py:76-79).
-Pre- and post-processing are host code as in the reference (SURVEY.md 8(f) rows 1-2 move them to the device later).
+Only what differs from the reference lives here: engine construction, process / process_u8, the device-side box transform.
+pre_process, merge_outputs and run keep the reference's contract (same inputs, outputs and timer keys) in this package's own
+decomposition (input_geometry / _Stages / group_by_class); INTEGRATION.md section 2 shows the patch for users who keep the reference's BaseDetector.
 """
 import time
 from types import SimpleNamespace
@@ -65,20 +67,46 @@ def transform_preds(coords, center, scale, output_size):
     return (pts.astype(np.float64) @ t.T)
 
 
+def boxes_to_image_space(dets, center, scale, out_w, out_h):
+    """Both corners of every box [N,6] through the inverse of the network-input affine (what ctdet_post_process,
+    lib/utils/post_process.py:86-103, does corner by corner): one 2x3 matrix, one matrix product per corner set."""
+    t = get_affine_transform(center, scale, 0, (out_w, out_h), inv=1)
+    d = np.array(dets, dtype=np.float32, copy=True)
+    corners = d[:, :4].reshape(-1, 2).astype(np.float32)
+    homog = np.concatenate([corners, np.ones((corners.shape[0], 1), np.float32)], 1).astype(np.float64)
+    d[:, :4] = (homog @ t.T).reshape(-1, 4)
+    return d
+
+
+def group_by_class(dets, num_classes):
+    """[N,6] (x1,y1,x2,y2,score,class) -> {1-based class id: float32 [n,5]} in detection order."""
+    cls = dets[:, 5].astype(np.int64)
+    return {j + 1: np.ascontiguousarray(dets[cls == j, :5], dtype=np.float32).reshape(-1, 5) for j in range(num_classes)}
+
+
 def ctdet_post_process(dets, c, s, h, w, num_classes):
-    """lib/utils/post_process.py:86-103: boxes back to image coordinates, 1-based class dict per image."""
-    ret = []
-    for i in range(dets.shape[0]):
-        dets[i, :, :2] = transform_preds(dets[i, :, 0:2], c[i], s[i], (w, h))
-        dets[i, :, 2:4] = transform_preds(dets[i, :, 2:4], c[i], s[i], (w, h))
-        classes = dets[i, :, -1]
-        top = {}
-        for j in range(num_classes):
-            inds = classes == j
-            top[j + 1] = np.concatenate([dets[i, inds, :4].astype(np.float32), dets[i, inds, 4:5].astype(np.float32)],
-                                        axis=1).tolist()
-        ret.append(top)
-    return ret
+    """Host restatement used by the tests (the detector itself transforms on the device): per image, boxes back to image
+    coordinates and grouped per 1-based class."""
+    return [group_by_class(boxes_to_image_space(dets[i], c[i], s[i], w, h), num_classes) for i in range(dets.shape[0])]
+
+
+class _Stages:
+    """Wall-clock accounting of run(): the keys test.py prints (test.py:76-79)."""
+    KEYS = ("load", "pre", "net", "dec", "post", "merge")
+
+    def __init__(self):
+        self.t = dict.fromkeys(self.KEYS, 0.0)
+        self.start = self.mark = time.time()
+
+    def lap(self, key, now=None):
+        now = time.time() if now is None else now
+        self.t[key] += now - self.mark
+        self.mark = now
+
+    def result(self, results):
+        out = {"results": results, "tot": time.time() - self.start}
+        out.update(self.t)
+        return out
 
 
 class CtdetDetector:
@@ -131,30 +159,35 @@ class CtdetDetector:
         ck = torch.load(path, map_location="cpu")
         return self.load_state_dict(ck["state_dict"] if "state_dict" in ck else ck)
 
-    # -- reference API ---------------------------------------------------------------------------------------------------
-    def pre_process(self, image, scale, meta=None):
-        import cv2
-        height, width = image.shape[0:2]
-        new_height, new_width = int(height * scale), int(width * scale)
+    # -- geometry of the network input -------------------------------------------------------------------------------------
+    def input_geometry(self, height, width, scale):
+        """(input height, input width, centre, scale) of base_detector.py:48-60: fixed resolution -> the longer side is
+        mapped onto the input width; otherwise the scaled image is padded up to the next multiple of pad + 1."""
+        sh, sw = int(height * scale), int(width * scale)
         if self.opt.fix_res:
-            inp_height, inp_width = self.opt.input_h, self.opt.input_w
-            c = np.array([new_width / 2., new_height / 2.], dtype=np.float32)
-            s = max(height, width) * 1.0
-        else:
-            inp_height, inp_width = (new_height | self.opt.pad) + 1, (new_width | self.opt.pad) + 1
-            c = np.array([new_width // 2, new_height // 2], dtype=np.float32)
-            s = np.array([inp_width, inp_height], dtype=np.float32)
-        trans_input = get_affine_transform(c, s, 0, [inp_width, inp_height])
-        resized = cv2.resize(image, (new_width, new_height))
-        inp = cv2.warpAffine(resized, trans_input, (inp_width, inp_height), flags=cv2.INTER_LINEAR)
-        inp = ((inp / 255. - self.mean) / self.std).astype(np.float32)
-        images = inp.transpose(2, 0, 1).reshape(1, 3, inp_height, inp_width)
+            return (sh, sw), (self.opt.input_h, self.opt.input_w), np.array([sw / 2., sh / 2.], np.float32), float(max(height, width))
+        ih, iw = (sh | self.opt.pad) + 1, (sw | self.opt.pad) + 1
+        return (sh, sw), (ih, iw), np.array([sw // 2, sh // 2], np.float32), np.array([iw, ih], np.float32)
+
+    def _meta(self, c, s, ih, iw):
+        r = self.opt.down_ratio
+        return {'c': c, 's': s, 'out_height': ih // r, 'out_width': iw // r}
+
+    def pre_process(self, image, scale, meta=None):
+        """uint8 HWC image -> normalised fp32 [1|2,3,H,W] tensor + meta, cv2 resize / warpAffine as in the reference."""
+        import cv2
+        (sh, sw), (ih, iw), c, s = self.input_geometry(image.shape[0], image.shape[1], scale)
+        warped = cv2.warpAffine(cv2.resize(image, (sw, sh)), get_affine_transform(c, s, 0, [iw, ih]), (iw, ih), flags=cv2.INTER_LINEAR)
+        chw = ((warped / 255. - self.mean) / self.std).astype(np.float32).transpose(2, 0, 1)[None]
         if self.opt.flip_test:
-            images = np.concatenate((images, images[:, :, :, ::-1]), axis=0)
-        images = torch.from_numpy(np.ascontiguousarray(images))
-        meta = {'c': c, 's': s, 'out_height': inp_height // self.opt.down_ratio,
-                'out_width': inp_width // self.opt.down_ratio}
-        return images, meta
+            chw = np.concatenate([chw, chw[..., ::-1]], 0)
+        return torch.from_numpy(np.ascontiguousarray(chw)), self._meta(c, s, ih, iw)
+
+    def _is_identity_input(self, image, scale):
+        """True when resize + warpAffine leave the image untouched: uint8, already input-sized, landscape or square (for a
+        portrait image the longer side is the height, so the affine scales by input_w / height and pads)."""
+        return (scale == 1 and self.opt.fix_res and not self.opt.flip_test and image.dtype == np.uint8 and
+                image.shape[:2] == (self.opt.input_h, self.opt.input_w) and image.shape[1] >= image.shape[0])
 
     def _engine_for(self, H, W, batch, device):
         eng = self.model.compile_engine(H, W, max(batch, getattr(self.opt, "max_batch", 1)), device=device, K=self.opt.K)
@@ -203,106 +236,80 @@ class CtdetDetector:
                     C.c_void_p(out["hm"].data_ptr()), C.c_void_p(out["wh"].data_ptr()), pairs, hm.shape[1], hm.shape[2], hm.shape[3],
                     C.c_void_p(hm.data_ptr()), C.c_void_p(wh.data_ptr()),
                     C.c_void_p(torch.cuda.current_stream(images.device).cuda_stream)))
-            reg = out["reg"][0:1] if self.opt.reg_offset else None
+            reg = out["reg"][0::2].contiguous() if self.opt.reg_offset else None     # the unflipped image of every pair
             torch.cuda.synchronize(images.device)
             forward_time = time.time()
             dets = ctdet_decode(hm, wh, reg=reg, cat_spec_wh=self.opt.cat_spec_wh, K=self.opt.K)
         return (output, dets, forward_time) if return_time else (output, dets)
 
     def post_process(self, dets, meta, scale=1):
-        if torch.is_tensor(dets) and dets.is_cuda and dets.dtype == torch.float32:
-            # coordinate transform on the device (cdn_ctdet_post_affine), only the per-class grouping stays on the host
-            import ctypes as C
-            from .. import _lib
-            d = dets.detach().reshape(1, -1, dets.shape[2]).contiguous().clone()
-            t = np.ascontiguousarray(get_affine_transform(meta['c'], meta['s'], 0, (meta['out_width'], meta['out_height']),
-                                                          inv=1), dtype=np.float64).reshape(1, 6)
-            with torch.cuda.device(d.device):
-                _lib.check(_lib.load().cdn_ctdet_post_affine(C.c_void_p(d.data_ptr()), 1, d.shape[1], C.c_void_p(t.ctypes.data),
-                                                             C.c_void_p(torch.cuda.current_stream(d.device).cuda_stream)))
-            d = d.cpu().numpy()
-            classes = d[0, :, -1]
-            out = {}
-            for j in range(self.num_classes):
-                out[j + 1] = np.ascontiguousarray(d[0, classes == j, :5], dtype=np.float32).reshape(-1, 5)
-                out[j + 1][:, :4] /= scale
-            return out
-        dets = dets.detach().cpu().numpy()
-        dets = dets.reshape(1, -1, dets.shape[2])
-        dets = ctdet_post_process(dets.copy(), [meta['c']], [meta['s']], meta['out_height'], meta['out_width'],
-                                  self.opt.num_classes)
-        for j in range(1, self.num_classes + 1):
-            dets[0][j] = np.array(dets[0][j], dtype=np.float32).reshape(-1, 5)
-            dets[0][j][:, :4] /= scale
-        return dets[0]
+        """dets [1|B,K,6] in output-map coordinates -> {class: [n,5]} in image coordinates.  The affine runs on the device
+        (cdn_ctdet_post_affine); the grouping per class is a view operation on the K rows that come back."""
+        import ctypes as C
+        from .. import _lib
+        d = torch.as_tensor(dets, dtype=torch.float32, device=self.opt.device).detach().reshape(1, -1, 6).contiguous().clone()
+        t = np.ascontiguousarray(get_affine_transform(meta['c'], meta['s'], 0, (meta['out_width'], meta['out_height']), inv=1),
+                                 dtype=np.float64).reshape(1, 6)
+        with torch.cuda.device(d.device):
+            _lib.check(_lib.load().cdn_ctdet_post_affine(C.c_void_p(d.data_ptr()), 1, d.shape[1], C.c_void_p(t.ctypes.data),
+                                                         C.c_void_p(torch.cuda.current_stream(d.device).cuda_stream)))
+        out = group_by_class(d[0].cpu().numpy(), self.num_classes)
+        if scale != 1:
+            for v in out.values():
+                v[:, :4] /= scale
+        return out
 
     def merge_outputs(self, detections):
-        """lib/detectors/ctdet.py:59-74: concatenate the scales per class, soft-NMS (gaussian, Nt = 0.5, in place, as the
-        reference calls it) when testing at several scales or with --nms, keep the max_per_image best."""
-        results = {j: np.ascontiguousarray(np.concatenate([d[j] for d in detections], axis=0).astype(np.float32))
-                   for j in range(1, self.num_classes + 1)}
+        """Per class: all scales stacked; soft-NMS when several scales were run or --nms is set; then the max_per_image best
+        scores overall survive (lib/detectors/ctdet.py:59-74)."""
+        classes = range(1, self.num_classes + 1)
+        merged = {j: np.ascontiguousarray(np.vstack([d[j] for d in detections]), dtype=np.float32) for j in classes}
         if len(self.scales) > 1 or self.opt.nms:
-            for j in range(1, self.num_classes + 1):
-                soft_nms(results[j], Nt=0.5, method=2)
-        scores = np.hstack([results[j][:, 4] for j in range(1, self.num_classes + 1)])
-        if len(scores) > self.max_per_image:
-            kth = len(scores) - self.max_per_image
-            thresh = np.partition(scores, kth)[kth]
-            for j in range(1, self.num_classes + 1):
-                results[j] = results[j][results[j][:, 4] >= thresh]
-        return results
+            for j in classes:
+                soft_nms(merged[j], Nt=0.5, method=2)
+        total = sum(len(merged[j]) for j in classes)
+        if total > self.max_per_image:
+            cut = np.partition(np.concatenate([merged[j][:, 4] for j in classes]), total - self.max_per_image)[total - self.max_per_image]
+            merged = {j: v[v[:, 4] >= cut] for j, v in merged.items()}
+        return merged
+
+    def _image_of(self, src):
+        """ndarray | path | pre-processed dict of the prefetching loader (test.py:62-72) -> (image, pre-processed dict or None)"""
+        if isinstance(src, np.ndarray):
+            return src, None
+        if isinstance(src, str):
+            import cv2
+            return cv2.imread(src), None
+        return src['image'][0].numpy(), src
 
     def run(self, image_or_path_or_tensor, meta=None):
-        load_time = pre_time = net_time = dec_time = post_time = merge_time = tot_time = 0
-        start_time = time.time()
-        pre_processed = False
-        if isinstance(image_or_path_or_tensor, np.ndarray):
-            image = image_or_path_or_tensor
-        elif isinstance(image_or_path_or_tensor, str):
-            import cv2
-            image = cv2.imread(image_or_path_or_tensor)
-        else:
-            image = image_or_path_or_tensor['image'][0].numpy()
-            pre_processed_images = image_or_path_or_tensor
-            pre_processed = True
-        loaded_time = time.time()
-        load_time += loaded_time - start_time
-        detections = []
+        clock = _Stages()
+        image, prepared = self._image_of(image_or_path_or_tensor)
+        clock.lap("load")
+        per_scale = []
         for scale in self.scales:
-            scale_start_time = time.time()
-            fast = (not pre_processed and scale == 1 and not self.opt.flip_test and self.opt.fix_res and
-                    image.dtype == np.uint8 and image.shape[:2] == (self.opt.input_h, self.opt.input_w))
-            if fast:
-                # identity resize/affine: ship the uint8 image, normalise inside the stem kernel
+            if prepared is not None:
+                images = prepared['images'][scale][0]
+                meta = {k: (v.numpy()[0] if torch.is_tensor(v) else v) for k, v in prepared['meta'][scale].items()}
+                fn = self.process
+            elif self._is_identity_input(image, scale):
+                # ship the uint8 image as it is; the stem kernel normalises through the 3 x 256 table
                 h, w = image.shape[:2]
-                meta = {'c': np.array([w / 2., h / 2.], dtype=np.float32), 's': max(h, w) * 1.0,
-                        'out_height': h // self.opt.down_ratio, 'out_width': w // self.opt.down_ratio}
                 images = torch.from_numpy(np.ascontiguousarray(image[None]))
-            elif not pre_processed:
-                images, meta = self.pre_process(image, scale, meta)
+                meta = self._meta(np.array([w / 2., h / 2.], np.float32), float(max(h, w)), h, w)
+                fn = self.process_u8
             else:
-                images = pre_processed_images['images'][scale][0]
-                meta = pre_processed_images['meta'][scale]
-                meta = {k: (v.numpy()[0] if torch.is_tensor(v) else v) for k, v in meta.items()}
+                images, meta = self.pre_process(image, scale, meta)
+                fn = self.process
             images = images.to(self.opt.device)
             torch.cuda.synchronize()
-            pre_process_time = time.time()
-            pre_time += pre_process_time - scale_start_time
-            if fast:
-                output, dets, forward_time = self.process_u8(images, return_time=True)
-            else:
-                output, dets, forward_time = self.process(images, return_time=True)
+            clock.lap("pre")
+            output, dets, t_forward = fn(images, return_time=True)
             torch.cuda.synchronize()
-            net_time += forward_time - pre_process_time
-            decode_time = time.time()
-            dec_time += decode_time - forward_time
-            dets = self.post_process(dets, meta, scale)
-            post_process_time = time.time()
-            post_time += post_process_time - decode_time
-            detections.append(dets)
-        results = self.merge_outputs(detections)
-        end_time = time.time()
-        merge_time += end_time - post_process_time
-        tot_time += end_time - start_time
-        return {'results': results, 'tot': tot_time, 'load': load_time, 'pre': pre_time, 'net': net_time,
-                'dec': dec_time, 'post': post_time, 'merge': merge_time}
+            clock.lap("net", t_forward)
+            clock.lap("dec")
+            per_scale.append(self.post_process(dets, meta, scale))
+            clock.lap("post")
+        results = self.merge_outputs(per_scale)
+        clock.lap("merge")
+        return clock.result(results)

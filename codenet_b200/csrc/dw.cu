@@ -1017,6 +1017,9 @@ int deform_launch(const DwDevice& d, const cdn_deform_scale* sc, const int8_t* i
   CDN_CHECK(sc->bound >= 1 && sc->bound <= 64, CDN_ERR_INVALID, "deform: offset bound %d out of range", sc->bound);
   CDN_CHECK(in_shift == 0 || (in_shift == 1 && H % 2 == 0 && W % 2 == 0), CDN_ERR_INVALID, "deform: bad in_shift");
   CDN_CHECK(in_pitch >= d.cw_total * 4 && out_pitch >= d.cw_total * 4, CDN_ERR_INVALID, "deform: pitch smaller than channels");
+  if ((long long)batch * H * W == 0) return 0;
+  if (deform_tile_ok(d, sc, in_pitch, out_pitch, batch, H, W, in_shift))
+    return deform_tile_launch(d, sc, in, in_pitch, out, out_pitch, batch, H, W, in_shift, zx, sval, st);
   DwParams p; memset(&p, 0, sizeof(p));
   fill_common(p, d, in, in_pitch, out, out_pitch, batch, H, W, in_shift, 1, zx);
   p.Ms = sc->Ms; p.bs = sc->bs; p.ss = sc->ss; p.zs = sc->zs;

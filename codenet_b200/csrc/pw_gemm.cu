@@ -556,6 +556,25 @@ int make_tmap_nhwc(CUtensorMap* m, const void* base, uint64_t pitch, uint64_t W,
   return 0;
 }
 
+// NHWC int8 tensor of any pixel pitch, box = {box_c channel bytes (<= 256), box_w, box_h, 1}: a channel SLICE of a row band
+int make_tmap_nhwc_box(CUtensorMap* m, const void* base, uint64_t pitch, uint64_t W, uint64_t H, uint64_t batch,
+                       uint32_t box_c, uint32_t box_w, uint32_t box_h) {
+  PFN_encodeTiled enc = get_encode();
+  CDN_CHECK(enc != nullptr, CDN_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  CDN_CHECK(((uintptr_t)base & 15) == 0 && pitch % 16 == 0 && box_c % 16 == 0 && box_c <= 256 && box_w <= 256 && box_h <= 256 &&
+            box_c >= 16 && box_w >= 1 && box_h >= 1, CDN_ERR_INVALID, "TMA: base/pitch/slice must be 16-byte aligned, box dimensions <= 256");
+  cuuint64_t dims[4] = {pitch, W, H, batch};
+  cuuint64_t strides[3] = {pitch, W * pitch, H * W * pitch};
+  cuuint32_t box[4] = {box_c, box_w, box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, (void*)base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CDN_CHECK(r == CUDA_SUCCESS, CDN_ERR_CUDA, "cuTensorMapEncodeTiled (NHWC box) failed with CUresult %d (pitch=%llu W=%llu H=%llu batch=%llu box=%u,%u,%u)",
+            (int)r, (unsigned long long)pitch, (unsigned long long)W, (unsigned long long)H, (unsigned long long)batch, box_c, box_w, box_h);
+  return 0;
+}
+
 void pw_device_free(PwDevice& d) {
   cudaFree(d.w); cudaFree(d.chunks); cudaFree(d.segs); cudaFree(d.tile_seg); cudaFree(d.kc); cudaFree(d.Mf); cudaFree(d.bf);
   dev_requant_free(d.rq);
