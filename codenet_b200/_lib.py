@@ -124,6 +124,8 @@ def load():
     for name, (res, args) in EXPORTS.items():
         fn = getattr(lib, name)                  # AttributeError if a declared symbol is not exported
         fn.restype, fn.argtypes = res, args
+    if os.environ.get("CODENET_DEBUG_FLAGS"):        # kernel A/B experiments only (cdn_set_debug_flags)
+        lib.cdn_set_debug_flags(int(os.environ["CODENET_DEBUG_FLAGS"]))
     _lib = lib
     return lib
 

@@ -23,6 +23,7 @@ class NetConfig:
     w_bit: int = 4
     a_bit: int = 8
     offset_bound: int = 8                  # Hardtanh(-bound+1, bound), dcn_deform_conv.py:304-305
+    wt_percentile: bool = False            # --wt-percentile: weight ranges from the 0.1 / 99.9 percentiles (quant_modules.py:382-395)
     heads: Tuple[Tuple[str, int], ...] = ()
 
     def head_list(self) -> List[Tuple[str, int]]:

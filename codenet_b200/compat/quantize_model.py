@@ -15,9 +15,12 @@ def quantize_shufflenetv2_dcn(model, quant_conv, quant_bn, quant_act, wt_quant_m
     if deform_backbone:
         raise NotImplementedError("deform_backbone=True imports a module that does not exist in the reference "
                                   "(quant_modules.py:982, SURVEY.md F2); not built")
-    if wt_quant_mode != "symmetric" or not wt_per_channel or wt_percentile or act_percentile:
+    if wt_quant_mode != "symmetric" or not wt_per_channel:
         raise NotImplementedError("the engine implements the reference's inference configuration: symmetric per-channel "
-                                  "weights without percentile clipping (lib/detectors/base_detector.py:29-34)")
+                                  "weights (lib/detectors/base_detector.py:29-34)")
+    # wt_percentile changes the weight ranges at plan time (plan.weight_range); act_percentile only changes how QuantAct
+    # collects its running range (quant_modules.py:203-219) and has no effect once the ranges are frozen
+    model.wt_percentile = bool(wt_percentile)
     kw = dict(act_percentile=act_percentile, wt_quant_mode=wt_quant_mode, act_quant_mode=act_quant_mode,
               per_channel=wt_per_channel, weight_percentile=wt_percentile)
 

@@ -79,7 +79,8 @@ class Engine:
             bound = int(round(float(model.deconv_layers[0].quant_act[0].max_val)))
         except Exception:
             pass
-        cfg = NetConfig(num_classes=heads[0][1], w2=w2, maxpool=maxpool, heads=heads, offset_bound=bound)
+        cfg = NetConfig(num_classes=heads[0][1], w2=w2, maxpool=maxpool, heads=heads, offset_bound=bound,
+                        wt_percentile=bool(getattr(model, "wt_percentile", False)))
         return cls.from_state_dict(cfg, sd, in_H, in_W, max_batch, offset_mode, device, K)
 
     def close(self):

@@ -40,10 +40,26 @@ def act_params(lo, hi, bits=8):
     return s, z
 
 
-def quant_weight(w, bits):
+def weight_range(flat, percentile=False):
+    """Per-output-channel (w_min, w_max) of the flattened weights [Cout, n] (quant_modules.py:373-395): plain min / max, or with
+    --wt-percentile the k-th smallest values at k = ceil(0.1 % n) and ceil(99.9 % n) (1-based, torch.kthvalue); rows of fewer
+    than 10 values (every depthwise 3x3 kernel) take 0.95 * min / max instead."""
+    lo, hi = flat.min(1), flat.max(1)
+    if not percentile:
+        return lo, hi
+    n = flat.shape[1]
+    if n < 10:
+        return lo * F(0.95), hi * F(0.95)
+    srt = np.sort(flat, axis=1)
+    kl, ku = int(np.ceil(n * 0.1 * 0.01)), int(np.ceil(n * 99.9 * 0.01))
+    return srt[:, kl - 1], srt[:, ku - 1]
+
+
+def quant_weight(w, bits, percentile=False):
     """w: [Cout, ...] fp64.  Returns integer weights (int64) and the per-channel scale sigma."""
     flat = w.reshape(w.shape[0], -1)
-    mag = np.maximum(np.abs(flat.min(1)), np.abs(flat.max(1)))
+    lo, hi = weight_range(flat, percentile)
+    mag = np.maximum(np.abs(lo), np.abs(hi))
     sigma = (F(1) / np.maximum(mag, F(1e-10))) * F(2 ** (bits - 1) - 1)   # reciprocal * n, as torch evaluates n / tensor
     q = np.rint(sigma.reshape(-1, *([1] * (w.ndim - 1))) * w)
     q = np.clip(q, -(2 ** (bits - 1)), 2 ** (bits - 1) - 1)
@@ -195,7 +211,7 @@ class IntOracle:
             b = self.st[c.q_conv + ".bias"].astype(F)
         else:
             b = np.zeros(c.cout, F)
-        wq, sigma = quant_weight(w, c.w_bit)
+        wq, sigma = quant_weight(w, c.w_bit, getattr(self.cfg, "wt_percentile", False))
         return wq, sigma, b
 
     def sat(self, q):

@@ -74,6 +74,24 @@ def quant_kat():
                bnconv_beta=bn.bias.detach().numpy(), bnconv_mean=bn.running_mean.numpy(),
                bnconv_var=bn.running_var.numpy(), bnconv_eps=np.array(bn.eps), bnconv_x=xi,
                bnconv_y=yo.numpy())
+    # --wt-percentile (quant_modules.py:382-395, :296-309, :491-504): ranges from kthvalue at ceil(0.1 % n) / ceil(99.9 % n),
+    # 0.95 * min / max for rows of fewer than 10 values; through the reference's own modules
+    wide = torch.nn.Conv2d(1200, 6, 1, bias=False).double()
+    narrow = torch.nn.Conv2d(5, 7, 1, bias=False).double()
+    dwc = torch.nn.Conv2d(8, 8, 3, padding=1, groups=8, bias=True).double()
+    with torch.no_grad():
+        wide.weight.copy_(T(rng.standard_normal((6, 1200, 1, 1)) * np.array([0.02, 0.3, 1, 2, 5, 1e-3]).reshape(6, 1, 1, 1)))
+        narrow.weight.copy_(T(rng.standard_normal((7, 5, 1, 1))))
+        dwc.weight.copy_(T(rng.standard_normal((8, 1, 3, 3)))); dwc.bias.copy_(T(rng.standard_normal(8) * 0.1))
+    for tag, conv, xin in (("pct_wide", wide, rng.standard_normal((1, 1200, 2, 2))), ("pct_narrow", narrow, rng.standard_normal((1, 5, 3, 3))),
+                           ("pct_dw", dwc, rng.standard_normal((1, 8, 5, 5)))):
+        qp = R.qm.Quant_Conv2d(4, quant_mode="symmetric", per_channel=True, weight_percentile=True)
+        qp.set_param(conv)
+        with torch.no_grad():
+            yp = qp(T(xin))
+        out.update({tag + "_w": conv.weight.detach().numpy(), tag + "_x": xin, tag + "_y": yp.numpy()})
+        if conv.bias is not None:
+            out[tag + "_b"] = conv.bias.detach().numpy()
     # QuantAct stateful init then frozen (quant_modules.py:202-225)
     qa = R.qm.QuantAct(8, quant_mode="asymmetric").double()
     xa = rng.standard_normal((3, 4, 5, 5))

@@ -32,6 +32,27 @@ def test_weight_quant_kat(golden, bits):
     assert wq.min() >= -(2 ** (bits - 1)) and wq.max() <= 2 ** (bits - 1) - 1
 
 
+@pytest.mark.parametrize("tag", ["pct_wide", "pct_narrow", "pct_dw"])
+def test_weight_percentile_kat(golden, tag):
+    """--wt-percentile (quant_modules.py:296-309, :382-395): the oracle's and the plan compiler's weight ranges against the
+    reference's own Quant_Conv2d(weight_percentile=True) -- 1200 inputs per row (k-th values), 5 and 9 (0.95 * min / max)."""
+    from codenet_b200 import plan
+    g = golden("quant_kat.npz")
+    w, x = g[tag + "_w"], g[tag + "_x"]
+    for qw in (io.quant_weight, plan.quant_weight):
+        wq, sigma = qw(w, 4, True)
+        wd = wq / sigma.reshape(-1, 1, 1, 1)
+        if tag == "pct_dw":
+            xp = np.pad(x, ((0, 0), (0, 0), (1, 1), (1, 1)))
+            y = sum(wd[:, 0, i, j].reshape(1, -1, 1, 1) * xp[:, :, i:i + 5, j:j + 5] for i in range(3) for j in range(3))
+            y = y + g[tag + "_b"].reshape(1, -1, 1, 1)
+        else:
+            y = np.einsum("oc,bchw->bohw", wd.reshape(wd.shape[0], -1), x)
+        np.testing.assert_allclose(y, g[tag + "_y"], rtol=1e-12, atol=1e-12)
+    # the plain ranges give different integers for the wide rows: the option is not a no-op
+    assert not np.array_equal(io.quant_weight(g["pct_wide_w"], 4, False)[0], io.quant_weight(g["pct_wide_w"], 4, True)[0])
+
+
 def test_bn_fold_conv_kat(golden):
     g = golden("quant_kat.npz")
     w, b = io.fold_bn(g["bnconv_w"], g["bnconv_gamma"], g["bnconv_beta"], g["bnconv_mean"], g["bnconv_var"],
