@@ -24,6 +24,7 @@
 //            transposes, 12 dp4a, 4 x (IMAD.HI + SHF), 2 I2IP + one store; the taps of the next pixel are in flight while
 //            this one is computed.
 #include "layers.cuh"
+#include "dw_params.cuh"
 #include "tc_ptx.cuh"
 #include <algorithm>
 #include <cooperative_groups.h>
@@ -238,6 +239,229 @@ __global__ void __launch_bounds__(NT, MINB) deform_tile_int_kernel(const __grid_
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Bilinear offsets (the reference's default: fractional s, quant_modules.py:668-671) on the same staged tile.
+//
+// The 36 corners of the 9 taps lie on a 5 x 5 lattice of stored pixels (rows hl0, hl0+1, h, hl2, hl2+1 and the same for
+// columns; the centre row / column is integral); the blend is separable and runs in fp32, two channels per instruction
+// (FADD2 / FMUL2 / FFMA2), exactly the operation sequence of deform_dw_v2_kernel<1> (dw.cu), so the host-derived error
+// bound `thr_bil` applies unchanged: words that come within it of a rounding boundary are queued and re-evaluated by all
+// threads at the end of the tile with the fp64 code that follows dcn_deform_conv_cuda_kernel.cu:83-114,210-227 on exact
+// integers (deform_bilinear_exact_word, from global memory) -- bit-exact against the fp64 oracle.
+// The tile carries one extra pixel column and one extra pixel row holding q = -zx (real zero): out-of-image lattice rows /
+// columns index them, so address = row offset + column offset with no validity test in the gather loop.
+// ---------------------------------------------------------------------------------------------------------
+#define DTB_ENT 80                             // bytes per unit: 5 row offsets, 5 column offsets, 4 fractions, pixel, s (double)
+#define DTB_QCAP 1024
+
+struct DefTBil { const float2* mb; float lo_f, thr_bil; double Ms, bs, ss, zs, u_lo, u_hi; long long acc_s_bias; };
+
+template <int NT>
+__global__ void __launch_bounds__(NT, 2) deform_tile_bil_kernel(const __grid_constant__ CUtensorMap tmI, const DefTParams p, const DefTBil f,
+                                                                const DwParams dwp) {
+  pdl_launch_dependents();
+  extern __shared__ uint8_t dtl_smem_raw[];
+  const uint32_t s0 = (smem_u32(dtl_smem_raw) + 127u) & ~127u;
+  uint8_t* const g0 = dtl_smem_raw + (s0 - smem_u32(dtl_smem_raw));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cs = blockIdx.x, band = blockIdx.y, b = blockIdx.z;
+  const int r0 = band * p.R;
+  const int sr0 = max(r0 - p.reach, 0) >> p.shift;
+  const int rows_here = min(p.R, p.H - r0);
+  const uint32_t bar = s0 + p.off_bar;
+  const int rowpx = p.Ws + 1;                                         // pixels per staged row (the last one is the pad column)
+  int* const q_n = reinterpret_cast<int*>(g0 + p.off_bar + 8);
+  uint32_t* const q_ent = reinterpret_cast<uint32_t*>(g0 + p.off_thr);   // the exact-evaluation queue lives where the int kernel keeps its thresholds
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    *q_n = 0;
+    pdl_wait();
+    mbar_expect_tx(bar, p.tile_bytes);
+    tma_load_4d(s0, &tmI, cs * p.SLB, 0, sr0, b, bar);
+  }
+  if (p.ns > 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+  const int wps = p.SLB >> 2;
+  for (int i = tid; i < wps; i += NT) {
+    const int gw = cs * wps + i;
+    reinterpret_cast<uint32_t*>(g0 + p.off_ws)[i] = gw < p.cw_total ? __ldg(p.ws + gw) : 0u;
+  }
+  const int cl = lane % p.lpp, sub = lane / p.lpp;
+  const bool lane_on = cl < wps && sub < p.ppw && cs * wps + cl < p.cw_total;
+  const int gwl = min(cs * wps + cl, p.cw_total - 1);
+  float wf[4][9], Mh[4], Bh[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int ch = gwl * 4 + c;
+    const uint32_t a = __ldg(p.wA + ch), bb = __ldg(p.wB + ch), cc = __ldg(p.wC + ch);
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const uint32_t wword = t < 4 ? a : (t < 8 ? bb : cc);
+      const int sh = t < 8 ? 8 * (t & 3) : 8 * c;
+      wf[c][t] = (float)(int)(int8_t)((wword >> sh) & 0xff);
+    }
+    const float2 mb = __ldg(f.mb + ch);
+    Mh[c] = mb.x; Bh[c] = mb.y;
+  }
+  __syncthreads();
+  pdl_wait();
+  mbar_wait(bar, 0);
+  if (p.ns > 1) asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+  // pad column of every staged row and the pad row behind the tile: q = -zx
+  {
+    const int npad = p.tile_rows + rowpx;                            // pixels to fill
+    for (int i = tid; i < npad * wps; i += NT) {
+      const int px = i / wps, wd = i - px * wps;
+      const int pix = px < p.tile_rows ? px * rowpx + p.Ws : p.tile_rows * rowpx + (px - p.tile_rows);
+      reinterpret_cast<uint32_t*>(g0 + (size_t)pix * p.SLB)[wd] = p.pad_word;
+    }
+  }
+  // ---------------- phase A ----------------
+  const int st_r0 = r0 >> p.shift;
+  const int nst = ((rows_here + (1 << p.shift) - 1) >> p.shift) * p.Ws;
+  const int nchunk = p.SLB >> 4;
+  int* const part_own = reinterpret_cast<int*>(g0 + p.off_part);
+  for (int j = tid; j < nst; j += NT) {
+    const int srow = j / p.Ws, scol = j - srow * p.Ws;
+    const uint32_t px = s0 + (uint32_t)(((st_r0 + srow - sr0) * rowpx + scol) * p.SLB);
+    int acc = 0;
+    for (int k = 0; k < nchunk; ++k) {
+      int ch = j + k; ch -= (ch / nchunk) * nchunk;
+      const uint4 x = lds_u128(px + 16u * ch), w = lds_u128(s0 + p.off_ws + 16u * ch);
+      acc = dp4a_ss(x.x, w.x, acc); acc = dp4a_ss(x.y, w.y, acc); acc = dp4a_ss(x.z, w.z, acc); acc = dp4a_ss(x.w, w.w, acc);
+    }
+    if (p.ns > 1) {
+      cg::cluster_group cluster = cg::this_cluster();
+      for (int r = 0; r < p.ns; ++r) cluster.map_shared_rank(part_own, r)[cs * p.nst_max + j] = acc;
+    } else part_own[j] = acc;
+  }
+  if (p.ns > 1) asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  const uint32_t pad_row_off = (uint32_t)(p.tile_rows * rowpx) * (uint32_t)p.SLB, pad_col_off = (uint32_t)p.Ws * (uint32_t)p.SLB;
+  for (int j = tid; j < nst; j += NT) {
+    long long v = 0;
+    for (int r = 0; r < p.ns; ++r) v += part_own[r * p.nst_max + j];
+    // fp64, product and sum rounded separately as in the oracle (dcn_deform_conv.py:295-330, quant_modules.py:648-653)
+    double u = __dadd_rn(__dmul_rn((double)(v + f.acc_s_bias), f.Ms), f.bs);
+    u = fmin(fmax(u, f.u_lo), f.u_hi);
+    const double qs = rint(__dsub_rn(__dmul_rn(f.ss, u), f.zs));
+    const double sv = __ddiv_rn(__dadd_rn(qs, f.zs), f.ss);
+    const double dd = __dsub_rn(sv, 1.0);
+    const int srow = j / p.Ws, scol = j - srow * p.Ws;
+    const int nrep = 1 << p.shift;
+    for (int dy = 0; dy < nrep; ++dy)
+      for (int dx = 0; dx < nrep; ++dx) {
+        const int h = r0 + (srow << p.shift) + dy, w = (scol << p.shift) + dx;
+        if (h >= p.H || w >= p.W) continue;
+        const int pl = (h - r0) * p.W + w;
+        uint32_t* t = reinterpret_cast<uint32_t*>(g0 + p.off_tab + (uint32_t)pl * DTB_ENT);
+        int R[5], Cc[5];
+        R[2] = h; Cc[2] = w;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const double sg = e ? 1.0 : -1.0;
+          const double him = __dadd_rn((double)(h - 1 + 2 * e), sg * dd), wim = __dadd_rn((double)(w - 1 + 2 * e), sg * dd);
+          const double hf = floor(him), wfl = floor(wim);
+          R[3 * e] = (int)hf; R[3 * e + 1] = (int)hf + 1; Cc[3 * e] = (int)wfl; Cc[3 * e + 1] = (int)wfl + 1;
+          t[10 + e] = __float_as_uint((float)__dsub_rn(him, hf));
+          t[12 + e] = __float_as_uint((float)__dsub_rn(wim, wfl));
+        }
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          t[k] = (unsigned)R[k] < (unsigned)p.H ? (uint32_t)(((R[k] >> p.shift) - sr0) * rowpx) * (uint32_t)p.SLB : pad_row_off;
+          t[5 + k] = (unsigned)Cc[k] < (unsigned)p.W ? (uint32_t)(Cc[k] >> p.shift) * (uint32_t)p.SLB : pad_col_off;
+        }
+        t[14] = (uint32_t)pl;
+        *reinterpret_cast<double*>(t + 16) = sv;
+        if (p.sval != nullptr && cs == 0) p.sval[((size_t)b * p.H + h) * p.W + w] = (float)sv;
+      }
+  }
+  __syncthreads();
+  // ---------------- phase C ----------------
+  const int npx = rows_here * p.W;
+  const uint32_t lane_base = s0 + (uint32_t)cl * 4u;
+  const uint32_t tab0 = s0 + p.off_tab;
+  uint32_t* const out_l = p.out + ((size_t)b * p.H + r0) * p.W * (size_t)p.pitch_out_w + cs * wps + cl;
+  const int zx = -(int)(int8_t)(p.pad_word & 0xff);
+  const float unb = 8388608.0f + 128.0f - (float)zx;                 // as_float(0x4B000000 | (q ^ 0x80)) - unb = q + zx
+  const float2 nunb = make_float2(-unb, -unb);
+  const int pstep = (NT / 32) * p.ppw;
+  if (lane_on) {
+#pragma unroll 1
+    for (int u = warp * p.ppw + sub; u < npx; u += pstep) {
+      const uint32_t ta = tab0 + (uint32_t)u * DTB_ENT;
+      const uint4 e0 = lds_u128(ta), e1 = lds_u128(ta + 16), e2 = lds_u128(ta + 32);
+      const uint2 e3 = lds_u64(ta + 48);
+      const uint32_t rowB[5] = {e0.x, e0.y, e0.z, e0.w, e1.x};
+      const uint32_t colB[5] = {e1.y + lane_base, e1.z + lane_base, e1.w + lane_base, e2.x + lane_base, e2.y + lane_base};
+      const float lh0 = __uint_as_float(e2.z), lh2 = __uint_as_float(e2.w), lw0 = __uint_as_float(e3.x), lw2 = __uint_as_float(e3.y);
+      const float rho[5] = {1.0f - lh0, lh0, 1.0f, 1.0f - lh2, lh2};
+      const float cwt[4] = {1.0f - lw0, lw0, 1.0f - lw2, lw2};
+      float2 acc2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+      for (int r = 0; r < 5; ++r) {
+        uint32_t xw[5];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) xw[q] = lds_u32(rowB[r] + colB[q]) ^ 0x80808080u;
+        const int ti = r < 2 ? 0 : (r == 2 ? 1 : 2);                 // tap row fed by this lattice row
+        const float2 rho2 = make_float2(rho[r], rho[r]);
+#pragma unroll
+        for (int cp = 0; cp < 2; ++cp) {
+          const int c = 2 * cp;
+          float2 a[5];
+#pragma unroll
+          for (int q = 0; q < 5; ++q)
+            a[q] = cdn_fadd2(make_float2(__uint_as_float(__byte_perm(xw[q], 0x4B000000u, 0x7650 + c)),
+                                         __uint_as_float(__byte_perm(xw[q], 0x4B000000u, 0x7650 + c + 1))), nunb);
+          const float2 u0 = cdn_ffma2(make_float2(cwt[1], cwt[1]), a[1], cdn_fmul2(make_float2(cwt[0], cwt[0]), a[0]));
+          const float2 u2 = cdn_ffma2(make_float2(cwt[3], cwt[3]), a[4], cdn_fmul2(make_float2(cwt[2], cwt[2]), a[3]));
+          const float2 w0 = make_float2(wf[c][ti * 3], wf[c + 1][ti * 3]), w1 = make_float2(wf[c][ti * 3 + 1], wf[c + 1][ti * 3 + 1]),
+                       w2 = make_float2(wf[c][ti * 3 + 2], wf[c + 1][ti * 3 + 2]);
+          const float2 t = cdn_ffma2(w2, u2, cdn_ffma2(w1, a[2], cdn_fmul2(w0, u0)));
+          acc2[cp] = cdn_ffma2(rho2, t, acc2[cp]);
+        }
+      }
+      const float acc[4] = {acc2[0].x, acc2[0].y, acc2[1].x, acc2[1].y};
+      RqGuard gd; rq_guard_init(gd);
+      uint32_t rr[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float t = fmaf(acc[c], Mh[c], Bh[c]);
+        t = fmaxf(t, f.lo_f);
+        gd.tmax = fmaxf(gd.tmax, t);
+        const float r_ = __fadd_rn(t, CDN_MAGIC_F), kk = __fadd_rn(r_, -CDN_MAGIC_F);
+        gd.d0 = fmaxf(gd.d0, fabsf(__fadd_rn(t, -kk)));
+        rr[c] = __float_as_uint(r_);
+      }
+      const uint32_t oword = pack4_lowbytes(rr[0], rr[1], rr[2], rr[3]);
+      bool queued = false;
+      if (rq_group_bad(gd, f.thr_bil)) {
+        const int pos = atomicAdd(q_n, 1);
+        if (pos < DTB_QCAP) { q_ent[pos] = ((uint32_t)u << 8) | (uint32_t)cl; queued = true; }
+      }
+      if (!queued) {
+        uint32_t* dst = word_ptr(out_l, (uint32_t)u * (uint32_t)p.pitch_out_w);
+        if (rq_group_bad(gd, f.thr_bil)) {                           // queue overflow: evaluate here
+          const int h = r0 + u / p.W, w = u - (u / p.W) * p.W;
+          const double sv = *reinterpret_cast<const double*>(g0 + p.off_tab + (uint32_t)u * DTB_ENT + 64);
+          *dst = deform_bilinear_exact_word(dwp, dwp.in + (size_t)b * dwp.Hs * dwp.Ws * dwp.in_pitch_w + gwl, h, w, sv, gwl);
+        } else *dst = oword;
+      }
+    }
+  }
+  __syncthreads();
+  // ---------------- exact re-evaluation of the queued words ----------------
+  const int nq = min(*q_n, DTB_QCAP);
+  for (int i = tid; i < nq; i += NT) {
+    const uint32_t e = q_ent[i];
+    const int u = (int)(e >> 8), lw = (int)(e & 0xffu);
+    const int gw = cs * wps + lw;
+    const int h = r0 + u / p.W, w = u - (u / p.W) * p.W;
+    const double sv = *reinterpret_cast<const double*>(g0 + p.off_tab + (uint32_t)u * DTB_ENT + 64);
+    p.out[(((size_t)b * p.H + h) * p.W + w) * (size_t)p.pitch_out_w + gw] =
+        deform_bilinear_exact_word(dwp, dwp.in + (size_t)b * dwp.Hs * dwp.Ws * dwp.in_pitch_w + gw, h, w, sv, gw);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------
 // kernel variants (A/B through cdn_set_debug_flags): 0 = 8 channels per lane, 256 threads, 2 CTAs per SM, software pipeline;
@@ -246,12 +470,13 @@ __global__ void __launch_bounds__(NT, MINB) deform_tile_int_kernel(const __grid_
 struct DefTPlan { int ok, variant, V, NT, SLB, ns, R, nbands, tile_rows, lpp, ppw; uint32_t off_tab, off_part, off_ws, off_thr, off_bar, tile_bytes; size_t smem; };
 
 // Chooses slice, band height and the shared-memory layout; ok = 0 when the shape does not fit (the caller keeps deform_int_v3_kernel).
-static DefTPlan deform_tile_plan(int cw_total, int in_pitch, int H, int W, int in_shift, int reach, int batch) {
+static DefTPlan deform_tile_plan(int cw_total, int in_pitch, int H, int W, int in_shift, int bound, int batch, int mode) {
+  const int reach = mode == 1 ? bound + 1 : bound;              // the high corner of a fractional tap reaches one pixel further
   DefTPlan P; memset(&P, 0, sizeof(P));
   const int Hs = H >> in_shift, Ws = W >> in_shift;
   const int cp = cw_total * 4;                                       // channel bytes the layer processes
   P.SLB = cp >= 256 ? 256 : cp;
-  if (P.SLB % 16 || in_pitch % 16 || Ws > 256 || Ws < 1) return P;
+  if (P.SLB % 16 || in_pitch % 16 || Ws + (mode == 1 ? 1 : 0) > 256 || Ws < 1) return P;
   P.ns = (cp + P.SLB - 1) / P.SLB;
   if (P.ns > 8) return P;                                            // portable cluster size
   P.variant = DTL_DEFAULT_VARIANT;
@@ -259,6 +484,7 @@ static DefTPlan deform_tile_plan(int cw_total, int in_pitch, int H, int W, int i
   if (g_cdn_debug_flags & 8192u) P.variant = 2;
   if ((g_cdn_debug_flags & 12288u) == 12288u) P.variant = 0;
   if (P.SLB < 64 && P.variant == 0) P.variant = 2;
+  if (mode == 1) P.variant = 3;                                     // bilinear kernel: 4 channels per lane, 256 threads, 2 CTAs per SM
   P.V = P.variant == 0 ? 2 : 1;
   P.NT = P.variant == 1 ? 512 : 256;
   const int wps = P.SLB / 4, lanes = (wps + P.V - 1) / P.V;
@@ -275,13 +501,13 @@ static DefTPlan deform_tile_plan(int cw_total, int in_pitch, int H, int W, int i
     int rows = ((R - 1 + 2 * reach) >> in_shift) + 2;
     rows = std::min(rows, Hs);
     if (rows > 256) continue;
-    const size_t tile = (size_t)rows * Ws * P.SLB;
-    size_t off = tile + P.SLB;                                       // + pad pixel
-    off = (off + 15) / 16 * 16; const size_t off_tab = off; off += (size_t)R * W * DTL_TAB_STRIDE;
+    const size_t tile = (size_t)rows * (Ws + (mode == 1 ? 1 : 0)) * P.SLB;   // bytes the TMA box delivers
+    size_t off = mode == 1 ? (size_t)(rows + 1) * (Ws + 1) * P.SLB : tile + P.SLB;   // + pad row / pad pixel
+    off = (off + 15) / 16 * 16; const size_t off_tab = off; off += (size_t)R * W * (mode == 1 ? DTB_ENT : DTL_TAB_STRIDE);
     const int nst_max = (R >> in_shift) * Ws;
     const size_t off_part = off; off += (size_t)P.ns * nst_max * 4;
     off = (off + 15) / 16 * 16; const size_t off_ws = off; off += P.SLB;
-    const size_t off_thr = off; off += 128 * 4;
+    const size_t off_thr = off; off += mode == 1 ? DTB_QCAP * 4 : 128 * 4;
     const size_t off_bar = off; off += 16;
     P.R = R;
     if (off + 128 > budget) continue;
@@ -297,19 +523,21 @@ static DefTPlan deform_tile_plan(int cw_total, int in_pitch, int H, int W, int i
 }
 
 bool deform_tile_ok(const DwDevice& d, const cdn_deform_scale* sc, int in_pitch, int out_pitch, int batch, int H, int W, int in_shift) {
-  if (sc->mode != 0 || !d.use_int || !d.ki || !d.s_mode0_ok || (g_cdn_debug_flags & 2048u)) return false;   // bit 11: v3 kernel (A/B)
+  if (g_cdn_debug_flags & 2048u) return false;                                              // bit 11: the LDG kernels of dw.cu (A/B)
+  if (sc->mode == 0 && (!d.use_int || !d.ki || !d.s_mode0_ok)) return false;
+  if (sc->mode == 1 && (!d.mb || (long long)H * W > (1 << 23))) return false;
   if (H >= 65536 || W >= 65536 || batch > 65535) return false;
-  return deform_tile_plan(d.cw_total, in_pitch, H, W, in_shift, sc->bound, batch).ok != 0;
+  return deform_tile_plan(d.cw_total, in_pitch, H, W, in_shift, sc->bound, batch, sc->mode).ok != 0;
 }
 
 int deform_tile_launch(const DwDevice& d, const cdn_deform_scale* sc, const int8_t* in, int in_pitch, int8_t* out, int out_pitch,
-                       int batch, int H, int W, int in_shift, int zx, float* sval, cudaStream_t st) {
-  const DefTPlan P = deform_tile_plan(d.cw_total, in_pitch, H, W, in_shift, sc->bound, batch);
+                       int batch, int H, int W, int in_shift, int zx, float* sval, const DwParams* dwp, cudaStream_t st) {
+  const DefTPlan P = deform_tile_plan(d.cw_total, in_pitch, H, W, in_shift, sc->bound, batch, sc->mode);
   CDN_CHECK(P.ok, CDN_ERR_STATE, "deform (tile): shape not eligible");
   DefTParams p; memset(&p, 0, sizeof(p));
   p.Hs = H >> in_shift; p.Ws = W >> in_shift; p.H = H; p.W = W; p.shift = in_shift;
   p.pitch_out_w = out_pitch / 4; p.cw_total = d.cw_total;
-  p.SLB = P.SLB; p.ns = P.ns; p.R = P.R; p.reach = sc->bound; p.tile_rows = P.tile_rows;
+  p.SLB = P.SLB; p.ns = P.ns; p.R = P.R; p.reach = sc->mode == 1 ? sc->bound + 1 : sc->bound; p.tile_rows = P.tile_rows;
   p.nst_max = (P.R >> in_shift) * p.Ws; p.lpp = P.lpp; p.ppw = P.ppw;
   p.off_tab = P.off_tab; p.off_part = P.off_part; p.off_ws = P.off_ws; p.off_thr = P.off_thr; p.off_bar = P.off_bar; p.tile_bytes = P.tile_bytes;
   p.wA = d.wA; p.wB = d.wB; p.wC = d.wC; p.ki = (const int4*)d.ki; p.lo_i = d.rq.lo;
@@ -319,18 +547,23 @@ int deform_tile_launch(const DwDevice& d, const cdn_deform_scale* sc, const int8
   p.no_dedup = (g_cdn_debug_flags & 16384u) ? 1 : 0;                // bit 14: no 2x2 block units (A/B)
   CUtensorMap tmI;
   if (int r = make_tmap_nhwc_box(&tmI, in, (uint64_t)in_pitch, (uint64_t)p.Ws, (uint64_t)p.Hs, (uint64_t)batch, (uint32_t)P.SLB,
-                                 (uint32_t)p.Ws, (uint32_t)P.tile_rows)) return r;
+                                 (uint32_t)(p.Ws + (sc->mode == 1 ? 1 : 0)), (uint32_t)P.tile_rows)) return r;
   const bool lo_on = d.rq.lo > -128;
   typedef void (*Kern)(CUtensorMap, DefTParams);
   static const Kern kerns[3][2] = {
       {deform_tile_int_kernel<2, 1, 256, 2, true>, deform_tile_int_kernel<2, 2, 256, 2, true>},
       {deform_tile_int_kernel<1, 1, 512, 2, false>, deform_tile_int_kernel<1, 2, 512, 2, false>},
       {deform_tile_int_kernel<1, 1, 256, 3, true>, deform_tile_int_kernel<1, 2, 256, 3, true>}};
-  const Kern kern = kerns[P.variant][lo_on ? 1 : 0];
-  static bool attr_set[6][64] = {};
-  if (cdn_first_on_device(attr_set[P.variant * 2 + (lo_on ? 1 : 0)])) {
-    CDN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-    CDN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  static bool attr_set[7][64] = {};
+  if (sc->mode == 1) {
+    CDN_CHECK(dwp != nullptr, CDN_ERR_STATE, "deform (tile, bilinear): missing parameter block");
+    if (cdn_first_on_device(attr_set[6])) {
+      CDN_CUDA(cudaFuncSetAttribute(deform_tile_bil_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+      CDN_CUDA(cudaFuncSetAttribute(deform_tile_bil_kernel<256>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    }
+  } else if (cdn_first_on_device(attr_set[P.variant * 2 + (lo_on ? 1 : 0)])) {
+    CDN_CUDA(cudaFuncSetAttribute(kerns[P.variant][lo_on ? 1 : 0], cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    CDN_CUDA(cudaFuncSetAttribute(kerns[P.variant][lo_on ? 1 : 0], cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   }
   cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)P.ns, (unsigned)P.nbands, (unsigned)batch); cfg.blockDim = dim3((unsigned)P.NT); cfg.stream = st;
@@ -344,7 +577,13 @@ int deform_tile_launch(const DwDevice& d, const cdn_deform_scale* sc, const int8
     attr[1].val.clusterDim.x = (unsigned)P.ns; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
     cfg.numAttrs = 2;
   }
-  CDN_CUDA(cudaLaunchKernelEx(&cfg, kern, tmI, p));
-  CDN_LAUNCH_CHECK("deform_tile_int_kernel");
+  if (sc->mode == 1) {
+    DefTBil f; memset(&f, 0, sizeof(f));
+    f.mb = d.mb; f.lo_f = (float)d.rq.lo; f.thr_bil = d.thr_bil;
+    f.Ms = sc->Ms; f.bs = sc->bs; f.ss = sc->ss; f.zs = sc->zs; f.u_lo = (double)(-sc->bound + 1); f.u_hi = (double)sc->bound;
+    f.acc_s_bias = d.acc_s_bias;
+    CDN_CUDA(cudaLaunchKernelEx(&cfg, deform_tile_bil_kernel<256>, tmI, p, f, *dwp));
+  } else CDN_CUDA(cudaLaunchKernelEx(&cfg, kerns[P.variant][lo_on ? 1 : 0], tmI, p));
+  CDN_LAUNCH_CHECK("deform_tile kernel");
   return 0;
 }

@@ -28,8 +28,9 @@ int deform_launch(const DwDevice& d, const cdn_deform_scale* sc, const int8_t* i
 // integer-offset layer with the input tile + halo staged in shared memory by TMA (deform_tile.cu); deform_launch picks it
 // when the shape is eligible
 bool deform_tile_ok(const DwDevice& d, const cdn_deform_scale* sc, int in_pitch, int out_pitch, int batch, int H, int W, int in_shift);
+struct DwParams;
 int deform_tile_launch(const DwDevice& d, const cdn_deform_scale* sc, const int8_t* in, int in_pitch, int8_t* out, int out_pitch,
-                       int batch, int H, int W, int in_shift, int zx, float* sval, cudaStream_t st);
+                       int batch, int H, int W, int in_shift, int zx, float* sval, const DwParams* dwp, cudaStream_t st);
 int make_tmap_nhwc_box(CUtensorMap* m, const void* base, uint64_t pitch, uint64_t W, uint64_t H, uint64_t batch,
                        uint32_t box_c, uint32_t box_w, uint32_t box_h);
 

@@ -147,3 +147,42 @@ int stem_launch(const StemDevice& d, const float* img, int batch, int H, int W, 
   }
   return 0;
 }
+
+
+// ---- module-level helpers (compat.QuantAct / MaxPool on an int8 grid) --------------------------------------------------
+// QuantAct.forward on a real-valued tensor (quant_modules.py:202-225 with frozen range; quant_utils.py:31-39):
+// q = rint(fl64(fl64(s * x) - z)) saturated to int8, fp32 NCHW in, int8 NHWC out (channels beyond C zero-filled).
+__global__ void quantize_f32_i8_kernel(const float* __restrict__ in, int8_t* __restrict__ out, int C, int pitch, long long hw,
+                                       long long total, double s, double z) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // one thread per (pixel, channel slot)
+  if (i >= total) return;
+  const int c = (int)(i % pitch); const long long pix = i / pitch;
+  const long long b = pix / hw, r = pix - b * hw;
+  int q = 0;
+  if (c < C) {
+    const double t = __dsub_rn(__dmul_rn(s, (double)__ldg(in + ((size_t)b * C + c) * hw + r)), z);
+    q = (int)fmin(fmax(rint(t), -128.0), 127.0);
+  }
+  out[i] = (int8_t)q;
+}
+extern "C" int cdn_quantize_f32_i8(const float* d_in, int batch, int C, int H, int W, double scale, double zero, int8_t* d_out,
+                                   int out_pitch, cdn_stream_t stream) {
+  CDN_CHECK(d_in && d_out && batch >= 0 && C >= 1 && H >= 1 && W >= 1 && out_pitch >= C, CDN_ERR_INVALID, "quantize: bad arguments");
+  const long long total = (long long)batch * H * W * out_pitch;
+  if (total == 0) return 0;
+  quantize_f32_i8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_in, d_out, C, out_pitch, (long long)H * W,
+                                                                                             total, scale, zero);
+  CDN_LAUNCH_CHECK("quantize_f32_i8_kernel");
+  return 0;
+}
+// nn.MaxPool2d(3, 2, 1) on an int8 NHWC grid (the stem's pool when the graph is run module by module)
+extern "C" int cdn_maxpool3s2_i8(const int8_t* d_in, int batch, int H, int W, int pitch, int8_t* d_out, cdn_stream_t stream) {
+  CDN_CHECK(d_in && d_out && batch >= 0 && H >= 1 && W >= 1 && pitch % 4 == 0, CDN_ERR_INVALID, "maxpool: bad arguments");
+  const int Hp = (H - 1) / 2 + 1, Wp = (W - 1) / 2 + 1;
+  const long long words = (long long)batch * Hp * Wp * (pitch / 4);
+  if (words == 0) return 0;
+  maxpool3s2_kernel<<<(unsigned)((words + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const uint32_t*)d_in, (uint32_t*)d_out, H, W, Hp, Wp,
+                                                                                        pitch / 4, words);
+  CDN_LAUNCH_CHECK("maxpool3s2_kernel");
+  return 0;
+}

@@ -118,6 +118,14 @@ int cdn_deform_layer_run(cdn_deform_layer* layer, const int8_t* d_in, int in_pit
                          int8_t* d_out, int out_pitch, float* d_sval, cdn_stream_t stream);
 int cdn_deform_layer_destroy(cdn_deform_layer* layer);
 
+/* ---- module-level helpers: QuantAct on a real-valued tensor, MaxPool on the int8 grid -----------------------------
+ * What compat.QuantAct.forward (portable_quantizer/quant_modules.py:202-225, frozen range) runs when it is handed an fp32
+ * NCHW tensor: q = rint(fl64(fl64(scale*x) - zero)) (quant_utils.py:31-39) saturated to int8, written as int8 NHWC with
+ * `out_pitch` bytes per pixel.  cdn_maxpool3s2_i8: nn.MaxPool2d(3, 2, 1) of an int8 NHWC grid (quantize_model.py:31-35). */
+int cdn_quantize_f32_i8(const float* d_in, int batch, int C, int H, int W, double scale, double zero, int8_t* d_out,
+                        int out_pitch, cdn_stream_t stream);
+int cdn_maxpool3s2_i8(const int8_t* d_in, int batch, int H, int W, int pitch, int8_t* d_out, cdn_stream_t stream);
+
 /* ---- 1x1 convolution as int8 tcgen05 GEMM ---------------------------------------------------------------
  * acc[p][n] = sum_k wq[n][k] * (in[p][k_off + k] + zx)   (exact int32; the library adds zx*sum_k wq[n][k] itself)
  * Output "chunks" describe where each group of <=16 output channels lands in the NHWC row, so that split /
