@@ -17,7 +17,8 @@ checkpoints load unchanged and tests read like the reference's own usage -- but 
 
 The quantised modules are parameter containers: the reference evaluates them eagerly, one fake-quant tensor at a
 time; here the whole quantised graph is compiled once into an int8 plan (codenet_b200.plan) and executed by
-libcodenet_b200 on the GPU.  Calling forward() on an individual quantised module raises NotCompiledError.
+libcodenet_b200 on the GPU.  forward() of an individual quantised module runs its own kernels through the C ABI on QTensor
+values (int8 NHWC + scale / zero point; qtensor.py, module_exec.py): boundary B2 at module granularity.
 """
 from .dcn import deform_conv, DeformConvFunction, DeformConv, DeformConvWithOffsetScaleBoundPositive  # noqa: F401
 from .shufflenetv2_dcn import BaseNode, PoseShuffleNetV2, get_shufflenetv2_dcn, channel_shuffle  # noqa: F401
@@ -28,3 +29,4 @@ from .quantize_model import quantize_shufflenetv2_dcn, freeze_ranges  # noqa: F4
 from .decode import ctdet_decode  # noqa: F401
 from .nms import soft_nms  # noqa: F401
 from .detector import CtdetDetector  # noqa: F401
+from .qtensor import QTensor, PendingConv  # noqa: F401

@@ -4,24 +4,33 @@ Same names, constructor signatures, `set_param` / `set_act` protocol and state-d
 (QuantAct :163-225, Quant_Conv2d :228-321, QuantBnConv2d :324-419, QuantDeformConv2d :422-517,
 QuantDeformConvWithOffsetScaleBoundPositive :621-671, QuantBaseNode :809-907, QuantDepthwiseNode :1013-1071,
 QuantLinear :23-160).  The reference evaluates these eagerly in fake-quant fp32 and re-quantises every weight on
-every call; here they are containers that the plan compiler (codenet_b200.plan) reads ONCE: BN folding, weight
-quantisation and activation scales are computed at compile time in fp64 with the reference's formulae
-(quantization_utils/quant_utils.py:31-82, :170-223) and the graph runs as int8 kernels.
+every call.  Here they work at two levels:
+
+  * whole network: the plan compiler (codenet_b200.plan) reads them ONCE -- BN folding, weight quantisation and activation
+    scales in fp64 with the reference's formulae (quantization_utils/quant_utils.py:31-82, :170-223) -- and the graph runs as
+    one compiled engine (PoseShuffleNetV2.forward);
+  * module by module (boundary B2): every forward() below runs on the GPU through the stand-alone kernels of the C ABI
+    (compat/module_exec.py), passing QTensor values (int8 NHWC + scale / zero point, compat/qtensor.py) instead of the
+    reference's fake-quantised fp32 tensors; `.dequantize()` gives the reference's fp32 view.  Results are bit-identical to
+    the compiled engine.  QuantAct ranges must be frozen.  There is no CPU path.
 """
 import torch
 import torch.nn as nn
 from torch.nn import Module, Parameter
 
 
+from .qtensor import QTensor, PendingConv
+
+
 class NotCompiledError(RuntimeError):
     pass
 
 
-def _eager(name):
-    raise NotCompiledError(
-        "codenet_b200.%s is part of a compiled int8 graph and cannot be evaluated eagerly on its own; run the "
-        "network (PoseShuffleNetV2.forward / Engine.from_module), which executes the whole quantised graph on the GPU"
-        % name)
+def _need_q(x, who):
+    if not isinstance(x, QTensor):
+        raise TypeError("codenet_b200.%s.forward takes a QTensor (an activation on a QuantAct grid); got %s -- quantise real "
+                        "values with a QuantAct first" % (who, type(x).__name__))
+    return x
 
 
 def _check_mode(quant_mode):
@@ -55,7 +64,24 @@ class QuantAct(Module):
             self.__class__.__name__, self.activation_bit, self.full_precision_flag, self.x_min.item(), self.x_max.item())
 
     def forward(self, x):
-        _eager("QuantAct")
+        """PendingConv -> the conv, its ReLU and this quantiser as ONE kernel; fp32 CUDA tensor (real values) -> quantised
+        (cdn_quantize_f32_i8, quant_utils.py:31-39 with saturation); QTensor on this grid -> itself."""
+        from . import module_exec as X
+        act = X.act_of(self)
+        if isinstance(x, PendingConv):
+            return x.module._fused(x.x, act, x.relu)
+        if isinstance(x, QTensor):
+            if x.same_grid(act):
+                return x
+            raise NotImplementedError("QuantAct on a tensor that already lives on another grid is not part of the CoDeNet graph")
+        if torch.is_tensor(x):
+            if not x.is_cuda:
+                raise RuntimeError("codenet_b200 has no CPU execution path: QuantAct needs a CUDA tensor")
+            from .. import ops
+            B, Cc, H, W = x.shape
+            pitch = (Cc + 31) // 32 * 32
+            return QTensor(ops.quantize(x, Cc, H, W, act[0], act[1], pitch), Cc, act)
+        raise TypeError("QuantAct.forward: unsupported input %s" % type(x).__name__)
 
 
 class Quant_Conv2d(Module):
@@ -78,8 +104,26 @@ class Quant_Conv2d(Module):
         except AttributeError:
             self.bias = None
 
+    # a Quant_Conv2d has no BatchNorm: `self` plays the conv's role for the shared helpers
+    @property
+    def _percentile(self):
+        return bool(self.weight_percentile)
+
+    def _out_shape(self, x):
+        return (x.shape[0], self.out_channels, x.shape[2], x.shape[3])
+
+    def _fused(self, x, act, relu):
+        from . import module_exec as X
+        return X.fused_conv(self, None, self.weight_bit, self._percentile, x, act, relu)
+
+    def _float_out(self, x):
+        from . import module_exec as X
+        return X.float_conv(self, None, self.weight_bit, self._percentile, _need_q(x, "Quant_Conv2d"))
+
     def forward(self, x):
-        _eager("Quant_Conv2d")
+        """1x1 conv on a QTensor -> fp32 NCHW (the reference's use: head output convs and the offset-scale conv, neither is
+        followed by a QuantAct that could close the kernel; quant_modules.py:278-321)"""
+        return self._float_out(x)
 
 
 class QuantBnConv2d(Module):
@@ -98,8 +142,25 @@ class QuantBnConv2d(Module):
         self.conv = conv
         self.bn = bn
 
+    def _out_shape(self, x):
+        st = self.conv.stride[0]
+        return (x.shape[0], self.conv.out_channels, (x.shape[2] - 1) // st + 1, (x.shape[3] - 1) // st + 1)
+
+    def _fused(self, x, act, relu):
+        from . import module_exec as X
+        return X.fused_conv(self.conv, self.bn, self.weight_bit, bool(self.weight_percentile), x, act, relu)
+
+    def _float_out(self, x):
+        from . import module_exec as X
+        return X.float_conv(self.conv, self.bn, self.weight_bit, bool(self.weight_percentile), _need_q(x, "QuantBnConv2d"))
+
     def forward(self, x):
-        _eager("QuantBnConv2d")
+        """conv + folded BN (quant_modules.py:364-419).  The requantisation of the following QuantAct lives in the conv
+        kernel's epilogue, so this returns a PendingConv that nn.ReLU marks and QuantAct.forward executes;
+        `.dequantize()` on it gives the reference's fp32 return value (1x1 convs)."""
+        if not (isinstance(x, QTensor) or (torch.is_tensor(x) and x.is_cuda)):
+            raise TypeError("QuantBnConv2d.forward takes a QTensor (or the CUDA fp32 image for the stem conv)")
+        return PendingConv(self, x)
 
 
 class QuantDeformConv2d(Module):
@@ -121,7 +182,24 @@ class QuantDeformConv2d(Module):
         self.bias = None
 
     def forward(self, x, offset):
-        _eager("QuantDeformConv2d")
+        """The general op of the reference (quant_modules.py:473-517 -> deform_conv): real-valued input (fp32 NCHW or a QTensor,
+        dequantised), an explicit offset tensor [B,18,Ho,Wo], weights quantised per channel -> fp32 NCHW, through
+        cdn_deform_conv_forward_f32.  The fused W4A8 layer is QuantDeformConvWithOffsetScaleBoundPositive.forward."""
+        from .. import ops
+        from ..plan import quant_weight
+        xf = x.dequantize() if isinstance(x, QTensor) else x
+        if not (torch.is_tensor(xf) and xf.is_cuda):
+            raise RuntimeError("codenet_b200 has no CPU execution path: QuantDeformConv2d needs CUDA tensors")
+        w = self.weight.detach().double().cpu().numpy()
+        if self.full_precision_flag:
+            wd = w
+        else:
+            if not self.per_channel:
+                raise NotImplementedError("per-tensor deformable weights are not used by CoDeNet (base_detector.py:29-34)")
+            wq, sigma = quant_weight(w, self.weight_bit, bool(self.weight_percentile))
+            wd = wq / sigma.reshape(-1, 1, 1, 1)
+        wt = torch.from_numpy(wd.astype("float32")).to(xf.device)
+        return ops.deform_conv_f32(xf, offset, wt, self.stride, self.padding, self.dilation, self.groups, self.deformable_groups)
 
 
 class _Compound(Module):
@@ -161,7 +239,12 @@ class QuantDeformConvWithOffsetScaleBoundPositive(_Compound):
         self.quant_conv_channel_bn = self._bnconv(deform_conv.conv_channel, bn)
 
     def forward(self, x):
-        _eager("QuantDeformConvWithOffsetScaleBoundPositive")
+        """quant_modules.py:668-671: scale conv + Hardtanh + QuantAct(s) + offsets + depthwise deformable conv + QuantAct as the
+        fused kernel (cdn_deform_dw_w4a8; `self.offset_mode` = "bilinear", the reference's arithmetic, or "round"), then the
+        1x1 conv_channel + BN as a PendingConv for the caller's ReLU + QuantAct, exactly where the reference returns."""
+        from . import module_exec as X
+        y = X.deform_block(self, _need_q(x, "QuantDeformConvWithOffsetScaleBoundPositive"))
+        return self.quant_conv_channel_bn(y)
 
 
 class QuantBaseNode(_Compound):
@@ -187,7 +270,8 @@ class QuantBaseNode(_Compound):
         self.quant_act = share_quant_act
 
     def forward(self, x):
-        _eager("QuantBaseNode")
+        from . import module_exec as X
+        return X.base_node(self, _need_q(x, "QuantBaseNode"))
 
 
 class QuantDepthwiseNode(_Compound):
@@ -204,7 +288,8 @@ class QuantDepthwiseNode(_Compound):
         self.quant_conv.set_param(head_node[6])
 
     def forward(self, x):
-        _eager("QuantDepthwiseNode")
+        from . import module_exec as X
+        return X.head_node(self, _need_q(x, "QuantDepthwiseNode"))
 
 
 class QuantLinear(nn.Linear):
@@ -219,4 +304,5 @@ class QuantLinear(nn.Linear):
         _check_mode(quant_mode)
 
     def forward(self, x):
-        _eager("QuantLinear")
+        raise NotCompiledError("QuantLinear is not instantiated by any CoDeNet graph (quantize_model.py never creates one); "
+                               "no kernel backs it")

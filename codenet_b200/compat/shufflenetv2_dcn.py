@@ -133,6 +133,24 @@ class PoseShuffleNetV2(nn.Module):
         out = e.run(x.contiguous().float(), maps=True, dets=False, raw_hm=True)
         return [{h: out[h] for h in self.heads}]
 
+    def forward_modules(self, x):
+        """The reference's forward (shufflenetv2_dcn.py:314-330) module by module: every Quant* member runs its own kernels
+        through the C ABI on QTensor values (boundary B2; compat/module_exec.py).  Same bits as forward(), many more launches:
+        meant for graphs that keep the reference's module structure, not for speed.  x: CUDA fp32 [B,3,H,W]."""
+        if not x.is_cuda:
+            raise RuntimeError("codenet_b200 has no CPU execution path: move the input to a B200")
+        from .quant_modules import QuantDeformConvWithOffsetScaleBoundPositive
+        for m in self.modules():
+            if isinstance(m, QuantDeformConvWithOffsetScaleBoundPositive):
+                m.offset_mode = self.offset_mode
+        x = self.layer0(x.contiguous().float())
+        x = self.layer1(x)
+        x = self.layer2(x)
+        x = self.layer3(x)
+        x = self.layer4(x)
+        x = self.deconv_layers(x)
+        return [{head: getattr(self, head)(x) for head in self.heads}]
+
     def init_weights(self, num_layers):
         """The reference builds a renamed state dict from a downloaded pytorchcv model and never loads it
         (shufflenetv2_dcn.py:332-361): a no-op here (no network access either)."""

@@ -83,6 +83,16 @@ class Engine:
                         wt_percentile=bool(getattr(model, "wt_percentile", False)))
         return cls.from_state_dict(cfg, sd, in_H, in_W, max_batch, offset_mode, device, K)
 
+    @classmethod
+    def from_plan_file(cls, path: str, max_batch: int, device: int = 0, K: int = 100):
+        """Runs a compiled plan saved by codenet_b200.plan_io.save_plan: no checkpoint, network definition or torch.load."""
+        from .plan_io import load_plan
+        return cls(load_plan(path), max_batch, device, K)
+
+    def save_plan(self, path: str):
+        from .plan_io import save_plan
+        save_plan(self.plan, path)
+
     def close(self):
         if self._h:
             self.lib.cdn_engine_destroy(self._h)

@@ -61,10 +61,15 @@ def test_modules_refuse_eager_and_cpu_execution():
     x = torch.zeros(1, 3, 64, 64)
     with pytest.raises(RuntimeError, match="no CPU execution path"):
         m(x)
-    with pytest.raises(compat.NotCompiledError):
+    with pytest.raises(TypeError, match="takes a QTensor"):            # module-level forwards run on QTensor values ...
         m.layer1[0](torch.zeros(1, 24, 16, 16))
-    with pytest.raises(compat.NotCompiledError):
+    with pytest.raises(RuntimeError, match="running statistic"):       # ... need frozen ranges ...
         compat.QuantAct(8, quant_mode="asymmetric")(x)
+    qa = compat.QuantAct(8, quant_mode="asymmetric"); qa.set_range(-1.0, 1.0)
+    with pytest.raises(RuntimeError, match="no CPU execution path"):   # ... and a GPU
+        qa(x)
+    with pytest.raises(compat.NotCompiledError):
+        compat.QuantLinear(4, 8, 8)(torch.zeros(1, 8))
     with pytest.raises(NotImplementedError):                 # the reference refuses CPU tensors the same way
         compat.deform_conv(torch.zeros(1, 4, 5, 5), torch.zeros(1, 18, 5, 5), torch.zeros(4, 1, 3, 3), 1, 1, 1, 4, 1)
     with pytest.raises(ValueError, match="Expected 4D tensor"):

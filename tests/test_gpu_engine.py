@@ -377,3 +377,24 @@ def test_repeated_runs_are_identical_at_large_batch(calib):
     d_host, i_host = eng.run_host(x.cpu().numpy())
     assert i_host.tobytes() == ref[1] and d_host.tobytes() == ref[0]
     eng.close()
+
+
+def test_engine_from_plan_file_equals_engine_from_checkpoint(calib, tmp_path):
+    """the compiled plan saved to disk (plan_io) and run without the checkpoint gives the same bytes."""
+    import torch
+    st = make_quant_state(CFG, calib, "bilinear", 256)
+    eng = Engine.from_state_dict(CFG, st, 256, 256, 2, offset_mode="bilinear")
+    f = str(tmp_path / "m.cdnplan.npz")
+    eng.save_plan(f)
+    x = torch.from_numpy(make_images(2, 256, seed=2)).cuda()
+    a = eng.run(x)
+    torch.cuda.synchronize()
+    want = (eng.read_heads(2).copy(), a["dets"].cpu().numpy(), a["inds"].cpu().numpy())
+    eng.close()
+    eng2 = Engine.from_plan_file(f, 2)
+    b = eng2.run(x)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(eng2.read_heads(2), want[0])
+    np.testing.assert_array_equal(b["dets"].cpu().numpy(), want[1])
+    np.testing.assert_array_equal(b["inds"].cpu().numpy(), want[2])
+    eng2.close()

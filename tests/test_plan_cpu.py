@@ -113,3 +113,70 @@ def test_no_cpu_fallback():
     import ctypes as C
     h = C.c_void_p()
     assert lib.cdn_engine_create(C.byref(h), 0) == -3
+
+
+def test_plan_file_round_trip(calib, tmp_path):
+    """The compiled-plan artefact (plan_io: one .npz, no pickle): every tensor record, op argument (arrays and fp64 scalars
+    bit for bit) and tap survives save -> load."""
+    from codenet_b200.plan import build_plan
+    from codenet_b200.plan_io import save_plan, load_plan
+    cfg = NetConfig(num_classes=20)
+    st = make_quant_state(cfg, calib, "bilinear", 256)
+    p = build_plan(cfg, st, 256, 256, "bilinear")
+    f = str(tmp_path / "codenet1x_256.cdnplan.npz")
+    save_plan(p, f)
+    q = load_plan(f)
+    assert q.cfg == p.cfg and (q.in_H, q.in_W, q.offset_mode, q.cat, q.out_H, q.out_W) == (p.in_H, p.in_W, p.offset_mode, p.cat, p.out_H, p.out_W)
+    assert q.taps == p.taps and len(q.tensors) == len(p.tensors) and len(q.ops) == len(p.ops)
+    for a, b in zip(p.tensors, q.tensors):
+        assert (a.id, a.H, a.W, a.C, a.pitch, a.half, a.name) == (b.id, b.H, b.W, b.C, b.pitch, b.half, b.name)
+        assert tuple(float(v) for v in a.act) == tuple(b.act)
+    for a, b in zip(p.ops, q.ops):
+        assert (a.kind, a.name) == (b.kind, b.name) and set(a.a) == set(b.a)
+        for k, v in a.a.items():
+            if isinstance(v, np.ndarray):
+                assert v.dtype == b.a[k].dtype and np.array_equal(v, b.a[k]), (a.name, k)
+            else:
+                assert type(b.a[k]) in (int, float) and b.a[k] == v, (a.name, k)
+    import os
+    assert os.path.getsize(f) < 2.5e6                      # 1.6 M parameters as int8 + constants
+
+
+def test_reference_written_checkpoint_loads(tmp_path):
+    """A checkpoint written by the REFERENCE's own save_model (lib/models/model.py:91-100: {'epoch', 'state_dict'}) from its own
+    quantised network loads into the compat detector's model through load_model (:35-88 semantics: 'module.' prefix stripped,
+    optimizer entry ignored) with every tensor identical.  Needs the reference tree (build container)."""
+    from oracle import ref_harness as H
+    if not H.available():
+        pytest.skip("reference tree not available")
+    import torch
+    from codenet_b200 import compat
+    from codenet_b200.synth import make_raw_state
+    H.load_reference()
+    from models.model import save_model
+    cfg = NetConfig(num_classes=20)
+    raw = make_raw_state(cfg, 0)
+    ref = H.build_reference_model({k: torch.from_numpy(v) for k, v in raw.items()}, dict(cfg.head_list()), dtype=torch.float32)
+    ref.eval()
+    H.quantize_reference_model(ref)
+    with torch.no_grad():
+        for n, b in ref.named_buffers():                   # give the QuantAct ranges recognisable values
+            if n.endswith("x_min"):
+                b.fill_(-1.25)
+            if n.endswith("x_max"):
+                b.fill_(3.5)
+    f = str(tmp_path / "model_last.pth")
+    save_model(f, 7, torch.nn.DataParallel(ref) if False else ref)
+    ck = torch.load(f, map_location="cpu")
+    assert set(ck) >= {"epoch", "state_dict"}
+    # as a DataParallel training run would have written it
+    torch.save({"epoch": 7, "state_dict": {"module." + k: v for k, v in ck["state_dict"].items()}, "optimizer": {}}, f)
+    det = compat.CtdetDetector.__new__(compat.CtdetDetector)
+    det.model = compat.PoseShuffleNetV2({"hm": 20, "wh": 2, "reg": 2}, 64)
+    compat.quantize_shufflenetv2_dcn(det.model, 4, None, 8, "symmetric", "asymmetric", True, False, False, False)
+    unexpected = det.load_model(f)
+    assert not unexpected
+    mine, theirs = det.model.state_dict(), ref.state_dict()
+    assert set(mine) == set(theirs)
+    for k in theirs:
+        assert torch.equal(mine[k].float(), theirs[k].float()), k
