@@ -309,7 +309,7 @@ def run_ours(args):
 
     # ---- the reference's default semantics (fractional offsets -> bilinear gather) on the same workload --------------------
     bil = None
-    if args.offset_mode == "round" and not args.no_bilinear:
+    if args.offset_mode == "round" and not args.no_bilinear and ("ranges_bilinear_%d/stem" % R) in calib.files:
         st_b = make_quant_state(cfg, calib, "bilinear", R)
         eng_b = Engine.from_state_dict(cfg, st_b, R, R, B, offset_mode="bilinear", device=local)
         ob = {}

@@ -47,6 +47,7 @@ struct DefTParams {
   uint32_t pad_word;
   uint32_t* out; float* sval;
   int no_dedup;                              // A/B: every output pixel gathers for itself
+  int dbg;                                   // timing experiments only (results are wrong): 1 no phase C, 2 no tap loads, 4 no MAC
 };
 
 __device__ __forceinline__ bool g_dtl_no_dedup(const DefTParams& p) { return p.no_dedup != 0; }
@@ -166,7 +167,7 @@ __global__ void __launch_bounds__(NT, MINB) deform_tile_int_kernel(const __grid_
   }
   __syncthreads();
   // ---------------- phase C: gather from shared memory, MAC, requantise, store ----------------
-  if (!lane_on) return;
+  if (!lane_on || (p.dbg & 1)) return;
   const int nu = *n_units;
   const uint32_t lane_base = s0 + (uint32_t)lw0 * 4u;
   const uint32_t tab0 = s0 + p.off_tab;
@@ -181,12 +182,17 @@ __global__ void __launch_bounds__(NT, MINB) deform_tile_int_kernel(const __grid_
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
       const uint32_t a = idx[t] * slb + lane_base;
+      if (p.dbg & 2) { x[0][t] = a; x[V - 1][t] = a * 3u; continue; }
       if (V == 2) { const uint2 r = lds_u64(a); x[0][t] = r.x; x[V - 1][t] = r.y; }
       else x[0][t] = lds_u32(a);
     }
   };
   auto compute = [&](uint32_t meta, const uint32_t (&x)[V][9]) {
     uint32_t o[V];
+    if (p.dbg & 4) {
+#pragma unroll
+      for (int v = 0; v < V; ++v) { o[v] = 0; for (int t = 0; t < 9; ++t) o[v] ^= x[v][t]; }
+    } else
 #pragma unroll
     for (int v = 0; v < V; ++v) {
       uint32_t a0, a1, a2, a3, b0, b1, b2, b3;
@@ -545,6 +551,7 @@ int deform_tile_launch(const DwDevice& d, const cdn_deform_scale* sc, const int8
   p.pad_word = (uint32_t)(uint8_t)(int8_t)(-zx) * 0x01010101u;
   p.out = (uint32_t*)out; p.sval = sval;
   p.no_dedup = (g_cdn_debug_flags & 16384u) ? 1 : 0;                // bit 14: no 2x2 block units (A/B)
+  p.dbg = (int)((g_cdn_debug_flags >> 16) & 7u);                    // bits 16-18: timing experiments (wrong results)
   CUtensorMap tmI;
   if (int r = make_tmap_nhwc_box(&tmI, in, (uint64_t)in_pitch, (uint64_t)p.Ws, (uint64_t)p.Hs, (uint64_t)batch, (uint32_t)P.SLB,
                                  (uint32_t)(p.Ws + (sc->mode == 1 ? 1 : 0)), (uint32_t)P.tile_rows)) return r;
