@@ -183,6 +183,25 @@ class CtdetDetector:
             chw = np.concatenate([chw, chw[..., ::-1]], 0)
         return torch.from_numpy(np.ascontiguousarray(chw)), self._meta(c, s, ih, iw)
 
+    def pre_process_device(self, image, scale=1, meta=None):
+        """pre_process for a raw uint8 HWC image at test scale 1 ON THE DEVICE: the frame is uploaded as it is and
+        cdn_warp_affine_u8 (bit-identical to the cv2.warpAffine call of base_detector.py:61-65; at scale 1 the cv2.resize in
+        front of it is the identity) writes the network-sized uint8 image, mirrored copy included for --flip_test.  The
+        normalisation then happens inside the stem kernel.  Returns (uint8 CUDA tensor [1|2, H, W, 3], meta)."""
+        import ctypes as C
+        from .. import _lib
+        if scale != 1 or image.dtype != np.uint8 or image.ndim != 3 or image.shape[2] != 3:
+            raise ValueError("pre_process_device takes a uint8 HWC image at test scale 1")
+        (sh, sw), (ih, iw), c, s = self.input_geometry(image.shape[0], image.shape[1], 1)
+        M = np.ascontiguousarray(get_affine_transform(c, s, 0, [iw, ih]), dtype=np.float64)
+        src = torch.from_numpy(np.ascontiguousarray(image)).to(self.opt.device)
+        n = 2 if self.opt.flip_test else 1
+        dst = torch.empty((n, ih, iw, 3), dtype=torch.uint8, device=self.opt.device)
+        with torch.cuda.device(self.opt.device):
+            _lib.check(_lib.load().cdn_warp_affine_u8(C.c_void_p(src.data_ptr()), sh, sw, C.c_void_p(M.ctypes.data), C.c_void_p(dst.data_ptr()),
+                                                      ih, iw, n - 1, C.c_void_p(torch.cuda.current_stream(self.opt.device).cuda_stream)))
+        return dst, self._meta(c, s, ih, iw)
+
     def _is_identity_input(self, image, scale):
         """True when resize + warpAffine leave the image untouched: uint8, already input-sized, landscape or square (for a
         portrait image the longer side is the height, so the affine scales by input_w / height and pads)."""
@@ -208,13 +227,18 @@ class CtdetDetector:
         return (output, out["dets"], forward_time) if return_time else (output, out["dets"])
 
     def process(self, images, return_time=False):
-        """images: CUDA fp32 [B,3,H,W].  Returns (output {'hm' (post-sigmoid), 'wh', 'reg'}, dets [B|1,K,6][, time])."""
+        """images: CUDA fp32 [B,3,H,W] (the reference's tensor) or uint8 [B,H,W,3] (pre_process_device).
+        Returns (output {'hm' (post-sigmoid), 'wh', 'reg'}, dets [B|1,K,6][, time])."""
         if not images.is_cuda:
             raise RuntimeError("codenet_b200 has no CPU execution path: process() needs CUDA images")
-        B, _, H, W = images.shape
+        if images.dtype == torch.uint8:
+            B, H, W, _ = images.shape
+            x = images.contiguous()
+        else:
+            B, _, H, W = images.shape
+            x = images.contiguous().float()
         dev = images.device.index if images.device.index is not None else torch.cuda.current_device()
         eng = self._engine_for(H, W, B, dev)
-        x = images.contiguous().float()
         if not self.opt.flip_test:
             # forward + sigmoid + decode in one graph replay; `hm` comes back post-sigmoid like output['hm'].sigmoid_()
             out = eng.run(x, maps=True, dets=True)
@@ -250,10 +274,18 @@ class CtdetDetector:
         d = torch.as_tensor(dets, dtype=torch.float32, device=self.opt.device).detach().reshape(1, -1, 6).contiguous().clone()
         t = np.ascontiguousarray(get_affine_transform(meta['c'], meta['s'], 0, (meta['out_width'], meta['out_height']), inv=1),
                                  dtype=np.float64).reshape(1, 6)
+        g = torch.empty_like(d)
+        counts = torch.empty((1, self.num_classes), dtype=torch.int32, device=d.device)
         with torch.cuda.device(d.device):
-            _lib.check(_lib.load().cdn_ctdet_post_affine(C.c_void_p(d.data_ptr()), 1, d.shape[1], C.c_void_p(t.ctypes.data),
-                                                         C.c_void_p(torch.cuda.current_stream(d.device).cuda_stream)))
-        out = group_by_class(d[0].cpu().numpy(), self.num_classes)
+            st = C.c_void_p(torch.cuda.current_stream(d.device).cuda_stream)
+            L = _lib.load()
+            _lib.check(L.cdn_ctdet_post_affine(C.c_void_p(d.data_ptr()), 1, d.shape[1], C.c_void_p(t.ctypes.data), st))
+            _lib.check(L.cdn_ctdet_group_by_class(C.c_void_p(d.data_ptr()), 1, d.shape[1], self.num_classes, C.c_void_p(g.data_ptr()),
+                                                  C.c_void_p(counts.data_ptr()), st))
+        rows, cnt = g[0].cpu().numpy(), counts[0].cpu().numpy()
+        ends = np.cumsum(cnt)
+        out = {j + 1: np.ascontiguousarray(rows[ends[j] - cnt[j]:ends[j], :5], dtype=np.float32).reshape(-1, 5)
+               for j in range(self.num_classes)}
         if scale != 1:
             for v in out.values():
                 v[:, :4] /= scale
@@ -298,6 +330,9 @@ class CtdetDetector:
                 images = torch.from_numpy(np.ascontiguousarray(image[None]))
                 meta = self._meta(np.array([w / 2., h / 2.], np.float32), float(max(h, w)), h, w)
                 fn = self.process_u8
+            elif scale == 1 and image.dtype == np.uint8 and image.ndim == 3 and getattr(self.opt, "device_pre_process", True):
+                images, meta = self.pre_process_device(image, scale, meta)           # warpAffine (+ mirror) on the device
+                fn = self.process
             else:
                 images, meta = self.pre_process(image, scale, meta)
                 fn = self.process

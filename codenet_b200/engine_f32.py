@@ -45,8 +45,11 @@ class EngineF32:
         self.g = build_graph(cfg)
         st = {k: (v.detach().cpu().numpy() if hasattr(v, "detach") else np.asarray(v)) for k, v in state.items()}
         self.P = {}
+        self.scale_bias = {}                    # host copies of the offset-scale conv biases (kernel arguments by value)
         for c in self.g.all_convs():
             w, b = _fold(st, c)
+            if c.kind == "scale":
+                self.scale_bias[c.name] = float(b[0])
             self.P[c.name] = (torch.from_numpy(np.ascontiguousarray(w.reshape(c.cout, -1))).to(self.dev),
                               torch.from_numpy(np.ascontiguousarray(b)).to(self.dev))
 
@@ -120,7 +123,7 @@ class EngineF32:
                 wd, _ = self.P["up%d.deform" % i]
                 Bc, Cc, H, W = x.shape
                 y = x.new_empty(x.shape)
-                _lib.check(L.cdn_deform_dw_f32(self._p(x), self._p(ws), C.c_float(float(bs[0])), cfg.offset_bound, self._p(wd), self._p(y),
+                _lib.check(L.cdn_deform_dw_f32(self._p(x), self._p(ws), C.c_float(self.scale_bias["up%d.scale" % i]), cfg.offset_bound, self._p(wd), self._p(y),
                                                Bc, Cc, H, W, 1, self._st()))
                 z = self._new(y, up["cout"])
                 self._pw(y, 0, Cc, "up%d.channel" % i, z, 0, 1, True)

@@ -118,6 +118,18 @@ int cdn_deform_layer_run(cdn_deform_layer* layer, const int8_t* d_in, int in_pit
                          int8_t* d_out, int out_pitch, float* d_sval, cdn_stream_t stream);
 int cdn_deform_layer_destroy(cdn_deform_layer* layer);
 
+/* ---- the steps either side of the path, on the device -----------------------------------
+ * cdn_warp_affine_u8: cv2.warpAffine(image, M, (dst_w, dst_h), flags=cv2.INTER_LINEAR) of BaseDetector.pre_process
+ * (lib/detectors/base_detector.py:61-65) on a uint8 HWC image [H][W][3], bit-identical to OpenCV (M6 = the 2x3 source ->
+ * destination matrix cv2 receives, row-major doubles on the HOST); flip_copy != 0 also writes the mirrored image behind
+ * the first one (dst [2][dst_h][dst_w][3], what --flip_test concatenates, :69-70).
+ * cdn_ctdet_group_by_class: the grouping of ctdet_post_process (lib/utils/post_process.py:86-103): d_out [B][K][6] = the
+ * detections ordered by class, original (score) order inside a class; d_counts [B][num_classes]. */
+int cdn_warp_affine_u8(const uint8_t* d_src, int H, int W, const double* M6, uint8_t* d_dst, int dst_h, int dst_w, int flip_copy,
+                       cdn_stream_t stream);
+int cdn_ctdet_group_by_class(const float* d_dets, int batch, int K, int num_classes, float* d_out, int32_t* d_counts,
+                             cdn_stream_t stream);
+
 /* ---- module-level helpers: QuantAct on a real-valued tensor, MaxPool on the int8 grid -----------------------------
  * What compat.QuantAct.forward (portable_quantizer/quant_modules.py:202-225, frozen range) runs when it is handed an fp32
  * NCHW tensor: q = rint(fl64(fl64(scale*x) - zero)) (quant_utils.py:31-39) saturated to int8, written as int8 NHWC with

@@ -164,3 +164,59 @@ def test_post_process_on_device_matches_host_restatement(calib):
     for j in range(1, 21):
         w = np.array(want[j], dtype=np.float32).reshape(-1, 5)
         np.testing.assert_array_equal(got[j], w)
+
+
+def test_device_pre_process_equals_opencv_path(calib):
+    """cdn_warp_affine_u8 against the oracle (pinned to cv2.warpAffine by tests/test_prepost_cpu.py) on
+    landscape, portrait and input-sized frames with and without the --flip_test mirror; and run() through the device
+    pre-process against run() through the reference's host pre_process (cv2), detection for detection."""
+    import torch
+    from oracle import warp_ref
+    from codenet_b200.compat.detector import get_affine_transform
+    det = _detector(calib, "round", 256, max_batch=2)
+    rng = np.random.default_rng(8)
+    for (h, w), flip in (((300, 400), False), ((400, 300), True), ((256, 256), False), ((97, 203), True)):
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        det.opt.flip_test = flip
+        got, meta = det.pre_process_device(img, 1)
+        c, s = np.array([w / 2., h / 2.], np.float32), max(h, w) * 1.0
+        want = warp_ref.warp_affine(img, get_affine_transform(c, s, 0, [256, 256]), (256, 256))
+        g = got.cpu().numpy()
+        np.testing.assert_array_equal(g[0], want)
+        if flip:
+            np.testing.assert_array_equal(g[1], want[:, ::-1])
+        assert meta["out_height"] == 64 and float(meta["s"]) == s
+    pytest.importorskip("cv2")
+    img = rng.integers(0, 256, (300, 400, 3), dtype=np.uint8)
+    for flip in (False, True):
+        det.opt.flip_test = flip
+        det.opt.device_pre_process = True
+        a = det.run(img)["results"]
+        det.opt.device_pre_process = False
+        b = det.run(img)["results"]
+        for j in range(1, 21):
+            np.testing.assert_array_equal(a[j], b[j])
+    det.opt.flip_test = False
+
+
+def test_group_by_class_on_device():
+    """cdn_ctdet_group_by_class against a stable numpy grouping (lib/utils/post_process.py:86-103), out-of-range classes last."""
+    import ctypes as C
+    import torch
+    from codenet_b200 import _lib
+    L = _lib.load()
+    rng = np.random.default_rng(6)
+    B, K, NC = 3, 100, 20
+    dets = rng.uniform(0, 100, (B, K, 6)).astype(np.float32)
+    dets[..., 5] = rng.integers(0, NC, (B, K))
+    dets[1, 7, 5] = 25.0; dets[2, 3, 5] = -1.0
+    d = torch.from_numpy(dets).cuda(); out = torch.zeros_like(d); cnt = torch.zeros((B, NC), dtype=torch.int32, device="cuda")
+    _lib.check(L.cdn_ctdet_group_by_class(C.c_void_p(d.data_ptr()), B, K, NC, C.c_void_p(out.data_ptr()), C.c_void_p(cnt.data_ptr()),
+                                          C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    o, c = out.cpu().numpy(), cnt.cpu().numpy()
+    for b in range(B):
+        cls = dets[b, :, 5]
+        key = np.where((cls >= 0) & (cls < NC), cls, NC)
+        order = np.argsort(key, kind="stable")
+        np.testing.assert_array_equal(o[b], dets[b][order])
+        np.testing.assert_array_equal(c[b], np.bincount(key.astype(int), minlength=NC + 1)[:NC])

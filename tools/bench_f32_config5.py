@@ -94,9 +94,8 @@ def run_ours(args, C):
             eng.detect(x)
         torch.cuda.current_stream().wait_stream(side)
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            d, i, _ = eng.detect(x)
-            static["dets"], static["inds"] = d, i
+        with torch.cuda.graph(graph):                # the ~110 launches of the forward; the decode entry point allocates its
+            static["views"] = eng.forward(x)         # scratch per call and therefore stays outside the graph
         graph.replay()
         torch.cuda.synchronize()
     except Exception as e:                       # noqa: BLE001 -- fall back to eager launches, say so in the line
@@ -104,11 +103,24 @@ def run_ours(args, C):
         static["graph_error"] = str(e)[:200]
         torch.cuda.synchronize()
 
+    def decode(v):
+        import ctypes as C
+        from codenet_b200 import _lib
+        hm, wh, reg = v["hm"].contiguous(), v["wh"].contiguous(), v["reg"].contiguous()
+        Bn, cat, H, W = hm.shape
+        if "dets" not in static:
+            static["dets"] = torch.empty((Bn, 100, 6), dtype=torch.float32, device=x.device)
+            static["inds"] = torch.empty((Bn, 100), dtype=torch.int32, device=x.device)
+        p = lambda t: C.c_void_p(t.data_ptr())
+        _lib.check(eng.lib.cdn_ctdet_decode(p(hm), p(wh), p(reg), Bn, cat, H, W, 100, p(static["dets"]), p(static["inds"]),
+                                            C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)))
+
     def step():
         if graph is not None:
             graph.replay()
+            decode(static["views"])
         else:
-            static["dets"], static["inds"], _ = eng.detect(x)
+            decode(eng.forward(x))
 
     for _ in range(max(args.warmup, 3)):
         step()
