@@ -95,3 +95,38 @@ def check_reference_dets(g_dets, hm, wh, reg, K=100):
     more, minds = io.ctdet_decode(hm, wh, reg, K + 60)
     for b in range(g_dets.shape[0]):
         assert_dets_match_tie_aware(g_dets[b], odets[b], more[b], hm=hm[b], more_inds=minds[b])
+
+
+def assert_deform_f32_close(out, x, off, w, y_ref, stride, pad, dil, groups, dg, name=""):
+    """fp32 deformable-conv output against the fp64 reference vector, EVERY element bounded (north star: 1e-4 relative).
+
+    The fixture is the reference evaluated in fp64; the kernel sees the same tensors rounded to fp32.  Elements whose error
+    exceeds 1e-4 * max(1, |y|max) are allowed only where (i) some tap of that output pixel samples within 2e-5 of an integer
+    row / column -- there the fp32 coordinate may fall on the other side of floor(), which moves a bilinear corner by one
+    pixel with a weight below 2e-5 -- and (ii) the error is still below the effect of that move, 4e-5 * sum|w| * max|x|."""
+    from oracle import deform_ref
+    f64 = np.float64
+    x32, o32, w32 = (np.asarray(a, np.float32).astype(f64) for a in (x, off, w))
+    y = deform_ref.deform_conv(x32, o32, w32, stride, pad, dil, groups, dg)          # the fp64 oracle on the fp32-rounded inputs
+    scale = max(1.0, float(np.abs(y_ref).max()))
+    np.testing.assert_allclose(y, y_ref, rtol=0, atol=2e-5 * scale, err_msg=name + ": oracle vs fixture")
+    err = np.abs(np.asarray(out, f64) - y)
+    bad = err > 1e-4 * scale
+    if not bad.any():
+        return 0
+    B, _, Ho, Wo = y.shape
+    kH, kW = w.shape[2], w.shape[3]
+    hs = (np.arange(Ho) * stride - pad).reshape(1, Ho, 1)
+    ws = (np.arange(Wo) * stride - pad).reshape(1, 1, Wo)
+    near = np.zeros((B, Ho, Wo), bool)
+    for g in range(dg):
+        for i in range(kH):
+            for j in range(kW):
+                t = (g * kH * kW + i * kW + j) * 2
+                for pos in (hs + i * dil + o32[:, t], ws + j * dil + o32[:, t + 1]):
+                    near |= np.abs(pos - np.rint(pos)) < 2e-5
+    assert not (bad & ~near[:, None]).any(), "%s: %d elements beyond 1e-4 away from any floor() boundary (max %.3g)" % (
+        name, int((bad & ~near[:, None]).sum()), float(err[bad & ~near[:, None]].max()))
+    cap = 4e-5 * float(np.abs(w32).reshape(w32.shape[0], -1).sum(1).max()) * float(np.abs(x32).max()) + 1e-4 * scale
+    assert err[bad].max() <= cap, "%s: floor()-boundary outlier %.3g exceeds its bound %.3g" % (name, float(err[bad].max()), cap)
+    return int(bad.sum())

@@ -21,7 +21,15 @@ LAUNCHES_PER_STEP = 66          # kernels of one forward + decode (memset exclud
 
 def fam(name):
     n = name.split("(")[0].replace("void ", "").split("<")[0]
-    return "dw3x3_kernels" if n in ("dw3x3_v2_kernel", "dw3x3_tma_kernel") else n      # bench.py's family names
+    if n in ("dw3x3_v2_kernel", "dw3x3_tma_kernel"):
+        return "dw3x3_kernels"                                        # bench.py's family names
+    if n in ("deform_tile_int_kernel", "deform_int_v3_kernel"):
+        return "deform_int_kernel"
+    if n in ("deform_tile_bil_kernel", "deform_dw_v2_kernel"):
+        return "deform_bilinear_kernel"
+    if n in ("ctdet_peaks_rows_kernel", "ctdet_peaks_kernel", "ctdet_decode_kernel"):
+        return "ctdet_decode"
+    return n
 
 
 def launch_list():
@@ -106,5 +114,5 @@ def full(kernel):
 
 if __name__ == "__main__":
     launch_list()
-    for k in ("pw_gemm_tc", "deform_int_v3", "dw3x3_tma", "heads_fused"):
+    for k in ("pw_gemm_tc", "deform_tile_int", "deform_tile_bil", "dw3x3_tma", "heads_fused"):
         full(k)
