@@ -163,6 +163,26 @@ def decode_kat():
             assert len(np.unique(top)) == K + 8 and top[-1] > 0
         out.update({name + "_hm": hm, name + "_wh": wh, name + "_reg": reg, name + "_dets": d.numpy(),
                     name + "_dets_noreg": d2.numpy(), name + "_K": np.array(K)})
+    # edge cases of the reference's peak test on fp32 PROBABILITIES (decode.py:10-16, :110-126):
+    #  "sparse": fewer than K positive peaks -- the rest of the K rows are score-0 entries picked arbitrarily by topk;
+    #  "saturated": logits so large that fp32 sigmoid maps distinct neighbours to the same probability (1.0): both stay
+    #   peaks under `hmax == heat`; rows inside a tie group come out in topk's unspecified order.
+    B, cat, Hh, W, K = 1, 3, 16, 16, 40
+    hm = np.zeros((B, cat, Hh, W), np.float32)
+    pos = rng.choice(cat * Hh * W // 9, 25, replace=False)
+    for n, pidx in enumerate(pos):                                     # isolated peaks on a 3-pixel lattice
+        c_, r_ = divmod(int(pidx), (Hh // 3) * (W // 3))
+        hm[0, c_ % cat, 1 + 3 * (r_ // (W // 3)), 1 + 3 * (r_ % (W // 3))] = 0.05 + 0.03 * n
+    wh = rng.uniform(1, 20, (B, 2, Hh, W)).astype(np.float32); reg = rng.uniform(0, 1, (B, 2, Hh, W)).astype(np.float32)
+    out.update(sparse_hm=hm, sparse_wh=wh, sparse_reg=reg, sparse_K=np.array(K),
+               sparse_dets=R.decode.ctdet_decode(T(hm), T(wh), reg=T(reg), K=K).numpy())
+    logit = rng.standard_normal((B, cat, Hh, W)).astype(np.float32) * 2 - 3
+    logit[0, 0, 4, 4:7] = [17.5, 18.0, 19.0]                           # three saturated neighbours: sigmoid == 1.0f for all
+    logit[0, 1, 9, 9] = 30.0
+    hm = torch.sigmoid(T(logit)).numpy()
+    assert (hm[0, 0, 4, 4:7] == 1.0).all()
+    out.update(saturated_hm=hm, saturated_wh=wh, saturated_reg=reg, saturated_K=np.array(K),
+               saturated_dets=R.decode.ctdet_decode(T(hm), T(wh), reg=T(reg), K=K).numpy())
     np.savez_compressed(os.path.join(OUT, "decode_kat.npz"), **out)
     print("decode_kat ok")
 

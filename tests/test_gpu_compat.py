@@ -239,3 +239,33 @@ def test_group_by_class_on_device():
         order = np.argsort(key, kind="stable")
         np.testing.assert_array_equal(o[b], dets[b][order])
         np.testing.assert_array_equal(c[b], np.bincount(key.astype(int), minlength=NC + 1)[:NC])
+
+
+def test_ctdet_decode_edge_cases_from_the_reference(golden):
+    """The reference's peak test runs on fp32 PROBABILITIES (decode.py:10-16 after hm.sigmoid_()): vectors generated from it
+    with (i) fewer than K positive peaks -- the reference fills the K rows with score-0 entries in topk's arbitrary order, only
+    the positive rows are defined -- and (ii) saturated neighbours whose distinct logits all map to probability 1.0f, which
+    `hmax == heat` keeps as separate peaks (rows inside the tie group in unspecified order)."""
+    import torch
+    from codenet_b200 import compat
+    g = golden("decode_kat.npz")
+    hm, wh, reg = (torch.from_numpy(g["sparse" + s]).cuda() for s in ("_hm", "_wh", "_reg"))
+    d = compat.ctdet_decode(hm, wh, reg=reg, K=int(g["sparse_K"])).cpu().numpy()[0]
+    ref = g["sparse_dets"][0]
+    n = int((ref[:, 4] > 0).sum())
+    assert n == 25 and (d[:n, 4] > 0).all() and (d[n:, 4] == 0).all() and (ref[n:, 4] == 0).all()
+    np.testing.assert_array_equal(d[:n, 4:], ref[:n, 4:])
+    np.testing.assert_allclose(d[:n, :4], ref[:n, :4], rtol=1e-6, atol=1e-5)
+    hm, wh, reg = (torch.from_numpy(g["saturated" + s]).cuda() for s in ("_hm", "_wh", "_reg"))
+    d = compat.ctdet_decode(hm, wh, reg=reg, K=int(g["saturated_K"])).cpu().numpy()[0]
+    ref = g["saturated_dets"][0]
+    np.testing.assert_array_equal(d[:, 4], ref[:, 4])                     # the score list, ties included
+    assert (ref[:4, 4] == 1.0).all()                                      # three saturated neighbours + one isolated peak
+    key = lambda r: tuple(np.round(r.astype(np.float64), 3))
+    i = 0
+    while i < len(ref):                                                   # rows as multisets inside every group of equal score
+        j = i
+        while j + 1 < len(ref) and ref[j + 1, 4] == ref[i, 4]:
+            j += 1
+        assert sorted(map(key, d[i:j + 1])) == sorted(map(key, ref[i:j + 1])), (i, j)
+        i = j + 1
