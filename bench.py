@@ -108,8 +108,13 @@ def op_bytes(plan, op, batch, stored=False):
         # heads tail as one kernel: stored int8 input read once, fp32 planes written once; nothing in between touches HBM
         ti = T[a["in_t"]]
         return batch * (ti.C * ti.H * ti.W + 4 * a["fused_n_f32"] * 4 * ti.H * ti.W) + 9 * ti.C
-    if op.kind == "pw" and a.get("fused_with_prev"):
+    if a.get("fused_with_prev"):
         return 0
+    if a.get("unit_head"):
+        # a whole stride-1 unit as one kernel: the stage tensor (both halves) read once, the unit's output written once, the
+        # weights of its three convs; the two int8 tensors between the convs never touch HBM
+        ti = T[a["in_t"]]
+        return batch * ti.H * ti.W * 2 * ti.C + a["unit_weights"]
     if op.kind == "deform" and not stored:
         to = T[a["out_t"]]
         return batch * 2 * to.C * to.H * to.W + 9 * to.C
@@ -127,6 +132,8 @@ def op_bytes(plan, op, batch, stored=False):
 
 
 def family(op):
+    if op.a.get("unit_head") or op.a.get("unit_member"):
+        return "unit_fused_kernel"
     if op.a.get("fused_into_next") or op.a.get("fused_with_prev"):
         return "heads_fused_kernel"
     if op.kind == "deform":
@@ -192,6 +199,15 @@ def run_ours(args):
         ops = eng.plan.ops
         i = next(k for k, o in enumerate(ops) if o.name == "heads.dw2")
         ops[i].a["fused_into_next"], ops[i].a["fused_n_f32"], ops[i + 1].a["fused_with_prev"] = True, ops[i + 1].a["n_f32"], True
+    if args.no_fuse_units:
+        eng.set_option("fuse_units", 0)
+    ops = eng.plan.ops
+    for i in range(len(ops)):                    # stride-1 units that run as one kernel: account the three ops as one launch
+        if eng.op_fusion(i) == 2:
+            ops[i].a["unit_head"] = True
+            ops[i].a["unit_weights"] = int(ops[i].a["wq"].size + ops[i + 1].a["wq"].size + ops[i + 2].a["wq"].size)
+            for o in ops[i + 1:i + 3]:
+                o.a["fused_with_prev"], o.a["unit_member"] = True, True
     eng.set_option("host_chunk", args.host_chunk)
     # synthetic images: 16 distinct ones per rank, tiled to the batch (805 MB fp32 at B=256: larger than L2)
     base = make_images(min(16, B), R, seed=100 + rank)
@@ -420,7 +436,7 @@ def run_ours(args):
                                   "ranks at once, no compute" % (fab_n, world)}},
         "gpu_launches": int(eng.num_launches * args.steps),
         "requant": dict(zip(("int_layers", "guarded_fp32_layers"), eng.requant_stats)),
-        "heads_fused": bool(eng.heads_fused),
+        "heads_fused": bool(eng.heads_fused), "units_fused": int(eng.units_fused),
         "clocks": clocks, "roofline": roofline, "deform": deform, "reference_semantics": bil, "cpu_baseline": cpu,
     }
     print(json.dumps(line))
@@ -510,6 +526,7 @@ def main():
     ap.add_argument("--host-chunk", type=int, default=64)
     ap.add_argument("--parity-images", type=int, default=16, help="distinct images compared with the oracle after the timed loop")
     ap.add_argument("--no-fuse-heads", action="store_true", help="run heads.dw2 and heads.out as separate kernels (A/B)")
+    ap.add_argument("--no-fuse-units", action="store_true", help="run every ShuffleNetV2 unit as three launches (A/B)")
     ap.add_argument("--no-bilinear", action="store_true", help="skip the reference-semantics (bilinear offsets) leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs only)")
     ap.add_argument("--no-port", action="store_true", help="cpu_baseline: skip the numpy-port number beside the reference's")

@@ -107,6 +107,8 @@ EXPORTS = {
     "cdn_engine_read_heads": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "cdn_engine_num_launches": (C.c_int, [C.c_void_p]),
     "cdn_engine_heads_fused": (C.c_int, [C.c_void_p]),
+    "cdn_engine_units_fused": (C.c_int, [C.c_void_p]),
+    "cdn_engine_op_fusion": (C.c_int, [C.c_void_p, C.c_int]),
     "cdn_engine_requant_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "cdn_engine_profile": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
 }

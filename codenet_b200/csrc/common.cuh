@@ -169,6 +169,13 @@ __device__ __forceinline__ int rq_int_hi(int v, int Mi, int sh, long long Bi) {
       : "=r"(hi) : "r"(v), "r"(Mi), "l"(Bi));
   return hi >> sh;
 }
+// shift 0 (every channel of a layer whose DwDevice / PwDevice has sh0 set): the high word IS the result, one IMAD.HI
+__device__ __forceinline__ int rq_int_hi0(int v, int Mi, long long Bi) {
+  int hi;
+  asm("{\n\t.reg .b64 t;\n\t.reg .b32 lo;\n\tmul.wide.s32 t, %1, %2;\n\tadd.s64 t, t, %3;\n\tmov.b64 {lo, %0}, t;\n\t}"
+      : "=r"(hi) : "r"(v), "r"(Mi), "l"(Bi));
+  return hi;
+}
 __device__ __forceinline__ int rq_int(int v, const int4& r) {
   return rq_int(v, r.x, r.y, (long long)(((unsigned long long)(uint32_t)r.w << 32) | (uint32_t)r.z));
 }

@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(NT, MINB) deform_tile_int_kernel(const __grid_
       acc[2] = dp4a_ss(x[v][8], wC[v][2], dp4a_ss(b2, wB[v][2], dp4a_ss(a2, wA[v][2], 0)));
       acc[3] = dp4a_ss(x[v][8], wC[v][3], dp4a_ss(b3, wB[v][3], dp4a_ss(a3, wA[v][3], 0)));
 #pragma unroll
-      for (int c = 0; c < 4; ++c) { q[c] = rq_int_hi(acc[c], Mi[v][c], sh[v][c], Bi[v][c]); if (RQ == 2) q[c] = max(q[c], p.lo_i); }
+      for (int c = 0; c < 4; ++c) { q[c] = RQ == 3 ? rq_int_hi0(acc[c], Mi[v][c], Bi[v][c]) : rq_int_hi(acc[c], Mi[v][c], sh[v][c], Bi[v][c]); if (RQ == 2) q[c] = max(q[c], p.lo_i); }   // RQ 3: shift 0 in every channel
       o[v] = pack_sat4(q[0], q[1], q[2], q[3]);
     }
     const uint32_t pl = meta & 0x7fffffffu;
@@ -557,20 +557,21 @@ int deform_tile_launch(const DwDevice& d, const cdn_deform_scale* sc, const int8
                                  (uint32_t)(p.Ws + (sc->mode == 1 ? 1 : 0)), (uint32_t)P.tile_rows)) return r;
   const bool lo_on = d.rq.lo > -128;
   typedef void (*Kern)(CUtensorMap, DefTParams);
-  static const Kern kerns[3][2] = {
-      {deform_tile_int_kernel<2, 1, 256, 2, true>, deform_tile_int_kernel<2, 2, 256, 2, true>},
-      {deform_tile_int_kernel<1, 1, 512, 2, false>, deform_tile_int_kernel<1, 2, 512, 2, false>},
-      {deform_tile_int_kernel<1, 1, 256, 3, true>, deform_tile_int_kernel<1, 2, 256, 3, true>}};
-  static bool attr_set[7][64] = {};
+  static const Kern kerns[3][3] = {
+      {deform_tile_int_kernel<2, 1, 256, 2, true>, deform_tile_int_kernel<2, 2, 256, 2, true>, deform_tile_int_kernel<2, 3, 256, 2, true>},
+      {deform_tile_int_kernel<1, 1, 512, 2, false>, deform_tile_int_kernel<1, 2, 512, 2, false>, deform_tile_int_kernel<1, 3, 512, 2, false>},
+      {deform_tile_int_kernel<1, 1, 256, 3, true>, deform_tile_int_kernel<1, 2, 256, 3, true>, deform_tile_int_kernel<1, 3, 256, 3, true>}};
+  const int rqv = lo_on ? 1 : ((d.sh0 && !(g_cdn_debug_flags & (1u << 22))) ? 2 : 0);       // requantisation variant: plain, lower clamp, shift 0
+  static bool attr_set[10][64] = {};
   if (sc->mode == 1) {
     CDN_CHECK(dwp != nullptr, CDN_ERR_STATE, "deform (tile, bilinear): missing parameter block");
-    if (cdn_first_on_device(attr_set[6])) {
+    if (cdn_first_on_device(attr_set[9])) {
       CDN_CUDA(cudaFuncSetAttribute(deform_tile_bil_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
       CDN_CUDA(cudaFuncSetAttribute(deform_tile_bil_kernel<256>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     }
-  } else if (cdn_first_on_device(attr_set[P.variant * 2 + (lo_on ? 1 : 0)])) {
-    CDN_CUDA(cudaFuncSetAttribute(kerns[P.variant][lo_on ? 1 : 0], cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-    CDN_CUDA(cudaFuncSetAttribute(kerns[P.variant][lo_on ? 1 : 0], cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  } else if (cdn_first_on_device(attr_set[P.variant * 3 + rqv])) {
+    CDN_CUDA(cudaFuncSetAttribute(kerns[P.variant][rqv], cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    CDN_CUDA(cudaFuncSetAttribute(kerns[P.variant][rqv], cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   }
   cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)P.ns, (unsigned)P.nbands, (unsigned)batch); cfg.blockDim = dim3((unsigned)P.NT); cfg.stream = st;
@@ -590,7 +591,7 @@ int deform_tile_launch(const DwDevice& d, const cdn_deform_scale* sc, const int8
     f.Ms = sc->Ms; f.bs = sc->bs; f.ss = sc->ss; f.zs = sc->zs; f.u_lo = (double)(-sc->bound + 1); f.u_hi = (double)sc->bound;
     f.acc_s_bias = d.acc_s_bias;
     CDN_CUDA(cudaLaunchKernelEx(&cfg, deform_tile_bil_kernel<256>, tmI, p, f, *dwp));
-  } else CDN_CUDA(cudaLaunchKernelEx(&cfg, kerns[P.variant][lo_on ? 1 : 0], tmI, p));
+  } else CDN_CUDA(cudaLaunchKernelEx(&cfg, kerns[P.variant][rqv], tmI, p));
   CDN_LAUNCH_CHECK("deform_tile kernel");
   return 0;
 }

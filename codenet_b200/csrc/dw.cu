@@ -762,7 +762,11 @@ int dw_device_build(DwDevice& d, const int8_t* wq, const int8_t* ws, int C, int 
         ok = rq_int_solve(rq->M[c], rq->B[c], std::max(-128, std::min(127, rq->lo)), -A * asum, A * asum, &ki[c]) &&
              rq_int_rebase(&ki[c], ab[c], 128 * asum);
       }
-      if (ok) { if (dev_upload((RqInt**)&d.ki, ki.data(), ki.size())) return CDN_ERR_CUDA; d.use_int = 1; }
+      if (ok) {
+        if (dev_upload((RqInt**)&d.ki, ki.data(), ki.size())) return CDN_ERR_CUDA;
+        d.use_int = 1; d.sh0 = 1;
+        for (const RqInt& k : ki) if (k.sh != 0) d.sh0 = 0;
+      }
     }
     // fp32 bilinear fast path (deform MODE 1), u = 2^-24, A = 255 >= |q + zx|, S = sum_ij |w_ij| of the channel:
     //   column blend u0 = fl(c1*a1 + fl(c0*a0)), c0 + c1 = 1, weights off by <= u each:        |err| <= 4 A u

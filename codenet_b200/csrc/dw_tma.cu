@@ -26,7 +26,8 @@ struct DwTParams {
   uint32_t* out; int out_pitch_w;
 };
 
-template <int S, bool LO>
+// NS: every channel requantises with shift 0 (DwDevice::sh0) -- no SHF after the IMAD.HI
+template <int S, bool LO, bool NS>
 __global__ void __launch_bounds__(DT_THREADS, DT_CTAS) dw3x3_tma_kernel(const __grid_constant__ CUtensorMap tmI, const DwTParams p) {
   pdl_launch_dependents();
   extern __shared__ uint8_t dt_smem_raw[];
@@ -108,7 +109,8 @@ __global__ void __launch_bounds__(DT_THREADS, DT_CTAS) dw3x3_tma_kernel(const __
         }
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          q0[c] = rq_int_hi(a0[c], km[c].x, km[c].y, kb[c]); q1[c] = rq_int_hi(a1[c], km[c].x, km[c].y, kb[c]);
+          q0[c] = NS ? rq_int_hi0(a0[c], km[c].x, kb[c]) : rq_int_hi(a0[c], km[c].x, km[c].y, kb[c]);
+          q1[c] = NS ? rq_int_hi0(a1[c], km[c].x, kb[c]) : rq_int_hi(a1[c], km[c].x, km[c].y, kb[c]);
           if (LO) { q0[c] = max(q0[c], p.lo_i); q1[c] = max(q1[c], p.lo_i); }
         }
         o[0] = pack_sat4(q0[0], q0[1], q0[2], q0[3]);
@@ -126,7 +128,7 @@ __global__ void __launch_bounds__(DT_THREADS, DT_CTAS) dw3x3_tma_kernel(const __
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const int a = dp4a_ss(Tp[c], Wt[c][2], dp4a_ss(Tc[c], Wt[c][1], dp4a_ss(Tm[c], Wt[c][0], 0)));
-          q0[c] = rq_int_hi(a, km[c].x, km[c].y, kb[c]);
+          q0[c] = NS ? rq_int_hi0(a, km[c].x, kb[c]) : rq_int_hi(a, km[c].x, km[c].y, kb[c]);
           if (LO) q0[c] = max(q0[c], p.lo_i);
         }
         o[0] = pack_sat4(q0[0], q0[1], q0[2], q0[3]);
@@ -174,10 +176,11 @@ int dw_tma_launch(const DwDevice& d, const int8_t* in, int in_pitch, int8_t* out
   const size_t smem = 128 + 2 * (size_t)p.buf_stride + 32;
   CDN_CHECK(smem <= 64 * 1024, CDN_ERR_INVALID, "dw (TMA): %zu bytes of shared memory", smem);
   const bool lo_on = p.lo_i > -128;
-  void (*kern)(CUtensorMap, DwTParams) = stride == 2 ? (lo_on ? dw3x3_tma_kernel<2, true> : dw3x3_tma_kernel<2, false>)
-                                                     : (lo_on ? dw3x3_tma_kernel<1, true> : dw3x3_tma_kernel<1, false>);
-  static bool attr_set[4][64] = {};
-  const int ai = (stride == 2 ? 2 : 0) + (lo_on ? 1 : 0);
+  const bool ns = d.sh0 && !lo_on && !(g_cdn_debug_flags & (1u << 22));       // bit 22: keep the shift (A/B)
+  void (*kern)(CUtensorMap, DwTParams) = stride == 2 ? (lo_on ? dw3x3_tma_kernel<2, true, false> : (ns ? dw3x3_tma_kernel<2, false, true> : dw3x3_tma_kernel<2, false, false>))
+                                                     : (lo_on ? dw3x3_tma_kernel<1, true, false> : (ns ? dw3x3_tma_kernel<1, false, true> : dw3x3_tma_kernel<1, false, false>));
+  static bool attr_set[6][64] = {};
+  const int ai = (stride == 2 ? 3 : 0) + (lo_on ? 1 : (ns ? 2 : 0));
   if (cdn_first_on_device(attr_set[ai])) {
     CDN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     CDN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));

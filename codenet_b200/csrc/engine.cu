@@ -66,15 +66,9 @@ bool rq_int_solve(double M, double B, int lo, long long vmin, long long vmax, Rq
   }
   if (!(M > 0.0)) return false;
   int e = 0; (void)frexp(M, &e);               // M in [2^(e-1), 2^e)  ->  M * 2^(31-e) in [2^30, 2^31)
-  int S = 31 - e;
-  if (S < 32) S = 32;
-  if (S > 63) return false;
-  double mi_d = ldexp(M, S);
-  if (mi_d >= 2147483648.0 - 256.0) {          // keep room for the +-d search below
-    if (S == 32) return false;                 // multiplier >= 0.5: the output grid is as fine as the accumulator's
-    --S; mi_d *= 0.5;
-  }
-  const long long Mi0 = llrint(mi_d);
+  int S_nat = 31 - e;
+  if (S_nat < 32) S_nat = 32;
+  if (S_nat > 63) return false;
   // a[k]: smallest v with result >= k (vmax + 1 when none, vmin when all), k = lo+1 .. 127
   const int nk = 127 - lo;
   std::vector<long long> a((size_t)std::max(nk, 0));
@@ -99,28 +93,40 @@ bool rq_int_solve(double M, double B, int lo, long long vmin, long long vmax, Rq
     a[i] = hi_v;
   }
   const __int128 one = 1;
-  const __int128 nominal = (__int128)ldexpl((long double)B + 0.5L, S);
   const __int128 vm = std::max(vmin < 0 ? -(__int128)vmin : (__int128)vmin, vmax < 0 ? -(__int128)vmax : (__int128)vmax);
-  for (int t = 0; t <= 256; ++t) {
-    const long long d = (t & 1) ? (t + 1) / 2 : -(long long)(t / 2);       // 0, 1, -1, 2, -2, ...
-    const long long Mi = Mi0 + d;
-    if (Mi <= 0 || Mi >= (1ll << 31)) continue;
-    __int128 L = 0, U = 0; bool hasL = false, hasU = false;
-    for (int i = 0; i < nk; ++i) {
-      const __int128 K2 = (__int128)(lo + 1 + i) * (one << S);
-      if (a[i] <= vmax) { const __int128 c = K2 - (__int128)a[i] * Mi; if (!hasL || c > L) L = c; hasL = true; }
-      if (a[i] - 1 >= vmin) { const __int128 c = K2 - (__int128)(a[i] - 1) * Mi - 1; if (!hasU || c < U) U = c; hasU = true; }
+  // Scale candidates: S = 32 first (shift 0: the device then needs no SHF after the IMAD.HI -- kernels whose layers solve with
+  // shift 0 in every channel run a variant without it), then the scale that uses all 31 multiplier bits.
+  for (int pass = 0; pass < 2; ++pass) {
+    int S = pass == 0 ? 32 : S_nat;
+    if (pass == 1 && S_nat == 32) break;
+    double mi_d = ldexp(M, S);
+    if (mi_d >= 2147483648.0 - 256.0) {        // keep room for the +-d search below
+      if (S == 32) { if (pass == 0) continue; return false; }   // multiplier >= 0.5: the output grid is as fine as the accumulator's
+      --S; mi_d *= 0.5;
     }
-    if (hasL && hasU && L > U) continue;
-    __int128 Bi;
-    if (hasL && hasU) Bi = L + (U - L) / 2;
-    else if (hasL) Bi = std::max(L, nominal);
-    else if (hasU) Bi = std::min(U, nominal);
-    else Bi = nominal;
-    const __int128 absB = Bi < 0 ? -Bi : Bi;
-    if (absB + vm * Mi >= (one << 62)) return false;
-    out->Mi = (int32_t)Mi; out->sh = S - 32; out->Bi = (long long)Bi;
-    return true;
+    const long long Mi0 = llrint(mi_d);
+    const __int128 nominal = (__int128)ldexpl((long double)B + 0.5L, S);
+    for (int t = 0; t <= 256; ++t) {
+      const long long d = (t & 1) ? (t + 1) / 2 : -(long long)(t / 2);       // 0, 1, -1, 2, -2, ...
+      const long long Mi = Mi0 + d;
+      if (Mi <= 0 || Mi >= (1ll << 31)) continue;
+      __int128 L = 0, U = 0; bool hasL = false, hasU = false;
+      for (int i = 0; i < nk; ++i) {
+        const __int128 K2 = (__int128)(lo + 1 + i) * (one << S);
+        if (a[i] <= vmax) { const __int128 c = K2 - (__int128)a[i] * Mi; if (!hasL || c > L) L = c; hasL = true; }
+        if (a[i] - 1 >= vmin) { const __int128 c = K2 - (__int128)(a[i] - 1) * Mi - 1; if (!hasU || c < U) U = c; hasU = true; }
+      }
+      if (hasL && hasU && L > U) continue;
+      __int128 Bi;
+      if (hasL && hasU) Bi = L + (U - L) / 2;
+      else if (hasL) Bi = std::max(L, nominal);
+      else if (hasU) Bi = std::min(U, nominal);
+      else Bi = nominal;
+      const __int128 absB = Bi < 0 ? -Bi : Bi;
+      if (absB + vm * Mi >= (one << 62)) break;
+      out->Mi = (int32_t)Mi; out->sh = S - 32; out->Bi = (long long)Bi;
+      return true;
+    }
   }
   return false;
 }
@@ -299,6 +305,7 @@ struct cdn_engine {
   } slots[2];
   int host_chunk = 64, use_graph = 1, hm_logits = 0;
   int fuse_heads = 1;                        // heads.dw2 + heads.out as one kernel when the pair is eligible (heads_fused.cu)
+  int fuse_units = 1;                        // stride-1 ShuffleNetV2 units (pw1 -> dw2 -> pw3) as one kernel (unit_fused.cu); 2: also write the tensors in between
   // graph cache
   struct GraphKey { const void* a[6]; int batch; bool operator==(const GraphKey& o) const { return memcmp(this, &o, sizeof(*this)) == 0; } };
   std::vector<std::pair<GraphKey, cudaGraphExec_t>> graphs;
@@ -356,6 +363,7 @@ extern "C" int cdn_engine_set_option(cdn_engine* e, const char* name, int value)
   else if (!strcmp(name, "use_graph")) e->use_graph = value;
   else if (!strcmp(name, "hm_logits")) e->hm_logits = value ? 1 : 0;
   else if (!strcmp(name, "fuse_heads")) e->fuse_heads = value ? 1 : 0;
+  else if (!strcmp(name, "fuse_units")) e->fuse_units = std::max(0, std::min(2, value));
   else return cdn_fail(CDN_ERR_INVALID, "unknown engine option '%s'", name);
   return 0;
 }
@@ -498,6 +506,19 @@ static bool engine_fuses_heads(const cdn_engine* e, size_t oi) {
   return heads_fused_ok(a->dw, b->pw, ti.pitch, tm.pitch, ti.H, ti.W) && 2 * ti.H == e->hH && 2 * ti.W == e->hW;
 }
 
+// ops oi, oi+1, oi+2 = the branch of a stride-1 ShuffleNetV2 unit (1x1 conv on the second half of the stage tensor, depthwise
+// 3x3, 1x1 conv interleaving its columns with the first half), eligible for unit_fused.cu
+static bool engine_fuses_unit(const cdn_engine* e, size_t oi) {
+  if (!e->fuse_units || (g_cdn_debug_flags & (1u << 19)) || oi + 2 >= e->ops.size()) return false;   // bit 19: never fuse (A/B)
+  const EngOp *a = e->ops[oi], *b = e->ops[oi + 1], *c = e->ops[oi + 2];
+  if (a->kind != 3 || b->kind != 1 || c->kind != 3) return false;
+  if (a->out_t < 0 || a->pass_t >= 0 || b->in_t != a->out_t || b->in_shift != 0 || b->stride != 1 || c->in_t != b->out_t ||
+      c->pass_t != a->in_t || c->out_t < 0) return false;
+  const EngTensor &tx = e->tensors[a->in_t], &t1 = e->tensors[a->out_t], &t2 = e->tensors[b->out_t], &to = e->tensors[c->out_t];
+  if (t1.pitch != t2.pitch) return false;
+  return unit_fused_ok(a->pw, b->dw, c->pw, tx.pitch, t1.pitch, to.pitch, tx.H, tx.W);
+}
+
 // d_img: fp32 NCHW image, or (is_u8) uint8 NHWC image normalised in the stem through e->lut
 static int engine_enqueue(cdn_engine* e, const void* d_img, int is_u8, int batch, float* d_hm, float* d_wh, float* d_reg,
                           float* d_dets, int32_t* d_inds, cudaStream_t st, std::vector<cudaEvent_t>* marks = nullptr) {
@@ -516,6 +537,18 @@ static int engine_enqueue(cdn_engine* e, const void* d_img, int is_u8, int batch
       launches++;
       mark(); mark();                        // the second op of the pair takes no time of its own
       ++oi;
+      continue;
+    }
+    if (engine_fuses_unit(e, oi)) {
+      // a whole stride-1 unit as one kernel; the two int8 tensors inside it are written only on request (fuse_units = 2)
+      const EngOp *dwo = e->ops[oi + 1], *p3 = e->ops[oi + 2];
+      const EngTensor &tx = e->tensors[op->in_t], &t1 = e->tensors[op->out_t], &t2 = e->tensors[dwo->out_t], &to = e->tensors[p3->out_t];
+      r = unit_fused_launch(op->pw, dwo->dw, p3->pw, tx.ptr, to.ptr, t1.pitch, batch, tx.H, tx.W, dwo->zx,
+                            e->fuse_units == 2 ? t1.ptr : nullptr, e->fuse_units == 2 ? t2.ptr : nullptr, st);
+      if (r) return r;
+      launches++;
+      mark(); mark(); mark();                // the other two ops of the unit take no time of their own
+      oi += 2;
       continue;
     }
     switch (op->kind) {
@@ -601,7 +634,7 @@ static int engine_run_any(cdn_engine* e, const void* d_img, int is_u8, int batch
   cudaStream_t st = (cudaStream_t)stream;
   if (!e->use_graph || (g_cdn_debug_flags & 2u)) return engine_enqueue(e, d_img, is_u8, batch, d_hm, d_wh, d_reg, d_dets, d_inds, st);
   cdn_engine::GraphKey key; memset(&key, 0, sizeof(key));
-  key.a[0] = d_img; key.a[1] = d_hm; key.a[2] = d_wh; key.a[3] = d_reg; key.a[4] = d_dets; key.a[5] = d_inds; key.batch = batch | (e->hm_logits << 30) | (is_u8 << 29) | (e->fuse_heads << 28);
+  key.a[0] = d_img; key.a[1] = d_hm; key.a[2] = d_wh; key.a[3] = d_reg; key.a[4] = d_dets; key.a[5] = d_inds; key.batch = batch | (e->hm_logits << 30) | (is_u8 << 29) | (e->fuse_heads << 28) | (e->fuse_units << 26);
   for (auto& g : e->graphs) if (g.first == key) { CDN_CUDA(cudaGraphLaunch(g.second, st)); return 0; }
   // capture once per (pointers, batch)
   cudaStream_t cap = e->s_compute;
@@ -771,6 +804,23 @@ extern "C" int cdn_engine_num_launches(cdn_engine* e) { return e ? e->launches :
 extern "C" int cdn_engine_heads_fused(cdn_engine* e) {
   if (!e || !e->finalized) return 0;
   for (size_t oi = 0; oi < e->ops.size(); ++oi) if (engine_fuses_heads(e, oi)) return 1;
+  return 0;
+}
+extern "C" int cdn_engine_units_fused(cdn_engine* e) {       // how many stride-1 units run as one kernel
+  if (!e || !e->finalized) return 0;
+  int n = 0;
+  for (size_t oi = 0; oi < e->ops.size(); ++oi) if (engine_fuses_unit(e, oi)) { ++n; oi += 2; }
+  return n;
+}
+// how plan op i runs: 0 = a launch of its own, 1 = first op of the fused heads tail, 2 = first op of a fused unit,
+// -1 = folded into the launch of an earlier op
+extern "C" int cdn_engine_op_fusion(cdn_engine* e, int i) {
+  if (!e || !e->finalized || i < 0 || i >= (int)e->ops.size()) return 0;
+  for (size_t oi = 0; oi < e->ops.size(); ++oi) {
+    const int span = engine_fuses_heads(e, oi) ? 2 : (engine_fuses_unit(e, oi) ? 3 : 1);
+    if ((size_t)i >= oi && (size_t)i < oi + span) return (size_t)i == oi ? (span == 2 ? 1 : (span == 3 ? 2 : 0)) : -1;
+    oi += span - 1;
+  }
   return 0;
 }
 extern "C" int cdn_engine_requant_stats(cdn_engine* e, int* int_layers, int* guarded_layers) {

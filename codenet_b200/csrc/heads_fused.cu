@@ -44,11 +44,12 @@ struct HfParams {
   float* out; int ppi, Wout;                 // fp32 planes [B][n_f32][ppi]
 };
 
-template <bool LO>
+// LO = 2: no lower clamp AND shift 0 in every channel (DwDevice::sh0): no SHF after the IMAD.HI
+template <int LO>
 __device__ __forceinline__ uint32_t hf_rq_word(const int (&acc)[4], const int2 (&km)[4], const long long (&kb)[4], int lo) {
   int q[4];
 #pragma unroll
-  for (int c = 0; c < 4; ++c) { q[c] = HF_RQ(acc[c], km[c].x, km[c].y, kb[c]); if (LO) q[c] = max(q[c], lo); }
+  for (int c = 0; c < 4; ++c) { q[c] = LO == 2 ? rq_int_hi0(acc[c], km[c].x, kb[c]) : HF_RQ(acc[c], km[c].x, km[c].y, kb[c]); if (LO == 1) q[c] = max(q[c], lo); }
   return pack_sat4(q[0], q[1], q[2], q[3]);
 }
 // one stored row of the staged tile -> the three pixels x-1, x, x+1 of this thread's channel word; TMA zero-fills pixels
@@ -60,7 +61,7 @@ __device__ __forceinline__ void hf_row(uint32_t rowp, int pitch, bool yok, const
   transpose4x4(w[0], w[1], w[2], pad, T[0], T[1], T[2], T[3]);
 }
 
-template <bool LO>
+template <int LO>
 __global__ void __launch_bounds__(HF_MAX_THREADS, HF_CTAS) heads_fused_kernel(const __grid_constant__ CUtensorMap tmI, const HfParams p) {
   pdl_launch_dependents();
   extern __shared__ uint8_t hf_smem_raw[];
@@ -248,9 +249,10 @@ int heads_fused_launch(const DwDevice& dw, const PwDevice& pw, const int8_t* in,
   const size_t smem = 1024 + 2 * 16384 + 2 * (size_t)p.NB * 128 + 2 * (size_t)p.in_bytes + (size_t)p.NB * 32 + 64;
   CDN_CHECK(smem <= HF_SMEM_MAX, CDN_ERR_INVALID, "heads_fused: %zu bytes of shared memory", smem);
   const bool lo_on = p.lo_i > -128;
-  auto kern = lo_on ? heads_fused_kernel<true> : heads_fused_kernel<false>;
-  static bool attr_set[2][64] = {};
-  if (cdn_first_on_device(attr_set[lo_on])) {
+  const int var = lo_on ? 1 : ((dw.sh0 && !(g_cdn_debug_flags & (1u << 22))) ? 2 : 0);
+  auto kern = var == 1 ? heads_fused_kernel<1> : (var == 2 ? heads_fused_kernel<2> : heads_fused_kernel<0>);
+  static bool attr_set[3][64] = {};
+  if (cdn_first_on_device(attr_set[var])) {
     CDN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, HF_SMEM_MAX));
     // the kernel lives in shared memory (input by TMA, A tile, weights) and has no use for L1: without this the driver's
     // carve-out left room for two CTAs per SM only (0.67 instead of 0.43 ms)

@@ -7,6 +7,7 @@ struct DwDevice {                            // depthwise / deformable layer con
   uint32_t *wpk1 = nullptr, *wpk2 = nullptr, *wpku = nullptr;   // v2 packings: stride 1, stride 2, upsample-folded
   float2* mb = nullptr; int32_t* abm = nullptr; float thr = 0.5f, thr_bil = 0.01f; int u_ok = 1;
   RqInt* ki = nullptr; int use_int = 0;        // exact integer requantisation constants (acc_bias folded in)
+  int sh0 = 0;                                 // use_int and every channel's shift is 0 (kernels may drop the SHF after the IMAD.HI)
   uint32_t* pad_px = nullptr;                  // integer-offset mode: one pixel of pad words (q = -zx), the target of out-of-image taps
   int32_t* s_thr = nullptr; int s_n = 0, s_lo = 0, s_mode0_ok = 0;   // integer-offset mode: thresholds of s over the scale conv's dot product
   DevRequant rq;
@@ -49,6 +50,9 @@ struct PwDevice {
   int has_pass = 0, pass_segs = 0, pass_bufs = 1, groups = 2, nbuf = 0, resident = 0, n_chunks = 0, n_segs = 0, n_f32 = 0;
   float thr = 0.5f;                          // layer-wide rounding-boundary guard (min over columns)
   int use_int = 0;                           // kc holds RqInt records (exact integer requantisation) instead of the fp32 pairs
+  int sh0 = 0;                               // use_int and every column's shift is 0
+  int il_hp = 0;                             // ... and il_hp bytes per group in the output pixel
+  int il_pg = 0;                             // > 0: the chunk table is the canonical cat + channel_shuffle interleave with il_pg channels per group
   size_t smem_bytes = 0;
   int8_t* w = nullptr;                       // [BN*n_tiles][Kp]
   cdn_pw_chunk* chunks = nullptr; void* segs = nullptr; int* tile_seg = nullptr; void* kc = nullptr;
@@ -66,6 +70,10 @@ int pw_launch(const PwDevice& d, const int8_t* in, int in_pitch, long long pixel
 bool heads_fused_ok(const DwDevice& dw, const PwDevice& pw, int in_pitch, int mid_pitch, int Hs, int Ws);
 int heads_fused_launch(const DwDevice& dw, const PwDevice& pw, const int8_t* in, int in_pitch, int batch, int Hs, int Ws,
                        int zx, float* out_f32, cudaStream_t st);
+// a whole stride-1 ShuffleNetV2 unit (1x1 conv, depthwise 3x3, 1x1 conv + cat + channel shuffle) as one kernel (unit_fused.cu)
+bool unit_fused_ok(const PwDevice& pw1, const DwDevice& dw, const PwDevice& pw3, int x_pitch, int mid_pitch, int out_pitch, int H, int W);
+int unit_fused_launch(const PwDevice& pw1, const DwDevice& dw, const PwDevice& pw3, const int8_t* x, int8_t* out, int HP,
+                      int batch, int H, int W, int zx_mid, int8_t* dump_c1, int8_t* dump_d2, cudaStream_t st);
 int make_tmap_nhwc(CUtensorMap* m, const void* base, uint64_t pitch, uint64_t W, uint64_t H, uint64_t batch, uint32_t box_w, uint32_t box_h);
 int make_tmap_2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t pitch, uint32_t box_rows);
 

@@ -130,7 +130,12 @@ __device__ __forceinline__ uint4 chunk_bytes(const cdn_pw_chunk& ck, const uint3
 }
 
 // The same 16 output bytes with the integer requantisation (RqInt per column, raw accumulators): no guard, no slow path.
-template <bool LO>
+// NS: every column of the layer requantises with shift 0 (PwDevice::sh0): the SHF after the IMAD.HI is dropped
+template <bool NS> __device__ __forceinline__ int rq_int_sel(int v, const int4& r) {
+  if (NS) { const long long x = (long long)v * r.x + (long long)(((unsigned long long)(uint32_t)r.w << 32) | (uint32_t)r.z); return (int)(x >> 32); }
+  return rq_int(v, r);
+}
+template <bool LO, bool NS = false>
 __device__ __forceinline__ uint4 chunk_bytes_int(const cdn_pw_chunk& ck, const uint32_t (&acc)[16], const int4* __restrict__ kc,
                                                  int lo, uint32_t pass_lo, uint32_t pass_hi) {
   const int4* __restrict__ k = kc + ck.col;
@@ -139,16 +144,16 @@ __device__ __forceinline__ uint4 chunk_bytes_int(const cdn_pw_chunk& ck, const u
   if (ck.pass_off < 0) {
     if (ck.count == 0) return make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { q[i] = rq_int((int)acc[i], k[i]); if (LO) q[i] = max(q[i], lo); }
+    for (int i = 0; i < 8; ++i) { q[i] = rq_int_sel<NS>((int)acc[i], k[i]); if (LO) q[i] = max(q[i], lo); }
     o.x = pack_sat4(q[0], q[1], q[2], q[3]);   o.y = pack_sat4(q[4], q[5], q[6], q[7]);
     asm volatile("" ::: "memory");             // keeps the second half's 8 LDS.128 (32 registers) from being hoisted too
 #pragma unroll
-    for (int i = 8; i < 16; ++i) { q[i] = rq_int((int)acc[i], k[i]); if (LO) q[i] = max(q[i], lo); }
+    for (int i = 8; i < 16; ++i) { q[i] = rq_int_sel<NS>((int)acc[i], k[i]); if (LO) q[i] = max(q[i], lo); }
     o.z = pack_sat4(q[8], q[9], q[10], q[11]); o.w = pack_sat4(q[12], q[13], q[14], q[15]);
     if (ck.count < 16) o = mask_tail(o, ck.count);   // pad bytes of the pixel stay zero
   } else {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { q[i] = rq_int((int)acc[i], k[i]); if (LO) q[i] = max(q[i], lo); }
+    for (int i = 0; i < 8; ++i) { q[i] = rq_int_sel<NS>((int)acc[i], k[i]); if (LO) q[i] = max(q[i], lo); }
     const uint32_t n_lo = pack_sat4(q[0], q[1], q[2], q[3]), n_hi = pack_sat4(q[4], q[5], q[6], q[7]);
     o.x = __byte_perm(pass_lo, n_lo, 0x5140); o.y = __byte_perm(pass_lo, n_lo, 0x7362);
     o.z = __byte_perm(pass_hi, n_hi, 0x5140); o.w = __byte_perm(pass_hi, n_hi, 0x7362);
@@ -165,7 +170,8 @@ __device__ __forceinline__ uint4 chunk_bytes_int(const cdn_pw_chunk& ck, const u
 //   [ring: stages x (A 16 KB [+ B block BN x 128 B rounded to 1 KB when streamed])]
 //   [pass: 2 x pass_segs x 16 KB] [staging: nbuf x 16 KB] [kc: Ntot x 16 B] [chunks] [segs] [tile_seg] [barriers]
 // RQ selects the epilogue at compile time, so the hot loop holds one variant only: 0 = guarded fp32 requantisation,
-// 1 = integer requantisation, 2 = integer with an explicit lower clamp (lo > -128), 3 = fp32 NCHW head planes.
+// 1 = integer requantisation, 2 = integer with an explicit lower clamp (lo > -128), 3 = fp32 NCHW head planes,
+// 4 = integer requantisation with shift 0 in every column (no SHF after the IMAD.HI).
 template <int RQ>
 __global__ void __launch_bounds__(PW_THREADS, 1)
 pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -426,7 +432,8 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
             tmem_ld_wait();
             uint4 o;
-            if (RQ == 1) o = chunk_bytes_int<false>(ck, acc, (const int4*)s_kc, p.lo_i, pass_lo, pass_hi);
+            if (RQ == 4) o = chunk_bytes_int<false, true>(ck, acc, (const int4*)s_kc, p.lo_i, pass_lo, pass_hi);
+            else if (RQ == 1) o = chunk_bytes_int<false>(ck, acc, (const int4*)s_kc, p.lo_i, pass_lo, pass_hi);
             else if (RQ == 2) o = chunk_bytes_int<true>(ck, acc, (const int4*)s_kc, p.lo_i, pass_lo, pass_hi);
             else if (p.dbg & 4u) o = make_uint4(acc[0], acc[1], pass_lo, pass_hi);     // experiment: no requant math
             else o = chunk_bytes(ck, acc, s_kc, p.M, p.B, p.lo_f, p.thr, pass_lo, pass_hi);
@@ -656,6 +663,33 @@ int pw_device_build(PwDevice& d, const cdn_pw_desc* desc, int pass_pitch) {
         static_assert(sizeof(RqInt) == sizeof(float4), "RqInt must be one 16-byte record");
         memcpy(kc.data(), ki.data(), (size_t)Np * sizeof(RqInt));
         d.use_int = 1;
+        d.sh0 = 1;
+        for (int n = 0; n < Np; ++n) if (ki[n].sh != 0) d.sh0 = 0;
+      }
+    }
+    // the canonical interleave of a ShuffleNetV2 unit (plan.py emit_pw): group g = 0, 1 of PG channels, chunk j of a group takes
+    // columns g*Gp + 8j, pass-through bytes g*PG + 8j and lands at byte g*Hp + 16j (unit_fused.cu has variants with PG fixed)
+    {
+      int pg = 0, hp = 0;
+      // PG = half of the interleaved columns; Hp = 16 bytes per chunk of a group
+      int n_il = 0; bool all_il = true;
+      for (int i = 0; i < desc->n_chunks; ++i) { const cdn_pw_chunk& c = desc->chunks[i]; if (c.count > 0) { n_il += c.count; if (c.pass_off < 0) all_il = false; } }
+      if (all_il && n_il > 0 && n_il % 2 == 0 && desc->n_chunks % 2 == 0) {
+        pg = n_il / 2; hp = 16 * (desc->n_chunks / 2);
+        const int Gp = (pg + 7) & ~7;
+        bool ok = true;
+        for (int g = 0; g < 2 && ok; ++g)
+          for (int j = 0; j < hp / 16 && ok; ++j) {
+            const int cnt = std::max(0, std::min(8, pg - 8 * j)), dst = g * hp + 16 * j;
+            bool found = false;
+            for (int i = 0; i < desc->n_chunks && !found; ++i) {
+              const cdn_pw_chunk& c = desc->chunks[i];
+              if (c.dst_off != dst) continue;
+              found = cnt == 0 ? c.count == 0 : (c.count == cnt && c.col == g * Gp + 8 * j && c.pass_off == g * pg + 8 * j);
+            }
+            ok = found;
+          }
+        d.il_pg = ok ? pg : 0; d.il_hp = ok ? hp : 0;
       }
     }
     // chunks grouped by N tile, then by 128-byte output segment; every tile owns whole segments
@@ -754,6 +788,7 @@ int pw_init_attrs() {
     CDN_CUDA(cudaFuncSetAttribute(pw_gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_LIMIT));
     CDN_CUDA(cudaFuncSetAttribute(pw_gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_LIMIT));
     CDN_CUDA(cudaFuncSetAttribute(pw_gemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_LIMIT));
+    CDN_CUDA(cudaFuncSetAttribute(pw_gemm_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_LIMIT));
   }
   return 0;
 }
@@ -803,6 +838,7 @@ int pw_launch(const PwDevice& d, const int8_t* in, int in_pitch, long long pixel
   if (d.n_f32 > 0) CDN_CUDA(cudaLaunchKernelEx(&cfg, pw_gemm_tc_kernel<3>, a, d.tmB, pm, o, p));
   else if (!d.use_int) CDN_CUDA(cudaLaunchKernelEx(&cfg, pw_gemm_tc_kernel<0>, a, d.tmB, pm, o, p));
   else if (d.rq.lo > -128) CDN_CUDA(cudaLaunchKernelEx(&cfg, pw_gemm_tc_kernel<2>, a, d.tmB, pm, o, p));
+  else if (d.sh0 && !(g_cdn_debug_flags & (1u << 22))) CDN_CUDA(cudaLaunchKernelEx(&cfg, pw_gemm_tc_kernel<4>, a, d.tmB, pm, o, p));   // bit 22: keep the shift (A/B)
   else CDN_CUDA(cudaLaunchKernelEx(&cfg, pw_gemm_tc_kernel<1>, a, d.tmB, pm, o, p));
   CDN_LAUNCH_CHECK("pw_gemm_tc_kernel");
   return 0;

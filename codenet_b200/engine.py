@@ -192,6 +192,16 @@ class Engine:
         return bool(self.lib.cdn_engine_heads_fused(self._h))
 
     @property
+    def units_fused(self) -> int:
+        """How many stride-1 ShuffleNetV2 units run as one kernel (option "fuse_units", default on; unit_fused.cu)."""
+        return int(self.lib.cdn_engine_units_fused(self._h))
+
+    def op_fusion(self, i: int) -> int:
+        """How plan op i runs: 0 = its own launch, 1 = head of the fused heads tail, 2 = head of a fused unit, -1 = folded into an
+        earlier op's launch."""
+        return int(self.lib.cdn_engine_op_fusion(self._h, int(i)))
+
+    @property
     def num_launches(self):
         return int(self.lib.cdn_engine_num_launches(self._h))
 

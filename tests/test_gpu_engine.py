@@ -29,6 +29,8 @@ def test_engine_matches_reference_vectors_256(golden, calib, mode):
     eng = _engine(calib, mode, 256, 4)
     x = make_images(2, 256, seed=2)
     eng.set_option("fuse_heads", 0)                     # the int8 grid between heads.dw2 and heads.out is only written unfused
+    eng.set_option("fuse_units", 2)                     # the fused unit kernel also writes the two int8 grids inside every unit
+    assert eng.units_fused == 10
     out = eng.run(torch.from_numpy(x).cuda())
     torch.cuda.synchronize()
     heads_unfused = eng.read_heads(2)
@@ -47,6 +49,7 @@ def test_engine_matches_reference_vectors_256(golden, calib, mode):
     assert checked >= (16 if mode == "round" else 8)
     # the default path: heads.dw2 + heads.out as one kernel (heads_fused.cu); everything below is checked on ITS output
     eng.set_option("fuse_heads", 1)
+    eng.set_option("fuse_units", 1)
     assert eng.heads_fused
     out = eng.run(torch.from_numpy(x).cuda())
     torch.cuda.synchronize()
@@ -195,6 +198,53 @@ def test_heads_fused_equals_separate_kernels(calib, res, batch):
     for key in ((0, 1), (1, 0), (1, 1)):
         for a, b in zip(got[0, 0], got[key]):
             np.testing.assert_array_equal(a, b)
+    eng.close()
+
+
+@pytest.mark.parametrize("res,batch", [(256, 5), (512, 3), (384, 2), (512, 40)])
+def test_units_fused_equal_separate_kernels(calib, res, batch):
+    """Every stride-1 ShuffleNetV2 unit of stages 2 and 3 as ONE kernel (unit_fused.cu: 1x1 conv on the halo'd tile -> int8
+    tile in shared memory -> depthwise stencil -> A tile of the second 1x1 conv -> interleaving epilogue) against the three
+    separate launches per unit: every tapped int8 grid -- the two tensors INSIDE each unit included, which the fused kernel
+    writes only in its dump mode --, the heads and the detections identical bit for bit, eager and as a graph, at tile counts
+    below and above the persistent grid (2 CTAs per SM) and at a size (384 -> 48x48 / 24x24 maps) where stage 3 is not
+    eligible (24 % 16 != 0) and keeps its three launches."""
+    import torch
+    st = make_quant_state(CFG, calib, "round", 256)
+    eng = Engine.from_state_dict(CFG, st, res, res, batch, offset_mode="round")
+    xt = torch.from_numpy(make_images(batch, res, seed=13, clamp=4.0)).cuda()
+    labels = [k for k in eng.plan.taps if k.startswith("layer")]
+    inner = [k for k in labels if k.endswith("act1") or k.endswith("act2")]
+    assert len(inner) >= 32
+
+    def snapshot(names):
+        out = eng.run(xt, maps=False)
+        torch.cuda.synchronize()
+        return ({k: eng.read_logical(k, batch) for k in names}, eng.read_heads(batch).copy(), out["inds"].cpu().numpy(),
+                out["dets"].cpu().numpy())
+
+    eng.set_option("fuse_units", 0)
+    assert eng.units_fused == 0
+    ref = snapshot(labels)
+    n_launch0 = eng.num_launches
+    eng.set_option("fuse_units", 2)
+    n_fused = eng.units_fused
+    assert n_fused == (3 if res == 384 else 10)
+    for graph in (0, 1):
+        eng.set_option("use_graph", graph)
+        got = snapshot(labels)
+        for k in labels:
+            assert int8_mismatch(got[0][k], ref[0][k]) == 0, (k, graph)
+        for a, b in zip(got[1:], ref[1:]):
+            np.testing.assert_array_equal(a, b)
+    assert eng.num_launches == n_launch0 - 2 * n_fused
+    eng.set_option("fuse_units", 1)                     # the default: nothing inside the units is written
+    outer = [k for k in labels if k not in inner]
+    got = snapshot(outer)
+    for k in outer:
+        assert int8_mismatch(got[0][k], ref[0][k]) == 0, k
+    for a, b in zip(got[1:], ref[1:]):
+        np.testing.assert_array_equal(a, b)
     eng.close()
 
 
