@@ -114,6 +114,9 @@ def op_bytes(plan, op, batch, stored=False):
         # a whole stride-1 unit as one kernel: the stage tensor (both halves) read once, the unit's output written once, the
         # weights of its three convs; the two int8 tensors between the convs never touch HBM
         ti = T[a["in_t"]]
+        if a["unit_head"] == 2:                  # stride-2 branch: input read once, branch 1's output read once, unit output written once
+            co = 2 * a["N_real"]
+            return batch * (ti.H * ti.W * ti.C + (ti.H // 2) * (ti.W // 2) * (co // 2 + co)) + a["unit_weights"]
         return batch * ti.H * ti.W * 2 * ti.C + a["unit_weights"]
     if op.kind == "deform" and not stored:
         to = T[a["out_t"]]
@@ -203,9 +206,10 @@ def run_ours(args):
         eng.set_option("fuse_units", 0)
     ops = eng.plan.ops
     for i in range(len(ops)):                    # stride-1 units that run as one kernel: account the three ops as one launch
-        if eng.op_fusion(i) == 2:
-            ops[i].a["unit_head"] = True
+        if eng.op_fusion(i) in (2, 3):
+            ops[i].a["unit_head"] = 2 if eng.op_fusion(i) == 3 else 1
             ops[i].a["unit_weights"] = int(ops[i].a["wq"].size + ops[i + 1].a["wq"].size + ops[i + 2].a["wq"].size)
+            ops[i].a["N_real"] = int(eng.plan.tensors[ops[i].a["out_t"]].C)
             for o in ops[i + 1:i + 3]:
                 o.a["fused_with_prev"], o.a["unit_member"] = True, True
     eng.set_option("host_chunk", args.host_chunk)

@@ -519,6 +519,20 @@ static bool engine_fuses_unit(const cdn_engine* e, size_t oi) {
   return unit_fused_ok(a->pw, b->dw, c->pw, tx.pitch, t1.pitch, to.pitch, tx.H, tx.W);
 }
 
+// ops oi, oi+1, oi+2 = branch 2 of the first stride-2 unit (1x1 conv at full resolution, depthwise 3x3 stride 2, 1x1 conv
+// interleaving its columns with branch 1's output), eligible for unit_s2_fused.cu
+static bool engine_fuses_unit_s2(const cdn_engine* e, size_t oi) {
+  if (!e->fuse_units || (g_cdn_debug_flags & (1u << 19)) || oi + 2 >= e->ops.size()) return false;
+  const EngOp *a = e->ops[oi], *b = e->ops[oi + 1], *c = e->ops[oi + 2];
+  if (a->kind != 3 || b->kind != 1 || c->kind != 3) return false;
+  if (a->out_t < 0 || a->pass_t >= 0 || b->in_t != a->out_t || b->in_shift != 0 || b->stride != 2 || c->in_t != b->out_t ||
+      c->pass_t < 0 || c->pass_t == a->in_t || c->out_t < 0) return false;
+  const EngTensor &tx = e->tensors[a->in_t], &t1 = e->tensors[a->out_t], &t2 = e->tensors[b->out_t], &tp = e->tensors[c->pass_t],
+                  &to = e->tensors[c->out_t];
+  if (t1.pitch != t2.pitch || t1.H != tx.H || t1.W != tx.W || tp.H != to.H || tp.W != to.W || 2 * to.H != tx.H || 2 * to.W != tx.W) return false;
+  return unit_s2_fused_ok(a->pw, b->dw, c->pw, tx.pitch, t1.pitch, tp.pitch, to.pitch, tx.H, tx.W);
+}
+
 // d_img: fp32 NCHW image, or (is_u8) uint8 NHWC image normalised in the stem through e->lut
 static int engine_enqueue(cdn_engine* e, const void* d_img, int is_u8, int batch, float* d_hm, float* d_wh, float* d_reg,
                           float* d_dets, int32_t* d_inds, cudaStream_t st, std::vector<cudaEvent_t>* marks = nullptr) {
@@ -548,6 +562,18 @@ static int engine_enqueue(cdn_engine* e, const void* d_img, int is_u8, int batch
       if (r) return r;
       launches++;
       mark(); mark(); mark();                // the other two ops of the unit take no time of their own
+      oi += 2;
+      continue;
+    }
+    if (engine_fuses_unit_s2(e, oi)) {
+      const EngOp *dwo = e->ops[oi + 1], *p3 = e->ops[oi + 2];
+      const EngTensor &tx = e->tensors[op->in_t], &t1 = e->tensors[op->out_t], &t2 = e->tensors[dwo->out_t], &tp = e->tensors[p3->pass_t],
+                      &to = e->tensors[p3->out_t];
+      r = unit_s2_fused_launch(op->pw, dwo->dw, p3->pw, tx.ptr, tp.ptr, tp.pitch, to.ptr, batch, tx.H, tx.W, dwo->zx,
+                               e->fuse_units == 2 ? t1.ptr : nullptr, e->fuse_units == 2 ? t2.ptr : nullptr, st);
+      if (r) return r;
+      launches++;
+      mark(); mark(); mark();
       oi += 2;
       continue;
     }
@@ -809,16 +835,18 @@ extern "C" int cdn_engine_heads_fused(cdn_engine* e) {
 extern "C" int cdn_engine_units_fused(cdn_engine* e) {       // how many stride-1 units run as one kernel
   if (!e || !e->finalized) return 0;
   int n = 0;
-  for (size_t oi = 0; oi < e->ops.size(); ++oi) if (engine_fuses_unit(e, oi)) { ++n; oi += 2; }
+  for (size_t oi = 0; oi < e->ops.size(); ++oi) if (engine_fuses_unit(e, oi) || engine_fuses_unit_s2(e, oi)) { ++n; oi += 2; }
   return n;
 }
-// how plan op i runs: 0 = a launch of its own, 1 = first op of the fused heads tail, 2 = first op of a fused unit,
+// how plan op i runs: 0 = a launch of its own, 1 = first op of the fused heads tail, 2 = first op of a fused stride-1 unit,
+// 3 = first op of the fused stride-2 branch,
 // -1 = folded into the launch of an earlier op
 extern "C" int cdn_engine_op_fusion(cdn_engine* e, int i) {
   if (!e || !e->finalized || i < 0 || i >= (int)e->ops.size()) return 0;
   for (size_t oi = 0; oi < e->ops.size(); ++oi) {
-    const int span = engine_fuses_heads(e, oi) ? 2 : (engine_fuses_unit(e, oi) ? 3 : 1);
-    if ((size_t)i >= oi && (size_t)i < oi + span) return (size_t)i == oi ? (span == 2 ? 1 : (span == 3 ? 2 : 0)) : -1;
+    const bool s2 = engine_fuses_unit_s2(e, oi);
+    const int span = engine_fuses_heads(e, oi) ? 2 : ((engine_fuses_unit(e, oi) || s2) ? 3 : 1);
+    if ((size_t)i >= oi && (size_t)i < oi + span) return (size_t)i == oi ? (span == 2 ? 1 : (span == 3 ? (s2 ? 3 : 2) : 0)) : -1;
     oi += span - 1;
   }
   return 0;

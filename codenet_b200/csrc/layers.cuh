@@ -74,6 +74,14 @@ int heads_fused_launch(const DwDevice& dw, const PwDevice& pw, const int8_t* in,
 bool unit_fused_ok(const PwDevice& pw1, const DwDevice& dw, const PwDevice& pw3, int x_pitch, int mid_pitch, int out_pitch, int H, int W);
 int unit_fused_launch(const PwDevice& pw1, const DwDevice& dw, const PwDevice& pw3, const int8_t* x, int8_t* out, int HP,
                       int batch, int H, int W, int zx_mid, int8_t* dump_c1, int8_t* dump_d2, cudaStream_t st);
+int make_tmap_nhwc_swz(CUtensorMap* m, const void* base, uint64_t pitch, uint64_t W, uint64_t H, uint64_t batch,
+                       uint32_t box_c, uint32_t box_w, uint32_t box_h);
+// the branch of the FIRST stride-2 unit (1x1 conv at full resolution, depthwise 3x3 stride 2, 1x1 conv + cat + channel shuffle)
+// as one kernel (unit_s2_fused.cu)
+bool unit_s2_fused_ok(const PwDevice& pw1, const DwDevice& dw, const PwDevice& pw3, int x_pitch, int mid_pitch, int pass_pitch,
+                      int out_pitch, int H, int W);
+int unit_s2_fused_launch(const PwDevice& pw1, const DwDevice& dw, const PwDevice& pw3, const int8_t* x, const int8_t* pass, int pass_pitch,
+                         int8_t* out, int batch, int H, int W, int zx_mid, int8_t* dump_c1, int8_t* dump_d2, cudaStream_t st);
 int make_tmap_nhwc(CUtensorMap* m, const void* base, uint64_t pitch, uint64_t W, uint64_t H, uint64_t batch, uint32_t box_w, uint32_t box_h);
 int make_tmap_2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t pitch, uint32_t box_rows);
 

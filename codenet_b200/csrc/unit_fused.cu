@@ -20,8 +20,7 @@
 //       load) through the layer's chunk table = cat + channel_shuffle -> 128B-swizzled staging -> 4-D TMA store
 // The next tile's A1 load is issued as soon as its buffer is free, so it flies during S / G2 / E2 (or, when `mid` has its own
 // buffer, during E1 as well); the next pass-through tile is requested right after E2.
-#include "layers.cuh"
-#include "tc_ptx.cuh"
+#include "unit_fused.cuh"
 #include <algorithm>
 
 #define UF_THREADS 256
@@ -37,6 +36,7 @@ extern unsigned long long* g_pw_dbg;           // cycle accumulators shared with
 
 struct UfParams {
   int H, W, tiles_x, tiles_y; unsigned ntiles;
+  int txs, tys;                              // log2 of tiles_x / tiles_y when both are powers of two, else -1
   int N1, N3, tmem_cols;
   int early;                                 // 1: `mid` has its own buffer (A1 is refilled right after G1); 0: it aliases A1
   uint32_t off_mid, off_a2, off_pass, off_w1, off_w3, off_kc1, off_kc3, off_chunks, off_bar;   // from the 1024-aligned base
@@ -49,121 +49,6 @@ struct UfParams {
   unsigned long long* dbg_cyc;               // experiments (cdn_set_debug_flags bit 21): per-phase cycles of block 0, warp 7
 };
 #define UF_CYC(slot) do { if (p.dbg_cyc && blockIdx.x == 0 && tid == 224) { const long long t1__ = clock64(); atomicAdd(p.dbg_cyc + (slot), (unsigned long long)(t1__ - t0__)); t0__ = t1__; } } while (0)
-
-// `mid` tile: pixel p = r*18 + c at p*HP, 16-byte unit u XOR-swizzled by the pixel's COLUMN so that (i) the epilogue's
-// row-per-lane 16-byte stores and (ii) the stencil's pixel-per-(half-)warp word loads are both conflict-free, and (iii) a
-// stencil thread's four pixel offsets are constants (the row advances by a multiple of 128 bytes).
-template <int HP> __device__ __forceinline__ uint32_t uf_mid_swz(uint32_t c) {
-  return HP == 128 ? (c & 7u) : ((((c >> 1) & 1u) << 2) | ((c >> 1) & 3u));   // HP = 64: bit 2 swaps the two 64-byte halves of a line
-}
-template <int HP> __device__ __forceinline__ uint32_t uf_mid_off(uint32_t p, uint32_t c, uint32_t u) {
-  return (p * (uint32_t)HP + (u << 4)) ^ (uf_mid_swz<HP>(c) << 4);
-}
-
-// hi32(v * Mi + Bi): the requantisation of a channel whose shift is 0 (every channel of every CoDeNet layer: rq_int_solve
-// tries the scale 2^32 first), one IMAD.HI
-__device__ __forceinline__ int uf_rq_ns(int v, int Mi, long long Bi) {
-  int hi;
-  asm("{\n\t.reg .b64 t;\n\t.reg .b32 lo;\n\tmul.wide.s32 t, %1, %2;\n\tadd.s64 t, t, %3;\n\tmov.b64 {lo, %0}, t;\n\t}"
-      : "=r"(hi) : "r"(v), "r"(Mi), "l"(Bi));
-  return hi;
-}
-// FAST: shift 0 and no lower clamp (lo = -128 is the saturation); generic: RqInt with its shift, max(., lo)
-template <bool FAST> __device__ __forceinline__ int uf_rq(int v, const uint4& k, int lo) {
-  const long long Bi = (long long)(((unsigned long long)k.w << 32) | k.z);
-  if (FAST) return uf_rq_ns(v, (int)k.x, Bi);
-  return max(rq_int(v, (int)k.x, (int)k.y, Bi), lo);
-}
-template <bool FAST>
-__device__ __forceinline__ uint32_t uf_rq_word(const int (&acc)[4], const int2 (&km)[4], const long long (&kb)[4]) {
-  int q[4];
-#pragma unroll
-  for (int c = 0; c < 4; ++c) q[c] = FAST ? uf_rq_ns(acc[c], km[c].x, kb[c]) : rq_int_hi(acc[c], km[c].x, km[c].y, kb[c]);
-  return pack_sat4(q[0], q[1], q[2], q[3]);
-}
-__device__ __forceinline__ uint32_t uf_mask_word(uint32_t w, int rem) {
-  return rem >= 4 ? w : (rem <= 0 ? 0u : (w & (0xffffffffu >> (8 * (4 - rem)))));
-}
-__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t src) {
-  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];"
-               ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(src) : "memory");
-}
-__device__ __forceinline__ void sts_u128(uint32_t dst, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-// mbarrier wait that suspends in hardware for up to ~20 us per try: all 256 threads wait for the tensor core / TMA here, and a
-// plain try_wait loop cost 9 % of the kernel's issue slots in spin iterations
-__device__ __forceinline__ void uf_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0, spins = 0;
-  while (true) {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(done) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
-    if (done) break;
-    if (++spins > (1u << 20)) { printf("cdn unit_fused: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
-  }
-}
-
-// E2 of the fast path for the warps of group G (= first / second half of the unit's output channels): chunk j takes 8 new
-// columns G*Gp + 8j and the 8 pass-through bytes G*PG + 8j and writes 16 interleaved bytes at G*HP + 16j; with PG (channels per
-// group) a template constant every offset, shift and mask below is an immediate, and chunks go two at a time (one 16-column
-// TMEM load, pass-through words shared between neighbours).
-template <int HP, int PG, int G>
-__device__ __forceinline__ void uf_e2_fast(uint32_t taddr, uint32_t prow, uint32_t srow, uint32_t x7s, uint32_t s_kc3) {
-  constexpr int Gp = (PG + 7) & ~7, NCH = HP / 16;
-#pragma unroll
-  for (int j = 0; j < NCH; j += 2) {
-    const int col = G * Gp + 8 * j, pass_off = G * PG + 8 * j, dst = G * HP + 16 * j;
-    const int cnt0 = PG - 8 * j < 0 ? 0 : (PG - 8 * j > 8 ? 8 : PG - 8 * j), cnt1 = PG - 8 * j - 8 < 0 ? 0 : (PG - 8 * j - 8 > 8 ? 8 : PG - 8 * j - 8);
-    uint32_t o[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-    if (cnt0 > 0) {
-      uint32_t acc[16];
-      tmem_ld16(taddr + (uint32_t)col, acc);
-      // 16 pass-through bytes from byte pass_off: aligned 8-byte words (each inside one 16-byte swizzle unit) + funnel shifts
-      const int o8 = pass_off & ~7, b = pass_off & 7;
-      uint32_t w[6];
-#pragma unroll
-      for (int t = 0; t < 3; ++t) {
-        if (t == 2 && b == 0) { w[4] = 0u; w[5] = 0u; continue; }
-        const int ob = o8 + 8 * t;
-        const uint2 v = lds_u64(prow + ((((uint32_t)(ob >> 4)) << 4) ^ x7s) + (uint32_t)(ob & 8));
-        w[2 * t] = v.x; w[2 * t + 1] = v.y;
-      }
-      uint32_t ps[4];
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int wi = t + (b >> 2), sh = 8 * (b & 3);
-        ps[t] = sh == 0 ? w[wi] : __funnelshift_r(w[wi], w[wi + 1], sh);
-      }
-      tmem_ld_wait();
-      int v[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        if (i >= 8 && cnt1 == 0) { v[i] = 0; continue; }
-        const uint4 k = lds_u128(s_kc3 + (uint32_t)(col + i) * 16u);
-        v[i] = uf_rq<true>((int)acc[i], k, -128);
-      }
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int cnt = h ? cnt1 : cnt0;
-        if (cnt == 0) continue;
-        const uint32_t n_lo = pack_sat4(v[8 * h], v[8 * h + 1], v[8 * h + 2], v[8 * h + 3]);
-        const uint32_t n_hi = pack_sat4(v[8 * h + 4], v[8 * h + 5], v[8 * h + 6], v[8 * h + 7]);
-        // out[2i] = pass[i], out[2i+1] = new[i]
-        o[4 * h] = __byte_perm(ps[2 * h], n_lo, 0x5140); o[4 * h + 1] = __byte_perm(ps[2 * h], n_lo, 0x7362);
-        o[4 * h + 2] = __byte_perm(ps[2 * h + 1], n_hi, 0x5140); o[4 * h + 3] = __byte_perm(ps[2 * h + 1], n_hi, 0x7362);
-        if (cnt < 8) {
-#pragma unroll
-          for (int t = 0; t < 4; ++t) o[4 * h + t] = uf_mask_word(o[4 * h + t], 2 * cnt - 4 * t);
-        }
-      }
-    }
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int d = dst + 16 * h;
-      sts_u128(srow + (uint32_t)(d >> 7) * 16384u + ((((uint32_t)(d & 127) >> 4) << 4) ^ x7s), o[4 * h], o[4 * h + 1], o[4 * h + 2], o[4 * h + 3]);
-    }
-  }
-}
 
 // PG > 0: channels per output group as a template constant and the fast requantisation (shift 0, no lower clamp) in all three
 // layers; PG = 0: the layer's chunk table from shared memory, RqInt with shift, lower clamp applied
@@ -182,8 +67,13 @@ unit_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   auto tile_coords = [&](unsigned tile, int& tx, int& ty, int& b) {
-    tx = (int)(tile % (unsigned)p.tiles_x); tile /= (unsigned)p.tiles_x;
-    ty = (int)(tile % (unsigned)p.tiles_y); b = (int)(tile / (unsigned)p.tiles_y);
+    if (p.txs >= 0) {                          // the usual case: no integer division on the per-tile path
+      tx = (int)(tile & (unsigned)(p.tiles_x - 1)); tile >>= p.txs;
+      ty = (int)(tile & (unsigned)(p.tiles_y - 1)); b = (int)(tile >> p.tys);
+    } else {
+      tx = (int)(tile % (unsigned)p.tiles_x); tile /= (unsigned)p.tiles_x;
+      ty = (int)(tile % (unsigned)p.tiles_y); b = (int)(tile / (unsigned)p.tiles_y);
+    }
   };
   auto load_a1 = [&](unsigned tile) {          // one thread: branch half of the tile + halo, zero-filled outside the image
     int tx, ty, b; tile_coords(tile, tx, ty, b);
@@ -284,14 +174,16 @@ unit_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           umma_i8(tmem_base + (uint32_t)(blk * p.N1), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc1, k != 0 ? 1u : 0u);
       }
       umma_commit(bar_m);
-    }
-    uf_wait(bar_m, mph); mph ^= 1u;
-    tc_fence_after();
-    UF_CYC(0);
-    if (tid == 0) {
-      if (p.early && has_next) load_a1(tile + gridDim.x);       // A1 has been consumed by the tensor core
+      // only this thread polls the mbarrier; the other warps sleep in the hardware barrier below (when all 256 threads polled,
+      // the spin iterations were 7-9 % of the kernel's issued instructions)
+      uf_wait(bar_m, mph);
+      if (p.early && has_next) { tc_fence_after(); load_a1(tile + gridDim.x); }   // A1 has been consumed by the tensor core
       tma_store_wait_read0();                                    // the previous tile's stores have read the staging (= A2) buffers
     }
+    mph ^= 1u;
+    __syncthreads();
+    tc_fence_after();
+    UF_CYC(0);
     // ---- E1: accumulators -> int8 `mid` (dense columns = channels), real zero outside the image ----------------------------
     const int nblk = q < 2 ? 1 : 2;          // rows 128..179 live in lane quarters 2 and 3 of the second block
 #pragma unroll 1
@@ -374,9 +266,11 @@ unit_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int k = 0; k < HP / 32; ++k)
         umma_i8(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc3, k != 0 ? 1u : 0u);
       umma_commit(bar_m);
+      uf_wait(bar_p, it & 1u);                 // the pass-through tile (requested one tile ago)
+      uf_wait(bar_m, mph);
     }
-    uf_wait(bar_p, it & 1u);                   // the pass-through tile (requested one tile ago)
-    uf_wait(bar_m, mph); mph ^= 1u;
+    mph ^= 1u;
+    __syncthreads();
     tc_fence_after();
     UF_CYC(5);
     // ---- E2: accumulators + pass-through bytes -> interleaved output bytes in the staging segments (which alias A2) --------
@@ -449,10 +343,10 @@ typedef CUresult (*PFN_encodeTiledUf)(CUtensorMap*, CUtensorMapDataType, cuuint3
                                       const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-// NHWC int8 tensor, box = {128 bytes, box_w, box_h, 1} with the 128-byte swizzle: box rows land as the rows of a UMMA K-major
-// operand / of a swizzled staging segment, in (y, x) order
-static int make_tmap_nhwc_sw128(CUtensorMap* m, const void* base, uint64_t pitch, uint64_t W, uint64_t H, uint64_t batch,
-                                uint32_t box_w, uint32_t box_h) {
+// NHWC int8 tensor, box = {box_c bytes, box_w, box_h, 1} with the swizzle whose span is box_c (32 / 64 / 128 bytes): box rows land as
+// the rows of a UMMA K-major operand / of a swizzled staging segment, in (y, x) order
+int make_tmap_nhwc_swz(CUtensorMap* m, const void* base, uint64_t pitch, uint64_t W, uint64_t H, uint64_t batch,
+                       uint32_t box_c, uint32_t box_w, uint32_t box_h) {
   static PFN_encodeTiledUf enc = nullptr;
   if (!enc) {
     void* ptr = nullptr; cudaDriverEntryPointQueryResult qres;
@@ -460,15 +354,17 @@ static int make_tmap_nhwc_sw128(CUtensorMap* m, const void* base, uint64_t pitch
       enc = (PFN_encodeTiledUf)ptr;
   }
   CDN_CHECK(enc != nullptr, CDN_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-  CDN_CHECK(((uintptr_t)base & 15) == 0 && pitch % 16 == 0 && box_w <= 256 && box_h <= 256, CDN_ERR_INVALID, "TMA: base/pitch must be 16-byte aligned");
+  CDN_CHECK(((uintptr_t)base & 15) == 0 && pitch % 16 == 0 && box_w <= 256 && box_h <= 256 && (box_c == 32 || box_c == 64 || box_c == 128),
+            CDN_ERR_INVALID, "TMA: base/pitch must be 16-byte aligned, swizzled box of 32 / 64 / 128 bytes");
   cuuint64_t dims[4] = {pitch, W, H, batch};
   cuuint64_t strides[3] = {pitch, W * pitch, H * W * pitch};
-  cuuint32_t box[4] = {128, box_w, box_h, 1};
+  cuuint32_t box[4] = {box_c, box_w, box_h, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUtensorMapSwizzle sw = box_c == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (box_c == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  CDN_CHECK(r == CUDA_SUCCESS, CDN_ERR_CUDA, "cuTensorMapEncodeTiled (NHWC, 128B swizzle) failed with CUresult %d (pitch=%llu W=%llu H=%llu batch=%llu)",
-            (int)r, (unsigned long long)pitch, (unsigned long long)W, (unsigned long long)H, (unsigned long long)batch);
+                   sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CDN_CHECK(r == CUDA_SUCCESS, CDN_ERR_CUDA, "cuTensorMapEncodeTiled (NHWC, swizzled) failed with CUresult %d (pitch=%llu W=%llu H=%llu batch=%llu box=%u,%u,%u)",
+            (int)r, (unsigned long long)pitch, (unsigned long long)W, (unsigned long long)H, (unsigned long long)batch, box_c, box_w, box_h);
   return 0;
 }
 
@@ -496,6 +392,11 @@ int unit_fused_launch(const PwDevice& pw1, const DwDevice& dw, const PwDevice& p
   if (ntiles == 0) return 0;
   CDN_CHECK(ntiles < (1ll << 31) - 4 * 160, CDN_ERR_INVALID, "unit_fused: tensor too large for 32-bit indexing");
   p.ntiles = (unsigned)ntiles;
+  p.txs = p.tys = -1;
+  if (!(p.tiles_x & (p.tiles_x - 1)) && !(p.tiles_y & (p.tiles_y - 1))) {
+    p.txs = 0; while ((1 << p.txs) < p.tiles_x) ++p.txs;
+    p.tys = 0; while ((1 << p.tys) < p.tiles_y) ++p.tys;
+  }
   p.N1 = pw1.BN; p.N3 = pw3.BN;
   p.tmem_cols = 32; while (p.tmem_cols < 2 * p.N1 || p.tmem_cols < p.N3) p.tmem_cols <<= 1;
   p.w1 = pw1.w; p.w3 = pw3.w; p.kc1 = (const int4*)pw1.kc; p.kc3 = (const int4*)pw3.kc; p.lo1 = pw1.rq.lo; p.lo3 = pw3.rq.lo;
@@ -528,9 +429,9 @@ int unit_fused_launch(const PwDevice& pw1, const DwDevice& dw, const PwDevice& p
   if (smem > room || (g_cdn_debug_flags & (1u << 20))) smem = carve(false);
   CDN_CHECK(smem <= UF_SMEM_LIMIT, CDN_ERR_INVALID, "unit_fused: %zu bytes of shared memory", smem);
   CUtensorMap tmA, tmP, tmO;
-  if (int r = make_tmap_nhwc_sw128(&tmA, x, (uint64_t)(2 * HP), (uint64_t)W, (uint64_t)H, (uint64_t)batch, UF_IW, UF_IH)) return r;
-  if (int r = make_tmap_nhwc_sw128(&tmP, x, (uint64_t)(2 * HP), (uint64_t)W, (uint64_t)H, (uint64_t)batch, UF_TW, UF_TH)) return r;
-  if (int r = make_tmap_nhwc_sw128(&tmO, out, (uint64_t)(2 * HP), (uint64_t)W, (uint64_t)H, (uint64_t)batch, UF_TW, UF_TH)) return r;
+  if (int r = make_tmap_nhwc_swz(&tmA, x, (uint64_t)(2 * HP), (uint64_t)W, (uint64_t)H, (uint64_t)batch, 128, UF_IW, UF_IH)) return r;
+  if (int r = make_tmap_nhwc_swz(&tmP, x, (uint64_t)(2 * HP), (uint64_t)W, (uint64_t)H, (uint64_t)batch, 128, UF_TW, UF_TH)) return r;
+  if (int r = make_tmap_nhwc_swz(&tmO, out, (uint64_t)(2 * HP), (uint64_t)W, (uint64_t)H, (uint64_t)batch, 128, UF_TW, UF_TH)) return r;
   // fast variants: every channel of the three layers requantises with shift 0, no lower clamp beyond the int8 saturation, and
   // pw3's chunk table is the canonical cat + channel_shuffle interleave with PG channels per group
   const bool fast_rq = pw1.sh0 && pw3.sh0 && dw.sh0 && p.lo1 <= -128 && p.lo3 <= -128 && !(g_cdn_debug_flags & (1u << 22));   // bit 22: generic variant (A/B)

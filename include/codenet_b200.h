@@ -280,14 +280,17 @@ int cdn_engine_wait(cdn_engine* e, int slot);
  * which is what cdn_engine_read_tensor needs to see that tensor.  Same results bit for bit), "fuse_units" (default 1: every
  * eligible stride-1 ShuffleNetV2 unit -- QuantBaseNode.forward, quant_modules.py:878-907: 1x1 conv, depthwise 3x3, 1x1 conv,
  * cat + channel_shuffle -- runs as ONE kernel and the two int8 tensors inside the unit stay on the SM; 2 = the same kernel
- * also writes those two tensors for cdn_engine_read_tensor; 0 = three launches per unit.  Same results bit for bit). */
+ * also writes those two tensors for cdn_engine_read_tensor; 0 = three launches per unit.  The second branch of the first
+ * stride-2 unit (1x1 conv at full resolution, depthwise 3x3 stride 2, 1x1 conv + cat + shuffle) is fused the same way.
+ * Same results bit for bit). */
 int cdn_engine_set_option(cdn_engine* e, const char* name, int value);
 /* 1 when the finalized plan runs the heads' tail fused (option on and the layer pair eligible), else 0. */
 int cdn_engine_heads_fused(cdn_engine* e);
 /* Number of ShuffleNetV2 units of the finalized plan that run as one kernel (option "fuse_units" on and the unit eligible). */
 int cdn_engine_units_fused(cdn_engine* e);
 /* How plan op i (order of the cdn_engine_add_* calls) runs: 0 = a launch of its own, 1 = first op of the fused heads tail,
- * 2 = first op of a fused unit, -1 = folded into the launch of an earlier op. */
+ * 2 = first op of a fused stride-1 unit, 3 = first op of the fused branch of the first stride-2 unit, -1 = folded into the
+ * launch of an earlier op. */
 int cdn_engine_op_fusion(cdn_engine* e, int i);
 /* Debug/test access to an activation tensor of the last run: copies batch*H*W*pitch bytes to host. */
 int cdn_engine_read_tensor(cdn_engine* e, int tensor, int batch, int8_t* h_out);

@@ -30,7 +30,7 @@ def test_engine_matches_reference_vectors_256(golden, calib, mode):
     x = make_images(2, 256, seed=2)
     eng.set_option("fuse_heads", 0)                     # the int8 grid between heads.dw2 and heads.out is only written unfused
     eng.set_option("fuse_units", 2)                     # the fused unit kernel also writes the two int8 grids inside every unit
-    assert eng.units_fused == 10
+    assert eng.units_fused == 11                        # 10 stride-1 units + branch 2 of layer1.0 (stride 2)
     out = eng.run(torch.from_numpy(x).cuda())
     torch.cuda.synchronize()
     heads_unfused = eng.read_heads(2)
@@ -203,7 +203,8 @@ def test_heads_fused_equals_separate_kernels(calib, res, batch):
 
 @pytest.mark.parametrize("res,batch", [(256, 5), (512, 3), (384, 2), (512, 40)])
 def test_units_fused_equal_separate_kernels(calib, res, batch):
-    """Every stride-1 ShuffleNetV2 unit of stages 2 and 3 as ONE kernel (unit_fused.cu: 1x1 conv on the halo'd tile -> int8
+    """Every stride-1 ShuffleNetV2 unit of stages 2 and 3, and branch 2 of the first stride-2 unit (unit_s2_fused.cu: 1x1 conv on
+    the 17 x 33 input pixels of a tile, stride-2 stencil), as ONE kernel each (unit_fused.cu: 1x1 conv on the halo'd tile -> int8
     tile in shared memory -> depthwise stencil -> A tile of the second 1x1 conv -> interleaving epilogue) against the three
     separate launches per unit: every tapped int8 grid -- the two tensors INSIDE each unit included, which the fused kernel
     writes only in its dump mode --, the heads and the detections identical bit for bit, eager and as a graph, at tile counts
@@ -229,7 +230,7 @@ def test_units_fused_equal_separate_kernels(calib, res, batch):
     n_launch0 = eng.num_launches
     eng.set_option("fuse_units", 2)
     n_fused = eng.units_fused
-    assert n_fused == (3 if res == 384 else 10)
+    assert n_fused == (4 if res == 384 else 11)         # + branch 2 of the first stride-2 unit (unit_s2_fused.cu)
     for graph in (0, 1):
         eng.set_option("use_graph", graph)
         got = snapshot(labels)
