@@ -49,6 +49,7 @@ struct UfParams {
   unsigned long long* dbg_cyc;               // experiments (cdn_set_debug_flags bit 21): per-phase cycles of block 0, warp 7
 };
 #define UF_CYC(slot) do { if (p.dbg_cyc && blockIdx.x == 0 && tid == 224) { const long long t1__ = clock64(); atomicAdd(p.dbg_cyc + (slot), (unsigned long long)(t1__ - t0__)); t0__ = t1__; } } while (0)
+#define UF_CYC0(slot, stmt) do { if (p.dbg_cyc && blockIdx.x == 0) { const long long a__ = clock64(); stmt; atomicAdd(p.dbg_cyc + (slot), (unsigned long long)(clock64() - a__)); } else { stmt; } } while (0)
 
 // PG > 0: channels per output group as a template constant and the fast requantisation (shift 0, no lower clamp) in all three
 // layers; PG = 0: the layer's chunk table from shared memory, RqInt with shift, lower clamp applied
@@ -153,9 +154,14 @@ unit_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t idesc3 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.N3 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   const int q = warp & 3, hf = warp >> 2;      // TMEM lane quarter of this warp; which half of the columns / chunks it takes
   const uint32_t pad = p.pad_word;
+  // operand descriptors are constants of the kernel: the issuing thread's serial section between two barriers stays short
+  const uint64_t d_a1 = make_smem_desc(s_a1), d_a1b = make_smem_desc(s_a1 + UF_BLK1 * 128u), d_w1 = make_smem_desc(s_w1);
+  const uint64_t d_a2 = make_smem_desc(s_a2), d_w3 = make_smem_desc(s_w3);
 
   pdl_wait();                                  // everything above is constant; activations need the previous grid
-  if (tid == 0 && blockIdx.x < p.ntiles) { load_a1(blockIdx.x); load_pass(blockIdx.x); }
+  // warp 0's elected lane issues the MMAs and waits for them; warp 1's issues every TMA load / store: the two serial sections
+  // between a pair of barriers run side by side instead of one after the other
+  if (warp == 1 && blockIdx.x < p.ntiles) { if (uf_elect()) { load_a1(blockIdx.x); load_pass(blockIdx.x); } }
   uint32_t it = 0, mph = 0;
   long long t0__ = p.dbg_cyc ? clock64() : 0;
   const long long tstart__ = t0__;
@@ -163,61 +169,51 @@ unit_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int tx, ty, b; tile_coords(tile, tx, ty, b);
     const bool has_next = (unsigned long long)tile + gridDim.x < p.ntiles;
     // ---- G1: [180 x HP] x [HP x N1] as two M = 128 blocks (rows 0..127, 64..191) --------------------------------------------
-    if (tid == 0) {
-      uf_wait(bar_a, it & 1u);
+    if (warp == 0) { if (uf_elect()) {
+      UF_CYC0(10, uf_wait(bar_a, it & 1u));
       tc_fence_after();
 #pragma unroll
       for (int blk = 0; blk < 2; ++blk) {
-        const uint64_t adesc = make_smem_desc(s_a1 + (uint32_t)blk * UF_BLK1 * 128u), bdesc = make_smem_desc(s_w1);
 #pragma unroll
         for (int k = 0; k < HP / 32; ++k)
-          umma_i8(tmem_base + (uint32_t)(blk * p.N1), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc1, k != 0 ? 1u : 0u);
+          umma_i8(tmem_base + (uint32_t)(blk * p.N1), (blk ? d_a1b : d_a1) + (uint64_t)(2 * k), d_w1 + (uint64_t)(2 * k), idesc1, k != 0 ? 1u : 0u);
       }
       umma_commit(bar_m);
       // only this thread polls the mbarrier; the other warps sleep in the hardware barrier below (when all 256 threads polled,
       // the spin iterations were 7-9 % of the kernel's issued instructions)
-      uf_wait(bar_m, mph);
-      if (p.early && has_next) { tc_fence_after(); load_a1(tile + gridDim.x); }   // A1 has been consumed by the tensor core
-      tma_store_wait_read0();                                    // the previous tile's stores have read the staging (= A2) buffers
-    }
+      UF_CYC0(11, uf_wait(bar_m, mph));
+    } }
     mph ^= 1u;
     __syncthreads();
     tc_fence_after();
     UF_CYC(0);
+    if (warp == 1 && p.early && has_next) { if (uf_elect()) load_a1(tile + gridDim.x); }   // A1 has been consumed by the tensor core
     // ---- E1: accumulators -> int8 `mid` (dense columns = channels), real zero outside the image ----------------------------
-    const int nblk = q < 2 ? 1 : 2;          // rows 128..179 live in lane quarters 2 and 3 of the second block
-#pragma unroll 1
-    for (int blk = 0; blk < nblk; ++blk) {
-      const int row = blk * UF_BLK1 + q * 32 + lane;
-      const bool valid = blk == 0 || (row >= 128 && row < UF_PIX1);
-      const int r = (row * 3641) >> 16, c = row - r * UF_IW;   // row / 18 for row < 192
-      const bool inside = (unsigned)(ty * UF_TH - 1 + r) < (unsigned)p.H && (unsigned)(tx * UF_TW - 1 + c) < (unsigned)p.W;
-      const uint32_t taddr = tmem_base + (uint32_t)(blk * p.N1) + ((uint32_t)(q * 32) << 16);
-      const uint32_t mrow = s_mid + (uint32_t)row * (uint32_t)HP, mswz = uf_mid_swz<HP>((uint32_t)c) << 4;
+    {
+      // block 0: rows q*32 + lane (all valid); block 1: rows 64 + q*32 + lane, of which 128..179 are new -- they live in lane
+      // quarters 2 and 3, whose warps requantise both blocks with one fetch of the per-column constants
+      uint32_t taddr[2], mpix[2], mswz[2]; bool valid[2], inside[2]; int8_t* dump[2];
 #pragma unroll
-      for (int c0 = 0; c0 < HP; c0 += 32) {
-        uint32_t acc[16];
-        tmem_ld16(taddr + (uint32_t)(c0 + hf * 16), acc);
-        tmem_ld_wait();
-        const uint32_t kc = s_kc1 + (uint32_t)(c0 + hf * 16) * 16u;
-        uint32_t o[4];
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          int v[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) v[i] = uf_rq<FAST>((int)acc[4 * g + i], lds_u128(kc + (uint32_t)(4 * g + i) * 16u), p.lo1);
-          o[g] = inside ? pack_sat4(v[0], v[1], v[2], v[3]) : pad;
-        }
-        if (valid) {
-          sts_u128((mrow + (uint32_t)(c0 + hf * 16)) ^ mswz, o[0], o[1], o[2], o[3]);
-          if (p.dump_c1 && r >= 1 && r <= UF_TH && c >= 1 && c <= UF_TW) {
-            int8_t* d = p.dump_c1 + (((size_t)b * p.H + (ty * UF_TH - 1 + r)) * p.W + (tx * UF_TW - 1 + c)) * HP + c0 + hf * 16;
-            *(uint4*)d = make_uint4(o[0], o[1], o[2], o[3]);
-          }
-        }
+      for (int blk = 0; blk < 2; ++blk) {
+        const int row = blk * UF_BLK1 + q * 32 + lane;
+        const int r = (row * 3641) >> 16, c = row - r * UF_IW;   // row / 18 for row < 192
+        valid[blk] = blk == 0 || (row >= 128 && row < UF_PIX1);
+        inside[blk] = (unsigned)(ty * UF_TH - 1 + r) < (unsigned)p.H && (unsigned)(tx * UF_TW - 1 + c) < (unsigned)p.W;
+        taddr[blk] = tmem_base + (uint32_t)(blk * p.N1) + ((uint32_t)(q * 32) << 16);
+        mpix[blk] = s_mid + (uint32_t)row * (uint32_t)HP; mswz[blk] = uf_mid_swz<HP>((uint32_t)c) << 4;
+        dump[blk] = (p.dump_c1 && valid[blk] && r >= 1 && r <= UF_TH && c >= 1 && c <= UF_TW)
+                        ? p.dump_c1 + (((size_t)b * p.H + (ty * UF_TH - 1 + r)) * p.W + (tx * UF_TW - 1 + c)) * HP : nullptr;
+      }
+      if (q < 2) {
+        const uint32_t t1[1] = {taddr[0]}, m1[1] = {mpix[0]}, s1[1] = {mswz[0]}; const bool v1[1] = {true}, i1[1] = {inside[0]};
+        int8_t* const d1[1] = {dump[0]};
+        uf_e1<HP, FAST, 1>(t1, m1, s1, v1, i1, hf, s_kc1, p.lo1, pad, d1);
+      } else {
+        uf_e1<HP, FAST, 2>(taddr, mpix, mswz, valid, inside, hf, s_kc1, p.lo1, pad, dump);
       }
     }
     UF_CYC(1);
+    if (warp == 1) { if (uf_elect()) tma_store_wait_read0(); }   // the previous tile's stores have read the staging (= A2) buffers: the stencil may write A2
     tc_fence_before();
     __syncthreads();                           // `mid` complete; the accumulators of G1 are drained
     UF_CYC(2);
@@ -258,17 +254,16 @@ unit_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     __syncthreads();
     UF_CYC(4);
     // ---- G2: [128 x HP] x [HP x N3] -------------------------------------------------------------------------------------------
-    if (tid == 0) {
-      if (!p.early && has_next) load_a1(tile + gridDim.x);      // `mid` (aliasing A1) has been consumed by the stencil
+    if (warp == 1 && !p.early && has_next) { if (uf_elect()) load_a1(tile + gridDim.x); }   // `mid` (aliasing A1) has been consumed by the stencil
+    if (warp == 0) { if (uf_elect()) {
       tc_fence_after();
-      const uint64_t adesc = make_smem_desc(s_a2), bdesc = make_smem_desc(s_w3);
 #pragma unroll
       for (int k = 0; k < HP / 32; ++k)
-        umma_i8(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc3, k != 0 ? 1u : 0u);
+        umma_i8(tmem_base, d_a2 + (uint64_t)(2 * k), d_w3 + (uint64_t)(2 * k), idesc3, k != 0 ? 1u : 0u);
       umma_commit(bar_m);
-      uf_wait(bar_p, it & 1u);                 // the pass-through tile (requested one tile ago)
-      uf_wait(bar_m, mph);
-    }
+      UF_CYC0(12, uf_wait(bar_p, it & 1u));    // the pass-through tile (requested one tile ago)
+      UF_CYC0(13, uf_wait(bar_m, mph));
+    } }
     mph ^= 1u;
     __syncthreads();
     tc_fence_after();
@@ -320,14 +315,14 @@ unit_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tc_fence_before();                         // the next tile's G1 overwrites the accumulator columns after this barrier
     __syncthreads();
     UF_CYC(7);
-    if (tid == 0) {
+    if (warp == 1) { if (uf_elect()) {
       for (int s = 0; s < p.n_segs; ++s) tma_store_4d(&tmO, s * 128, tx * UF_TW, ty * UF_TH, b, s_a2 + (uint32_t)s * 16384u);
       tma_store_commit();
       if (has_next) load_pass(tile + gridDim.x);                 // this tile's pass-through bytes have been consumed
-    }
+    } }
   }
   if (p.dbg_cyc && blockIdx.x == 0 && tid == 224) { atomicAdd(p.dbg_cyc + 8, (unsigned long long)(clock64() - tstart__)); atomicAdd(p.dbg_cyc + 9, (unsigned long long)it); }
-  if (tid == 0) tma_store_wait_all();
+  if (warp == 1) { if (uf_elect()) tma_store_wait_all(); }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -404,7 +399,7 @@ int unit_fused_launch(const PwDevice& pw1, const DwDevice& dw, const PwDevice& p
   p.pad_word = (uint32_t)(uint8_t)(int8_t)(-zx_mid) * 0x01010101u;
   p.chunks = pw3.chunks; p.n_chunks = pw3.n_chunks; p.n_segs = pw3.n_segs;
   p.dump_c1 = dump_c1; p.dump_d2 = dump_d2;
-  p.dbg_cyc = (g_cdn_debug_flags & (1u << 21)) ? g_pw_dbg : nullptr;
+  p.dbg_cyc = ((g_cdn_debug_flags & (1u << 21)) && (!(g_cdn_debug_flags & (1u << 24)) || HP == 128) && (!(g_cdn_debug_flags & (1u << 25)) || HP == 64)) ? g_pw_dbg : nullptr;   // bits 24 / 25: only the HP = 128 / 64 launches
   // shared-memory carve: [A1 192 x 128][mid 180 x HP (early) | aliasing A1][A2 / staging n_segs x 16 KB][pass 16 KB][W1][W3][kc1][kc3][chunks][barriers]
   const uint32_t a1_bytes = UF_A1_BYTES, mid_bytes = (UF_PIX1 * (uint32_t)HP + 1023u) & ~1023u;
   auto carve = [&](bool early) {

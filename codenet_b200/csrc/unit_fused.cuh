@@ -118,3 +118,49 @@ __device__ __forceinline__ void uf_e2_fast(uint32_t taddr, uint32_t prow, uint32
   }
 }
 
+
+// one lane of a converged warp (the lowest): single-thread tcgen05 / TMA issue without the per-instruction BRA.U.ANY loops the
+// compiler wraps around them under a divergent `tid == 0` predicate
+__device__ __forceinline__ bool uf_elect() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
+// E1 of NB accumulator blocks at once: this lane's row of every block (TMEM address taddr[b], `mid` pixel address mpix[b] with
+// swizzle term mswz[b]) is requantised with ONE fetch of the per-column constants -- the broadcast LDS.128 per column is a third of
+// the epilogue's instructions when every block fetches its own.  Columns hf*16 + {0, 32, ...}; rows that are not `valid` are
+// skipped, rows outside the image store the real zero `pad`; dump[b] (tests) is the row's pixel in the global copy of `mid` or null.
+template <int HP, bool FAST, int NB>
+__device__ __forceinline__ void uf_e1(const uint32_t (&taddr)[NB], const uint32_t (&mpix)[NB], const uint32_t (&mswz)[NB],
+                                      const bool (&valid)[NB], const bool (&inside)[NB], int hf, uint32_t s_kc1, int lo, uint32_t pad,
+                                      int8_t* const (&dump)[NB]) {
+#pragma unroll
+  for (int c0 = 0; c0 < HP; c0 += 32) {
+    const uint32_t col = (uint32_t)(c0 + hf * 16);
+    uint32_t acc[NB][16];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) tmem_ld16(taddr[b] + col, acc[b]);
+    tmem_ld_wait();
+    const uint32_t kc = s_kc1 + col * 16u;
+    uint32_t o[NB][4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      int v[NB][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint4 k = lds_u128(kc + (uint32_t)(4 * g + i) * 16u);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) v[b][i] = uf_rq<FAST>((int)acc[b][4 * g + i], k, lo);
+      }
+#pragma unroll
+      for (int b = 0; b < NB; ++b) o[b][g] = inside[b] ? pack_sat4(v[b][0], v[b][1], v[b][2], v[b][3]) : pad;
+    }
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+      if (valid[b]) {
+        sts_u128((mpix[b] + col) ^ mswz[b], o[b][0], o[b][1], o[b][2], o[b][3]);
+        if (dump[b]) *(uint4*)(dump[b] + col) = make_uint4(o[b][0], o[b][1], o[b][2], o[b][3]);
+      }
+  }
+}

@@ -142,79 +142,67 @@ unit_s2_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   const int q = warp & 3, hf = warp >> 2;
   const uint32_t pad = p.pad_word;
+  const uint64_t d_a1 = us_desc_sw32(s_a1), d_w1 = us_desc_sw32(s_w1), d_a2 = make_smem_desc(s_a2), d_w3 = make_smem_desc(s_w3);
 
   pdl_wait();
-  if (tid == 0 && blockIdx.x < p.ntiles) { load_a1(blockIdx.x); load_pass(blockIdx.x); }
+  // warp 0's elected lane issues the MMAs, warp 1's every TMA load / store (see unit_fused.cu)
+  if (warp == 1 && blockIdx.x < p.ntiles) { if (uf_elect()) { load_a1(blockIdx.x); load_pass(blockIdx.x); } }
   uint32_t it = 0, mph = 0;
   for (unsigned tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
     int tx, ty, b; tile_coords(tile, tx, ty, b);
     const bool has_next = (unsigned long long)tile + gridDim.x < p.ntiles;
     const int iy0 = 2 * ty * US_TH - 1, ix0 = 2 * tx * US_TW - 1;
-    // E1 of one block: 128 rows of the first GEMM -> int8 `mid` pixels (real zero outside the image)
-    auto e1_block = [&](int blk, uint32_t tcol) {
+    // E1 of one block or of two blocks sharing the per-column constants: 128 rows of the first GEMM each -> int8 `mid` pixels
+    auto e1_setup = [&](int blk, uint32_t tcol, uint32_t& taddr, uint32_t& mpix, uint32_t& mswz, bool& valid, bool& inside, int8_t*& dump) {
       const int row = blk * 128 + q * 32 + lane;
-      const bool valid = row < US_PIX;
       const int r = (row * 1986) >> 16, c = row - r * US_IW;   // row / 33 for row < 640
-      const bool inside = (unsigned)(iy0 + r) < (unsigned)p.Hin && (unsigned)(ix0 + c) < (unsigned)p.Win;
-      const uint32_t taddr = tmem_base + tcol + ((uint32_t)(q * 32) << 16);
-      const uint32_t mrow = s_mid + (uint32_t)(r * US_MW + c) * (uint32_t)HP, mswz = uf_mid_swz<HP>((uint32_t)c) << 4;
-#pragma unroll
-      for (int c0 = 0; c0 < HP; c0 += 32) {
-        uint32_t acc[16];
-        tmem_ld16(taddr + (uint32_t)(c0 + hf * 16), acc);
-        tmem_ld_wait();
-        const uint32_t kc = s_kc1 + (uint32_t)(c0 + hf * 16) * 16u;
-        uint32_t o[4];
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          int v[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) v[i] = uf_rq<true>((int)acc[4 * g + i], lds_u128(kc + (uint32_t)(4 * g + i) * 16u), -128);
-          o[g] = inside ? pack_sat4(v[0], v[1], v[2], v[3]) : pad;
-        }
-        if (valid) {
-          sts_u128((mrow + (uint32_t)(c0 + hf * 16)) ^ mswz, o[0], o[1], o[2], o[3]);
-          if (p.dump_c1 && inside && r >= 1 && c >= 1) {
-            int8_t* d = p.dump_c1 + (((size_t)b * p.Hin + (iy0 + r)) * p.Win + (ix0 + c)) * HP + c0 + hf * 16;
-            *(uint4*)d = make_uint4(o[0], o[1], o[2], o[3]);
-          }
-        }
-      }
+      valid = row < US_PIX;
+      inside = (unsigned)(iy0 + r) < (unsigned)p.Hin && (unsigned)(ix0 + c) < (unsigned)p.Win;
+      taddr = tmem_base + tcol + ((uint32_t)(q * 32) << 16);
+      mpix = s_mid + (uint32_t)(r * US_MW + c) * (uint32_t)HP; mswz = uf_mid_swz<HP>((uint32_t)c) << 4;
+      dump = (p.dump_c1 && valid && inside && r >= 1 && c >= 1) ? p.dump_c1 + (((size_t)b * p.Hin + (iy0 + r)) * p.Win + (ix0 + c)) * HP : nullptr;
+    };
+    auto e1_pair = [&](int blk0, uint32_t tcol0) {
+      uint32_t taddr[2], mpix[2], mswz[2]; bool valid[2], inside[2]; int8_t* dump[2];
+      e1_setup(blk0, tcol0, taddr[0], mpix[0], mswz[0], valid[0], inside[0], dump[0]);
+      e1_setup(blk0 + 1, tcol0 + 64u, taddr[1], mpix[1], mswz[1], valid[1], inside[1], dump[1]);
+      uf_e1<HP, true, 2>(taddr, mpix, mswz, valid, inside, hf, s_kc1, -128, pad, dump);
+    };
+    auto e1_block = [&](int blk, uint32_t tcol) {
+      uint32_t taddr[1], mpix[1], mswz[1]; bool valid[1], inside[1]; int8_t* dump[1];
+      e1_setup(blk, tcol, taddr[0], mpix[0], mswz[0], valid[0], inside[0], dump[0]);
+      uf_e1<HP, true, 1>(taddr, mpix, mswz, valid, inside, hf, s_kc1, -128, pad, dump);
     };
     // ---- G1, blocks 0..3 -> TMEM columns 0 / 64 / 128 / 192 ------------------------------------------------------------------
-    if (tid == 0) {
+    if (warp == 0) { if (uf_elect()) {
       uf_wait(bar_a, it & 1u);
       tc_fence_after();
 #pragma unroll
       for (int blk = 0; blk < 4; ++blk)
-        umma_i8(tmem_base + (uint32_t)(blk * 64), us_desc_sw32(s_a1 + (uint32_t)blk * 128u * 32u), us_desc_sw32(s_w1), idesc, 0u);
+        umma_i8(tmem_base + (uint32_t)(blk * 64), d_a1 + (uint64_t)(blk * 256), d_w1, idesc, 0u);   // 128 rows x 32 B = 4096 B = 256 units
       umma_commit(bar_m);
       uf_wait(bar_m, mph);
-    }
+    } }
     mph ^= 1u;
     __syncthreads();
     tc_fence_after();
-    e1_block(0, 0u);
+    e1_pair(0, 0u);
     tc_fence_before();
-    __syncthreads();                           // block 0's columns are drained: block 4 goes there, behind the epilogue of blocks 1..3
-    if (tid == 0) {
+    __syncthreads();                           // block 0's columns are drained: block 4 goes there, behind the epilogue of blocks 2 and 3
+    if (warp == 0) { if (uf_elect()) {
       tc_fence_after();
-      umma_i8(tmem_base, us_desc_sw32(s_a1 + 4u * 128u * 32u), us_desc_sw32(s_w1), idesc, 0u);
+      umma_i8(tmem_base, d_a1 + (uint64_t)(4 * 256), d_w1, idesc, 0u);
       umma_commit(bar_m);
-    }
-    e1_block(1, 64u);
-    e1_block(2, 128u);
-    e1_block(3, 192u);
-    if (tid == 0) {
-      uf_wait(bar_m, mph);
-      if (has_next) { tc_fence_after(); load_a1(tile + gridDim.x); }   // the input tile has been consumed by the tensor core
-      tma_store_wait_read0();                                            // the previous tile's stores have read the staging (= A2) buffer
-    }
+    } }
+    e1_pair(2, 128u);
+    if (warp == 0) { if (uf_elect()) uf_wait(bar_m, mph); }
     mph ^= 1u;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (warp == 1 && has_next) { if (uf_elect()) load_a1(tile + gridDim.x); }   // the input tile has been consumed by the tensor core
     if (q < 2) e1_block(4, 0u);                // rows 512..560 live in lane quarters 0 and 1
+    if (warp == 1) { if (uf_elect()) tma_store_wait_read0(); }   // the previous tile's store has read the staging (= A2) buffer: the stencil may write A2
     tc_fence_before();
     __syncthreads();                           // `mid` complete, all accumulators drained
     // ---- S: depthwise 3x3 stride 2 over `mid` -> A tile of the second GEMM (row = oy*16 + ox) ---------------------------------
@@ -248,16 +236,15 @@ unit_s2_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     tc_fence_before();
     __syncthreads();
     // ---- G2: [128 x 64] x [64 x 64] -> TMEM columns 64.. --------------------------------------------------------------------------
-    if (tid == 0) {
+    if (warp == 0) { if (uf_elect()) {
       tc_fence_after();
-      const uint64_t adesc = make_smem_desc(s_a2), bdesc = make_smem_desc(s_w3);
 #pragma unroll
       for (int k = 0; k < HP / 32; ++k)
-        umma_i8(tmem_base + 64u, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k != 0 ? 1u : 0u);
+        umma_i8(tmem_base + 64u, d_a2 + (uint64_t)(2 * k), d_w3 + (uint64_t)(2 * k), idesc, k != 0 ? 1u : 0u);
       umma_commit(bar_m);
       uf_wait(bar_p, it & 1u);
       uf_wait(bar_m, mph);
-    }
+    } }
     mph ^= 1u;
     __syncthreads();
     tc_fence_after();
@@ -272,13 +259,13 @@ unit_s2_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 1) { if (uf_elect()) {
       tma_store_4d(&tmO, 0, tx * US_TW, ty * US_TH, b, s_a2);
       tma_store_commit();
       if (has_next) load_pass(tile + gridDim.x);
-    }
+    } }
   }
-  if (tid == 0) tma_store_wait_all();
+  if (warp == 1) { if (uf_elect()) tma_store_wait_all(); }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {

@@ -26,3 +26,4 @@ v = list(buf)
 names = ["wait A1+G1", "E1", "sync1", "S", "sync2", "wait pass+G2", "E2", "sync3"]
 print("all 10 fused units, block 0 warp 7: %d cycles total (%.1f us), %d tiles -> %.0f cycles per tile" % (v[8], v[8] / 1965.0, v[9], v[8] / max(v[9], 1)))
 print("   " + "  ".join("%s %.1f%%" % (n, 100.0 * c / max(v[8], 1)) for n, c in zip(names, v)))
+print("   thread 0 of block 0, cycles per tile: wait A1 %.0f, wait G1 %.0f, wait pass %.0f, wait G2 %.0f" % tuple(c / max(v[9], 1) for c in v[10:14]))
