@@ -351,6 +351,8 @@ def test_engine_w2_maxpool_matches_reference_vectors(golden):
     eng = Engine.from_state_dict(cfg, st, 256, 256, 2, offset_mode="round")
     x = make_images(2, 256, seed=2)[:1]
     eng.set_option("fuse_heads", 0)
+    eng.set_option("fuse_units", 2)                     # stage-2 units (122 channels per half) run fused; dump the grids inside them
+    assert eng.units_fused == 3
     out = eng.run(torch.from_numpy(x.copy()).cuda())
     torch.cuda.synchronize()
     heads_unfused = eng.read_heads(1)

@@ -62,6 +62,46 @@ def _check_ops(sim256, kinds, flags=0):
 
 def test_stem_every_layer(sim256):
     _check_ops(sim256, ("stem",))
+    _check_ops(sim256, ("stem",), flags=1 << 26)        # the all-fp64 kernel (the definition), bit 26
+
+
+def test_stem_fast_path_equals_fp64_kernel(sim256):
+    """stem.cu's guarded fp32 fast path (packed FFMA2 dot product, fp64 re-evaluation of every channel whose value is within the
+    derived error bound of a rounding boundary) against the all-fp64 kernel on inputs chosen to stress the guard: ordinary images,
+    huge and tiny magnitudes, exact cancellation between large taps, constant images whose requantised value sits ON a rounding
+    boundary for some channel, and non-finite pixels.  Bit-identical int8 grids for both strides and with the max-pool."""
+    from gpu_util import run_op
+    plan, _, T, _ = sim256
+    op = next(o for o in plan.ops if o.kind == "stem")
+    rng = np.random.default_rng(7)
+    H = W = 64
+    imgs = [make_images(2, H, seed=9)]
+    imgs.append((rng.standard_normal((2, 3, H, W)) * 1e6).astype(np.float32))
+    imgs.append((rng.standard_normal((2, 3, H, W)) * 1e-6).astype(np.float32))
+    big = rng.standard_normal((2, 3, H, W)).astype(np.float32) * 3e4
+    big[:, :, ::2] = -big[:, :, 1::2]                                  # rows cancel pairwise: tiny sums of huge terms
+    imgs.append(big)
+    w = op.a["wq"].astype(np.float64).reshape(op.a["C"], 27)
+    M, B = np.asarray(op.a["M"], np.float64), np.asarray(op.a["B"], np.float64)
+    const = np.zeros((2, 3, H, W), np.float32)
+    for b in range(2):                                                 # interior value v with M_c * v * sum(w_c) + B_c = k + 0.5 for channel c
+        c = 3 + 5 * b
+        k = np.floor(B[c]) + 2
+        const[b] = np.float32((k + 0.5 - B[c]) / (M[c] * w[c].sum()))
+    imgs.append(const)
+    nf = make_images(2, H, seed=10)
+    nf[0, 1, 10, 10] = np.nan; nf[1, 2, 20, 33] = np.inf; nf[1, 0, 5, 7] = -np.inf
+    imgs.append(nf)
+    L = _lib.load()
+    for x in imgs:
+        for stride, pool in ((4, 0), (2, 1), (2, 0)):
+            o2 = Op("stem", "stem", dict(op.a, H=H, W=W, stride=stride, pool=pool))
+            L.cdn_set_debug_flags(0)
+            fast = run_op(plan, o2, T, images=x)
+            L.cdn_set_debug_flags(1 << 26)
+            ref = run_op(plan, o2, T, images=x)
+            assert fast.shape == ref.shape and fast.tobytes() == ref.tobytes(), (stride, pool, int((fast != ref).sum()))
+    L.cdn_set_debug_flags(0)
 
 
 def test_depthwise_every_layer(sim256):
