@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 TAG = sys.argv[1] if len(sys.argv) > 1 else "r01"
 OUT = os.path.join(ROOT, "profiles")
 GO = os.path.join(ROOT, "gpurun_out")
-LAUNCHES_PER_STEP = 66          # kernels of one forward + decode (memset excluded; heads.dw2 + heads.out are one launch)
+LAUNCHES_PER_STEP = int(os.environ.get("LAUNCHES_PER_STEP", "44"))   # kernels of one forward + decode (memset excluded; fused groups are one launch each)
 
 
 def fam(name):
@@ -27,6 +27,10 @@ def fam(name):
         return "deform_int_kernel"
     if n in ("deform_tile_bil_kernel", "deform_dw_v2_kernel"):
         return "deform_bilinear_kernel"
+    if n in ("unit_fused_kernel", "unit_s2_fused_kernel"):
+        return "unit_fused_kernel"
+    if n in ("stem_kernel", "stem_fast_kernel"):
+        return "stem_kernel"
     if n in ("ctdet_peaks_rows_kernel", "ctdet_peaks_kernel", "ctdet_decode_kernel"):
         return "ctdet_decode"
     return n
@@ -48,9 +52,9 @@ def launch_list():
             d["dram_rd" if "read" in r[im] else "dram_wr"] = v * mult
     L = list(launches.values())
     # the bench runs 3 warm-up + 1 timed step on the device-resident fp32 batch first: take the LAST full step of those
-    first_e2e = next((i for i, d in enumerate(L) if d["kernel"].startswith("stem_kernel<1>")), len(L))
+    first_e2e = next((i for i, d in enumerate(L) if d["kernel"].startswith(("stem_kernel<1>", "stem_fast_kernel<1"))), len(L))
     step = L[first_e2e - LAUNCHES_PER_STEP:first_e2e]
-    assert step and step[0]["kernel"].startswith("stem_kernel"), (first_e2e, step[:2])
+    assert step and step[0]["kernel"].startswith(("stem_kernel", "stem_fast_kernel")), (first_e2e, step[:2])
     with open(os.path.join(OUT, TAG + "_launches.csv"), "w") as f:
         f.write("# one timed step of bench.py (batch 256), ncu --metrics gpu__time_duration.sum,dram__bytes_*.sum "
                 "--clock-control none: cold-cache, serialised -> compare SHARES\nidx,kernel,us,dram_read_MB,dram_write_MB\n")
@@ -88,7 +92,7 @@ def full(kernel):
         for w in WANT:
             if w in hdr:
                 out.append("    %-70s %s %s" % (w, r[hdr.index(w)], units[hdr.index(w)]))
-    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-id", "::regex:%s:1" % kernel[:8]],
+    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--launch-skip", "0", "--launch-count", "1"],
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(src.splitlines()))
     if len(rows) > 3:
@@ -114,5 +118,5 @@ def full(kernel):
 
 if __name__ == "__main__":
     launch_list()
-    for k in ("pw_gemm_tc", "deform_tile_int", "deform_tile_bil", "dw3x3_tma", "heads_fused"):
+    for k in ("unit_fused", "stem_fast", "pw_gemm_tc", "deform_tile_int", "deform_tile_bil", "dw3x3_tma", "heads_fused"):
         full(k)
