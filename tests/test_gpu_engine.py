@@ -310,7 +310,7 @@ def test_batch_independence_graph_and_host_path(calib):
     o5 = eng.run(xt[:3].contiguous(), maps=False)
     torch.cuda.synchronize()
     np.testing.assert_array_equal(o5["dets"].cpu().numpy(), d1[:3])
-    assert eng.num_launches >= 60
+    assert eng.num_launches >= 40                        # 44 with the fused units and heads tail (66 without)
     eng.close()
 
 
