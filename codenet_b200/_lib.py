@@ -57,6 +57,9 @@ EXPORTS = {
     "cdn_deform_layer_destroy": (C.c_int, [C.c_void_p]),
     "cdn_pw_gemm_i8": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.POINTER(PwDesc), C.c_void_p, C.c_int, C.c_void_p,
                                  C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "cdn_shuffle_unit_i8": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(PwDesc), C.POINTER(C.c_int8),
+                                      C.c_int, C.c_int, C.POINTER(Requant), C.POINTER(PwDesc), C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                      C.c_void_p]),
     "cdn_ctdet_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_void_p]),
     "cdn_ctdet_decode_prob": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

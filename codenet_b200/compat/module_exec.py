@@ -79,8 +79,18 @@ class Mini(PlanBuilder):
 
     def run(self, images=None):
         out = None
-        for op in self.plan.ops:
-            out = ops.run_op(self.plan, op, self.bufs, images=images)
+        P = self.plan.ops
+        i = 0
+        while i < len(P):
+            # a unit's branch -- 1x1 conv, depthwise 3x3, interleaving 1x1 conv -- runs as ONE kernel where the fused kernels take it
+            if (i + 2 < len(P) and P[i].kind == "pw" and P[i + 1].kind == "dw" and P[i + 2].kind == "pw" and
+                    P[i + 1].a["in_t"] == P[i].a["out_t"] and P[i + 2].a["in_t"] == P[i + 1].a["out_t"] and P[i + 2].a["pass_t"] >= 0):
+                out = ops.run_unit(self.plan, P[i], P[i + 1], P[i + 2], self.bufs)
+                if out is not None:
+                    i += 3
+                    continue
+            out = ops.run_op(self.plan, P[i], self.bufs, images=images)
+            i += 1
         return out
 
     def result(self, t, up=0):

@@ -220,6 +220,31 @@ extern "C" int cdn_pw_gemm_i8(const int8_t* d_in, int in_pitch, int64_t pixels, 
   return r;
 }
 
+extern "C" int cdn_shuffle_unit_i8(const int8_t* d_x, int x_pitch, int batch, int H, int W, int stride,
+                                   const cdn_pw_desc* pw1, const int8_t* dw_wq, int dw_C, int dw_zx, const cdn_requant* dw_rq,
+                                   const cdn_pw_desc* pw3, const int8_t* d_pass, int pass_pitch,
+                                   int8_t* d_out, int out_pitch, cdn_stream_t stream) {
+  CDN_CHECK(d_x && pw1 && dw_wq && dw_rq && pw3 && d_pass && d_out, CDN_ERR_INVALID, "shuffle unit: null argument");
+  CDN_CHECK(stride == 1 || stride == 2, CDN_ERR_INVALID, "shuffle unit: stride must be 1 or 2");
+  PwDevice a{}, c{}; DwDevice b{};
+  const int mid_pitch = (pw1->N + 31) / 32 * 32;
+  int r = pw_device_build(a, pw1, 0);
+  if (!r) r = dw_device_build(b, dw_wq, nullptr, dw_C, mid_pitch, dw_zx, dw_rq);
+  if (!r) r = pw_device_build(c, pw3, pass_pitch);
+  if (!r) {
+    const bool ok = stride == 1 ? (d_pass == d_x && unit_fused_ok(a, b, c, x_pitch, mid_pitch, out_pitch, H, W))
+                                : unit_s2_fused_ok(a, b, c, x_pitch, mid_pitch, pass_pitch, out_pitch, H, W);
+    if (!ok) r = cdn_fail(CDN_ERR_INVALID, "unit not fusable: stride %d, pitches %d / %d / %d, map %dx%d (DESIGN.md 4.1b lists what the fused kernels take)",
+                          stride, x_pitch, mid_pitch, out_pitch, H, W);
+    else if (stride == 1) r = unit_fused_launch(a, b, c, d_x, d_out, mid_pitch, batch, H, W, dw_zx, nullptr, nullptr, (cudaStream_t)stream);
+    else r = unit_s2_fused_launch(a, b, c, d_x, d_pass, pass_pitch, d_out, batch, H, W, dw_zx, nullptr, nullptr, (cudaStream_t)stream);
+  }
+  cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+  if (!r && e != cudaSuccess) r = cdn_fail(CDN_ERR_CUDA, "shuffle unit: %s", cudaGetErrorString(e));
+  pw_device_free(a); pw_device_free(c); dw_device_free(b);
+  return r;
+}
+
 // ---- persistent fused deformable layer (constants uploaded once; used by the layer sweep and by integrations that
 // keep the reference's module structure) ------------------------------------------------------------------------------
 struct cdn_deform_layer { DwDevice dw; cdn_deform_scale sc; std::vector<int8_t> ws; int C, Cp, zx, device; };

@@ -78,6 +78,34 @@ def run_op(plan, op, bufs, images=None, want_sval=False):
     raise ValueError(op.kind)
 
 
+def run_unit(plan, op_pw1, op_dw, op_pw3, bufs):
+    """The three ops of a ShuffleNetV2 unit's branch (1x1 conv, depthwise 3x3, 1x1 conv + cat + channel_shuffle) as ONE kernel
+    through cdn_shuffle_unit_i8 (QuantBaseNode.forward, quant_modules.py:878-907).  Returns the unit's output tensor, or None when
+    the fused kernels do not take this unit's shapes (the caller then runs the three ops one by one)."""
+    import torch
+    L = _lib.load()
+    keep = _lib.Keep()
+    a1, ad, a3 = op_pw1.a, op_dw.a, op_pw3.a
+    if ad["in_shift"] or a3["pass_t"] < 0 or a1["n_f32"] or a3["n_f32"]:
+        return None
+    tin, tpass, tout = plan.tensors[a1["in_t"]], plan.tensors[a3["pass_t"]], plan.tensors[a3["out_t"]]
+    x, pas = bufs[tin.id], bufs[tpass.id]
+    B = x.shape[0]
+    with torch.cuda.device(x.device):
+        stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+        out = torch.zeros((B, tout.H, tout.W, tout.pitch), dtype=torch.int8, device=x.device)
+        rq = keep.requant(ad["M"], ad["B"], ad["lo"])
+        d1, d3 = keep.pw_desc(a1), keep.pw_desc(a3)
+        r = L.cdn_shuffle_unit_i8(_ptr(x), tin.pitch, B, tin.H, tin.W, ad["stride"], C.byref(d1), keep.i8(ad["wq"]), ad["C"], ad["zx"],
+                                  C.byref(rq), C.byref(d3), _ptr(pas), tpass.pitch, _ptr(out), tout.pitch, stream)
+    if r != 0:
+        if L.cdn_last_error().decode().startswith("unit not fusable"):
+            return None
+        _lib.check(r)
+    bufs[tout.id] = out
+    return out
+
+
 def quantize(x, C_, H, W, scale, zero, pitch):
     """fp32 NCHW CUDA tensor -> int8 NHWC [B,H,W,pitch] on the grid (scale, zero): cdn_quantize_f32_i8."""
     import torch

@@ -168,6 +168,23 @@ int cdn_pw_gemm_i8(const int8_t* d_in, int in_pitch, int64_t pixels, const cdn_p
                    const int8_t* d_pass, int pass_pitch, int8_t* d_out, int out_pitch,
                    float* d_out_f32, int pixels_per_image, cdn_stream_t stream);
 
+/* ---- a whole ShuffleNetV2 unit as ONE kernel ----------------------------------------------------------------
+ * QuantBaseNode.forward (portable_quantizer/quant_modules.py:878-907; graph of lib/models/networks/shufflenetv2_dcn.py:57-114):
+ *   branch = conv 1x1 (pw1) + BN + ReLU + QuantAct -> depthwise 3x3 (stride 1 | 2) + BN + QuantAct -> conv 1x1 (pw3) + BN + ReLU +
+ *   QuantAct;  out = channel_shuffle(cat(pass-through, branch))
+ * with the two int8 tensors inside the branch kept in shared memory.  The three layers are described exactly as for
+ * cdn_pw_gemm_i8 / cdn_dw3x3_i8 (pw3 carries the interleaving chunk table); results equal the three separate calls bit for bit.
+ *   stride 1: d_x = [B][H][W][2*Hp] in the half layout (pass-through half at byte 0, branch half at byte Hp = pw1->k_off),
+ *             d_pass = d_x, Hp = 64 or 128, H % 8 == 0, W % 16 == 0
+ *   stride 2: d_x = [B][H][W][32] (24 channels), d_pass = the other branch's output [B][H/2][W/2][pass_pitch], 58 channels per half
+ * Returns CDN_ERR_INVALID with cdn_last_error() starting with "unit not fusable" when the shapes / constants are outside what the
+ * fused kernels take (wider halves, maps that are not a whole number of 8 x 16 tiles, layers without an exact shift-free
+ * requantisation): the caller then issues the three calls. */
+int cdn_shuffle_unit_i8(const int8_t* d_x, int x_pitch, int batch, int H, int W, int stride,
+                        const cdn_pw_desc* pw1, const int8_t* dw_wq, int dw_C, int dw_zx, const cdn_requant* dw_rq,
+                        const cdn_pw_desc* pw3, const int8_t* d_pass, int pass_pitch,
+                        int8_t* d_out, int out_pitch, cdn_stream_t stream);
+
 /* ---- ctdet decode ---------------------------------------------------------------------------------------
  * hm: LOGITS fp32 [batch][cat][H][W]; wh, reg: fp32 [batch][2][H][W] (reg may be NULL -> +0.5).
  * Peaks = elements equal to the max of their 3x3 neighbourhood; the K best by (logit desc, class asc, index asc).

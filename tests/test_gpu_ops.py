@@ -65,6 +65,31 @@ def test_stem_every_layer(sim256):
     _check_ops(sim256, ("stem",), flags=1 << 26)        # the all-fp64 kernel (the definition), bit 26
 
 
+def test_shuffle_unit_op_equals_three_ops(sim256):
+    """cdn_shuffle_unit_i8 (QuantBaseNode.forward as one kernel: unit_fused.cu for the stride-1 units of stages 2 and 3,
+    unit_s2_fused.cu for the main branch of the first stride-2 unit) against the simulated plan, unit by unit through the C ABI;
+    units the fused kernels do not take (stage 4, the stride-2 units of stages 3 and 4) must answer "unit not fusable"."""
+    import torch
+    from codenet_b200 import ops
+    plan, x, T, heads = sim256
+    P = plan.ops
+    fused, refused = [], []
+    for i in range(len(P) - 2):
+        a, b, c = P[i], P[i + 1], P[i + 2]
+        if not (a.kind == "pw" and b.kind == "dw" and c.kind == "pw" and b.a["in_t"] == a.a["out_t"] and c.a["in_t"] == b.a["out_t"]
+                and c.a["pass_t"] >= 0):
+            continue
+        bufs = {t: torch.from_numpy(T[t].astype(np.int8)).cuda() for t in (a.a["in_t"], c.a["pass_t"])}
+        out = ops.run_unit(plan, a, b, c, bufs)
+        if out is None:
+            refused.append(a.name)
+            continue
+        assert int8_mismatch(out.cpu().numpy(), T[c.a["out_t"]]) == 0, a.name
+        fused.append(a.name)
+    assert len(fused) == 11 and fused[0] == "layer1.0.pw1", fused
+    assert sorted(refused) == ["layer2.0.pw1", "layer3.0.pw1", "layer3.1.pw1", "layer3.2.pw1", "layer3.3.pw1"], refused
+
+
 def test_stem_fast_path_equals_fp64_kernel(sim256):
     """stem.cu's guarded fp32 fast path (packed FFMA2 dot product, fp64 re-evaluation of every channel whose value is within the
     derived error bound of a rounding boundary) against the all-fp64 kernel on inputs chosen to stress the guard: ordinary images,
