@@ -9,10 +9,10 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 TAG = sys.argv[1] if len(sys.argv) > 1 else "r01"
-WANT = ["UTCIMMA", "LDTM", "UTCBAR", "UTMALDG", "UTMASTG", "SYNCS", "IDP", "IMAD.HI", "DMUL", "LDG", "LDS", "STS", "STG"]
+WANT = ["UTCIMMA", "LDTM", "UTCBAR", "UTMALDG", "UTMASTG", "SYNCS", "IDP", "IMAD.HI", "FFMA2", "DMUL", "DFMA", "LDG", "LDS", "STS", "STG"]
 out = ["# static SASS mnemonic counts per kernel (cuobjdump -sass of codenet_b200/csrc/*.o, sm_100a); see tools/sass_evidence.py",
        "%-58s " % "kernel" + " ".join("%8s" % w for w in WANT)]
-for obj in ("pw_gemm", "heads_fused", "dw_tma", "dw", "stem", "decode"):
+for obj in ("unit_fused", "unit_s2_fused", "pw_gemm", "heads_fused", "dw_tma", "deform_tile", "dw", "stem", "decode"):
     txt = subprocess.run(["cuobjdump", "-sass", os.path.join(ROOT, "codenet_b200", "csrc", obj + ".o")], capture_output=True, text=True).stdout
     fn, cnt = None, collections.OrderedDict()
     for line in txt.splitlines():
