@@ -443,7 +443,8 @@ int unit_fused_launch(const PwDevice& pw1, const DwDevice& dw, const PwDevice& p
     CDN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, UF_SMEM_LIMIT));
     CDN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   }
-  const int per_sm = std::max(1, std::min<int>(want, (int)(UF_SMEM_LIMIT / (smem + 1024))));
+  int per_sm = std::max(1, std::min<int>(want, (int)(UF_SMEM_LIMIT / (smem + 1024))));
+  if (g_cdn_debug_flags & (1u << 28)) per_sm = std::max(1, per_sm - 1);           // bit 28: one resident CTA fewer per SM (A/B: what residency buys)
   const unsigned blocks = (unsigned)std::min<long long>(ntiles, (long long)cdn_num_sms() * per_sm);
   cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(UF_THREADS); cfg.stream = st; cfg.dynamicSmemBytes = smem;
