@@ -236,6 +236,8 @@ extern "C" int cdn_shuffle_unit_i8(const int8_t* d_x, int x_pitch, int batch, in
                                 : unit_s2_fused_ok(a, b, c, x_pitch, mid_pitch, pass_pitch, out_pitch, H, W);
     if (!ok) r = cdn_fail(CDN_ERR_INVALID, "unit not fusable: stride %d, pitches %d / %d / %d, map %dx%d (DESIGN.md 4.1b lists what the fused kernels take)",
                           stride, x_pitch, mid_pitch, out_pitch, H, W);
+    else if (stride == 1 && unit_fused_ws_ok(a, b, c, x_pitch, mid_pitch, out_pitch, H, W))
+      r = unit_fused_ws_launch(a, b, c, d_x, d_out, batch, H, W, dw_zx, nullptr, nullptr, (cudaStream_t)stream);
     else if (stride == 1) r = unit_fused_launch(a, b, c, d_x, d_out, mid_pitch, batch, H, W, dw_zx, nullptr, nullptr, (cudaStream_t)stream);
     else r = unit_s2_fused_launch(a, b, c, d_x, d_pass, pass_pitch, d_out, batch, H, W, dw_zx, nullptr, nullptr, (cudaStream_t)stream);
   }
@@ -582,8 +584,12 @@ static int engine_enqueue(cdn_engine* e, const void* d_img, int is_u8, int batch
       // a whole stride-1 unit as one kernel; the two int8 tensors inside it are written only on request (fuse_units = 2)
       const EngOp *dwo = e->ops[oi + 1], *p3 = e->ops[oi + 2];
       const EngTensor &tx = e->tensors[op->in_t], &t1 = e->tensors[op->out_t], &t2 = e->tensors[dwo->out_t], &to = e->tensors[p3->out_t];
-      r = unit_fused_launch(op->pw, dwo->dw, p3->pw, tx.ptr, to.ptr, t1.pitch, batch, tx.H, tx.W, dwo->zx,
-                            e->fuse_units == 2 ? t1.ptr : nullptr, e->fuse_units == 2 ? t2.ptr : nullptr, st);
+      if (unit_fused_ws_ok(op->pw, dwo->dw, p3->pw, tx.pitch, t1.pitch, to.pitch, tx.H, tx.W))
+        r = unit_fused_ws_launch(op->pw, dwo->dw, p3->pw, tx.ptr, to.ptr, batch, tx.H, tx.W, dwo->zx,
+                                 e->fuse_units == 2 ? t1.ptr : nullptr, e->fuse_units == 2 ? t2.ptr : nullptr, st);
+      else
+        r = unit_fused_launch(op->pw, dwo->dw, p3->pw, tx.ptr, to.ptr, t1.pitch, batch, tx.H, tx.W, dwo->zx,
+                              e->fuse_units == 2 ? t1.ptr : nullptr, e->fuse_units == 2 ? t2.ptr : nullptr, st);
       if (r) return r;
       launches++;
       mark(); mark(); mark();                // the other two ops of the unit take no time of their own

@@ -74,6 +74,10 @@ int heads_fused_launch(const DwDevice& dw, const PwDevice& pw, const int8_t* in,
 bool unit_fused_ok(const PwDevice& pw1, const DwDevice& dw, const PwDevice& pw3, int x_pitch, int mid_pitch, int out_pitch, int H, int W);
 int unit_fused_launch(const PwDevice& pw1, const DwDevice& dw, const PwDevice& pw3, const int8_t* x, int8_t* out, int HP,
                       int batch, int H, int W, int zx_mid, int8_t* dump_c1, int8_t* dump_d2, cudaStream_t st);
+// the same unit, warp-specialised (unit_fused_ws.cu): the phases of consecutive tiles on different warps, 116 / 122-channel halves
+bool unit_fused_ws_ok(const PwDevice& pw1, const DwDevice& dw, const PwDevice& pw3, int x_pitch, int mid_pitch, int out_pitch, int H, int W);
+int unit_fused_ws_launch(const PwDevice& pw1, const DwDevice& dw, const PwDevice& pw3, const int8_t* x, int8_t* out,
+                         int batch, int H, int W, int zx_mid, int8_t* dump_c1, int8_t* dump_d2, cudaStream_t st);
 int make_tmap_nhwc_swz(CUtensorMap* m, const void* base, uint64_t pitch, uint64_t W, uint64_t H, uint64_t batch,
                        uint32_t box_c, uint32_t box_w, uint32_t box_h);
 // the branch of the FIRST stride-2 unit (1x1 conv at full resolution, depthwise 3x3 stride 2, 1x1 conv + cat + channel shuffle)
