@@ -241,11 +241,17 @@ def test_units_fused_equal_separate_kernels(calib, res, batch):
     assert eng.num_launches == n_launch0 - 2 * n_fused
     eng.set_option("fuse_units", 1)                     # the default: nothing inside the units is written
     outer = [k for k in labels if k not in inner]
-    got = snapshot(outer)
-    for k in outer:
-        assert int8_mismatch(got[0][k], ref[0][k]) == 0, k
-    for a, b in zip(got[1:], ref[1:]):
-        np.testing.assert_array_equal(a, b)
+    # default kernels (warp-specialised for the wide stage), then the barrier-phased kernel everywhere (debug bit 29), then the
+    # table-driven variants with the shifted requantisation (bit 22) -- all must give the same bits
+    for flags in (0, 1 << 29, (1 << 29) | (1 << 22)):
+        _lib.load().cdn_set_debug_flags(flags)
+        eng.set_option("use_graph", 0)
+        got = snapshot(outer)
+        for k in outer:
+            assert int8_mismatch(got[0][k], ref[0][k]) == 0, (k, flags)
+        for a, b in zip(got[1:], ref[1:]):
+            np.testing.assert_array_equal(a, b)
+    _lib.load().cdn_set_debug_flags(0)
     eng.close()
 
 
