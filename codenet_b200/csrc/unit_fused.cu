@@ -6,8 +6,9 @@
 // (C = channels of the stage tensor) and pays three launch ramps; here it reads C (+ the halo) and writes C, and the two int8
 // tensors between the convs never leave the SM.  The arithmetic is that of the three kernels, bit for bit.
 //
-// A CTA (256 threads, two per SM so that one CTA's tensor / TMA waits hide behind the other's CUDA-core phases) walks over
-// tiles of 8 x 16 output pixels:
+// A CTA (256 threads; three per SM for 58-channel halves, two for 116: one CTA's tensor / TMA waits hide behind the others' CUDA-core
+// phases -- the wide stage normally runs the warp-specialised form of this kernel, unit_fused_ws.cu) walks over tiles of 8 x 16
+// output pixels:
 //   A1  the branch half x2 of the tile's 10 x 18 input pixels (tile + one-pixel halo) arrives by ONE 4-D TMA load in the UMMA
 //       K-major 128B-swizzled layout (row = pixel r*18 + c): it IS the A operand of the first GEMM
 //   G1  two tcgen05.mma blocks (M = 128 each: rows 0..127 and 64..191 of the 180) against the resident pw1 weights -> TMEM
@@ -19,7 +20,9 @@
 //   E2  all warps: TMEM -> requantisation -> bytes interleaved with the pass-through half x1 (its tile arrives by its own TMA
 //       load) through the layer's chunk table = cat + channel_shuffle -> 128B-swizzled staging -> 4-D TMA store
 // The next tile's A1 load is issued as soon as its buffer is free, so it flies during S / G2 / E2 (or, when `mid` has its own
-// buffer, during E1 as well); the next pass-through tile is requested right after E2.
+// buffer, during E1 as well); the next pass-through tile is requested right after E2.  The elected lane of warp 0 issues the MMAs
+// and polls their mbarrier, the elected lane of warp 1 issues every TMA load / store; all other threads sleep in bar.sync.
+// PG > 0 variants hard-wire the interleave (PG channels per output group) and the shift-free requantisation; PG = 0 is table-driven.
 #include "unit_fused.cuh"
 #include <algorithm>
 
