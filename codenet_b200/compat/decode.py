@@ -11,6 +11,8 @@ import torch
 
 from .. import _lib
 
+_WS = {}
+
 
 def ctdet_decode(heat, wh, reg=None, cat_spec_wh=False, K=100):
     if cat_spec_wh:
@@ -24,9 +26,14 @@ def ctdet_decode(heat, wh, reg=None, cat_spec_wh=False, K=100):
         raise RuntimeError("ctdet_decode: wh / reg must be [B,2,H,W] matching heat {}".format(tuple(heat.shape)))
     dets = torch.empty((batch, K, 6), dtype=torch.float32, device=heat.device)
     L = _lib.load()
+    need = int(L.cdn_ctdet_decode_ws_bytes(batch, cat, height, width))
+    ws = _WS.get(heat.device)
+    if ws is None or ws.numel() < need:              # candidate buffer kept between calls: the call only enqueues kernels
+        ws = _WS[heat.device] = torch.empty(need, dtype=torch.uint8, device=heat.device)
     stream = C.c_void_p(torch.cuda.current_stream(heat.device).cuda_stream)
     with torch.cuda.device(heat.device):
-        _lib.check(L.cdn_ctdet_decode_prob(C.c_void_p(heat_c.data_ptr()), C.c_void_p(wh_c.data_ptr()),
-                                           C.c_void_p(reg_c.data_ptr()) if reg_c is not None else None,
-                                           batch, cat, height, width, K, C.c_void_p(dets.data_ptr()), None, stream))
+        _lib.check(L.cdn_ctdet_decode_ws(C.c_void_p(heat_c.data_ptr()), 0, C.c_void_p(wh_c.data_ptr()), 0,
+                                         C.c_void_p(reg_c.data_ptr()) if reg_c is not None else None, 0,
+                                         batch, cat, height, width, K, 1, C.c_void_p(dets.data_ptr()), None,
+                                         C.c_void_p(ws.data_ptr()), ws.numel(), stream))
     return dets

@@ -292,6 +292,27 @@ static int decode_standalone(const float* d_hm, const float* d_wh, const float* 
   cudaFree(scratch);
   return r;
 }
+extern "C" size_t cdn_ctdet_decode_ws_bytes(int batch, int cat, int H, int W) {
+  if (batch < 0 || cat < 1 || H < 1 || W < 1) return 0;
+  size_t n = (size_t)batch * cat * H * W;
+  return (n ? n : 1) * sizeof(unsigned long long) + ((size_t)batch + 1) * sizeof(unsigned int);
+}
+extern "C" int cdn_ctdet_decode_ws(const float* d_hm, long long hm_img_stride, const float* d_wh, long long wh_img_stride,
+                                   const float* d_reg, long long reg_img_stride, int batch, int cat, int H, int W,
+                                   int K, int is_prob, float* d_dets, int32_t* d_inds, void* d_ws, size_t ws_bytes,
+                                   cdn_stream_t stream) {
+  CDN_CHECK(batch >= 0 && cat >= 1 && H >= 1 && W >= 1, CDN_ERR_INVALID, "decode: bad shape");
+  CDN_CHECK(d_ws && ((uintptr_t)d_ws & 7) == 0 && ws_bytes >= cdn_ctdet_decode_ws_bytes(batch, cat, H, W), CDN_ERR_INVALID,
+            "decode: workspace of %zu bytes (8-byte aligned) needed, got %zu", cdn_ctdet_decode_ws_bytes(batch, cat, H, W), ws_bytes);
+  size_t n = (size_t)batch * cat * H * W;
+  long long hw = (long long)H * W;
+  CDN_CHECK((!hm_img_stride || hm_img_stride >= cat * hw) && (!wh_img_stride || wh_img_stride >= 2 * hw) &&
+            (!reg_img_stride || reg_img_stride >= 2 * hw), CDN_ERR_INVALID, "decode: image stride smaller than one image");
+  unsigned long long* scratch = (unsigned long long*)d_ws;
+  return decode_launch(d_hm, hm_img_stride ? hm_img_stride : cat * hw, d_wh, wh_img_stride ? wh_img_stride : 2 * hw, d_reg,
+                       reg_img_stride ? reg_img_stride : 2 * hw, batch, cat, H, W, K, is_prob, scratch,
+                       (unsigned int*)(scratch + (n ? n : 1)), d_dets, d_inds, (cudaStream_t)stream);
+}
 extern "C" int cdn_ctdet_decode(const float* d_hm, const float* d_wh, const float* d_reg, int batch, int cat, int H, int W,
                                 int K, float* d_dets, int32_t* d_inds, cdn_stream_t stream) {
   return decode_standalone(d_hm, d_wh, d_reg, batch, cat, H, W, K, 0, d_dets, d_inds, stream);

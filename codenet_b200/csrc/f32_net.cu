@@ -199,11 +199,12 @@ __global__ void __launch_bounds__(128) pw_slice_f32_kernel(const float* __restri
 #define PWT_CO 64
 #define PWT_PX 128
 #define PWT_K 16
+template <bool F2>
 __global__ void __launch_bounds__(256, 2) pw_tile_f32_kernel(const float* __restrict__ in, int in_ctotal, int in_coff, int C,
                                                           const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out,
                                                           int out_ctotal, int out_coff, int out_cstride, int Co, int relu, int ppi) {
   __shared__ __align__(16) float sA[2][PWT_K][PWT_CO];          // weights, [k][co]
-  __shared__ __align__(16) float sB[2][PWT_K][PWT_PX];          // activations, [k][pixel]
+  __shared__ __align__(16) float sB[2][PWT_K][(F2 ? 2 : 1) * PWT_PX];   // activations, [k][pixel]; F2: every value stored twice = the (v, v) operand of FFMA2
   const int tiles_per_img = ppi / PWT_PX;
   const int b = blockIdx.x / tiles_per_img, px0 = (blockIdx.x - b * tiles_per_img) * PWT_PX;
   const int co0 = blockIdx.y * PWT_CO;
@@ -225,8 +226,15 @@ __global__ void __launch_bounds__(256, 2) pw_tile_f32_kernel(const float* __rest
   auto sstore = [&](int buf) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) sA[buf][a_k + i][a_r] = ra[i];
-    *(float4*)&sB[buf][b_k][b_p] = rb0;
-    *(float4*)&sB[buf][b_k + 8][b_p] = rb1;
+    if constexpr (F2) {
+      *(float4*)&sB[buf][b_k][2 * b_p] = make_float4(rb0.x, rb0.x, rb0.y, rb0.y);
+      *(float4*)&sB[buf][b_k][2 * b_p + 4] = make_float4(rb0.z, rb0.z, rb0.w, rb0.w);
+      *(float4*)&sB[buf][b_k + 8][2 * b_p] = make_float4(rb1.x, rb1.x, rb1.y, rb1.y);
+      *(float4*)&sB[buf][b_k + 8][2 * b_p + 4] = make_float4(rb1.z, rb1.z, rb1.w, rb1.w);
+    } else {
+      *(float4*)&sB[buf][b_k][b_p] = rb0;
+      *(float4*)&sB[buf][b_k + 8][b_p] = rb1;
+    }
   };
   double tot[8][4];
 #pragma unroll
@@ -235,11 +243,16 @@ __global__ void __launch_bounds__(256, 2) pw_tile_f32_kernel(const float* __rest
 #pragma unroll
     for (int q = 0; q < 4; ++q) tot[r][q] = bv;
   }
+  // F2 (debug bit 30, A/B only): two output channels per instruction with Blackwell's packed fp32 FMA -- per lane the same
+  // operations in the same order as the scalar form, identical bits, half the FMA issue slots; acc2[rp][q] = (channel 2 rp,
+  // channel 2 rp + 1) of pixel q.  Measured SLOWER (60.2 vs 42.5 ms per 128-image forward of the 2x COCO model): the (v, v)
+  // operand doubles the activation tile's shared-memory reads and the kernel is bound there, not on FMA issue.
+  unsigned long long acc2[4][4];
   float acc[8][4];
 #pragma unroll
-  for (int r = 0; r < 8; ++r)
+  for (int r = 0; r < 4; ++r)
 #pragma unroll
-    for (int q = 0; q < 4; ++q) acc[r][q] = 0.f;
+    for (int q = 0; q < 4; ++q) { acc2[r][q] = 0ull; acc[2 * r][q] = acc[2 * r + 1][q] = 0.f; }
   const int nchunks = (C + PWT_K - 1) / PWT_K;
   gload(0); sstore(0);
   __syncthreads();
@@ -248,20 +261,42 @@ __global__ void __launch_bounds__(256, 2) pw_tile_f32_kernel(const float* __rest
     if (ch + 1 < nchunks) gload((ch + 1) * PWT_K);              // next chunk's global loads fly during this chunk's FMAs
 #pragma unroll
     for (int k = 0; k < PWT_K; ++k) {
-      const float4 wa = *(const float4*)&sA[buf][k][ty * 8], wb = *(const float4*)&sA[buf][k][ty * 8 + 4];
-      const float4 v = *(const float4*)&sB[buf][k][tx * 4];
-      const float ww[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-      const float vv[4] = {v.x, v.y, v.z, v.w};
+      if constexpr (F2) {
+        const ulonglong2 wa = *(const ulonglong2*)&sA[buf][k][ty * 8], wb = *(const ulonglong2*)&sA[buf][k][ty * 8 + 4];
+        const ulonglong2 va = *(const ulonglong2*)&sB[buf][k][tx * 8], vb = *(const ulonglong2*)&sB[buf][k][tx * 8 + 4];
+        const unsigned long long ww[4] = {wa.x, wa.y, wb.x, wb.y};
+        const unsigned long long vv[4] = {va.x, va.y, vb.x, vb.y};
 #pragma unroll
-      for (int r = 0; r < 8; ++r)
+        for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) acc[r][q] = fmaf(ww[r], vv[q], acc[r][q]);
+          for (int q = 0; q < 4; ++q)
+            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[r][q]) : "l"(ww[r]), "l"(vv[q]));
+      } else {
+        const float4 wa = *(const float4*)&sA[buf][k][ty * 8], wb = *(const float4*)&sA[buf][k][ty * 8 + 4];
+        const float4 v = *(const float4*)&sB[buf][k][tx * 4];
+        const float ww[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[r][q] = fmaf(ww[r], vv[q], acc[r][q]);
+      }
     }
     if ((ch & 1) == 1 || ch + 1 == nchunks) {                   // a block of 32 input channels is complete
 #pragma unroll
-      for (int r = 0; r < 8; ++r)
+      for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { tot[r][q] += (double)acc[r][q]; acc[r][q] = 0.f; }
+        for (int q = 0; q < 4; ++q) {
+          if constexpr (F2) {
+            tot[2 * r][q] += (double)__uint_as_float((uint32_t)acc2[r][q]);
+            tot[2 * r + 1][q] += (double)__uint_as_float((uint32_t)(acc2[r][q] >> 32));
+            acc2[r][q] = 0ull;
+          } else {
+            tot[2 * r][q] += (double)acc[2 * r][q];
+            tot[2 * r + 1][q] += (double)acc[2 * r + 1][q];
+            acc[2 * r][q] = acc[2 * r + 1][q] = 0.f;
+          }
+        }
     }
     if (ch + 1 < nchunks) sstore(buf ^ 1);                      // the other buffer was last read in the previous iteration
     __syncthreads();
@@ -290,8 +325,12 @@ extern "C" int cdn_pw_slice_f32(const float* input, int in_ctotal, int in_coff, 
   if (total == 0) return 0;
   if (pixels_per_image % PWT_PX == 0 && (long long)B * (pixels_per_image / PWT_PX) < (1ll << 31)) {
     dim3 grid((unsigned)(B * (pixels_per_image / PWT_PX)), (unsigned)((Co + PWT_CO - 1) / PWT_CO));
-    pw_tile_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(input, in_ctotal, in_coff, C, weight, bias, output, out_ctotal, out_coff,
-                                                              out_cstride, Co, relu, pixels_per_image);
+    if (!(g_cdn_debug_flags & (1u << 30)))
+      pw_tile_f32_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(input, in_ctotal, in_coff, C, weight, bias, output, out_ctotal,
+                                                                       out_coff, out_cstride, Co, relu, pixels_per_image);
+    else
+      pw_tile_f32_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(input, in_ctotal, in_coff, C, weight, bias, output, out_ctotal,
+                                                                      out_coff, out_cstride, Co, relu, pixels_per_image);
     CDN_LAUNCH_CHECK("pw_tile_f32_kernel");
     return 0;
   }

@@ -45,6 +45,7 @@ class EngineF32:
         self.g = build_graph(cfg)
         st = {k: (v.detach().cpu().numpy() if hasattr(v, "detach") else np.asarray(v)) for k, v in state.items()}
         self.P = {}
+        self._dec_ws = None                     # ctdet decode candidate buffer, grown on demand
         self.scale_bias = {}                    # host copies of the offset-scale conv biases (kernel arguments by value)
         for c in self.g.all_convs():
             w, b = _fold(st, c)
@@ -143,15 +144,24 @@ class EngineF32:
         self._heads = heads
         return views
 
-    def detect(self, x):
-        """forward + ctdet decode (lib/detectors/ctdet.py:31-41 without flip): dets [B,K,6], heads views."""
+    def detect(self, x, out=None):
+        """forward + ctdet decode (lib/detectors/ctdet.py:31-41 without flip): dets [B,K,6], heads views.  The decode reads the
+        head tensors as channel slices of the one [B, n_out, H, W] buffer the forward wrote (no copies) and takes its candidate
+        buffer from a workspace kept between calls, so the whole call only enqueues kernels and can be captured in a CUDA graph
+        (`out` = (dets, inds) to write into fixed buffers)."""
         torch = self.torch
         v = self.forward(x)
-        hm, wh = v["hm"].contiguous(), v["wh"].contiguous()
-        reg = v["reg"].contiguous() if "reg" in v else None
+        hm, wh, reg = v["hm"], v["wh"], v.get("reg")
         B, cat, H, W = hm.shape
-        dets = torch.empty((B, self.K, 6), dtype=torch.float32, device=self.dev)
-        inds = torch.empty((B, self.K), dtype=torch.int32, device=self.dev)
+        for t in (hm, wh) + ((reg,) if reg is not None else ()):
+            assert t.stride()[1:] == (H * W, W, 1), "head views must be channel slices of a contiguous tensor"
+        dets, inds = out if out is not None else (torch.empty((B, self.K, 6), dtype=torch.float32, device=self.dev),
+                                                  torch.empty((B, self.K), dtype=torch.int32, device=self.dev))
+        need = int(self.lib.cdn_ctdet_decode_ws_bytes(B, cat, H, W))
+        if self._dec_ws is None or self._dec_ws.numel() < need:
+            self._dec_ws = torch.empty(need, dtype=torch.uint8, device=self.dev)
         with torch.cuda.device(self.dev):
-            _lib.check(self.lib.cdn_ctdet_decode(self._p(hm), self._p(wh), self._p(reg), B, cat, H, W, self.K, self._p(dets), self._p(inds), self._st()))
+            _lib.check(self.lib.cdn_ctdet_decode_ws(self._p(hm), hm.stride(0), self._p(wh), wh.stride(0), self._p(reg),
+                                                    reg.stride(0) if reg is not None else 0, B, cat, H, W, self.K, 0, self._p(dets),
+                                                    self._p(inds), self._p(self._dec_ws), self._dec_ws.numel(), self._st()))
         return dets, inds, v

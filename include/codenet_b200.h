@@ -196,6 +196,14 @@ int cdn_ctdet_decode(const float* d_hm, const float* d_wh, const float* d_reg, i
  * hm.sigmoid_(), lib/detectors/ctdet.py:32): peaks, order and the score written are taken from the values as given. */
 int cdn_ctdet_decode_prob(const float* d_heat, const float* d_wh, const float* d_reg, int batch, int cat, int H, int W,
                           int K, float* d_dets, int32_t* d_inds, cdn_stream_t stream);
+/* The two calls above allocate their candidate buffer per call and wait for the stream.  The _ws form takes the buffer from
+ * the caller (cdn_ctdet_decode_ws_bytes bytes, 8-byte aligned), only enqueues work on `stream`, and can therefore be captured
+ * into a CUDA graph; is_prob selects between the two input conventions.  *_img_stride: distance between two images of that
+ * tensor in floats (0 = contiguous), so that the three tensors may be channel slices of one [batch][C][H][W] head tensor. */
+size_t cdn_ctdet_decode_ws_bytes(int batch, int cat, int H, int W);
+int cdn_ctdet_decode_ws(const float* d_hm, long long hm_img_stride, const float* d_wh, long long wh_img_stride,
+                        const float* d_reg, long long reg_img_stride, int batch, int cat, int H, int W,
+                        int K, int is_prob, float* d_dets, int32_t* d_inds, void* d_ws, size_t ws_bytes, cdn_stream_t stream);
 
 /* ctdet_post_process's coordinate transform on the device (lib/utils/post_process.py:86-103, transform_preds /
  * affine_transform lib/utils/image.py:14-21,58-61): both corners of every box of dets [batch][K][6] (in place) go through

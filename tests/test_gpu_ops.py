@@ -308,6 +308,34 @@ def test_decode_kat_gpu(golden, name):
         np.testing.assert_array_equal(d[..., 5], ref[..., 5])
 
 
+def test_decode_workspace_form_on_channel_slices():
+    """cdn_ctdet_decode_ws on three channel slices of one [B, C, H, W] head tensor (image strides, caller's workspace, no stream
+    wait) = cdn_ctdet_decode on contiguous copies, bit for bit; too small a workspace is refused."""
+    import ctypes as C
+    import torch
+    from gpu_util import ptr, stream
+    rng = np.random.default_rng(5)
+    Bn, cat, H, W, K = 4, 20, 64, 64, 100
+    heads = torch.from_numpy(rng.normal(-2, 2, (Bn, cat + 4, H, W)).astype(np.float32)).cuda()
+    hm, wh, reg = heads[:, :cat], heads[:, cat:cat + 2], heads[:, cat + 2:]
+    L = _lib.load()
+    want_d, want_i = torch.zeros((Bn, K, 6), device="cuda"), torch.zeros((Bn, K), dtype=torch.int32, device="cuda")
+    hc, wc, rc = hm.contiguous(), wh.contiguous(), reg.contiguous()
+    _lib.check(L.cdn_ctdet_decode(ptr(hc), ptr(wc), ptr(rc), Bn, cat, H, W, K, ptr(want_d), ptr(want_i), stream()))
+    need = int(L.cdn_ctdet_decode_ws_bytes(Bn, cat, H, W))
+    assert need == Bn * cat * H * W * 8 + (Bn + 1) * 4
+    ws = torch.empty(need, dtype=torch.uint8, device="cuda")
+    for it in range(2):                                               # second call: the workspace is re-used as it was left
+        got_d, got_i = torch.zeros_like(want_d), torch.zeros_like(want_i)
+        _lib.check(L.cdn_ctdet_decode_ws(ptr(hm), hm.stride(0), ptr(wh), wh.stride(0), ptr(reg), reg.stride(0), Bn, cat, H, W, K, 0,
+                                         ptr(got_d), ptr(got_i), ptr(ws), need, stream()))
+        torch.cuda.synchronize()
+        assert torch.equal(got_i, want_i) and torch.equal(got_d, want_d)
+    assert L.cdn_ctdet_decode_ws(ptr(hm), hm.stride(0), ptr(wh), wh.stride(0), ptr(reg), reg.stride(0), Bn, cat, H, W, K, 0,
+                                 ptr(got_d), ptr(got_i), ptr(ws), need - 8, stream()) == -1
+    assert b"workspace" in L.cdn_last_error()
+
+
 @pytest.mark.parametrize("cat,H,W,K,levels", [(20, 64, 64, 100, 37), (80, 32, 48, 100, 500), (3, 16, 16, 40, 5), (1, 8, 8, 100, 3),
                                               (20, 128, 128, 100, 2000)])
 def test_decode_with_ties(cat, H, W, K, levels):
