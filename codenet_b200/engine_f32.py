@@ -35,7 +35,7 @@ def _fold(st, c, eps=1e-5):
 
 
 class EngineF32:
-    def __init__(self, cfg: NetConfig, state: Dict[str, np.ndarray], device: int = 0, K: int = 100):
+    def __init__(self, cfg: NetConfig, state: Dict[str, np.ndarray], device: int = 0, K: int = 100, gemm: str = "fp32"):
         import torch
         self.torch = torch
         self.cfg, self.K = cfg, int(K)
@@ -44,7 +44,13 @@ class EngineF32:
         self.dev = torch.device("cuda", device)
         self.g = build_graph(cfg)
         st = {k: (v.detach().cpu().numpy() if hasattr(v, "detach") else np.asarray(v)) for k, v in state.items()}
+        assert gemm in ("tf32x3", "fp32"), gemm
+        # 1x1 convs: "fp32" = SIMT fp32 products with fp64 block sums (tightest: half the reference's own fp32-vs-fp64 deviation);
+        # "tf32x3" = tensor cores with a 3-way TF32 split (pw_tf32.cu): 1.7x the throughput of the whole model, deviation at the
+        # level of the reference's own fp32 evaluation (tests/test_gpu_f32.py states both bounds)
+        self.gemm = gemm
         self.P = {}
+        self.Ptc = {}                           # name -> (w_hi, w_lo) packed for cdn_pw_slice_tf32x3
         self._dec_ws = None                     # ctdet decode candidate buffer, grown on demand
         self.scale_bias = {}                    # host copies of the offset-scale conv biases (kernel arguments by value)
         for c in self.g.all_convs():
@@ -53,6 +59,13 @@ class EngineF32:
                 self.scale_bias[c.name] = float(b[0])
             self.P[c.name] = (torch.from_numpy(np.ascontiguousarray(w.reshape(c.cout, -1))).to(self.dev),
                               torch.from_numpy(np.ascontiguousarray(b)).to(self.dev))
+            if gemm == "tf32x3" and c.kind in ("pw", "head_out") and c.k == 1:
+                wd = self.P[c.name][0]
+                n = int(self.lib.cdn_pw_tf32x3_packed_floats(wd.shape[0], wd.shape[1]))
+                hi, lo = torch.empty(n, dtype=torch.float32, device=self.dev), torch.empty(n, dtype=torch.float32, device=self.dev)
+                with torch.cuda.device(self.dev):
+                    _lib.check(self.lib.cdn_pw_tf32x3_pack(self._p(wd), wd.shape[0], wd.shape[1], self._p(hi), self._p(lo), self._st()))
+                self.Ptc[c.name] = (hi, lo)
 
     # -- thin kernel wrappers ---------------------------------------------------------------------------------------------
     def _st(self):
@@ -65,6 +78,11 @@ class EngineF32:
     def _pw(self, x, in_off, cin, name, out, out_off, out_stride, relu):
         w, b = self.P[name]
         B, ct, H, W = x.shape
+        if name in self.Ptc and (H * W) % 256 == 0 and w.shape[1] == cin:
+            hi, lo = self.Ptc[name]
+            _lib.check(self.lib.cdn_pw_slice_tf32x3(self._p(x), ct, in_off, cin, self._p(hi), self._p(lo), self._p(b), self._p(out), out.shape[1],
+                                                    out_off, out_stride, w.shape[0], 1 if relu else 0, B, H * W, self._st()))
+            return
         _lib.check(self.lib.cdn_pw_slice_f32(self._p(x), ct, in_off, cin, self._p(w), self._p(b), self._p(out), out.shape[1], out_off,
                                              out_stride, w.shape[0], 1 if relu else 0, B, H * W, self._st()))
 

@@ -64,7 +64,8 @@ def run_ours(args, C):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     raw, g = _state()
-    eng = EngineF32(_cfg(), raw, device=local)
+    gemm = os.environ.get("CODENET_F32_GEMM", "tf32x3")           # "fp32" = the SIMT kernel with fp64 block sums (strict accuracy mode)
+    eng = EngineF32(_cfg(), raw, device=local, gemm=gemm)
     B, R = args.batch or C["batch"], C["res"]
     base = make_images(8, R, seed=100 + rank)
     host = torch.from_numpy(np.concatenate([base] * ((B + 7) // 8))[:B].copy()).pin_memory()
@@ -155,7 +156,8 @@ def run_ours(args, C):
                 "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "codenet_b200",
                 "config": {"workload": C["workload"] % B, "name": "2x_fp32", "batch_per_gpu": B, "offset_mode": "bilinear",
-                           "arithmetic": "fp32 (1x1 convs: SIMT fp32 with two-level fp32 -> fp64 accumulation)",
+                           "arithmetic": ("fp32; 1x1 convs on tcgen05 kind::tf32 with a 3-way split (hi*hi + hi*lo + lo*hi), 16-channel chunk sums added in fp32 registers"
+                                          if gemm == "tf32x3" else "fp32 (1x1 convs: SIMT fp32 with two-level fp32 -> fp64 accumulation)"), "gemm": gemm,
                            "parallelism": "batch-sharded, no collective",
                            "l2": "inputs larger than L2 (%.0f MB fp32 images per step)" % (B * 3 * R * R * 4 / 1e6),
                            "launch": "CUDA graph" if graph is not None else "eager (%s)" % static.get("graph_error", "")},
