@@ -4,6 +4,7 @@
 // buffer, no per-group GEMM and no transposed copy.  One thread per output element; lanes run along W so the
 // offset reads and the output store are coalesced.
 #include "common.cuh"
+#include <algorithm>
 
 struct DefF32Params {
   const float* in; const float* w; const float* off; float* out;
@@ -84,85 +85,140 @@ extern "C" int cdn_deform_conv_forward_f32(const float* input, const float* weig
 //   DeformConvWithOffsetScaleBoundPositive.forward, lib/models/external/modules/dcn_deform_conv.py:323-330 --
 //   s = Hardtanh[-bound+1, bound](conv1x1_{C->1, stride}(x) + bias);  o = anchor * (s - 1);
 //   y = deform_conv(x, o, W_dw[C,1,3,3], stride, pad 1, groups = C)
-// in ONE kernel: one thread per output pixel (lanes along W: coalesced NCHW rows).  The scale scalar is reduced over
-// the channels first; the 9 taps then share their sample geometry across all channels -- row / column floors and
-// fractions are computed once per pixel and kept in registers (the outer taps sit at (i-1)*s from the centre, the centre
-// row / column is integral), so the 18-channel offset tensor, the im2col buffer and the per-channel GEMMs of the
-// reference (dcn_deform_conv_cuda.cpp:196-245) never exist.  Sampling follows dcn_deform_conv_cuda_kernel.cu:83-114
-// (zero outside the image, per corner).
+// in two launches: the scale scalar per output pixel (8 bytes per pixel of scratch), then the gather -- the 18-channel
+// offset tensor, the im2col buffer and the per-channel GEMMs of the reference (dcn_deform_conv_cuda.cpp:196-245) never
+// exist.  Lanes run along W (coalesced NCHW rows).
 // ---------------------------------------------------------------------------------------------------------
 struct DefDwF32Params {
   const float* in; const float* ws; const float* wdw; float* out;
+  double* sd;                                   // [B][Ho*Wo] clamped scale per output pixel (phase A -> phase B)
   float bs, lo, hi;
   int B, C, H, W, Ho, Wo, stride;
-  long long total;
 };
 
-__global__ void __launch_bounds__(128) deform_dw_f32_kernel(DefDwF32Params p) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= p.total) return;
-  const int wo = (int)(idx % p.Wo); const long long t = idx / p.Wo; const int ho = (int)(t % p.Ho); const int b = (int)(t / p.Ho);
-  const size_t plane = (size_t)p.H * p.W;
-  const float* xb = p.in + (size_t)b * p.C * plane;
-  const int hc = ho * p.stride, wc = wo * p.stride;             // conv_scale has kernel 1, padding 0, stride = stride
-  // The scale scalar moves the sample positions, and the sampled features can vary by O(1) per pixel: an fp32 error
-  // in s is amplified into the output, so the C -> 1 reduction and the positions are kept in fp64 (C DFMA per pixel
-  // against 36 C fp32 operations for the gather: free).
-  double sd = (double)p.bs;
-  for (int c = 0; c < p.C; ++c) sd = fma((double)__ldg(p.ws + c), (double)__ldg(xb + c * plane + (size_t)hc * p.W + wc), sd);
-  sd = fmin(fmax(sd, (double)p.lo), (double)p.hi);
-  const double d = sd - 1.0;
+// Phase A: s = Hardtanh(w_scale . x + b_scale) per output pixel.  The scale scalar moves the sample positions, and the sampled
+// features can vary by O(1) per pixel: an fp32 error in s is amplified into the output, so the C -> 1 reduction is kept in fp64.
+// 32 pixels x 8 channel groups per CTA: a group sums channels g, g + 8, ... (coalesced 128-byte rows of the planes), the eight
+// partial sums are added in a fixed order.
+__global__ void __launch_bounds__(256) deform_scale_f32_kernel(DefDwF32Params p) {
+  __shared__ double part[8][33];
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int npx = p.Ho * p.Wo;
+  const int px = blockIdx.x * 32 + lane, b = blockIdx.y;
+  double sd = 0.0;
+  if (px < npx) {
+    const int ho = px / p.Wo, wo = px - ho * p.Wo;
+    const size_t plane = (size_t)p.H * p.W;
+    const float* x = p.in + (size_t)b * p.C * plane + (size_t)(ho * p.stride) * p.W + wo * p.stride;   // conv_scale: kernel 1, padding 0
+    for (int c = grp; c < p.C; c += 8) sd = fma((double)__ldg(p.ws + c), (double)__ldg(x + c * plane), sd);
+  }
+  part[grp][lane] = sd;
+  __syncthreads();
+  if (grp == 0 && px < npx) {
+    double t = (double)p.bs;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) t += part[g][lane];
+    p.sd[(size_t)b * npx + px] = fmin(fmax(t, (double)p.lo), (double)p.hi);
+  }
+}
+
+// Phase B: one thread = one output pixel x DDF_CG channels.  The 9 taps share their sample geometry across all channels: row /
+// column floors and fractions are computed once per thread (the outer taps sit at (i-1)*(s-1) from the regular position, the
+// centre row / column is integral); corners outside the image get weight 0 and a clamped address, which is the reference's
+// "zero outside the image, per corner" (dcn_deform_conv_cuda_kernel.cu:83-114) without a select per load.  The grid runs over
+// (pixel block, channel group, image): the 16 x 16 layer with 2153 channels gets 69 k CTAs where one thread per pixel looping
+// over every channel (round 1) left the GPU with 220 threads per SM.
+#define DDF_CG 8
+__global__ void __launch_bounds__(128, 4) deform_gather_f32_kernel(DefDwF32Params p) {
+  const int npx = p.Ho * p.Wo;
+  const int px = blockIdx.x * 128 + threadIdx.x, b = blockIdx.z;
+  if (px >= npx) return;
+  const int ho = px / p.Wo, wo = px - ho * p.Wo;
+  const int hc = ho * p.stride, wc = wo * p.stride;
+  const double d = p.sd[(size_t)b * npx + px] - 1.0;
   // sample rows / columns of the three tap rows / columns: h_im = ho*stride - 1 + i + (i - 1)*d
-  int r0[3], c0[3]; float lr[3], lc[3];
+  int ra[3], rb[3], ca[3], cb[3]; float wra[3], wrb[3], wca[3], wcb[3];
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     const double him = (double)(hc - 1 + i) + (double)(i - 1) * d, wim = (double)(wc - 1 + i) + (double)(i - 1) * d;
     const double hf = floor(him), wf = floor(wim);
-    r0[i] = (int)hf; lr[i] = (float)(him - hf); c0[i] = (int)wf; lc[i] = (float)(wim - wf);
+    const int y = (int)hf, x = (int)wf;
+    const float lh = (float)(him - hf), lw = (float)(wim - wf);
     // outside the reference's range test (h_im > -1 && h_im < H): every corner is invalid or has weight zero already
+    wra[i] = ((unsigned)y < (unsigned)p.H) ? 1.f - lh : 0.f;        wrb[i] = ((unsigned)(y + 1) < (unsigned)p.H) ? lh : 0.f;
+    wca[i] = ((unsigned)x < (unsigned)p.W) ? 1.f - lw : 0.f;        wcb[i] = ((unsigned)(x + 1) < (unsigned)p.W) ? lw : 0.f;
+    ra[i] = min(max(y, 0), p.H - 1) * p.W;  rb[i] = min(max(y + 1, 0), p.H - 1) * p.W;
+    ca[i] = min(max(x, 0), p.W - 1);        cb[i] = min(max(x + 1, 0), p.W - 1);
   }
-  float* ob = p.out + ((size_t)b * p.C * p.Ho + ho) * p.Wo + wo;
-  for (int c = 0; c < p.C; ++c) {
-    const float* img = xb + c * plane;
+  const size_t plane = (size_t)p.H * p.W;
+  const int c_begin = blockIdx.y * DDF_CG, c_end = min(c_begin + DDF_CG, p.C);
+  const float* img = p.in + ((size_t)b * p.C + c_begin) * plane;
+  float* ob = p.out + ((size_t)b * p.C + c_begin) * npx + px;
+  for (int c = c_begin; c < c_end; ++c, img += plane, ob += npx) {
     const float* wk = p.wdw + c * 9;
     float acc = 0.f;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-      const int ya = r0[i], yb = ya + 1;
-      const bool va = (unsigned)ya < (unsigned)p.H, vb = (unsigned)yb < (unsigned)p.H;
-      const float* ra = img + (size_t)min(max(ya, 0), p.H - 1) * p.W;
-      const float* rb = img + (size_t)min(max(yb, 0), p.H - 1) * p.W;
+      const float* pa = img + ra[i];
+      const float* pb = img + rb[i];
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
-        const int xa = c0[j], xb2 = xa + 1;
-        const bool ua = (unsigned)xa < (unsigned)p.W, ub = (unsigned)xb2 < (unsigned)p.W;
-        const int xac = min(max(xa, 0), p.W - 1), xbc = min(max(xb2, 0), p.W - 1);
-        const float v1 = (va && ua) ? __ldg(ra + xac) : 0.f, v2 = (va && ub) ? __ldg(ra + xbc) : 0.f;
-        const float v3 = (vb && ua) ? __ldg(rb + xac) : 0.f, v4 = (vb && ub) ? __ldg(rb + xbc) : 0.f;
-        const float lh = lr[i], lw = lc[j], hh = 1.f - lh, hw = 1.f - lw;
-        const float val = hh * hw * v1 + hh * lw * v2 + lh * hw * v3 + lh * lw * v4;
+        const float v1 = __ldg(pa + ca[j]), v2 = __ldg(pa + cb[j]), v3 = __ldg(pb + ca[j]), v4 = __ldg(pb + cb[j]);
+        const float val = wra[i] * wca[j] * v1 + wra[i] * wcb[j] * v2 + wrb[i] * wca[j] * v3 + wrb[i] * wcb[j] * v4;
         acc = fmaf(__ldg(wk + i * 3 + j), val, acc);
       }
     }
-    ob[(size_t)c * p.Ho * p.Wo] = acc;
+    *ob = acc;
   }
 }
 
-extern "C" int cdn_deform_dw_f32(const float* input, const float* w_scale, float b_scale, int offset_bound, const float* w_dw,
-                                 float* output, int B, int C, int H, int W, int stride, cdn_stream_t stream) {
+extern "C" size_t cdn_deform_dw_f32_ws_bytes(int B, int H, int W, int stride) {
+  if (B < 0 || H < 1 || W < 1 || (stride != 1 && stride != 2)) return 0;
+  const size_t Ho = (size_t)((H + 2 - 3) / stride + 1), Wo = (size_t)((W + 2 - 3) / stride + 1);
+  return std::max<size_t>(B * Ho * Wo, 1) * sizeof(double);
+}
+
+extern "C" int cdn_deform_dw_f32_ws(const float* input, const float* w_scale, float b_scale, int offset_bound, const float* w_dw,
+                                    float* output, int B, int C, int H, int W, int stride, void* d_ws, size_t ws_bytes,
+                                    cdn_stream_t stream) {
   CDN_CHECK(input && w_scale && w_dw && output, CDN_ERR_INVALID, "deform_dw_f32: null tensor");
-  CDN_CHECK(B >= 0 && C >= 1 && H >= 1 && W >= 1 && (stride == 1 || stride == 2) && offset_bound >= 1, CDN_ERR_INVALID,
+  CDN_CHECK(B >= 0 && B <= 65535 && C >= 1 && H >= 1 && W >= 1 && (stride == 1 || stride == 2) && offset_bound >= 1, CDN_ERR_INVALID,
             "deform_dw_f32: bad shape / stride / bound");
+  CDN_CHECK(d_ws && ((uintptr_t)d_ws & 7) == 0 && ws_bytes >= cdn_deform_dw_f32_ws_bytes(B, H, W, stride), CDN_ERR_INVALID,
+            "deform_dw_f32: workspace of %zu bytes (8-byte aligned) needed, got %zu", cdn_deform_dw_f32_ws_bytes(B, H, W, stride), ws_bytes);
   DefDwF32Params p;
-  p.in = input; p.ws = w_scale; p.wdw = w_dw; p.out = output; p.bs = b_scale;
+  p.in = input; p.ws = w_scale; p.wdw = w_dw; p.out = output; p.bs = b_scale; p.sd = (double*)d_ws;
   p.lo = (float)(-offset_bound + 1); p.hi = (float)offset_bound;
   p.B = B; p.C = C; p.H = H; p.W = W; p.stride = stride;
   p.Ho = (H + 2 - 3) / stride + 1; p.Wo = (W + 2 - 3) / stride + 1;
-  p.total = (long long)B * p.Ho * p.Wo;
-  if (p.total == 0) return 0;
-  deform_dw_f32_kernel<<<(unsigned)((p.total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(p);
-  CDN_LAUNCH_CHECK("deform_dw_f32_kernel");
+  const int npx = p.Ho * p.Wo;
+  if (B == 0) return 0;
+  CDN_CHECK((C + DDF_CG - 1) / DDF_CG <= 65535, CDN_ERR_INVALID, "deform_dw_f32: too many channels");
+  deform_scale_f32_kernel<<<dim3((unsigned)((npx + 31) / 32), (unsigned)B), 256, 0, (cudaStream_t)stream>>>(p);
+  CDN_LAUNCH_CHECK("deform_scale_f32_kernel");
+  deform_gather_f32_kernel<<<dim3((unsigned)((npx + 127) / 128), (unsigned)((C + DDF_CG - 1) / DDF_CG), (unsigned)B), 128, 0, (cudaStream_t)stream>>>(p);
+  CDN_LAUNCH_CHECK("deform_gather_f32_kernel");
   return 0;
+}
+
+// The form without a workspace argument keeps one scratch buffer per device, grown on demand (a growth allocates and therefore
+// must not happen inside a stream capture: call once eagerly first, or use cdn_deform_dw_f32_ws).
+extern "C" int cdn_deform_dw_f32(const float* input, const float* w_scale, float b_scale, int offset_bound, const float* w_dw,
+                                 float* output, int B, int C, int H, int W, int stride, cdn_stream_t stream) {
+  static void* scratch[64] = {}; static size_t scratch_bytes[64] = {};
+  int dev = 0;
+  CDN_CUDA(cudaGetDevice(&dev));
+  CDN_CHECK(dev >= 0 && dev < 64, CDN_ERR_INVALID, "deform_dw_f32: device index out of range");
+  const size_t need = cdn_deform_dw_f32_ws_bytes(B, H, W, stride);
+  CDN_CHECK(need > 0, CDN_ERR_INVALID, "deform_dw_f32: bad shape / stride");
+  if (scratch_bytes[dev] < need) {
+    CDN_CUDA(cudaDeviceSynchronize());
+    if (scratch[dev]) cudaFree(scratch[dev]);
+    scratch[dev] = nullptr; scratch_bytes[dev] = 0;
+    CDN_CUDA(cudaMalloc(&scratch[dev], need));
+    scratch_bytes[dev] = need;
+  }
+  return cdn_deform_dw_f32_ws(input, w_scale, b_scale, offset_bound, w_dw, output, B, C, H, W, stride, scratch[dev], scratch_bytes[dev], stream);
 }
 
 // ---------------------------------------------------------------------------------------------------------

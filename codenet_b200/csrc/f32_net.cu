@@ -2,6 +2,7 @@
 // the host, so every layer is conv + bias (+ ReLU).  These are plain SIMT kernels (coalesced along W, fp32 FMA
 // accumulation -- the 1e-4 contract of the float path rules TF32 out); the W4A8 path is the optimised one.
 #include "common.cuh"
+#include <algorithm>
 
 // ---- dense 3x3 conv for the stem (Ci = 3): one thread per output pixel computes every output channel --------------
 #define C3_MAXCO 32
@@ -351,12 +352,29 @@ __global__ void copy_channels_f32_kernel(const float* __restrict__ in, int in_ct
   const int pi = (int)(idx % ppi); long long t = idx / ppi; const int c = (int)(t % n); const long long b = t / n;
   out[((size_t)b * out_ctotal + out_coff + (size_t)c * out_cstride) * ppi + pi] = in[((size_t)b * in_ctotal + in_coff + c) * ppi + pi];
 }
+// the same with planes that are a multiple of 4 floats and 16-byte aligned tensors: grid = (plane quarter-blocks, channel, image),
+// 16 bytes per thread and no index division (the scalar form spent its time in two 64-bit divisions per element)
+__global__ void __launch_bounds__(256) copy_channels_f32_v4_kernel(const float4* __restrict__ in, int in_ctotal, int in_coff, float4* __restrict__ out,
+                                                                   int out_ctotal, int out_coff, int out_cstride, int ppi4) {
+  const int c = blockIdx.y, b = blockIdx.z;
+  const float4* src = in + ((size_t)b * in_ctotal + in_coff + c) * ppi4;
+  float4* dst = out + ((size_t)b * out_ctotal + out_coff + (size_t)c * out_cstride) * ppi4;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < ppi4; i += gridDim.x * 256) dst[i] = __ldg(src + i);
+}
 extern "C" int cdn_copy_channels_f32(const float* input, int in_ctotal, int in_coff, float* output, int out_ctotal, int out_coff,
                                      int out_cstride, int n, int B, int pixels_per_image, cdn_stream_t stream) {
   CDN_CHECK(input && output && n >= 1 && in_coff >= 0 && in_coff + n <= in_ctotal && out_coff >= 0 &&
             out_coff + (n - 1) * out_cstride < out_ctotal, CDN_ERR_INVALID, "copy_channels_f32: slice out of range");
   const long long total = (long long)B * n * pixels_per_image;
   if (total == 0) return 0;
+  if (pixels_per_image % 4 == 0 && (((uintptr_t)input | (uintptr_t)output) & 15) == 0 && n <= 65535 && B <= 65535) {
+    const int ppi4 = pixels_per_image / 4;
+    dim3 grid((unsigned)std::min((ppi4 + 255) / 256, 8), (unsigned)n, (unsigned)B);
+    copy_channels_f32_v4_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)input, in_ctotal, in_coff, (float4*)output, out_ctotal,
+                                                                       out_coff, out_cstride, ppi4);
+    CDN_LAUNCH_CHECK("copy_channels_f32_v4_kernel");
+    return 0;
+  }
   copy_channels_f32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(input, in_ctotal, in_coff, output, out_ctotal,
                                                                                              out_coff, out_cstride, n, pixels_per_image, total);
   CDN_LAUNCH_CHECK("copy_channels_f32_kernel");

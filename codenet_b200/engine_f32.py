@@ -51,6 +51,7 @@ class EngineF32:
         self.gemm = gemm
         self.P = {}
         self.Ptc = {}                           # name -> (w_hi, w_lo) packed for cdn_pw_slice_tf32x3
+        self._def_ws = None                     # scale scalars of the deformable modules (8 bytes per pixel), grown on demand
         self._dec_ws = None                     # ctdet decode candidate buffer, grown on demand
         self.scale_bias = {}                    # host copies of the offset-scale conv biases (kernel arguments by value)
         for c in self.g.all_convs():
@@ -59,13 +60,17 @@ class EngineF32:
                 self.scale_bias[c.name] = float(b[0])
             self.P[c.name] = (torch.from_numpy(np.ascontiguousarray(w.reshape(c.cout, -1))).to(self.dev),
                               torch.from_numpy(np.ascontiguousarray(b)).to(self.dev))
-            if gemm == "tf32x3" and c.kind in ("pw", "head_out") and c.k == 1:
-                wd = self.P[c.name][0]
+        for kind in ("pw1", "dw2"):             # the heads' first two layers, stacked along the output channels
+            self.P["heads." + kind] = tuple(torch.cat([self.P[h["name"] + "." + kind][i] for h in self.g.heads]).contiguous() for i in (0, 1))
+        if gemm == "tf32x3":
+            pw_names = [c.name for c in self.g.all_convs() if c.kind in ("pw", "head_out") and c.k == 1] + ["heads.pw1"]
+            for name in pw_names:
+                wd = self.P[name][0]
                 n = int(self.lib.cdn_pw_tf32x3_packed_floats(wd.shape[0], wd.shape[1]))
                 hi, lo = torch.empty(n, dtype=torch.float32, device=self.dev), torch.empty(n, dtype=torch.float32, device=self.dev)
                 with torch.cuda.device(self.dev):
                     _lib.check(self.lib.cdn_pw_tf32x3_pack(self._p(wd), wd.shape[0], wd.shape[1], self._p(hi), self._p(lo), self._st()))
-                self.Ptc[c.name] = (hi, lo)
+                self.Ptc[name] = (hi, lo)
 
     # -- thin kernel wrappers ---------------------------------------------------------------------------------------------
     def _st(self):
@@ -142,8 +147,11 @@ class EngineF32:
                 wd, _ = self.P["up%d.deform" % i]
                 Bc, Cc, H, W = x.shape
                 y = x.new_empty(x.shape)
-                _lib.check(L.cdn_deform_dw_f32(self._p(x), self._p(ws), C.c_float(self.scale_bias["up%d.scale" % i]), cfg.offset_bound, self._p(wd), self._p(y),
-                                               Bc, Cc, H, W, 1, self._st()))
+                need = int(L.cdn_deform_dw_f32_ws_bytes(Bc, H, W, 1))
+                if self._def_ws is None or self._def_ws.numel() < need:
+                    self._def_ws = torch.empty(need, dtype=torch.uint8, device=self.dev)
+                _lib.check(L.cdn_deform_dw_f32_ws(self._p(x), self._p(ws), C.c_float(self.scale_bias["up%d.scale" % i]), cfg.offset_bound, self._p(wd),
+                                                  self._p(y), Bc, Cc, H, W, 1, self._p(self._def_ws), self._def_ws.numel(), self._st()))
                 z = self._new(y, up["cout"])
                 self._pw(y, 0, Cc, "up%d.channel" % i, z, 0, 1, True)
                 x = z.new_empty((Bc, up["cout"], 2 * H, 2 * W))
@@ -152,11 +160,15 @@ class EngineF32:
             heads = self._new(x, n_out)
             off = 0
             views = {}
-            for h in g.heads:                                      # depthwise-separable heads, :244-271
-                a = self._new(x, 64)
-                self._pw(x, 0, 64, h["name"] + ".pw1", a, 0, 1, True)
-                d = self._dw(a, h["name"] + ".dw2", 1, True)
-                self._pw(d, 0, 64, h["name"] + ".out", heads, off, 1, False)
+            # depthwise-separable heads, :244-271.  The three heads' first 1x1 conv and depthwise conv read the same tensor: they run
+            # as ONE 64 -> 64*heads conv and ONE depthwise conv on the stacked channels (weights stacked at construction), each
+            # head's output conv then reads its 64-channel slice -- the 128 x 128 feature map is read once instead of three times
+            nh = len(g.heads)
+            a = self._new(x, 64 * nh)
+            self._pw(x, 0, 64, "heads.pw1", a, 0, 1, True)
+            d = self._dw(a, "heads.dw2", 1, True)
+            for k, h in enumerate(g.heads):
+                self._pw(d, 64 * k, 64, h["name"] + ".out", heads, off, 1, False)
                 views[h["name"]] = heads[:, off:off + h["classes"]]
                 off += h["classes"]
         self._heads = heads

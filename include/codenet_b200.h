@@ -229,10 +229,16 @@ int cdn_deform_conv_forward_f32(const float* input, const float* weight, const f
 /* ---- fused co-designed deformable module, fp32 (the float model's layer) -------------------------------------
  * DeformConvWithOffsetScaleBoundPositive.forward (lib/models/external/modules/dcn_deform_conv.py:323-330) without its
  * optional conv_channel: s = Hardtanh[-bound+1, bound](w_scale . x + b_scale) per output pixel (1x1 conv C -> 1 with
- * stride `stride`), offsets anchor*(s-1), depthwise 3x3 deformable conv (pad 1, bilinear) -- one kernel, no offset
+ * stride `stride`), offsets anchor*(s-1), depthwise 3x3 deformable conv (pad 1, bilinear) -- two launches, no offset
  * tensor.  input [B][C][H][W], w_scale [C], w_dw [C][3][3], output [B][C][Ho][Wo] (contiguous NCHW device pointers). */
 int cdn_deform_dw_f32(const float* input, const float* w_scale, float b_scale, int offset_bound, const float* w_dw,
                       float* output, int B, int C, int H, int W, int stride, cdn_stream_t stream);
+/* cdn_deform_dw_f32 keeps its scratch (the scale scalar per output pixel) in a per-device buffer grown on demand; the _ws
+ * form takes it from the caller (cdn_deform_dw_f32_ws_bytes bytes, 8-byte aligned) and never allocates, so it can be captured
+ * into a CUDA graph from the first call. */
+size_t cdn_deform_dw_f32_ws_bytes(int B, int H, int W, int stride);
+int cdn_deform_dw_f32_ws(const float* input, const float* w_scale, float b_scale, int offset_bound, const float* w_dw,
+                         float* output, int B, int C, int H, int W, int stride, void* d_ws, size_t ws_bytes, cdn_stream_t stream);
 /* fp32 1x1 convolution NCHW (the module's conv_channel): output [B][Co][P] = weight [Co][C] x input [B][C][P] (+ bias). */
 int cdn_pw_f32(const float* input, const float* weight, const float* bias, float* output, int B, int C, int Co,
                int pixels_per_image, cdn_stream_t stream);

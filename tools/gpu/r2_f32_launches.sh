@@ -10,7 +10,7 @@ from tools.bench_f32_config5 import _cfg, _state
 from codenet_b200.engine_f32 import EngineF32
 from codenet_b200.synth import make_images
 raw, g = _state()
-eng = EngineF32(_cfg(), raw, device=0)
+eng = EngineF32(_cfg(), raw, device=0, gemm=os.environ.get("CODENET_F32_GEMM", "tf32x3"))
 x = torch.from_numpy(np.concatenate([make_images(8, 512, seed=100)] * 4).copy()).cuda()
 eng.detect(x); torch.cuda.synchronize()
 PY
