@@ -96,6 +96,12 @@ __device__ __forceinline__ void pt_wait(uint32_t bar, uint32_t parity) {
 // round to TF32 (10 explicit mantissa bits), nearest with ties away from zero = cvt.rna.tf32.f32 for finite inputs, in two
 // integer instructions (the cvt itself expands to ~9 with its NaN handling)
 __device__ __forceinline__ uint32_t pt_tf32(float v) { return (__float_as_uint(v) + 0x1000u) & 0xffffe000u; }
+__device__ __forceinline__ void sts_f32(uint32_t saddr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory"); }
+__device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
 __device__ __forceinline__ bool pt_elect() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
@@ -134,6 +140,7 @@ pw_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = s_tmem;
   const uint32_t w_bytes = (uint32_t)p.BN * PT_KC * 4;
+  const uint32_t stage_u32 = smem_u32(ring) + PT_STAGES * PT_STAGE_BYTES;   // 32 KB output staging slab behind the ring
   const int nch = (p.num_k + PT_CHUNK - 1) / PT_CHUNK;              // accumulation chunks per tile
   // chunk accumulators: two pixel blocks x bnp columns each; 512 TMEM columns hold 2 of them at BN > 64 and 4 at BN <= 64 (the
   // memory-bound layers: the tensor core then runs a whole short tile ahead while the epilogue stores the previous one)
@@ -289,21 +296,51 @@ pw_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         __syncwarp();
         if (lane == 0) mbar_arrive(CEMPTY(cb));
       }
+      // End of tile: the totals leave through a 32-channel x 256-pixel staging slab in shared memory (conflict-free 128-byte
+      // rows per warp), from which all eight epilogue warps store 16 bytes per lane (512 contiguous bytes of one channel plane per
+      // warp) after adding the bias / applying ReLU.  A warp owns two slabs (its columns jb = 0 and jb = 32); with BN > 64 the
+      // tile has four rounds, the warps of column half `ch` filling rounds 2 ch and 2 ch + 1.  (Storing straight from the
+      // registers -- 128 predicated 4-byte stores per lane, each with its own address -- cost 6 us per tile.)
       const int n0 = nt * p.per;
+      const int nreal = min(p.per, p.Co - n0);                      // real output channels of this N tile
       const size_t plane = (size_t)p.out_cstride * p.ppi;
-      const int nvalid = min(p.per, p.Co - n0) - col0;              // real output channels among this warp's 64 columns
+      float* obase = p.out + ((size_t)b * p.out_ctotal + p.out_coff + (size_t)n0 * p.out_cstride) * p.ppi + px0;
+      const int nround = small ? 2 : 4;
+      const int et = threadIdx.x - 256;                             // 0..255 among the epilogue warps
+      for (int round = 0; round < nround; ++round) {
+        const int nv = min(max(nreal - round * 32, 0), 32);
+        if (nv > 0) {
+          if (small || (round >> 1) == ch) {
+            const uint32_t sp = stage_u32 + (uint32_t)((mb0 * 128 + q * 32 + lane) * 4);
+            if ((round & 1) == 0) {
 #pragma unroll
-      for (int mbi = 0; mbi < 2; ++mbi) {
-        if (mbi < nmb) {
-          float* o = p.out + ((size_t)b * p.out_ctotal + p.out_coff + (size_t)(n0 + col0) * p.out_cstride) * p.ppi + px0 + (mb0 + mbi) * 128 + q * 32 + lane;
+              for (int mbi = 0; mbi < 2; ++mbi)
+                if (mbi < nmb) {
 #pragma unroll
-          for (int j = 0; j < 64; ++j) {
-            if (j < nvalid) {
-              float v = tot[mbi][j] + (p.bias ? __ldg(p.bias + n0 + col0 + j) : 0.f);
-              if (p.relu) v = fmaxf(v, 0.f);
-              o[(size_t)j * plane] = v;
+                  for (int j = 0; j < 32; ++j) sts_f32(sp + (uint32_t)((j * 256 + mbi * 128) * 4), tot[mbi][j]);
+                }
+            } else {
+#pragma unroll
+              for (int mbi = 0; mbi < 2; ++mbi)
+                if (mbi < nmb) {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) sts_f32(sp + (uint32_t)((j * 256 + mbi * 128) * 4), tot[mbi][32 + j]);
+                }
             }
           }
+          named_bar_sync(1, 256);
+#pragma unroll 2
+          for (int i = 0; i < 8; ++i) {
+            const int idx = et + 256 * i, co = idx >> 6, f4 = idx & 63;
+            if (co < nv) {
+              float4 v = lds_f4(stage_u32 + (uint32_t)((co * 256 + f4 * 4) * 4));
+              const float bv = p.bias ? __ldg(p.bias + n0 + round * 32 + co) : 0.f;
+              v.x += bv; v.y += bv; v.z += bv; v.w += bv;
+              if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+              *(float4*)(obase + (size_t)(round * 32 + co) * plane + f4 * 4) = v;
+            }
+          }
+          named_bar_sync(1, 256);
         }
       }
     }
@@ -415,7 +452,7 @@ extern "C" int cdn_pw_slice_tf32x3(const float* input, int in_ctotal, int in_cof
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     CDN_CHECK(r == CUDA_SUCCESS, CDN_ERR_CUDA, "pw_slice_tf32x3: weight tensor map failed with CUresult %d", (int)r);
   }
-  const size_t smem = (size_t)PT_STAGES * PT_STAGE_BYTES + 1024;
+  const size_t smem = (size_t)PT_STAGES * PT_STAGE_BYTES + 32768 + 1024;   // ring + output staging slab + alignment slack
   static bool attr_set[64] = {};
   if (cdn_first_on_device(attr_set)) {
     CDN_CUDA(cudaFuncSetAttribute(pw_tf32x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

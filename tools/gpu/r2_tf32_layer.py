@@ -10,7 +10,7 @@ st = lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream)
 only = sys.argv[1] if len(sys.argv) > 1 else None
 B = 128
 shapes = [("l1.pw", 122, 122, 4096), ("l2.pw", 244, 244, 1024), ("l3.pw", 488, 488, 256), ("layer4", 976, 2153, 256), ("up0.ch", 2153, 256, 256),
-          ("l2.0.pw1", 244, 244, 4096), ("hm.pw1", 64, 64, 16384), ("hm.out", 64, 80, 16384)]
+          ("l2.0.pw1", 244, 244, 4096), ("hm.pw1", 64, 64, 16384), ("hm.out", 64, 80, 16384), ("heads.pw1", 64, 192, 16384), ("l1.0.pw1", 24, 122, 16384)]
 for name, Cc, Co, ppi in shapes:
     if only and name != only: continue
     x = torch.randn(B, Cc, ppi, device="cuda"); w = torch.randn(Co, Cc, device="cuda") / Cc ** 0.5
