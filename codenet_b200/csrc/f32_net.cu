@@ -111,12 +111,142 @@ __global__ void __launch_bounds__(256) dw3x3_f32_s1v4_kernel(const float* __rest
   *(float4*)(out + (size_t)t * H * W + (size_t)y * W + x0) = o4;
 }
 
+// stride 1 with H and W multiples of 4: one thread = 4 x 4 outputs.  Six row reads (one 16-byte load each; the two halo
+// columns come from the neighbouring lanes by shuffle when a row's threads share a warp) feed 16 outputs, where the 4 x 1
+// kernel above issues 9 loads per 4 outputs and three 64-bit index divisions per thread.  Same taps in the same order per
+// output (rows top to bottom, columns left to right); taps outside the image add an exact zero instead of being skipped.
+template <bool SHFL>
+__global__ void __launch_bounds__(256) dw3x3_f32_s1r4_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
+                                                             float* __restrict__ out, int C, int H, int W, int relu, unsigned total) {
+  unsigned idx = blockIdx.x * 256u + threadIdx.x;
+  const bool active = idx < total;
+  if (!active) idx = total - 1;                                     // keeps the lane alive for the shuffles
+  const unsigned W4 = (unsigned)W >> 2, H4 = (unsigned)H >> 2;
+  const unsigned x4 = idx % W4; unsigned t = idx / W4; const unsigned ys = t % H4; const unsigned pl = t / H4; const int c = (int)(pl % (unsigned)C);
+  const int x0 = (int)x4 * 4, y0 = (int)ys * 4;
+  const float* plane = in + (size_t)pl * H * W;
+  float wk[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) wk[i] = __ldg(w + c * 9 + i);
+  const float b0 = bias ? __ldg(bias + c) : 0.f;
+  float acc[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int o = 0; o < 4; ++o) acc[r][o] = b0;
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    const int yy = y0 - 1 + r;
+    const bool rv = (unsigned)yy < (unsigned)H;
+    const float* rp = plane + (size_t)(rv ? yy : 0) * W + x0;
+    float4 q = __ldg((const float4*)rp);
+    if (!rv) q = make_float4(0.f, 0.f, 0.f, 0.f);
+    float left, right;
+    if (SHFL) {
+      left = __shfl_up_sync(0xffffffffu, q.w, 1); right = __shfl_down_sync(0xffffffffu, q.x, 1);
+      if (x4 == 0) left = 0.f;
+      if (x4 == W4 - 1) right = 0.f;
+    } else {
+      left = (rv && x0 > 0) ? __ldg(rp - 1) : 0.f; right = (rv && x0 + 4 < W) ? __ldg(rp + 4) : 0.f;
+    }
+    const float v[6] = {left, q.x, q.y, q.z, q.w, right};
+#pragma unroll
+    for (int orow = 0; orow < 4; ++orow) {
+      const int i = r - orow;
+      if (i >= 0 && i < 3) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+          for (int o = 0; o < 4; ++o) acc[orow][o] = fmaf(wk[i * 3 + j], v[o + j], acc[orow][o]);
+      }
+    }
+  }
+  if (!active) return;
+  float* op = out + (size_t)pl * H * W + (size_t)y0 * W + x0;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    float4 o4 = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+    if (relu) { o4.x = fmaxf(o4.x, 0.f); o4.y = fmaxf(o4.y, 0.f); o4.z = fmaxf(o4.z, 0.f); o4.w = fmaxf(o4.w, 0.f); }
+    *(float4*)(op + (size_t)r * W) = o4;
+  }
+}
+
+// depthwise 3x3 (pad 1, stride 1) over the NEAREST x2 UPSAMPLED map without ever writing it: out[Y][X] = b + sum_ij w[i][j] *
+// a[(Y+i-1) >> 1][(X+j-1) >> 1] (zero outside), a = the low-resolution plane.  Used for the heads: their first 1x1 conv + ReLU
+// commute with nearest upsampling exactly (pointwise), so conv(upsample(z)) is computed as upsample(conv(z)) at a quarter of
+// the pixels and the 4x larger tensor is only ever produced as this kernel's output (shufflenetv2_dcn.py:244-271 after the last
+// deconv block :286-300).  One thread = 4 low-resolution pixels of a row = 2 x 8 outputs; taps in the order of the plain kernel.
+__global__ void __launch_bounds__(256) dw3x3_up2_f32_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
+                                                            float* __restrict__ out, int C, int h, int wd, int relu, unsigned total) {
+  const unsigned idx = blockIdx.x * 256u + threadIdx.x;
+  if (idx >= total) return;
+  const unsigned W4 = (unsigned)wd >> 2;
+  const unsigned x4 = idx % W4; unsigned t = idx / W4; const unsigned y = t % (unsigned)h; const unsigned pl = t / (unsigned)h;
+  const int c = (int)(pl % (unsigned)C), x0 = (int)x4 * 4;
+  const float* plane = in + (size_t)pl * h * wd;
+  float wk[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) wk[i] = __ldg(w + c * 9 + i);
+  const float b0 = bias ? __ldg(bias + c) : 0.f;
+  float v[3][6];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int yy = (int)y - 1 + r;
+    const bool rv = (unsigned)yy < (unsigned)h;
+    const float* rp = plane + (size_t)(rv ? yy : 0) * wd + x0;
+    const float4 q = __ldg((const float4*)rp);
+    v[r][0] = (rv && x0 > 0) ? __ldg(rp - 1) : 0.f;
+    v[r][1] = rv ? q.x : 0.f; v[r][2] = rv ? q.y : 0.f; v[r][3] = rv ? q.z : 0.f; v[r][4] = rv ? q.w : 0.f;
+    v[r][5] = (rv && x0 + 4 < wd) ? __ldg(rp + 4) : 0.f;
+  }
+  float* op = out + (size_t)pl * (4 * h * wd) + (size_t)(2 * y) * (2 * wd) + 2 * x0;
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy) {
+    float o[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        float acc = b0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const int rr = 1 + ((dy + i - 1) >> 1);                         // low row of tap row i, relative to y - 1 .. y + 1: floor((dy + i - 1) / 2)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) acc = fmaf(wk[i * 3 + j], v[rr][1 + k + ((dx + j - 1) >> 1)], acc);
+        }
+        o[2 * k + dx] = relu ? fmaxf(acc, 0.f) : acc;
+      }
+    *(float4*)(op + (size_t)dy * (2 * wd)) = make_float4(o[0], o[1], o[2], o[3]);
+    *(float4*)(op + (size_t)dy * (2 * wd) + 4) = make_float4(o[4], o[5], o[6], o[7]);
+  }
+}
+extern "C" int cdn_dw3x3_up2_f32(const float* input, const float* weight, const float* bias, float* output, int B, int C, int h, int w,
+                                 int relu, cdn_stream_t stream) {
+  CDN_CHECK(input && weight && output && C >= 1 && h >= 1 && w >= 4 && w % 4 == 0 && B >= 0, CDN_ERR_INVALID,
+            "dw3x3_up2_f32: bad arguments (the low-resolution width must be a multiple of 4)");
+  CDN_CHECK(((((uintptr_t)input) | ((uintptr_t)output)) & 15) == 0, CDN_ERR_INVALID, "dw3x3_up2_f32: tensors must be 16-byte aligned");
+  const long long total = (long long)B * C * h * (w / 4);
+  CDN_CHECK(total < (1ll << 32) - 256, CDN_ERR_INVALID, "dw3x3_up2_f32: tensor too large");
+  if (total == 0) return 0;
+  dw3x3_up2_f32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(input, weight, bias, output, C, h, w, relu, (unsigned)total);
+  CDN_LAUNCH_CHECK("dw3x3_up2_f32_kernel");
+  return 0;
+}
+
 extern "C" int cdn_dw3x3_f32(const float* input, const float* weight, const float* bias, float* output, int B, int C, int H, int W,
                              int stride, int relu, cdn_stream_t stream) {
   CDN_CHECK(input && weight && output && C >= 1 && (stride == 1 || stride == 2), CDN_ERR_INVALID, "dw3x3_f32: bad arguments");
   const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
   const long long total = (long long)B * C * Ho * Wo;
   if (total == 0) return 0;
+  if (stride == 1 && W % 4 == 0 && H % 4 == 0 && ((((uintptr_t)input) | ((uintptr_t)output)) & 15) == 0 && total / 16 < (1ll << 32) - 256) {
+    const unsigned total16 = (unsigned)(total / 16);
+    const int W4 = W / 4;
+    if (W4 <= 32 && 32 % W4 == 0) dw3x3_f32_s1r4_kernel<true><<<(total16 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(input, weight, bias, output, C, H, W, relu, total16);
+    else dw3x3_f32_s1r4_kernel<false><<<(total16 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(input, weight, bias, output, C, H, W, relu, total16);
+    CDN_LAUNCH_CHECK("dw3x3_f32_s1r4_kernel");
+    return 0;
+  }
   if (stride == 1 && W % 4 == 0 && ((((uintptr_t)input) | ((uintptr_t)output)) & 15) == 0) {
     const long long total4 = total / 4;
     dw3x3_f32_s1v4_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(input, weight, bias, output, C, H, W, relu, total4);

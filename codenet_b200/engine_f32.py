@@ -154,19 +154,34 @@ class EngineF32:
                                                   self._p(y), Bc, Cc, H, W, 1, self._p(self._def_ws), self._def_ws.numel(), self._st()))
                 z = self._new(y, up["cout"])
                 self._pw(y, 0, Cc, "up%d.channel" % i, z, 0, 1, True)
+                if up is g.ups[-1] and W % 4 == 0:
+                    break                                          # the last x2 upsampling is virtual: see the heads below
                 x = z.new_empty((Bc, up["cout"], 2 * H, 2 * W))
                 _lib.check(L.cdn_upsample2x_f32(self._p(z), self._p(x), Bc * up["cout"], H, W, self._st()))
+            else:
+                z = None
             n_out = sum(h["classes"] for h in g.heads)
-            heads = self._new(x, n_out)
             off = 0
             views = {}
             # depthwise-separable heads, :244-271.  The three heads' first 1x1 conv and depthwise conv read the same tensor: they run
             # as ONE 64 -> 64*heads conv and ONE depthwise conv on the stacked channels (weights stacked at construction), each
             # head's output conv then reads its 64-channel slice -- the 128 x 128 feature map is read once instead of three times
+            # A 1x1 conv + ReLU commutes with nearest upsampling exactly, so with the last upsampling still pending (z, low
+            # resolution) the stacked conv runs on a quarter of the pixels and the depthwise conv reads its result through the virtual
+            # upsampling (cdn_dw3x3_up2_f32): the upsampled 64-channel map and the upsampled conv output are never written.
             nh = len(g.heads)
-            a = self._new(x, 64 * nh)
-            self._pw(x, 0, 64, "heads.pw1", a, 0, 1, True)
-            d = self._dw(a, "heads.dw2", 1, True)
+            if z is not None:
+                Bc, _, H, W = z.shape
+                a = self._new(z, 64 * nh)
+                self._pw(z, 0, 64, "heads.pw1", a, 0, 1, True)
+                d = z.new_empty((Bc, 64 * nh, 2 * H, 2 * W))
+                wdw, bdw = self.P["heads.dw2"]
+                _lib.check(L.cdn_dw3x3_up2_f32(self._p(a), self._p(wdw), self._p(bdw), self._p(d), Bc, 64 * nh, H, W, 1, self._st()))
+            else:
+                a = self._new(x, 64 * nh)
+                self._pw(x, 0, 64, "heads.pw1", a, 0, 1, True)
+                d = self._dw(a, "heads.dw2", 1, True)
+            heads = self._new(d, n_out)
             for k, h in enumerate(g.heads):
                 self._pw(d, 64 * k, 64, h["name"] + ".out", heads, off, 1, False)
                 views[h["name"]] = heads[:, off:off + h["classes"]]

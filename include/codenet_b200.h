@@ -252,6 +252,10 @@ int cdn_conv3x3_f32(const float* input, const float* weight, const float* bias, 
                     int H, int W, int stride, int relu, cdn_stream_t stream);
 int cdn_dw3x3_f32(const float* input, const float* weight, const float* bias, float* output, int B, int C, int H, int W,
                   int stride, int relu, cdn_stream_t stream);
+/* The same depthwise conv (stride 1) over the nearest x2 upsampling of `input` [B][C][h][w], which is never materialised:
+ * output [B][C][2h][2w].  w must be a multiple of 4. */
+int cdn_dw3x3_up2_f32(const float* input, const float* weight, const float* bias, float* output, int B, int C, int h, int w,
+                      int relu, cdn_stream_t stream);
 int cdn_pw_slice_f32(const float* input, int in_ctotal, int in_coff, int C, const float* weight, const float* bias,
                      float* output, int out_ctotal, int out_coff, int out_cstride, int Co, int relu, int B,
                      int pixels_per_image, cdn_stream_t stream);

@@ -96,3 +96,64 @@ def test_pw_tf32x3_matches_fp64(C, Co, ppi, B, in_ct, in_off, out_ct, out_off, o
     # pixel counts that are not a multiple of 256 are refused (the caller keeps cdn_pw_slice_f32 for them)
     assert L.cdn_pw_slice_tf32x3(ptr(tx), in_ct, in_off, C, ptr(hi), ptr(lo), ptr(tb), ptr(out), out_ct, out_off, out_cs, Co, relu,
                                  B, 128, stream()) == -1
+
+
+@pytest.mark.parametrize("B,C,H,W,stride", [(2, 5, 16, 16, 1), (1, 7, 32, 32, 1), (2, 3, 64, 64, 1), (1, 4, 128, 128, 1), (1, 3, 8, 256, 1),
+                                            (2, 4, 10, 12, 1), (1, 3, 9, 7, 1), (2, 4, 16, 16, 2), (1, 3, 9, 7, 2)])
+def test_dw3x3_f32_matches_numpy(B, C, H, W, stride):
+    """cdn_dw3x3_f32 (depthwise 3x3, pad 1, + bias + ReLU: the float BaseNode's second conv, shufflenetv2_dcn.py:77-80): every
+    kernel variant (4 x 4 outputs per thread with shuffled halos, with loaded halos, 4 x 1, scalar) against the fp64 sum."""
+    import torch
+    from codenet_b200 import _lib
+    from gpu_util import ptr, stream
+    rng = np.random.default_rng(B * 100 + H + W)
+    x = rng.normal(0, 1, (B, C, H, W)).astype(np.float32)
+    w = rng.normal(0, 1, (C, 3, 3)).astype(np.float32)
+    bias = rng.normal(0, 1, C).astype(np.float32)
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    xp = np.pad(x.astype(np.float64), ((0, 0), (0, 0), (1, 1), (1, 1)))
+    ref = np.zeros((B, C, Ho, Wo))
+    for i in range(3):
+        for j in range(3):
+            ref += w[None, :, i, j, None, None] * xp[:, :, i:i + stride * Ho:stride, j:j + stride * Wo:stride][:, :, :Ho, :Wo]
+    ref = np.maximum(ref + bias[None, :, None, None], 0)
+    tx, tw, tb = torch.from_numpy(x).cuda(), torch.from_numpy(w).cuda(), torch.from_numpy(bias).cuda()
+    out = torch.full((B, C, Ho, Wo), -7.0, device="cuda")
+    _lib.check(_lib.load().cdn_dw3x3_f32(ptr(tx), ptr(tw), ptr(tb), ptr(out), B, C, H, W, stride, 1, stream()))
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=2e-6, atol=2e-6)
+
+
+@pytest.mark.parametrize("ppi", [256, 6])
+def test_copy_channels_f32(ppi):
+    """cdn_copy_channels_f32 = the pass-through half of a stride-1 unit written to the even channels (cat + channel_shuffle,
+    shufflenetv2_dcn.py:29-34,108-114); 16-byte and scalar forms."""
+    import torch
+    from codenet_b200 import _lib
+    from gpu_util import ptr, stream
+    B, ct, n = 3, 10, 5
+    x = torch.randn(B, ct, ppi, device="cuda")
+    out = torch.full((B, ct, ppi), -7.0, device="cuda")
+    _lib.check(_lib.load().cdn_copy_channels_f32(ptr(x), ct, 0, ptr(out), ct, 0, 2, n, B, ppi, stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(out[:, 0::2], x[:, :n]) and bool((out[:, 1::2] == -7.0).all())
+
+
+@pytest.mark.parametrize("B,C,h,w", [(2, 5, 8, 8), (1, 3, 64, 64), (2, 4, 3, 12)])
+def test_dw3x3_over_virtual_upsample_equals_upsample_then_dw(B, C, h, w):
+    """cdn_dw3x3_up2_f32(a) == cdn_dw3x3_f32(cdn_upsample2x_f32(a)) bit for bit (same taps in the same order): the heads' fused
+    form of nearest x2 upsampling followed by their depthwise conv."""
+    import torch
+    from codenet_b200 import _lib
+    from gpu_util import ptr, stream
+    L = _lib.load()
+    a = torch.randn(B, C, h, w, device="cuda")
+    wt, bias = torch.randn(C, 3, 3, device="cuda"), torch.randn(C, device="cuda")
+    up = torch.empty(B, C, 2 * h, 2 * w, device="cuda")
+    _lib.check(L.cdn_upsample2x_f32(ptr(a), ptr(up), B * C, h, w, stream()))
+    assert torch.equal(up, a.repeat_interleave(2, 2).repeat_interleave(2, 3))
+    want, got = torch.empty_like(up), torch.empty_like(up)
+    _lib.check(L.cdn_dw3x3_f32(ptr(up), ptr(wt), ptr(bias), ptr(want), B, C, 2 * h, 2 * w, 1, 1, stream()))
+    _lib.check(L.cdn_dw3x3_up2_f32(ptr(a), ptr(wt), ptr(bias), ptr(got), B, C, h, w, 1, stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(got, want)
