@@ -13,8 +13,8 @@
 //
 // Shape.  D[256 pixels][BN channels] per tile = X^T W^T: the activation tile is the A operand in MN-major form -- exactly
 // what a SWIZZLE_128B TMA box {32 pixels, 16 channels} of the NCHW tensor writes to shared memory, so no transposition
-// is ever executed; the packed weights [Co_pad][K_pad] (hi and lo, cdn_pw_tf32x3_pack) are the K-major B operand
-// (SWIZZLE_64B rows of 16 channels).  Warp roles: 0 TMA producer, 1-2 MMA issuers (one per 128-pixel block), 4-7 split the raw activation tile
+// is ever executed; the packed weights (cdn_pw_tf32x3_pack: 128-byte rows of 16 channels hi + the same 16 lo) are the K-major
+// B operand (SWIZZLE_128B).  Warp roles: 0 TMA producer, 1-2 MMA issuers (one per 128-pixel block), 4-7 split the raw activation tile
 // in place (hi) and into its sibling buffer (lo), 8-15 epilogue (lane = pixel).
 // Accumulation.  The tensor core adds into its fp32 accumulator with truncation; over a long K that is a systematic shrink
 // (measured 7e-9 * K relative).  So it only ever sums ONE 16-channel stage: the cross terms first (small), then the two exact
@@ -30,8 +30,8 @@
 #define PT_KC 16                       // channels per pipeline stage (two K = 8 steps)
 #define PT_STAGES 4
 #define PT_XBYTES (PT_M * PT_KC * 4)   // 16 KB: raw / hi activation tile of a stage; the same again for lo
-#define PT_WMAX (128 * PT_KC * 4)      // 8 KB: weight tile (hi or lo) of a stage at BN = 128
-#define PT_STAGE_BYTES (2 * PT_XBYTES + 2 * PT_WMAX)
+#define PT_WMAX (128 * 128)             // 16 KB: weight tile of a stage at BN = 128 (rows of 16 hi + 16 lo floats)
+#define PT_STAGE_BYTES (2 * PT_XBYTES + PT_WMAX)
 #define PT_THREADS 512                 // 16 warps: TMA, 2 x MMA, 1 idle | 4 split | 8 epilogue
 #define PT_EPI_WARPS 8
 
@@ -64,14 +64,15 @@ __device__ __forceinline__ uint64_t pt_desc_a(uint32_t saddr, uint32_t lbo) {
   d |= (uint64_t)1 << 61;                    // SWIZZLE_128B_BASE32B
   return d;
 }
-// B: K-major, SWIZZLE_64B.  64-byte rows = 16 channels of one output channel, 8-row groups 512 bytes apart.
+// B: K-major, SWIZZLE_128B.  128-byte rows = [16 channels hi | 16 channels lo] of one output channel, 8-row groups 1 KB apart;
+// a K = 8 step is 32 bytes inside the row (hi: 0 / 32, lo: 64 / 96).
 __device__ __forceinline__ uint64_t pt_desc_b(uint32_t saddr) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3fff);
   d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)(1024 >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)4 << 61;                    // SWIZZLE_64B
+  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
   return d;
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -107,15 +108,10 @@ __device__ __forceinline__ bool pt_elect() {
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
   return pred != 0;
 }
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
-  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-               ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
-}
 
 template <int PT_CHUNK>
 __global__ void __launch_bounds__(PT_THREADS, 1)
-pw_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWh,
-                 const __grid_constant__ CUtensorMap tmWl, const PtParams p) {
+pw_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const PtParams p) {
   extern __shared__ __align__(1024) uint8_t pt_smem[];
   __shared__ __align__(8) unsigned long long s_bar[3 * PT_STAGES + 8];
   __shared__ uint32_t s_tmem;
@@ -139,7 +135,7 @@ pw_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = s_tmem;
-  const uint32_t w_bytes = (uint32_t)p.BN * PT_KC * 4;
+  const uint32_t w_bytes = (uint32_t)p.BN * 128;                     // one weight tile: BN rows of (16 hi + 16 lo) floats
   const uint32_t stage_u32 = smem_u32(ring) + PT_STAGES * PT_STAGE_BYTES;   // 32 KB output staging slab behind the ring
   const int nch = (p.num_k + PT_CHUNK - 1) / PT_CHUNK;              // accumulation chunks per tile
   // chunk accumulators: two pixel blocks x bnp columns each; 512 TMEM columns hold 2 of them at BN > 64 and 4 at BN <= 64 (the
@@ -166,16 +162,10 @@ pw_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           for (int kc = 0; kc < p.num_k; ++kc) {
             pt_wait(EMPTY(stage), phase ^ 1);
             const uint32_t sx = smem_u32(ring + (size_t)stage * PT_STAGE_BYTES);
-            mbar_expect_tx(RAW(stage), ((p.dbg & 2) ? 0u : (uint32_t)PT_XBYTES) + 2 * w_bytes);
-            if (!(p.dbg & 2)) {
-#pragma unroll
-              for (int j = 0; j < PT_M / 32; ++j)                     // 8 boxes of 32 pixels x 16 channels (2 KB each)
-                tma_load_3d(sx + j * 2048, &tmX, px0 + j * 32, kc * PT_KC, b, RAW(stage));
-            }
-            {
-              tma_load_2d(sx + 2 * PT_XBYTES, &tmWh, kc * PT_KC, nt * p.BN, RAW(stage));
-              tma_load_2d(sx + 2 * PT_XBYTES + PT_WMAX, &tmWl, kc * PT_KC, nt * p.BN, RAW(stage));
-            }
+            mbar_expect_tx(RAW(stage), ((p.dbg & 2) ? 0u : (uint32_t)PT_XBYTES) + w_bytes);
+            // one box = 32 pixels x 16 channels x 8 pixel groups: 128-byte rows, channel rows 128 bytes apart, pixel groups 2 KB apart
+            if (!(p.dbg & 2)) tma_load_4d(sx, &tmX, 0, kc * PT_KC, px0 >> 5, b, RAW(stage));
+            tma_load_2d(sx + 2 * PT_XBYTES, &tmW, kc * 32, nt * p.BN, RAW(stage));   // BN rows of 128 bytes: [hi 16 channels | lo 16 channels]
             if (++stage == PT_STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -208,10 +198,10 @@ pw_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
               const uint64_t so = (uint64_t)((uint32_t)st * (PT_STAGE_BYTES >> 4));
               const uint64_t ah = a_base + so, bh = b_base + so;
               if (leader) {
-                umma_tf32(tacc, ah + (PT_XBYTES >> 4), bh, idesc, s != 0 ? 1u : 0u);
-                umma_tf32(tacc, ah, bh + (PT_WMAX >> 4), idesc, 1u);
-                umma_tf32(tacc, ah + ((PT_XBYTES + 1024) >> 4), bh + 2, idesc, 1u);
-                umma_tf32(tacc, ah + (1024 >> 4), bh + ((PT_WMAX >> 4) + 2), idesc, 1u);
+                umma_tf32(tacc, ah + (PT_XBYTES >> 4), bh, idesc, s != 0 ? 1u : 0u);         // x_lo * w_hi, channels 0..7
+                umma_tf32(tacc, ah, bh + 4, idesc, 1u);                                      // x_hi * w_lo
+                umma_tf32(tacc, ah + ((PT_XBYTES + 1024) >> 4), bh + 2, idesc, 1u);          // channels 8..15
+                umma_tf32(tacc, ah + (1024 >> 4), bh + 6, idesc, 1u);
               }
               if (++st == PT_STAGES) { st = 0; ph ^= 1; }
             }
@@ -300,7 +290,8 @@ pw_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       // rows per warp), from which all eight epilogue warps store 16 bytes per lane (512 contiguous bytes of one channel plane per
       // warp) after adding the bias / applying ReLU.  A warp owns two slabs (its columns jb = 0 and jb = 32); with BN > 64 the
       // tile has four rounds, the warps of column half `ch` filling rounds 2 ch and 2 ch + 1.  (Storing straight from the
-      // registers -- 128 predicated 4-byte stores per lane, each with its own address -- cost 6 us per tile.)
+      // registers -- 128 predicated 4-byte stores per lane, each with its own address -- cost 6 us per tile; handing the slab's 1 KB
+      // rows to the bulk-copy engine instead of storing them with LDS + STG.128 was measured 1.3-1.4x slower.)
       const int n0 = nt * p.per;
       const int nreal = min(p.per, p.Co - n0);                      // real output channels of this N tile
       const size_t plane = (size_t)p.out_cstride * p.ppi;
@@ -365,33 +356,31 @@ static inline int pt_kpad(int C) { return (C + PT_KC - 1) / PT_KC * PT_KC; }
 
 extern "C" size_t cdn_pw_tf32x3_packed_floats(int Co, int C) {
   if (Co < 1 || C < 1) return 0;
-  return (size_t)pt_nt(Co) * pt_bn(Co) * pt_kpad(C);
+  return (size_t)pt_nt(Co) * pt_bn(Co) * pt_kpad(C) * 2;
 }
 
-__global__ void pw_tf32x3_pack_kernel(const float* __restrict__ w, int Co, int C, int rows, int kpad, int bn, float* __restrict__ hi,
-                                      float* __restrict__ lo) {
+// packed[row][kc][0..15] = hi, [16..31] = lo of channels kc*16 .. +16 of the row's output channel (zero padding everywhere else):
+// one 128-byte TMA row per (output channel, 16 input channels)
+__global__ void pw_tf32x3_pack_kernel(const float* __restrict__ w, int Co, int C, int rows, int kpad, int bn, float* __restrict__ packed) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)rows * kpad) return;
-  const int r = (int)(i / kpad), k = (int)(i - (long long)r * kpad);
+  if (i >= (long long)rows * kpad * 2) return;
+  const int r = (int)(i / (2 * kpad)), col = (int)(i - (long long)r * 2 * kpad);
+  const int kc = col >> 5, within = col & 31, k = kc * 16 + (within & 15);
   // packed row r = N tile r / bn, column r % bn; output channel = tile * per_tile + column with per_tile = ceil(Co / NT)
   const int nt = (Co + 127) / 128, per = (Co + nt - 1) / nt;
-  const int tile = r / bn, col = r - tile * bn;
-  const int co = tile * per + col;
+  const int tile = r / bn, cl = r - tile * bn;
+  const int co = tile * per + cl;
   float v = 0.f;
-  if (col < per && co < Co && k < C) v = w[(size_t)co * C + k];
-  uint32_t h;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
-  hi[i] = __uint_as_float(h);
-  uint32_t l;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - __uint_as_float(h)));
-  lo[i] = __uint_as_float(l);
+  if (cl < per && co < Co && k < C) v = w[(size_t)co * C + k];
+  const float h = __uint_as_float(pt_tf32(v));
+  packed[i] = (within < 16) ? h : __uint_as_float(pt_tf32(v - h));
 }
 
-extern "C" int cdn_pw_tf32x3_pack(const float* d_w, int Co, int C, float* d_hi, float* d_lo, cdn_stream_t stream) {
-  CDN_CHECK(d_w && d_hi && d_lo && Co >= 1 && C >= 1, CDN_ERR_INVALID, "pw_tf32x3_pack: bad arguments");
+extern "C" int cdn_pw_tf32x3_pack(const float* d_w, int Co, int C, float* d_packed, cdn_stream_t stream) {
+  CDN_CHECK(d_w && d_packed && Co >= 1 && C >= 1, CDN_ERR_INVALID, "pw_tf32x3_pack: bad arguments");
   const int rows = pt_nt(Co) * pt_bn(Co), kpad = pt_kpad(C);
-  const long long n = (long long)rows * kpad;
-  pw_tf32x3_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_w, Co, C, rows, kpad, pt_bn(Co), d_hi, d_lo);
+  const long long n = (long long)rows * kpad * 2;
+  pw_tf32x3_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_w, Co, C, rows, kpad, pt_bn(Co), d_packed);
   CDN_LAUNCH_CHECK("pw_tf32x3_pack_kernel");
   return 0;
 }
@@ -409,14 +398,14 @@ static PFN_encodeTiled_pt pt_get_encode() {
   return fn;
 }
 
-extern "C" int cdn_pw_slice_tf32x3(const float* input, int in_ctotal, int in_coff, int C, const float* d_whi, const float* d_wlo,
+extern "C" int cdn_pw_slice_tf32x3(const float* input, int in_ctotal, int in_coff, int C, const float* d_wpacked,
                                    const float* bias, float* output, int out_ctotal, int out_coff, int out_cstride, int Co, int relu,
                                    int B, int pixels_per_image, cdn_stream_t stream) {
-  CDN_CHECK(input && d_whi && d_wlo && output && C >= 1 && Co >= 1 && in_coff >= 0 && in_coff + C <= in_ctotal && out_cstride >= 1 &&
+  CDN_CHECK(input && d_wpacked && output && C >= 1 && Co >= 1 && in_coff >= 0 && in_coff + C <= in_ctotal && out_cstride >= 1 &&
             out_coff >= 0 && out_coff + (long long)(Co - 1) * out_cstride < out_ctotal, CDN_ERR_INVALID, "pw_slice_tf32x3: channel slice out of range");
   CDN_CHECK(pixels_per_image >= PT_M && pixels_per_image % PT_M == 0, CDN_ERR_INVALID,
             "pw_slice_tf32x3: pixels per image (%d) must be a multiple of %d", pixels_per_image, PT_M);
-  CDN_CHECK((((uintptr_t)input | (uintptr_t)output | (uintptr_t)d_whi | (uintptr_t)d_wlo) & 15) == 0, CDN_ERR_INVALID,
+  CDN_CHECK((((uintptr_t)input | (uintptr_t)output | (uintptr_t)d_wpacked) & 15) == 0, CDN_ERR_INVALID,
             "pw_slice_tf32x3: tensors must be 16-byte aligned");
   CDN_CHECK(B >= 0 && B <= 65535, CDN_ERR_INVALID, "pw_slice_tf32x3: batch out of range");
   if (B == 0) return 0;
@@ -430,25 +419,27 @@ extern "C" int cdn_pw_slice_tf32x3(const float* input, int in_ctotal, int in_cof
   CDN_CHECK(tiles < (1ull << 31), CDN_ERR_INVALID, "pw_slice_tf32x3: too many tiles");
   p.total_tiles = (unsigned)tiles; p.num_k = pt_kpad(C) / PT_KC;
   p.per = (Co + p.NT - 1) / p.NT;              // N tile nt holds channels [nt * per, nt * per + per) in its first `per` columns
-  CUtensorMap tmX, tmWh, tmWl;
+  CUtensorMap tmX, tmW;
   {
-    cuuint64_t dims[3] = {(cuuint64_t)pixels_per_image, (cuuint64_t)C, (cuuint64_t)B};
-    cuuint64_t strides[2] = {(cuuint64_t)pixels_per_image * 4, (cuuint64_t)in_ctotal * pixels_per_image * 4};
-    cuuint32_t box[3] = {32, PT_KC, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)(input + (size_t)in_coff * pixels_per_image), dims, strides, box, estr,
+    // pixels as (32, ppi / 32): dims = {32 pixels, C channels, ppi / 32 pixel groups, B}; the box order (pixels, channels, groups) is
+    // the shared-memory layout the A descriptors expect
+    cuuint64_t dims[4] = {32, (cuuint64_t)C, (cuuint64_t)pixels_per_image / 32, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)pixels_per_image * 4, 128, (cuuint64_t)in_ctotal * pixels_per_image * 4};
+    cuuint32_t box[4] = {32, PT_KC, PT_M / 32, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)(input + (size_t)in_coff * pixels_per_image), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     CDN_CHECK(r == CUDA_SUCCESS, CDN_ERR_CUDA, "pw_slice_tf32x3: activation tensor map failed with CUresult %d", (int)r);
   }
-  for (int i = 0; i < 2; ++i) {
+  {
     const int kpad = pt_kpad(C);
-    cuuint64_t dims[2] = {(cuuint64_t)kpad, (cuuint64_t)p.NT * p.BN};
-    cuuint64_t strides[1] = {(cuuint64_t)kpad * 4};
-    cuuint32_t box[2] = {PT_KC, (cuuint32_t)p.BN};
+    cuuint64_t dims[2] = {(cuuint64_t)kpad * 2, (cuuint64_t)p.NT * p.BN};
+    cuuint64_t strides[1] = {(cuuint64_t)kpad * 8};
+    cuuint32_t box[2] = {32, (cuuint32_t)p.BN};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(i ? &tmWl : &tmWh, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)(i ? d_wlo : d_whi), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+    CUresult r = enc(&tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)d_wpacked, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     CDN_CHECK(r == CUDA_SUCCESS, CDN_ERR_CUDA, "pw_slice_tf32x3: weight tensor map failed with CUresult %d", (int)r);
   }
@@ -463,8 +454,8 @@ extern "C" int cdn_pw_slice_tf32x3(const float* input, int in_ctotal, int in_cof
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const unsigned grid = (unsigned)std::min<unsigned long long>(tiles, (unsigned long long)sms);
   // template argument = pipeline stages (of 16 channels) accumulated in the tensor core before the sum moves to registers
-  if (g_cdn_debug_flags & (1u << 31)) pw_tf32x3_kernel<2><<<grid, PT_THREADS, smem, (cudaStream_t)stream>>>(tmX, tmWh, tmWl, p);
-  else pw_tf32x3_kernel<1><<<grid, PT_THREADS, smem, (cudaStream_t)stream>>>(tmX, tmWh, tmWl, p);
+  if (g_cdn_debug_flags & (1u << 31)) pw_tf32x3_kernel<2><<<grid, PT_THREADS, smem, (cudaStream_t)stream>>>(tmX, tmW, p);
+  else pw_tf32x3_kernel<1><<<grid, PT_THREADS, smem, (cudaStream_t)stream>>>(tmX, tmW, p);
   CDN_LAUNCH_CHECK("pw_tf32x3_kernel");
   return 0;
 }

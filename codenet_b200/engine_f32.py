@@ -50,7 +50,7 @@ class EngineF32:
         # level of the reference's own fp32 evaluation (tests/test_gpu_f32.py states both bounds)
         self.gemm = gemm
         self.P = {}
-        self.Ptc = {}                           # name -> (w_hi, w_lo) packed for cdn_pw_slice_tf32x3
+        self.Ptc = {}                           # name -> weights split and packed for cdn_pw_slice_tf32x3
         self._def_ws = None                     # scale scalars of the deformable modules (8 bytes per pixel), grown on demand
         self._dec_ws = None                     # ctdet decode candidate buffer, grown on demand
         self.scale_bias = {}                    # host copies of the offset-scale conv biases (kernel arguments by value)
@@ -67,10 +67,10 @@ class EngineF32:
             for name in pw_names:
                 wd = self.P[name][0]
                 n = int(self.lib.cdn_pw_tf32x3_packed_floats(wd.shape[0], wd.shape[1]))
-                hi, lo = torch.empty(n, dtype=torch.float32, device=self.dev), torch.empty(n, dtype=torch.float32, device=self.dev)
+                packed = torch.empty(n, dtype=torch.float32, device=self.dev)
                 with torch.cuda.device(self.dev):
-                    _lib.check(self.lib.cdn_pw_tf32x3_pack(self._p(wd), wd.shape[0], wd.shape[1], self._p(hi), self._p(lo), self._st()))
-                self.Ptc[name] = (hi, lo)
+                    _lib.check(self.lib.cdn_pw_tf32x3_pack(self._p(wd), wd.shape[0], wd.shape[1], self._p(packed), self._st()))
+                self.Ptc[name] = packed
 
     # -- thin kernel wrappers ---------------------------------------------------------------------------------------------
     def _st(self):
@@ -84,8 +84,7 @@ class EngineF32:
         w, b = self.P[name]
         B, ct, H, W = x.shape
         if name in self.Ptc and (H * W) % 256 == 0 and w.shape[1] == cin:
-            hi, lo = self.Ptc[name]
-            _lib.check(self.lib.cdn_pw_slice_tf32x3(self._p(x), ct, in_off, cin, self._p(hi), self._p(lo), self._p(b), self._p(out), out.shape[1],
+            _lib.check(self.lib.cdn_pw_slice_tf32x3(self._p(x), ct, in_off, cin, self._p(self.Ptc[name]), self._p(b), self._p(out), out.shape[1],
                                                     out_off, out_stride, w.shape[0], 1 if relu else 0, B, H * W, self._st()))
             return
         _lib.check(self.lib.cdn_pw_slice_f32(self._p(x), ct, in_off, cin, self._p(w), self._p(b), self._p(out), out.shape[1], out_off,

@@ -260,13 +260,14 @@ int cdn_pw_slice_f32(const float* input, int in_ctotal, int in_coff, int C, cons
                      float* output, int out_ctotal, int out_coff, int out_cstride, int Co, int relu, int B,
                      int pixels_per_image, cdn_stream_t stream);
 /* The same 1x1 convolution on the tensor cores (tcgen05 kind::tf32, csrc/pw_tf32.cu): every product is formed from a 3-way
- * TF32 split (x_hi*w_hi + x_hi*w_lo + x_lo*w_hi, each within ~2^-21 of the exact product) and summed in the fp32 TMEM
- * accumulator.  The weights are split once: cdn_pw_tf32x3_pack writes the two packed arrays (cdn_pw_tf32x3_packed_floats
- * floats each) from the [Co][C] fp32 matrix.  pixels_per_image must be a multiple of 256 (CDN_ERR_INVALID otherwise: use
- * cdn_pw_slice_f32); all other arguments as cdn_pw_slice_f32. */
+ * TF32 split (x_hi*w_hi + x_hi*w_lo + x_lo*w_hi, each within ~2^-21 of the exact product); the tensor core only ever sums 16
+ * input channels, these chunk sums are added in fp32 (round to nearest) in registers.  The weights are split once:
+ * cdn_pw_tf32x3_pack writes the packed array (cdn_pw_tf32x3_packed_floats floats) from the [Co][C] fp32 matrix.
+ * pixels_per_image must be a multiple of 256 (CDN_ERR_INVALID otherwise: use cdn_pw_slice_f32); all other arguments as
+ * cdn_pw_slice_f32. */
 size_t cdn_pw_tf32x3_packed_floats(int Co, int C);
-int cdn_pw_tf32x3_pack(const float* d_w, int Co, int C, float* d_hi, float* d_lo, cdn_stream_t stream);
-int cdn_pw_slice_tf32x3(const float* input, int in_ctotal, int in_coff, int C, const float* d_whi, const float* d_wlo,
+int cdn_pw_tf32x3_pack(const float* d_w, int Co, int C, float* d_packed, cdn_stream_t stream);
+int cdn_pw_slice_tf32x3(const float* input, int in_ctotal, int in_coff, int C, const float* d_wpacked,
                         const float* bias, float* output, int out_ctotal, int out_coff, int out_cstride, int Co, int relu,
                         int B, int pixels_per_image, cdn_stream_t stream);
 int cdn_copy_channels_f32(const float* input, int in_ctotal, int in_coff, float* output, int out_ctotal, int out_coff,

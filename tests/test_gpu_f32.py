@@ -72,10 +72,10 @@ def test_pw_tf32x3_matches_fp64(C, Co, ppi, B, in_ct, in_off, out_ct, out_off, o
     bias = rng.normal(0, 1, Co).astype(np.float32)
     tx, tw, tb = torch.from_numpy(x).cuda(), torch.from_numpy(w).cuda(), torch.from_numpy(bias).cuda()
     n = int(L.cdn_pw_tf32x3_packed_floats(Co, C))
-    hi, lo = torch.empty(n, device="cuda"), torch.empty(n, device="cuda")
-    _lib.check(L.cdn_pw_tf32x3_pack(ptr(tw), Co, C, ptr(hi), ptr(lo), stream()))
+    packed = torch.empty(n, device="cuda")
+    _lib.check(L.cdn_pw_tf32x3_pack(ptr(tw), Co, C, ptr(packed), stream()))
     out = torch.full((B, out_ct, ppi), -77.0, device="cuda")
-    _lib.check(L.cdn_pw_slice_tf32x3(ptr(tx), in_ct, in_off, C, ptr(hi), ptr(lo), ptr(tb), ptr(out), out_ct, out_off, out_cs, Co, relu,
+    _lib.check(L.cdn_pw_slice_tf32x3(ptr(tx), in_ct, in_off, C, ptr(packed), ptr(tb), ptr(out), out_ct, out_off, out_cs, Co, relu,
                                      B, ppi, stream()))
     torch.cuda.synchronize()
     got = out.cpu().numpy()
@@ -94,7 +94,7 @@ def test_pw_tf32x3_matches_fp64(C, Co, ppi, B, in_ct, in_off, out_ct, out_off, o
     d = (out2.cpu().numpy()[:, ch].astype(np.float64) - got[:, ch])
     assert np.sqrt((d ** 2).sum() / (ref ** 2).sum()) <= 1e-5
     # pixel counts that are not a multiple of 256 are refused (the caller keeps cdn_pw_slice_f32 for them)
-    assert L.cdn_pw_slice_tf32x3(ptr(tx), in_ct, in_off, C, ptr(hi), ptr(lo), ptr(tb), ptr(out), out_ct, out_off, out_cs, Co, relu,
+    assert L.cdn_pw_slice_tf32x3(ptr(tx), in_ct, in_off, C, ptr(packed), ptr(tb), ptr(out), out_ct, out_off, out_cs, Co, relu,
                                  B, 128, stream()) == -1
 
 

@@ -15,12 +15,12 @@ for name, Cc, Co, ppi in shapes:
     if only and name != only: continue
     x = torch.randn(B, Cc, ppi, device="cuda"); w = torch.randn(Co, Cc, device="cuda") / Cc ** 0.5
     n = int(L.cdn_pw_tf32x3_packed_floats(Co, Cc))
-    hi, lo = torch.empty(n, device="cuda"), torch.empty(n, device="cuda")
-    _lib.check(L.cdn_pw_tf32x3_pack(ptr(w), Co, Cc, ptr(hi), ptr(lo), st()))
+    packed = torch.empty(n, device="cuda")
+    _lib.check(L.cdn_pw_tf32x3_pack(ptr(w), Co, Cc, ptr(packed), st()))
     out = torch.empty(B, Co, ppi, device="cuda")
     for flags in ((0, 1 << 31) if not os.environ.get('PT_DBG') else (0, 1 << 8, 7 << 8)):
         L.cdn_set_debug_flags(flags)
-        f = lambda: _lib.check(L.cdn_pw_slice_tf32x3(ptr(x), Cc, 0, Cc, ptr(hi), ptr(lo), None, ptr(out), Co, 0, 1, Co, 1, B, ppi, st()))
+        f = lambda: _lib.check(L.cdn_pw_slice_tf32x3(ptr(x), Cc, 0, Cc, ptr(packed), None, ptr(out), Co, 0, 1, Co, 1, B, ppi, st()))
         for _ in range(3): f()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
