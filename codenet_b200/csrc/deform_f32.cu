@@ -110,7 +110,17 @@ __global__ void __launch_bounds__(256) deform_scale_f32_kernel(DefDwF32Params p)
     const int ho = px / p.Wo, wo = px - ho * p.Wo;
     const size_t plane = (size_t)p.H * p.W;
     const float* x = p.in + (size_t)b * p.C * plane + (size_t)(ho * p.stride) * p.W + wo * p.stride;   // conv_scale: kernel 1, padding 0
-    for (int c = grp; c < p.C; c += 8) sd = fma((double)__ldg(p.ws + c), (double)__ldg(x + c * plane), sd);
+    // four independent chains per thread (the single chain left the loads waiting behind a dependent fp64 FMA each)
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int c = grp;
+    for (; c + 24 < p.C; c += 32) {
+      s0 = fma((double)__ldg(p.ws + c), (double)__ldg(x + (size_t)c * plane), s0);
+      s1 = fma((double)__ldg(p.ws + c + 8), (double)__ldg(x + (size_t)(c + 8) * plane), s1);
+      s2 = fma((double)__ldg(p.ws + c + 16), (double)__ldg(x + (size_t)(c + 16) * plane), s2);
+      s3 = fma((double)__ldg(p.ws + c + 24), (double)__ldg(x + (size_t)(c + 24) * plane), s3);
+    }
+    for (; c < p.C; c += 8) s0 = fma((double)__ldg(p.ws + c), (double)__ldg(x + (size_t)c * plane), s0);
+    sd = (s0 + s1) + (s2 + s3);
   }
   part[grp][lane] = sd;
   __syncthreads();

@@ -40,6 +40,52 @@ __global__ void __launch_bounds__(128) conv3x3_f32_kernel(const float* __restric
   }
 }
 
+// the stride-4 stem (Ci = 3, W % 4 == 0): the three taps of a row are columns 4 wo - 1 .. 4 wo + 1, i.e. one aligned 16-byte load
+// per lane (fully coalesced where the scalar kernel reads every fourth float) plus the left halo; weights transposed to
+// [ci][tap][co] in shared memory so that one broadcast LDS.128 feeds four output channels.  Same FMA order per output.
+__global__ void __launch_bounds__(128) conv3x3_s4_f32_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
+                                                             float* __restrict__ out, int Ci, int Co, int H, int W, int Ho, int Wo, int relu,
+                                                             unsigned total) {
+  extern __shared__ __align__(16) float sw[];   // [Ci][9][C3_MAXCO] + [C3_MAXCO]
+  for (int i = threadIdx.x; i < Ci * 9 * C3_MAXCO; i += blockDim.x) {
+    const int co = i % C3_MAXCO, t = i / C3_MAXCO;                  // t = ci * 9 + tap
+    sw[i] = co < Co ? w[(size_t)co * Ci * 9 + t] : 0.f;
+  }
+  for (int i = threadIdx.x; i < C3_MAXCO; i += blockDim.x) sw[Ci * 9 * C3_MAXCO + i] = (bias && i < Co) ? bias[i] : 0.f;
+  __syncthreads();
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const unsigned wo = idx % (unsigned)Wo; const unsigned t = idx / (unsigned)Wo; const unsigned ho = t % (unsigned)Ho; const unsigned b = t / (unsigned)Ho;
+  float acc[C3_MAXCO];
+#pragma unroll
+  for (int c = 0; c < C3_MAXCO; ++c) acc[c] = sw[Ci * 9 * C3_MAXCO + c];
+  for (int ci = 0; ci < Ci; ++ci) {
+    const float* plane = in + ((size_t)b * Ci + ci) * H * W;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int y = (int)ho * 4 - 1 + i;
+      const bool rv = (unsigned)y < (unsigned)H;
+      const float* rp = plane + (size_t)(rv ? y : 0) * W + 4 * wo;
+      const float4 q = __ldg((const float4*)rp);
+      const float v[3] = {(rv && wo > 0) ? __ldg(rp - 1) : 0.f, rv ? q.x : 0.f, rv ? q.y : 0.f};
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const float4* wp = (const float4*)(sw + ((ci * 9 + i * 3 + j) * C3_MAXCO));
+#pragma unroll
+        for (int c4 = 0; c4 < C3_MAXCO / 4; ++c4) {
+          const float4 ww = wp[c4];
+          acc[4 * c4] = fmaf(ww.x, v[j], acc[4 * c4]); acc[4 * c4 + 1] = fmaf(ww.y, v[j], acc[4 * c4 + 1]);
+          acc[4 * c4 + 2] = fmaf(ww.z, v[j], acc[4 * c4 + 2]); acc[4 * c4 + 3] = fmaf(ww.w, v[j], acc[4 * c4 + 3]);
+        }
+      }
+    }
+  }
+  float* op = out + ((size_t)b * Co * Ho + ho) * Wo + wo;
+#pragma unroll
+  for (int c = 0; c < C3_MAXCO; ++c)
+    if (c < Co) op[(size_t)c * Ho * Wo] = relu ? fmaxf(acc[c], 0.f) : acc[c];
+}
+
 extern "C" int cdn_conv3x3_f32(const float* input, const float* weight, const float* bias, float* output, int B, int Ci, int Co,
                                int H, int W, int stride, int relu, cdn_stream_t stream) {
   CDN_CHECK(input && weight && output && Ci >= 1 && Co >= 1 && Co <= C3_MAXCO && stride >= 1, CDN_ERR_INVALID,
@@ -47,6 +93,12 @@ extern "C" int cdn_conv3x3_f32(const float* input, const float* weight, const fl
   const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
   const long long total = (long long)B * Ho * Wo;
   if (total == 0) return 0;
+  if (stride == 4 && W % 4 == 0 && ((uintptr_t)input & 15) == 0 && total < (1ll << 32) - 128 && (size_t)(Ci * 9 + 1) * C3_MAXCO * 4 <= 48 * 1024) {
+    conv3x3_s4_f32_kernel<<<(unsigned)((total + 127) / 128), 128, (size_t)(Ci * 9 + 1) * C3_MAXCO * sizeof(float), (cudaStream_t)stream>>>(
+        input, weight, bias, output, Ci, Co, H, W, Ho, Wo, relu, (unsigned)total);
+    CDN_LAUNCH_CHECK("conv3x3_s4_f32_kernel");
+    return 0;
+  }
   const size_t smem = ((size_t)Co * Ci * 9 + Co) * sizeof(float);
   conv3x3_f32_kernel<<<(unsigned)((total + 127) / 128), 128, smem, (cudaStream_t)stream>>>(input, weight, bias, output, Ci, Co, H, W, Ho, Wo,
                                                                                          stride, relu, total);
@@ -109,6 +161,39 @@ __global__ void __launch_bounds__(256) dw3x3_f32_s1v4_kernel(const float* __rest
   float4 o4 = make_float4(acc[0], acc[1], acc[2], acc[3]);
   if (relu) { o4.x = fmaxf(o4.x, 0.f); o4.y = fmaxf(o4.y, 0.f); o4.z = fmaxf(o4.z, 0.f); o4.w = fmaxf(o4.w, 0.f); }
   *(float4*)(out + (size_t)t * H * W + (size_t)y * W + x0) = o4;
+}
+
+// stride 2, W % 8 == 0: one thread = 4 adjacent outputs of a row from two aligned 16-byte loads + the left halo per input row
+// (9 loads per 4 outputs instead of 36, 32-bit index arithmetic); same taps in the same order per output.
+__global__ void __launch_bounds__(256) dw3x3_f32_s2v4_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
+                                                             float* __restrict__ out, int C, int H, int W, int Ho, int Wo, int relu, unsigned total4) {
+  const unsigned idx = blockIdx.x * 256u + threadIdx.x;
+  if (idx >= total4) return;
+  const unsigned Wo4 = (unsigned)Wo >> 2;
+  const unsigned x4 = idx % Wo4; unsigned t = idx / Wo4; const unsigned ho = t % (unsigned)Ho; const unsigned pl = t / (unsigned)Ho;
+  const int c = (int)(pl % (unsigned)C);
+  const float* plane = in + (size_t)pl * H * W;
+  float wk[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) wk[i] = __ldg(w + c * 9 + i);
+  const float b0 = bias ? __ldg(bias + c) : 0.f;
+  float acc[4] = {b0, b0, b0, b0};
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int y = (int)ho * 2 - 1 + i;
+    const bool rv = (unsigned)y < (unsigned)H;
+    const float* rp = plane + (size_t)(rv ? y : 0) * W + 8 * x4;
+    float4 a = __ldg((const float4*)rp), b = __ldg((const float4*)rp + 1);
+    if (!rv) { a = make_float4(0.f, 0.f, 0.f, 0.f); b = a; }
+    const float v[9] = {(rv && x4 > 0) ? __ldg(rp - 1) : 0.f, a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+      for (int o = 0; o < 4; ++o) acc[o] = fmaf(wk[i * 3 + j], v[2 * o + j], acc[o]);
+  }
+  float4 o4 = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  if (relu) { o4.x = fmaxf(o4.x, 0.f); o4.y = fmaxf(o4.y, 0.f); o4.z = fmaxf(o4.z, 0.f); o4.w = fmaxf(o4.w, 0.f); }
+  *(float4*)(out + ((size_t)pl * Ho + ho) * Wo + 4 * x4) = o4;
 }
 
 // stride 1 with H and W multiples of 4: one thread = 4 x 4 outputs.  Six row reads (one 16-byte load each; the two halo
@@ -251,6 +336,12 @@ extern "C" int cdn_dw3x3_f32(const float* input, const float* weight, const floa
     const long long total4 = total / 4;
     dw3x3_f32_s1v4_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(input, weight, bias, output, C, H, W, relu, total4);
     CDN_LAUNCH_CHECK("dw3x3_f32_s1v4_kernel");
+    return 0;
+  }
+  if (stride == 2 && W % 8 == 0 && ((((uintptr_t)input) | ((uintptr_t)output)) & 15) == 0 && total / 4 < (1ll << 32) - 256) {
+    const unsigned total4 = (unsigned)(total / 4);
+    dw3x3_f32_s2v4_kernel<<<(total4 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(input, weight, bias, output, C, H, W, Ho, Wo, relu, total4);
+    CDN_LAUNCH_CHECK("dw3x3_f32_s2v4_kernel");
     return 0;
   }
   dw3x3_f32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(input, weight, bias, output, C, H, W, Ho, Wo, stride, relu, total);

@@ -157,3 +157,28 @@ def test_dw3x3_over_virtual_upsample_equals_upsample_then_dw(B, C, h, w):
     _lib.check(L.cdn_dw3x3_up2_f32(ptr(a), ptr(wt), ptr(bias), ptr(got), B, C, h, w, 1, stream()))
     torch.cuda.synchronize()
     assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("B,Co,H,W,stride", [(2, 24, 64, 64, 4), (1, 24, 32, 48, 4), (2, 24, 30, 26, 4), (1, 24, 32, 32, 2), (1, 7, 16, 20, 4)])
+def test_stem_conv3x3_f32_matches_numpy(B, Co, H, W, stride):
+    """cdn_conv3x3_f32 = the float model's stem conv (3 -> Co, 3x3, pad 1, stride 4 or 2, + folded BN bias + ReLU,
+    shufflenetv2_dcn.py:196-203): the stride-4 kernel with 16-byte loads and the general scalar kernel against the fp64 sum."""
+    import torch
+    from codenet_b200 import _lib
+    from gpu_util import ptr, stream
+    rng = np.random.default_rng(H * 7 + W + Co)
+    x = rng.normal(0, 1, (B, 3, H, W)).astype(np.float32)
+    w = (rng.normal(0, 1, (Co, 3, 3, 3)) / 5).astype(np.float32)
+    bias = rng.normal(0, 1, Co).astype(np.float32)
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    xp = np.pad(x.astype(np.float64), ((0, 0), (0, 0), (1, 1), (1, 1)))
+    ref = np.zeros((B, Co, Ho, Wo))
+    for i in range(3):
+        for j in range(3):
+            ref += np.einsum("oc,bchw->bohw", w[:, :, i, j].astype(np.float64), xp[:, :, i:i + stride * Ho:stride, j:j + stride * Wo:stride][:, :, :Ho, :Wo])
+    ref = np.maximum(ref + bias[None, :, None, None], 0)
+    tx, tw, tb = torch.from_numpy(x).cuda(), torch.from_numpy(w).cuda(), torch.from_numpy(bias).cuda()
+    out = torch.full((B, Co, Ho, Wo), -7.0, device="cuda")
+    _lib.check(_lib.load().cdn_conv3x3_f32(ptr(tx), ptr(tw), ptr(tb), ptr(out), B, 3, Co, H, W, stride, 1, stream()))
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=3e-6, atol=3e-6)
