@@ -164,6 +164,16 @@ __global__ void __launch_bounds__(128, 4) deform_gather_f32_kernel(DefDwF32Param
   const int c_begin = blockIdx.y * DDF_CG, c_end = min(c_begin + DDF_CG, p.C);
   const float* img = p.in + ((size_t)b * p.C + c_begin) * plane;
   float* ob = p.out + ((size_t)b * p.C + c_begin) * npx + px;
+  // The centre tap row / column sits at an integral position (its offset is 0 * d): its lower / right corners carry weight
+  // exactly 0 and are not loaded -- 25 loads per channel instead of 36 (corner taps 4, edge taps 2, centre 1); a skipped term is
+  // an exact +0 in the reference's sum.  The corner weights are per pixel, not per channel: hoisted out of the channel loop.
+  float w4[3][3][4];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      w4[i][j][0] = wra[i] * wca[j]; w4[i][j][1] = wra[i] * wcb[j]; w4[i][j][2] = wrb[i] * wca[j]; w4[i][j][3] = wrb[i] * wcb[j];
+    }
   for (int c = c_begin; c < c_end; ++c, img += plane, ob += npx) {
     const float* wk = p.wdw + c * 9;
     float acc = 0.f;
@@ -173,8 +183,10 @@ __global__ void __launch_bounds__(128, 4) deform_gather_f32_kernel(DefDwF32Param
       const float* pb = img + rb[i];
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
-        const float v1 = __ldg(pa + ca[j]), v2 = __ldg(pa + cb[j]), v3 = __ldg(pb + ca[j]), v4 = __ldg(pb + cb[j]);
-        const float val = wra[i] * wca[j] * v1 + wra[i] * wcb[j] * v2 + wrb[i] * wca[j] * v3 + wrb[i] * wcb[j] * v4;
+        float val = w4[i][j][0] * __ldg(pa + ca[j]);
+        if (j != 1) val += w4[i][j][1] * __ldg(pa + cb[j]);
+        if (i != 1) val += w4[i][j][2] * __ldg(pb + ca[j]);
+        if (i != 1 && j != 1) val += w4[i][j][3] * __ldg(pb + cb[j]);
         acc = fmaf(__ldg(wk + i * 3 + j), val, acc);
       }
     }
