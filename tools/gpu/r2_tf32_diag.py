@@ -5,6 +5,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, torch, ctypes as C
 from codenet_b200 import _lib
 L = _lib.load()
+L.cdn_set_debug_flags(int(os.environ.get('PT_FLAGS', '0')))
 ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
 st = lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream)
 def run(x, w, Co, Cc, ppi, B):
