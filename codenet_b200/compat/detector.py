@@ -114,8 +114,26 @@ class CtdetDetector:
         if opt.gpus[0] < 0 or not torch.cuda.is_available():
             raise RuntimeError("codenet_b200 has no CPU execution path: CtdetDetector needs a B200 (opt.gpus >= 0)")
         opt.device = torch.device("cuda", opt.gpus[0])
-        if not opt.resume_quantize:
-            raise NotImplementedError("only the quantised (W4A8) path is built; pass resume_quantize=True")
+        self.opt = opt
+        self.float_model = not opt.resume_quantize
+        self.mean = np.array(opt.mean, dtype=np.float32).reshape(1, 1, 3)
+        self.std = np.array(opt.std, dtype=np.float32).reshape(1, 1, 3)
+        self.max_per_image = 100
+        self.num_classes = opt.num_classes
+        self.scales = opt.test_scales
+        if self.float_model:
+            # the unquantised model (test.py without --resume-quantize): its state dict in the reference's key space feeds
+            # engine_f32.EngineF32 (fp32 NCHW kernels; opt.f32_gemm = "fp32" | "tf32x3" selects the 1x1-conv arithmetic)
+            sd = getattr(opt, "state_dict", None)
+            if getattr(opt, "load_model", ""):
+                ck = torch.load(opt.load_model, map_location="cpu")
+                sd = ck["state_dict"] if "state_dict" in ck else ck
+            if sd is None:
+                raise RuntimeError("float CtdetDetector needs opt.load_model or opt.state_dict")
+            self._f32_state = {(k[7:] if k.startswith("module.") else k): v for k, v in sd.items()}
+            self._f32_engines = {}
+            self.model = None
+            return
         self.model = PoseShuffleNetV2(opt.heads, opt.head_conv, w2=opt.w2, maxpool=opt.maxpool)
         quantize_shufflenetv2_dcn(self.model, quant_conv=opt.w_bit, quant_bn=None, quant_act=opt.a_bit,
                                   wt_quant_mode='symmetric', act_quant_mode='asymmetric', wt_per_channel=True,
@@ -218,6 +236,8 @@ class CtdetDetector:
         """Fast path of run(): uint8 [B,H,W,3] images already at the network's input size (then the reference's
         resize + warpAffine of pre_process are the identity and only the normalisation is left, which the stem kernel
         applies).  CUDA tensor in, same outputs as process()."""
+        if self.float_model:
+            return self._process_float(images_u8, return_time)
         B, H, W, _ = images_u8.shape
         dev = images_u8.device.index if images_u8.device.index is not None else torch.cuda.current_device()
         out = self._engine_for(H, W, B, dev).run(images_u8.contiguous(), maps=True, dets=True)
@@ -226,11 +246,47 @@ class CtdetDetector:
         output = {h: out[h] for h in self.opt.heads}
         return (output, out["dets"], forward_time) if return_time else (output, out["dets"])
 
+    def _process_float(self, images, return_time):
+        """process() for the unquantised model: EngineF32 forward (logits), hm.sigmoid_() as ctdet.py:32, decode on the device."""
+        from ..arch import NetConfig
+        from ..engine_f32 import EngineF32
+        if images.dtype == torch.uint8:                              # pre_process_device's layout: normalise as base_detector.py:66-68
+            mean = torch.as_tensor(self.mean.reshape(3), device=images.device)
+            std = torch.as_tensor(self.std.reshape(3), device=images.device)
+            images = ((images.float() / 255.0 - mean) / std).permute(0, 3, 1, 2)
+        x = images.contiguous().float()
+        B = x.shape[0]
+        dev = x.device.index if x.device.index is not None else torch.cuda.current_device()
+        eng = self._f32_engines.get(dev)
+        if eng is None:
+            cfg = NetConfig(num_classes=int(self.opt.heads["hm"]), w2=bool(self.opt.w2), maxpool=bool(self.opt.maxpool))
+            eng = self._f32_engines[dev] = EngineF32(cfg, self._f32_state, device=dev, K=self.opt.K,
+                                                     gemm=getattr(self.opt, "f32_gemm", "fp32"))
+        if not self.opt.flip_test and self.opt.reg_offset:
+            dets, _, v = eng.detect(x)
+            hm, wh, reg = v["hm"].sigmoid(), v["wh"], v.get("reg")
+        else:
+            v = eng.forward(x)
+            hm, wh, reg = v["hm"].sigmoid(), v["wh"].contiguous(), (v.get("reg") if self.opt.reg_offset else None)
+            if self.opt.flip_test:
+                hm = (hm[0::2] + torch.flip(hm[1::2], [3])) / 2
+                wh = (wh[0::2] + torch.flip(wh[1::2], [3])) / 2
+                reg = reg[0::2] if reg is not None else None
+            dets = ctdet_decode(hm, wh, reg=reg, cat_spec_wh=self.opt.cat_spec_wh, K=self.opt.K)
+        output = {"hm": hm, "wh": wh}
+        if reg is not None:
+            output["reg"] = reg
+        torch.cuda.synchronize(x.device)
+        forward_time = time.time()
+        return (output, dets, forward_time) if return_time else (output, dets)
+
     def process(self, images, return_time=False):
         """images: CUDA fp32 [B,3,H,W] (the reference's tensor) or uint8 [B,H,W,3] (pre_process_device).
         Returns (output {'hm' (post-sigmoid), 'wh', 'reg'}, dets [B|1,K,6][, time])."""
         if not images.is_cuda:
             raise RuntimeError("codenet_b200 has no CPU execution path: process() needs CUDA images")
+        if self.float_model:
+            return self._process_float(images, return_time)
         if images.dtype == torch.uint8:
             B, H, W, _ = images.shape
             x = images.contiguous()

@@ -269,3 +269,38 @@ def test_ctdet_decode_edge_cases_from_the_reference(golden):
             j += 1
         assert sorted(map(key, d[i:j + 1])) == sorted(map(key, ref[i:j + 1])), (i, j)
         i = j + 1
+
+
+@pytest.mark.parametrize("gemm", ["fp32", "tf32x3"])
+def test_detector_float_model(golden, gemm):
+    """CtdetDetector with resume_quantize=False (the reference's float test.py run) routes through EngineF32: the heads equal the
+    fp64 reference run within the float-path bounds of tests/test_gpu_f32.py, `hm` comes back post-sigmoid (ctdet.py:32), and
+    flip_test averages the mirrored pass like ctdet.py:35-38."""
+    import torch
+    from codenet_b200 import compat
+    from codenet_b200.compat.detector import default_opt
+    from codenet_b200.synth import make_raw_state
+    g = golden("codenet_float_1x_256.npz")
+    raw = make_raw_state(CFG, 0)
+    for k in g.files:
+        if k.startswith("bn/"):
+            raw[k[3:]] = g[k]
+    opt = default_opt(resume_quantize=False, state_dict={k: torch.from_numpy(np.asarray(v)) for k, v in raw.items()}, input_h=256, input_w=256,
+                      f32_gemm=gemm)
+    det = compat.CtdetDetector(opt)
+    x = torch.from_numpy(make_images(2, 256, seed=2)).cuda()
+    output, dets = det.process(x[:1])
+    slack = 1.5 if gemm == "tf32x3" else 1.0
+    for name, ref in (("hm", 1 / (1 + np.exp(-g["hm_logit"].astype(np.float64)))), ("wh", g["wh"].astype(np.float64)), ("reg", g["reg"].astype(np.float64))):
+        got = output[name].cpu().numpy().astype(np.float64)
+        l2 = np.sqrt(((got - ref) ** 2).sum() / (ref ** 2).sum())
+        assert l2 <= max(1e-4, slack * float(g["ref_fp32_l2rel/" + name])), (name, l2)
+    assert dets.shape == (1, 100, 6)
+    np.testing.assert_allclose(np.sort(dets[0, :, 4].cpu().numpy())[::-1][:50], np.sort(g["dets"][0][:, 4])[::-1][:50], rtol=1e-3)
+    det.opt.flip_test = True
+    pair = torch.cat([x[:1], torch.flip(x[:1], [3])])
+    o2, d2 = det.process(pair)
+    det.opt.flip_test = False
+    o3, _ = det.process(pair)
+    want_hm = (o3["hm"][0:1] + torch.flip(o3["hm"][1:2], [3])) / 2
+    assert torch.equal(o2["hm"], want_hm) and d2.shape == (1, 100, 6)

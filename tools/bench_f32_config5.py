@@ -130,19 +130,41 @@ def run_ours(args, C):
     value = world * B * args.steps / (ms / 1e3)
     # end to end: fp32 NCHW images from pinned host memory each step, detections back to the host
     dets_h = torch.empty((B, 100, 6), dtype=torch.float32).pin_memory()
-    n_e2e = max(2, min(args.steps, 5))
+    n_e2e = max(4, min(args.steps, 10))
 
-    def e2e_step():
-        x.copy_(host, non_blocking=True)
-        step()
-        dets_h.copy_(static["dets"], non_blocking=True)
+    # pipelined submit: the H2D copy of step n + 1 (copy stream, its own staging buffer) runs under the compute of step n; every
+    # step's detections are copied back to pinned memory.  Two staging buffers, events in both directions.
+    copy_stream = torch.cuda.Stream()
+    xs = [torch.empty_like(x) for _ in range(2)]
+    h2d_done = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    main = torch.cuda.current_stream()
+
+    def submit_copy(j):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[j])
+            xs[j].copy_(host, non_blocking=True)
+            h2d_done[j].record(copy_stream)
+
+    def e2e_run(n):
+        for j in range(2):
+            consumed[j].record(main)
+        submit_copy(0)
+        for i in range(n):
+            j = i & 1
+            if i + 1 < n:
+                submit_copy(j ^ 1)
+            main.wait_event(h2d_done[j])
+            x.copy_(xs[j], non_blocking=True)                     # the graph reads the fixed tensor x
+            consumed[j].record(main)
+            step()
+            dets_h.copy_(static["dets"], non_blocking=True)
         torch.cuda.synchronize()
 
-    e2e_step()
+    e2e_run(2)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(n_e2e):
-        e2e_step()
+    e2e_run(n_e2e)
     e2e = world * B * n_e2e / maxr(time.perf_counter() - t0)
     clocks = sampler.stop() if rank == 0 else None
     ok, worst = check_parity(eng, g)
@@ -164,7 +186,7 @@ def run_ours(args, C):
                 "parity_checked": bool(ok_all), "parity": worst,
                 "e2e": {"value": round(e2e, 1), "unit": UNIT, "h2d_bytes_per_step": int(B * 3 * R * R * 4),
                         "d2h_bytes_per_step": int(B * 100 * 6 * 4), "steps": n_e2e,
-                        "api": "EngineF32.detect on images copied from pinned host memory every step"},
+                        "api": "EngineF32.detect on images copied from pinned host memory every step (copy of step n+1 under the compute of step n)"},
                 "gpu_launches": None, "clocks": clocks, "roofline": None, "cpu_baseline": None}
         print(json.dumps(line))
     if not ok_all:
