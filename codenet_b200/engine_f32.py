@@ -51,6 +51,8 @@ class EngineF32:
         self.gemm = gemm
         self.P = {}
         self.Ptc = {}                           # name -> weights split and packed for cdn_pw_slice_tf32x3
+        self.launches = 0                       # kernel launches issued so far (bench: gpu_launches per step)
+        self.trace = None
         self._def_ws = None                     # scale scalars of the deformable modules (8 bytes per pixel), grown on demand
         self._dec_ws = None                     # ctdet decode candidate buffer, grown on demand
         self.scale_bias = {}                    # host copies of the offset-scale conv biases (kernel arguments by value)
@@ -83,6 +85,17 @@ class EngineF32:
     def _pw(self, x, in_off, cin, name, out, out_off, out_stride, relu):
         w, b = self.P[name]
         B, ct, H, W = x.shape
+        self.launches += 1
+        if self.trace is not None:                   # per-call CUDA events of the 1x1 convs (bench roofline), eager runs only
+            e0, e1 = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
+            e0.record()
+            self.trace, tr = None, self.trace
+            self._pw(x, in_off, cin, name, out, out_off, out_stride, relu)
+            self.launches -= 1
+            self.trace = tr
+            e1.record()
+            tr.append((name, 2.0 * cin * w.shape[0] * B * H * W, e0, e1))
+            return
         if name in self.Ptc and (H * W) % 256 == 0 and w.shape[1] == cin:
             _lib.check(self.lib.cdn_pw_slice_tf32x3(self._p(x), ct, in_off, cin, self._p(self.Ptc[name]), self._p(b), self._p(out), out.shape[1],
                                                     out_off, out_stride, w.shape[0], 1 if relu else 0, B, H * W, self._st()))
@@ -92,6 +105,7 @@ class EngineF32:
 
     def _dw(self, x, name, stride, relu):
         w, b = self.P[name]
+        self.launches += 1
         B, Cc, H, W = x.shape
         out = x.new_empty((B, Cc, (H - 1) // stride + 1, (W - 1) // stride + 1))
         _lib.check(self.lib.cdn_dw3x3_f32(self._p(x), self._p(w), self._p(b), self._p(out), B, Cc, H, W, stride, 1 if relu else 0, self._st()))
@@ -111,9 +125,11 @@ class EngineF32:
             w, b = self.P["layer0"]
             s = g.stem.stride
             y = x.new_empty((B, g.stem.cout, (x.shape[2] - 1) // s + 1, (x.shape[3] - 1) // s + 1))
+            self.launches += 1
             _lib.check(L.cdn_conv3x3_f32(self._p(x), self._p(w), self._p(b), self._p(y), B, 3, g.stem.cout, x.shape[2], x.shape[3], s, 1, self._st()))
             if cfg.maxpool:
                 z = x.new_empty((B, y.shape[1], (y.shape[2] - 1) // 2 + 1, (y.shape[3] - 1) // 2 + 1))
+                self.launches += 1
                 _lib.check(L.cdn_maxpool3s2_f32(self._p(y), self._p(z), B * y.shape[1], y.shape[2], y.shape[3], self._st()))
                 y = z
             x = y
@@ -130,6 +146,7 @@ class EngineF32:
                     self._pw(d2, 0, half, r + "pw3", out, 1, 2, True)                  # x2 -> odd channels
                 else:
                     out = self._new(x, u["oup"])
+                    self.launches += 1
                     _lib.check(L.cdn_copy_channels_f32(self._p(x), u["oup"], 0, self._p(out), u["oup"], 0, 2, half, B,
                                                        x.shape[2] * x.shape[3], self._st()))
                     c1 = self._new(x, half)
@@ -149,6 +166,7 @@ class EngineF32:
                 need = int(L.cdn_deform_dw_f32_ws_bytes(Bc, H, W, 1))
                 if self._def_ws is None or self._def_ws.numel() < need:
                     self._def_ws = torch.empty(need, dtype=torch.uint8, device=self.dev)
+                self.launches += 2
                 _lib.check(L.cdn_deform_dw_f32_ws(self._p(x), self._p(ws), C.c_float(self.scale_bias["up%d.scale" % i]), cfg.offset_bound, self._p(wd),
                                                   self._p(y), Bc, Cc, H, W, 1, self._p(self._def_ws), self._def_ws.numel(), self._st()))
                 z = self._new(y, up["cout"])
@@ -156,6 +174,7 @@ class EngineF32:
                 if up is g.ups[-1] and W % 4 == 0:
                     break                                          # the last x2 upsampling is virtual: see the heads below
                 x = z.new_empty((Bc, up["cout"], 2 * H, 2 * W))
+                self.launches += 1
                 _lib.check(L.cdn_upsample2x_f32(self._p(z), self._p(x), Bc * up["cout"], H, W, self._st()))
             else:
                 z = None
@@ -175,6 +194,7 @@ class EngineF32:
                 self._pw(z, 0, 64, "heads.pw1", a, 0, 1, True)
                 d = z.new_empty((Bc, 64 * nh, 2 * H, 2 * W))
                 wdw, bdw = self.P["heads.dw2"]
+                self.launches += 1
                 _lib.check(L.cdn_dw3x3_up2_f32(self._p(a), self._p(wdw), self._p(bdw), self._p(d), Bc, 64 * nh, H, W, 1, self._st()))
             else:
                 a = self._new(x, 64 * nh)
@@ -205,6 +225,7 @@ class EngineF32:
         if self._dec_ws is None or self._dec_ws.numel() < need:
             self._dec_ws = torch.empty(need, dtype=torch.uint8, device=self.dev)
         with torch.cuda.device(self.dev):
+            self.launches += 2
             _lib.check(self.lib.cdn_ctdet_decode_ws(self._p(hm), hm.stride(0), self._p(wh), wh.stride(0), self._p(reg),
                                                     reg.stride(0) if reg is not None else 0, B, cat, H, W, self.K, 0, self._p(dets),
                                                     self._p(inds), self._p(self._dec_ws), self._dec_ws.numel(), self._st()))

@@ -167,6 +167,32 @@ def run_ours(args, C):
     e2e_run(n_e2e)
     e2e = world * B * n_e2e / maxr(time.perf_counter() - t0)
     clocks = sampler.stop() if rank == 0 else None
+    # launches per step and the 1x1-conv family's rate: one eager, event-traced forward outside the timed region
+    torch.cuda.synchronize()
+    eng.launches = 0
+    eng.trace = []
+    eng.detect(x, out)
+    torch.cuda.synchronize()
+    trace, eng.trace = eng.trace, None
+    launches = eng.launches
+    pw_ms = sum(e0.elapsed_time(e1) for _, _, e0, e1 in trace)
+    pw_flops = sum(f for _, f, _, _ in trace)
+    roofline = None
+    if gemm == "tf32x3" and pw_ms > 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:                            # noqa: BLE001
+            pass
+        bf16 = float(peaks.get("bf16_tflops_sustained", 0) or 0)
+        peak, src = (bf16 / 2.0, "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (kind::tf32 runs at half the bf16 rate)") if bf16 else \
+                    (1125.0, "fallback: nominal dense tf32 (B200_PROFILING.md: 2250 bf16 / 2)")
+        ach = pw_flops / (pw_ms * 1e-3) / 1e12
+        roofline = {"kernel": "pw_tf32x3_kernel (%d launches)" % len(trace), "bound": "tensor", "achieved": round(ach, 1), "peak": round(peak, 1),
+                    "unit": "TFLOP/s", "frac": round(ach / peak, 4), "traffic": None, "peak_source": src, "ms_per_step": round(pw_ms, 3),
+                    "share_of_step": round(pw_ms / (ms / args.steps), 3),
+                    "note": "achieved = algorithmic fp32 flops (2*C*Co*pixels, unpadded); every fp32 product costs three tf32 MMAs, so the "
+                            "ceiling of frac is 1/3; timed per launch with CUDA events in an eager pass"}
     ok, worst = check_parity(eng, g)
     t = torch.tensor([0 if ok else 1], device="cuda")
     if world > 1:
@@ -187,7 +213,7 @@ def run_ours(args, C):
                 "e2e": {"value": round(e2e, 1), "unit": UNIT, "h2d_bytes_per_step": int(B * 3 * R * R * 4),
                         "d2h_bytes_per_step": int(B * 100 * 6 * 4), "steps": n_e2e,
                         "api": "EngineF32.detect on images copied from pinned host memory every step (copy of step n+1 under the compute of step n)"},
-                "gpu_launches": None, "clocks": clocks, "roofline": None, "cpu_baseline": None}
+                "gpu_launches": launches * args.steps, "launches_per_step": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": None}
         print(json.dumps(line))
     if not ok_all:
         sys.stderr.write("bench.py --config 2x_fp32: PARITY FAILURE %s\n" % worst)
