@@ -263,11 +263,11 @@ pw_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     uint32_t g = 0;
     for (unsigned t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
       int b, px0, nt; split_tile(t, b, px0, nt);
-      float tot[2][64];
+      float2 tot[2][32];                                            // column pairs: the flush adds two columns per FADD2
 #pragma unroll
       for (int mb = 0; mb < 2; ++mb)
 #pragma unroll
-        for (int j = 0; j < 64; ++j) tot[mb][j] = 0.f;
+        for (int j = 0; j < 32; ++j) tot[mb][j] = make_float2(0.f, 0.f);
       for (int c = 0; c < nch; ++c, ++g) {
         const int cb = (int)(g & nbuf_mask); const uint32_t cph = (g >> nbuf_shift) & 1;
         pt_wait(CFULL(cb), cph);
@@ -283,7 +283,8 @@ pw_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                 tmem_ld32(tbase + (uint32_t)(i * 32), r0);
                 tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) tot[mbi][i * 32 + j] += __uint_as_float(r0[j]);
+                for (int j = 0; j < 16; ++j)
+                  tot[mbi][i * 16 + j] = cdn_fadd2(tot[mbi][i * 16 + j], make_float2(__uint_as_float(r0[2 * j]), __uint_as_float(r0[2 * j + 1])));
               }
             }
           }
@@ -314,14 +315,14 @@ pw_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
               for (int mbi = 0; mbi < 2; ++mbi)
                 if (mbi < nmb) {
 #pragma unroll
-                  for (int j = 0; j < 32; ++j) sts_f32(sp + (uint32_t)((j * 256 + mbi * 128) * 4), tot[mbi][j]);
+                  for (int j = 0; j < 32; ++j) sts_f32(sp + (uint32_t)((j * 256 + mbi * 128) * 4), (j & 1) ? tot[mbi][j >> 1].y : tot[mbi][j >> 1].x);
                 }
             } else {
 #pragma unroll
               for (int mbi = 0; mbi < 2; ++mbi)
                 if (mbi < nmb) {
 #pragma unroll
-                  for (int j = 0; j < 32; ++j) sts_f32(sp + (uint32_t)((j * 256 + mbi * 128) * 4), tot[mbi][32 + j]);
+                  for (int j = 0; j < 32; ++j) sts_f32(sp + (uint32_t)((j * 256 + mbi * 128) * 4), (j & 1) ? tot[mbi][16 + (j >> 1)].y : tot[mbi][16 + (j >> 1)].x);
                 }
             }
           }
