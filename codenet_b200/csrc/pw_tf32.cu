@@ -22,6 +22,8 @@
 // hi*hi products; the epilogue warps move every such chunk sum into register totals with round-to-nearest fp32 adds
 // (2 or 4 chunk accumulators in TMEM rotate, so the tensor core runs ahead), and bias / ReLU / the stores happen once per
 // tile through a shared-memory slab.  Measured error of one layer: 1.0-1.3e-7 relative L2, independent of K.
+// Tried and dropped: a deeper raw-activation ring (6 x 16 KB in flight) with double-buffered operand stages -- the 128 x 128
+// layers did not move (they are not bound by bytes in flight), the compute-heavy ones lost 5-15 %.
 // Bound.  Per 16-channel stage the shared memory moves 176 KB (tensor-core operand reads 96, TMA writes 32, split 48) = 1375
 // clocks at 128 B/clock against 768 clocks of tensor time: the compute-heavy layers run at 50-55 % of the kind::tf32 rate
 // (x3 instruction slots), the 128 x 128 layers at 0.4-0.5 of HBM.
