@@ -295,54 +295,67 @@ pw_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         __syncwarp();
         if (lane == 0) mbar_arrive(CEMPTY(cb));
       }
-      // End of tile: the totals leave through a 32-channel x 256-pixel staging slab in shared memory (conflict-free 128-byte
-      // rows per warp), from which all eight epilogue warps store 16 bytes per lane (512 contiguous bytes of one channel plane per
-      // warp) after adding the bias / applying ReLU.  A warp owns two slabs (its columns jb = 0 and jb = 32); with BN > 64 the
-      // tile has four rounds, the warps of column half `ch` filling rounds 2 ch and 2 ch + 1.  (Storing straight from the
-      // registers -- 128 predicated 4-byte stores per lane, each with its own address -- cost 6 us per tile; handing the slab's 1 KB
-      // rows to the bulk-copy engine instead of storing them with LDS + STG.128 was measured 1.3-1.4x slower.)
+      // End of tile: the totals leave through a staging slab in shared memory (conflict-free 128-byte rows per warp), from which
+      // all eight epilogue warps store 16 bytes per lane (512 contiguous bytes of one channel plane per warp) after adding the
+      // bias / applying ReLU.  (Storing straight from the registers -- 128 predicated 4-byte stores per lane, each with its own
+      // address -- cost 6 us per tile; handing the slab's 1 KB rows to the bulk-copy engine instead of LDS + STG.128 was measured
+      // 1.3-1.4x slower; 61 instructions of 64-bit address arithmetic per stored float4 in the first LDS + STG loop cost 15 %.)
       const int n0 = nt * p.per;
       const int nreal = min(p.per, p.Co - n0);                      // real output channels of this N tile
       const size_t plane = (size_t)p.out_cstride * p.ppi;
       float* obase = p.out + ((size_t)b * p.out_ctotal + p.out_coff + (size_t)n0 * p.out_cstride) * p.ppi + px0;
-      const int nround = small ? 2 : 4;
       const int et = threadIdx.x - 256;                             // 0..255 among the epilogue warps
-      for (int round = 0; round < nround; ++round) {
-        const int nv = min(max(nreal - round * 32, 0), 32);
-        if (nv > 0) {
-          if (small || (round >> 1) == ch) {
-            const uint32_t sp = stage_u32 + (uint32_t)((mb0 * 128 + q * 32 + lane) * 4);
-            if ((round & 1) == 0) {
+      const int srow0 = et >> 6, f4 = et & 63;                      // store phase: this thread's float4 of slab rows srow0 + 4 i
+      // Rounds of 16 channels through two 16 KB slab halves (one barrier per round: when a thread passes the barrier of round
+      // r + 1 every thread has finished storing round r, so round r + 2 may refill that half).  BN > 64: a round takes 8 columns
+      // from each column half (all eight warps fill it); BN <= 64: 16 consecutive columns of both pixel blocks.
+      named_bar_sync(1, 256);                                       // the previous tile's last round has been stored (it may have used half 0)
+#define PT_STORE_ROUND(R, CHAN_OF_ROW)                                                                                    \
+      {                                                                                                                   \
+        named_bar_sync(1, 256);                                                                                           \
+        const uint32_t half_u32 = stage_u32 + (uint32_t)(((R) & 1) * 16384);                                              \
+        _Pragma("unroll")                                                                                                 \
+        for (int i = 0; i < 4; ++i) {                                                                                     \
+          const int row = srow0 + 4 * i, chn = CHAN_OF_ROW;                                                               \
+          if (chn < nreal) {                                                                                              \
+            float4 v = lds_f4(half_u32 + (uint32_t)((row * 256 + f4 * 4) * 4));                                           \
+            const float bv = p.bias ? __ldg(p.bias + n0 + chn) : 0.f;                                                     \
+            v.x += bv; v.y += bv; v.z += bv; v.w += bv;                                                                   \
+            if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }   \
+            *(float4*)(obase + (size_t)chn * plane + f4 * 4) = v;                                                         \
+          }                                                                                                               \
+        }                                                                                                                 \
+      }
+      if (small) {
+        const uint32_t sp = stage_u32 + (uint32_t)((mb0 * 128 + q * 32 + lane) * 4);
 #pragma unroll
-              for (int mbi = 0; mbi < 2; ++mbi)
-                if (mbi < nmb) {
+        for (int r = 0; r < 4; ++r) {
+          if (r * 16 < nreal) {                                       // uniform over the CTA
 #pragma unroll
-                  for (int j = 0; j < 32; ++j) sts_f32(sp + (uint32_t)((j * 256 + mbi * 128) * 4), (j & 1) ? tot[mbi][j >> 1].y : tot[mbi][j >> 1].x);
-                }
-            } else {
-#pragma unroll
-              for (int mbi = 0; mbi < 2; ++mbi)
-                if (mbi < nmb) {
-#pragma unroll
-                  for (int j = 0; j < 32; ++j) sts_f32(sp + (uint32_t)((j * 256 + mbi * 128) * 4), (j & 1) ? tot[mbi][16 + (j >> 1)].y : tot[mbi][16 + (j >> 1)].x);
-                }
+            for (int j = 0; j < 16; ++j) {
+              const float2 t2 = tot[0][(16 * r + j) >> 1];
+              sts_f32(sp + (uint32_t)((r & 1) * 16384 + j * 1024), (j & 1) ? t2.y : t2.x);
             }
+            PT_STORE_ROUND(r, 16 * r + row)
           }
-          named_bar_sync(1, 256);
-#pragma unroll 2
-          for (int i = 0; i < 8; ++i) {
-            const int idx = et + 256 * i, co = idx >> 6, f4 = idx & 63;
-            if (co < nv) {
-              float4 v = lds_f4(stage_u32 + (uint32_t)((co * 256 + f4 * 4) * 4));
-              const float bv = p.bias ? __ldg(p.bias + n0 + round * 32 + co) : 0.f;
-              v.x += bv; v.y += bv; v.z += bv; v.w += bv;
-              if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-              *(float4*)(obase + (size_t)(round * 32 + co) * plane + f4 * 4) = v;
-            }
+        }
+      } else {
+        const uint32_t sp = stage_u32 + (uint32_t)((ch * 8 * 256 + q * 32 + lane) * 4);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          if (r * 8 < nreal) {                                        // uniform over the CTA (the low column half is never empty then)
+#pragma unroll
+            for (int mbi = 0; mbi < 2; ++mbi)
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float2 t2 = tot[mbi][(8 * r + j) >> 1];
+                sts_f32(sp + (uint32_t)((r & 1) * 16384 + j * 1024 + mbi * 512), (j & 1) ? t2.y : t2.x);
+              }
+            PT_STORE_ROUND(r, (row < 8 ? 8 * r + row : 56 + 8 * r + row))
           }
-          named_bar_sync(1, 256);
         }
       }
+#undef PT_STORE_ROUND
     }
   }
   tc_fence_before();
