@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(256) deform_scale_f32_kernel(DefDwF32Params p)
 // "zero outside the image, per corner" (dcn_deform_conv_cuda_kernel.cu:83-114) without a select per load.  The grid runs over
 // (pixel block, channel group, image): the 16 x 16 layer with 2153 channels gets 69 k CTAs where one thread per pixel looping
 // over every channel (round 1) left the GPU with 220 threads per SM.
-#define DDF_CG 8
+#define DDF_CG 16
 __global__ void __launch_bounds__(128, 4) deform_gather_f32_kernel(DefDwF32Params p) {
   const int npx = p.Ho * p.Wo;
   const int px = blockIdx.x * 128 + threadIdx.x, b = blockIdx.z;
