@@ -94,6 +94,7 @@ struct DefDwF32Params {
   double* sd;                                   // [B][Ho*Wo] clamped scale per output pixel (phase A -> phase B)
   float bs, lo, hi;
   int B, C, H, W, Ho, Wo, stride;
+  int up;                                       // 1: `in` is [B][C][H/2][W/2] and is read through a virtual nearest x2 upsampling
 };
 
 // Phase A: s = Hardtanh(w_scale . x + b_scale) per output pixel.  The scale scalar moves the sample positions, and the sampled
@@ -108,8 +109,9 @@ __global__ void __launch_bounds__(256) deform_scale_f32_kernel(DefDwF32Params p)
   double sd = 0.0;
   if (px < npx) {
     const int ho = px / p.Wo, wo = px - ho * p.Wo;
-    const size_t plane = (size_t)p.H * p.W;
-    const float* x = p.in + (size_t)b * p.C * plane + (size_t)(ho * p.stride) * p.W + wo * p.stride;   // conv_scale: kernel 1, padding 0
+    const int Ws = p.W >> p.up;                                     // stored row length / plane of the (possibly low-resolution) input
+    const size_t plane = (size_t)(p.H >> p.up) * Ws;
+    const float* x = p.in + (size_t)b * p.C * plane + (size_t)((ho * p.stride) >> p.up) * Ws + ((wo * p.stride) >> p.up);   // conv_scale: kernel 1, padding 0
     // four independent chains per thread (the single chain left the loads waiting behind a dependent fp64 FMA each)
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     int c = grp;
@@ -157,10 +159,11 @@ __global__ void __launch_bounds__(128, 4) deform_gather_f32_kernel(DefDwF32Param
     // outside the reference's range test (h_im > -1 && h_im < H): every corner is invalid or has weight zero already
     wra[i] = ((unsigned)y < (unsigned)p.H) ? 1.f - lh : 0.f;        wrb[i] = ((unsigned)(y + 1) < (unsigned)p.H) ? lh : 0.f;
     wca[i] = ((unsigned)x < (unsigned)p.W) ? 1.f - lw : 0.f;        wcb[i] = ((unsigned)(x + 1) < (unsigned)p.W) ? lw : 0.f;
-    ra[i] = min(max(y, 0), p.H - 1) * p.W;  rb[i] = min(max(y + 1, 0), p.H - 1) * p.W;
-    ca[i] = min(max(x, 0), p.W - 1);        cb[i] = min(max(x + 1, 0), p.W - 1);
+    // addresses in the stored plane: with the virtual upsampling, sample (y, x) of the 2x map is element (y >> 1, x >> 1)
+    ra[i] = (min(max(y, 0), p.H - 1) >> p.up) * (p.W >> p.up);  rb[i] = (min(max(y + 1, 0), p.H - 1) >> p.up) * (p.W >> p.up);
+    ca[i] = min(max(x, 0), p.W - 1) >> p.up;                    cb[i] = min(max(x + 1, 0), p.W - 1) >> p.up;
   }
-  const size_t plane = (size_t)p.H * p.W;
+  const size_t plane = (size_t)(p.H >> p.up) * (p.W >> p.up);
   const int c_begin = blockIdx.y * DDF_CG, c_end = min(c_begin + DDF_CG, p.C);
   const float* img = p.in + ((size_t)b * p.C + c_begin) * plane;
   float* ob = p.out + ((size_t)b * p.C + c_begin) * npx + px;
@@ -200,9 +203,9 @@ extern "C" size_t cdn_deform_dw_f32_ws_bytes(int B, int H, int W, int stride) {
   return std::max<size_t>(B * Ho * Wo, 1) * sizeof(double);
 }
 
-extern "C" int cdn_deform_dw_f32_ws(const float* input, const float* w_scale, float b_scale, int offset_bound, const float* w_dw,
-                                    float* output, int B, int C, int H, int W, int stride, void* d_ws, size_t ws_bytes,
-                                    cdn_stream_t stream) {
+static int deform_dw_f32_run(const float* input, const float* w_scale, float b_scale, int offset_bound, const float* w_dw,
+                             float* output, int B, int C, int H, int W, int stride, int up, void* d_ws, size_t ws_bytes,
+                             cdn_stream_t stream) {
   CDN_CHECK(input && w_scale && w_dw && output, CDN_ERR_INVALID, "deform_dw_f32: null tensor");
   CDN_CHECK(B >= 0 && B <= 65535 && C >= 1 && H >= 1 && W >= 1 && (stride == 1 || stride == 2) && offset_bound >= 1, CDN_ERR_INVALID,
             "deform_dw_f32: bad shape / stride / bound");
@@ -211,7 +214,7 @@ extern "C" int cdn_deform_dw_f32_ws(const float* input, const float* w_scale, fl
   DefDwF32Params p;
   p.in = input; p.ws = w_scale; p.wdw = w_dw; p.out = output; p.bs = b_scale; p.sd = (double*)d_ws;
   p.lo = (float)(-offset_bound + 1); p.hi = (float)offset_bound;
-  p.B = B; p.C = C; p.H = H; p.W = W; p.stride = stride;
+  p.B = B; p.C = C; p.H = H; p.W = W; p.stride = stride; p.up = up;
   p.Ho = (H + 2 - 3) / stride + 1; p.Wo = (W + 2 - 3) / stride + 1;
   const int npx = p.Ho * p.Wo;
   if (B == 0) return 0;
@@ -221,6 +224,20 @@ extern "C" int cdn_deform_dw_f32_ws(const float* input, const float* w_scale, fl
   deform_gather_f32_kernel<<<dim3((unsigned)((npx + 127) / 128), (unsigned)((C + DDF_CG - 1) / DDF_CG), (unsigned)B), 128, 0, (cudaStream_t)stream>>>(p);
   CDN_LAUNCH_CHECK("deform_gather_f32_kernel");
   return 0;
+}
+
+extern "C" int cdn_deform_dw_f32_ws(const float* input, const float* w_scale, float b_scale, int offset_bound, const float* w_dw,
+                                    float* output, int B, int C, int H, int W, int stride, void* d_ws, size_t ws_bytes,
+                                    cdn_stream_t stream) {
+  return deform_dw_f32_run(input, w_scale, b_scale, offset_bound, w_dw, output, B, C, H, W, stride, 0, d_ws, ws_bytes, stream);
+}
+// The module applied to the nearest x2 upsampling of `input` [B][C][h][w] (stride 1), which is never written: the block
+// "ReLU -> nn.Upsample(2) -> DeformConvWithOffsetScaleBoundPositive" of the up path (shufflenetv2_dcn.py:286-300).  Samples of
+// the 2h x 2w map are read as element (y >> 1, x >> 1); output [B][C][2h][2w]; workspace cdn_deform_dw_f32_ws_bytes(B, 2h, 2w, 1).
+extern "C" int cdn_deform_dw_up2_f32_ws(const float* input, const float* w_scale, float b_scale, int offset_bound, const float* w_dw,
+                                        float* output, int B, int C, int h, int w, void* d_ws, size_t ws_bytes, cdn_stream_t stream) {
+  CDN_CHECK(h >= 1 && w >= 1 && h < (1 << 14) && w < (1 << 14), CDN_ERR_INVALID, "deform_dw_up2_f32: bad shape");
+  return deform_dw_f32_run(input, w_scale, b_scale, offset_bound, w_dw, output, B, C, 2 * h, 2 * w, 1, 1, d_ws, ws_bytes, stream);
 }
 
 // The form without a workspace argument keeps one scratch buffer per device, grown on demand (a growth allocates and therefore

@@ -157,26 +157,36 @@ class EngineF32:
             y = self._new(x, g.layer4.cout)
             self._pw(x, 0, g.layer4.cin, "layer4", y, 0, 1, True)
             x = y
-            for up in g.ups:                                       # deform module + BN + ReLU + nearest x2
+            # up path: deform module + 1x1 conv + BN + ReLU + nearest x2.  No upsampled tensor is ever written: the next block's
+            # deformable module reads its input through the virtual upsampling (cdn_deform_dw_up2_f32_ws, identical results), and
+            # the last one is consumed the same way by the heads below.
+            pending_up = False                                     # x still has to be read as its x2 upsampling
+            z = None
+            for up in g.ups:
                 i = up["idx"]
                 ws, bs = self.P["up%d.scale" % i]
                 wd, _ = self.P["up%d.deform" % i]
-                Bc, Cc, H, W = x.shape
-                y = x.new_empty(x.shape)
+                Bc, Cc, h, w = x.shape
+                H, W = (2 * h, 2 * w) if pending_up else (h, w)
+                y = x.new_empty((Bc, Cc, H, W))
                 need = int(L.cdn_deform_dw_f32_ws_bytes(Bc, H, W, 1))
                 if self._def_ws is None or self._def_ws.numel() < need:
                     self._def_ws = torch.empty(need, dtype=torch.uint8, device=self.dev)
                 self.launches += 2
-                _lib.check(L.cdn_deform_dw_f32_ws(self._p(x), self._p(ws), C.c_float(self.scale_bias["up%d.scale" % i]), cfg.offset_bound, self._p(wd),
-                                                  self._p(y), Bc, Cc, H, W, 1, self._p(self._def_ws), self._def_ws.numel(), self._st()))
+                if pending_up:
+                    _lib.check(L.cdn_deform_dw_up2_f32_ws(self._p(x), self._p(ws), C.c_float(self.scale_bias["up%d.scale" % i]), cfg.offset_bound,
+                                                          self._p(wd), self._p(y), Bc, Cc, h, w, self._p(self._def_ws), self._def_ws.numel(), self._st()))
+                else:
+                    _lib.check(L.cdn_deform_dw_f32_ws(self._p(x), self._p(ws), C.c_float(self.scale_bias["up%d.scale" % i]), cfg.offset_bound,
+                                                      self._p(wd), self._p(y), Bc, Cc, H, W, 1, self._p(self._def_ws), self._def_ws.numel(), self._st()))
                 z = self._new(y, up["cout"])
                 self._pw(y, 0, Cc, "up%d.channel" % i, z, 0, 1, True)
-                if up is g.ups[-1] and W % 4 == 0:
-                    break                                          # the last x2 upsampling is virtual: see the heads below
-                x = z.new_empty((Bc, up["cout"], 2 * H, 2 * W))
+                x, pending_up = z, True
+            if z is not None and z.shape[3] % 4 != 0:              # the heads' virtual upsampling needs rows of whole float4s
+                Bc, Cc, h, w = z.shape
+                x = z.new_empty((Bc, Cc, 2 * h, 2 * w))
                 self.launches += 1
-                _lib.check(L.cdn_upsample2x_f32(self._p(z), self._p(x), Bc * up["cout"], H, W, self._st()))
-            else:
+                _lib.check(L.cdn_upsample2x_f32(self._p(z), self._p(x), Bc * Cc, h, w, self._st()))
                 z = None
             n_out = sum(h["classes"] for h in g.heads)
             off = 0

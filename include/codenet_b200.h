@@ -239,6 +239,11 @@ int cdn_deform_dw_f32(const float* input, const float* w_scale, float b_scale, i
 size_t cdn_deform_dw_f32_ws_bytes(int B, int H, int W, int stride);
 int cdn_deform_dw_f32_ws(const float* input, const float* w_scale, float b_scale, int offset_bound, const float* w_dw,
                          float* output, int B, int C, int H, int W, int stride, void* d_ws, size_t ws_bytes, cdn_stream_t stream);
+/* The module (stride 1) applied to the nearest x2 upsampling of input [B][C][h][w] without materialising it (the up path's
+ * Upsample -> deformable module, lib/models/networks/shufflenetv2_dcn.py:286-300): output [B][C][2h][2w]; workspace
+ * cdn_deform_dw_f32_ws_bytes(B, 2h, 2w, 1).  Identical results to upsampling first. */
+int cdn_deform_dw_up2_f32_ws(const float* input, const float* w_scale, float b_scale, int offset_bound, const float* w_dw,
+                             float* output, int B, int C, int h, int w, void* d_ws, size_t ws_bytes, cdn_stream_t stream);
 /* fp32 1x1 convolution NCHW (the module's conv_channel): output [B][Co][P] = weight [Co][C] x input [B][C][P] (+ bias). */
 int cdn_pw_f32(const float* input, const float* weight, const float* bias, float* output, int B, int C, int Co,
                int pixels_per_image, cdn_stream_t stream);

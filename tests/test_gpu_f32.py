@@ -182,3 +182,26 @@ def test_stem_conv3x3_f32_matches_numpy(B, Co, H, W, stride):
     _lib.check(_lib.load().cdn_conv3x3_f32(ptr(tx), ptr(tw), ptr(tb), ptr(out), B, 3, Co, H, W, stride, 1, stream()))
     torch.cuda.synchronize()
     np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=3e-6, atol=3e-6)
+
+
+@pytest.mark.parametrize("B,C,h,w,bound", [(2, 19, 8, 8, 8), (1, 40, 16, 12, 4), (2, 5, 3, 5, 8)])
+def test_deform_module_over_virtual_upsample_equals_upsample_then_module(B, C, h, w, bound):
+    """cdn_deform_dw_up2_f32_ws(a) == cdn_deform_dw_f32_ws(cdn_upsample2x_f32(a)) bit for bit: the up path's
+    Upsample -> DeformConvWithOffsetScaleBoundPositive (shufflenetv2_dcn.py:286-300) without the upsampled tensor."""
+    import ctypes as C_
+    import torch
+    from codenet_b200 import _lib
+    from gpu_util import ptr, stream
+    L = _lib.load()
+    a = torch.randn(B, C, h, w, device="cuda")
+    ws, wd = torch.randn(C, device="cuda") * 0.5, torch.randn(C, 3, 3, device="cuda")
+    up = torch.empty(B, C, 2 * h, 2 * w, device="cuda")
+    _lib.check(L.cdn_upsample2x_f32(ptr(a), ptr(up), B * C, h, w, stream()))
+    need = int(L.cdn_deform_dw_f32_ws_bytes(B, 2 * h, 2 * w, 1))
+    wsp = torch.empty(need, dtype=torch.uint8, device="cuda")
+    want, got = torch.empty_like(up), torch.empty_like(up)
+    _lib.check(L.cdn_deform_dw_f32_ws(ptr(up), ptr(ws), C_.c_float(1.3), bound, ptr(wd), ptr(want), B, C, 2 * h, 2 * w, 1, ptr(wsp), need, stream()))
+    _lib.check(L.cdn_deform_dw_up2_f32_ws(ptr(a), ptr(ws), C_.c_float(1.3), bound, ptr(wd), ptr(got), B, C, h, w, ptr(wsp), need, stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(got, want)
+    assert float(want.abs().max()) > 0
