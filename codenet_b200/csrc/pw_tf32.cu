@@ -49,7 +49,6 @@ struct PtParams {
   int ppi, tiles_per_img;              // pixels per image, ppi / 256
   unsigned total_tiles;                // batch * tiles_per_img * NT
   int num_k;                           // ceil(C / 16)
-  int dbg;                             // timing experiments (wrong results): 1 no TMEM flush, 2 no activation loads, 4 no split work
 };
 
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -168,9 +167,9 @@ pw_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           for (int kc = 0; kc < p.num_k; ++kc) {
             pt_wait(EMPTY(stage), phase ^ 1);
             const uint32_t sx = smem_u32(ring + (size_t)stage * PT_STAGE_BYTES);
-            mbar_expect_tx(RAW(stage), ((p.dbg & 2) ? 0u : (uint32_t)PT_XBYTES) + w_bytes);
+            mbar_expect_tx(RAW(stage), (uint32_t)PT_XBYTES + w_bytes);
             // one box = 32 pixels x 16 channels x 8 pixel groups: 128-byte rows, channel rows 128 bytes apart, pixel groups 2 KB apart
-            if (!(p.dbg & 2)) tma_load_4d(sx, &tmX, 0, kc * PT_KC, px0 >> 5, b, RAW(stage));
+            tma_load_4d(sx, &tmX, 0, kc * PT_KC, px0 >> 5, b, RAW(stage));
             tma_load_2d(sx + 2 * PT_XBYTES, &tmW, kc * 32, nt * p.BN, RAW(stage));   // BN rows of 128 bytes: [hi 16 channels | lo 16 channels]
             if (++stage == PT_STAGES) { stage = 0; phase ^= 1; }
           }
@@ -236,7 +235,6 @@ pw_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           const uint32_t sx = smem_u32(ring + (size_t)stage * PT_STAGE_BYTES);
 #pragma unroll
           for (int i = 0; i < PT_XBYTES / 16 / 128; ++i) {
-            if (p.dbg & 4) break;
             const uint32_t a = sx + (uint32_t)(i * 128 + tid) * 16;
             const uint4 v = lds_u128(a);
             uint4 h, l;
@@ -280,7 +278,7 @@ pw_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cb * 2u * bnp + (uint32_t)(mb0 + mbi) * bnp + (uint32_t)col0;
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
-              if (col0 + i * 32 < p.BN && !(p.dbg & 1)) {                             // columns past BN (a multiple of 16) hold stale data that is never stored
+              if (col0 + i * 32 < p.BN) {                             // columns past BN (a multiple of 16) hold stale data that is never stored
                 uint32_t r0[32];
                 tmem_ld32(tbase + (uint32_t)(i * 32), r0);
                 tmem_ld_wait();
@@ -436,7 +434,7 @@ extern "C" int cdn_pw_slice_tf32x3(const float* input, int in_ctotal, int in_cof
   PtParams p;
   p.bias = bias; p.out = output; p.C = C; p.Co = Co; p.NT = pt_nt(Co); p.BN = pt_bn(Co);
   p.out_ctotal = out_ctotal; p.out_coff = out_coff; p.out_cstride = out_cstride; p.relu = relu;
-  p.ppi = pixels_per_image; p.tiles_per_img = pixels_per_image / PT_M; p.dbg = (int)((g_cdn_debug_flags >> 8) & 15u);
+  p.ppi = pixels_per_image; p.tiles_per_img = pixels_per_image / PT_M;
   const unsigned long long tiles = (unsigned long long)B * p.tiles_per_img * p.NT;
   CDN_CHECK(tiles < (1ull << 31), CDN_ERR_INVALID, "pw_slice_tf32x3: too many tiles");
   p.total_tiles = (unsigned)tiles; p.num_k = pt_kpad(C) / PT_KC;

@@ -18,7 +18,7 @@ for name, Cc, Co, ppi in shapes:
     packed = torch.empty(n, device="cuda")
     _lib.check(L.cdn_pw_tf32x3_pack(ptr(w), Co, Cc, ptr(packed), st()))
     out = torch.empty(B, Co, ppi, device="cuda")
-    for flags in ((0, 1 << 31) if not os.environ.get('PT_DBG') else (0, 1 << 8, 7 << 8)):
+    for flags in (0, 1 << 31):                   # bit 31: two stages per accumulation chunk (A/B)
         L.cdn_set_debug_flags(flags)
         f = lambda: _lib.check(L.cdn_pw_slice_tf32x3(ptr(x), Cc, 0, Cc, ptr(packed), None, ptr(out), Co, 0, 1, Co, 1, B, ppi, st()))
         for _ in range(3): f()
