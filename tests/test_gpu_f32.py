@@ -205,3 +205,27 @@ def test_deform_module_over_virtual_upsample_equals_upsample_then_module(B, C, h
     torch.cuda.synchronize()
     assert torch.equal(got, want)
     assert float(want.abs().max()) > 0
+
+
+def test_float_model_gemm_modes_agree_on_a_non_square_batch():
+    """384 x 640 input, batch 3 (pixel counts 15360 / 3840 on the tensor-core path, 960 / 240 on the SIMT fallback, tile counts below
+    and above the SM count): the two 1x1-conv implementations must give the same network within the float-path bound, and the
+    same detections up to near-ties."""
+    import torch
+    from codenet_b200.engine_f32 import EngineF32
+    cfg = NetConfig(num_classes=20)
+    raw = make_raw_state(cfg, 0)
+    rng = np.random.default_rng(11)
+    x = torch.from_numpy(rng.normal(0, 1, (3, 3, 384, 640)).astype(np.float32)).cuda()
+    outs = {}
+    for gemm in ("fp32", "tf32x3"):
+        eng = EngineF32(cfg, raw, gemm=gemm)
+        dets, inds, v = eng.detect(x)
+        torch.cuda.synchronize()
+        outs[gemm] = (dets.cpu().numpy(), {k: t.cpu().numpy().astype(np.float64) for k, t in v.items()})
+    for name in ("hm", "wh", "reg"):
+        a, b = outs["fp32"][1][name], outs["tf32x3"][1][name]
+        assert a.shape == (3, {"hm": 20, "wh": 2, "reg": 2}[name], 96, 160)
+        l2 = np.sqrt(((a - b) ** 2).sum() / (a ** 2).sum())
+        assert l2 <= 5e-4, (name, l2)
+    np.testing.assert_allclose(np.sort(outs["tf32x3"][0][..., 4], 1)[:, ::-1][:, :30], np.sort(outs["fp32"][0][..., 4], 1)[:, ::-1][:, :30], rtol=2e-3)
