@@ -102,6 +102,22 @@ def test_library_exports_every_declared_symbol():
     assert lib.cdn_version() >= 100
 
 
+def test_workspace_and_packing_sizes_are_host_arithmetic():
+    """The size queries of the C ABI need no device: ctdet decode workspace (8 bytes per heat-map element + one counter per image
+    + 1), the deformable module's scale scratch (8 bytes per output pixel), and the packed weights of the tensor-core float GEMM
+    (N tiles of <= 128 output channels, columns padded to 16, input channels padded to 16, hi + lo)."""
+    lib = _lib.load()
+    assert lib.cdn_ctdet_decode_ws_bytes(4, 20, 64, 64) == 4 * 20 * 64 * 64 * 8 + 5 * 4
+    assert lib.cdn_ctdet_decode_ws_bytes(0, 20, 64, 64) == 8 + 4 and lib.cdn_ctdet_decode_ws_bytes(1, 0, 64, 64) == 0
+    assert lib.cdn_deform_dw_f32_ws_bytes(3, 16, 16, 1) == 3 * 256 * 8 and lib.cdn_deform_dw_f32_ws_bytes(3, 16, 16, 2) == 3 * 64 * 8
+    assert lib.cdn_deform_dw_f32_ws_bytes(3, 16, 16, 3) == 0
+    for Co, Cin, nt, bn in ((122, 24, 1, 128), (244, 244, 2, 128), (2153, 976, 17, 128), (80, 64, 1, 80), (2, 64, 1, 16), (192, 64, 2, 96),
+                            (300, 976, 3, 112)):
+        kpad = (Cin + 15) // 16 * 16
+        assert lib.cdn_pw_tf32x3_packed_floats(Co, Cin) == nt * bn * kpad * 2, (Co, Cin)
+    assert lib.cdn_pw_tf32x3_packed_floats(0, 5) == 0
+
+
 def test_no_cpu_fallback():
     """Without a GPU the product path must fail loudly, never compute on the CPU."""
     import torch
