@@ -193,6 +193,12 @@ def run_ours(args, C):
                     "share_of_step": round(pw_ms / (ms / args.steps), 3),
                     "note": "achieved = algorithmic fp32 flops (2*C*Co*pixels, unpadded); every fp32 product costs three tf32 MMAs, so the "
                             "ceiling of frac is 1/3; timed per launch with CUDA events in an eager pass"}
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not getattr(args, "no_cpu", False):
+        try:                                         # bounded sample (2 timed steps of batch 8) of the unmodified reference on the host cores
+            cpu_baseline, _, _ = time_reference(C, raw, _cfg(), 2, 1, budget_s=60.0)
+        except Exception as e:                       # noqa: BLE001 -- the reference tree is not on this box
+            cpu_baseline = {"value": None, "unit": UNIT, "kind": "reference", "unavailable": str(e)[:160]}
     ok, worst = check_parity(eng, g)
     t = torch.tensor([0 if ok else 1], device="cuda")
     if world > 1:
@@ -213,21 +219,19 @@ def run_ours(args, C):
                 "e2e": {"value": round(e2e, 1), "unit": UNIT, "h2d_bytes_per_step": int(B * 3 * R * R * 4),
                         "d2h_bytes_per_step": int(B * 100 * 6 * 4), "steps": n_e2e,
                         "api": "EngineF32.detect on images copied from pinned host memory every step (copy of step n+1 under the compute of step n)"},
-                "gpu_launches": launches * args.steps, "launches_per_step": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": None}
+                "gpu_launches": launches * args.steps, "launches_per_step": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline}
         print(json.dumps(line))
     if not ok_all:
         sys.stderr.write("bench.py --config 2x_fp32: PARITY FAILURE %s\n" % worst)
         sys.exit(3)
 
 
-def run_reference(args, C):
-    if int(os.environ.get("RANK", "0")) != 0:
-        return
+def time_reference(C, raw, cfg, steps, warmup, budget_s=150.0):
+    """The UNMODIFIED reference's float forward + sigmoid + ctdet_decode on the host cores (oracle/ref_harness.py), batch 8:
+    (cpu_baseline dict, median seconds per step, timed steps)."""
     import torch
     from oracle import ref_harness as H
     from codenet_b200.synth import make_images
-    raw, g = _state()
-    cfg = _cfg()
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     R_ = H.load_reference()
@@ -241,24 +245,32 @@ def run_reference(args, C):
             o = m(x)[-1]
             return R_.decode.ctdet_decode(o["hm"].sigmoid_(), o["wh"], reg=o["reg"], K=100)
 
-    for _ in range(max(1, min(args.warmup, 2))):
+    for _ in range(max(1, min(warmup, 2))):
         step()
     times = []
     t_all = time.perf_counter()
-    for i in range(max(args.steps, 2)):
+    for i in range(max(steps, 2)):
         t0 = time.perf_counter()
         step()
         times.append(time.perf_counter() - t0)
-        if i >= 1 and time.perf_counter() - t_all > 150:
+        if i >= 1 and time.perf_counter() - t_all > budget_s:
             break
     med = float(np.median(times))
-    B = args.batch or C["batch"]
     cpu = {"value": round(8 / med, 3), "unit": UNIT, "cores": threads, "kind": "reference",
            "sample": "%d timed steps (median) of the UNMODIFIED reference's float PoseShuffleNetV2(w2) forward + sigmoid + ctdet_decode on "
                      "a batch of 8 512x512 images, fp32, torch.set_num_threads(%d), torchvision CPU deform_conv2d in place of the "
                      "CUDA-only op" % (len(times), threads)}
+    return cpu, med, len(times)
+
+
+def run_reference(args, C):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    raw, g = _state()
+    cpu, med, n = time_reference(C, raw, _cfg(), args.steps, args.warmup)
+    B = args.batch or C["batch"]
     print(json.dumps({"metric": C["metric"], "value": cpu["value"], "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
-                      "steps": len(times), "warmup": args.warmup, "ms_per_step": round(med * 1e3, 3), "higher_is_better": True,
+                      "steps": n, "warmup": args.warmup, "ms_per_step": round(med * 1e3, 3), "higher_is_better": True,
                       "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
                       "config": {"workload": C["workload"] % B, "name": "2x_fp32", "batch_per_gpu": B, "offset_mode": "bilinear"},
                       "cpu_baseline": cpu,
