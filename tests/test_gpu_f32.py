@@ -229,3 +229,24 @@ def test_float_model_gemm_modes_agree_on_a_non_square_batch():
         l2 = np.sqrt(((a - b) ** 2).sum() / (a ** 2).sum())
         assert l2 <= 5e-4, (name, l2)
     np.testing.assert_allclose(np.sort(outs["tf32x3"][0][..., 4], 1)[:, ::-1][:, :30], np.sort(outs["fp32"][0][..., 4], 1)[:, ::-1][:, :30], rtol=2e-3)
+
+
+@pytest.mark.parametrize("Co,C", [(122, 24), (244, 61), (80, 64), (2, 64), (300, 130)])
+def test_tf32x3_weight_packing_equals_the_restatement(Co, C):
+    """cdn_pw_tf32x3_pack against oracle/tf32_split.pack_weights, bit for bit (rounding to TF32 with ties away from zero, exact
+    remainder, N-tile / padding layout)."""
+    import torch
+    from codenet_b200 import _lib
+    from gpu_util import ptr, stream
+    from oracle import tf32_split as ts
+    rng = np.random.default_rng(Co + C)
+    w = rng.normal(0, 1, (Co, C)).astype(np.float32)
+    w[0, 0], w[-1, -1] = np.float32(1 + 2 ** -11), np.float32(-(1 + 2 ** -11))         # exact ties
+    L = _lib.load()
+    n = int(L.cdn_pw_tf32x3_packed_floats(Co, C))
+    want = ts.pack_weights(w)
+    assert want.size == n
+    packed = torch.empty(n, device="cuda")
+    _lib.check(L.cdn_pw_tf32x3_pack(ptr(torch.from_numpy(w).cuda()), Co, C, ptr(packed), stream()))
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(packed.cpu().numpy().view(np.uint32), want.view(np.uint32))

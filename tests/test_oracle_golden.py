@@ -168,3 +168,26 @@ def test_int_oracle_w2_maxpool(golden):
     for n, k in (("hm", "hm_logit"), ("wh", "wh"), ("reg", "reg")):
         np.testing.assert_allclose(out[n], g[k], rtol=1e-12, atol=1e-12)
     check_reference_dets(g["dets"][:1], out["hm"], out["wh"], out["reg"])
+
+
+def test_tf32_split_properties():
+    """oracle/tf32_split.py (the operand split of the tensor-core float GEMM): hi carries at most 11 significant bits, the fp32
+    remainder is exact, |lo| <= 2^-11 |x|, the product of two hi parts is exactly representable in fp32, and x - hi - lo (what the
+    GEMM drops) is below 2^-22 |x|."""
+    from oracle import tf32_split as ts
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.normal(0, 1, 20000), rng.normal(0, 1e-6, 1000), rng.normal(0, 1e6, 1000), [0.0, 1.0, -1.0, 1.0009765625,
+                        np.float32(1 + 2 ** -11), np.float32(1 + 2 ** -11 + 2 ** -23)]]).astype(np.float32)
+    hi, lo = ts.split(x)
+    assert not (hi.view(np.uint32) & 0x1FFF).any() and not (lo.view(np.uint32) & 0x1FFF).any()
+    rem = (x.astype(np.float64) - hi.astype(np.float64))
+    assert (rem == (x - hi).astype(np.float64)).all()                                  # the fp32 subtraction is exact
+    assert (np.abs(rem) <= np.abs(x.astype(np.float64)) * 2.0 ** -11).all()
+    assert (np.abs(rem - lo) <= np.abs(x.astype(np.float64)) * 2.0 ** -22).all()
+    w = rng.normal(0, 1, x.size).astype(np.float32)
+    wh, _ = ts.split(w)
+    p64 = hi.astype(np.float64) * wh.astype(np.float64)
+    assert (p64 == (hi * wh).astype(np.float64)).all()                                 # hi * hi: 22-bit product, exact in fp32
+    assert ts.tf32_rna(np.float32([1 + 2 ** -11]))[0] == np.float32(1 + 2 ** -10)      # ties away from zero
+    assert ts.tiling(244) == (2, 122, 128) and ts.tiling(2153) == (17, 127, 128) and ts.tiling(2) == (1, 2, 16)
+    assert ts.pack_weights(rng.normal(0, 1, (244, 61)).astype(np.float32)).size == 2 * 128 * 64 * 2
